@@ -1,0 +1,163 @@
+/* libitn_b200 — C ABI of the B200-native belief-propagation / simple-update engine.
+ *
+ * The reference (ITensorNetworks.jl) has no FFI: its extension mechanism is Julia multiple
+ * dispatch on `AbstractBeliefPropagationCache` (src/caches/abstractbeliefpropagationcache.jl:44-69)
+ * plus the `cache!` / `cache_update_kwargs` protocol (src/expect.jl:21-41, src/normalize.jl:13-34,
+ * src/environment.jl:21-39, src/contract.jl:41-58).  A Julia `B200BeliefPropagationCache <:
+ * AbstractBeliefPropagationCache` holds an `itn_net*` and forwards those methods to the entry points
+ * below through `ccall`.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - status codes: 0 = OK, >0 = error; `itn_last_error()` has the text (thread local).  No C++
+ *     exception or longjmp crosses this boundary.
+ *   - the library owns every device allocation; host pointers are borrowed for the duration of one
+ *     call only.  Every call that writes through a host pointer returns after the data is complete.
+ *   - dtype 0 = Float64, 1 = ComplexF64 (host layout: interleaved re,im as in Julia/NumPy).
+ *   - vertices are 0..nv-1, undirected edges 0..ne-1 with endpoints (esrc[e], edst[e]).
+ *     Directed message "u -> v" is addressed by its endpoints.
+ *   - host tensors are column-major (Julia order).  A site tensor's axes are described by
+ *     `axis_edge[i]` = edge id carried by axis i, or -1 for the physical (site) axis.
+ *   - messages are chi x chi column-major matrices M[a, a'] with a = ket-side bond index and
+ *     a' = bra-side (primed) copy.
+ *   - a handle is used by one host thread at a time; distinct handles may be used concurrently.
+ */
+#ifndef ITN_B200_H
+#define ITN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct itn_ctx itn_ctx;
+typedef struct itn_net itn_net;
+
+enum {
+  ITN_OK = 0,
+  ITN_EINVAL = 1,       /* bad argument (reference: `error(...)` -> ErrorException) */
+  ITN_ESHAPE = 2,       /* shape / dimension mismatch */
+  ITN_ECUDA = 3,        /* CUDA runtime failure (incl. "no device": there is no CPU fallback) */
+  ITN_ENCCL = 4,        /* NCCL failure */
+  ITN_ENOMEM = 5,       /* device allocation failed */
+  ITN_EUNSUPPORTED = 6  /* valid in the reference but outside this engine's scope */
+};
+
+enum { ITN_F64 = 0, ITN_C128 = 1 };
+
+/* ---- library / context ------------------------------------------------------------------- */
+
+const char* itn_last_error(void);
+int itn_version(void);
+
+/* One context per process and GPU.  `stream` may be an existing cudaStream_t (e.g. the host
+ * framework's current stream, so that the host can bracket calls with its own CUDA events) or
+ * NULL to let the library create one. */
+int itn_ctx_create(int device, void* stream, itn_ctx** out);
+int itn_ctx_destroy(itn_ctx* ctx);
+int itn_ctx_sync(itn_ctx* ctx);
+
+/* Multi-GPU (one process per GPU).  Rank 0 obtains an id, the host broadcasts its 128 bytes by
+ * any means (MPI.jl, Distributed, torch.distributed), every rank calls itn_ctx_init_dist.  The
+ * library then exchanges boundary messages itself over NCCL/NVLink; no reference counterpart
+ * (the reference is single-process). */
+int itn_nccl_unique_id(void* out_128_bytes);
+int itn_ctx_init_dist(itn_ctx* ctx, int rank, int nranks, const void* id_128_bytes);
+
+/* ---- network = partitioned <psi|psi> tensor network + messages ----------------------------
+ * Replaces BeliefPropagationCache(ptn; messages) (src/caches/beliefpropagationcache.jl:13-35) over
+ * QuadraticFormNetwork(psi) with the default one-site partition
+ * (src/formnetworks/abstractformnetwork.jl:89-91): only the ket is stored, bra = conj(ket) and the
+ * identity operator layer are implicit.  `owner[v]` = rank owning vertex v (NULL: all on rank 0). */
+int itn_net_create(itn_ctx* ctx, int dtype, int nv, int ne, const int32_t* esrc, const int32_t* edst,
+                   const int32_t* edim, const int32_t* sdim, const int32_t* owner, itn_net** out);
+int itn_net_clone(const itn_net* net, itn_net** out); /* Base.copy (beliefpropagationcache.jl:43-47) */
+int itn_net_destroy(itn_net* net);                    /* callable from a Julia finalizer */
+int itn_sync(itn_net* net);
+
+int itn_net_edge_dim(const itn_net* net, int e, int32_t* out);
+int itn_net_tensor_size(const itn_net* net, int v, int64_t* out_elems);
+
+/* bpc[v] = t / update_factor (abstractbeliefpropagationcache.jl:158-171, beliefpropagationcache.jl:88-91).
+ * Bond extents must match the current edge dims. */
+int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd, const int32_t* axis_edge);
+int itn_net_get_tensor(const itn_net* net, int v, void* host, int nd, const int32_t* axis_edge);
+
+/* identity_messages (src/formnetworks/quadraticformnetwork.jl:96-124): delta on every directed edge. */
+int itn_msg_set_identity(itn_net* net);
+/* set_message! / message (abstractbeliefpropagationcache.jl:173-200). */
+int itn_msg_set(itn_net* net, int src, int dst, const void* host_chi2);
+int itn_msg_get(const itn_net* net, int src, int dst, void* host_chi2);
+
+/* ---- belief propagation ------------------------------------------------------------------ */
+
+/* update(::Algorithm"bp", bpc) (abstractbeliefpropagationcache.jl:313-329) with
+ * update_iteration sequential (:272-287; group_ptr == NULL: Gauss-Seidel over the list, executed as
+ * dependency wavefronts with identical arithmetic) or grouped/synchronous (:294-308; group_ptr =
+ * ngroups+1 offsets into the list; every group reads the pre-sweep messages, results are written
+ * back at the end of the sweep.  Only single-edge groups are supported).
+ * updated_message(::Algorithm"contract") (:225-239) and message_diff (:32-36) run on the device.
+ * tol < 0: `tol = nothing` (no diff computed).  Outputs may be NULL. */
+int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t* seq_dst, int nseq,
+                  const int32_t* group_ptr, int ngroups, int maxiter, double tol, int normalize,
+                  int32_t* iters, double* last_mean_diff);
+
+/* updated_message(bpc, edge) without storing it (test_belief_propagation.jl:51). */
+int itn_updated_message(itn_net* net, int src, int dst, int normalize, void* host_chi2);
+/* message_diff(updated_message(bpc, e), message(bpc, e)) for the n given directed edges. */
+int itn_message_residuals(itn_net* net, const int32_t* src, const int32_t* dst, int n, double* out_n);
+
+/* ---- scalars, rescale, observables --------------------------------------------------------- */
+
+/* vertex_scalars / edge_scalars (abstract :83-97; region_scalar beliefpropagationcache.jl:107-119).
+ * z_v: nv scalars, z_e: ne scalars, in the network dtype. */
+int itn_region_scalars(itn_net* net, void* z_v, void* z_e);
+/* logscalar(bpc) (abstract :397-408); out = {re, im}; re = -Inf if an edge scalar is zero. */
+int itn_logscalar(itn_net* net, double out_re_im[2]);
+/* rescale(bpc) = rescale_messages + rescale_partitions over all ket/bra vertices
+ * (beliefpropagationcache.jl:121-139, abstract :349-395; normalize.jl:63-80). */
+int itn_rescale(itn_net* net);
+
+/* expect(psiIpsi, op) (src/expect.jl:5-19) for n vertices; ops: n matrices d x d, column-major
+ * O[s_out, s_in]; out: n scalars (network dtype). */
+int itn_expect1(itn_net* net, const int32_t* verts, int n, const void* ops, void* out_n);
+/* two-site RDM idiom (test_belief_propagation.jl:64-91) on n edges: out = n matrices
+ * (d_u d_v) x (d_u d_v), column-major, row index = s_u + d_u * s_v, unit trace. */
+int itn_rdm2(itn_net* net, const int32_t* eids, int n, void* out);
+
+/* ---- gates ---------------------------------------------------------------------------------- */
+
+/* one-site apply (src/apply.jl:108-116): A'[s',..] = sum_s gate[s', s] A[s,..]. */
+int itn_apply1(itn_net* net, const int32_t* verts, int n, const void* gates_n_dxd, int normalize);
+
+/* two-site apply with BP product environments = simple_update_bp (src/apply.jl:33-95,117-139) on a
+ * vertex-disjoint batch of n edges.  gates: n arrays g[s1', s2', s1, s2] column-major with
+ * (1, 2) = (esrc, edst) of the edge.  maxdim <= 0: none; cutoff < 0: `cutoff = nothing`.
+ * The environments are the cache's current messages.  Outputs (nullable): new bond dimension,
+ * truncation error (callback's truncation_error, apply.jl:89) and singular values (svals_stride
+ * doubles per edge, zero padded).  msg_mode: what to store as both messages on a gated edge —
+ * 0 = identity, 1 = diag(singular values) (the Vidal-gauge fixed point of the updated pair). */
+int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* gates, int maxdim,
+               double cutoff, int normalize, int msg_mode, int32_t* newdim_n, double* truncerr_n,
+               double* svals, int svals_stride);
+
+/* map_eigvals(f, A, ...; ishermitian = true, cutoff) (src/apply.jl:21-25) for a batch of n
+ * Hermitian chi x chi host matrices; fn: 0 = sqrt, 1 = inv o sqrt, 2 = inv.  cutoff < 0: none. */
+int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, const void* host_in,
+                    void* host_out, double cutoff);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+
+/* Number of kernels this library has launched on ctx since creation (bench.py "gpu_launches"). */
+int itn_ctx_launch_count(const itn_ctx* ctx, int64_t* out);
+/* Select the message-update implementation: 0 = auto (DMMA fast path where a bucket qualifies,
+ * generic otherwise), 1 = force the generic kernels (used by the parity tests as a second opinion). */
+int itn_ctx_set_path(itn_ctx* ctx, int mode);
+/* Device time of the last itn_bp_update in milliseconds (CUDA events on the context stream) and
+ * the share spent in the dominant contraction kernels. */
+int itn_bp_last_timing(const itn_net* net, double* total_ms, double* contract_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITN_B200_H */

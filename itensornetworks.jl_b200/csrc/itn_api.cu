@@ -1,0 +1,1261 @@
+// C ABI of libitn_b200: handle lifetime, host<->device marshalling, BP driver, scalars, observables.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <memory>
+#include <numeric>
+
+#include "itn_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+void itn_set_error(const std::string& s) { g_err = s; }
+extern "C" const char* itn_last_error(void) { return g_err.c_str(); }
+extern "C" int itn_version(void) { return 100; }
+
+#define API_BEGIN try {
+#define API_END                                  \
+  }                                              \
+  catch (const ItnError& e) {                    \
+    itn_set_error(e.what());                     \
+    return e.code;                               \
+  }                                              \
+  catch (const std::bad_alloc&) {                \
+    itn_set_error("host allocation failed");     \
+    return ITN_ENOMEM;                           \
+  }                                              \
+  catch (const std::exception& e) {              \
+    itn_set_error(e.what());                     \
+    return ITN_EINVAL;                           \
+  }                                              \
+  return ITN_OK;
+
+void* itn_dev_alloc(itn_ctx* ctx, size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw ItnError(ITN_ENOMEM, std::string("device allocation of ") + std::to_string(bytes) +
+                                   " bytes failed: " + cudaGetErrorString(e));
+  }
+  return p;
+}
+void itn_dev_free(itn_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+static void set_device(const itn_ctx* ctx) { CUDA_CHECK(cudaSetDevice(ctx->device)); }
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Marshal {
+  int nd;
+  int dims[ITN_MAX_MODES];          // host axis extents
+  long long cstride[ITN_MAX_MODES]; // canonical stride of host axis i
+};
+
+// host (interleaved complex, arbitrary axis order) -> device planar canonical
+template <bool C>
+__global__ void k_import(const double* __restrict__ in, double* __restrict__ out, long long n, Marshal m) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i, off = 0;
+    for (int a = 0; a < m.nd; ++a) {
+      int d = m.dims[a];
+      long long q = r / d;
+      off += (r - q * d) * m.cstride[a];
+      r = q;
+    }
+    if (C) {
+      out[off] = in[2 * i];
+      out[n + off] = in[2 * i + 1];
+    } else {
+      out[off] = in[i];
+    }
+  }
+}
+template <bool C>
+__global__ void k_export(const double* __restrict__ in, double* __restrict__ out, long long n, Marshal m) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i, off = 0;
+    for (int a = 0; a < m.nd; ++a) {
+      int d = m.dims[a];
+      long long q = r / d;
+      off += (r - q * d) * m.cstride[a];
+      r = q;
+    }
+    if (C) {
+      out[2 * i] = in[off];
+      out[2 * i + 1] = in[n + off];
+    } else {
+      out[i] = in[off];
+    }
+  }
+}
+
+struct IdJob {
+  double* p;
+  int chi;
+};
+template <bool C>
+__global__ void k_identity(const IdJob* __restrict__ jobs) {
+  IdJob J = jobs[blockIdx.x];
+  int n2 = J.chi * J.chi;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    J.p[i] = (i % J.chi == i / J.chi) ? 1.0 : 0.0;
+    if (C) J.p[n2 + i] = 0.0;
+  }
+}
+
+__global__ void k_sum_fixed(const double* __restrict__ x, int n, double* __restrict__ out) {
+  // deterministic single-block sum
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+struct EdgePair {
+  double* m1;  // planar
+  double* m2;
+  int n2;
+};
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Z_e = sum m1[l,l'] * m2[l,l'] (no conjugate)   beliefpropagationcache.jl:115-119
+template <bool C>
+__global__ void k_edge_scalar(const EdgePair* __restrict__ ep, double* __restrict__ out /*2 per edge*/) {
+  EdgePair E = ep[blockIdx.x];
+  double sr = 0, si = 0;
+  for (int i = threadIdx.x; i < E.n2; i += 32) {
+    double ar = E.m1[i], br = E.m2[i];
+    if (C) {
+      double ai = E.m1[E.n2 + i], bi = E.m2[E.n2 + i];
+      sr += ar * br - ai * bi;
+      si += ar * bi + ai * br;
+    } else {
+      sr += ar * br;
+    }
+  }
+  sr = wsum(sr);
+  si = wsum(si);
+  if (threadIdx.x == 0) {
+    out[2 * blockIdx.x] = sr;
+    out[2 * blockIdx.x + 1] = si;
+  }
+}
+
+// rescale_messages (beliefpropagationcache.jl:121-139), one warp per edge
+template <bool C>
+__global__ void k_rescale_msgs(const EdgePair* __restrict__ ep) {
+  EdgePair E = ep[blockIdx.x];
+  double s1 = 0, s2 = 0, nr = 0, ni = 0;
+  for (int i = threadIdx.x; i < E.n2; i += 32) {
+    double ar = E.m1[i], br = E.m2[i];
+    double ai = C ? E.m1[E.n2 + i] : 0.0, bi = C ? E.m2[E.n2 + i] : 0.0;
+    s1 += ar * ar + ai * ai;
+    s2 += br * br + bi * bi;
+    nr += ar * br - ai * bi;
+    ni += ar * bi + ai * br;
+  }
+  s1 = wsum(s1); s2 = wsum(s2); nr = wsum(nr); ni = wsum(ni);
+  const double n1 = sqrt(s1), n2 = sqrt(s2);
+  nr /= (n1 * n2);
+  ni /= (n1 * n2);
+  double sgn = 1.0;
+  if (ni == 0.0) {  // isreal(n): me[1] *= sign(n); n *= sign(n)
+    sgn = (nr > 0.0) ? 1.0 : ((nr < 0.0) ? -1.0 : 0.0);
+    nr *= sgn;
+  }
+  // sf = inv(sqrt(n)), principal branch
+  double mod = sqrt(nr * nr + ni * ni);
+  double sq_r, sq_i;
+  if (ni == 0.0) {
+    sq_r = sqrt(nr);
+    sq_i = 0.0;
+  } else {
+    sq_r = sqrt(0.5 * (mod + nr));
+    sq_i = copysign(sqrt(0.5 * (mod - nr)), ni);
+  }
+  double den = sq_r * sq_r + sq_i * sq_i;
+  double fr = sq_r / den, fi = -sq_i / den;
+  const double a1 = sgn / n1, a2 = 1.0 / n2;
+  for (int i = threadIdx.x; i < E.n2; i += 32) {
+    double ar = E.m1[i] * a1, br = E.m2[i] * a2;
+    if (C) {
+      double ai = E.m1[E.n2 + i] * a1, bi = E.m2[E.n2 + i] * a2;
+      E.m1[i] = fr * ar - fi * ai;
+      E.m1[E.n2 + i] = fr * ai + fi * ar;
+      E.m2[i] = fr * br - fi * bi;
+      E.m2[E.n2 + i] = fr * bi + fi * br;
+    } else {
+      E.m1[i] = fr * ar;
+      E.m2[i] = fr * br;
+    }
+  }
+}
+
+struct ScaleJob {
+  double* p;
+  long long n;      // total doubles (both planes)
+  const double* z;  // {re, im} of Z_v, or null
+  double s;         // explicit factor when z is null
+};
+// A *= |Z_v|^(-1/2)   (rescale_partitions, abstractbeliefpropagationcache.jl:349-379 with k = 2)
+__global__ void k_scale(const ScaleJob* __restrict__ jobs) {
+  ScaleJob J = jobs[blockIdx.x];
+  double f = J.s;
+  if (J.z) f = 1.0 / sqrt(sqrt(J.z[0] * J.z[0] + J.z[1] * J.z[1]));
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < J.n; i += (long long)gridDim.y * blockDim.x)
+    J.p[i] *= f;
+}
+
+struct ExpectJob {
+  const double* rho;  // planar d x d, rho[s + d*s']
+  const double* op;   // planar d x d, O[s_out + d*s_in]
+  int d;
+};
+template <bool C>
+__global__ void k_expect_finalize(const ExpectJob* __restrict__ jobs, int n, double* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  ExpectJob J = jobs[j];
+  const int d = J.d, d2 = d * d;
+  double nr = 0, ni = 0, tr = 0, ti = 0;
+  for (int s = 0; s < d; ++s) {
+    tr += J.rho[s + d * s];
+    if (C) ti += J.rho[d2 + s + d * s];
+    for (int sp = 0; sp < d; ++sp) {
+      double orr = J.op[sp + d * s], rr = J.rho[s + d * sp];
+      if (C) {
+        double oi = J.op[d2 + sp + d * s], ri = J.rho[d2 + s + d * sp];
+        nr += orr * rr - oi * ri;
+        ni += orr * ri + oi * rr;
+      } else {
+        nr += orr * rr;
+      }
+    }
+  }
+  double den = tr * tr + ti * ti;
+  out[2 * j] = (nr * tr + ni * ti) / den;
+  out[2 * j + 1] = (ni * tr - nr * ti) / den;
+}
+
+struct Rdm2Job {
+  const double* eu;  // planar (du*chi)^2 : E[(s + du*l) + Nu*(s' + du*l')]
+  const double* ev;
+  int du, dv, chi;
+};
+template <bool C>
+__global__ void __launch_bounds__(256) k_rdm2_finalize(const Rdm2Job* __restrict__ jobs, double* __restrict__ out, int out_stride) {
+  __shared__ double res[2 * 256];
+  Rdm2Job J = jobs[blockIdx.x];
+  const int du = J.du, dv = J.dv, chi = J.chi;
+  const int Nu = du * chi, Nv = dv * chi, D = du * dv, nout = D * D;
+  const long long pu = (long long)Nu * Nu, pv = (long long)Nv * Nv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < nout; o += nw) {
+    int row = o % D, col = o / D;
+    int su = row % du, sv = row / du, sup = col % du, svp = col / du;
+    double sr = 0, si = 0;
+    for (int t = lane; t < chi * chi; t += 32) {
+      int l = t % chi, lp = t / chi;
+      long long iu = (su + du * l) + (long long)Nu * (sup + du * lp);
+      long long iv = (sv + dv * l) + (long long)Nv * (svp + dv * lp);
+      double ar = J.eu[iu], br = J.ev[iv];
+      if (C) {
+        double ai = J.eu[pu + iu], bi = J.ev[pv + iv];
+        sr += ar * br - ai * bi;
+        si += ar * bi + ai * br;
+      } else {
+        sr += ar * br;
+      }
+    }
+    sr = wsum(sr);
+    si = wsum(si);
+    if (lane == 0) {
+      res[2 * o] = sr;
+      res[2 * o + 1] = si;
+    }
+  }
+  __syncthreads();
+  double tr = 0, ti = 0;
+  for (int s = 0; s < D; ++s) {
+    tr += res[2 * (s + D * s)];
+    ti += res[2 * (s + D * s) + 1];
+  }
+  double den = tr * tr + ti * ti;
+  double* o_ = out + (long long)blockIdx.x * out_stride;
+  for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+    double r = res[2 * o], i = res[2 * o + 1];
+    o_[2 * o] = (r * tr + i * ti) / den;
+    o_[2 * o + 1] = (i * tr - r * ti) / den;
+  }
+}
+
+struct Apply1Job {
+  double* t;        // planar tensor, site index fastest
+  long long n;
+  const double* g;  // planar d x d gate, g[s' + d*s]
+  int d;
+  int normalize;
+};
+template <bool C>
+__global__ void __launch_bounds__(256) k_apply1(const Apply1Job* __restrict__ jobs, double* __restrict__ sumsq) {
+  Apply1Job J = jobs[blockIdx.x];
+  const int d = J.d, d2 = d * d;
+  const long long cols = J.n / d;
+  double ss = 0.0;
+  for (long long c = (long long)blockIdx.y * blockDim.x + threadIdx.x; c < cols; c += (long long)gridDim.y * blockDim.x) {
+    double xr[8], xi[8];
+    for (int s = 0; s < d; ++s) {
+      xr[s] = J.t[c * d + s];
+      xi[s] = C ? J.t[J.n + c * d + s] : 0.0;
+    }
+    for (int sp = 0; sp < d; ++sp) {
+      double yr = 0, yi = 0;
+      for (int s = 0; s < d; ++s) {
+        double gr = J.g[sp + d * s];
+        double gi = C ? J.g[d2 + sp + d * s] : 0.0;
+        yr += gr * xr[s] - gi * xi[s];
+        yi += gr * xi[s] + gi * xr[s];
+      }
+      J.t[c * d + sp] = yr;
+      if (C) J.t[J.n + c * d + sp] = yi;
+      ss += yr * yr + yi * yi;
+    }
+  }
+  if (sumsq) {
+    ss = wsum(ss);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sumsq[blockIdx.x], ss);
+  }
+}
+
+struct NormJob {
+  double* p;
+  long long n;  // total doubles
+};
+// deterministic per-tensor Frobenius norm then scale (one block per tensor)
+__global__ void __launch_bounds__(256) k_normalize(const NormJob* __restrict__ jobs) {
+  __shared__ double sh[8];
+  __shared__ double tot;
+  NormJob J = jobs[blockIdx.x];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < J.n; i += blockDim.x) s += J.p[i] * J.p[i];
+  s = wsum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    tot = t;
+  }
+  __syncthreads();
+  double f = 1.0 / sqrt(tot);
+  for (long long i = threadIdx.x; i < J.n; i += blockDim.x) J.p[i] *= f;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int itn_ctx_create(int device, void* stream, itn_ctx** out) {
+  API_BEGIN
+  ITN_REQUIRE(out != nullptr, ITN_EINVAL, "out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw ItnError(ITN_ECUDA, "no CUDA device available: libitn_b200 has no CPU fallback");
+  }
+  ITN_REQUIRE(device >= 0 && device < ndev, ITN_EINVAL, "device index out of range");
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  ITN_REQUIRE(prop.major >= 10, ITN_ECUDA,
+              std::string("libitn_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) +
+                  std::to_string(prop.minor));
+  itn_ctx* c = new itn_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  cudaMemPool_t pool;
+  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  size_t freeb = 0, totalb = 0;
+  CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb));
+  c->ws_budget = std::max<size_t>((size_t)1 << 30, freeb / 8);
+  *out = c;
+  API_END
+}
+
+extern "C" int itn_ctx_destroy(itn_ctx* ctx) {
+  API_BEGIN
+  if (!ctx) return ITN_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->nccl && ctx->nccl_lib) {
+    typedef int (*destroy_t)(void*);
+    destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+    if (f) f(ctx->nccl);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  API_END
+}
+
+extern "C" int itn_ctx_sync(itn_ctx* ctx) {
+  API_BEGIN
+  ITN_REQUIRE(ctx, ITN_EINVAL, "ctx is NULL");
+  set_device(ctx);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+extern "C" int itn_ctx_launch_count(const itn_ctx* ctx, int64_t* out) {
+  API_BEGIN
+  ITN_REQUIRE(ctx && out, ITN_EINVAL, "NULL argument");
+  *out = ctx->launches;
+  API_END
+}
+
+extern "C" int itn_ctx_set_path(itn_ctx* ctx, int mode) {
+  API_BEGIN
+  ITN_REQUIRE(ctx, ITN_EINVAL, "ctx is NULL");
+  ITN_REQUIRE(mode == 0 || mode == 1, ITN_EINVAL, "mode must be 0 (auto) or 1 (generic)");
+  ctx->path_mode = mode;
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// network
+// ------------------------------------------------------------------------------------------------
+static void alloc_message(itn_net* net, int did) {
+  int e = did / 2;
+  long long n2 = (long long)net->edim[e] * net->edim[e];
+  if (net->M[did].p && net->M[did].n == n2) return;
+  if (net->M[did].p) itn_dev_free(net->ctx, net->M[did].p);
+  net->M[did].p = (double*)itn_dev_alloc(net->ctx, (size_t)n2 * net->planes() * sizeof(double));
+  net->M[did].n = n2;
+}
+
+static void set_identity_messages(itn_net* net, const std::vector<int>& dids) {
+  if (dids.empty()) return;
+  std::vector<IdJob> jobs;
+  for (int did : dids) {
+    alloc_message(net, did);
+    jobs.push_back({net->M[did].p, net->edim[did / 2]});
+  }
+  DevBuf b(net->ctx, jobs.size() * sizeof(IdJob));
+  const IdJob* d = itn_upload(net->ctx, jobs, b);
+  if (net->cplx) k_identity<true><<<(unsigned)jobs.size(), 128, 0, net->ctx->stream>>>(d);
+  else k_identity<false><<<(unsigned)jobs.size(), 128, 0, net->ctx->stream>>>(d);
+  ITN_LAUNCH_CHECK(net->ctx);
+}
+
+extern "C" int itn_net_create(itn_ctx* ctx, int dtype, int nv, int ne, const int32_t* esrc, const int32_t* edst,
+                              const int32_t* edim, const int32_t* sdim, const int32_t* owner, itn_net** out) {
+  API_BEGIN
+  ITN_REQUIRE(ctx && out, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(dtype == ITN_F64 || dtype == ITN_C128, ITN_EUNSUPPORTED, "dtype must be 0 (Float64) or 1 (ComplexF64)");
+  ITN_REQUIRE(nv > 0 && ne >= 0, ITN_EINVAL, "nv must be > 0 and ne >= 0");
+  ITN_REQUIRE(sdim && (ne == 0 || (esrc && edst && edim)), ITN_EINVAL, "NULL graph arrays");
+  set_device(ctx);
+  std::unique_ptr<itn_net> net(new itn_net());
+  net->ctx = ctx;
+  net->dtype = dtype;
+  net->cplx = dtype == ITN_C128;
+  net->nv = nv;
+  net->ne = ne;
+  net->esrc.assign(esrc, esrc + ne);
+  net->edst.assign(edst, edst + ne);
+  net->edim.assign(edim, edim + ne);
+  net->sdim.assign(sdim, sdim + nv);
+  net->owner.assign(nv, 0);
+  if (owner) net->owner.assign(owner, owner + nv);
+  net->inc.assign(nv, {});
+  for (int v = 0; v < nv; ++v) ITN_REQUIRE(sdim[v] >= 1 && sdim[v] <= 8, ITN_EUNSUPPORTED, "site dimension must be in 1..8");
+  for (int e = 0; e < ne; ++e) {
+    int s = esrc[e], d = edst[e];
+    ITN_REQUIRE(s >= 0 && s < nv && d >= 0 && d < nv && s != d, ITN_EINVAL, "edge endpoint out of range or self loop");
+    ITN_REQUIRE(edim[e] >= 1, ITN_ESHAPE, "bond dimension must be >= 1");
+    ITN_REQUIRE(net->did(s, d) < 0 && net->did(d, s) < 0, ITN_EUNSUPPORTED, "multi-edges are not supported");
+    net->dmap[((uint64_t)(uint32_t)s << 32) | (uint32_t)d] = 2 * e;
+    net->dmap[((uint64_t)(uint32_t)d << 32) | (uint32_t)s] = 2 * e + 1;
+    net->inc[s].push_back(e);
+    net->inc[d].push_back(e);
+  }
+  for (int v = 0; v < nv; ++v)
+    ITN_REQUIRE((int)net->inc[v].size() + 1 <= ITN_MAX_MODES, ITN_EUNSUPPORTED, "vertex degree above 9 is not supported");
+  net->T.assign(nv, DevTensor());
+  net->M.assign(2 * (size_t)ne, DevTensor());
+  *out = net.release();
+  API_END
+}
+
+static void free_net_storage(itn_net* net) {
+  for (auto& t : net->T)
+    if (t.p) itn_dev_free(net->ctx, t.p), t.p = nullptr;
+  for (auto& m : net->M)
+    if (m.p) itn_dev_free(net->ctx, m.p), m.p = nullptr;
+  itn_fast_release(net);
+}
+
+extern "C" int itn_net_destroy(itn_net* net) {
+  API_BEGIN
+  if (!net) return ITN_OK;
+  cudaSetDevice(net->ctx->device);
+  free_net_storage(net);
+  delete net;
+  API_END
+}
+
+extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
+  API_BEGIN
+  ITN_REQUIRE(src && out, ITN_EINVAL, "NULL argument");
+  set_device(src->ctx);
+  std::unique_ptr<itn_net> net(new itn_net(*src));
+  net->fast = nullptr;
+  for (auto& t : net->T) t.p = nullptr;
+  for (auto& m : net->M) m.p = nullptr;
+  const int P = src->planes();
+  for (int v = 0; v < src->nv; ++v)
+    if (src->T[v].p) {
+      size_t b = (size_t)src->T[v].n * P * sizeof(double);
+      net->T[v].p = (double*)itn_dev_alloc(src->ctx, b);
+      CUDA_CHECK(cudaMemcpyAsync(net->T[v].p, src->T[v].p, b, cudaMemcpyDeviceToDevice, src->ctx->stream));
+    }
+  for (size_t d = 0; d < src->M.size(); ++d)
+    if (src->M[d].p) {
+      size_t b = (size_t)src->M[d].n * P * sizeof(double);
+      net->M[d].p = (double*)itn_dev_alloc(src->ctx, b);
+      CUDA_CHECK(cudaMemcpyAsync(net->M[d].p, src->M[d].p, b, cudaMemcpyDeviceToDevice, src->ctx->stream));
+    }
+  *out = net.release();
+  API_END
+}
+
+extern "C" int itn_sync(itn_net* net) {
+  API_BEGIN
+  ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  set_device(net->ctx);
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  API_END
+}
+
+extern "C" int itn_net_edge_dim(const itn_net* net, int e, int32_t* out) {
+  API_BEGIN
+  ITN_REQUIRE(net && out, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(e >= 0 && e < net->ne, ITN_EINVAL, "edge id out of range");
+  *out = net->edim[e];
+  API_END
+}
+
+extern "C" int itn_net_tensor_size(const itn_net* net, int v, int64_t* out) {
+  API_BEGIN
+  ITN_REQUIRE(net && out, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "vertex out of range");
+  *out = net->tensor_elems(v);
+  API_END
+}
+
+static Marshal make_marshal(const itn_net* net, int v, int nd, const int32_t* axis_edge) {
+  const int z = (int)net->inc[v].size();
+  ITN_REQUIRE(nd == z + 1, ITN_ESHAPE,
+              "tensor of vertex " + std::to_string(v) + " must have " + std::to_string(z + 1) + " axes");
+  // canonical strides
+  std::vector<long long> cs(z + 1);
+  long long s = 1;
+  cs[0] = 1;
+  s = net->sdim[v];
+  for (int k = 0; k < z; ++k) {
+    cs[k + 1] = s;
+    s *= net->edim[net->inc[v][k]];
+  }
+  Marshal m;
+  m.nd = nd;
+  std::vector<bool> seen(z + 1, false);
+  for (int a = 0; a < nd; ++a) {
+    int mode;
+    if (!axis_edge) {
+      mode = a;
+    } else if (axis_edge[a] < 0) {
+      mode = 0;
+    } else {
+      int k = net->slot(v, axis_edge[a]);
+      ITN_REQUIRE(k >= 0, ITN_EINVAL, "axis_edge names an edge that is not incident to the vertex");
+      mode = k + 1;
+    }
+    ITN_REQUIRE(!seen[mode], ITN_EINVAL, "axis_edge repeats an axis");
+    seen[mode] = true;
+    m.dims[a] = mode == 0 ? net->sdim[v] : net->edim[net->inc[v][mode - 1]];
+    m.cstride[a] = cs[mode];
+  }
+  return m;
+}
+
+extern "C" int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd, const int32_t* axis_edge) {
+  API_BEGIN
+  ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "vertex out of range");
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  Marshal m = make_marshal(net, v, nd, axis_edge);
+  const long long n = net->tensor_elems(v);
+  const int P = net->planes();
+  if (!net->T[v].p || net->T[v].n != n) {
+    if (net->T[v].p) itn_dev_free(ctx, net->T[v].p);
+    net->T[v].p = (double*)itn_dev_alloc(ctx, (size_t)n * P * sizeof(double));
+    net->T[v].n = n;
+  }
+  net->topo_version++;
+  DevBuf stage(ctx, (size_t)n * P * sizeof(double));
+  CUDA_CHECK(cudaMemcpyAsync(stage.p, host, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  unsigned g = (unsigned)std::min<long long>((n + 255) / 256, 4096);
+  if (net->cplx) k_import<true><<<g, 256, 0, ctx->stream>>>(stage.as<double>(), net->T[v].p, n, m);
+  else k_import<false><<<g, 256, 0, ctx->stream>>>(stage.as<double>(), net->T[v].p, n, m);
+  ITN_LAUNCH_CHECK(ctx);
+  API_END
+}
+
+extern "C" int itn_net_get_tensor(const itn_net* net_, int v, void* host, int nd, const int32_t* axis_edge) {
+  API_BEGIN
+  itn_net* net = const_cast<itn_net*>(net_);
+  ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "vertex out of range");
+  ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor is not set");
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  Marshal m = make_marshal(net, v, nd, axis_edge);
+  const long long n = net->T[v].n;
+  const int P = net->planes();
+  DevBuf stage(ctx, (size_t)n * P * sizeof(double));
+  unsigned g = (unsigned)std::min<long long>((n + 255) / 256, 4096);
+  if (net->cplx) k_export<true><<<g, 256, 0, ctx->stream>>>(net->T[v].p, stage.as<double>(), n, m);
+  else k_export<false><<<g, 256, 0, ctx->stream>>>(net->T[v].p, stage.as<double>(), n, m);
+  ITN_LAUNCH_CHECK(ctx);
+  CUDA_CHECK(cudaMemcpyAsync(host, stage.p, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+extern "C" int itn_msg_set_identity(itn_net* net) {
+  API_BEGIN
+  ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  set_device(net->ctx);
+  std::vector<int> dids(2 * (size_t)net->ne);
+  std::iota(dids.begin(), dids.end(), 0);
+  set_identity_messages(net, dids);
+  API_END
+}
+
+static Marshal msg_marshal(int chi) {
+  Marshal m;
+  m.nd = 2;
+  m.dims[0] = m.dims[1] = chi;
+  m.cstride[0] = 1;
+  m.cstride[1] = chi;
+  return m;
+}
+
+extern "C" int itn_msg_set(itn_net* net, int src, int dst, const void* host) {
+  API_BEGIN
+  ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
+  int did = net->did(src, dst);
+  ITN_REQUIRE(did >= 0, ITN_EINVAL, "(src, dst) is not an edge of the network");
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  alloc_message(net, did);
+  const long long n2 = net->M[did].n;
+  const int P = net->planes();
+  DevBuf stage(ctx, (size_t)n2 * P * sizeof(double));
+  CUDA_CHECK(cudaMemcpyAsync(stage.p, host, (size_t)n2 * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  Marshal m = msg_marshal(net->edim[did / 2]);
+  if (net->cplx) k_import<true><<<1, 256, 0, ctx->stream>>>(stage.as<double>(), net->M[did].p, n2, m);
+  else k_import<false><<<1, 256, 0, ctx->stream>>>(stage.as<double>(), net->M[did].p, n2, m);
+  ITN_LAUNCH_CHECK(ctx);
+  API_END
+}
+
+static void download_planar(itn_net* net, const double* dev, long long n, void* host) {
+  // planar device -> interleaved host
+  itn_ctx* ctx = net->ctx;
+  const int P = net->planes();
+  std::vector<double> tmp((size_t)n * P);
+  CUDA_CHECK(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  double* h = (double*)host;
+  if (net->cplx) {
+    for (long long i = 0; i < n; ++i) {
+      h[2 * i] = tmp[i];
+      h[2 * i + 1] = tmp[n + i];
+    }
+  } else {
+    memcpy(h, tmp.data(), (size_t)n * sizeof(double));
+  }
+}
+
+extern "C" int itn_msg_get(const itn_net* net_, int src, int dst, void* host) {
+  API_BEGIN
+  itn_net* net = const_cast<itn_net*>(net_);
+  ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
+  int did = net->did(src, dst);
+  ITN_REQUIRE(did >= 0, ITN_EINVAL, "(src, dst) is not an edge of the network");
+  ITN_REQUIRE(net->M[did].p, ITN_EINVAL, "message is not set");
+  set_device(net->ctx);
+  download_planar(net, net->M[did].p, net->M[did].n, host);
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// belief propagation driver
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct MsgJob {
+  int did, v, k;  // directed id, source vertex, slot of the edge at v
+};
+
+std::vector<MsgJob> make_msg_jobs(itn_net* net, const int32_t* src, const int32_t* dst, int n) {
+  std::vector<MsgJob> jobs(n);
+  for (int i = 0; i < n; ++i) {
+    int did = net->did(src[i], dst[i]);
+    ITN_REQUIRE(did >= 0, ITN_EINVAL,
+                "sequence entry " + std::to_string(i) + " (" + std::to_string(src[i]) + " -> " +
+                    std::to_string(dst[i]) + ") is not an edge of the network");
+    jobs[i] = {did, src[i], net->slot(src[i], did / 2)};
+  }
+  return jobs;
+}
+
+// staged outputs for a list of message jobs
+struct Staged {
+  DevBuf buf;
+  std::vector<double*> ptr;
+  Staged(itn_net* net, const std::vector<MsgJob>& jobs) : buf(net->ctx, total(net, jobs)) {
+    size_t off = 0;
+    ptr.resize(jobs.size());
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      ptr[i] = (double*)((char*)buf.p + off);
+      long long chi = net->edim[jobs[i].did / 2];
+      off += (size_t)chi * chi * net->planes() * sizeof(double);
+    }
+  }
+  static size_t total(itn_net* net, const std::vector<MsgJob>& jobs) {
+    size_t t = 0;
+    for (auto& j : jobs) {
+      long long chi = net->edim[j.did / 2];
+      t += (size_t)chi * chi * net->planes() * sizeof(double);
+    }
+    return t;
+  }
+};
+
+void compute_messages(itn_net* net, const std::vector<MsgJob>& jobs, size_t lo, size_t hi,
+                      const std::vector<double*>& staged) {
+  // fast path first (synchronous full-bucket sweeps), generic otherwise
+  std::vector<JobSpec> specs;
+  specs.reserve(hi - lo);
+  for (size_t i = lo; i < hi; ++i) specs.push_back({jobs[i].v, 1u << (jobs[i].k + 1), staged[i]});
+  itn_run_vertex_jobs(net, specs);
+}
+
+}  // namespace
+
+extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t* seq_dst, int nseq,
+                             const int32_t* group_ptr, int ngroups, int maxiter, double tol, int normalize,
+                             int32_t* iters, double* last_mean_diff) {
+  API_BEGIN
+  ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  // update(::Algorithm"bp"): "You need to specify a number of iterations for BP!" (:315-317)
+  ITN_REQUIRE(maxiter >= 0, ITN_EINVAL, "You need to specify a number of iterations for BP!");
+  ITN_REQUIRE(nseq >= 0 && (nseq == 0 || (seq_src && seq_dst)), ITN_EINVAL, "bad edge sequence");
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  if (iters) *iters = 0;
+  if (last_mean_diff) *last_mean_diff = NAN;
+  if (nseq == 0 || maxiter == 0) return ITN_OK;
+  const bool sync_mode = group_ptr != nullptr;
+  if (sync_mode) {
+    ITN_REQUIRE(ngroups == nseq && group_ptr[0] == 0, ITN_EUNSUPPORTED,
+                "grouped update supports single-edge groups only (ngroups must equal nseq)");
+    for (int i = 0; i < ngroups; ++i)
+      ITN_REQUIRE(group_ptr[i + 1] - group_ptr[i] == 1, ITN_EUNSUPPORTED, "grouped update supports single-edge groups only");
+  }
+  std::vector<MsgJob> jobs = make_msg_jobs(net, seq_src, seq_dst, nseq);
+  const bool want_diff = tol >= 0.0;
+
+  // availability simulation + dependency levels
+  std::vector<char> valid(net->M.size());
+  for (size_t d = 0; d < net->M.size(); ++d) valid[d] = net->M[d].p != nullptr;
+  std::vector<int> level(nseq, 0);
+  {
+    std::vector<int> lastw(net->M.size(), -1), lastr(net->M.size(), 0);
+    for (int i = 0; i < nseq; ++i) {
+      const MsgJob& J = jobs[i];
+      int lv = 0;
+      for (int e : net->inc[J.v]) {
+        if (e == J.did / 2) continue;
+        int m = net->msg_into(J.v, e);
+        ITN_REQUIRE(valid[m], ITN_EINVAL,
+                    "message into vertex " + std::to_string(J.v) + " on edge " + std::to_string(e) +
+                        " does not exist when updating " + std::to_string(seq_src[i]) + " -> " +
+                        std::to_string(seq_dst[i]) + " (initialise messages or use the forest-cover sequence)");
+        if (!sync_mode) lv = std::max(lv, lastw[m] + 1);
+      }
+      if (want_diff)
+        ITN_REQUIRE(net->M[J.did].p != nullptr || (!sync_mode && lastw[J.did] >= 0) , ITN_EINVAL,
+                    "tol requires an existing message on every edge of the sequence (tol = nothing on trees)");
+      if (!sync_mode) {
+        lv = std::max(lv, lastw[J.did] + 1);
+        lv = std::max(lv, lastr[J.did]);
+        for (int e : net->inc[J.v]) {
+          if (e == J.did / 2) continue;
+          int m = net->msg_into(J.v, e);
+          lastr[m] = std::max(lastr[m], lv);
+        }
+        lastw[J.did] = lv;
+        valid[J.did] = 1;
+      }
+      level[i] = lv;
+    }
+  }
+  // messages that do not exist yet get storage (filled before first read by construction)
+  for (auto& J : jobs) {
+    if (!net->M[J.did].p) {
+      alloc_message(net, J.did);
+      CUDA_CHECK(cudaMemsetAsync(net->M[J.did].p, 0, (size_t)net->M[J.did].n * net->planes() * sizeof(double), ctx->stream));
+    }
+  }
+  // stable order by level
+  std::vector<int> order(nseq);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return level[a] < level[b]; });
+  std::vector<MsgJob> sjobs(nseq);
+  for (int i = 0; i < nseq; ++i) sjobs[i] = jobs[order[i]];
+  std::vector<size_t> lvl_ptr{0};
+  for (int i = 1; i < nseq; ++i)
+    if (level[order[i]] != level[order[i - 1]]) lvl_ptr.push_back(i);
+  lvl_ptr.push_back(nseq);
+
+  Staged staged(net, sjobs);
+  DevBuf diffs(ctx, (size_t)nseq * sizeof(double));
+  DevBuf dsum(ctx, sizeof(double));
+  std::vector<int> all_dids(nseq);
+  for (int i = 0; i < nseq; ++i) all_dids[i] = sjobs[i].did;
+  const bool fast = sync_mode && ctx->path_mode == 0 && itn_fast_bp_supported(net, all_dids);
+
+  cudaEvent_t ev0, ev1;
+  CUDA_CHECK(cudaEventCreate(&ev0));
+  CUDA_CHECK(cudaEventCreate(&ev1));
+  CUDA_CHECK(cudaEventRecord(ev0, ctx->stream));
+  int done = 0;
+  double mean = NAN;
+  try {
+    for (int it = 0; it < maxiter; ++it) {
+      for (size_t l = 0; l + 1 < lvl_ptr.size(); ++l) {
+        const size_t lo = lvl_ptr[l], hi = lvl_ptr[l + 1];
+        if (fast) itn_fast_bp_sweep(net, all_dids, staged.ptr.data());
+        else compute_messages(net, sjobs, lo, hi, staged.ptr);
+        std::vector<CommitJob> cj(hi - lo);
+        for (size_t i = lo; i < hi; ++i) {
+          int chi = net->edim[sjobs[i].did / 2];
+          cj[i - lo] = {staged.ptr[i], net->M[sjobs[i].did].p, want_diff ? net->M[sjobs[i].did].p : nullptr, chi * chi};
+        }
+        itn_run_commit(net, cj, normalize, want_diff ? diffs.as<double>() + lo : nullptr);
+      }
+      ++done;
+      if (want_diff) {
+        k_sum_fixed<<<1, 256, 0, ctx->stream>>>(diffs.as<double>(), nseq, dsum.as<double>());
+        ITN_LAUNCH_CHECK(ctx);
+        double s = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&s, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        mean = s / nseq;
+        if (mean <= tol) break;
+      }
+    }
+    CUDA_CHECK(cudaEventRecord(ev1, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    net->last_total_ms = ms;
+  } catch (...) {
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    throw;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (iters) *iters = done;
+  if (last_mean_diff) *last_mean_diff = mean;
+  API_END
+}
+
+extern "C" int itn_bp_last_timing(const itn_net* net, double* total_ms, double* contract_ms) {
+  API_BEGIN
+  ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  if (total_ms) *total_ms = net->last_total_ms;
+  if (contract_ms) *contract_ms = net->last_contract_ms;
+  API_END
+}
+
+static void updated_messages_to_scratch(itn_net* net, const std::vector<MsgJob>& jobs, int normalize,
+                                        Staged& staged, Staged& dest, double* d_diffs) {
+  for (auto& J : jobs)
+    for (int e : net->inc[J.v])
+      if (e != J.did / 2)
+        ITN_REQUIRE(net->M[net->msg_into(J.v, e)].p, ITN_EINVAL, "an incoming message is not set");
+  compute_messages(net, jobs, 0, jobs.size(), staged.ptr);
+  std::vector<CommitJob> cj(jobs.size());
+  for (size_t i = 0; i < jobs.size(); ++i) {
+    int chi = net->edim[jobs[i].did / 2];
+    cj[i] = {staged.ptr[i], dest.ptr[i], d_diffs ? net->M[jobs[i].did].p : nullptr, chi * chi};
+  }
+  itn_run_commit(net, cj, normalize, d_diffs);
+}
+
+extern "C" int itn_updated_message(itn_net* net, int src, int dst, int normalize, void* host) {
+  API_BEGIN
+  ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
+  set_device(net->ctx);
+  int32_t s = src, d = dst;
+  std::vector<MsgJob> jobs = make_msg_jobs(net, &s, &d, 1);
+  Staged staged(net, jobs), dest(net, jobs);
+  updated_messages_to_scratch(net, jobs, normalize, staged, dest, nullptr);
+  long long chi = net->edim[jobs[0].did / 2];
+  download_planar(net, dest.ptr[0], chi * chi, host);
+  API_END
+}
+
+extern "C" int itn_message_residuals(itn_net* net, const int32_t* src, const int32_t* dst, int n, double* out) {
+  API_BEGIN
+  ITN_REQUIRE(net && out && (n == 0 || (src && dst)), ITN_EINVAL, "NULL argument");
+  if (n == 0) return ITN_OK;
+  set_device(net->ctx);
+  std::vector<MsgJob> jobs = make_msg_jobs(net, src, dst, n);
+  for (auto& J : jobs) ITN_REQUIRE(net->M[J.did].p, ITN_EINVAL, "message is not set");
+  Staged staged(net, jobs), dest(net, jobs);
+  DevBuf diffs(net->ctx, (size_t)n * sizeof(double));
+  updated_messages_to_scratch(net, jobs, 1, staged, dest, diffs.as<double>());
+  CUDA_CHECK(cudaMemcpyAsync(out, diffs.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, net->ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalars / rescale
+// ------------------------------------------------------------------------------------------------
+static void require_all_set(itn_net* net) {
+  for (int v = 0; v < net->nv; ++v) ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor of vertex " + std::to_string(v) + " is not set");
+  for (size_t d = 0; d < net->M.size(); ++d) ITN_REQUIRE(net->M[d].p, ITN_EINVAL, "a message is not set (run itn_bp_update first)");
+}
+
+// d_zv: 2 doubles per vertex {re, im}
+static void vertex_scalars_dev(itn_net* net, double* d_zv) {
+  std::vector<JobSpec> specs(net->nv);
+  // planar No=1 output: out[0] = re, out[1] = im for complex; real writes out[0] only
+  CUDA_CHECK(cudaMemsetAsync(d_zv, 0, (size_t)net->nv * 2 * sizeof(double), net->ctx->stream));
+  for (int v = 0; v < net->nv; ++v) specs[v] = {v, 0u, d_zv + 2 * v};
+  itn_run_vertex_jobs(net, specs);
+}
+
+static void edge_scalars_dev(itn_net* net, double* d_ze) {
+  if (net->ne == 0) return;
+  std::vector<EdgePair> ep(net->ne);
+  for (int e = 0; e < net->ne; ++e) ep[e] = {net->M[2 * e].p, net->M[2 * e + 1].p, (int)net->M[2 * e].n};
+  DevBuf b(net->ctx, ep.size() * sizeof(EdgePair));
+  const EdgePair* d = itn_upload(net->ctx, ep, b);
+  if (net->cplx) k_edge_scalar<true><<<net->ne, 32, 0, net->ctx->stream>>>(d, d_ze);
+  else k_edge_scalar<false><<<net->ne, 32, 0, net->ctx->stream>>>(d, d_ze);
+  ITN_LAUNCH_CHECK(net->ctx);
+}
+
+static void region_scalars_host(itn_net* net, std::vector<std::complex<double>>& zv, std::vector<std::complex<double>>& ze) {
+  require_all_set(net);
+  DevBuf dz(net->ctx, (size_t)(net->nv + net->ne) * 2 * sizeof(double));
+  vertex_scalars_dev(net, dz.as<double>());
+  edge_scalars_dev(net, dz.as<double>() + 2 * (size_t)net->nv);
+  std::vector<double> h((size_t)(net->nv + net->ne) * 2);
+  CUDA_CHECK(cudaMemcpyAsync(h.data(), dz.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, net->ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
+  zv.resize(net->nv);
+  ze.resize(net->ne);
+  for (int v = 0; v < net->nv; ++v) zv[v] = {h[2 * v], h[2 * v + 1]};
+  for (int e = 0; e < net->ne; ++e) ze[e] = {h[2 * (net->nv + e)], h[2 * (net->nv + e) + 1]};
+}
+
+extern "C" int itn_region_scalars(itn_net* net, void* z_v, void* z_e) {
+  API_BEGIN
+  ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  set_device(net->ctx);
+  std::vector<std::complex<double>> zv, ze;
+  region_scalars_host(net, zv, ze);
+  if (net->cplx) {
+    if (z_v) memcpy(z_v, zv.data(), zv.size() * sizeof(std::complex<double>));
+    if (z_e) memcpy(z_e, ze.data(), ze.size() * sizeof(std::complex<double>));
+  } else {
+    if (z_v) for (int v = 0; v < net->nv; ++v) ((double*)z_v)[v] = zv[v].real();
+    if (z_e) for (int e = 0; e < net->ne; ++e) ((double*)z_e)[e] = ze[e].real();
+  }
+  API_END
+}
+
+extern "C" int itn_logscalar(itn_net* net, double out[2]) {
+  API_BEGIN
+  ITN_REQUIRE(net && out, ITN_EINVAL, "NULL argument");
+  set_device(net->ctx);
+  std::vector<std::complex<double>> zv, ze;
+  region_scalars_host(net, zv, ze);
+  // logscalar (abstractbeliefpropagationcache.jl:397-408): the O(nv + ne) log-sum over the device-computed scalars
+  for (auto& z : ze)
+    if (z == std::complex<double>(0.0, 0.0)) {
+      out[0] = -INFINITY;
+      out[1] = 0.0;
+      return ITN_OK;
+    }
+  std::complex<double> acc(0.0, 0.0);
+  for (auto& z : zv) acc += std::log(z);
+  for (auto& z : ze) acc -= std::log(z);
+  out[0] = acc.real();
+  out[1] = acc.imag();
+  API_END
+}
+
+extern "C" int itn_rescale(itn_net* net) {
+  API_BEGIN
+  ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  require_all_set(net);
+  if (net->ne > 0) {
+    std::vector<EdgePair> ep(net->ne);
+    for (int e = 0; e < net->ne; ++e) ep[e] = {net->M[2 * e].p, net->M[2 * e + 1].p, (int)net->M[2 * e].n};
+    DevBuf b(ctx, ep.size() * sizeof(EdgePair));
+    const EdgePair* d = itn_upload(ctx, ep, b);
+    if (net->cplx) k_rescale_msgs<true><<<net->ne, 32, 0, ctx->stream>>>(d);
+    else k_rescale_msgs<false><<<net->ne, 32, 0, ctx->stream>>>(d);
+    ITN_LAUNCH_CHECK(ctx);
+  }
+  DevBuf dz(ctx, (size_t)net->nv * 2 * sizeof(double));
+  vertex_scalars_dev(net, dz.as<double>());
+  std::vector<ScaleJob> sj(net->nv);
+  long long maxn = 0;
+  for (int v = 0; v < net->nv; ++v) {
+    sj[v] = {net->T[v].p, net->T[v].n * net->planes(), dz.as<double>() + 2 * v, 1.0};
+    maxn = std::max<long long>(maxn, sj[v].n);
+  }
+  DevBuf sb(ctx, sj.size() * sizeof(ScaleJob));
+  const ScaleJob* dj = itn_upload(ctx, sj, sb);
+  unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + 1023) / 1024, 32));
+  k_scale<<<dim3(net->nv, gy), 256, 0, ctx->stream>>>(dj);
+  ITN_LAUNCH_CHECK(ctx);
+  net->topo_version++;
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// observables
+// ------------------------------------------------------------------------------------------------
+static void upload_planar(itn_net* net, const void* host, long long n_each, int count, double* dev) {
+  // host: `count` interleaved arrays of n_each elements -> device planar per array
+  const int P = net->planes();
+  std::vector<double> tmp((size_t)n_each * P * count);
+  const double* h = (const double*)host;
+  for (int c = 0; c < count; ++c)
+    for (long long i = 0; i < n_each; ++i) {
+      if (net->cplx) {
+        tmp[(size_t)c * n_each * 2 + i] = h[((size_t)c * n_each + i) * 2];
+        tmp[(size_t)c * n_each * 2 + n_each + i] = h[((size_t)c * n_each + i) * 2 + 1];
+      } else {
+        tmp[(size_t)c * n_each + i] = h[(size_t)c * n_each + i];
+      }
+    }
+  CUDA_CHECK(cudaMemcpyAsync(dev, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, net->ctx->stream));
+}
+
+extern "C" int itn_expect1(itn_net* net, const int32_t* verts, int n, const void* ops, void* out) {
+  API_BEGIN
+  ITN_REQUIRE(net && verts && ops && out && n >= 0, ITN_EINVAL, "NULL argument");
+  if (n == 0) return ITN_OK;
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  const int P = net->planes();
+  // all ops must share the layout d_v x d_v; they are packed back to back with their own d
+  size_t op_elems = 0, rho_elems = 0;
+  for (int i = 0; i < n; ++i) {
+    ITN_REQUIRE(verts[i] >= 0 && verts[i] < net->nv, ITN_EINVAL, "vertex out of range");
+    int d = net->sdim[verts[i]];
+    op_elems += (size_t)d * d;
+    rho_elems += (size_t)d * d;
+  }
+  DevBuf dops(ctx, op_elems * P * sizeof(double)), drho(ctx, rho_elems * P * sizeof(double));
+  DevBuf dout(ctx, (size_t)n * 2 * sizeof(double));
+  std::vector<JobSpec> specs(n);
+  std::vector<ExpectJob> ej(n);
+  size_t off = 0, hoff = 0;
+  for (int i = 0; i < n; ++i) {
+    int v = verts[i], d = net->sdim[v];
+    for (int e : net->inc[v]) ITN_REQUIRE(net->M[net->msg_into(v, e)].p, ITN_EINVAL, "an incoming message is not set");
+    double* rho = drho.as<double>() + off * P;
+    double* op = dops.as<double>() + off * P;
+    upload_planar(net, (const char*)ops + hoff * P * sizeof(double), (long long)d * d, 1, op);
+    specs[i] = {v, 1u, rho};
+    ej[i] = {rho, op, d};
+    off += (size_t)d * d;
+    hoff += (size_t)d * d;
+  }
+  itn_run_vertex_jobs(net, specs);
+  DevBuf jb(ctx, ej.size() * sizeof(ExpectJob));
+  const ExpectJob* dj = itn_upload(ctx, ej, jb);
+  if (net->cplx) k_expect_finalize<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(dj, n, dout.as<double>());
+  else k_expect_finalize<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(dj, n, dout.as<double>());
+  ITN_LAUNCH_CHECK(ctx);
+  std::vector<double> h((size_t)n * 2);
+  CUDA_CHECK(cudaMemcpyAsync(h.data(), dout.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (net->cplx) memcpy(out, h.data(), h.size() * sizeof(double));
+  else for (int i = 0; i < n; ++i) ((double*)out)[i] = h[2 * i];
+  API_END
+}
+
+extern "C" int itn_rdm2(itn_net* net, const int32_t* eids, int n, void* out) {
+  API_BEGIN
+  ITN_REQUIRE(net && eids && out && n >= 0, ITN_EINVAL, "NULL argument");
+  if (n == 0) return ITN_OK;
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  const int P = net->planes();
+  size_t env_elems = 0, out_elems = 0;
+  int maxD2 = 0;
+  for (int i = 0; i < n; ++i) {
+    int e = eids[i];
+    ITN_REQUIRE(e >= 0 && e < net->ne, ITN_EINVAL, "edge id out of range");
+    int u = net->esrc[e], v = net->edst[e];
+    long long nu = (long long)net->sdim[u] * net->edim[e], nv_ = (long long)net->sdim[v] * net->edim[e];
+    env_elems += (size_t)(nu * nu + nv_ * nv_);
+    int D = net->sdim[u] * net->sdim[v];
+    ITN_REQUIRE(D * D <= 256, ITN_EUNSUPPORTED, "rdm2 supports d_u*d_v <= 16");
+    maxD2 = std::max(maxD2, D * D);
+    out_elems += (size_t)D * D;
+  }
+  DevBuf denv(ctx, env_elems * P * sizeof(double));
+  DevBuf dout(ctx, (size_t)n * maxD2 * 2 * sizeof(double));
+  std::vector<JobSpec> specs;
+  std::vector<Rdm2Job> rj(n);
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    int e = eids[i], u = net->esrc[e], v = net->edst[e];
+    long long nu = (long long)net->sdim[u] * net->edim[e], nv_ = (long long)net->sdim[v] * net->edim[e];
+    double* eu = denv.as<double>() + off * P;
+    off += (size_t)(nu * nu);
+    double* ev = denv.as<double>() + off * P;
+    off += (size_t)(nv_ * nv_);
+    for (int w : {u, v})
+      for (int f : net->inc[w])
+        if (f != e) ITN_REQUIRE(net->M[net->msg_into(w, f)].p, ITN_EINVAL, "an incoming message is not set");
+    specs.push_back({u, 1u | (1u << (net->slot(u, e) + 1)), eu});
+    specs.push_back({v, 1u | (1u << (net->slot(v, e) + 1)), ev});
+    rj[i] = {eu, ev, net->sdim[u], net->sdim[v], net->edim[e]};
+  }
+  itn_run_vertex_jobs(net, specs);
+  DevBuf jb(ctx, rj.size() * sizeof(Rdm2Job));
+  const Rdm2Job* dj = itn_upload(ctx, rj, jb);
+  if (net->cplx) k_rdm2_finalize<true><<<n, 256, 0, ctx->stream>>>(dj, dout.as<double>(), maxD2 * 2);
+  else k_rdm2_finalize<false><<<n, 256, 0, ctx->stream>>>(dj, dout.as<double>(), maxD2 * 2);
+  ITN_LAUNCH_CHECK(ctx);
+  std::vector<double> h((size_t)n * maxD2 * 2);
+  CUDA_CHECK(cudaMemcpyAsync(h.data(), dout.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  double* o = (double*)out;
+  size_t oo = 0;
+  for (int i = 0; i < n; ++i) {
+    int e = eids[i];
+    int D = net->sdim[net->esrc[e]] * net->sdim[net->edst[e]];
+    for (int t = 0; t < D * D; ++t) {
+      if (net->cplx) {
+        o[2 * (oo + t)] = h[(size_t)i * maxD2 * 2 + 2 * t];
+        o[2 * (oo + t) + 1] = h[(size_t)i * maxD2 * 2 + 2 * t + 1];
+      } else {
+        o[oo + t] = h[(size_t)i * maxD2 * 2 + 2 * t];
+      }
+    }
+    oo += (size_t)D * D;
+  }
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-site gates
+// ------------------------------------------------------------------------------------------------
+extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void* gates, int normalize) {
+  API_BEGIN
+  ITN_REQUIRE(net && verts && gates && n >= 0, ITN_EINVAL, "NULL argument");
+  if (n == 0) return ITN_OK;
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  const int P = net->planes();
+  size_t g_elems = 0;
+  std::vector<char> seen(net->nv, 0);
+  for (int i = 0; i < n; ++i) {
+    int v = verts[i];
+    ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "Gate being applied does not share indices with tensor network.");
+    ITN_REQUIRE(!seen[v], ITN_EINVAL, "a batch of one-site gates must act on distinct vertices");
+    seen[v] = 1;
+    ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor is not set");
+    g_elems += (size_t)net->sdim[v] * net->sdim[v];
+  }
+  DevBuf dg(ctx, g_elems * P * sizeof(double));
+  std::vector<Apply1Job> jobs(n);
+  std::vector<NormJob> nj(n);
+  size_t off = 0;
+  long long maxn = 0;
+  for (int i = 0; i < n; ++i) {
+    int v = verts[i], d = net->sdim[v];
+    double* g = dg.as<double>() + off * P;
+    upload_planar(net, (const char*)gates + off * P * sizeof(double), (long long)d * d, 1, g);
+    jobs[i] = {net->T[v].p, net->T[v].n, g, d, normalize};
+    nj[i] = {net->T[v].p, net->T[v].n * P};
+    maxn = std::max<long long>(maxn, net->T[v].n);
+    off += (size_t)d * d;
+  }
+  DevBuf jb(ctx, jobs.size() * sizeof(Apply1Job));
+  const Apply1Job* dj = itn_upload(ctx, jobs, jb);
+  unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn / 2 + 255) / 256, 64));
+  if (net->cplx) k_apply1<true><<<dim3(n, gy), 256, 0, ctx->stream>>>(dj, nullptr);
+  else k_apply1<false><<<dim3(n, gy), 256, 0, ctx->stream>>>(dj, nullptr);
+  ITN_LAUNCH_CHECK(ctx);
+  if (normalize) {
+    DevBuf nb(ctx, nj.size() * sizeof(NormJob));
+    const NormJob* dn = itn_upload(ctx, nj, nb);
+    k_normalize<<<n, 256, 0, ctx->stream>>>(dn);
+    ITN_LAUNCH_CHECK(ctx);
+  }
+  net->topo_version++;
+  API_END
+}

@@ -1,0 +1,415 @@
+// Generic (any degree, any per-bond extent, real or complex) vertex-contraction kernels.
+//
+// A job contracts one site tensor with its conjugate and the incoming messages on every closed
+// bond, leaving a set of modes open:
+//   out[o, o'] = sum_x B[x, o] * conj(A'[x, o'])        (x = closed multi-index, o = open multi-index)
+// with A' = A permuted to [closed..., open...] and B = A' with every closed bond's incoming message
+// absorbed (one mode product per bond).  This restates
+//   updated_message(::Algorithm"contract")  src/caches/abstractbeliefpropagationcache.jl:225-239  (open = {k})
+//   region_scalar(bpc, vertex)              src/caches/beliefpropagationcache.jl:107-113          (open = {})
+//   expect numerator/denominator            src/expect.jl:5-19                                    (open = {site})
+//   two-site RDM environment                test/test_belief_propagation.jl:64-91                 (open = {site, k})
+// with the closed-form pairwise order "absorb z-1 messages into the ket, close with the bra"
+// instead of a per-call optimaltree search (abstract...cache.jl:232).
+//
+// Storage is planar (re plane, im plane).  These kernels are the shape-agnostic path and the on-GPU
+// second opinion for the DMMA fast path (itn_fast.cu); FP64 FMA pipe, not tensor cores.
+#include <algorithm>
+#include <cstring>
+
+#include "itn_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <bool C>
+__global__ void __launch_bounds__(kThreads) k_permute(const VJob* __restrict__ jobs) {
+  const VJob& J = jobs[blockIdx.x];
+  if (J.identity_perm) return;
+  const long long n = J.n;
+  const double* __restrict__ a = J.a;
+  double* __restrict__ ap = J.ap;
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.y * blockDim.x) {
+    long long r = i, off = 0;
+#pragma unroll 1
+    for (int m = 0; m < J.nm; ++m) {
+      int d = J.dims[m];
+      long long q = r / d;
+      off += (r - q * d) * J.pstride[m];
+      r = q;
+    }
+    ap[off] = a[i];
+    if (C) ap[n + off] = a[n + i];
+  }
+}
+
+// out[l, b, r] = sum_a in[l, a, r] * m(a, b);   m(a,b) = M[a + K*b]  (or M[b + N*a] if trans), optionally conj
+template <bool C>
+__global__ void __launch_bounds__(kThreads) k_modeprod(const VJob* __restrict__ jobs, int step, int smem_elems) {
+  extern __shared__ double sm[];
+  const VJob& J = jobs[blockIdx.x];
+  if (step >= J.nsteps) return;
+  const ModeStep S = J.steps[step];
+  const double* __restrict__ src = (step == 0) ? J.ap : J.w[(step - 1) & 1];
+  double* __restrict__ dst = J.w[step & 1];
+  const long long L = S.L, R = S.R;
+  const int K = S.K, N = S.N;
+  const long long n_in = L * K * R, n_out = L * N * R;
+  const int kn = K * N;
+  const bool use_sm = kn <= smem_elems;
+  // stage m as mm[a + K*b] (already transposed / conjugated)
+  if (use_sm) {
+    for (int i = threadIdx.x; i < kn; i += blockDim.x) {
+      int a = i % K, b = i / K;
+      int srcidx = S.trans ? (b + N * a) : i;
+      sm[i] = S.m[srcidx];
+      if (C) sm[kn + i] = S.conj ? -S.m[S.mplane + srcidx] : S.m[S.mplane + srcidx];
+    }
+    __syncthreads();
+  }
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < n_out;
+       idx += (long long)gridDim.y * blockDim.x) {
+    long long l = idx % L;
+    long long t = idx / L;
+    int b = (int)(t % N);
+    long long r = t / N;
+    const double* __restrict__ s = src + l + L * (long long)K * r;
+    double accr = 0.0, acci = 0.0;
+    if (use_sm) {
+      const double* mr = sm + (long long)K * b;
+      const double* mi = sm + kn + (long long)K * b;
+      for (int a = 0; a < K; ++a) {
+        double xr = s[L * a];
+        if (C) {
+          double xi = s[n_in + L * a];
+          accr += xr * mr[a] - xi * mi[a];
+          acci += xr * mi[a] + xi * mr[a];
+        } else {
+          accr += xr * mr[a];
+        }
+      }
+    } else {
+      for (int a = 0; a < K; ++a) {
+        int mi_ = S.trans ? (b + N * a) : (a + K * b);
+        double mr = S.m[mi_];
+        double xr = s[L * a];
+        if (C) {
+          double mi = S.conj ? -S.m[S.mplane + mi_] : S.m[S.mplane + mi_];
+          double xi = s[n_in + L * a];
+          accr += xr * mr - xi * mi;
+          acci += xr * mi + xi * mr;
+        } else {
+          accr += xr * mr;
+        }
+      }
+    }
+    dst[idx] = accr;
+    if (C) dst[n_out + idx] = acci;
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[o + No*o'] = sum_x B[x + X*o] * conj(A'[x + X*o'])
+template <bool C>
+__global__ void __launch_bounds__(kThreads) k_gram(const VJob* __restrict__ jobs) {
+  __shared__ double part[8 * 64 * 2];  // S <= 8 splits, No*No <= 64 when S > 1
+  const VJob& J = jobs[blockIdx.x];
+  const long long X = J.X;
+  const int No = J.No;
+  const long long n = J.n;
+  const double* __restrict__ B = (J.nsteps == 0) ? J.ap : J.w[(J.nsteps - 1) & 1];
+  const double* __restrict__ A = J.ap;
+  double* __restrict__ out = J.out;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t1 = (No + 3) >> 2, T = t1 * t1;
+  const int S = (T >= nwarps) ? 1 : (nwarps / T);
+  const int n2 = No * No;
+  for (int item = warp; item < T * S; item += nwarps) {
+    const int tile = item / S, split = item % S;
+    const int o0 = (tile % t1) * 4, p0 = (tile / t1) * 4;
+    const long long xlo = X * split / S, xhi = X * (split + 1) / S;
+    double ar[4][4], ai[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ar[i][j] = ai[i][j] = 0.0;
+    for (long long x = xlo + lane; x < xhi; x += 32) {
+      double br[4], bi[4], cr[4], ci[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bool ok = (o0 + i) < No;
+        br[i] = ok ? B[x + X * (o0 + i)] : 0.0;
+        bi[i] = (C && ok) ? B[n + x + X * (o0 + i)] : 0.0;
+        bool ok2 = (p0 + i) < No;
+        cr[i] = ok2 ? A[x + X * (p0 + i)] : 0.0;
+        ci[i] = (C && ok2) ? A[n + x + X * (p0 + i)] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // b * conj(c) = (br*cr + bi*ci) + i (bi*cr - br*ci)
+          ar[i][j] += br[i] * cr[j];
+          if (C) {
+            ar[i][j] += bi[i] * ci[j];
+            ai[i][j] += bi[i] * cr[j] - br[i] * ci[j];
+          }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double vr = warp_sum(ar[i][j]);
+        double vi = C ? warp_sum(ai[i][j]) : 0.0;
+        if (lane == 0 && (o0 + i) < No && (p0 + j) < No) {
+          int oi = (o0 + i) + No * (p0 + j);
+          if (S == 1) {
+            out[oi] = vr;
+            if (C) out[n2 + oi] = vi;
+          } else {
+            part[(split * 64 + oi) * 2] = vr;
+            part[(split * 64 + oi) * 2 + 1] = vi;
+          }
+        }
+      }
+  }
+  if (S > 1) {
+    __syncthreads();
+    for (int oi = threadIdx.x; oi < n2; oi += blockDim.x) {
+      double vr = 0.0, vi = 0.0;
+      for (int s = 0; s < S; ++s) {
+        vr += part[(s * 64 + oi) * 2];
+        vi += part[(s * 64 + oi) * 2 + 1];
+      }
+      out[oi] = vr;
+      if (C) out[n2 + oi] = vi;
+    }
+  }
+}
+
+// Block-wide deterministic sum of up to 3 values.
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* sh) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  c = warp_sum(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) {
+    sh[warp * 3] = a;
+    sh[warp * 3 + 1] = b;
+    sh[warp * 3 + 2] = c;
+  }
+  __syncthreads();
+  double ta = 0, tb = 0, tc = 0;
+  for (int w = 0; w < nw; ++w) {
+    ta += sh[w * 3];
+    tb += sh[w * 3 + 1];
+    tc += sh[w * 3 + 2];
+  }
+  a = ta;
+  b = tb;
+  c = tc;
+  __syncthreads();
+}
+
+// Frobenius-normalise the staged message, message_diff against the old one, write to dest.
+// message_diff (abstractbeliefpropagationcache.jl:32-36): 1 - |<a^, b^>|^2.
+template <bool C>
+__global__ void __launch_bounds__(128) k_commit(const CommitJob* __restrict__ jobs, int normalize,
+                                                double* __restrict__ diffs) {
+  __shared__ double sh[16];
+  const CommitJob J = jobs[blockIdx.x];
+  const int n2 = J.n2;
+  double ss = 0.0, so = 0.0, dr = 0.0;
+  double di = 0.0;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    double nr = J.staged[i], ni = C ? J.staged[n2 + i] : 0.0;
+    ss += nr * nr + ni * ni;
+    if (J.old) {
+      double orr = J.old[i], oi = C ? J.old[n2 + i] : 0.0;
+      so += orr * orr + oi * oi;
+      dr += nr * orr + ni * oi;   // conj(new) * old
+      di += nr * oi - ni * orr;
+    }
+  }
+  block_sum3(ss, so, dr, sh);
+  double dummy1 = 0, dummy2 = 0;
+  block_sum3(di, dummy1, dummy2, sh);
+  const double nrm = sqrt(ss);
+  const double scale = (normalize && nrm != 0.0) ? 1.0 / nrm : 1.0;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    J.dest[i] = J.staged[i] * scale;
+    if (C) J.dest[n2 + i] = J.staged[n2 + i] * scale;
+  }
+  if (diffs && threadIdx.x == 0) {
+    double f = (dr * dr + di * di) / (ss * so);
+    diffs[blockIdx.x] = J.old ? 1.0 - f : 0.0;
+  }
+}
+
+}  // namespace
+
+int itn_open_extent(const itn_net* net, int v, uint32_t open_mask) {
+  long long no = 1;
+  if (open_mask & 1u) no *= net->sdim[v];
+  for (size_t k = 0; k < net->inc[v].size(); ++k)
+    if (open_mask & (1u << (k + 1))) no *= net->edim[net->inc[v][k]];
+  return (int)no;
+}
+
+void itn_run_commit(itn_net* net, const std::vector<CommitJob>& jobs, int normalize, double* d_diffs) {
+  if (jobs.empty()) return;
+  itn_ctx* ctx = net->ctx;
+  DevBuf buf(ctx, jobs.size() * sizeof(CommitJob));
+  const CommitJob* d = itn_upload(ctx, jobs, buf);
+  if (net->cplx)
+    k_commit<true><<<(unsigned)jobs.size(), 128, 0, ctx->stream>>>(d, normalize, d_diffs);
+  else
+    k_commit<false><<<(unsigned)jobs.size(), 128, 0, ctx->stream>>>(d, normalize, d_diffs);
+  ITN_LAUNCH_CHECK(ctx);
+}
+
+void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
+  if (specs.empty()) return;
+  itn_ctx* ctx = net->ctx;
+  const int P = net->planes();
+  // Build descriptors (workspace pointers filled per batch).
+  std::vector<VJob> jobs(specs.size());
+  for (size_t j = 0; j < specs.size(); ++j) {
+    const JobSpec& sp = specs[j];
+    const int v = sp.v;
+    ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "vertex out of range");
+    ITN_REQUIRE(net->T[v].p != nullptr, ITN_EINVAL, "site tensor of vertex " + std::to_string(v) + " is not set");
+    const int z = (int)net->inc[v].size();
+    ITN_REQUIRE(z + 1 <= ITN_MAX_MODES, ITN_EUNSUPPORTED, "vertex degree too large");
+    VJob J;
+    memset(&J, 0, sizeof(J));
+    J.a = net->T[v].p;
+    J.n = net->T[v].n;
+    J.nm = z + 1;
+    J.dims[0] = net->sdim[v];
+    for (int k = 0; k < z; ++k) J.dims[k + 1] = net->edim[net->inc[v][k]];
+    // order: closed modes first (ascending), then open modes (ascending)
+    int order[ITN_MAX_MODES], pos = 0;
+    for (int m = 0; m < J.nm; ++m)
+      if (!(sp.open_mask & (1u << m))) order[pos++] = m;
+    const int nclosed = pos;
+    for (int m = 0; m < J.nm; ++m)
+      if (sp.open_mask & (1u << m)) order[pos++] = m;
+    long long stride = 1;
+    bool ident = true;
+    long long X = 1, No = 1;
+    int pdims[ITN_MAX_MODES];
+    for (int q = 0; q < J.nm; ++q) {
+      int m = order[q];
+      if (m != q) ident = false;
+      J.pstride[m] = stride;
+      pdims[q] = J.dims[m];
+      stride *= J.dims[m];
+      if (q < nclosed) X *= J.dims[m]; else No *= J.dims[m];
+    }
+    J.identity_perm = ident ? 1 : 0;
+    J.X = X;
+    J.No = (int)No;
+    // mode-product chain over closed bond modes
+    long long Lacc = 1;
+    for (int q = 0; q < nclosed; ++q) {
+      int m = order[q];
+      if (m >= 1) {
+        int e = net->inc[v][m - 1];
+        const DevTensor& msg = net->M[net->msg_into(v, e)];
+        ITN_REQUIRE(msg.p != nullptr, ITN_EINVAL,
+                    "message into vertex " + std::to_string(v) + " on edge " + std::to_string(e) +
+                        " is not set (on trees use the forest-cover sequence)");
+        ModeStep& S = J.steps[J.nsteps++];
+        S.L = Lacc;
+        S.K = S.N = pdims[q];
+        S.R = J.n / (Lacc * pdims[q]);
+        S.m = msg.p;
+        S.mplane = msg.n;
+        S.trans = 0;
+        S.conj = 0;
+      }
+      Lacc *= pdims[q];
+    }
+    J.out = sp.out;
+    jobs[j] = J;
+  }
+  // Batches bounded by the scratch budget: each job needs up to 3 planar copies.
+  size_t lo = 0;
+  const size_t N = jobs.size();
+  while (lo < N) {
+    size_t hi = lo;
+    size_t bytes = 0;
+    long long maxn = 0;
+    int maxsteps = 0, maxkn = 0;
+    while (hi < N) {
+      const VJob& J = jobs[hi];
+      size_t need = (size_t)J.n * P * sizeof(double) * ((J.identity_perm ? 0 : 1) + (J.nsteps >= 2 ? 2 : J.nsteps));
+      if (hi > lo && bytes + need > ctx->ws_budget) break;
+      bytes += need;
+      ++hi;
+    }
+    DevBuf ws(ctx, std::max<size_t>(bytes, 16));
+    char* base = ws.as<char>();
+    size_t off = 0;
+    std::vector<VJob> batch(jobs.begin() + lo, jobs.begin() + hi);
+    for (VJob& J : batch) {
+      size_t tb = (size_t)J.n * P * sizeof(double);
+      if (J.identity_perm) {
+        J.ap = const_cast<double*>(J.a);
+      } else {
+        J.ap = (double*)(base + off);
+        off += tb;
+      }
+      for (int i = 0; i < std::min(J.nsteps, 2); ++i) {
+        J.w[i] = (double*)(base + off);
+        off += tb;
+      }
+      maxn = std::max<long long>(maxn, J.n);
+      maxsteps = std::max(maxsteps, J.nsteps);
+      for (int s = 0; s < J.nsteps; ++s) maxkn = std::max(maxkn, J.steps[s].K * J.steps[s].N);
+    }
+    DevBuf jb(ctx, batch.size() * sizeof(VJob));
+    const VJob* dj = itn_upload(ctx, batch, jb);
+    const unsigned nb = (unsigned)batch.size();
+    unsigned gy = (unsigned)std::min<long long>((maxn + kThreads * 4 - 1) / (kThreads * 4), 64);
+    if (gy < 1) gy = 1;
+    // keep the total grid reasonable for huge batches
+    while (gy > 1 && (unsigned long long)gy * nb > 148ull * 64ull) gy = (gy + 1) / 2;
+    dim3 grid(nb, gy);
+    bool any_perm = false;
+    for (const VJob& J : batch) any_perm |= !J.identity_perm;
+    if (any_perm) {
+      if (net->cplx) k_permute<true><<<grid, kThreads, 0, ctx->stream>>>(dj);
+      else k_permute<false><<<grid, kThreads, 0, ctx->stream>>>(dj);
+      ITN_LAUNCH_CHECK(ctx);
+    }
+    int smem_elems = maxkn;
+    size_t smem_bytes = (size_t)smem_elems * P * sizeof(double);
+    if (smem_bytes > 96 * 1024) {  // too large to stage: kernels read the matrix from global memory
+      smem_elems = 0;
+      smem_bytes = 0;
+    }
+    if (smem_bytes > 48 * 1024) {
+      if (net->cplx) CUDA_CHECK(cudaFuncSetAttribute(k_modeprod<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      else CUDA_CHECK(cudaFuncSetAttribute(k_modeprod<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    }
+    for (int s = 0; s < maxsteps; ++s) {
+      if (net->cplx) k_modeprod<true><<<grid, kThreads, smem_bytes, ctx->stream>>>(dj, s, smem_elems);
+      else k_modeprod<false><<<grid, kThreads, smem_bytes, ctx->stream>>>(dj, s, smem_elems);
+      ITN_LAUNCH_CHECK(ctx);
+    }
+    if (net->cplx) k_gram<true><<<nb, kThreads, 0, ctx->stream>>>(dj);
+    else k_gram<false><<<nb, kThreads, 0, ctx->stream>>>(dj);
+    ITN_LAUNCH_CHECK(ctx);
+    lo = hi;
+  }
+}

@@ -1,0 +1,177 @@
+// Internal data model of libitn_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "itn_b200.h"
+
+#define ITN_MAX_MODES 10  // site + up to 9 bonds
+
+struct ItnError : std::runtime_error {
+  int code;
+  ItnError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void itn_set_error(const std::string& s);
+
+#define CUDA_CHECK(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      throw ItnError(_e == cudaErrorMemoryAllocation ? ITN_ENOMEM : ITN_ECUDA,                   \
+                     std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+  } while (0)
+
+#define ITN_REQUIRE(cond, code, msg)          \
+  do {                                        \
+    if (!(cond)) throw ItnError((code), (msg)); \
+  } while (0)
+
+struct itn_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int rank = 0, nranks = 1;
+  void* nccl = nullptr;      // ncclComm_t
+  void* nccl_lib = nullptr;  // dlopen handle
+  int64_t launches = 0;
+  int path_mode = 0;
+  int sm_count = 148;
+  size_t ws_budget = (size_t)6 << 30;  // scratch budget for the generic path (bytes)
+};
+
+// Planar storage: re plane [0, n), im plane [n, 2n) (complex only).
+struct DevTensor {
+  double* p = nullptr;
+  int64_t n = 0;
+};
+
+// One step of a mode-product chain: out[l, b, r] = sum_a in[l, a, r] * m(a, b)
+struct ModeStep {
+  long long L, R;
+  int K, N;          // K = summed extent, N = output extent
+  const double* m;   // planar matrix, K x N column-major (or N x K if trans)
+  long long mplane;  // offset of the imaginary plane of m
+  int trans, conj;
+};
+
+// "Contract vertex v leaving a set of modes open" job (generic path).
+struct VJob {
+  const double* a;   // source tensor, planar, canonical order [site, bonds...]
+  double* ap;        // permuted copy: closed modes first, open modes last (== a if identity)
+  double* w[2];      // ping-pong scratch (planar, n each)
+  double* out;       // staged result, planar No x No:  out[o + No*o'] = sum_x B[x,o] conj(A'[x,o'])
+  long long n;       // elements of the tensor
+  long long X;       // product of closed extents
+  int No;            // product of open extents
+  int nm;            // number of modes
+  int dims[ITN_MAX_MODES];
+  long long pstride[ITN_MAX_MODES];  // stride (in ap) of source mode i
+  int identity_perm;
+  int nsteps;
+  ModeStep steps[ITN_MAX_MODES];
+};
+
+struct CommitJob {
+  const double* staged;  // planar No x No
+  double* dest;          // planar message (may be scratch)
+  const double* old;     // planar message to diff against (may be null)
+  int n2;                // No*No
+};
+
+struct itn_net {
+  itn_ctx* ctx = nullptr;
+  int dtype = 0;
+  bool cplx = false;
+  int nv = 0, ne = 0;
+  std::vector<int> esrc, edst, edim, sdim, owner;
+  std::vector<std::vector<int>> inc;  // incident edge ids, ascending
+  std::unordered_map<uint64_t, int> dmap;  // (src,dst) -> directed id (2e: esrc->edst, 2e+1: reverse)
+  std::vector<DevTensor> T;  // per vertex
+  std::vector<DevTensor> M;  // per directed edge
+  uint64_t topo_version = 0;  // bumped whenever a tensor pointer / bond dim changes
+  double last_total_ms = 0, last_contract_ms = 0;
+  void* fast = nullptr;  // fast-path cache (owned by itn_fast.cu)
+
+  int planes() const { return cplx ? 2 : 1; }
+  int other(int e, int v) const { return esrc[e] == v ? edst[e] : esrc[e]; }
+  int slot(int v, int e) const {
+    for (size_t i = 0; i < inc[v].size(); ++i)
+      if (inc[v][i] == e) return (int)i;
+    return -1;
+  }
+  // message flowing INTO v along edge e
+  int msg_into(int v, int e) const { return edst[e] == v ? 2 * e : 2 * e + 1; }
+  int did(int s, int d) const {
+    auto it = dmap.find(((uint64_t)(uint32_t)s << 32) | (uint32_t)d);
+    return it == dmap.end() ? -1 : it->second;
+  }
+  long long tensor_elems(int v) const {
+    long long n = sdim[v];
+    for (int e : inc[v]) n *= edim[e];
+    return n;
+  }
+};
+
+// ---- device memory helpers (stream ordered) ----
+void* itn_dev_alloc(itn_ctx* ctx, size_t bytes);
+void itn_dev_free(itn_ctx* ctx, void* p);
+
+struct DevBuf {  // RAII scratch buffer
+  itn_ctx* ctx;
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf(itn_ctx* c, size_t b) : ctx(c), bytes(b) { p = b ? itn_dev_alloc(c, b) : nullptr; }
+  ~DevBuf() {
+    if (p) itn_dev_free(ctx, p);
+  }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+
+// ---- generic vertex-contraction engine (itn_generic.cu) ----
+struct JobSpec {
+  int v;
+  uint32_t open_mask;  // bit i set: mode i (0 = site, 1+k = k-th incident edge) stays open
+  double* out;         // device, planar No x No
+};
+// Runs all specs in [lo, hi) batches bounded by the workspace budget. Results in spec.out.
+void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs);
+void itn_run_commit(itn_net* net, const std::vector<CommitJob>& jobs, int normalize, double* d_diffs);
+int itn_open_extent(const itn_net* net, int v, uint32_t open_mask);
+
+// ---- fast path (itn_fast.cu) ----
+// Returns true if it handled the whole synchronous sweep set (all edges), false to fall back.
+bool itn_fast_bp_supported(itn_net* net, const std::vector<int>& dids);
+void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, double** staged_out);
+void itn_fast_release(itn_net* net);
+
+// ---- small linear algebra (itn_linalg.cu) ----
+// Batched Hermitian Jacobi eigen-decomposition based matrix function, planar matrices on device.
+void itn_dev_map_eigvals(itn_ctx* ctx, bool cplx, int fn, int chi, int n, const double* const* d_in_ptrs,
+                         double* const* d_out_ptrs, double cutoff);
+
+template <class T>
+static inline T* itn_upload(itn_ctx* ctx, const std::vector<T>& h, DevBuf& buf) {
+  if (h.empty()) return nullptr;
+  cudaError_t e = cudaMemcpyAsync(buf.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) throw ItnError(ITN_ECUDA, std::string("upload: ") + cudaGetErrorString(e));
+  // the host vector may die before the copy executes: pageable copies are staged synchronously by the
+  // runtime, so this is safe for std::vector sources.
+  return (T*)buf.p;
+}
+
+#define ITN_LAUNCH_CHECK(ctx)                                                        \
+  do {                                                                               \
+    (ctx)->launches++;                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess)                                                           \
+      throw ItnError(ITN_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+  } while (0)

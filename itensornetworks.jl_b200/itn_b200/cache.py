@@ -1,0 +1,459 @@
+"""Host mirror of the reference's BP-cache API, forwarding to libitn_b200 through the C ABI.
+
+Mirrors (same names, argument meaning and error behaviour):
+  BeliefPropagationCache            src/caches/beliefpropagationcache.jl:13-35
+  update / update_message / updated_message / message(s) / set_message
+                                    src/caches/abstractbeliefpropagationcache.jl:173-337
+  environment                       src/caches/beliefpropagationcache.jl:100-105
+  region_scalar / vertex_scalars / edge_scalars / logscalar / scalar
+                                    beliefpropagationcache.jl:107-119, abstract :83-97,:397-412
+  rescale / normalize               abstract :349-395, src/normalize.jl:13-80
+  expect                            src/expect.jl:5-109
+  apply                             src/apply.jl:97-160
+The reference's mutators are out-of-place (every one returns a fresh cache); the mirror keeps that
+default and offers `inplace=True` where copying device state would dominate.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ITNError, check, i32, lib
+from .graphs import default_edge_sequence
+from .network import ITensorNetwork
+
+_DTYPE_CODE = {np.dtype(np.float64): 0, np.dtype(np.complex128): 1}
+
+
+class Context:
+    """One per process and GPU (itn_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        check(lib().itn_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def sync(self):
+        check(lib().itn_ctx_sync(self.h))
+
+    def launch_count(self):
+        n = C.c_int64()
+        check(lib().itn_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def set_path(self, mode):
+        """0 = auto (DMMA fast path where it applies), 1 = generic kernels only."""
+        check(lib().itn_ctx_set_path(self.h, int(mode)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().itn_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class BeliefPropagationCache:
+    """BP cache of <psi|psi> with the default one-site partition; state lives on the device."""
+
+    def __init__(self, psi: ITensorNetwork = None, ctx: Context = None, messages="identity", _handle=None,
+                 _like=None):
+        if _handle is not None:  # clone
+            self.ctx, self.graph, self.dtype, self.h = _like.ctx, _like.graph, _like.dtype, _handle
+            self.sdims = list(_like.sdims)
+            return
+        self.ctx = ctx or default_context()
+        self.graph = psi.graph
+        self.dtype = psi.dtype
+        g = self.graph
+        self.sdims = [t.shape[0] for t in psi.tensors]
+        a0, p0 = i32([u for u, _ in g.edges])
+        a1, p1 = i32([v for _, v in g.edges])
+        a2, p2 = i32([psi.edge_dim(e) for e in range(g.ne)])
+        a3, p3 = i32(self.sdims)
+        h = C.c_void_p()
+        check(lib().itn_net_create(self.ctx.h, _DTYPE_CODE[self.dtype], g.nv, g.ne, p0, p1, p2, p3, None, C.byref(h)))
+        self.h = h
+        for v in range(g.nv):
+            self.set_factor(v, psi.tensors[v])
+        # initialize_cache (src/initialize_cache.jl:14-29): identity messages on loopy graphs, none on trees
+        if messages == "identity" or (messages == "default" and not g.is_tree()):
+            check(lib().itn_msg_set_identity(self.h))
+        elif isinstance(messages, dict):
+            for (u, v), m in messages.items():
+                self.set_message((u, v), m)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def copy(self):
+        h = C.c_void_p()
+        check(lib().itn_net_clone(self.h, C.byref(h)))
+        return BeliefPropagationCache(_handle=h, _like=self)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().itn_net_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(lib().itn_sync(self.h))
+
+    # -- factors ------------------------------------------------------------------------------
+    def edge_dim(self, e):
+        d = C.c_int32()
+        check(lib().itn_net_edge_dim(self.h, int(e), C.byref(d)))
+        return d.value
+
+    def _shape(self, v):
+        return (self.sdims[v],) + tuple(self.edge_dim(e) for e in self.graph.inc[v])
+
+    def set_factor(self, v, t):
+        """bpc[v] = t (ket; the bra is dag(prime(ket)) implicitly, test_belief_propagation.jl:41-45)."""
+        t = np.asarray(t, dtype=self.dtype)
+        if t.shape != self._shape(v):
+            raise ITNError(2, f"tensor of vertex {v} has shape {t.shape}, expected {self._shape(v)}")
+        f = np.asfortranarray(t)  # column-major bytes with axes [site, bonds...]
+        check(lib().itn_net_set_tensor(self.h, int(v), f.ctypes.data_as(C.c_void_p), f.ndim, None))
+
+    def factor(self, v):
+        shape = self._shape(v)
+        out = np.empty(shape, dtype=self.dtype, order="F")
+        check(lib().itn_net_get_tensor(self.h, int(v), out.ctypes.data_as(C.c_void_p), len(shape), None))
+        return np.ascontiguousarray(out)
+
+    def tensornetwork(self):
+        return ITensorNetwork(self.graph, [self.factor(v) for v in range(self.graph.nv)], self.dtype)
+
+    # -- messages -----------------------------------------------------------------------------
+    def message(self, edge):
+        u, v = edge
+        chi = self.edge_dim(self.graph.eid[(u, v)])
+        out = np.empty((chi, chi), dtype=self.dtype, order="F")
+        check(lib().itn_msg_get(self.h, int(u), int(v), out.ctypes.data_as(C.c_void_p)))
+        return np.ascontiguousarray(out)
+
+    def set_message(self, edge, m):
+        u, v = edge
+        f = np.asfortranarray(np.asarray(m, dtype=self.dtype))
+        check(lib().itn_msg_set(self.h, int(u), int(v), f.ctypes.data_as(C.c_void_p)))
+
+    def messages(self):
+        out = {}
+        for (u, v) in self.graph.edges:
+            out[(u, v)] = self.message((u, v))
+            out[(v, u)] = self.message((v, u))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# update
+# ---------------------------------------------------------------------------------------------
+
+
+def default_bp_maxiter(bpc):
+    """default_bp_maxiter (abstractbeliefpropagationcache.jl:38-42): 1 on trees, otherwise unspecified."""
+    return 1 if bpc.graph.is_tree() else None
+
+
+def update(bpc, maxiter="default", tol=None, edge_sequence=None, normalize=True, inplace=False, info=None):
+    """update(bpc; alg="bp", maxiter, tol, edge_sequence, message_update_alg=(; normalize)).
+
+    edge_sequence: list of directed edges (sequential sweep) or list of single-edge lists (parallel sweep)."""
+    if maxiter == "default":
+        maxiter = default_bp_maxiter(bpc)
+    if maxiter is None:
+        raise ITNError(1, "You need to specify a number of iterations for BP!")
+    if edge_sequence is None:
+        edge_sequence = default_edge_sequence(bpc.graph)
+    grouped = len(edge_sequence) > 0 and isinstance(edge_sequence[0], (list,)) and not isinstance(edge_sequence[0], tuple)
+    if grouped:
+        flat = [e for grp in edge_sequence for e in grp]
+        ptr = np.cumsum([0] + [len(grp) for grp in edge_sequence])
+        _, gp = i32(ptr)
+        ng = len(edge_sequence)
+    else:
+        flat, gp, ng, _ = list(edge_sequence), None, 0, None
+    out = bpc if inplace else bpc.copy()
+    a, ps = i32([u for u, _ in flat])
+    b, pd = i32([v for _, v in flat])
+    iters, diff = C.c_int32(), C.c_double()
+    check(lib().itn_bp_update(out.h, ps, pd, len(flat), gp, ng, int(maxiter), -1.0 if tol is None else float(tol),
+                              1 if normalize else 0, C.byref(iters), C.byref(diff)))
+    if info is not None:
+        info["iterations"] = iters.value
+        info["mean_diff"] = diff.value
+    return out
+
+
+def updated_message(bpc, edge, normalize=True):
+    u, v = edge
+    chi = bpc.edge_dim(bpc.graph.eid[(u, v)])
+    out = np.empty((chi, chi), dtype=bpc.dtype, order="F")
+    check(lib().itn_updated_message(bpc.h, int(u), int(v), 1 if normalize else 0, out.ctypes.data_as(C.c_void_p)))
+    return np.ascontiguousarray(out)
+
+
+def update_message(bpc, edge, normalize=True):
+    out = bpc.copy()
+    out.set_message(edge, updated_message(bpc, edge, normalize))
+    return out
+
+
+def message(bpc, edge):
+    return bpc.message(edge)
+
+
+def message_diff(a, b):
+    """message_diff (abstractbeliefpropagationcache.jl:32-36) for two host messages."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return 1.0 - abs(np.vdot(a / np.linalg.norm(a), b / np.linalg.norm(b))) ** 2
+
+
+def message_residuals(bpc, edges=None):
+    """message_diff(updated_message(bpc, e), message(bpc, e)) for every directed edge, on the device."""
+    if edges is None:
+        edges = list(bpc.graph.edges) + [(v, u) for u, v in bpc.graph.edges]
+    a, ps = i32([u for u, _ in edges])
+    b, pd = i32([v for _, v in edges])
+    out = np.zeros(len(edges), dtype=np.float64)
+    check(lib().itn_message_residuals(bpc.h, ps, pd, len(edges), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def environment(bpc, verts):
+    """environment(bpc, verts) for whole-site vertex sets: the incoming messages on the boundary
+    of `verts` (edges inside the set are excluded).  Returns [((u, v), M_{u->v}), ...]."""
+    vs = set(int(v) for v in verts)
+    out = []
+    for v in sorted(vs):
+        for e in bpc.graph.inc[v]:
+            u = bpc.graph.other(e, v)
+            if u not in vs:
+                out.append(((u, v), bpc.message((u, v))))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# scalars, rescale, normalize
+# ---------------------------------------------------------------------------------------------
+
+
+def scalar_factors_quotient(bpc):
+    zv = np.empty(bpc.graph.nv, dtype=bpc.dtype)
+    ze = np.empty(max(bpc.graph.ne, 1), dtype=bpc.dtype)
+    check(lib().itn_region_scalars(bpc.h, zv.ctypes.data_as(C.c_void_p), ze.ctypes.data_as(C.c_void_p)))
+    return zv, ze[: bpc.graph.ne]
+
+
+def vertex_scalars(bpc):
+    return scalar_factors_quotient(bpc)[0]
+
+
+def edge_scalars(bpc):
+    return scalar_factors_quotient(bpc)[1]
+
+
+def region_scalar(bpc, region):
+    if isinstance(region, tuple):
+        return edge_scalars(bpc)[bpc.graph.eid[region]]
+    return vertex_scalars(bpc)[region]
+
+
+def logscalar(bpc):
+    out = (C.c_double * 2)()
+    check(lib().itn_logscalar(bpc.h, out))
+    return complex(out[0], out[1]) if out[1] != 0.0 else out[0]
+
+
+def scalar(bpc):
+    return np.exp(logscalar(bpc))
+
+
+def rescale(bpc, inplace=False):
+    out = bpc if inplace else bpc.copy()
+    check(lib().itn_rescale(out.h))
+    return out
+
+
+def _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx=None):
+    """The `cache!` / `update_cache` / `cache_update_kwargs` protocol (src/expect.jl:21-41)."""
+    if isinstance(psi, BeliefPropagationCache):
+        cache, psi = psi, None
+        update_cache = False if update_cache is None else update_cache
+    if cache is None:
+        cache = BeliefPropagationCache(psi, ctx=ctx, messages="default")
+        update_cache = True if update_cache is None else update_cache
+    elif update_cache is None:
+        update_cache = False
+    if update_cache:
+        cache = update(cache, inplace=True, **(cache_update_kwargs or {}))
+    return cache
+
+
+def normalize(psi, alg="bp", cache=None, update_cache=None, cache_update_kwargs=None, ctx=None):
+    """normalize(psi; alg="bp", cache!, update_cache, cache_update_kwargs) (src/normalize.jl:63-80)."""
+    assert alg == "bp", "only alg=\"bp\" runs on the engine"
+    cache = _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx)
+    check(lib().itn_rescale(cache.h))
+    return cache.tensornetwork()
+
+
+def norm_sqr(psi, cache=None, update_cache=None, cache_update_kwargs=None, ctx=None):
+    cache = _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx)
+    return scalar(cache)
+
+
+# ---------------------------------------------------------------------------------------------
+# observables
+# ---------------------------------------------------------------------------------------------
+
+_OPS = {
+    "Z": np.array([[1, 0], [0, -1]], dtype=np.complex128),
+    "X": np.array([[0, 1], [1, 0]], dtype=np.complex128),
+    "Y": np.array([[0, -1j], [1j, 0]], dtype=np.complex128),
+    "Sz": 0.5 * np.array([[1, 0], [0, -1]], dtype=np.complex128),
+    "Sx": 0.5 * np.array([[0, 1], [1, 0]], dtype=np.complex128),
+    "Id": np.eye(2, dtype=np.complex128),
+}
+
+
+def op(name, dtype=np.complex128):
+    m = _OPS[name]
+    if np.dtype(dtype).kind != "c":
+        assert np.all(m.imag == 0), f"operator {name} is not real"
+        return m.real.astype(dtype)
+    return m.astype(dtype)
+
+
+def expect(psi, operator, vertices=None, alg="bp", cache=None, update_cache=None, cache_update_kwargs=None, ctx=None):
+    """expect(psi, op, vertices; alg="bp", cache!, update_cache, cache_update_kwargs) (src/expect.jl:58-109).
+
+    `operator` is a name ("Sz", "Z", ...) or a d x d matrix O[s_out, s_in]. Returns {vertex: value}."""
+    assert alg == "bp", "only alg=\"bp\" runs on the engine"
+    cache = _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx)
+    if vertices is None:
+        vertices = list(range(cache.graph.nv))
+    o = op(operator, cache.dtype) if isinstance(operator, str) else np.asarray(operator, dtype=cache.dtype)
+    ops = np.stack([np.asfortranarray(o).ravel(order="F")] * len(vertices)) if len(vertices) else np.zeros((0, 4))
+    ops = np.ascontiguousarray(ops, dtype=cache.dtype)
+    out = np.empty(len(vertices), dtype=cache.dtype)
+    _, pv = i32(vertices)
+    check(lib().itn_expect1(cache.h, pv, len(vertices), ops.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    return {int(v): out[i] for i, v in enumerate(vertices)}
+
+
+def rdm2(bpc, edges):
+    """Two-site reduced density matrices from the BP environment (test_belief_propagation.jl:64-91)."""
+    eids = [bpc.graph.eid[tuple(e)] if not np.isscalar(e) else int(e) for e in edges]
+    ds = [bpc.sdims[bpc.graph.edges[e][0]] * bpc.sdims[bpc.graph.edges[e][1]] for e in eids]
+    tot = sum(d * d for d in ds)
+    out = np.empty(tot, dtype=bpc.dtype)
+    _, pe = i32(eids)
+    check(lib().itn_rdm2(bpc.h, pe, len(eids), out.ctypes.data_as(C.c_void_p)))
+    res, off = [], 0
+    for d in ds:
+        res.append(out[off:off + d * d].reshape(d, d, order="F").copy())
+        off += d * d
+    return res
+
+
+def expect2(bpc, edges, op_u, op_v):
+    """<O_u O_v> on edges (u, v) = tr(rho_uv (O_u (x) O_v)); row index of rho = s_u + d_u * s_v."""
+    ou = op(op_u, bpc.dtype) if isinstance(op_u, str) else np.asarray(op_u)
+    ov = op(op_v, bpc.dtype) if isinstance(op_v, str) else np.asarray(op_v)
+    kron = np.kron(ov, ou)
+    return [np.trace(r @ kron) for r in rdm2(bpc, edges)]
+
+
+# ---------------------------------------------------------------------------------------------
+# gates
+# ---------------------------------------------------------------------------------------------
+
+
+def apply(gate, bpc, verts, maxdim=None, cutoff=None, normalize=False, callback=None, inplace=False, msg_mode=0):
+    """apply(o, psi; envs, maxdim, cutoff, normalize, callback) (src/apply.jl:97-146) on a BP cache:
+    the product environment is the cache's current messages.  `verts` = (v,) or (v1, v2)."""
+    verts = tuple(int(v) for v in verts)
+    out = bpc if inplace else bpc.copy()
+    if len(verts) == 1:
+        g = np.asfortranarray(np.asarray(gate, dtype=bpc.dtype))
+        _, pv = i32(verts)
+        check(lib().itn_apply1(out.h, pv, 1, g.ctypes.data_as(C.c_void_p), 1 if normalize else 0))
+        return out
+    if len(verts) == 2:
+        if not bpc.graph.has_edge(*verts):
+            raise ITNError(1, "Vertices where the gates are being applied must be neighbors for now.")
+        info = apply_layer([gate], out, [verts], maxdim=maxdim, cutoff=cutoff, normalize=normalize, msg_mode=msg_mode)
+        if callback is not None:
+            callback(singular_values=info["singular_values"][0], truncation_error=info["truncation_error"][0])
+        return out
+    if len(verts) < 1:
+        raise ITNError(1, "Gate being applied does not share indices with tensor network.")
+    raise ITNError(1, "Gates with more than 2 sites is not supported yet.")
+
+
+def apply_layer(gates, bpc, pairs, maxdim=None, cutoff=None, normalize=False, msg_mode=0):
+    """A vertex-disjoint layer of two-site gates in one batched call (in place).
+    gates[i][s1', s2', s1, s2] acts on pairs[i] = (v1, v2)."""
+    g = bpc.graph
+    eids, packed = [], []
+    for gate, (v1, v2) in zip(gates, pairs):
+        e = g.eid[(v1, v2)]
+        gt = np.asarray(gate, dtype=bpc.dtype)
+        d1, d2 = bpc.sdims[v1], bpc.sdims[v2]
+        gt = gt.reshape(d1, d2, d1, d2)
+        if g.edges[e] != (v1, v2):  # engine orientation is (esrc, edst)
+            gt = gt.transpose(1, 0, 3, 2)
+        eids.append(e)
+        packed.append(np.asfortranarray(gt).ravel(order="F"))
+    n = len(eids)
+    packed = np.ascontiguousarray(np.concatenate(packed)) if n else np.zeros(0, dtype=bpc.dtype)
+    stride = max([bpc.sdims[g.edges[e][0]] * bpc.sdims[g.edges[e][1]] * bpc.edge_dim(e) * 4 for e in eids] + [1])
+    newdim = np.zeros(n, dtype=np.int32)
+    terr = np.zeros(n, dtype=np.float64)
+    sv = np.zeros((n, stride), dtype=np.float64)
+    _, pe = i32(eids)
+    check(lib().itn_apply2(bpc.h, pe, n, packed.ctypes.data_as(C.c_void_p), 0 if maxdim is None else int(maxdim),
+                           -1.0 if cutoff is None else float(cutoff), 1 if normalize else 0, int(msg_mode),
+                           newdim.ctypes.data_as(C.POINTER(C.c_int32)), terr.ctypes.data_as(C.POINTER(C.c_double)),
+                           sv.ctypes.data_as(C.POINTER(C.c_double)), stride))
+    return {"newdim": newdim, "truncation_error": terr,
+            "singular_values": [sv[i, :newdim[i]].copy() for i in range(n)]}
+
+
+def map_eigvals(f, mats, cutoff=None, ctx=None):
+    """map_eigvals(f, A, ...; ishermitian=true, cutoff) (src/apply.jl:21-25) for a batch of Hermitian
+    matrices; f in {"sqrt", "invsqrt", "inv"}."""
+    ctx = ctx or default_context()
+    mats = np.asarray(mats)
+    dtype = np.dtype(np.complex128 if mats.dtype.kind == "c" else np.float64)
+    single = mats.ndim == 2
+    m = mats[None] if single else mats
+    n, chi = m.shape[0], m.shape[1]
+    inp = np.ascontiguousarray(np.stack([np.asfortranarray(x.astype(dtype)).ravel(order="F") for x in m]))
+    out = np.empty_like(inp)
+    fn = {"sqrt": 0, "invsqrt": 1, "inv": 2}[f]
+    check(lib().itn_map_eigvals(ctx.h, _DTYPE_CODE[dtype], fn, chi, n, inp.ctypes.data_as(C.c_void_p),
+                                out.ctypes.data_as(C.c_void_p), -1.0 if cutoff is None else float(cutoff)))
+    res = np.stack([o.reshape(chi, chi, order="F") for o in out])
+    return res[0] if single else res
