@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- BP edge-message updates/s (BASELINE.json metric) on synthetic lattices.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one synchronous BP sweep (every directed edge updated once from the pre-sweep messages,
+abstractbeliefpropagationcache.jl:294-308) over the whole lattice.  Default workload: the configuration
+north_star quotes the target on and that fits one GPU -- 64x64 square-lattice PEPS, chi=16, d=2,
+ComplexF64 (BASELINE.json configs[3]; 16,128 directed messages and 1.034e12 algorithmic flops per sweep).
+
+  value     device-resident: K sweeps in one `update(bpc; maxiter=K)` call, psi and messages already in HBM,
+            timed with CUDA events on the library's stream, max over ranks.
+  e2e       the same metric through the public API with HOST buffers: every step uploads psi from pinned
+            host memory (BeliefPropagationCache(psi)), runs one sweep and downloads every message.
+  roofline  FP64 tensor (DMMA) bound: algorithmic flops of SURVEY.md 8(d) (F_msg = 8*z*d*chi^(z+1)) over
+            the device time of the contraction kernels, against the FP64 peak measured on this pool
+            (profiles/r1_fp64_peak.json, tools/fp64_peak.cu; MEASURED_PEAKS.json has no FP64 entry).
+  cpu_baseline / --impl reference
+            the restated reference algorithm (oracle/itn_oracle.py: NumPy + OpenBLAS, one message at a time,
+            updated_message :225-239) on the box's host cores over a bounded sample of the same workload.
+            The Julia reference itself cannot run here (no Julia runtime).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "itensornetworks.jl_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (dims, chi, dtype, BASELINE.json config index)
+    "grid64x64_chi16_c128": ((64, 64), 16, np.complex128, 3),
+    "grid32x32_chi8_c128": ((32, 32), 8, np.complex128, 1),
+    "grid4x4_chi2_f64": ((4, 4), 2, np.float64, 0),
+    "cubic16_chi6_c128": ((16, 16, 16), 6, np.complex128, 4),
+    "grid16x16_chi16_c128": ((16, 16), 16, np.complex128, None),
+}
+METRIC = "bp_edge_message_updates_per_s"
+UNIT = "updates/s"
+
+
+def algorithmic_flops_per_sweep(graph, chi, d, cplx):
+    """F_msg = c*z*d*chi^(z+1), c = 2 (Float64) / 8 (ComplexF64), summed over directed edges."""
+    c = 8.0 if cplx else 2.0
+    tot = 0.0
+    for v in range(graph.nv):
+        z = graph.degree(v)
+        tot += z * (c * z * d * float(chi) ** (z + 1))
+    return tot
+
+
+def fp64_peak():
+    """FP64 roofline denominator: measured cuBLAS ZGEMM burst on this pool (tools/fp64_peak.cu)."""
+    path = os.path.join(ROOT, "profiles", "r1_fp64_peak.json")
+    try:
+        j = json.load(open(path))
+        return {"burst": float(j["zgemm_tflops_burst"]), "sustained": float(j["zgemm_tflops_sustained"]),
+                "source": "profiles/r1_fp64_peak.json (cuBLAS ZGEMM 4096^3 measured on this pool's B200; "
+                          "MEASURED_PEAKS.json has no FP64 entry)"}
+    except Exception:
+        return {"burst": 37.0, "sustained": 37.0, "source": "fallback: 148 SM x 64 FMA/clk x 1.965 GHz"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, r[5:9]):
+                if val.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_sample(dims, chi, dtype, budget_s, seed=1234):
+    """Time the restated reference algorithm on a bounded sample: a (<=6)^n corner patch of the same
+    lattice with the same chi/dtype, message updates one at a time in the reference's sequential
+    order (only the interior degree mix differs slightly; flops per update are reported)."""
+    from oracle import itn_oracle as O
+    pdims = tuple(min(int(x), 6) for x in dims)
+    g = O.grid_graph(pdims)
+    net = O.random_network(g, chi, dtype=dtype, seed=seed)
+    msgs = O.identity_messages(net)
+    seq = O.default_edge_sequence(g)
+    # prefer full-degree vertices first so the sample matches the bulk of the big lattice
+    zmax = max(g.degree(v) for v in range(g.nv))
+    seq = [e for e in seq if g.degree(e[0]) == zmax] + [e for e in seq if g.degree(e[0]) != zmax]
+    O.updated_message(net, msgs, *seq[0])  # warm-up (BLAS thread pool)
+    n = 0
+    t0 = time.perf_counter()
+    while True:
+        v, w = seq[n % len(seq)]
+        msgs[(v, w)] = O.updated_message(net, msgs, v, w)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 4 * len(seq):
+            break
+    dt = time.perf_counter() - t0
+    return n, dt, f"{n} sequential updated_message calls (vertices of degree {zmax} first) on a {'x'.join(map(str, pdims))} patch, chi={chi}, {np.dtype(dtype).name}"
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dims, chi, dtype, cfg = WORKLOADS[args.workload]
+    for _ in range(args.warmup):
+        cpu_reference_sample(dims, chi, dtype, 0.5)
+    tot_n, tot_t, sample = 0, 0.0, ""
+    per_step_budget = max(1.0, min(20.0, 90.0 / max(args.steps, 1)))
+    for _ in range(args.steps):
+        n, dt, sample = cpu_reference_sample(dims, chi, dtype, per_step_budget)
+        tot_n += n
+        tot_t += dt
+    val = tot_n / tot_t
+    cores = blas_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "c128" if np.dtype(dtype).kind == "c" else "f64",
+        "data": "synthetic", "config": {"workload": args.workload, "baseline_config_index": cfg,
+                                        "note": "restated reference algorithm (NumPy+OpenBLAS oracle port), not ITensorNetworks.jl: no Julia runtime in this image"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f", per step, x{args.steps} steps"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import itn_b200 as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libitn_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dims, chi, dtype, cfg = WORKLOADS[args.workload]
+    cplx = np.dtype(dtype).kind == "c"
+    d = 2
+    graph = E.named_grid(dims)
+    stream = torch.cuda.Stream()
+    ctx = E.Context(local_rank, stream=stream.cuda_stream)
+    if args.path is not None:
+        ctx.set_path(args.path)
+
+    # synthetic psi in pinned host memory: iid N(0,1) / CN(0,1), F-ordered [site, bonds...] per vertex
+    gen = torch.Generator().manual_seed(1234)
+    sizes = [d * chi ** graph.degree(v) for v in range(graph.nv)]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    comps = 2 if cplx else 1
+    host = torch.empty(int(offs[-1]) * comps, dtype=torch.float64).pin_memory()
+    torch.randn(host.shape, generator=gen, out=host)
+    if cplx:
+        host.mul_(2.0 ** -0.5)
+    hnp = host.numpy()
+    tensors = []
+    for v in range(graph.nv):
+        flat = hnp[int(offs[v]) * comps:int(offs[v + 1]) * comps]
+        if cplx:
+            flat = flat.view(np.complex128)
+        tensors.append(np.ndarray((d,) + (chi,) * graph.degree(v), dtype=dtype, buffer=flat, order="F"))
+    psi = E.ITensorNetwork(graph, tensors, dtype)
+    owner = None  # multi-GPU partition: see run_ours_dist
+    seq = E.parallel_edge_sequence(graph)
+    n_updates = 2 * graph.ne
+    flops_sweep = algorithmic_flops_per_sweep(graph, chi, d, cplx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ---------------------------------------------------------------------
+    bpc = E.BeliefPropagationCache(psi, ctx=ctx, owner=owner, dist=(rank, world) if world > 1 else None)
+    E.update(bpc, maxiter=args.warmup, edge_sequence=seq, inplace=True)
+    barrier()
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        E.update(bpc, maxiter=args.steps, edge_sequence=seq, inplace=True)
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    tm = bpc.last_timing()
+    if world > 1:
+        t = torch.tensor([ms, tm["contract_ms"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, tm["contract_ms"] = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    value = n_updates * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, host buffers out, every step ------------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = int(offs[-1]) * comps * 8
+    d2h = n_updates * chi * chi * comps * 8
+    out_host = torch.empty(n_updates * chi * chi * comps, dtype=torch.float64).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        c2 = E.BeliefPropagationCache(psi, ctx=ctx, owner=owner, dist=(rank, world) if world > 1 else None)
+        E.update(c2, maxiter=1, edge_sequence=seq, inplace=True)
+        c2.messages_into(out_host.numpy())
+        c2.close()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_val = n_updates / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak = fp64_peak()
+    # per-GPU roofline of the contraction kernels (message-update DMMA / FMA kernels), live CUDA events inside the library
+    contract_ms_per_sweep = tm["contract_ms"] / max(args.steps, 1)
+    flops_per_gpu = flops_sweep / world
+    achieved = flops_per_gpu / (contract_ms_per_sweep * 1e-3) / 1e12 if contract_ms_per_sweep > 0 else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "c128" if cplx else "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "baseline_config_index": cfg, "lattice": list(dims), "chi": chi, "d": d,
+                   "schedule": "synchronous sweep (one group per directed edge)", "messages_per_sweep": n_updates,
+                   "algorithmic_flops_per_sweep": flops_sweep, "path": tm.get("path", "auto"),
+                   "l2": "inputs larger than L2 (psi %.2f GB per sweep)" % (h2d / 1e9) if h2d > 2e8 else "working set fits L2; no flush (latency-bound config)",
+                   "parallelism": "graph partition x%d, NCCL boundary messages" % world if world > 1 else "single GPU"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak["sustained"], "unit": "TFLOP/s",
+                     "frac": (achieved / peak["sustained"]) if achieved else None, "traffic": None,
+                     "kernel": "message-update contraction kernels (per sweep, per GPU)", "peak_source": peak["source"],
+                     "contract_ms_per_sweep": contract_ms_per_sweep,
+                     "note": "achieved = algorithmic flops (8*z*d*chi^(z+1) per message) / device time; FP64 DMMA peak, not bf16"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "what": "BeliefPropagationCache(psi from pinned host) + update(maxiter=1) + download of all messages"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if args.cpu_baseline:
+        n, dt, sample = cpu_reference_sample(dims, chi, dtype, args.cpu_budget)
+        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="grid64x64_chi16_c128", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", type=int, default=None, help="0 = auto (DMMA fast path), 1 = generic kernels only")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,10 @@ int itn_msg_set_identity(itn_net* net);
 /* set_message! / message (abstractbeliefpropagationcache.jl:173-200). */
 int itn_msg_set(itn_net* net, int src, int dst, const void* host_chi2);
 int itn_msg_get(const itn_net* net, int src, int dst, void* host_chi2);
+/* messages(bpc) in one call: every message stored on this rank, back to back in directed-id order
+ * (2e = esrc->edst, 2e+1 = edst->esrc), each chi x chi column-major; `bytes` = capacity of `host`
+ * (may be pinned memory: one device->host copy).  Unset / remote messages are skipped. */
+int itn_msg_get_all(const itn_net* net, void* host, int64_t bytes);
 
 /* ---- belief propagation ------------------------------------------------------------------ */
 

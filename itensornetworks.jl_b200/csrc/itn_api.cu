@@ -732,6 +732,59 @@ extern "C" int itn_msg_get(const itn_net* net_, int src, int dst, void* host) {
   API_END
 }
 
+namespace {
+struct PackJob {
+  const double* src;  // planar
+  long long n;        // elements
+  long long off;      // element offset in the packed output
+};
+// planar device arrays -> one packed buffer; interleave = 1: (re, im) pairs (host layout), 0: planar
+template <bool C>
+__global__ void k_pack(const PackJob* __restrict__ jobs, double* __restrict__ out, int interleave) {
+  PackJob J = jobs[blockIdx.x];
+  const int P = C ? 2 : 1;
+  for (long long i = threadIdx.x; i < J.n; i += blockDim.x) {
+    if (C) {
+      if (interleave) {
+        out[2 * (J.off + i)] = J.src[i];
+        out[2 * (J.off + i) + 1] = J.src[J.n + i];
+      } else {
+        out[P * J.off + i] = J.src[i];
+        out[P * J.off + J.n + i] = J.src[J.n + i];
+      }
+    } else {
+      out[J.off + i] = J.src[i];
+    }
+  }
+}
+}  // namespace
+
+extern "C" int itn_msg_get_all(const itn_net* net_, void* host, int64_t bytes) {
+  API_BEGIN
+  itn_net* net = const_cast<itn_net*>(net_);
+  ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  std::vector<PackJob> jobs;
+  long long off = 0;
+  for (size_t d = 0; d < net->M.size(); ++d)
+    if (net->M[d].p) {
+      jobs.push_back({net->M[d].p, net->M[d].n, off});
+      off += net->M[d].n;
+    }
+  const size_t need = (size_t)off * net->planes() * sizeof(double);
+  ITN_REQUIRE((size_t)bytes >= need, ITN_ESHAPE, "host buffer too small for all messages");
+  if (jobs.empty()) return ITN_OK;
+  DevBuf jb(ctx, jobs.size() * sizeof(PackJob)), stage(ctx, need);
+  const PackJob* dj = itn_upload(ctx, jobs, jb);
+  if (net->cplx) k_pack<true><<<(unsigned)jobs.size(), 128, 0, ctx->stream>>>(dj, stage.as<double>(), 1);
+  else k_pack<false><<<(unsigned)jobs.size(), 128, 0, ctx->stream>>>(dj, stage.as<double>(), 1);
+  ITN_LAUNCH_CHECK(ctx);
+  CUDA_CHECK(cudaMemcpyAsync(host, stage.p, need, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
 // ------------------------------------------------------------------------------------------------
 // belief propagation driver
 // ------------------------------------------------------------------------------------------------
@@ -866,9 +919,18 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   Staged staged(net, sjobs);
   DevBuf diffs(ctx, (size_t)nseq * sizeof(double));
   DevBuf dsum(ctx, sizeof(double));
-  std::vector<int> all_dids(nseq);
-  for (int i = 0; i < nseq; ++i) all_dids[i] = sjobs[i].did;
-  const bool fast = sync_mode && ctx->path_mode == 0 && itn_fast_bp_supported(net, all_dids);
+  std::vector<int> all_dids(nseq), all_src(nseq);
+  for (int i = 0; i < nseq; ++i) {
+    all_dids[i] = sjobs[i].did;
+    all_src[i] = sjobs[i].v;
+  }
+  // synchronous sweeps: vertices that qualify go to the DMMA kernels, the rest to the generic kernels
+  std::vector<char> handled;
+  const int nfast = sync_mode ? itn_fast_bp_plan(net, all_dids, all_src, handled) : 0;
+  std::vector<JobSpec> slow_specs;
+  if (nfast > 0)
+    for (int i = 0; i < nseq; ++i)
+      if (!handled[i]) slow_specs.push_back({sjobs[i].v, 1u << (sjobs[i].k + 1), staged.ptr[i]});
 
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
@@ -876,12 +938,27 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   CUDA_CHECK(cudaEventRecord(ev0, ctx->stream));
   int done = 0;
   double mean = NAN;
+  std::vector<cudaEvent_t> cev;  // event pairs around the contraction kernels
   try {
     for (int it = 0; it < maxiter; ++it) {
       for (size_t l = 0; l + 1 < lvl_ptr.size(); ++l) {
         const size_t lo = lvl_ptr[l], hi = lvl_ptr[l + 1];
-        if (fast) itn_fast_bp_sweep(net, all_dids, staged.ptr.data());
-        else compute_messages(net, sjobs, lo, hi, staged.ptr);
+        const bool timed = cev.size() < 4096;
+        if (timed) {
+          cudaEvent_t a, b;
+          CUDA_CHECK(cudaEventCreate(&a));
+          cev.push_back(a);
+          CUDA_CHECK(cudaEventCreate(&b));
+          cev.push_back(b);
+          CUDA_CHECK(cudaEventRecord(a, ctx->stream));
+        }
+        if (nfast > 0) {
+          itn_fast_bp_sweep(net, all_dids, all_src, handled, staged.ptr.data());
+          itn_run_vertex_jobs(net, slow_specs);
+        } else {
+          compute_messages(net, sjobs, lo, hi, staged.ptr);
+        }
+        if (timed) CUDA_CHECK(cudaEventRecord(cev.back(), ctx->stream));
         std::vector<CommitJob> cj(hi - lo);
         for (size_t i = lo; i < hi; ++i) {
           int chi = net->edim[sjobs[i].did / 2];
@@ -905,13 +982,22 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     net->last_total_ms = ms;
+    double cms = 0;
+    for (size_t i = 0; i + 1 < cev.size(); i += 2) {
+      float t = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&t, cev[i], cev[i + 1]));
+      cms += t;
+    }
+    net->last_contract_ms = cms;
   } catch (...) {
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    for (auto e : cev) cudaEventDestroy(e);
     throw;
   }
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
+  for (auto e : cev) cudaEventDestroy(e);
   if (iters) *iters = done;
   if (last_mean_diff) *last_mean_diff = mean;
   API_END

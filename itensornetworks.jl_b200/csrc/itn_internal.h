@@ -148,9 +148,12 @@ void itn_run_commit(itn_net* net, const std::vector<CommitJob>& jobs, int normal
 int itn_open_extent(const itn_net* net, int v, uint32_t open_mask);
 
 // ---- fast path (itn_fast.cu) ----
-// Returns true if it handled the whole synchronous sweep set (all edges), false to fall back.
-bool itn_fast_bp_supported(itn_net* net, const std::vector<int>& dids);
-void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, double** staged_out);
+// Plans a synchronous sweep: handled[i] = 1 for the message jobs (directed id dids[i], source vertex
+// srcv[i]) that the DMMA kernels compute; returns their number.  The sweep writes the un-normalised
+// new messages of those jobs to staged[i].
+int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled);
+void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
+                       const std::vector<char>& handled, double* const* staged);
 void itn_fast_release(itn_net* net);
 
 // ---- small linear algebra (itn_linalg.cu) ----

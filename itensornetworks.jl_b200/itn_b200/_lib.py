@@ -43,6 +43,7 @@ _SIGS = {
     "itn_msg_set_identity": (C.c_int, [_vp]),
     "itn_msg_set": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "itn_msg_get": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "itn_msg_get_all": (C.c_int, [_vp, _vp, C.c_int64]),
     "itn_bp_update": (C.c_int, [_vp, _i32p, _i32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_double, C.c_int, _i32p, _dp]),
     "itn_updated_message": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "itn_message_residuals": (C.c_int, [_vp, _i32p, _i32p, C.c_int, _dp]),

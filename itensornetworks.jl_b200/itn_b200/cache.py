@@ -70,26 +70,32 @@ def default_context(device=0):
 class BeliefPropagationCache:
     """BP cache of <psi|psi> with the default one-site partition; state lives on the device."""
 
-    def __init__(self, psi: ITensorNetwork = None, ctx: Context = None, messages="identity", _handle=None,
-                 _like=None):
+    def __init__(self, psi: ITensorNetwork = None, ctx: Context = None, messages="identity", owner=None, dist=None,
+                 _handle=None, _like=None):
         if _handle is not None:  # clone
             self.ctx, self.graph, self.dtype, self.h = _like.ctx, _like.graph, _like.dtype, _handle
             self.sdims = list(_like.sdims)
+            self.owner, self.rank = _like.owner, _like.rank
             return
         self.ctx = ctx or default_context()
         self.graph = psi.graph
         self.dtype = psi.dtype
         g = self.graph
         self.sdims = [t.shape[0] for t in psi.tensors]
+        # multi-GPU: owner[v] = rank that stores vertex v; dist = (rank, nranks) of this process
+        self.owner = None if owner is None else [int(x) for x in owner]
+        self.rank = 0 if dist is None else int(dist[0])
         a0, p0 = i32([u for u, _ in g.edges])
         a1, p1 = i32([v for _, v in g.edges])
         a2, p2 = i32([psi.edge_dim(e) for e in range(g.ne)])
         a3, p3 = i32(self.sdims)
         h = C.c_void_p()
-        check(lib().itn_net_create(self.ctx.h, _DTYPE_CODE[self.dtype], g.nv, g.ne, p0, p1, p2, p3, None, C.byref(h)))
+        a4, p4 = i32(self.owner) if self.owner is not None else (None, None)
+        check(lib().itn_net_create(self.ctx.h, _DTYPE_CODE[self.dtype], g.nv, g.ne, p0, p1, p2, p3, p4, C.byref(h)))
         self.h = h
         for v in range(g.nv):
-            self.set_factor(v, psi.tensors[v])
+            if self.owner is None or self.owner[v] == self.rank:
+                self.set_factor(v, psi.tensors[v])
         # initialize_cache (src/initialize_cache.jl:14-29): identity messages on loopy graphs, none on trees
         if messages == "identity" or (messages == "default" and not g.is_tree()):
             check(lib().itn_msg_set_identity(self.h))
@@ -155,6 +161,17 @@ class BeliefPropagationCache:
         u, v = edge
         f = np.asfortranarray(np.asarray(m, dtype=self.dtype))
         check(lib().itn_msg_set(self.h, int(u), int(v), f.ctypes.data_as(C.c_void_p)))
+
+    def last_timing(self):
+        """Device time of the last update() in ms (CUDA events on the library stream) and the share of the
+        contraction kernels."""
+        a, b = C.c_double(), C.c_double()
+        check(lib().itn_bp_last_timing(self.h, C.byref(a), C.byref(b)))
+        return {"total_ms": a.value, "contract_ms": b.value}
+
+    def messages_into(self, out):
+        """Download every locally stored message into one host array (directed id order 2e, 2e+1), interleaved complex."""
+        check(lib().itn_msg_get_all(self.h, out.ctypes.data_as(C.c_void_p), out.nbytes))
 
     def messages(self):
         out = {}

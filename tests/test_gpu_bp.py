@@ -195,3 +195,31 @@ def test_midsize_parity(ctx):
     msgs, _, _ = O.bp_update(net, O.identity_messages(net), seq=seq, groups=O.synchronous_groups(seq), maxiter=4)
     bpc = E.update(E.BeliefPropagationCache(psi, ctx=ctx), maxiter=4, edge_sequence=[[e] for e in seq])
     assert_messages_close(bpc, msgs, TOL)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dmma_fast_path_chi16(dtype):
+    # degree-4, chi=16 vertices run on the DMMA kernels (itn_fast.cu); boundary vertices on the generic ones.
+    g = O.grid_graph((5, 5))
+    net, psi = make_pair(g, 16, dtype)
+    seq = O.parallel_edge_sequence(g)
+    msgs, _, diff_o = O.bp_update(net, O.identity_messages(net), seq=seq, groups=O.synchronous_groups(seq), maxiter=3,
+                                  tol=0.0)
+    c = E.Context(0)
+    bpc = E.BeliefPropagationCache(psi, ctx=c)
+    l0 = c.launch_count()
+    info = {}
+    E.update(bpc, maxiter=3, tol=0.0, edge_sequence=[[e] for e in seq], inplace=True, info=info)
+    assert_messages_close(bpc, msgs, TOL)
+    assert abs(info["mean_diff"] - diff_o) < 1e-12
+    # the generic kernels give the same answer (second opinion on the device)
+    c2 = E.Context(0)
+    c2.set_path(1)
+    b2 = E.BeliefPropagationCache(psi, ctx=c2)
+    E.update(b2, maxiter=3, edge_sequence=[[e] for e in seq], inplace=True)
+    for k in msgs:
+        assert rel_err(bpc.message(k), b2.message(k)) < 1e-12
+    # observables downstream of the fast path
+    ez = E.expect(bpc, "Z")
+    for v in (0, 6, 12):
+        assert abs(ez[v] - O.expect1(net, msgs, v, O.PAULI_Z)) < TOL
