@@ -209,11 +209,18 @@ def run_ours(args):
     ctx = E.Context(local_rank, stream=stream.cuda_stream)
     if args.path is not None:
         ctx.set_path(args.path)
+    if world > 1:
+        E.init_distributed(ctx, rank, world)  # the library's own NCCL communicator (boundary messages)
+    owner = E.partition_vertices(graph, world) if world > 1 else None
 
     # synthetic psi in pinned host memory: iid N(0,1) / CN(0,1), F-ordered [site, bonds...] per vertex
     gen = torch.Generator().manual_seed(1234)
-    sizes = [d * chi ** graph.degree(v) for v in range(graph.nv)]
+    # (multi-GPU: a rank only materialises the tensors of the vertices it owns; the others alias one scratch block)
+    mine = [owner is None or owner[v] == rank for v in range(graph.nv)]
+    full = [d * chi ** graph.degree(v) for v in range(graph.nv)]
+    sizes = [full[v] if mine[v] else 0 for v in range(graph.nv)]
     offs = np.concatenate([[0], np.cumsum(sizes)])
+    scratch = np.zeros(max(full) * (2 if cplx else 1))
     comps = 2 if cplx else 1
     host = torch.empty(int(offs[-1]) * comps, dtype=torch.float64).pin_memory()
     torch.randn(host.shape, generator=gen, out=host)
@@ -222,12 +229,11 @@ def run_ours(args):
     hnp = host.numpy()
     tensors = []
     for v in range(graph.nv):
-        flat = hnp[int(offs[v]) * comps:int(offs[v + 1]) * comps]
+        flat = hnp[int(offs[v]) * comps:int(offs[v + 1]) * comps] if mine[v] else scratch[:full[v] * comps]
         if cplx:
             flat = flat.view(np.complex128)
         tensors.append(np.ndarray((d,) + (chi,) * graph.degree(v), dtype=dtype, buffer=flat, order="F"))
     psi = E.ITensorNetwork(graph, tensors, dtype)
-    owner = None  # multi-GPU partition: see run_ours_dist
     seq = E.parallel_edge_sequence(graph)
     n_updates = 2 * graph.ne
     flops_sweep = algorithmic_flops_per_sweep(graph, chi, d, cplx)
@@ -267,8 +273,10 @@ def run_ours(args):
     # ---- end-to-end arm: host buffers in, host buffers out, every step ------------------------------
     e2e_steps = max(1, min(args.steps, 3))
     h2d = int(offs[-1]) * comps * 8
-    d2h = n_updates * chi * chi * comps * 8
-    out_host = torch.empty(n_updates * chi * chi * comps, dtype=torch.float64).pin_memory()
+    n_stored = n_updates if owner is None else sum(
+        2 for (u, v) in graph.edges if owner[u] == rank or owner[v] == rank)
+    d2h = n_stored * chi * chi * comps * 8
+    out_host = torch.empty(n_stored * chi * chi * comps, dtype=torch.float64).pin_memory()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -282,6 +290,9 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
+        hb = torch.tensor([h2d, d2h], device="cuda", dtype=torch.int64)
+        dist.all_reduce(hb)
+        h2d, d2h = int(hb[0]), int(hb[1])
     e2e_val = n_updates / e2e_s
 
     if rank != 0:

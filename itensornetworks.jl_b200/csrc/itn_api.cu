@@ -144,6 +144,7 @@ __device__ __forceinline__ double wsum(double v) {
 template <bool C>
 __global__ void k_edge_scalar(const EdgePair* __restrict__ ep, double* __restrict__ out /*2 per edge*/) {
   EdgePair E = ep[blockIdx.x];
+  if (!E.m1) return;
   double sr = 0, si = 0;
   for (int i = threadIdx.x; i < E.n2; i += 32) {
     double ar = E.m1[i], br = E.m2[i];
@@ -238,6 +239,10 @@ __global__ void k_expect_finalize(const ExpectJob* __restrict__ jobs, int n, dou
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   ExpectJob J = jobs[j];
+  if (!J.rho) {
+    out[2 * j] = out[2 * j + 1] = 0.0;
+    return;
+  }
   const int d = J.d, d2 = d * d;
   double nr = 0, ni = 0, tr = 0, ti = 0;
   for (int s = 0; s < d; ++s) {
@@ -414,9 +419,21 @@ extern "C" int itn_ctx_create(int device, void* stream, itn_ctx** out) {
   API_END
 }
 
+static void ctx_destroy_now(itn_ctx* ctx);
+
 extern "C" int itn_ctx_destroy(itn_ctx* ctx) {
   API_BEGIN
   if (!ctx) return ITN_OK;
+  if (ctx->nets_alive > 0) {
+    // finalizers run in any order (Julia GC, Python cycles): the context goes away with its last network
+    ctx->destroy_pending = true;
+    return ITN_OK;
+  }
+  ctx_destroy_now(ctx);
+  API_END
+}
+
+static void ctx_destroy_now(itn_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->nccl && ctx->nccl_lib) {
@@ -426,7 +443,6 @@ extern "C" int itn_ctx_destroy(itn_ctx* ctx) {
   }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
-  API_END
 }
 
 extern "C" int itn_ctx_sync(itn_ctx* ctx) {
@@ -455,6 +471,12 @@ extern "C" int itn_ctx_set_path(itn_ctx* ctx, int mode) {
 // ------------------------------------------------------------------------------------------------
 // network
 // ------------------------------------------------------------------------------------------------
+// a rank stores the messages on every edge that touches one of its vertices
+static bool msg_stored(const itn_net* net, int did) {
+  const int e = did / 2;
+  return itn_is_local(net, net->esrc[e]) || itn_is_local(net, net->edst[e]);
+}
+
 static void alloc_message(itn_net* net, int did) {
   int e = did / 2;
   long long n2 = (long long)net->edim[e] * net->edim[e];
@@ -468,9 +490,11 @@ static void set_identity_messages(itn_net* net, const std::vector<int>& dids) {
   if (dids.empty()) return;
   std::vector<IdJob> jobs;
   for (int did : dids) {
+    if (!msg_stored(net, did)) continue;
     alloc_message(net, did);
     jobs.push_back({net->M[did].p, net->edim[did / 2]});
   }
+  if (jobs.empty()) return;
   DevBuf b(net->ctx, jobs.size() * sizeof(IdJob));
   const IdJob* d = itn_upload(net->ctx, jobs, b);
   if (net->cplx) k_identity<true><<<(unsigned)jobs.size(), 128, 0, net->ctx->stream>>>(d);
@@ -498,6 +522,9 @@ extern "C" int itn_net_create(itn_ctx* ctx, int dtype, int nv, int ne, const int
   net->sdim.assign(sdim, sdim + nv);
   net->owner.assign(nv, 0);
   if (owner) net->owner.assign(owner, owner + nv);
+  for (int v = 0; v < nv; ++v)
+    ITN_REQUIRE(net->owner[v] >= 0 && net->owner[v] < ctx->nranks, ITN_EINVAL,
+                "owner[v] must be a rank of the context (call itn_ctx_init_dist before itn_net_create)");
   net->inc.assign(nv, {});
   for (int v = 0; v < nv; ++v) ITN_REQUIRE(sdim[v] >= 1 && sdim[v] <= 8, ITN_EUNSUPPORTED, "site dimension must be in 1..8");
   for (int e = 0; e < ne; ++e) {
@@ -514,6 +541,7 @@ extern "C" int itn_net_create(itn_ctx* ctx, int dtype, int nv, int ne, const int
     ITN_REQUIRE((int)net->inc[v].size() + 1 <= ITN_MAX_MODES, ITN_EUNSUPPORTED, "vertex degree above 9 is not supported");
   net->T.assign(nv, DevTensor());
   net->M.assign(2 * (size_t)ne, DevTensor());
+  ctx->nets_alive++;
   *out = net.release();
   API_END
 }
@@ -524,6 +552,7 @@ static void free_net_storage(itn_net* net) {
   for (auto& m : net->M)
     if (m.p) itn_dev_free(net->ctx, m.p), m.p = nullptr;
   itn_fast_release(net);
+  itn_dist_release(net);
 }
 
 extern "C" int itn_net_destroy(itn_net* net) {
@@ -531,7 +560,9 @@ extern "C" int itn_net_destroy(itn_net* net) {
   if (!net) return ITN_OK;
   cudaSetDevice(net->ctx->device);
   free_net_storage(net);
+  itn_ctx* ctx = net->ctx;
   delete net;
+  if (--ctx->nets_alive == 0 && ctx->destroy_pending) ctx_destroy_now(ctx);
   API_END
 }
 
@@ -541,6 +572,7 @@ extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
   set_device(src->ctx);
   std::unique_ptr<itn_net> net(new itn_net(*src));
   net->fast = nullptr;
+  net->dist = nullptr;
   for (auto& t : net->T) t.p = nullptr;
   for (auto& m : net->M) m.p = nullptr;
   const int P = src->planes();
@@ -556,6 +588,7 @@ extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
       net->M[d].p = (double*)itn_dev_alloc(src->ctx, b);
       CUDA_CHECK(cudaMemcpyAsync(net->M[d].p, src->M[d].p, b, cudaMemcpyDeviceToDevice, src->ctx->stream));
     }
+  src->ctx->nets_alive++;
   *out = net.release();
   API_END
 }
@@ -623,6 +656,7 @@ extern "C" int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd,
   API_BEGIN
   ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
   ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "vertex out of range");
+  if (!itn_is_local(net, v)) return ITN_OK;  // another rank stores this vertex
   set_device(net->ctx);
   itn_ctx* ctx = net->ctx;
   Marshal m = make_marshal(net, v, nd, axis_edge);
@@ -688,6 +722,7 @@ extern "C" int itn_msg_set(itn_net* net, int src, int dst, const void* host) {
   ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
   int did = net->did(src, dst);
   ITN_REQUIRE(did >= 0, ITN_EINVAL, "(src, dst) is not an edge of the network");
+  if (!msg_stored(net, did)) return ITN_OK;  // neither endpoint lives on this rank
   set_device(net->ctx);
   itn_ctx* ctx = net->ctx;
   alloc_message(net, did);
@@ -862,6 +897,20 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   }
   std::vector<MsgJob> jobs = make_msg_jobs(net, seq_src, seq_dst, nseq);
   const bool want_diff = tol >= 0.0;
+  // multi-GPU: every rank receives the same full sequence and keeps the updates whose source vertex it owns;
+  // the messages crossing a cut are exchanged once per sweep (itn_dist.cu)
+  const int nseq_global = nseq;
+  std::vector<int> global_dids(nseq);
+  for (int i = 0; i < nseq; ++i) global_dids[i] = jobs[i].did;
+  if (ctx->nranks > 1) {
+    ITN_REQUIRE(sync_mode, ITN_EUNSUPPORTED,
+                "the sequential (Gauss-Seidel) schedule does not shard: use the grouped/parallel schedule on a partitioned network");
+    std::vector<MsgJob> loc;
+    for (auto& J : jobs)
+      if (itn_is_local(net, J.v)) loc.push_back(J);
+    jobs.swap(loc);
+    nseq = (int)jobs.size();
+  }
 
   // availability simulation + dependency levels
   std::vector<char> valid(net->M.size());
@@ -877,8 +926,8 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
         int m = net->msg_into(J.v, e);
         ITN_REQUIRE(valid[m], ITN_EINVAL,
                     "message into vertex " + std::to_string(J.v) + " on edge " + std::to_string(e) +
-                        " does not exist when updating " + std::to_string(seq_src[i]) + " -> " +
-                        std::to_string(seq_dst[i]) + " (initialise messages or use the forest-cover sequence)");
+                        " does not exist when updating " + std::to_string(J.v) + " -> " +
+                        std::to_string(net->other(J.did / 2, J.v)) + " (initialise messages or use the forest-cover sequence)");
         if (!sync_mode) lv = std::max(lv, lastw[m] + 1);
       }
       if (want_diff)
@@ -917,7 +966,7 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   lvl_ptr.push_back(nseq);
 
   Staged staged(net, sjobs);
-  DevBuf diffs(ctx, (size_t)nseq * sizeof(double));
+  DevBuf diffs(ctx, (size_t)std::max(nseq, 1) * sizeof(double));
   DevBuf dsum(ctx, sizeof(double));
   std::vector<int> all_dids(nseq), all_src(nseq);
   for (int i = 0; i < nseq; ++i) {
@@ -966,14 +1015,16 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
         }
         itn_run_commit(net, cj, normalize, want_diff ? diffs.as<double>() + lo : nullptr);
       }
+      if (ctx->nranks > 1) itn_dist_exchange(net, global_dids);
       ++done;
       if (want_diff) {
         k_sum_fixed<<<1, 256, 0, ctx->stream>>>(diffs.as<double>(), nseq, dsum.as<double>());
         ITN_LAUNCH_CHECK(ctx);
+        itn_dist_allreduce_sum(ctx, dsum.as<double>(), 1);
         double s = 0;
         CUDA_CHECK(cudaMemcpyAsync(&s, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        mean = s / nseq;
+        mean = s / nseq_global;
         if (mean <= tol) break;
       }
     }
@@ -1058,23 +1109,31 @@ extern "C" int itn_message_residuals(itn_net* net, const int32_t* src, const int
 // scalars / rescale
 // ------------------------------------------------------------------------------------------------
 static void require_all_set(itn_net* net) {
-  for (int v = 0; v < net->nv; ++v) ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor of vertex " + std::to_string(v) + " is not set");
-  for (size_t d = 0; d < net->M.size(); ++d) ITN_REQUIRE(net->M[d].p, ITN_EINVAL, "a message is not set (run itn_bp_update first)");
+  for (int v = 0; v < net->nv; ++v)
+    if (itn_is_local(net, v)) ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor of vertex " + std::to_string(v) + " is not set");
+  for (size_t d = 0; d < net->M.size(); ++d)
+    if (msg_stored(net, (int)d)) ITN_REQUIRE(net->M[d].p, ITN_EINVAL, "a message is not set (run itn_bp_update first)");
 }
 
 // d_zv: 2 doubles per vertex {re, im}
 static void vertex_scalars_dev(itn_net* net, double* d_zv) {
-  std::vector<JobSpec> specs(net->nv);
+  std::vector<JobSpec> specs;
   // planar No=1 output: out[0] = re, out[1] = im for complex; real writes out[0] only
   CUDA_CHECK(cudaMemsetAsync(d_zv, 0, (size_t)net->nv * 2 * sizeof(double), net->ctx->stream));
-  for (int v = 0; v < net->nv; ++v) specs[v] = {v, 0u, d_zv + 2 * v};
+  for (int v = 0; v < net->nv; ++v)
+    if (itn_is_local(net, v)) specs.push_back({v, 0u, d_zv + 2 * v});
   itn_run_vertex_jobs(net, specs);
 }
 
 static void edge_scalars_dev(itn_net* net, double* d_ze) {
   if (net->ne == 0) return;
+  // each edge scalar is computed by the rank owning esrc (zero elsewhere; summed by the all-reduce)
+  CUDA_CHECK(cudaMemsetAsync(d_ze, 0, (size_t)net->ne * 2 * sizeof(double), net->ctx->stream));
   std::vector<EdgePair> ep(net->ne);
-  for (int e = 0; e < net->ne; ++e) ep[e] = {net->M[2 * e].p, net->M[2 * e + 1].p, (int)net->M[2 * e].n};
+  for (int e = 0; e < net->ne; ++e) {
+    if (itn_is_local(net, net->esrc[e])) ep[e] = {net->M[2 * e].p, net->M[2 * e + 1].p, (int)net->M[2 * e].n};
+    else ep[e] = {nullptr, nullptr, 0};
+  }
   DevBuf b(net->ctx, ep.size() * sizeof(EdgePair));
   const EdgePair* d = itn_upload(net->ctx, ep, b);
   if (net->cplx) k_edge_scalar<true><<<net->ne, 32, 0, net->ctx->stream>>>(d, d_ze);
@@ -1087,6 +1146,7 @@ static void region_scalars_host(itn_net* net, std::vector<std::complex<double>>&
   DevBuf dz(net->ctx, (size_t)(net->nv + net->ne) * 2 * sizeof(double));
   vertex_scalars_dev(net, dz.as<double>());
   edge_scalars_dev(net, dz.as<double>() + 2 * (size_t)net->nv);
+  itn_dist_allreduce_sum(net->ctx, dz.as<double>(), (net->nv + net->ne) * 2);
   std::vector<double> h((size_t)(net->nv + net->ne) * 2);
   CUDA_CHECK(cudaMemcpyAsync(h.data(), dz.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, net->ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
@@ -1139,28 +1199,35 @@ extern "C" int itn_rescale(itn_net* net) {
   set_device(net->ctx);
   itn_ctx* ctx = net->ctx;
   require_all_set(net);
-  if (net->ne > 0) {
-    std::vector<EdgePair> ep(net->ne);
-    for (int e = 0; e < net->ne; ++e) ep[e] = {net->M[2 * e].p, net->M[2 * e + 1].p, (int)net->M[2 * e].n};
-    DevBuf b(ctx, ep.size() * sizeof(EdgePair));
-    const EdgePair* d = itn_upload(ctx, ep, b);
-    if (net->cplx) k_rescale_msgs<true><<<net->ne, 32, 0, ctx->stream>>>(d);
-    else k_rescale_msgs<false><<<net->ne, 32, 0, ctx->stream>>>(d);
-    ITN_LAUNCH_CHECK(ctx);
+  {
+    // every rank rescales the message pairs it stores (both owners of a cut edge do the same arithmetic)
+    std::vector<EdgePair> ep;
+    for (int e = 0; e < net->ne; ++e)
+      if (msg_stored(net, 2 * e)) ep.push_back({net->M[2 * e].p, net->M[2 * e + 1].p, (int)net->M[2 * e].n});
+    if (!ep.empty()) {
+      DevBuf b(ctx, ep.size() * sizeof(EdgePair));
+      const EdgePair* d = itn_upload(ctx, ep, b);
+      if (net->cplx) k_rescale_msgs<true><<<(unsigned)ep.size(), 32, 0, ctx->stream>>>(d);
+      else k_rescale_msgs<false><<<(unsigned)ep.size(), 32, 0, ctx->stream>>>(d);
+      ITN_LAUNCH_CHECK(ctx);
+    }
   }
   DevBuf dz(ctx, (size_t)net->nv * 2 * sizeof(double));
   vertex_scalars_dev(net, dz.as<double>());
-  std::vector<ScaleJob> sj(net->nv);
+  std::vector<ScaleJob> sj;
   long long maxn = 0;
   for (int v = 0; v < net->nv; ++v) {
-    sj[v] = {net->T[v].p, net->T[v].n * net->planes(), dz.as<double>() + 2 * v, 1.0};
-    maxn = std::max<long long>(maxn, sj[v].n);
+    if (!itn_is_local(net, v)) continue;
+    sj.push_back({net->T[v].p, net->T[v].n * net->planes(), dz.as<double>() + 2 * v, 1.0});
+    maxn = std::max<long long>(maxn, sj.back().n);
   }
-  DevBuf sb(ctx, sj.size() * sizeof(ScaleJob));
-  const ScaleJob* dj = itn_upload(ctx, sj, sb);
-  unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + 1023) / 1024, 32));
-  k_scale<<<dim3(net->nv, gy), 256, 0, ctx->stream>>>(dj);
-  ITN_LAUNCH_CHECK(ctx);
+  if (!sj.empty()) {
+    DevBuf sb(ctx, sj.size() * sizeof(ScaleJob));
+    const ScaleJob* dj = itn_upload(ctx, sj, sb);
+    unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + 1023) / 1024, 32));
+    k_scale<<<dim3((unsigned)sj.size(), gy), 256, 0, ctx->stream>>>(dj);
+    ITN_LAUNCH_CHECK(ctx);
+  }
   net->topo_version++;
   API_END
 }
@@ -1202,17 +1269,21 @@ extern "C" int itn_expect1(itn_net* net, const int32_t* verts, int n, const void
   }
   DevBuf dops(ctx, op_elems * P * sizeof(double)), drho(ctx, rho_elems * P * sizeof(double));
   DevBuf dout(ctx, (size_t)n * 2 * sizeof(double));
-  std::vector<JobSpec> specs(n);
+  std::vector<JobSpec> specs;
   std::vector<ExpectJob> ej(n);
   size_t off = 0, hoff = 0;
   for (int i = 0; i < n; ++i) {
     int v = verts[i], d = net->sdim[v];
-    for (int e : net->inc[v]) ITN_REQUIRE(net->M[net->msg_into(v, e)].p, ITN_EINVAL, "an incoming message is not set");
     double* rho = drho.as<double>() + off * P;
     double* op = dops.as<double>() + off * P;
     upload_planar(net, (const char*)ops + hoff * P * sizeof(double), (long long)d * d, 1, op);
-    specs[i] = {v, 1u, rho};
-    ej[i] = {rho, op, d};
+    if (itn_is_local(net, v)) {
+      for (int e : net->inc[v]) ITN_REQUIRE(net->M[net->msg_into(v, e)].p, ITN_EINVAL, "an incoming message is not set");
+      specs.push_back({v, 1u, rho});
+      ej[i] = {rho, op, d};
+    } else {
+      ej[i] = {nullptr, op, d};  // computed by the owning rank, summed in by the all-reduce below
+    }
     off += (size_t)d * d;
     hoff += (size_t)d * d;
   }
@@ -1222,6 +1293,7 @@ extern "C" int itn_expect1(itn_net* net, const int32_t* verts, int n, const void
   if (net->cplx) k_expect_finalize<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(dj, n, dout.as<double>());
   else k_expect_finalize<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(dj, n, dout.as<double>());
   ITN_LAUNCH_CHECK(ctx);
+  itn_dist_allreduce_sum(ctx, dout.as<double>(), n * 2);
   std::vector<double> h((size_t)n * 2);
   CUDA_CHECK(cudaMemcpyAsync(h.data(), dout.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1243,6 +1315,8 @@ extern "C" int itn_rdm2(itn_net* net, const int32_t* eids, int n, void* out) {
     int e = eids[i];
     ITN_REQUIRE(e >= 0 && e < net->ne, ITN_EINVAL, "edge id out of range");
     int u = net->esrc[e], v = net->edst[e];
+    ITN_REQUIRE(itn_is_local(net, u) && itn_is_local(net, v), ITN_EUNSUPPORTED,
+                "rdm2 on an edge that crosses a partition cut is not supported yet");
     long long nu = (long long)net->sdim[u] * net->edim[e], nv_ = (long long)net->sdim[v] * net->edim[e];
     env_elems += (size_t)(nu * nu + nv_ * nv_);
     int D = net->sdim[u] * net->sdim[v];
@@ -1313,6 +1387,7 @@ extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void*
     ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "Gate being applied does not share indices with tensor network.");
     ITN_REQUIRE(!seen[v], ITN_EINVAL, "a batch of one-site gates must act on distinct vertices");
     seen[v] = 1;
+    ITN_REQUIRE(itn_is_local(net, v), ITN_EUNSUPPORTED, "one-site gate on a vertex stored by another rank");
     ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor is not set");
     g_elems += (size_t)net->sdim[v] * net->sdim[v];
   }

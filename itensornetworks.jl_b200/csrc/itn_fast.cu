@@ -14,7 +14,7 @@
 // other two bonds is a 16x16 matrix X, and every step above is a 16x16x16 matrix product
 // (M^T X, X M, T^T conj(X), U conj(X)^T).  The device keeps two tile-major copies of each site tensor,
 //   F1[v][s][a4][a3] -> tile over (a1,a2)      F2[v][s][a2][a1] -> tile over (a3,a4)
-// each tile planar (re 16x16, im 16x16), column-major with the row index XOR-swizzled by 4*(col&3) so
+// each tile planar (re 16x16, im 16x16), column-major with the row index XOR-swizzled per column so
 // that all three DMMA fragment access patterns are bank-conflict free without padding.  Three launches
 // per sweep (one CTA = 8 tiles = one 32 KB contiguous half-cube per operand, one warp per tile):
 //   phase 1  X=F1            W = M1^T X M2           -> P12 (written in F2 layout)
@@ -33,7 +33,10 @@ constexpr int kChi = 16;
 constexpr int kTilesPerCta = 8;
 constexpr int kThreads = 256;
 
-__host__ __device__ __forceinline__ int swz(int r, int c) { return (r ^ ((c & 3) << 2)) + 16 * c; }
+// element (r, c) of a 16x16 column-major tile plane.  The row is XOR-ed with a column-dependent multiple of 4
+// chosen so that every DMMA fragment pattern -- (k, n) loads, (m, k) loads and the accumulator store with
+// columns 2t + j -- touches 16 distinct 8-byte bank slots per half-warp.
+__host__ __device__ __forceinline__ int swz(int r, int c) { return (r ^ (((c + (c >> 2)) & 3) << 2)) + 16 * c; }
 
 __device__ __forceinline__ void mma_16x8x8(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
   asm volatile(
@@ -130,11 +133,12 @@ template <bool C, bool HAS_P, bool DO_W>
 __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
   extern __shared__ __align__(16) double sm[];
   constexpr int TILE = C ? 512 : 256;
+  constexpr int TS = TILE + 2;  // shared-memory tile stride: +2 doubles rotates the banks from tile to tile
   double* Xs = sm;
-  double* Ss = Xs + kTilesPerCta * TILE;
-  double* MLs = Ss + kTilesPerCta * TILE;
-  double* MRs = MLs + TILE;
-  double* Ps = MRs + TILE;  // only when HAS_P
+  double* Ss = Xs + kTilesPerCta * TS;
+  double* MLs = Ss + kTilesPerCta * TS;
+  double* MRs = MLs + TS;
+  double* Ps = MRs + TS;  // only when HAS_P
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
   const int half = b & 1, q = (b >> 1) & 15, vs = b >> 5;
@@ -144,10 +148,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
 
   {
     const double* gx = a.X + cube;
-    for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) cp_async16(Xs + 2 * i, gx + 2 * i);
+    for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
+      const int w = i / (TILE / 2), r = i - w * (TILE / 2);
+      cp_async16(Xs + w * TS + 2 * r, gx + 2 * i);
+    }
     if (HAS_P) {
       const double* gp = a.P + cube;
-      for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) cp_async16(Ps + 2 * i, gp + 2 * i);
+      for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
+        const int w = i / (TILE / 2), r = i - w * (TILE / 2);
+        cp_async16(Ps + w * TS + 2 * r, gp + 2 * i);
+      }
     }
     const double* ml = a.msg[vi * 4 + a.kL];
     const double* mr = a.msg[vi * 4 + a.kR];
@@ -162,9 +172,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
   }
   __syncthreads();
 
-  double* X = Xs + warp * TILE;
-  double* S = Ss + warp * TILE;
-  double* P = Ps + warp * TILE;
+  double* X = Xs + warp * TS;
+  double* S = Ss + warp * TS;
+  double* P = Ps + warp * TS;
   double cre[2][4], cim[2][4];
   double lre[2][4], lim[2][4];  // "left" output, kept in registers until the end
   if (HAS_P) {
@@ -213,8 +223,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
       double sr = 0.0, sl = 0.0;
 #pragma unroll
       for (int w = 0; w < kTilesPerCta; ++w) {
-        sr += Ss[w * TILE + o];
-        sl += Ps[w * TILE + o];
+        sr += Ss[w * TS + o];
+        sl += Ps[w * TS + o];
       }
       pr[o] = sr;
       pl[o] = sl;
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
     double* wbase = a.W + (size_t)vs * 256 * TILE;
     for (int e = tid >> 3; e < TILE; e += kThreads / 8) {
       const int p = e >> 8, ij = e & 255, i = ij & 15, j = ij >> 4;
-      wbase[((size_t)(j * 16 + i)) * TILE + p * 256 + pos] = Xs[w * TILE + p * 256 + swz(i, j)];
+      wbase[((size_t)(j * 16 + i)) * TILE + p * 256 + pos] = Xs[w * TS + p * 256 + swz(i, j)];
     }
   }
 }
@@ -305,11 +315,12 @@ template <bool C, bool HAS_P, bool DO_W>
 void launch_phase(itn_net* net, const FastCache* fc, const FastArgs& a) {
   constexpr int TILE = C ? 512 : 256;
   // X, scratch, 2 messages (+P)
-  size_t smem = (size_t)(2 * kTilesPerCta + 2) * TILE * sizeof(double);
-  if (HAS_P) smem += (size_t)kTilesPerCta * TILE * sizeof(double);
+  size_t smem = (size_t)(2 * kTilesPerCta + 2) * (TILE + 2) * sizeof(double);
+  if (HAS_P) smem += (size_t)kTilesPerCta * (TILE + 2) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(k_fast<C, HAS_P, DO_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_fast<C, HAS_P, DO_W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   const unsigned grid = (unsigned)fc->nb * fc->d * 32;

@@ -325,15 +325,16 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
       if (m >= 1) {
         int e = net->inc[v][m - 1];
         const DevTensor& msg = net->M[net->msg_into(v, e)];
-        ITN_REQUIRE(msg.p != nullptr, ITN_EINVAL,
+        const double* ovr = sp.mats ? sp.mats[m - 1] : nullptr;
+        ITN_REQUIRE(ovr != nullptr || msg.p != nullptr, ITN_EINVAL,
                     "message into vertex " + std::to_string(v) + " on edge " + std::to_string(e) +
                         " is not set (on trees use the forest-cover sequence)");
         ModeStep& S = J.steps[J.nsteps++];
         S.L = Lacc;
         S.K = S.N = pdims[q];
         S.R = J.n / (Lacc * pdims[q]);
-        S.m = msg.p;
-        S.mplane = msg.n;
+        S.m = ovr ? ovr : msg.p;
+        S.mplane = (long long)pdims[q] * pdims[q];
         S.trans = 0;
         S.conj = 0;
       }
@@ -411,5 +412,67 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
     else k_gram<false><<<nb, kThreads, 0, ctx->stream>>>(dj);
     ITN_LAUNCH_CHECK(ctx);
     lo = hi;
+  }
+}
+
+// Mode products on tensors in canonical order (no permutation, no close): dst = src x_{mode_1} M_1 x_{mode_2} M_2 ...
+// Used for the environment-support projectors of the simple update (itn_linalg.cu).
+void itn_run_modeprods(itn_ctx* ctx, bool cplx, const std::vector<ModeProdSpec>& specs, std::vector<const double*>& result) {
+  result.assign(specs.size(), nullptr);
+  if (specs.empty()) return;
+  const int P = cplx ? 2 : 1;
+  std::vector<VJob> jobs(specs.size());
+  long long maxn = 0;
+  int maxsteps = 0, maxkn = 0;
+  for (size_t j = 0; j < specs.size(); ++j) {
+    const ModeProdSpec& sp = specs[j];
+    VJob J;
+    memset(&J, 0, sizeof(J));
+    J.a = sp.src;
+    J.ap = const_cast<double*>(sp.src);
+    J.identity_perm = 1;
+    J.n = sp.n;
+    J.nm = sp.nm;
+    J.w[0] = sp.w0;
+    J.w[1] = sp.w1;
+    for (int m = 0; m < sp.nm; ++m) J.dims[m] = sp.dims[m];
+    for (int t = 0; t < sp.nsteps; ++t) {
+      const int m = sp.mode[t];
+      long long L = 1;
+      for (int q = 0; q < m; ++q) L *= sp.dims[q];
+      ModeStep& S = J.steps[J.nsteps++];
+      S.L = L;
+      S.K = S.N = sp.dims[m];
+      S.R = sp.n / (L * sp.dims[m]);
+      S.m = sp.mat[t];
+      S.mplane = (long long)sp.dims[m] * sp.dims[m];
+      S.trans = 0;
+      S.conj = 0;
+      maxkn = std::max(maxkn, S.K * S.N);
+    }
+    maxn = std::max(maxn, J.n);
+    maxsteps = std::max(maxsteps, J.nsteps);
+    result[j] = J.nsteps == 0 ? sp.src : J.w[(J.nsteps - 1) & 1];
+    jobs[j] = J;
+  }
+  DevBuf jb(ctx, jobs.size() * sizeof(VJob));
+  const VJob* dj = itn_upload(ctx, jobs, jb);
+  unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + kThreads * 4 - 1) / (kThreads * 4), 64));
+  while (gy > 1 && (unsigned long long)gy * jobs.size() > 148ull * 64ull) gy = (gy + 1) / 2;
+  dim3 grid((unsigned)jobs.size(), gy);
+  int smem_elems = maxkn;
+  size_t smem_bytes = (size_t)smem_elems * P * sizeof(double);
+  if (smem_bytes > 96 * 1024) {
+    smem_elems = 0;
+    smem_bytes = 0;
+  }
+  if (smem_bytes > 48 * 1024) {
+    if (cplx) CUDA_CHECK(cudaFuncSetAttribute(k_modeprod<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    else CUDA_CHECK(cudaFuncSetAttribute(k_modeprod<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  }
+  for (int t = 0; t < maxsteps; ++t) {
+    if (cplx) k_modeprod<true><<<grid, kThreads, smem_bytes, ctx->stream>>>(dj, t, smem_elems);
+    else k_modeprod<false><<<grid, kThreads, smem_bytes, ctx->stream>>>(dj, t, smem_elems);
+    ITN_LAUNCH_CHECK(ctx);
   }
 }

@@ -40,6 +40,8 @@ struct itn_ctx {
   void* nccl = nullptr;      // ncclComm_t
   void* nccl_lib = nullptr;  // dlopen handle
   int64_t launches = 0;
+  int nets_alive = 0;          // handles created on this context and not yet destroyed
+  bool destroy_pending = false;  // itn_ctx_destroy was called while networks were alive (finalizer order)
   int path_mode = 0;
   int sm_count = 148;
   size_t ws_budget = (size_t)6 << 30;  // scratch budget for the generic path (bytes)
@@ -97,6 +99,7 @@ struct itn_net {
   uint64_t topo_version = 0;  // bumped whenever a tensor pointer / bond dim changes
   double last_total_ms = 0, last_contract_ms = 0;
   void* fast = nullptr;  // fast-path cache (owned by itn_fast.cu)
+  void* dist = nullptr;  // halo exchange plan and buffers (owned by itn_dist.cu)
 
   int planes() const { return cplx ? 2 : 1; }
   int other(int e, int v) const { return esrc[e] == v ? edst[e] : esrc[e]; }
@@ -141,11 +144,25 @@ struct JobSpec {
   int v;
   uint32_t open_mask;  // bit i set: mode i (0 = site, 1+k = k-th incident edge) stays open
   double* out;         // device, planar No x No
+  // optional: mats[k] != nullptr replaces the incoming message on bond slot k (planar chi x chi, device)
+  const double* const* mats = nullptr;
 };
 // Runs all specs in [lo, hi) batches bounded by the workspace budget. Results in spec.out.
 void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs);
 void itn_run_commit(itn_net* net, const std::vector<CommitJob>& jobs, int normalize, double* d_diffs);
 int itn_open_extent(const itn_net* net, int v, uint32_t open_mask);
+
+struct ModeProdSpec {
+  const double* src;  // planar, canonical order
+  long long n;        // elements
+  int nm;
+  int dims[ITN_MAX_MODES];
+  int nsteps;
+  int mode[ITN_MAX_MODES];          // which mode each step acts on
+  const double* mat[ITN_MAX_MODES];  // planar dims[mode] x dims[mode]: out[.., b, ..] = sum_a in[.., a, ..] mat[a + K b]
+  double *w0, *w1;                   // ping-pong outputs, n * planes doubles each
+};
+void itn_run_modeprods(itn_ctx* ctx, bool cplx, const std::vector<ModeProdSpec>& specs, std::vector<const double*>& result);
 
 // ---- fast path (itn_fast.cu) ----
 // Plans a synchronous sweep: handled[i] = 1 for the message jobs (directed id dids[i], source vertex
@@ -155,6 +172,14 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
 void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
                        const std::vector<char>& handled, double* const* staged);
 void itn_fast_release(itn_net* net);
+
+// ---- multi-GPU (itn_dist.cu) ----
+bool itn_is_local(const itn_net* net, int v);
+// Sends every message listed in `dids` whose destination vertex lives on another rank to that rank and
+// receives the matching ones (ordered by directed id on both sides); one grouped NCCL send/recv per peer.
+void itn_dist_exchange(itn_net* net, const std::vector<int>& dids);
+void itn_dist_allreduce_sum(itn_ctx* ctx, double* dev, int n);
+void itn_dist_release(itn_net* net);
 
 // ---- small linear algebra (itn_linalg.cu) ----
 // Batched Hermitian Jacobi eigen-decomposition based matrix function, planar matrices on device.

@@ -1,20 +1,1105 @@
-// Batched small dense linear algebra for simple update (placeholder).
+// Batched small dense linear algebra and the simple-update gate (apply.jl:33-95) on the device.
+//
+// simple_update_bp, restated so that the big site tensors are touched only twice per side
+// (one environment contraction, one rebuild) instead of absorb / QR / un-absorb:
+//
+//   reference (apply.jl:40-93)                         this engine
+//   --------------------------------------------       ---------------------------------------------
+//   S_j = sqrt(E_j), W_j = E_j^-1/2 (eigen)             E_j <- (E_j + E_j^H)/2          (k_hermitize)
+//   A~ = A x_j S_j                                     C = A~^T conj(A~) = bond environment of (s, l) with the
+//   Q, R = qr(A~)  (rows: outer bonds, cols: (s,l))        messages E_j absorbed            (generic kernels)
+//                                                      C = V L V^H (Jacobi); R = L^1/2 V^T, R^+ = conj(V) L^-1/2
+//   theta = R1 R2 ; theta' = gate theta                 same, on the r x (s,l) factors     (k_su_theta)
+//   U S V = svd(theta'), truncate (maxdim, cutoff)      one-sided Jacobi SVD + ITensors truncation rule
+//   R1' = U sqrt(S), R2' = sqrt(S) V                    same
+//   A' = (Q x_j conj(W_j)) R' = A x_j (S_j W_j^H) R^+ R'   A' = A . (R^+ R')   on the fused (s, l) index
+//
+// S_j W_j^H = P_j is the projector onto the support of E_j (eigenvalues below the reference's eigen cutoff,
+// 10 eps relative, are dropped): the identity for full-rank messages; otherwise A is replaced by A x_j P_j
+// before the rebuild (k_eig_fn with f = 1 builds P_j, itn_run_modeprods applies it).  Q is never formed: with R R^+ = 1 the product Q R' equals A~ R^+ R', and the
+// sqrt / inverse-sqrt gauges cancel.  Singular values, truncation error, kept dimension and the
+// contracted pair A1'.A2' are identical to the reference's in exact arithmetic (they do not depend on
+// the orthonormal basis chosen for the r index).
+//
+// map_eigvals (apply.jl:21-25) runs on the same Jacobi kernel.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
 #include "itn_internal.h"
 
-extern "C" int itn_apply2(itn_net*, const int32_t*, int, const void*, int, double, int, int, int32_t*, double*,
-                          double*, int) {
-  itn_set_error("itn_apply2: not implemented yet");
-  return ITN_EUNSUPPORTED;
+namespace {
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
-extern "C" int itn_map_eigvals(itn_ctx*, int, int, int, int, const void*, void*, double) {
-  itn_set_error("itn_map_eigvals: not implemented yet");
-  return ITN_EUNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------------
+// one-sided (Hestenes) Jacobi SVD, one CTA per matrix, planar storage, column-major
+//   in : A (m x n)                     out: A = U diag(sigma) (columns not normalised), V (n x n),
+//                                           sigma[n] sorted descending, perm[n] (sorted rank -> column)
+// ------------------------------------------------------------------------------------------------
+struct SvdJob {
+  double* a;      // planar m x n (im plane at +m*n)
+  double* v;      // planar n x n (im plane at +n*n)
+  double* sigma;  // n
+  int* perm;      // n
+  int m, n;
+};
+
+constexpr int kSvdThreads = 256;
+constexpr int kSvdMaxSweeps = 40;
+
+template <bool C>
+__global__ void __launch_bounds__(kSvdThreads) k_jacobi_svd(const SvdJob* __restrict__ jobs, int smem_doubles) {
+  extern __shared__ double sm[];
+  __shared__ int s_rot;
+  __shared__ double s_norm[256];
+  const SvdJob J = jobs[blockIdx.x];
+  const int m = J.m, n = J.n;
+  if (n == 0 || m == 0) return;
+  const long long mn = (long long)m * n, nn = (long long)n * n;
+  const int P = C ? 2 : 1;
+  const bool in_smem = (mn + nn) * P <= smem_doubles;
+  double* Ar = in_smem ? sm : J.a;
+  double* Ai = C ? (in_smem ? sm + mn : J.a + mn) : nullptr;
+  double* Vr = in_smem ? sm + P * mn : J.v;
+  double* Vi = C ? (in_smem ? sm + P * mn + nn : J.v + nn) : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSvdThreads >> 5;
+  if (in_smem)
+    for (long long i = tid; i < mn * P; i += kSvdThreads) sm[i] = J.a[i];
+  for (long long i = tid; i < nn; i += kSvdThreads) {
+    Vr[i] = (i % n == i / n) ? 1.0 : 0.0;
+    if (C) Vi[i] = 0.0;
+  }
+  __syncthreads();
+  // columns whose norm is below ~1e-19 ||A||_F are numerically null: rotating them only amplifies underflow
+  // noise (they appear whenever rank(A) < n, e.g. wide matrices and rank-deficient Gram matrices)
+  {
+    double f2 = 0.0;
+    for (long long i = tid; i < mn; i += kSvdThreads) {
+      f2 += Ar[i] * Ar[i];
+      if (C) f2 += Ai[i] * Ai[i];
+    }
+    f2 = wsum(f2);
+    if (lane == 0) s_norm[warp] = f2;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < nwarps; ++w) t += s_norm[w];
+      s_norm[255] = t * (2.220446049250313e-19 * 2.220446049250313e-19);
+    }
+    __syncthreads();
+  }
+  const double tiny = s_norm[255];
+  __syncthreads();
+  const int ne = n + (n & 1);  // even number of players; index n (if any) is a bye
+  const double tol = 4.0 * 2.220446049250313e-16;
+  for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int round = 0; round < ne - 1; ++round) {
+      for (int k = warp; k < ne / 2; k += nwarps) {
+        int p, q;
+        if (k == 0) {
+          p = ne - 1;
+          q = round;
+        } else {
+          p = (round + k) % (ne - 1);
+          q = (round - k + (ne - 1)) % (ne - 1);
+        }
+        if (p >= n || q >= n) continue;
+        if (p > q) {
+          int t = p;
+          p = q;
+          q = t;
+        }
+        double* apr = Ar + (long long)p * m;
+        double* aqr = Ar + (long long)q * m;
+        double* api = C ? Ai + (long long)p * m : nullptr;
+        double* aqi = C ? Ai + (long long)q * m : nullptr;
+        double alpha = 0, beta = 0, gr = 0, gi = 0;
+        for (int i = lane; i < m; i += 32) {
+          const double pr = apr[i], qr = aqr[i];
+          const double pi = C ? api[i] : 0.0, qi = C ? aqi[i] : 0.0;
+          alpha += pr * pr + pi * pi;
+          beta += qr * qr + qi * qi;
+          gr += pr * qr + pi * qi;  // conj(a_p) . a_q
+          gi += pr * qi - pi * qr;
+        }
+        alpha = wsum(alpha);
+        beta = wsum(beta);
+        gr = wsum(gr);
+        gi = C ? wsum(gi) : 0.0;
+        const double g2 = gr * gr + gi * gi;
+        if (g2 == 0.0 || alpha <= tiny || beta <= tiny || !(g2 > tol * tol * alpha * beta)) continue;
+        const double gabs = sqrt(g2);
+        // phase e^{-i phi} applied to column q so that the inner product becomes real positive
+        const double er = gr / gabs, ei = -gi / gabs;
+        const double zeta = (beta - alpha) / (2.0 * gabs);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = lane; i < m; i += 32) {
+          const double pr = apr[i], qr0 = aqr[i];
+          const double pi = C ? api[i] : 0.0, qi0 = C ? aqi[i] : 0.0;
+          const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
+          apr[i] = c * pr - s * qr;
+          aqr[i] = s * pr + c * qr;
+          if (C) {
+            api[i] = c * pi - s * qi;
+            aqi[i] = s * pi + c * qi;
+          }
+        }
+        double* vpr = Vr + (long long)p * n;
+        double* vqr = Vr + (long long)q * n;
+        double* vpi = C ? Vi + (long long)p * n : nullptr;
+        double* vqi = C ? Vi + (long long)q * n : nullptr;
+        for (int i = lane; i < n; i += 32) {
+          const double pr = vpr[i], qr0 = vqr[i];
+          const double pi = C ? vpi[i] : 0.0, qi0 = C ? vqi[i] : 0.0;
+          const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
+          vpr[i] = c * pr - s * qr;
+          vqr[i] = s * pr + c * qr;
+          if (C) {
+            vpi[i] = c * pi - s * qi;
+            vqi[i] = s * pi + c * qi;
+          }
+        }
+        if (lane == 0) s_rot = 1;
+      }
+      __syncthreads();
+    }
+    const int any = s_rot;
+    __syncthreads();
+    if (!any) break;
+  }
+  // singular values = column norms; stable descending order
+  for (int j = warp; j < n; j += nwarps) {
+    double a2 = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const double r = Ar[(long long)j * m + i], im = C ? Ai[(long long)j * m + i] : 0.0;
+      a2 += r * r + im * im;
+    }
+    a2 = wsum(a2);
+    if (lane == 0) s_norm[j] = sqrt(a2);
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += kSvdThreads) {
+    const double sj = s_norm[j];
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+      const double sk = s_norm[k];
+      rank += (sk > sj) || (sk == sj && k < j);
+    }
+    J.sigma[rank] = sj;
+    J.perm[rank] = j;
+  }
+  if (in_smem) {
+    for (long long i = tid; i < mn * P; i += kSvdThreads) J.a[i] = sm[i];
+    for (long long i = tid; i < nn * P; i += kSvdThreads) J.v[i] = sm[P * mn + i];
+  }
 }
-extern "C" int itn_nccl_unique_id(void*) {
-  itn_set_error("itn_nccl_unique_id: not implemented yet");
-  return ITN_EUNSUPPORTED;
+
+void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
+  if (jobs.empty()) return;
+  int maxn = 0;
+  size_t need = 0;
+  for (auto& j : jobs) {
+    ITN_REQUIRE(j.n <= 256, ITN_EUNSUPPORTED, "Jacobi SVD supports at most 256 columns");
+    maxn = std::max(maxn, j.n);
+    need = std::max(need, ((size_t)j.m * j.n + (size_t)j.n * j.n) * (cplx ? 2 : 1));
+  }
+  size_t smem = std::min<size_t>(need * sizeof(double), 200 * 1024);
+  DevBuf jb(ctx, jobs.size() * sizeof(SvdJob));
+  const SvdJob* dj = itn_upload(ctx, jobs, jb);
+  if (cplx) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_jacobi_svd<true><<<(unsigned)jobs.size(), kSvdThreads, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_jacobi_svd<false><<<(unsigned)jobs.size(), kSvdThreads, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
+  }
+  ITN_LAUNCH_CHECK(ctx);
 }
-extern "C" int itn_ctx_init_dist(itn_ctx*, int, int, const void*) {
-  itn_set_error("itn_ctx_init_dist: not implemented yet");
-  return ITN_EUNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------------
+// map_eigvals
+// ------------------------------------------------------------------------------------------------
+struct HermJob {
+  const double* src;  // planar chi x chi
+  double* dst;
+  int chi;
+};
+// dst = (src + src^H) / 2
+template <bool C>
+__global__ void k_hermitize(const HermJob* __restrict__ jobs) {
+  const HermJob J = jobs[blockIdx.x];
+  const int n = J.chi, n2 = n * n;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const int r = i % n, c = i / n, t = c + n * r;
+    J.dst[i] = 0.5 * (J.src[i] + J.src[t]);
+    if (C) J.dst[n2 + i] = 0.5 * (J.src[n2 + i] - J.src[n2 + t]);
+  }
 }
+
+// ITensors / NDTensors truncate! rule on weights p[0..n) sorted by decreasing magnitude.
+__device__ int truncate_spectrum(double* p, int n, int maxdim, double cutoff, double* truncerr_out) {
+  for (int i = n - 1; i >= 0; --i) {
+    if (p[i] >= 0.0) break;
+    p[i] = 0.0;
+  }
+  if (n == 1) {
+    *truncerr_out = 0.0;
+    return 1;
+  }
+  int md = (maxdim > 0 && maxdim < n) ? maxdim : n;
+  int k = n;
+  double terr = 0.0;
+  while (k > md) {
+    terr += p[k - 1];
+    --k;
+  }
+  double scale = 0.0;
+  for (int i = 0; i < n; ++i) scale += p[i];
+  if (scale == 0.0) scale = 1.0;
+  if (cutoff >= 0.0) {
+    while (k > 1 && terr + p[k - 1] <= cutoff * scale) {
+      terr += p[k - 1];
+      --k;
+    }
+  }
+  *truncerr_out = terr / scale;
+  return k < 1 ? 1 : k;
+}
+
+struct EigFnJob {
+  const double* h;    // hermitised input (planar)
+  const double* us;   // Jacobi output U*Sigma (planar)
+  const double* v;    // Jacobi output V
+  const double* sigma;
+  const int* perm;
+  double* out;        // planar chi x chi
+  int chi;
+  int* deficient;     // optional: set to 1 when eigenvalues were dropped by the cutoff
+};
+// out = V_kept f(lambda) V_kept^H with lambda_j = sigma_j * sign(Re <v_j, (U Sigma)_j>); diagonal inputs
+// short-circuit to f(diag) (map_diag, apply.jl:22).  fn: 0 sqrt, 1 inv sqrt, 2 inv, 3 one (support projector).
+template <bool C>
+__global__ void __launch_bounds__(256) k_eig_fn(const EigFnJob* __restrict__ jobs, int fn, double cutoff) {
+  __shared__ double lam[256];
+  __shared__ double fr[256], fi[256];
+  __shared__ int s_keep, s_diag;
+  const EigFnJob J = jobs[blockIdx.x];
+  const int n = J.chi, n2 = n * n;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_diag = 1;
+  __syncthreads();
+  for (int i = tid; i < n2; i += blockDim.x) {
+    if (i % n != i / n && (J.h[i] != 0.0 || (C && J.h[n2 + i] != 0.0))) s_diag = 0;
+  }
+  __syncthreads();
+  auto apply_f = [&](double l, double& re, double& im) {
+    // f on a real eigenvalue; complex dtype follows the principal branch for negative arguments
+    double sr, si;
+    if (fn == 3) {
+      re = 1.0;
+      im = 0.0;
+      return;
+    }
+    if (l >= 0.0) {
+      sr = sqrt(l);
+      si = 0.0;
+    } else if (C) {
+      sr = 0.0;
+      si = sqrt(-l);
+    } else {
+      sr = nan("");
+      si = 0.0;
+    }
+    if (fn == 0) {
+      re = sr;
+      im = si;
+    } else if (fn == 1) {
+      if (si == 0.0) {
+        re = 1.0 / sr;
+        im = 0.0;
+      } else {
+        const double den = sr * sr + si * si;
+        re = sr / den;
+        im = -si / den;
+      }
+    } else {
+      re = 1.0 / l;
+      im = 0.0;
+    }
+  };
+  if (s_diag) {
+    for (int i = tid; i < n2; i += blockDim.x) {
+      double re = 0.0, im = 0.0;
+      if (i % n == i / n) apply_f(J.h[i], re, im);
+      J.out[i] = re;
+      if (C) J.out[n2 + i] = im;
+    }
+    return;
+  }
+  for (int j = tid; j < n; j += blockDim.x) {
+    const int col = J.perm[j];
+    double d = 0.0;
+    for (int i = 0; i < n; ++i) {
+      d += J.v[col * n + i] * J.us[col * n + i];
+      if (C) d += J.v[n2 + col * n + i] * J.us[n2 + col * n + i];
+    }
+    lam[j] = d < 0.0 ? -J.sigma[j] : J.sigma[j];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int keep = n;
+    if (cutoff >= 0.0) {
+      double terr;
+      double p[256];
+      for (int i = 0; i < n; ++i) p[i] = lam[i];
+      keep = truncate_spectrum(p, n, 0, cutoff, &terr);
+    }
+    s_keep = keep;
+    if (J.deficient && keep < n) *J.deficient = 1;
+  }
+  __syncthreads();
+  const int keep = s_keep;
+  for (int j = tid; j < keep; j += blockDim.x) apply_f(lam[j], fr[j], fi[j]);
+  __syncthreads();
+  for (int i = tid; i < n2; i += blockDim.x) {
+    const int r = i % n, c = i / n;
+    double ar = 0.0, ai = 0.0;
+    for (int j = 0; j < keep; ++j) {
+      const int col = J.perm[j];
+      const double vr = J.v[col * n + r], vi = C ? J.v[n2 + col * n + r] : 0.0;
+      const double wr = J.v[col * n + c], wi = C ? -J.v[n2 + col * n + c] : 0.0;  // conj(V[c, j])
+      const double pr = vr * wr - vi * wi, pi = vr * wi + vi * wr;
+      ar += pr * fr[j] - pi * fi[j];
+      ai += pr * fi[j] + pi * fr[j];
+    }
+    J.out[i] = ar;
+    if (C) J.out[n2 + i] = ai;
+  }
+}
+
+// host interleaved <-> device planar for batches of equally sized matrices
+template <bool C>
+__global__ void k_split(const double* __restrict__ in, double* __restrict__ out, int each, int count) {
+  const long long tot = (long long)each * count;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / each, r = i % each;
+    if (C) {
+      out[b * 2 * each + r] = in[2 * i];
+      out[b * 2 * each + each + r] = in[2 * i + 1];
+    } else {
+      out[i] = in[i];
+    }
+  }
+}
+template <bool C>
+__global__ void k_merge(const double* __restrict__ in, double* __restrict__ out, int each, int count) {
+  const long long tot = (long long)each * count;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / each, r = i % each;
+    if (C) {
+      out[2 * i] = in[b * 2 * each + r];
+      out[2 * i + 1] = in[b * 2 * each + each + r];
+    } else {
+      out[i] = in[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// simple update glue kernels (one CTA per edge)
+// ------------------------------------------------------------------------------------------------
+struct SuEdge {
+  // per side (0: esrc, 1: edst)
+  const double* gus[2];   // Jacobi output of the bond environment C (n x n): U*Sigma (unused), kept for symmetry
+  const double* gv[2];    // eigenvectors V (n x n)
+  const double* gsig[2];  // eigenvalues, sorted descending
+  const int* gperm[2];
+  double* R[2];           // r x n
+  double* Rp[2];          // n x r
+  double* T[2];           // n x (d * chi_new), column-major: T[(s + d*l) + n*(s' + d*l')]
+  int d[2], n[2], r[2];
+  int chi;                // current bond dimension
+  const double* gate;     // planar d1 d2 d1 d2: g[s1' + d1*(s2' + d2*(s1 + d1*s2))]
+  double* theta;          // planar (r1 d1) x (r2 d2)
+  double* tv;             // V of theta
+  double* tsig;
+  int* tperm;
+  int newdim;             // filled on the host after truncation
+};
+
+// R[i, o] = sqrt(lambda_i) V[o, i];  R^+[o, i] = conj(V[o, i]) / sqrt(lambda_i)   (C = V L V^H = conj(A~^H A~))
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_build_R(const SuEdge* __restrict__ edges) {
+  const SuEdge E = edges[blockIdx.x >> 1];
+  const int side = blockIdx.x & 1;
+  const int n = E.n[side], r = E.r[side];
+  const long long n2 = (long long)n * n, rn = (long long)r * n;
+  const double lmax = E.gsig[side][0];
+  const double thr = lmax * n * 2.220446049250313e-16;
+  for (long long idx = threadIdx.x; idx < rn; idx += blockDim.x) {
+    const int i = (int)(idx % r), o = (int)(idx / r);
+    const int col = E.gperm[side][i];
+    const double lam = E.gsig[side][i];
+    const double sq = sqrt(lam);
+    const double inv = (lam > thr && lam > 0.0) ? 1.0 / sq : 0.0;
+    const double vr = E.gv[side][(long long)col * n + o];
+    const double vi = C ? E.gv[side][n2 + (long long)col * n + o] : 0.0;
+    E.R[side][i + (long long)r * o] = sq * vr;
+    E.Rp[side][o + (long long)n * i] = inv * vr;
+    if (C) {
+      E.R[side][rn + i + (long long)r * o] = sq * vi;
+      E.Rp[side][rn + o + (long long)n * i] = -inv * vi;
+    }
+  }
+}
+
+// theta'[(r1, s1'), (r2, s2')] = sum gate[s1', s2', s1, s2] sum_l R1[r1, (s1, l)] R2[r2, (s2, l)]
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_theta(const SuEdge* __restrict__ edges) {
+  const SuEdge E = edges[blockIdx.x];
+  const int d1 = E.d[0], d2 = E.d[1], r1 = E.r[0], r2 = E.r[1], chi = E.chi;
+  const int m = r1 * d1, nc = r2 * d2;
+  const long long mn = (long long)m * nc;
+  const long long p1 = (long long)r1 * E.n[0], p2 = (long long)r2 * E.n[1];
+  const int gsz = d1 * d2 * d1 * d2;
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < mn; idx += (long long)gridDim.y * blockDim.x) {
+    const int row = (int)(idx % m), colx = (int)(idx / m);
+    const int a = row % r1, s1p = row / r1, b = colx % r2, s2p = colx / r2;
+    double accr = 0.0, acci = 0.0;
+    for (int s1 = 0; s1 < d1; ++s1)
+      for (int s2 = 0; s2 < d2; ++s2) {
+        double tr = 0.0, ti = 0.0;
+        for (int l = 0; l < chi; ++l) {
+          const long long i1 = a + (long long)r1 * (s1 + d1 * l), i2 = b + (long long)r2 * (s2 + d2 * l);
+          const double xr = E.R[0][i1], yr = E.R[1][i2];
+          if (C) {
+            const double xi = E.R[0][p1 + i1], yi = E.R[1][p2 + i2];
+            tr += xr * yr - xi * yi;
+            ti += xr * yi + xi * yr;
+          } else {
+            tr += xr * yr;
+          }
+        }
+        const int gi = s1p + d1 * (s2p + d2 * (s1 + d1 * s2));
+        const double gr = E.gate[gi], gim = C ? E.gate[gsz + gi] : 0.0;
+        accr += gr * tr - gim * ti;
+        acci += gr * ti + gim * tr;
+      }
+    E.theta[idx] = accr;
+    if (C) E.theta[mn + idx] = acci;
+  }
+}
+
+struct SuTrunc {
+  const double* tsig;
+  int ncand;  // min(m, n)
+  int* newdim;
+  double* truncerr;
+  double* svals;  // stride entries
+};
+__global__ void k_su_truncate(const SuTrunc* __restrict__ jobs, int n, int maxdim, double cutoff, int stride) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const SuTrunc T = jobs[j];
+  double p[512];
+  const int nc = T.ncand;
+  for (int i = 0; i < nc; ++i) p[i] = T.tsig[i] * T.tsig[i];
+  double terr = 0.0;
+  const int keep = truncate_spectrum(p, nc, maxdim, cutoff, &terr);
+  *T.newdim = keep;
+  *T.truncerr = terr;
+  for (int i = 0; i < stride; ++i) T.svals[i] = i < keep ? T.tsig[i] : 0.0;
+}
+
+// T_side[(s, l), (s', l')] = sum_r R^+[(s, l), r] R'[r, s', l'],
+//   R1'[r, s', l'] = (U S)[(r, s'), l'] / sqrt(sigma_l'),  R2'[r, s', l'] = sqrt(sigma_l') conj(V[(r, s'), l'])
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_T(const SuEdge* __restrict__ edges) {
+  const SuEdge E = edges[blockIdx.x >> 1];
+  const int side = blockIdx.x & 1;
+  const int n = E.n[side], r = E.r[side], d = E.d[side], nd = E.newdim;
+  const int m = E.r[0] * E.d[0], nc = E.r[1] * E.d[1];
+  const long long mn = (long long)m * nc, nn = (long long)nc * nc, rn = (long long)r * n;
+  const long long tot = (long long)n * d * nd;
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.y * blockDim.x) {
+    const int o = (int)(idx % n);
+    const int q = (int)(idx / n);
+    const int sp = q % d, lp = q / d;
+    const int col = E.tperm[lp];
+    const double sig = E.tsig[lp];
+    const double f = side == 0 ? (sig > 0.0 ? 1.0 / sqrt(sig) : 0.0) : sqrt(sig);
+    double accr = 0.0, acci = 0.0;
+    for (int a = 0; a < r; ++a) {
+      const double pr = E.Rp[side][o + (long long)n * a];
+      const double pi = C ? E.Rp[side][rn + o + (long long)n * a] : 0.0;
+      double xr, xi;
+      if (side == 0) {
+        const long long i = (a + (long long)r * sp) + (long long)m * col;
+        xr = E.theta[i];
+        xi = C ? E.theta[mn + i] : 0.0;
+      } else {
+        const long long i = (a + (long long)r * sp) + (long long)nc * col;
+        xr = E.tv[i];
+        xi = C ? -E.tv[nn + i] : 0.0;
+      }
+      accr += pr * xr - pi * xi;
+      acci += pr * xi + pi * xr;
+    }
+    E.T[side][idx] = f * accr;
+    if (C) E.T[side][tot + idx] = f * acci;
+  }
+}
+
+struct SuSite {
+  const double* a;   // old tensor, canonical planar [s, bonds...]
+  double* out;       // new tensor
+  const double* T;   // n x (d * chi_new)
+  long long n_old, n_new;
+  long long lo;      // product of extents below the shared bond (incl. site): stride of l
+  long long hi;      // product of extents above the shared bond
+  int d, chi, chi_new;
+};
+// A'[s', lo.., l', hi..] = sum_{s, l} A[s, lo.., l, hi..] T[(s, l), (s', l')]
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_rebuild(const SuSite* __restrict__ sites) {
+  const SuSite S = sites[blockIdx.x];
+  const int d = S.d, chi = S.chi, cn = S.chi_new, n = d * chi;
+  const long long lo_rest = S.lo / d;  // extents between site and the shared bond
+  const long long tsz = (long long)n * d * cn;
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < S.n_new; idx += (long long)gridDim.y * blockDim.x) {
+    const int sp = (int)(idx % d);
+    long long r = idx / d;
+    const long long mid = r % lo_rest;
+    r /= lo_rest;
+    const int lp = (int)(r % cn);
+    const long long top = r / cn;
+    const long long base = d * mid + S.lo * (long long)chi * top;
+    const long long tcol = (long long)n * (sp + d * lp);
+    double accr = 0.0, acci = 0.0;
+    for (int l = 0; l < chi; ++l)
+      for (int s = 0; s < d; ++s) {
+        const long long ia = base + s + S.lo * l;
+        const double ar = S.a[ia], tr = S.T[tcol + s + d * l];
+        if (C) {
+          const double ai = S.a[S.n_old + ia], ti = S.T[tsz + tcol + s + d * l];
+          accr += ar * tr - ai * ti;
+          acci += ar * ti + ai * tr;
+        } else {
+          accr += ar * tr;
+        }
+      }
+    S.out[idx] = accr;
+    if (C) S.out[S.n_new + idx] = acci;
+  }
+}
+
+struct DiagMsgJob {
+  double* m;            // planar chi x chi
+  const double* svals;  // null: identity
+  int chi;
+};
+template <bool C>
+__global__ void k_diag_msg(const DiagMsgJob* __restrict__ jobs) {
+  const DiagMsgJob J = jobs[blockIdx.x];
+  const int n2 = J.chi * J.chi;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const int r = i % J.chi, c = i / J.chi;
+    J.m[i] = (r == c) ? (J.svals ? J.svals[r] : 1.0) : 0.0;
+    if (C) J.m[n2 + i] = 0.0;
+  }
+}
+
+struct NormJob2 {
+  double* p;
+  long long n;
+};
+__global__ void __launch_bounds__(256) k_normalize2(const NormJob2* __restrict__ jobs) {
+  __shared__ double sh[8];
+  __shared__ double tot;
+  const NormJob2 J = jobs[blockIdx.x];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < J.n; i += blockDim.x) s += J.p[i] * J.p[i];
+  s = wsum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    tot = t;
+  }
+  __syncthreads();
+  const double f = 1.0 / sqrt(tot);
+  for (long long i = threadIdx.x; i < J.n; i += blockDim.x) J.p[i] *= f;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// map_eigvals entry points
+// ------------------------------------------------------------------------------------------------
+void itn_dev_map_eigvals(itn_ctx* ctx, bool cplx, int fn, int chi, int n, const double* const* in_ptrs,
+                         double* const* out_ptrs, double cutoff) {
+  // in_ptrs / out_ptrs are HOST arrays of device pointers (planar chi x chi matrices)
+  if (n == 0) return;
+  ITN_REQUIRE(chi >= 1 && chi <= 256, ITN_EUNSUPPORTED, "map_eigvals supports 1 <= chi <= 256");
+  const int P = cplx ? 2 : 1;
+  const size_t n2 = (size_t)chi * chi;
+  DevBuf h(ctx, n * n2 * P * sizeof(double)), us(ctx, n * n2 * P * sizeof(double)), v(ctx, n * n2 * P * sizeof(double));
+  DevBuf sig(ctx, (size_t)n * chi * sizeof(double)), perm(ctx, (size_t)n * chi * sizeof(int));
+  std::vector<HermJob> hj(n);
+  std::vector<SvdJob> sj(n);
+  std::vector<EigFnJob> ej(n);
+  for (int i = 0; i < n; ++i) {
+    double* hi = h.as<double>() + i * n2 * P;
+    double* ui = us.as<double>() + i * n2 * P;
+    double* vi = v.as<double>() + i * n2 * P;
+    hj[i] = {in_ptrs[i], hi, chi};
+    sj[i] = {ui, vi, sig.as<double>() + (size_t)i * chi, perm.as<int>() + (size_t)i * chi, chi, chi};
+    ej[i] = {hi, ui, vi, sig.as<double>() + (size_t)i * chi, perm.as<int>() + (size_t)i * chi, out_ptrs[i], chi, nullptr};
+  }
+  DevBuf hb(ctx, hj.size() * sizeof(HermJob)), eb(ctx, ej.size() * sizeof(EigFnJob));
+  const HermJob* dh = itn_upload(ctx, hj, hb);
+  if (cplx) k_hermitize<true><<<n, 128, 0, ctx->stream>>>(dh);
+  else k_hermitize<false><<<n, 128, 0, ctx->stream>>>(dh);
+  ITN_LAUNCH_CHECK(ctx);
+  CUDA_CHECK(cudaMemcpyAsync(us.p, h.p, n * n2 * P * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  run_jacobi(ctx, cplx, sj);
+  const EigFnJob* de = itn_upload(ctx, ej, eb);
+  if (cplx) k_eig_fn<true><<<n, 256, 0, ctx->stream>>>(de, fn, cutoff);
+  else k_eig_fn<false><<<n, 256, 0, ctx->stream>>>(de, fn, cutoff);
+  ITN_LAUNCH_CHECK(ctx);
+}
+
+#define API_BEGIN try {
+#define API_END                              \
+  }                                          \
+  catch (const ItnError& e) {                \
+    itn_set_error(e.what());                 \
+    return e.code;                           \
+  }                                          \
+  catch (const std::bad_alloc&) {            \
+    itn_set_error("host allocation failed"); \
+    return ITN_ENOMEM;                       \
+  }                                          \
+  catch (const std::exception& e) {          \
+    itn_set_error(e.what());                 \
+    return ITN_EINVAL;                       \
+  }                                          \
+  return ITN_OK;
+
+extern "C" int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, const void* host_in, void* host_out,
+                               double cutoff) {
+  API_BEGIN
+  ITN_REQUIRE(ctx && host_in && host_out, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(dtype == ITN_F64 || dtype == ITN_C128, ITN_EUNSUPPORTED, "dtype must be 0 (Float64) or 1 (ComplexF64)");
+  ITN_REQUIRE(fn >= 0 && fn <= 2, ITN_EINVAL, "fn must be 0 (sqrt), 1 (inv sqrt) or 2 (inv)");
+  ITN_REQUIRE(n >= 0 && chi >= 1, ITN_EINVAL, "bad batch shape");
+  if (n == 0) return ITN_OK;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  const bool cplx = dtype == ITN_C128;
+  const int P = cplx ? 2 : 1;
+  const size_t n2 = (size_t)chi * chi, bytes = (size_t)n * n2 * P * sizeof(double);
+  DevBuf raw(ctx, bytes), in(ctx, bytes), out(ctx, bytes);
+  CUDA_CHECK(cudaMemcpyAsync(raw.p, host_in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned g = (unsigned)std::min<size_t>((n * n2 + 255) / 256, 2048);
+  if (cplx) k_split<true><<<g, 256, 0, ctx->stream>>>(raw.as<double>(), in.as<double>(), (int)n2, n);
+  else k_split<false><<<g, 256, 0, ctx->stream>>>(raw.as<double>(), in.as<double>(), (int)n2, n);
+  ITN_LAUNCH_CHECK(ctx);
+  std::vector<const double*> ip(n);
+  std::vector<double*> op(n);
+  for (int i = 0; i < n; ++i) {
+    ip[i] = in.as<double>() + i * n2 * P;
+    op[i] = out.as<double>() + i * n2 * P;
+  }
+  itn_dev_map_eigvals(ctx, cplx, fn, chi, n, ip.data(), op.data(), cutoff);
+  if (cplx) k_merge<true><<<g, 256, 0, ctx->stream>>>(out.as<double>(), raw.as<double>(), (int)n2, n);
+  else k_merge<false><<<g, 256, 0, ctx->stream>>>(out.as<double>(), raw.as<double>(), (int)n2, n);
+  ITN_LAUNCH_CHECK(ctx);
+  CUDA_CHECK(cudaMemcpyAsync(host_out, raw.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply2: simple update on a vertex-disjoint batch of edges
+// ------------------------------------------------------------------------------------------------
+extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* gates, int maxdim, double cutoff,
+                          int normalize, int msg_mode, int32_t* newdim_out, double* truncerr_out, double* svals_out,
+                          int svals_stride) {
+  API_BEGIN
+  ITN_REQUIRE(net && eids && gates && n >= 0, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(msg_mode == 0 || msg_mode == 1, ITN_EINVAL, "msg_mode must be 0 (identity) or 1 (singular values)");
+  if (n == 0) return ITN_OK;
+  CUDA_CHECK(cudaSetDevice(net->ctx->device));
+  itn_ctx* ctx = net->ctx;
+  const bool cplx = net->cplx;
+  const int P = net->planes();
+  // ---- validation (errors mirror src/apply.jl:118-129,140-144) ----
+  std::vector<char> used(net->nv, 0);
+  for (int i = 0; i < n; ++i) {
+    const int e = eids[i];
+    ITN_REQUIRE(e >= 0 && e < net->ne, ITN_EINVAL, "Vertices where the gates are being applied must be neighbors for now.");
+    for (int v : {net->esrc[e], net->edst[e]}) {
+      ITN_REQUIRE(!used[v], ITN_EINVAL, "a batch of two-site gates must be vertex-disjoint");
+      used[v] = 1;
+      ITN_REQUIRE(itn_is_local(net, v), ITN_EUNSUPPORTED, "two-site gate on an edge that crosses a partition cut is not supported yet");
+      ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor is not set");
+      for (int f : net->inc[v])
+        if (f != e)
+          ITN_REQUIRE(net->M[net->msg_into(v, f)].p, ITN_EINVAL,
+                      "environment message into vertex " + std::to_string(v) + " is not set (update the BP cache first)");
+    }
+  }
+  // ---- sizes and workspace ----
+  struct Geo {
+    int e, v[2], k[2], d[2], nn[2], r[2], chi, m, nc;
+    long long X[2];
+  };
+  std::vector<Geo> geo(n);
+  size_t ws_doubles = 0, env_doubles = 0, sig_total = 0;
+  int max_cand = 1;
+  for (int i = 0; i < n; ++i) {
+    Geo& g = geo[i];
+    g.e = eids[i];
+    g.v[0] = net->esrc[g.e];
+    g.v[1] = net->edst[g.e];
+    g.chi = net->edim[g.e];
+    for (int s = 0; s < 2; ++s) {
+      const int v = g.v[s];
+      g.k[s] = net->slot(v, g.e);
+      g.d[s] = net->sdim[v];
+      g.nn[s] = g.d[s] * g.chi;
+      g.X[s] = net->T[v].n / g.nn[s];
+      g.r[s] = (int)std::min<long long>(g.X[s], g.nn[s]);
+      ITN_REQUIRE(g.nn[s] <= 256, ITN_EUNSUPPORTED, "simple update supports d*chi <= 256");
+      // C, V, R, R^+ ; T sized for the largest possible new bond
+      ws_doubles += (size_t)P * (2 * (size_t)g.nn[s] * g.nn[s] + 2 * (size_t)g.r[s] * g.nn[s]);
+      sig_total += g.nn[s];
+      for (int f : net->inc[v])
+        if (f != g.e) env_doubles += (size_t)P * net->edim[f] * net->edim[f];
+    }
+    g.m = g.r[0] * g.d[0];
+    g.nc = g.r[1] * g.d[1];
+    ITN_REQUIRE(g.nc <= 256 && g.m <= 512, ITN_EUNSUPPORTED, "simple update supports bond matrices up to 512 x 256");
+    const int cand = std::min(g.m, g.nc);
+    max_cand = std::max(max_cand, cand);
+    ws_doubles += (size_t)P * ((size_t)g.m * g.nc + (size_t)g.nc * g.nc);
+    for (int s = 0; s < 2; ++s) ws_doubles += (size_t)P * g.nn[s] * g.d[s] * cand;
+    sig_total += g.nc;
+  }
+  ITN_REQUIRE(!svals_out || svals_stride >= 1, ITN_EINVAL, "svals_stride must be positive");
+  const int stride = std::max(max_cand, 1);
+  DevBuf ws(ctx, ws_doubles * sizeof(double)), envs(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double));
+  // eigen-decomposition of the environments: only their support projectors are needed (see file header)
+  size_t env_count = 0, env_sig = 0;
+  for (int i = 0; i < n; ++i)
+    for (int s = 0; s < 2; ++s)
+      for (int f : net->inc[geo[i].v[s]])
+        if (f != geo[i].e) {
+          ++env_count;
+          env_sig += net->edim[f];
+        }
+  DevBuf env_us(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double)), env_v(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double));
+  DevBuf env_pi(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double));
+  DevBuf env_s(ctx, std::max<size_t>(env_sig, 1) * sizeof(double)), env_p(ctx, std::max<size_t>(env_sig, 1) * sizeof(int));
+  DevBuf env_flag(ctx, std::max<size_t>(env_count, 1) * sizeof(int));
+  CUDA_CHECK(cudaMemsetAsync(env_flag.p, 0, std::max<size_t>(env_count, 1) * sizeof(int), ctx->stream));
+  struct EnvRef {
+    int edge_i, side, slot;
+    const double* pi;
+  };
+  std::vector<EnvRef> env_refs;
+  std::vector<SvdJob> ej_svd;
+  std::vector<EigFnJob> ej_fn;
+  DevBuf sigs(ctx, sig_total * sizeof(double)), perms(ctx, sig_total * sizeof(int));
+  DevBuf d_newdim(ctx, (size_t)n * sizeof(int)), d_terr(ctx, (size_t)n * sizeof(double)), d_sv(ctx, (size_t)n * stride * sizeof(double));
+  // gates: host interleaved -> planar
+  size_t gate_elems = 0;
+  std::vector<size_t> goff(n);
+  for (int i = 0; i < n; ++i) {
+    goff[i] = gate_elems;
+    gate_elems += (size_t)geo[i].d[0] * geo[i].d[1] * geo[i].d[0] * geo[i].d[1];
+  }
+  DevBuf d_gates(ctx, gate_elems * P * sizeof(double));
+  {
+    std::vector<double> tmp(gate_elems * P);
+    const double* h = (const double*)gates;
+    for (int i = 0; i < n; ++i) {
+      const size_t ge = (size_t)geo[i].d[0] * geo[i].d[1] * geo[i].d[0] * geo[i].d[1];
+      for (size_t t = 0; t < ge; ++t) {
+        if (cplx) {
+          tmp[goff[i] * 2 + t] = h[(goff[i] + t) * 2];
+          tmp[goff[i] * 2 + ge + t] = h[(goff[i] + t) * 2 + 1];
+        } else {
+          tmp[goff[i] + t] = h[goff[i] + t];
+        }
+      }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d_gates.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // tmp dies at scope end
+  }
+  // ---- carve workspace, build jobs ----
+  std::vector<SuEdge> se(n);
+  std::vector<HermJob> hj;
+  std::vector<JobSpec> specs;
+  std::vector<std::vector<const double*>> overrides;  // per spec: matrices per bond slot
+  overrides.reserve(2 * (size_t)n);
+  std::vector<SvdJob> gj, tj;
+  std::vector<SuTrunc> tr(n);
+  double* w = ws.as<double>();
+  double* envp = envs.as<double>();
+  size_t env_sig_off = 0;
+  double* sp = sigs.as<double>();
+  int* pp = perms.as<int>();
+  for (int i = 0; i < n; ++i) {
+    const Geo& g = geo[i];
+    SuEdge& E = se[i];
+    memset(&E, 0, sizeof(E));
+    E.chi = g.chi;
+    for (int s = 0; s < 2; ++s) {
+      const int v = g.v[s];
+      const size_t n2 = (size_t)g.nn[s] * g.nn[s], rn = (size_t)g.r[s] * g.nn[s];
+      double* Cm = w; w += P * n2;
+      double* Vm = w; w += P * n2;
+      E.R[s] = w; w += P * rn;
+      E.Rp[s] = w; w += P * rn;
+      E.gus[s] = Cm;
+      E.gv[s] = Vm;
+      E.gsig[s] = sp;
+      E.gperm[s] = pp;
+      E.d[s] = g.d[s];
+      E.n[s] = g.nn[s];
+      E.r[s] = g.r[s];
+      gj.push_back({Cm, Vm, sp, pp, g.nn[s], g.nn[s]});
+      sp += g.nn[s];
+      pp += g.nn[s];
+      // hermitised environments (map_eigvals symmetrises its argument, apply.jl:9-15 with ishermitian = true)
+      overrides.emplace_back(net->inc[v].size(), nullptr);
+      for (size_t j = 0; j < net->inc[v].size(); ++j) {
+        const int f = net->inc[v][j];
+        if (f == g.e) continue;
+        const int c = net->edim[f];
+        hj.push_back({net->M[net->msg_into(v, f)].p, envp, c});
+        overrides.back()[j] = envp;
+        {
+          const size_t off = envp - envs.as<double>();
+          double* us = env_us.as<double>() + off;
+          double* vv = env_v.as<double>() + off;
+          double* pi = env_pi.as<double>() + off;
+          const size_t k = env_refs.size();
+          ej_svd.push_back({us, vv, env_s.as<double>() + env_sig_off, env_p.as<int>() + env_sig_off, c, c});
+          ej_fn.push_back({envp, us, vv, env_s.as<double>() + env_sig_off, env_p.as<int>() + env_sig_off, pi, c,
+                           env_flag.as<int>() + k});
+          env_refs.push_back({i, s, (int)j, pi});
+          env_sig_off += c;
+        }
+        envp += (size_t)P * c * c;
+      }
+      JobSpec spx;
+      spx.v = v;
+      spx.open_mask = 1u | (1u << (g.k[s] + 1));
+      spx.out = Cm;
+      spx.mats = overrides.back().data();
+      specs.push_back(spx);
+    }
+    E.gate = d_gates.as<double>() + goff[i] * P;
+    E.theta = w; w += (size_t)P * g.m * g.nc;
+    E.tv = w; w += (size_t)P * g.nc * g.nc;
+    E.tsig = sp;
+    E.tperm = pp;
+    tj.push_back({E.theta, E.tv, sp, pp, g.m, g.nc});
+    sp += g.nc;
+    pp += g.nc;
+    const int cand = std::min(g.m, g.nc);
+    for (int s = 0; s < 2; ++s) {
+      E.T[s] = w;
+      w += (size_t)P * g.nn[s] * g.d[s] * cand;
+    }
+    tr[i] = {E.tsig, cand, d_newdim.as<int>() + i, d_terr.as<double>() + i, d_sv.as<double>() + (size_t)i * stride};
+  }
+  // ---- 1. hermitise environments, bond environments C_side, eigen-decompose ----
+  if (!hj.empty()) {
+    DevBuf hb(ctx, hj.size() * sizeof(HermJob));
+    const HermJob* dh = itn_upload(ctx, hj, hb);
+    if (cplx) k_hermitize<true><<<(unsigned)hj.size(), 128, 0, ctx->stream>>>(dh);
+    else k_hermitize<false><<<(unsigned)hj.size(), 128, 0, ctx->stream>>>(dh);
+    ITN_LAUNCH_CHECK(ctx);
+  }
+  itn_run_vertex_jobs(net, specs);
+  run_jacobi(ctx, cplx, gj);
+  if (!ej_svd.empty()) {
+    // projector onto the support of every environment: eigenvalues below 10 eps (relative) are dropped, as in
+    // map_eigvals(sqrt / inv o sqrt, env; cutoff = 10 eps) (apply.jl:36,40-69)
+    CUDA_CHECK(cudaMemcpyAsync(env_us.p, envs.p, env_doubles * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    run_jacobi(ctx, cplx, ej_svd);
+    DevBuf fb(ctx, ej_fn.size() * sizeof(EigFnJob));
+    const EigFnJob* de = itn_upload(ctx, ej_fn, fb);
+    const double eig_cutoff = 10.0 * 2.220446049250313e-16;
+    if (cplx) k_eig_fn<true><<<(unsigned)ej_fn.size(), 256, 0, ctx->stream>>>(de, 3, eig_cutoff);
+    else k_eig_fn<false><<<(unsigned)ej_fn.size(), 256, 0, ctx->stream>>>(de, 3, eig_cutoff);
+    ITN_LAUNCH_CHECK(ctx);
+  }
+  // ---- 2. R factors, theta', SVD, truncation ----
+  DevBuf seb(ctx, se.size() * sizeof(SuEdge));
+  const SuEdge* dse = itn_upload(ctx, se, seb);
+  if (cplx) k_su_build_R<true><<<2 * n, 256, 0, ctx->stream>>>(dse);
+  else k_su_build_R<false><<<2 * n, 256, 0, ctx->stream>>>(dse);
+  ITN_LAUNCH_CHECK(ctx);
+  if (cplx) k_su_theta<true><<<dim3(n, 8), 256, 0, ctx->stream>>>(dse);
+  else k_su_theta<false><<<dim3(n, 8), 256, 0, ctx->stream>>>(dse);
+  ITN_LAUNCH_CHECK(ctx);
+  run_jacobi(ctx, cplx, tj);
+  DevBuf trb(ctx, tr.size() * sizeof(SuTrunc));
+  const SuTrunc* dtr = itn_upload(ctx, tr, trb);
+  k_su_truncate<<<(n + 31) / 32, 32, 0, ctx->stream>>>(dtr, n, maxdim, cutoff, stride);
+  ITN_LAUNCH_CHECK(ctx);
+  std::vector<int> newdim(n);
+  std::vector<double> terr(n), sv((size_t)n * stride);
+  CUDA_CHECK(cudaMemcpyAsync(newdim.data(), d_newdim.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(terr.data(), d_terr.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(sv.data(), d_sv.p, sv.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<int> eflag(std::max<size_t>(env_count, 1), 0);
+  CUDA_CHECK(cudaMemcpyAsync(eflag.data(), env_flag.p, eflag.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  // sites with a rank-deficient environment: A <- A x_j P_j before the rebuild
+  std::vector<ModeProdSpec> pspecs;
+  std::vector<std::pair<int, int>> pspec_site;  // (edge_i, side)
+  std::vector<double*> pscratch;
+  std::vector<const double*> presult;
+  for (size_t k = 0; k < env_refs.size(); ++k) {
+    if (!eflag[k]) continue;
+    const EnvRef& r = env_refs[k];
+    const int v = geo[r.edge_i].v[r.side];
+    int idx = -1;
+    for (size_t q = 0; q < pspec_site.size(); ++q)
+      if (pspec_site[q] == std::make_pair(r.edge_i, r.side)) idx = (int)q;
+    if (idx < 0) {
+      ModeProdSpec sp;
+      memset(&sp, 0, sizeof(sp));
+      sp.src = net->T[v].p;
+      sp.n = net->T[v].n;
+      sp.nm = (int)net->inc[v].size() + 1;
+      sp.dims[0] = net->sdim[v];
+      for (size_t j = 0; j < net->inc[v].size(); ++j) sp.dims[j + 1] = net->edim[net->inc[v][j]];
+      sp.w0 = (double*)itn_dev_alloc(ctx, (size_t)sp.n * P * sizeof(double));
+      pscratch.push_back(sp.w0);
+      sp.w1 = (double*)itn_dev_alloc(ctx, (size_t)sp.n * P * sizeof(double));
+      pscratch.push_back(sp.w1);
+      pspecs.push_back(sp);
+      pspec_site.push_back({r.edge_i, r.side});
+      idx = (int)pspecs.size() - 1;
+    }
+    ModeProdSpec& sp = pspecs[idx];
+    sp.mode[sp.nsteps] = r.slot + 1;
+    sp.mat[sp.nsteps] = r.pi;
+    sp.nsteps++;
+  }
+  itn_run_modeprods(ctx, cplx, pspecs, presult);
+  // ---- 3. T factors and the new site tensors ----
+  for (int i = 0; i < n; ++i) se[i].newdim = newdim[i];
+  CUDA_CHECK(cudaMemcpyAsync((void*)dse, se.data(), se.size() * sizeof(SuEdge), cudaMemcpyHostToDevice, ctx->stream));
+  if (cplx) k_su_T<true><<<dim3(2 * n, 4), 256, 0, ctx->stream>>>(dse);
+  else k_su_T<false><<<dim3(2 * n, 4), 256, 0, ctx->stream>>>(dse);
+  ITN_LAUNCH_CHECK(ctx);
+  std::vector<SuSite> sites;
+  std::vector<double*> fresh;
+  std::vector<NormJob2> nj;
+  long long maxn = 0;
+  try {
+    for (int i = 0; i < n; ++i) {
+      const Geo& g = geo[i];
+      for (int s = 0; s < 2; ++s) {
+        const int v = g.v[s];
+        SuSite S;
+        S.a = net->T[v].p;
+        for (size_t q = 0; q < pspec_site.size(); ++q)
+          if (pspec_site[q] == std::make_pair(i, s)) S.a = presult[q];
+        S.T = se[i].T[s];
+        S.d = g.d[s];
+        S.chi = g.chi;
+        S.chi_new = newdim[i];
+        S.n_old = net->T[v].n;
+        S.n_new = net->T[v].n / g.chi * newdim[i];
+        long long lo = g.d[s];
+        for (int j = 0; j < g.k[s]; ++j) lo *= net->edim[net->inc[v][j]];
+        S.lo = lo;
+        S.hi = net->T[v].n / (lo * g.chi);
+        S.out = (double*)itn_dev_alloc(ctx, (size_t)S.n_new * P * sizeof(double));
+        fresh.push_back(S.out);
+        sites.push_back(S);
+        nj.push_back({S.out, S.n_new * P});
+        maxn = std::max(maxn, S.n_new);
+      }
+    }
+  } catch (...) {
+    for (double* p : fresh) itn_dev_free(ctx, p);
+    for (double* p : pscratch) itn_dev_free(ctx, p);
+    throw;
+  }
+  {
+    DevBuf sb(ctx, sites.size() * sizeof(SuSite));
+    const SuSite* ds = itn_upload(ctx, sites, sb);
+    unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + 255) / 256, 128));
+    while (gy > 1 && (unsigned long long)gy * sites.size() > 148ull * 32ull) gy = (gy + 1) / 2;
+    if (cplx) k_su_rebuild<true><<<dim3((unsigned)sites.size(), gy), 256, 0, ctx->stream>>>(ds);
+    else k_su_rebuild<false><<<dim3((unsigned)sites.size(), gy), 256, 0, ctx->stream>>>(ds);
+    ITN_LAUNCH_CHECK(ctx);
+    if (normalize) {
+      DevBuf nb(ctx, nj.size() * sizeof(NormJob2));
+      const NormJob2* dn = itn_upload(ctx, nj, nb);
+      k_normalize2<<<(unsigned)nj.size(), 256, 0, ctx->stream>>>(dn);
+      ITN_LAUNCH_CHECK(ctx);
+    }
+  }
+  for (double* p : pscratch) itn_dev_free(ctx, p);  // stream ordered: freed after the rebuild kernel
+  // ---- 4. commit: swap tensors, new bond dimensions, reset the messages on the gated edges ----
+  std::vector<DiagMsgJob> dj;
+  size_t si = 0;
+  for (int i = 0; i < n; ++i) {
+    const Geo& g = geo[i];
+    for (int s = 0; s < 2; ++s, ++si) {
+      const int v = g.v[s];
+      itn_dev_free(ctx, net->T[v].p);
+      net->T[v].p = sites[si].out;
+      net->T[v].n = sites[si].n_new;
+    }
+    net->edim[g.e] = newdim[i];
+    for (int dd = 0; dd < 2; ++dd) {
+      DevTensor& m = net->M[2 * g.e + dd];
+      const long long n2 = (long long)newdim[i] * newdim[i];
+      if (m.p) itn_dev_free(ctx, m.p);
+      m.p = (double*)itn_dev_alloc(ctx, (size_t)n2 * P * sizeof(double));
+      m.n = n2;
+      dj.push_back({m.p, msg_mode == 1 ? d_sv.as<double>() + (size_t)i * stride : nullptr, newdim[i]});
+    }
+  }
+  {
+    DevBuf db(ctx, dj.size() * sizeof(DiagMsgJob));
+    const DiagMsgJob* dd = itn_upload(ctx, dj, db);
+    if (cplx) k_diag_msg<true><<<(unsigned)dj.size(), 128, 0, ctx->stream>>>(dd);
+    else k_diag_msg<false><<<(unsigned)dj.size(), 128, 0, ctx->stream>>>(dd);
+    ITN_LAUNCH_CHECK(ctx);
+  }
+  net->topo_version++;
+  for (int i = 0; i < n; ++i) {
+    if (newdim_out) newdim_out[i] = newdim[i];
+    if (truncerr_out) truncerr_out[i] = terr[i];
+    if (svals_out)
+      for (int t = 0; t < svals_stride; ++t) svals_out[(size_t)i * svals_stride + t] = t < stride ? sv[(size_t)i * stride + t] : 0.0;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU plumbing lives in itn_dist.cu
+// ------------------------------------------------------------------------------------------------

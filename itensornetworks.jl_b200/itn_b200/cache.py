@@ -33,6 +33,7 @@ class Context:
         check(lib().itn_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.h = h
         self.device = device
+        self.rank, self.world = 0, 1  # set by itn_b200.init_distributed
 
     def sync(self):
         check(lib().itn_ctx_sync(self.h))
@@ -84,7 +85,7 @@ class BeliefPropagationCache:
         self.sdims = [t.shape[0] for t in psi.tensors]
         # multi-GPU: owner[v] = rank that stores vertex v; dist = (rank, nranks) of this process
         self.owner = None if owner is None else [int(x) for x in owner]
-        self.rank = 0 if dist is None else int(dist[0])
+        self.rank = self.ctx.rank if dist is None else int(dist[0])
         a0, p0 = i32([u for u, _ in g.edges])
         a1, p1 = i32([v for _, v in g.edges])
         a2, p2 = i32([psi.edge_dim(e) for e in range(g.ne)])

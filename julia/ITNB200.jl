@@ -1,0 +1,176 @@
+# ITNB200.jl -- Julia shim over libitn_b200.so (UNTESTED: there is no Julia runtime in the build image or on the
+# GPU boxes; the same ABI is exercised by the Python ctypes mirror in itensornetworks.jl_b200/itn_b200/).
+#
+# `B200BeliefPropagationCache <: AbstractBeliefPropagationCache` holds an `itn_net*` and forwards the interface
+# of src/caches/abstractbeliefpropagationcache.jl:44-69 to the C ABI declared in include/itn_b200.h.  Host code
+# (graphs, index bookkeeping, OpSum -> gate arrays, edge sequences) stays in ITensorNetworks.jl.
+module ITNB200
+
+using ITensors: ITensors, ITensor, Index, array, dim, inds, itensor, commonind, noncommoninds
+using ITensorNetworks: ITensorNetworks, AbstractBeliefPropagationCache, ITensorNetwork, default_edge_sequence,
+  edges, vertices, src, dst, siteinds, linkinds
+using NamedGraphs: NamedGraphs, NamedEdge
+
+const LIB = get(ENV, "ITN_B200_LIB", joinpath(@__DIR__, "..", "itensornetworks.jl_b200", "lib", "libitn_b200.so"))
+
+struct ITNError <: Exception
+  code::Cint
+  msg::String
+end
+# src/apply.jl:120-128 and friends raise ErrorException; keep that type so `@test_throws ErrorException` holds.
+function check(status::Cint)
+  status == 0 && return nothing
+  msg = unsafe_string(ccall((:itn_last_error, LIB), Cstring, ()))
+  return error(msg)
+end
+
+mutable struct Context
+  h::Ptr{Cvoid}
+  function Context(device::Integer=0; stream::Ptr{Cvoid}=C_NULL)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:itn_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), device, stream, out))
+    ctx = new(out[])
+    finalizer(c -> ccall((:itn_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), ctx)
+    return ctx
+  end
+end
+
+"""
+BP cache of <psi|psi> with the default one-site partition whose tensors and messages live on a B200.
+Mirrors BeliefPropagationCache (src/caches/beliefpropagationcache.jl:13-35).
+"""
+mutable struct B200BeliefPropagationCache{V} <: AbstractBeliefPropagationCache{V}
+  h::Ptr{Cvoid}
+  ctx::Context
+  psi::ITensorNetwork{V}          # host copy of the index structure (tensors are authoritative on the device)
+  verts::Vector{V}                # vertex <-> 0-based id
+  vid::Dict{V,Int}
+  eds::Vector{NamedEdge{V}}       # undirected edge list, id = position - 1
+  elt::Type
+end
+
+dtype_code(::Type{Float64}) = Cint(0)
+dtype_code(::Type{ComplexF64}) = Cint(1)
+
+function B200BeliefPropagationCache(psi::ITensorNetwork{V}; ctx::Context=Context(), messages=:default) where {V}
+  verts = collect(vertices(psi))
+  vid = Dict(v => i - 1 for (i, v) in enumerate(verts))
+  eds = collect(edges(psi))
+  elt = promote_type(map(v -> eltype(psi[v]), verts)...)
+  esrc = Int32[vid[src(e)] for e in eds]
+  edst = Int32[vid[dst(e)] for e in eds]
+  edim = Int32[dim(commonind(psi[src(e)], psi[dst(e)])) for e in eds]
+  sdim = Int32[dim(only(siteinds(psi, v))) for v in verts]
+  out = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:itn_net_create, LIB), Cint,
+    (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Cvoid}}),
+    ctx.h, dtype_code(elt), length(verts), length(eds), esrc, edst, edim, sdim, C_NULL, out))
+  bpc = B200BeliefPropagationCache{V}(out[], ctx, psi, verts, vid, eds, elt)
+  finalizer(b -> ccall((:itn_net_destroy, LIB), Cint, (Ptr{Cvoid},), b.h), bpc)
+  for v in verts
+    set_factor!(bpc, v, psi[v])
+  end
+  # initialize_cache (src/initialize_cache.jl:14-29): identity messages on loopy graphs only
+  if messages === :identity || (messages === :default && !NamedGraphs.is_tree(psi))
+    check(ccall((:itn_msg_set_identity, LIB), Cint, (Ptr{Cvoid},), bpc.h))
+  end
+  return bpc
+end
+
+# axis_edge[i] = edge id carried by axis i of the ITensor's storage, or -1 for the site index
+function axis_edges(bpc::B200BeliefPropagationCache, v, t::ITensor)
+  s = only(siteinds(bpc.psi, v))
+  return Int32[i == s ? -1 : findfirst(e -> (src(e) == v || dst(e) == v) &&
+                                       i == commonind(bpc.psi[src(e)], bpc.psi[dst(e)]), bpc.eds) - 1
+               for i in inds(t)]
+end
+
+function set_factor!(bpc::B200BeliefPropagationCache, v, t::ITensor)   # bpc[v] = t (beliefpropagationcache.jl:88-91)
+  a = array(t)                                   # column-major, axes in inds(t) order
+  ax = axis_edges(bpc, v, t)
+  GC.@preserve a ax check(ccall((:itn_net_set_tensor, LIB), Cint,
+    (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Int32}), bpc.h, bpc.vid[v], a, ndims(a), ax))
+  return bpc
+end
+
+Base.copy(bpc::B200BeliefPropagationCache{V}) where {V} = begin   # beliefpropagationcache.jl:43-47
+  out = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:itn_net_clone, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), bpc.h, out))
+  c = B200BeliefPropagationCache{V}(out[], bpc.ctx, bpc.psi, bpc.verts, bpc.vid, bpc.eds, bpc.elt)
+  finalizer(b -> ccall((:itn_net_destroy, LIB), Cint, (Ptr{Cvoid},), b.h), c)
+  c
+end
+
+# update(bpc; maxiter, tol, edge_sequence, message_update_alg = (; normalize))   (abstract...cache.jl:313-337)
+function ITensorNetworks.update(bpc::B200BeliefPropagationCache; maxiter=nothing, tol=nothing,
+  edge_sequence=default_edge_sequence(bpc.psi), normalize=true, kwargs...)
+  isnothing(maxiter) && NamedGraphs.is_tree(bpc.psi) && (maxiter = 1)
+  isnothing(maxiter) && error("You need to specify a number of iterations for BP!")
+  grouped = !isempty(edge_sequence) && first(edge_sequence) isa AbstractVector
+  flat = grouped ? reduce(vcat, edge_sequence) : edge_sequence
+  s = Int32[bpc.vid[src(e)] for e in flat]
+  d = Int32[bpc.vid[dst(e)] for e in flat]
+  gp = grouped ? Int32[0; cumsum(length.(edge_sequence))] : Int32[]
+  out = copy(bpc)
+  iters = Ref{Int32}(0); diff = Ref{Float64}(NaN)
+  GC.@preserve s d gp check(ccall((:itn_bp_update, LIB), Cint,
+    (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Cint, Cdouble, Cint, Ptr{Int32}, Ptr{Cdouble}),
+    out.h, s, d, length(flat), grouped ? pointer(gp) : C_NULL, grouped ? length(edge_sequence) : 0,
+    maxiter, isnothing(tol) ? -1.0 : tol, normalize, iters, diff))
+  return out
+end
+
+# message(bpc, edge) (abstract...cache.jl:173-175) as an ITensor on (prime(link)', link)-style indices is built by
+# the caller from this matrix M[a, a'] (a: ket link, a': bra link).
+function message_matrix(bpc::B200BeliefPropagationCache, e)
+  chi = Ref{Int32}(0)
+  eid = findfirst(x -> (src(x), dst(x)) == (src(e), dst(e)) || (src(x), dst(x)) == (dst(e), src(e)), bpc.eds) - 1
+  check(ccall((:itn_net_edge_dim, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}), bpc.h, eid, chi))
+  m = Matrix{bpc.elt}(undef, chi[], chi[])
+  GC.@preserve m check(ccall((:itn_msg_get, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}),
+    bpc.h, bpc.vid[src(e)], bpc.vid[dst(e)], m))
+  return m
+end
+
+function ITensorNetworks.logscalar(bpc::B200BeliefPropagationCache)      # abstract...cache.jl:397-408
+  out = zeros(Float64, 2)
+  check(ccall((:itn_logscalar, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), bpc.h, out))
+  return out[2] == 0 ? out[1] : complex(out[1], out[2])
+end
+
+function ITensorNetworks.rescale(bpc::B200BeliefPropagationCache; kwargs...)   # abstract...cache.jl:391-395
+  out = copy(bpc)
+  check(ccall((:itn_rescale, LIB), Cint, (Ptr{Cvoid},), out.h))
+  return out
+end
+
+# expect(psiIpsi, op) (src/expect.jl:5-19) for a list of vertices and one d x d operator matrix O[s_out, s_in]
+function expect_matrix(bpc::B200BeliefPropagationCache, O::AbstractMatrix, verts=bpc.verts)
+  ids = Int32[bpc.vid[v] for v in verts]
+  ops = repeat(vec(Matrix{bpc.elt}(O)), length(verts))
+  out = Vector{bpc.elt}(undef, length(verts))
+  GC.@preserve ids ops out check(ccall((:itn_expect1, LIB), Cint,
+    (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), bpc.h, ids, length(ids), ops, out))
+  return Dict(zip(verts, out))
+end
+
+# apply(o, psi; envs = environment(bpc, ...), maxdim, cutoff, normalize, callback) (src/apply.jl:97-146) with the
+# environments taken from the cache's own messages; `gate` is the d1 x d2 x d1 x d2 array g[s1', s2', s1, s2].
+function apply_gate!(bpc::B200BeliefPropagationCache, gate::AbstractArray, v1, v2; maxdim=nothing, cutoff=nothing,
+  normalize=false, callback=Returns(nothing), msg_mode=0)
+  eid = findfirst(x -> Set((src(x), dst(x))) == Set((v1, v2)), bpc.eds)
+  isnothing(eid) && error("Vertices where the gates are being applied must be neighbors for now.")
+  e = bpc.eds[eid]
+  g = Array{bpc.elt,4}(gate)
+  src(e) == v1 || (g = permutedims(g, (2, 1, 4, 3)))
+  newdim = Ref{Int32}(0); terr = Ref{Float64}(0.0); sv = zeros(Float64, 512)
+  ids = Int32[eid - 1]
+  GC.@preserve g ids sv check(ccall((:itn_apply2, LIB), Cint,
+    (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Cvoid}, Cint, Cdouble, Cint, Cint, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble}, Cint),
+    bpc.h, ids, 1, g, isnothing(maxdim) ? 0 : maxdim, isnothing(cutoff) ? -1.0 : cutoff, normalize, msg_mode,
+    newdim, terr, sv, length(sv)))
+  callback(; singular_values=sv[1:newdim[]], truncation_error=terr[])
+  return bpc
+end
+
+end # module
