@@ -295,6 +295,11 @@ def run_ours(args):
         h2d, d2h = int(hb[0]), int(hb[1])
     e2e_val = n_updates / e2e_s
 
+    # ---- simple-update gates/s (second half of BASELINE.json's metric), single GPU ------------------------
+    su = None
+    if world == 1 and args.gates:
+        su = bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -322,12 +327,56 @@ def run_ours(args):
                 "steps": e2e_steps, "what": "BeliefPropagationCache(psi from pinned host) + update(maxiter=1) + download of all messages"},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if su is not None:
+        su["frac_of_fp64_peak"] = su["algorithmic_tflops"] / peak["sustained"]
+        line["simple_update"] = su
     if args.cpu_baseline:
         n, dt, sample = cpu_reference_sample(dims, chi, dtype, args.cpu_budget)
         line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": sample}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def gate_flops(graph, chi, d, cplx):
+    """per site F_gemm = c*(2(z-1)+d)*d*chi^(z+1) (absorb, un-absorb, rebuild) and
+    F_qr = (c/2)*4*d^2*chi^(z+1); one gate touches two sites.  Summed over every edge of the lattice."""
+    c = 8.0 if cplx else 2.0
+    tot = 0.0
+    for (u, v) in graph.edges:
+        for w in (u, v):
+            z = graph.degree(w)
+            tot += c * (2 * (z - 1) + d) * d * float(chi) ** (z + 1) + (c / 2) * 4 * d * d * float(chi) ** (z + 1)
+    return tot
+
+
+def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch):
+    """One Trotter step = one two-site gate on every edge, applied as vertex-disjoint colour layers
+    (apply(o, psi; envs = BP messages, maxdim = chi, cutoff = 1e-12), src/apply.jl:97-146), in place on the device."""
+    rng = np.random.default_rng(7)
+    m = rng.standard_normal((d * d, d * d)) + (1j * rng.standard_normal((d * d, d * d)) if np.dtype(dtype).kind == "c" else 0)
+    h = (m + m.conj().T) / 2
+    w, v = np.linalg.eigh(h)
+    gate = ((v * np.exp(-0.05 * w)) @ v.conj().T).astype(dtype).reshape(d, d, d, d)  # exp(-tau H): imaginary-time step
+    layers = E.edge_coloring(graph)
+    work = bpc.copy()
+    E.apply_layer([gate] * len(layers[-1]), work, [graph.edges[e] for e in layers[-1]], maxdim=chi, cutoff=1e-12)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ngates = 0
+    terr = 0.0
+    for layer in layers:
+        info = E.apply_layer([gate] * len(layer), work, [graph.edges[e] for e in layer], maxdim=chi, cutoff=1e-12)
+        ngates += len(layer)
+        terr = max(terr, float(np.max(info["truncation_error"])))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    work.close()
+    fl = gate_flops(graph, chi, d, np.dtype(dtype).kind == "c")
+    return {"gates_per_s": ngates / dt, "ms_per_trotter_step": 1e3 * dt, "gates": ngates, "colour_layers": len(layers),
+            "max_truncation_error": terr, "algorithmic_tflops": fl / dt / 1e12,
+            "note": "wall clock incl. the host round trip per layer (new bond dimensions are read back); "
+                    "algorithmic flops = F_gemm + F_qr of SURVEY.md 8(d)"}
 
 
 def main():
@@ -339,6 +388,7 @@ def main():
     ap.add_argument("--workload", default="grid64x64_chi16_c128", choices=sorted(WORKLOADS))
     ap.add_argument("--path", type=int, default=None, help="0 = auto (DMMA fast path), 1 = generic kernels only")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-gates", dest="gates", action="store_false", help="skip the simple-update gates/s section")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

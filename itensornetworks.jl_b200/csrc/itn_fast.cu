@@ -266,26 +266,46 @@ struct RelayoutJob {
   const double* src;  // canonical planar [s, a1, a2, a3, a4]
   long long n;
 };
+// canonical planar [s, a1, a2, a3, a4] -> F1[s][a4][a3][tile(a1,a2)]: block (vertex, a4) streams one contiguous
+// d*4096 slab; a warp's stores land in d runs of 16 consecutive (swizzled) doubles.
 template <bool C>
-__global__ void __launch_bounds__(256) k_fast_relayout(const RelayoutJob* __restrict__ jobs, double* __restrict__ F1,
-                                                        double* __restrict__ F2, int d) {
+__global__ void __launch_bounds__(256) k_fast_relayout_f1(const RelayoutJob* __restrict__ jobs, double* __restrict__ F1, int d) {
   constexpr int TILE = C ? 512 : 256;
   const RelayoutJob J = jobs[blockIdx.x];
+  const int a4 = blockIdx.y;
   const size_t base = (size_t)blockIdx.x * d * 256 * TILE;
-  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < J.n; i += (long long)gridDim.y * blockDim.x) {
-    const int s = (int)(i % d);
-    const int r = (int)(i / d);
-    const int a1 = r & 15, a2 = (r >> 4) & 15, a3 = (r >> 8) & 15, a4 = r >> 12;
-    const size_t o1 = base + (((size_t)s * 16 + a4) * 16 + a3) * TILE + swz(a1, a2);
-    const size_t o2 = base + (((size_t)s * 16 + a2) * 16 + a1) * TILE + swz(a3, a4);
-    const double re = J.src[i];
-    F1[o1] = re;
-    F2[o2] = re;
-    if (C) {
-      const double im = J.src[J.n + i];
-      F1[o1 + 256] = im;
-      F2[o2 + 256] = im;
+  const double* src = J.src + (size_t)a4 * 4096 * d;
+  for (int i = threadIdx.x; i < 4096 * d; i += blockDim.x) {
+    const int s = i % d, r = i / d;
+    const int a1 = r & 15, a2 = (r >> 4) & 15, a3 = r >> 8;
+    const size_t o = base + (((size_t)s * 16 + a4) * 16 + a3) * TILE + swz(a1, a2);
+    F1[o] = src[i];
+    if (C) F1[o + 256] = src[J.n + i];
+  }
+}
+// canonical -> F2[s][a2][a1][tile(a3,a4)]: block (vertex, a2) gathers 256 runs of 16*d doubles, transposes them
+// through shared memory (tile stride 257 keeps the column writes conflict-free) and writes whole tiles.
+template <bool C>
+__global__ void __launch_bounds__(256) k_fast_relayout_f2(const RelayoutJob* __restrict__ jobs, double* __restrict__ F2, int d) {
+  extern __shared__ double sm[];
+  constexpr int TILE = C ? 512 : 256;
+  const RelayoutJob J = jobs[blockIdx.x];
+  const int a2 = blockIdx.y;
+  const size_t base = (size_t)blockIdx.x * d * 256 * TILE;
+  const int ntile = 16 * d;
+  for (int plane = 0; plane < (C ? 2 : 1); ++plane) {
+    const double* src = J.src + (size_t)plane * J.n;
+    for (int e = threadIdx.x; e < ntile * 256; e += blockDim.x) {
+      const int s = e % d, a1 = (e / d) & 15, r = e / (16 * d);  // r = a3 + 16 a4
+      sm[(s * 16 + a1) * 257 + swz(r & 15, r >> 4)] = src[s + (size_t)d * (a1 + 16 * a2 + 256 * (size_t)r)];
     }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ntile * 256; e += blockDim.x) {
+      const int t = e >> 8, o = e & 255;  // t = s*16 + a1
+      const int s = t >> 4, a1 = t & 15;
+      F2[base + (((size_t)s * 16 + a2) * 16 + a1) * TILE + plane * 256 + o] = sm[t * 257 + o];
+    }
+    __syncthreads();
   }
 }
 
@@ -397,9 +417,19 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
     for (int i = 0; i < fc->nb; ++i) jobs[i] = {net->T[verts[i]].p, net->T[verts[i]].n};
     DevBuf jb(ctx, jobs.size() * sizeof(RelayoutJob));
     const RelayoutJob* dj = itn_upload(ctx, jobs, jb);
-    dim3 grid(fc->nb, 32);
-    if (net->cplx) k_fast_relayout<true><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, fc->F2, d);
-    else k_fast_relayout<false><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, fc->F2, d);
+    dim3 grid(fc->nb, 16);
+    const size_t rsm = (size_t)16 * d * 257 * sizeof(double);
+    if (net->cplx) {
+      k_fast_relayout_f1<true><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, d);
+      ITN_LAUNCH_CHECK(ctx);
+      CUDA_CHECK(cudaFuncSetAttribute(k_fast_relayout_f2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+      k_fast_relayout_f2<true><<<grid, 256, rsm, ctx->stream>>>(dj, fc->F2, d);
+    } else {
+      k_fast_relayout_f1<false><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, d);
+      ITN_LAUNCH_CHECK(ctx);
+      CUDA_CHECK(cudaFuncSetAttribute(k_fast_relayout_f2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+      k_fast_relayout_f2<false><<<grid, 256, rsm, ctx->stream>>>(dj, fc->F2, d);
+    }
     ITN_LAUNCH_CHECK(ctx);
     fc->topo_version = net->topo_version;
   }
