@@ -83,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50", "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -187,6 +187,11 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def ms_estimate_short(args, world):
+    """True when the timed region is likely shorter than the clock sampler's period."""
+    return args.steps * 30.0 / max(world, 1) < 400.0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -245,11 +250,16 @@ def run_ours(args):
 
     # ---- device-resident arm ---------------------------------------------------------------------
     bpc = E.BeliefPropagationCache(psi, ctx=ctx, owner=owner, dist=(rank, world) if world > 1 else None)
-    E.update(bpc, maxiter=args.warmup, edge_sequence=seq, inplace=True)
-    barrier()
-    l0 = ctx.launch_count()
+    # clocks are sampled from the warm-up sweeps to the end of the timed region (the GPU is under the same load in both;
+    # nvidia-smi needs ~100 ms to deliver its first sample, longer than a short timed region)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    E.update(bpc, maxiter=max(args.warmup, 3), edge_sequence=seq, inplace=True)
+    barrier()
+    if ms_estimate_short(args, world):
+        E.update(bpc, maxiter=20, edge_sequence=seq, inplace=True)  # extra untimed sweeps so that the sampler sees load
+        barrier()
+    l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with torch.cuda.stream(stream):
@@ -277,13 +287,20 @@ def run_ours(args):
         2 for (u, v) in graph.edges if owner[u] == rank or owner[v] == rank)
     d2h = n_stored * chi * chi * comps * 8
     out_host = torch.empty(n_stored * chi * chi * comps, dtype=torch.float64).pin_memory()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    def e2e_step():
         c2 = E.BeliefPropagationCache(psi, ctx=ctx, owner=owner, dist=(rank, world) if world > 1 else None)
         E.update(c2, maxiter=1, edge_sequence=seq, inplace=True)
         c2.messages_into(out_host.numpy())
         c2.close()
+
+    e2e_step()  # untimed warm-up: the second network's device allocations grow the stream-ordered pool once
+    barrier()
+    per_step = []
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ta = time.perf_counter()
+        e2e_step()
+        per_step.append(time.perf_counter() - ta)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
@@ -324,7 +341,7 @@ def run_ours(args):
                      "contract_ms_per_sweep": contract_ms_per_sweep,
                      "note": "achieved = algorithmic flops (8*z*d*chi^(z+1) per message) / device time; FP64 DMMA peak, not bf16"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "what": "BeliefPropagationCache(psi from pinned host) + update(maxiter=1) + download of all messages"},
+                "steps": e2e_steps, "s_per_step": per_step, "what": "BeliefPropagationCache(psi from pinned host) + update(maxiter=1) + download of all messages"},
         "gpu_launches": launches, "clocks": clocks,
     }
     if su is not None:

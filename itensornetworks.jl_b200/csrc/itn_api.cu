@@ -49,6 +49,20 @@ void itn_dev_free(itn_ctx* ctx, void* p) {
   if (p) cudaFreeAsync(p, ctx->stream);
 }
 
+void itn_tensor_free(itn_ctx* ctx, DevTensor& t) {
+  if (t.slab) {
+    if (--t.slab->refs == 0) {
+      itn_dev_free(ctx, t.slab->base);
+      delete t.slab;
+    }
+  } else if (t.p) {
+    itn_dev_free(ctx, t.p);
+  }
+  t.p = nullptr;
+  t.n = 0;
+  t.slab = nullptr;
+}
+
 static void set_device(const itn_ctx* ctx) { CUDA_CHECK(cudaSetDevice(ctx->device)); }
 
 // ------------------------------------------------------------------------------------------------
@@ -481,7 +495,7 @@ static void alloc_message(itn_net* net, int did) {
   int e = did / 2;
   long long n2 = (long long)net->edim[e] * net->edim[e];
   if (net->M[did].p && net->M[did].n == n2) return;
-  if (net->M[did].p) itn_dev_free(net->ctx, net->M[did].p);
+  if (net->M[did].p) itn_tensor_free(net->ctx, net->M[did]);
   net->M[did].p = (double*)itn_dev_alloc(net->ctx, (size_t)n2 * net->planes() * sizeof(double));
   net->M[did].n = n2;
 }
@@ -548,9 +562,9 @@ extern "C" int itn_net_create(itn_ctx* ctx, int dtype, int nv, int ne, const int
 
 static void free_net_storage(itn_net* net) {
   for (auto& t : net->T)
-    if (t.p) itn_dev_free(net->ctx, t.p), t.p = nullptr;
+    if (t.p) itn_tensor_free(net->ctx, t);
   for (auto& m : net->M)
-    if (m.p) itn_dev_free(net->ctx, m.p), m.p = nullptr;
+    if (m.p) itn_tensor_free(net->ctx, m);
   itn_fast_release(net);
   itn_dist_release(net);
 }
@@ -573,8 +587,8 @@ extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
   std::unique_ptr<itn_net> net(new itn_net(*src));
   net->fast = nullptr;
   net->dist = nullptr;
-  for (auto& t : net->T) t.p = nullptr;
-  for (auto& m : net->M) m.p = nullptr;
+  for (auto& t : net->T) t.p = nullptr, t.slab = nullptr;
+  for (auto& m : net->M) m.p = nullptr, m.slab = nullptr;
   const int P = src->planes();
   for (int v = 0; v < src->nv; ++v)
     if (src->T[v].p) {
@@ -663,7 +677,7 @@ extern "C" int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd,
   const long long n = net->tensor_elems(v);
   const int P = net->planes();
   if (!net->T[v].p || net->T[v].n != n) {
-    if (net->T[v].p) itn_dev_free(ctx, net->T[v].p);
+    if (net->T[v].p) itn_tensor_free(ctx, net->T[v]);
     net->T[v].p = (double*)itn_dev_alloc(ctx, (size_t)n * P * sizeof(double));
     net->T[v].n = n;
   }

@@ -120,11 +120,11 @@ __device__ __forceinline__ void store_acc(double* __restrict__ Z, const double (
 }
 
 struct FastArgs {
-  const double* X;          // tile-major site tensors (F1 or F2)
-  const double* P;          // partially absorbed tensors (same indexing as X), or null
-  double* W;                // output of M_L^T X M_R, written in the *other* tile layout, or null
-  double* part;             // [nb][4][npart][TILE]
-  const double* const* msg; // [nb][4] incoming messages (planar, column-major)
+  const double* const* Xv;  // [n] per-vertex tile-major site tensor (F1 or F2 copy)
+  const double* const* Pv;  // [n] per-vertex partially absorbed tensor (same indexing as X), or null
+  double* const* Wv;        // [n] per-vertex output of M_L^T X M_R, written in the *other* tile layout, or null
+  double* part;             // [n][4][npart][TILE]
+  const double* const* msg; // [n][4] incoming messages (planar, column-major)
   int d;                    // site dimension
   int kL, kR;               // bond slots of the left / right index of the tiles
 };
@@ -141,19 +141,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
   double* Ps = MRs + TS;  // only when HAS_P
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
-  const int half = b & 1, q = (b >> 1) & 15, vs = b >> 5;
+  const int half = b & 1, q = (b >> 1) & 15;
   const int npart = 32 * a.d;
   const int vi = b / npart, pidx = b - vi * npart;
-  const size_t cube = (((size_t)vs * 16 + q) * 16 + half * kTilesPerCta) * TILE;
+  const int s_site = pidx >> 5;
+  const size_t cube = (((size_t)s_site * 16 + q) * 16 + half * kTilesPerCta) * TILE;
 
   {
-    const double* gx = a.X + cube;
+    const double* gx = a.Xv[vi] + cube;
     for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
       const int w = i / (TILE / 2), r = i - w * (TILE / 2);
       cp_async16(Xs + w * TS + 2 * r, gx + 2 * i);
     }
     if (HAS_P) {
-      const double* gp = a.P + cube;
+      const double* gp = a.Pv[vi] + cube;
       for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
         const int w = i / (TILE / 2), r = i - w * (TILE / 2);
         cp_async16(Ps + w * TS + 2 * r, gp + 2 * i);
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
     const int w = tid & 7;
     const int c = half * kTilesPerCta + w;
     const int pos = swz(c, q);
-    double* wbase = a.W + (size_t)vs * 256 * TILE;
+    double* wbase = a.Wv[vi] + (size_t)s_site * 256 * TILE;
     for (int e = tid >> 3; e < TILE; e += kThreads / 8) {
       const int p = e >> 8, ij = e & 255, i = ij & 15, j = ij >> 4;
       wbase[((size_t)(j * 16 + i)) * TILE + p * 256 + pos] = Xs[w * TS + p * 256 + swz(i, j)];
@@ -309,12 +310,207 @@ __global__ void __launch_bounds__(256) k_fast_relayout_f2(const RelayoutJob* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bond environments for the simple update (apply.jl:33-95 restated in itn_linalg.cu):
+//   C[(s,l),(s',l')] = sum_{outer} B_s[outer, l] conj(A_s'[outer, l'])     B = A with the 3 other messages absorbed
+// Two of the three absorptions are the phase-1 kernel above (P12 or S34); this kernel absorbs the third
+// message on one index of the tile and closes over everything but the gate bond, for every (s, s') pair.
+//   side 0: gate bond = right index of the tile:  O = (M^T P_s)^T conj(X_s')
+//   side 1: gate bond = left index of the tile:   O = (P_s M) conj(X_s')^T
+// ------------------------------------------------------------------------------------------------
+struct BenvArgs {
+  const double* const* Xv;  // [n] tile-major site tensor (layout of the pair that contains the gate bond)
+  const double* const* Pv;  // [n] tensor with the other pair's two messages absorbed (same layout)
+  const double* const* Mv;  // [n] message on the partner bond of the gate bond (planar 16 x 16)
+  const int* side;          // [n]
+  double* part;             // [n][d*d][32][TILE]
+  int d;
+};
+
+template <bool C>
+__global__ void __launch_bounds__(kThreads, 2) k_benv(const BenvArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int TILE = C ? 512 : 256;
+  constexpr int TS = TILE + 2;
+  double* Xs = sm;
+  double* Ps = Xs + kTilesPerCta * TS;
+  double* Ss = Ps + kTilesPerCta * TS;
+  double* Ms = Ss + kTilesPerCta * TS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const int half = b & 1, q = (b >> 1) & 15;
+  const int rest = b >> 5;
+  const int dd = a.d * a.d;
+  const int j = rest / dd, ss = rest - j * dd;
+  const int s = ss % a.d, sp = ss / a.d;  // s: ket copy (P), sp: bra copy (X)
+  const int side = a.side[j];
+  {
+    const double* gp = a.Pv[j] + (((size_t)s * 16 + q) * 16 + half * kTilesPerCta) * TILE;
+    const double* gx = a.Xv[j] + (((size_t)sp * 16 + q) * 16 + half * kTilesPerCta) * TILE;
+    for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
+      const int w = i / (TILE / 2), r = i - w * (TILE / 2);
+      cp_async16(Xs + w * TS + 2 * r, gx + 2 * i);
+      cp_async16(Ps + w * TS + 2 * r, gp + 2 * i);
+    }
+    const double* m = a.Mv[j];
+    const int o = swz(tid & 15, tid >> 4);
+    Ms[o] = m[tid];
+    if (C) Ms[256 + o] = m[256 + tid];
+    cp_async_commit_wait_all();
+  }
+  __syncthreads();
+  double* X = Xs + warp * TS;
+  double* S = Ss + warp * TS;
+  double* P = Ps + warp * TS;
+  double cre[2][4], cim[2][4];
+  zero_acc<C>(cre, cim);
+  if (side == 0) {
+    tile_mm<C, true, false, false>(Ms, P, cre, cim, lane);  // T = M^T P
+    store_acc<C>(S, cre, cim, lane);
+    __syncwarp();
+    zero_acc<C>(cre, cim);
+    tile_mm<C, true, false, true>(S, X, cre, cim, lane);    // O[l,l'] = sum_k T[k,l] conj(X[k,l'])
+  } else {
+    tile_mm<C, false, false, false>(P, Ms, cre, cim, lane); // U = P M
+    store_acc<C>(S, cre, cim, lane);
+    __syncwarp();
+    zero_acc<C>(cre, cim);
+    tile_mm<C, false, true, true>(S, X, cre, cim, lane);    // O[a,a''] = sum_k U[a,k] conj(X[a'',k])
+  }
+  __syncwarp();
+  store_acc<C>(S, cre, cim, lane);
+  __syncthreads();
+  double* pr = a.part + (((size_t)j * dd + ss) * 32 + (q * 2 + half)) * TILE;
+  for (int o = tid; o < TILE; o += kThreads) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTilesPerCta; ++w) acc += Ss[w * TS + o];
+    pr[o] = acc;
+  }
+}
+
+// C[(s + d l) + n (s' + d l')] = sum over the 32 per-CTA partials, un-swizzled; n = 16 d
+template <bool C>
+__global__ void __launch_bounds__(256) k_benv_reduce(const double* __restrict__ part, double* const* __restrict__ Cout, int d) {
+  constexpr int TILE = C ? 512 : 256;
+  const int dd = d * d;
+  const int j = blockIdx.x / dd, ss = blockIdx.x - j * dd;
+  const int s = ss % d, sp = ss / d;
+  const double* p = part + (size_t)blockIdx.x * 32 * TILE;
+  const int tid = threadIdx.x, l = tid & 15, lp = tid >> 4;
+  const int o = swz(l, lp);
+  double sr = 0.0, si = 0.0;
+  for (int i = 0; i < 32; ++i) {
+    sr += p[(size_t)i * TILE + o];
+    if (C) si += p[(size_t)i * TILE + 256 + o];
+  }
+  const int n = 16 * d;
+  double* out = Cout[j];
+  const size_t idx = (size_t)(s + d * l) + (size_t)n * (sp + d * lp);
+  out[idx] = sr;
+  if (C) out[(size_t)n * n + idx] = si;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rebuild after the gate: A'[.., s', l'] = sum_{s,l} A[.., s, l] T[(s,l),(s',l')] on tiles, d = 2 only
+//   side 0 (gate bond = right index):  out_s' = sum_s X_s T_ss'        side 1 (left index):  out_s' = sum_s T_ss'^T X_s
+// with T_ss'[l,l'] = T[(s + d l) + n (s' + d l')], zero padded to 16 columns.  The result is written straight
+// into the canonical layout of the new tensor (bond extent chi' <= 16).
+// ------------------------------------------------------------------------------------------------
+struct RebJob {
+  const double* X;   // tile-major old tensor (layout of the pair containing the gate bond)
+  const double* T;   // planar n x (d chi'), n = 16 d
+  double* out;       // canonical planar new tensor
+  long long n_out;   // elements of the new tensor (offset of its imaginary plane)
+  long long stI, stJ, stC, stQ;  // canonical strides of the tile's left / right index, the tile index and the CTA index
+  int side, chi_new, inner_is_c;  // inner_is_c: the tile index c is the fastest bond (F2 tiles), else the left index is
+};
+
+template <bool C>
+__global__ void __launch_bounds__(kThreads, 2) k_rebuild(const RebJob* __restrict__ jobs) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int TILE = C ? 512 : 256;
+  constexpr int TS = TILE + 2;
+  constexpr int D = 2;
+  double* Xs = sm;                          // [D][8] tiles, overwritten by the outputs
+  double* Ts = Xs + D * kTilesPerCta * TS;  // [D*D] blocks
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const int half = b & 1, q = (b >> 1) & 15, j = b >> 5;
+  const RebJob J = jobs[j];
+  for (int s = 0; s < D; ++s) {
+    const double* gx = J.X + (((size_t)s * 16 + q) * 16 + half * kTilesPerCta) * TILE;
+    for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
+      const int w = i / (TILE / 2), r = i - w * (TILE / 2);
+      cp_async16(Xs + (s * kTilesPerCta + w) * TS + 2 * r, gx + 2 * i);
+    }
+  }
+  {
+    const int n = 16 * D, ncol = D * J.chi_new;
+    const long long tplane = (long long)n * ncol;
+    const int l = tid & 15, lp = tid >> 4;
+    const int o = swz(l, lp);
+    for (int ss = 0; ss < D * D; ++ss) {
+      const int s = ss % D, sp = ss / D;
+      const bool ok = lp < J.chi_new;
+      const long long ti = (long long)(s + D * l) + (long long)n * (sp + D * lp);
+      Ts[ss * TS + o] = ok ? J.T[ti] : 0.0;
+      if (C) Ts[ss * TS + 256 + o] = ok ? J.T[tplane + ti] : 0.0;
+    }
+  }
+  cp_async_commit_wait_all();
+  __syncthreads();
+  double acc[D][2][2][4];  // [s'][re/im][nb][v]
+#pragma unroll
+  for (int sp = 0; sp < D; ++sp) {
+    zero_acc<C>(acc[sp][0], acc[sp][1]);
+#pragma unroll
+    for (int s = 0; s < D; ++s) {
+      const double* X = Xs + (s * kTilesPerCta + warp) * TS;
+      const double* Tb = Ts + (s + D * sp) * TS;
+      if (J.side == 0) tile_mm<C, false, false, false>(X, Tb, acc[sp][0], acc[sp][1], lane);
+      else tile_mm<C, true, false, false>(Tb, X, acc[sp][0], acc[sp][1], lane);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int sp = 0; sp < D; ++sp) store_acc<C>(Xs + (sp * kTilesPerCta + warp) * TS, acc[sp][0], acc[sp][1], lane);
+  __syncthreads();
+  // coalesced write-out: s' fastest, then the fastest bond of the canonical layout
+  const int total = kTilesPerCta * D * 256;
+  for (int e = tid; e < total; e += kThreads) {
+    const int sp = e % D;
+    int w, i, jj;
+    if (J.inner_is_c) {
+      w = (e / D) % kTilesPerCta;
+      const int r = e / (D * kTilesPerCta);
+      i = r & 15;
+      jj = r >> 4;
+    } else {
+      i = (e / D) & 15;
+      const int r = e / (D * 16);
+      jj = r & 15;
+      w = r >> 4;
+    }
+    if ((J.side == 0 ? jj : i) >= J.chi_new) continue;
+    const int c = half * kTilesPerCta + w;
+    const long long off = sp + J.stI * i + J.stJ * jj + J.stC * c + J.stQ * q;
+    const double* src = Xs + (sp * kTilesPerCta + w) * TS + swz(i, jj);
+    J.out[off] = src[0];
+    if (C) J.out[J.n_out + off] = src[256];
+  }
+}
+
 struct FastCache {
   uint64_t topo_version = ~0ull;
   int nb = 0, d = 0;
-  std::vector<int> verts;       // bucket members
-  std::vector<int> vslot;       // vertex -> bucket index or -1
+  std::vector<int> verts;  // bucket members: every degree-4, chi = 16 vertex stored on this rank
+  std::vector<int> vslot;  // vertex -> bucket index or -1
   double *F1 = nullptr, *F2 = nullptr, *P12 = nullptr, *S34 = nullptr, *part = nullptr;
+  size_t vstride = 0;      // doubles per vertex in F1/F2/P12/S34
+  // current BP sweep
+  std::vector<int> sweep;  // bucket indices taking part
+  const double** d_tab = nullptr;  // 4 pointer tables of nb entries: F1, F2, P12, S34 of the sweep's vertices
   const double** d_msg = nullptr;
   double** d_staged = nullptr;
 };
@@ -322,97 +518,104 @@ struct FastCache {
 void release(itn_net* net, FastCache* fc) {
   itn_ctx* ctx = net->ctx;
   for (double* p : {fc->F1, fc->F2, fc->P12, fc->S34, fc->part}) itn_dev_free(ctx, p);
+  itn_dev_free(ctx, (void*)fc->d_tab);
   itn_dev_free(ctx, (void*)fc->d_msg);
   itn_dev_free(ctx, (void*)fc->d_staged);
   fc->F1 = fc->F2 = fc->P12 = fc->S34 = fc->part = nullptr;
+  fc->d_tab = nullptr;
   fc->d_msg = nullptr;
   fc->d_staged = nullptr;
   fc->nb = 0;
   fc->verts.clear();
 }
 
-template <bool C, bool HAS_P, bool DO_W>
-void launch_phase(itn_net* net, const FastCache* fc, const FastArgs& a) {
+template <bool C>
+size_t fast_smem(bool has_p) {
   constexpr int TILE = C ? 512 : 256;
-  // X, scratch, 2 messages (+P)
-  size_t smem = (size_t)(2 * kTilesPerCta + 2) * (TILE + 2) * sizeof(double);
-  if (HAS_P) smem += (size_t)kTilesPerCta * (TILE + 2) * sizeof(double);
+  return (size_t)((has_p ? 3 : 2) * kTilesPerCta + 2) * (TILE + 2) * sizeof(double);
+}
+
+template <bool C, bool HAS_P, bool DO_W>
+void launch_phase(itn_net* net, int nverts, const FastArgs& a) {
+  const size_t smem = fast_smem<C>(HAS_P);
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(k_fast<C, HAS_P, DO_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_fast<C, HAS_P, DO_W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  const unsigned grid = (unsigned)fc->nb * fc->d * 32;
+  const unsigned grid = (unsigned)nverts * a.d * 32;
   k_fast<C, HAS_P, DO_W><<<grid, kThreads, smem, net->ctx->stream>>>(a);
   ITN_LAUNCH_CHECK(net->ctx);
 }
 
 template <bool C>
 void sweep(itn_net* net, FastCache* fc) {
+  const int ns = (int)fc->sweep.size();
+  const double* const* tF1 = fc->d_tab;
+  const double* const* tF2 = fc->d_tab + fc->nb;
+  const double* const* tP12 = fc->d_tab + 2 * (size_t)fc->nb;
+  const double* const* tS34 = fc->d_tab + 3 * (size_t)fc->nb;
   FastArgs a;
   a.msg = fc->d_msg;
   a.part = fc->part;
   a.d = fc->d;
   // phase 1: P12 = M1^T X M2 on F1 tiles
-  a.X = fc->F1; a.P = nullptr; a.W = fc->P12; a.kL = 0; a.kR = 1;
-  launch_phase<C, false, true>(net, fc, a);
+  a.Xv = tF1; a.Pv = nullptr; a.Wv = (double* const*)tP12; a.kL = 0; a.kR = 1;
+  launch_phase<C, false, true>(net, ns, a);
   // phase 2: out4 / out3 from P12 and F2 tiles; S34 = M3^T X M4
-  a.X = fc->F2; a.P = fc->P12; a.W = fc->S34; a.kL = 2; a.kR = 3;
-  launch_phase<C, true, true>(net, fc, a);
+  a.Xv = tF2; a.Pv = tP12; a.Wv = (double* const*)tS34; a.kL = 2; a.kR = 3;
+  launch_phase<C, true, true>(net, ns, a);
   // phase 3: out2 / out1 from S34 and F1 tiles
-  a.X = fc->F1; a.P = fc->S34; a.W = nullptr; a.kL = 0; a.kR = 1;
-  launch_phase<C, true, false>(net, fc, a);
-  k_fast_reduce<C><<<(unsigned)fc->nb * 4, 256, 0, net->ctx->stream>>>(fc->part, fc->d_staged, 32 * fc->d);
+  a.Xv = tF1; a.Pv = tS34; a.Wv = nullptr; a.kL = 0; a.kR = 1;
+  launch_phase<C, true, false>(net, ns, a);
+  k_fast_reduce<C><<<(unsigned)ns * 4, 256, 0, net->ctx->stream>>>(fc->part, fc->d_staged, 32 * fc->d);
   ITN_LAUNCH_CHECK(net->ctx);
 }
 
-}  // namespace
-
-void itn_fast_release(itn_net* net) {
-  if (!net->fast) return;
-  FastCache* fc = (FastCache*)net->fast;
-  release(net, fc);
-  delete fc;
-  net->fast = nullptr;
-}
-
-// Decide which message jobs the fast path computes: vertices of degree 4 whose four bonds all have
-// dimension 16, whose tensor is set and whose four outgoing messages are all part of this sweep.
-int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled) {
-  handled.assign(dids.size(), 0);
-  if (net->ctx->path_mode == 1) return 0;
-  std::vector<int> cnt(net->nv, 0);
-  for (size_t i = 0; i < dids.size(); ++i) cnt[srcv[i]]++;
+// (Re)builds the tile-major copies of every eligible vertex when the network changed.
+FastCache* ensure_cache(itn_net* net) {
+  if (net->ctx->path_mode == 1) return nullptr;
+  {
+    FastCache* cur = (FastCache*)net->fast;
+    if (cur && cur->nb > 0 && cur->topo_version == net->topo_version) return cur;
+  }
   std::vector<int> verts;
   int d = 0;
   for (int v = 0; v < net->nv; ++v) {
-    if (net->inc[v].size() != 4 || cnt[v] != 4 || !net->T[v].p) continue;
+    if (net->inc[v].size() != 4 || !net->T[v].p) continue;
     bool ok = true;
     for (int e : net->inc[v]) ok = ok && net->edim[e] == kChi;
     if (!ok) continue;
     if (d == 0) d = net->sdim[v];
-    if (net->sdim[v] != d) continue;
+    if (net->sdim[v] != d || d > 6) continue;
     verts.push_back(v);
   }
-  if (verts.empty()) return 0;
-  itn_ctx* ctx = net->ctx;
   FastCache* fc = (FastCache*)net->fast;
+  if (verts.empty()) {
+    if (fc) release(net, fc);
+    return nullptr;
+  }
+  itn_ctx* ctx = net->ctx;
   if (!fc) net->fast = fc = new FastCache();
   const int TILE = net->cplx ? 512 : 256;
   if (fc->topo_version != net->topo_version || fc->verts != verts) {
-    release(net, fc);
-    fc->verts = verts;
-    fc->nb = (int)verts.size();
-    fc->d = d;
-    const size_t tb = (size_t)fc->nb * d * 256 * TILE * sizeof(double);
-    fc->F1 = (double*)itn_dev_alloc(ctx, tb);
-    fc->F2 = (double*)itn_dev_alloc(ctx, tb);
-    fc->P12 = (double*)itn_dev_alloc(ctx, tb);
-    fc->S34 = (double*)itn_dev_alloc(ctx, tb);
-    fc->part = (double*)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * 32 * d * TILE * sizeof(double));
-    fc->d_msg = (const double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
-    fc->d_staged = (double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
+    if (fc->verts != verts || fc->d != d || !fc->F1) {  // same bucket (e.g. after a gate layer): keep the buffers
+      release(net, fc);
+      fc->verts = verts;
+      fc->nb = (int)verts.size();
+      fc->d = d;
+      fc->vstride = (size_t)d * 256 * TILE;
+      const size_t tb = (size_t)fc->nb * fc->vstride * sizeof(double);
+      fc->F1 = (double*)itn_dev_alloc(ctx, tb);
+      fc->F2 = (double*)itn_dev_alloc(ctx, tb);
+      fc->P12 = (double*)itn_dev_alloc(ctx, tb);
+      fc->S34 = (double*)itn_dev_alloc(ctx, tb);
+      fc->part = (double*)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * 32 * d * TILE * sizeof(double));
+      fc->d_tab = (const double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
+      fc->d_msg = (const double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
+      fc->d_staged = (double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
+    }
     std::vector<RelayoutJob> jobs(fc->nb);
     for (int i = 0; i < fc->nb; ++i) jobs[i] = {net->T[verts[i]].p, net->T[verts[i]].n};
     DevBuf jb(ctx, jobs.size() * sizeof(RelayoutJob));
@@ -432,15 +635,56 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
     }
     ITN_LAUNCH_CHECK(ctx);
     fc->topo_version = net->topo_version;
+    fc->vslot.assign(net->nv, -1);
+    for (int i = 0; i < fc->nb; ++i) fc->vslot[verts[i]] = i;
   }
-  fc->vslot.assign(net->nv, -1);
-  for (int i = 0; i < fc->nb; ++i) fc->vslot[verts[i]] = i;
+  return fc;
+}
+
+}  // namespace
+
+void itn_fast_release(itn_net* net) {
+  if (!net->fast) return;
+  FastCache* fc = (FastCache*)net->fast;
+  release(net, fc);
+  delete fc;
+  net->fast = nullptr;
+}
+
+// Decide which message jobs the fast path computes: vertices of degree 4 whose four bonds all have
+// dimension 16, whose tensor is set and whose four outgoing messages are all part of this sweep.
+int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled) {
+  handled.assign(dids.size(), 0);
+  FastCache* fc = ensure_cache(net);
+  if (!fc) return 0;
+  itn_ctx* ctx = net->ctx;
+  std::vector<int> cnt(net->nv, 0);
+  for (size_t i = 0; i < dids.size(); ++i) cnt[srcv[i]]++;
+  fc->sweep.clear();
+  std::vector<int> rank_in_sweep(fc->nb, -1);
+  for (int i = 0; i < fc->nb; ++i)
+    if (cnt[fc->verts[i]] == 4) {
+      rank_in_sweep[i] = (int)fc->sweep.size();
+      fc->sweep.push_back(i);
+    }
+  if (fc->sweep.empty()) return 0;
+  std::vector<const double*> tab((size_t)fc->nb * 4, nullptr);
+  for (size_t r = 0; r < fc->sweep.size(); ++r) {
+    const size_t off = (size_t)fc->sweep[r] * fc->vstride;
+    tab[r] = fc->F1 + off;
+    tab[fc->nb + r] = fc->F2 + off;
+    tab[2 * (size_t)fc->nb + r] = fc->P12 + off;
+    tab[3 * (size_t)fc->nb + r] = fc->S34 + off;
+  }
+  CUDA_CHECK(cudaMemcpyAsync((void*)fc->d_tab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
   int n = 0;
-  for (size_t i = 0; i < dids.size(); ++i)
-    if (fc->vslot[srcv[i]] >= 0) {
+  for (size_t i = 0; i < dids.size(); ++i) {
+    const int slot = fc->vslot[srcv[i]];
+    if (slot >= 0 && rank_in_sweep[slot] >= 0) {
       handled[i] = 1;
       ++n;
     }
+  }
   return n;
 }
 
@@ -448,26 +692,168 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
 void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
                        const std::vector<char>& handled, double* const* staged) {
   FastCache* fc = (FastCache*)net->fast;
-  ITN_REQUIRE(fc && fc->nb > 0, ITN_EINVAL, "fast path is not prepared");
+  ITN_REQUIRE(fc && !fc->sweep.empty(), ITN_EINVAL, "fast path is not prepared");
   itn_ctx* ctx = net->ctx;
-  std::vector<const double*> msg((size_t)fc->nb * 4, nullptr);
-  std::vector<double*> st((size_t)fc->nb * 4, nullptr);
-  for (int i = 0; i < fc->nb; ++i) {
-    const int v = fc->verts[i];
+  const size_t ns = fc->sweep.size();
+  std::vector<const double*> msg(ns * 4, nullptr);
+  std::vector<double*> st(ns * 4, nullptr);
+  std::vector<int> rank_in_sweep(fc->nb, -1);
+  for (size_t r = 0; r < ns; ++r) {
+    rank_in_sweep[fc->sweep[r]] = (int)r;
+    const int v = fc->verts[fc->sweep[r]];
     for (int k = 0; k < 4; ++k) {
       const DevTensor& m = net->M[net->msg_into(v, net->inc[v][k])];
       ITN_REQUIRE(m.p != nullptr, ITN_EINVAL, "an incoming message is not set");
-      msg[(size_t)i * 4 + k] = m.p;
+      msg[r * 4 + k] = m.p;
     }
   }
   for (size_t i = 0; i < dids.size(); ++i) {
     if (!handled[i]) continue;
     const int v = srcv[i];
     const int k = net->slot(v, dids[i] / 2);
-    st[(size_t)fc->vslot[v] * 4 + k] = staged[i];
+    st[(size_t)rank_in_sweep[fc->vslot[v]] * 4 + k] = staged[i];
   }
   CUDA_CHECK(cudaMemcpyAsync((void*)fc->d_msg, msg.data(), msg.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaMemcpyAsync((void*)fc->d_staged, st.data(), st.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
   if (net->cplx) sweep<true>(net, fc);
   else sweep<false>(net, fc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// simple-update helpers on the tile path (called from itn_linalg.cu)
+// ------------------------------------------------------------------------------------------------
+bool itn_fast_gate_site_ok(itn_net* net, int v) {
+  FastCache* fc = ensure_cache(net);
+  return fc && fc->d == 2 && fc->vslot[v] >= 0;
+}
+
+// Bond environments C (n x n planar, n = 16 d) of the listed (vertex, bond slot) pairs; mats[j][slot] are the
+// (hermitised) incoming messages to absorb.
+void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs) {
+  if (jobs.empty()) return;
+  FastCache* fc = ensure_cache(net);
+  ITN_REQUIRE(fc, ITN_EINVAL, "tile path is not available");
+  itn_ctx* ctx = net->ctx;
+  const int d = fc->d, TILE = net->cplx ? 512 : 256;
+  const size_t nj = jobs.size();
+  // phase-1 pass per group: slots 2,3 need P12 (X = F1, messages 0,1); slots 0,1 need S34 (X = F2, messages 2,3)
+  for (int grp = 0; grp < 2; ++grp) {
+    std::vector<const double*> xv, wv, msg;
+    for (const FastBenvJob& J : jobs) {
+      if ((J.slot >= 2) != (grp == 0)) continue;
+      const size_t off = (size_t)fc->vslot[J.v] * fc->vstride;
+      xv.push_back((grp == 0 ? fc->F1 : fc->F2) + off);
+      wv.push_back((grp == 0 ? fc->P12 : fc->S34) + off);
+      for (int k = 0; k < 4; ++k) msg.push_back(J.mats[k] ? J.mats[k] : net->M[net->msg_into(J.v, net->inc[J.v][k])].p);
+    }
+    if (xv.empty()) continue;
+    const size_t n = xv.size();
+    DevBuf tb(ctx, (2 * n + msg.size()) * sizeof(double*));
+    std::vector<const double*> all(xv);
+    all.insert(all.end(), wv.begin(), wv.end());
+    all.insert(all.end(), msg.begin(), msg.end());
+    const double** dt = (const double**)itn_upload(ctx, all, tb);
+    FastArgs a;
+    a.Xv = dt;
+    a.Pv = nullptr;
+    a.Wv = (double* const*)(dt + n);
+    a.msg = dt + 2 * n;
+    a.part = nullptr;
+    a.d = d;
+    a.kL = grp == 0 ? 0 : 2;
+    a.kR = grp == 0 ? 1 : 3;
+    if (net->cplx) launch_phase<true, false, true>(net, (int)n, a);
+    else launch_phase<false, false, true>(net, (int)n, a);
+  }
+  // close pass
+  std::vector<const double*> tabs;
+  std::vector<int> side(nj);
+  for (const FastBenvJob& J : jobs) tabs.push_back((J.slot >= 2 ? fc->F2 : fc->F1) + (size_t)fc->vslot[J.v] * fc->vstride);
+  for (const FastBenvJob& J : jobs) tabs.push_back((J.slot >= 2 ? fc->P12 : fc->S34) + (size_t)fc->vslot[J.v] * fc->vstride);
+  for (size_t j = 0; j < nj; ++j) {
+    const FastBenvJob& J = jobs[j];
+    const int partner = J.slot ^ 1;  // the other bond of the pair (0,1) or (2,3)
+    tabs.push_back(J.mats[partner] ? J.mats[partner] : net->M[net->msg_into(J.v, net->inc[J.v][partner])].p);
+    side[j] = (J.slot & 1) ? 0 : 1;  // odd slot = right index of the tile
+  }
+  for (const FastBenvJob& J : jobs) tabs.push_back(J.C);
+  DevBuf tb(ctx, tabs.size() * sizeof(double*)), sb(ctx, nj * sizeof(int));
+  const double** dt = (const double**)itn_upload(ctx, tabs, tb);
+  const int* ds = itn_upload(ctx, side, sb);
+  DevBuf part(ctx, nj * d * d * 32 * TILE * sizeof(double));
+  BenvArgs b;
+  b.Xv = dt;
+  b.Pv = dt + nj;
+  b.Mv = dt + 2 * nj;
+  b.side = ds;
+  b.part = part.as<double>();
+  b.d = d;
+  const unsigned grid = (unsigned)(nj * d * d * 32);
+  if (net->cplx) {
+    const size_t smem = (size_t)(3 * kTilesPerCta + 1) * (512 + 2) * sizeof(double);
+    CUDA_CHECK(cudaFuncSetAttribute(k_benv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_benv<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    k_benv<true><<<grid, kThreads, smem, ctx->stream>>>(b);
+    ITN_LAUNCH_CHECK(ctx);
+    k_benv_reduce<true><<<(unsigned)(nj * d * d), 256, 0, ctx->stream>>>(part.as<double>(), (double* const*)(dt + 3 * nj), d);
+  } else {
+    const size_t smem = (size_t)(3 * kTilesPerCta + 1) * (256 + 2) * sizeof(double);
+    CUDA_CHECK(cudaFuncSetAttribute(k_benv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_benv<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    k_benv<false><<<grid, kThreads, smem, ctx->stream>>>(b);
+    ITN_LAUNCH_CHECK(ctx);
+    k_benv_reduce<false><<<(unsigned)(nj * d * d), 256, 0, ctx->stream>>>(part.as<double>(), (double* const*)(dt + 3 * nj), d);
+  }
+  ITN_LAUNCH_CHECK(ctx);
+}
+
+// New site tensors after the gate: out (canonical layout, bond `slot` now chi_new <= 16) = A . T on the fused (s, l) index.
+void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs) {
+  if (jobs.empty()) return;
+  FastCache* fc = ensure_cache(net);
+  ITN_REQUIRE(fc && fc->d == 2, ITN_EINVAL, "tile path is not available");
+  itn_ctx* ctx = net->ctx;
+  std::vector<RebJob> rj(jobs.size());
+  for (size_t j = 0; j < jobs.size(); ++j) {
+    const FastRebuildJob& J = jobs[j];
+    ITN_REQUIRE(J.chi_new >= 1 && J.chi_new <= kChi, ITN_EINVAL, "tile rebuild needs chi_new <= 16");
+    long long dims[4] = {kChi, kChi, kChi, kChi}, st[4];
+    dims[J.slot] = J.chi_new;
+    long long acc = fc->d;
+    for (int k = 0; k < 4; ++k) {
+      st[k] = acc;
+      acc *= dims[k];
+    }
+    RebJob& R = rj[j];
+    const size_t off = (size_t)fc->vslot[J.v] * fc->vstride;
+    R.T = J.T;
+    R.out = J.out;
+    R.n_out = acc;
+    R.chi_new = J.chi_new;
+    R.side = (J.slot & 1) ? 0 : 1;
+    if (J.slot >= 2) {  // F2 tiles: (i, j) = (a3, a4), c = a1, q = a2
+      R.X = fc->F2 + off;
+      R.stI = st[2]; R.stJ = st[3]; R.stC = st[0]; R.stQ = st[1];
+      R.inner_is_c = 1;
+    } else {            // F1 tiles: (i, j) = (a1, a2), c = a3, q = a4
+      R.X = fc->F1 + off;
+      R.stI = st[0]; R.stJ = st[1]; R.stC = st[2]; R.stQ = st[3];
+      R.inner_is_c = 0;
+    }
+  }
+  DevBuf jb(ctx, rj.size() * sizeof(RebJob));
+  const RebJob* dj = itn_upload(ctx, rj, jb);
+  const unsigned grid = (unsigned)jobs.size() * 32;
+  if (net->cplx) {
+    const size_t smem = (size_t)(2 * kTilesPerCta + 4) * (512 + 2) * sizeof(double);
+    CUDA_CHECK(cudaFuncSetAttribute(k_rebuild<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_rebuild<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    k_rebuild<true><<<grid, kThreads, smem, ctx->stream>>>(dj);
+  } else {
+    const size_t smem = (size_t)(2 * kTilesPerCta + 4) * (256 + 2) * sizeof(double);
+    CUDA_CHECK(cudaFuncSetAttribute(k_rebuild<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_rebuild<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    k_rebuild<false><<<grid, kThreads, smem, ctx->stream>>>(dj);
+  }
+  ITN_LAUNCH_CHECK(ctx);
 }

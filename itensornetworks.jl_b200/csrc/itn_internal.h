@@ -48,9 +48,15 @@ struct itn_ctx {
 };
 
 // Planar storage: re plane [0, n), im plane [n, 2n) (complex only).
+// Several tensors created by one batched call (a gate layer) share one device allocation.
+struct DevSlab {
+  void* base = nullptr;
+  int refs = 0;
+};
 struct DevTensor {
   double* p = nullptr;
   int64_t n = 0;
+  DevSlab* slab = nullptr;  // null: p is its own allocation
 };
 
 // One step of a mode-product chain: out[l, b, r] = sum_a in[l, a, r] * m(a, b)
@@ -124,6 +130,8 @@ struct itn_net {
 // ---- device memory helpers (stream ordered) ----
 void* itn_dev_alloc(itn_ctx* ctx, size_t bytes);
 void itn_dev_free(itn_ctx* ctx, void* p);
+// releases the storage of t (its own allocation, or one reference on its slab) and clears it
+void itn_tensor_free(itn_ctx* ctx, DevTensor& t);
 
 struct DevBuf {  // RAII scratch buffer
   itn_ctx* ctx;
@@ -172,6 +180,20 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
 void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
                        const std::vector<char>& handled, double* const* staged);
 void itn_fast_release(itn_net* net);
+// simple update on the tile path (degree 4, all bonds 16, d = 2): bond environments and the rebuild A . T
+struct FastBenvJob {
+  int v, slot;                 // vertex and bond slot of the gate bond
+  const double* const* mats;   // [4] messages to absorb per slot (nullptr: the network's own), device planar
+  double* C;                   // out: planar n x n, n = 16 d, C[(s + d l) + n (s' + d l')]
+};
+struct FastRebuildJob {
+  int v, slot, chi_new;
+  const double* T;             // planar n x (d chi_new)
+  double* out;                 // new tensor, canonical planar
+};
+bool itn_fast_gate_site_ok(itn_net* net, int v);
+void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs);
+void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs);
 
 // ---- multi-GPU (itn_dist.cu) ----
 bool itn_is_local(const itn_net* net, int v);

@@ -50,14 +50,16 @@ struct SvdJob {
   int m, n;
 };
 
-constexpr int kSvdThreads = 256;
-constexpr int kSvdMaxSweeps = 40;
+constexpr int kSvdMaxThreads = 1024;
+constexpr int kSvdMaxSweeps = 30;
 
+// Block size: one warp per column pair of a round when possible (n/2 pairs), 4..32 warps.
 template <bool C>
-__global__ void __launch_bounds__(kSvdThreads) k_jacobi_svd(const SvdJob* __restrict__ jobs, int smem_doubles) {
+__global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __restrict__ jobs, int smem_doubles) {
   extern __shared__ double sm[];
   __shared__ int s_rot;
-  __shared__ double s_norm[256];
+  __shared__ double s_norm[256];  // squared column norms, kept up to date across rotations
+  __shared__ double s_red[33];
   const SvdJob J = jobs[blockIdx.x];
   const int m = J.m, n = J.n;
   if (n == 0 || m == 0) return;
@@ -68,36 +70,38 @@ __global__ void __launch_bounds__(kSvdThreads) k_jacobi_svd(const SvdJob* __rest
   double* Ai = C ? (in_smem ? sm + mn : J.a + mn) : nullptr;
   double* Vr = in_smem ? sm + P * mn : J.v;
   double* Vi = C ? (in_smem ? sm + P * mn + nn : J.v + nn) : nullptr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSvdThreads >> 5;
+  const int nthreads = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
   if (in_smem)
-    for (long long i = tid; i < mn * P; i += kSvdThreads) sm[i] = J.a[i];
-  for (long long i = tid; i < nn; i += kSvdThreads) {
+    for (long long i = tid; i < mn * P; i += nthreads) sm[i] = J.a[i];
+  for (long long i = tid; i < nn; i += nthreads) {
     Vr[i] = (i % n == i / n) ? 1.0 : 0.0;
     if (C) Vi[i] = 0.0;
   }
   __syncthreads();
+  // squared column norms
+  for (int j = warp; j < n; j += nwarps) {
+    double a2 = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const double r = Ar[(long long)j * m + i], im = C ? Ai[(long long)j * m + i] : 0.0;
+      a2 += r * r + im * im;
+    }
+    a2 = wsum(a2);
+    if (lane == 0) s_norm[j] = a2;
+  }
+  __syncthreads();
   // columns whose norm is below ~1e-19 ||A||_F are numerically null: rotating them only amplifies underflow
   // noise (they appear whenever rank(A) < n, e.g. wide matrices and rank-deficient Gram matrices)
-  {
-    double f2 = 0.0;
-    for (long long i = tid; i < mn; i += kSvdThreads) {
-      f2 += Ar[i] * Ar[i];
-      if (C) f2 += Ai[i] * Ai[i];
-    }
-    f2 = wsum(f2);
-    if (lane == 0) s_norm[warp] = f2;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < nwarps; ++w) t += s_norm[w];
-      s_norm[255] = t * (2.220446049250313e-19 * 2.220446049250313e-19);
-    }
-    __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int j = 0; j < n; ++j) t += s_norm[j];
+    s_red[32] = t * (2.220446049250313e-19 * 2.220446049250313e-19);
   }
-  const double tiny = s_norm[255];
   __syncthreads();
+  const double tiny = s_red[32];
   const int ne = n + (n & 1);  // even number of players; index n (if any) is a bye
-  const double tol = 4.0 * 2.220446049250313e-16;
+  // rotate while |<a_p, a_q>| > tol |a_p| |a_q|; sqrt(m) eps is the rounding level of the inner product (as in LAPACK xGESVJ)
+  const double tol = sqrt((double)m) * 2.220446049250313e-16;
   for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
     if (tid == 0) s_rot = 0;
     __syncthreads();
@@ -117,41 +121,44 @@ __global__ void __launch_bounds__(kSvdThreads) k_jacobi_svd(const SvdJob* __rest
           p = q;
           q = t;
         }
+        const double alpha = s_norm[p], beta = s_norm[q];
+        if (alpha <= tiny || beta <= tiny) continue;
         double* apr = Ar + (long long)p * m;
         double* aqr = Ar + (long long)q * m;
         double* api = C ? Ai + (long long)p * m : nullptr;
         double* aqi = C ? Ai + (long long)q * m : nullptr;
-        double alpha = 0, beta = 0, gr = 0, gi = 0;
+        double gr = 0, gi = 0;
         for (int i = lane; i < m; i += 32) {
           const double pr = apr[i], qr = aqr[i];
           const double pi = C ? api[i] : 0.0, qi = C ? aqi[i] : 0.0;
-          alpha += pr * pr + pi * pi;
-          beta += qr * qr + qi * qi;
           gr += pr * qr + pi * qi;  // conj(a_p) . a_q
           gi += pr * qi - pi * qr;
         }
-        alpha = wsum(alpha);
-        beta = wsum(beta);
         gr = wsum(gr);
         gi = C ? wsum(gi) : 0.0;
         const double g2 = gr * gr + gi * gi;
-        if (g2 == 0.0 || alpha <= tiny || beta <= tiny || !(g2 > tol * tol * alpha * beta)) continue;
+        if (g2 == 0.0 || !(g2 > tol * tol * alpha * beta)) continue;
         const double gabs = sqrt(g2);
         // phase e^{-i phi} applied to column q so that the inner product becomes real positive
         const double er = gr / gabs, ei = -gi / gabs;
         const double zeta = (beta - alpha) / (2.0 * gabs);
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        double na = 0.0, nb = 0.0;
         for (int i = lane; i < m; i += 32) {
           const double pr = apr[i], qr0 = aqr[i];
           const double pi = C ? api[i] : 0.0, qi0 = C ? aqi[i] : 0.0;
           const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
-          apr[i] = c * pr - s * qr;
-          aqr[i] = s * pr + c * qr;
+          const double npr = c * pr - s * qr, nqr = s * pr + c * qr;
+          const double npi = C ? c * pi - s * qi : 0.0, nqi = C ? s * pi + c * qi : 0.0;
+          apr[i] = npr;
+          aqr[i] = nqr;
           if (C) {
-            api[i] = c * pi - s * qi;
-            aqi[i] = s * pi + c * qi;
+            api[i] = npi;
+            aqi[i] = nqi;
           }
+          na += npr * npr + npi * npi;
+          nb += nqr * nqr + nqi * nqi;
         }
         double* vpr = Vr + (long long)p * n;
         double* vqr = Vr + (long long)q * n;
@@ -168,7 +175,14 @@ __global__ void __launch_bounds__(kSvdThreads) k_jacobi_svd(const SvdJob* __rest
             vqi[i] = s * pi + c * qi;
           }
         }
-        if (lane == 0) s_rot = 1;
+        na = wsum(na);
+        nb = wsum(nb);
+        if (lane == 0) {
+          s_norm[p] = na;  // recomputed, not updated by recurrence: no drift
+          s_norm[q] = nb;
+          // rotations at the rounding level of the inner product are applied but do not keep the iteration alive
+          if (g2 > 64.0 * tol * tol * alpha * beta) s_rot = 1;
+        }
       }
       __syncthreads();
     }
@@ -177,29 +191,19 @@ __global__ void __launch_bounds__(kSvdThreads) k_jacobi_svd(const SvdJob* __rest
     if (!any) break;
   }
   // singular values = column norms; stable descending order
-  for (int j = warp; j < n; j += nwarps) {
-    double a2 = 0.0;
-    for (int i = lane; i < m; i += 32) {
-      const double r = Ar[(long long)j * m + i], im = C ? Ai[(long long)j * m + i] : 0.0;
-      a2 += r * r + im * im;
-    }
-    a2 = wsum(a2);
-    if (lane == 0) s_norm[j] = sqrt(a2);
-  }
-  __syncthreads();
-  for (int j = tid; j < n; j += kSvdThreads) {
+  for (int j = tid; j < n; j += nthreads) {
     const double sj = s_norm[j];
     int rank = 0;
     for (int k = 0; k < n; ++k) {
       const double sk = s_norm[k];
       rank += (sk > sj) || (sk == sj && k < j);
     }
-    J.sigma[rank] = sj;
+    J.sigma[rank] = sqrt(sj);
     J.perm[rank] = j;
   }
   if (in_smem) {
-    for (long long i = tid; i < mn * P; i += kSvdThreads) J.a[i] = sm[i];
-    for (long long i = tid; i < nn * P; i += kSvdThreads) J.v[i] = sm[P * mn + i];
+    for (long long i = tid; i < mn * P; i += nthreads) J.a[i] = sm[i];
+    for (long long i = tid; i < nn * P; i += nthreads) J.v[i] = sm[P * mn + i];
   }
 }
 
@@ -213,14 +217,15 @@ void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
     need = std::max(need, ((size_t)j.m * j.n + (size_t)j.n * j.n) * (cplx ? 2 : 1));
   }
   size_t smem = std::min<size_t>(need * sizeof(double), 200 * 1024);
+  const int warps = std::min(32, std::max(4, (maxn + 1) / 2));
   DevBuf jb(ctx, jobs.size() * sizeof(SvdJob));
   const SvdJob* dj = itn_upload(ctx, jobs, jb);
   if (cplx) {
     CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_jacobi_svd<true><<<(unsigned)jobs.size(), kSvdThreads, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
+    k_jacobi_svd<true><<<(unsigned)jobs.size(), warps * 32, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
   } else {
     CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_jacobi_svd<false><<<(unsigned)jobs.size(), kSvdThreads, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
+    k_jacobi_svd<false><<<(unsigned)jobs.size(), warps * 32, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
   }
   ITN_LAUNCH_CHECK(ctx);
 }
@@ -854,6 +859,8 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   std::vector<std::vector<const double*>> overrides;  // per spec: matrices per bond slot
   overrides.reserve(2 * (size_t)n);
   std::vector<SvdJob> gj, tj;
+  std::vector<FastBenvJob> fast_env;
+  std::vector<char> fast_site(2 * (size_t)n, 0);
   std::vector<SuTrunc> tr(n);
   double* w = ws.as<double>();
   double* envp = envs.as<double>();
@@ -904,12 +911,18 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
         }
         envp += (size_t)P * c * c;
       }
-      JobSpec spx;
-      spx.v = v;
-      spx.open_mask = 1u | (1u << (g.k[s] + 1));
-      spx.out = Cm;
-      spx.mats = overrides.back().data();
-      specs.push_back(spx);
+      if (itn_fast_gate_site_ok(net, v)) {
+        // degree 4, all bonds 16, d = 2: bond environment on the DMMA tile path
+        fast_env.push_back({v, g.k[s], overrides.back().data(), Cm});
+        fast_site[2 * (size_t)i + s] = 1;
+      } else {
+        JobSpec spx;
+        spx.v = v;
+        spx.open_mask = 1u | (1u << (g.k[s] + 1));
+        spx.out = Cm;
+        spx.mats = overrides.back().data();
+        specs.push_back(spx);
+      }
     }
     E.gate = d_gates.as<double>() + goff[i] * P;
     E.theta = w; w += (size_t)P * g.m * g.nc;
@@ -935,6 +948,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     ITN_LAUNCH_CHECK(ctx);
   }
   itn_run_vertex_jobs(net, specs);
+  itn_fast_bond_envs(net, fast_env);
   run_jacobi(ctx, cplx, gj);
   if (!ej_svd.empty()) {
     // projector onto the support of every environment: eigenvalues below 10 eps (relative) are dropped, as in
@@ -1010,11 +1024,32 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   if (cplx) k_su_T<true><<<dim3(2 * n, 4), 256, 0, ctx->stream>>>(dse);
   else k_su_T<false><<<dim3(2 * n, 4), 256, 0, ctx->stream>>>(dse);
   ITN_LAUNCH_CHECK(ctx);
-  std::vector<SuSite> sites;
-  std::vector<double*> fresh;
+  std::vector<SuSite> sites, slow_sites;
+  std::vector<FastRebuildJob> fast_reb;
   std::vector<NormJob2> nj;
   long long maxn = 0;
+  // one allocation for all new site tensors of the layer, one for the new messages (shared, reference counted)
+  auto align32 = [](size_t x) { return (x + 31) & ~(size_t)31; };
+  size_t slab_doubles = 0, mslab_doubles = 0;
+  for (int i = 0; i < n; ++i)
+    for (int s = 0; s < 2; ++s) {
+      slab_doubles += align32((size_t)(net->T[geo[i].v[s]].n / geo[i].chi * newdim[i]) * P);
+      mslab_doubles += align32((size_t)newdim[i] * newdim[i] * P);
+    }
+  DevSlab* tslab = new DevSlab();
+  DevSlab* mslab = new DevSlab();
   try {
+    tslab->base = itn_dev_alloc(ctx, slab_doubles * sizeof(double));
+    mslab->base = itn_dev_alloc(ctx, mslab_doubles * sizeof(double));
+  } catch (...) {
+    if (tslab->base) itn_dev_free(ctx, tslab->base);
+    delete tslab;
+    delete mslab;
+    for (double* p : pscratch) itn_dev_free(ctx, p);
+    throw;
+  }
+  {
+    size_t toff = 0;
     for (int i = 0; i < n; ++i) {
       const Geo& g = geo[i];
       for (int s = 0; s < 2; ++s) {
@@ -1033,26 +1068,29 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
         for (int j = 0; j < g.k[s]; ++j) lo *= net->edim[net->inc[v][j]];
         S.lo = lo;
         S.hi = net->T[v].n / (lo * g.chi);
-        S.out = (double*)itn_dev_alloc(ctx, (size_t)S.n_new * P * sizeof(double));
-        fresh.push_back(S.out);
+        S.out = (double*)tslab->base + toff;
+        toff += align32((size_t)S.n_new * P);
         sites.push_back(S);
+        if (fast_site[2 * (size_t)i + s] && S.a == net->T[v].p && newdim[i] <= 16)
+          fast_reb.push_back({v, g.k[s], newdim[i], S.T, S.out});
+        else
+          slow_sites.push_back(S);
         nj.push_back({S.out, S.n_new * P});
         maxn = std::max(maxn, S.n_new);
       }
     }
-  } catch (...) {
-    for (double* p : fresh) itn_dev_free(ctx, p);
-    for (double* p : pscratch) itn_dev_free(ctx, p);
-    throw;
   }
   {
-    DevBuf sb(ctx, sites.size() * sizeof(SuSite));
-    const SuSite* ds = itn_upload(ctx, sites, sb);
-    unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + 255) / 256, 128));
-    while (gy > 1 && (unsigned long long)gy * sites.size() > 148ull * 32ull) gy = (gy + 1) / 2;
-    if (cplx) k_su_rebuild<true><<<dim3((unsigned)sites.size(), gy), 256, 0, ctx->stream>>>(ds);
-    else k_su_rebuild<false><<<dim3((unsigned)sites.size(), gy), 256, 0, ctx->stream>>>(ds);
-    ITN_LAUNCH_CHECK(ctx);
+    itn_fast_rebuild(net, fast_reb);
+    if (!slow_sites.empty()) {
+      DevBuf sb(ctx, slow_sites.size() * sizeof(SuSite));
+      const SuSite* ds = itn_upload(ctx, slow_sites, sb);
+      unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + 255) / 256, 128));
+      while (gy > 1 && (unsigned long long)gy * slow_sites.size() > 148ull * 32ull) gy = (gy + 1) / 2;
+      if (cplx) k_su_rebuild<true><<<dim3((unsigned)slow_sites.size(), gy), 256, 0, ctx->stream>>>(ds);
+      else k_su_rebuild<false><<<dim3((unsigned)slow_sites.size(), gy), 256, 0, ctx->stream>>>(ds);
+      ITN_LAUNCH_CHECK(ctx);
+    }
     if (normalize) {
       DevBuf nb(ctx, nj.size() * sizeof(NormJob2));
       const NormJob2* dn = itn_upload(ctx, nj, nb);
@@ -1063,22 +1101,27 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   for (double* p : pscratch) itn_dev_free(ctx, p);  // stream ordered: freed after the rebuild kernel
   // ---- 4. commit: swap tensors, new bond dimensions, reset the messages on the gated edges ----
   std::vector<DiagMsgJob> dj;
-  size_t si = 0;
+  size_t si = 0, moff = 0;
   for (int i = 0; i < n; ++i) {
     const Geo& g = geo[i];
     for (int s = 0; s < 2; ++s, ++si) {
       const int v = g.v[s];
-      itn_dev_free(ctx, net->T[v].p);
+      itn_tensor_free(ctx, net->T[v]);
       net->T[v].p = sites[si].out;
       net->T[v].n = sites[si].n_new;
+      net->T[v].slab = tslab;
+      tslab->refs++;
     }
     net->edim[g.e] = newdim[i];
     for (int dd = 0; dd < 2; ++dd) {
       DevTensor& m = net->M[2 * g.e + dd];
       const long long n2 = (long long)newdim[i] * newdim[i];
-      if (m.p) itn_dev_free(ctx, m.p);
-      m.p = (double*)itn_dev_alloc(ctx, (size_t)n2 * P * sizeof(double));
+      if (m.p) itn_tensor_free(ctx, m);
+      m.p = (double*)mslab->base + moff;
+      moff += align32((size_t)n2 * P);
       m.n = n2;
+      m.slab = mslab;
+      mslab->refs++;
       dj.push_back({m.p, msg_mode == 1 ? d_sv.as<double>() + (size_t)i * stride : nullptr, newdim[i]});
     }
   }

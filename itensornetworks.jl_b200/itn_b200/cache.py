@@ -435,18 +435,31 @@ def apply_layer(gates, bpc, pairs, maxdim=None, cutoff=None, normalize=False, ms
     gates[i][s1', s2', s1, s2] acts on pairs[i] = (v1, v2)."""
     g = bpc.graph
     eids, packed = [], []
+    memo = {}  # the same gate object on many edges (a Trotter layer) is packed once per orientation
     for gate, (v1, v2) in zip(gates, pairs):
-        e = g.eid[(v1, v2)]
-        gt = np.asarray(gate, dtype=bpc.dtype)
+        e = g.eid.get((v1, v2))
+        if e is None:
+            raise ITNError(1, "Vertices where the gates are being applied must be neighbors for now.")
         d1, d2 = bpc.sdims[v1], bpc.sdims[v2]
-        gt = gt.reshape(d1, d2, d1, d2)
-        if g.edges[e] != (v1, v2):  # engine orientation is (esrc, edst)
-            gt = gt.transpose(1, 0, 3, 2)
+        flip = g.edges[e] != (v1, v2)  # engine orientation is (esrc, edst)
+        key = (id(gate), d1, d2, flip)
+        if key not in memo:
+            gt = np.asarray(gate, dtype=bpc.dtype).reshape(d1, d2, d1, d2)
+            if flip:
+                gt = gt.transpose(1, 0, 3, 2)
+            memo[key] = np.asfortranarray(gt).ravel(order="F")
         eids.append(e)
-        packed.append(np.asfortranarray(gt).ravel(order="F"))
+        packed.append(memo[key])
     n = len(eids)
     packed = np.ascontiguousarray(np.concatenate(packed)) if n else np.zeros(0, dtype=bpc.dtype)
-    stride = max([bpc.sdims[g.edges[e][0]] * bpc.sdims[g.edges[e][1]] * bpc.edge_dim(e) * 4 for e in eids] + [1])
+    dmax = max(bpc.sdims) if bpc.sdims else 1
+    stride = 1
+    if n:
+        chis = {}
+        for e in eids:
+            if e not in chis:
+                chis[e] = bpc.edge_dim(e)
+        stride = max(dmax * dmax * c for c in chis.values())
     newdim = np.zeros(n, dtype=np.int32)
     terr = np.zeros(n, dtype=np.float64)
     sv = np.zeros((n, stride), dtype=np.float64)

@@ -180,3 +180,46 @@ def test_product_state_growth(ctx, dtype):
     assert rel_err(got["singular_values"], info["svals"][:2]) < TOL
     new = [out.factor(v) for v in range(g.nv)]
     assert rel_err(pair_tensor(new, g, 0), pair_tensor(ref.tensors, g, 0)) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("e,maxdim", [(17, 16), (18, 16), (17, 7), (18, 11), (8, 16), (4, 16)],
+                         ids=["interior_h", "interior_v", "interior_h_trunc7", "interior_v_trunc11", "mixed", "mixed2"])
+def test_apply2_dmma_tile_path(dtype, e, maxdim):
+    # degree-4, chi = 16, d = 2 sites take the DMMA tile kernels (k_fast phase 1 + k_benv + k_rebuild);
+    # the result must match the oracle AND the generic kernels.
+    g = O.grid_graph((4, 4))
+    net, psi = make_pair(g, 16, dtype)
+    c = E.Context(0)
+    msgs, bpc = bp_both(net, psi, c, 3)
+    v1, v2 = g.edges[e]
+    gate = O.random_unitary(4, seed=21, dtype=dtype).reshape(2, 2, 2, 2)
+    ref, info = O.simple_update_bp(net, msgs, e, gate, maxdim=maxdim, cutoff=1e-13)
+    got = {}
+    out = E.apply(gate, bpc, (v1, v2), maxdim=maxdim, cutoff=1e-13, callback=lambda **kw: got.update(kw))
+    assert out.edge_dim(e) == info["newdim"]
+    assert rel_err(got["singular_values"], info["svals"][:info["newdim"]]) < TOL
+    assert abs(got["truncation_error"] - info["truncerr"]) < TOL
+    new = [out.factor(v) for v in (v1, v2)]
+    tens = list(net.tensors)
+    tens[v1], tens[v2] = new
+    assert rel_err(pair_tensor(tens, g, e), pair_tensor(ref.tensors, g, e)) < 1e-9
+    # second opinion: generic kernels only
+    c2 = E.Context(0)
+    c2.set_path(1)
+    b2 = E.update(E.BeliefPropagationCache(psi, ctx=c2), maxiter=3, edge_sequence=E.parallel_edge_sequence(psi.graph))
+    got2 = {}
+    out2 = E.apply(gate, b2, (v1, v2), maxdim=maxdim, cutoff=1e-13, callback=lambda **kw: got2.update(kw))
+    assert rel_err(got["singular_values"], got2["singular_values"]) < 1e-11
+    tens2 = list(net.tensors)
+    tens2[v1], tens2[v2] = out2.factor(v1), out2.factor(v2)
+    assert rel_err(pair_tensor(tens, g, e), pair_tensor(tens2, g, e)) < 1e-9
+    # BP keeps working on the updated network (tile copies are refreshed)
+    if maxdim == 16:
+        seq = O.parallel_edge_sequence(g)
+        m2 = O.reset_edge_messages(ref, msgs, e)
+        m2, _, _ = O.bp_update(ref, m2, seq=seq, groups=O.synchronous_groups(seq), maxiter=2)
+        out = E.update(out, maxiter=2, edge_sequence=[[x] for x in seq])
+        for k, m in m2.items():
+            if g.eid[k] != e:
+                assert rel_err(out.message(k), m) < 1e-9
