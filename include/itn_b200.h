@@ -83,6 +83,20 @@ int itn_net_tensor_size(const itn_net* net, int v, int64_t* out_elems);
 int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd, const int32_t* axis_edge);
 int itn_net_get_tensor(const itn_net* net, int v, void* host, int nd, const int32_t* axis_edge);
 
+/* The constructor's data path, BeliefPropagationCache(ptn) over the whole network
+ * (src/caches/beliefpropagationcache.jl:20-35): n site tensors in one call.  hosts[i] is the column-major
+ * tensor of vertex verts[i]; nd / axis_edge (nullable = canonical [site, bonds...]) are the per-tensor axis
+ * counts and the concatenated axis descriptions of itn_net_set_tensor.  The copy is pipelined: a second stream
+ * moves chunk c + 1 over PCIe while the main stream de-interleaves and permutes chunk c.
+ *   flags = 0                  returns when every host buffer has been consumed.
+ *   flags = ITN_HOST_DEFERRED  only registers the buffers; they must stay valid and unchanged until the next
+ *       call on this handle that consumes tensors returns (itn_bp_update, itn_sync, any observable or gate).
+ *       A synchronous itn_bp_update then runs its first sweep vertex chunk by vertex chunk behind the copy,
+ *       so the upload of psi overlaps the DMMA kernels instead of preceding them. */
+enum { ITN_HOST_DEFERRED = 1 };
+int itn_net_set_tensors(itn_net* net, int n, const int32_t* verts, const void* const* hosts, const int32_t* nd,
+                        const int32_t* axis_edge, int flags);
+
 /* identity_messages (src/formnetworks/quadraticformnetwork.jl:96-124): delta on every directed edge. */
 int itn_msg_set_identity(itn_net* net);
 /* set_message! / message (abstractbeliefpropagationcache.jl:173-200). */

@@ -70,12 +70,6 @@ static void set_device(const itn_ctx* ctx) { CUDA_CHECK(cudaSetDevice(ctx->devic
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct Marshal {
-  int nd;
-  int dims[ITN_MAX_MODES];          // host axis extents
-  long long cstride[ITN_MAX_MODES]; // canonical stride of host axis i
-};
-
 // host (interleaved complex, arbitrary axis order) -> device planar canonical
 template <bool C>
 __global__ void k_import(const double* __restrict__ in, double* __restrict__ out, long long n, Marshal m) {
@@ -90,6 +84,48 @@ __global__ void k_import(const double* __restrict__ in, double* __restrict__ out
     if (C) {
       out[off] = in[2 * i];
       out[n + off] = in[2 * i + 1];
+    } else {
+      out[off] = in[i];
+    }
+  }
+}
+// the same for a batch of tensors staged back to back: block (job, y)
+struct ImportJob {
+  const double* src;  // staged host bytes
+  double* dst;        // canonical planar tensor
+  long long n;
+  Marshal m;
+};
+template <bool C>
+__global__ void __launch_bounds__(256) k_import_batch(const ImportJob* __restrict__ jobs) {
+  const ImportJob& J = jobs[blockIdx.x];
+  const long long n = J.n;
+  const double* __restrict__ in = J.src;
+  double* __restrict__ out = J.dst;
+  bool ident = true;
+  {
+    long long st = 1;
+    for (int a = 0; a < J.m.nd; ++a) {
+      ident = ident && J.m.cstride[a] == st;
+      st *= J.m.dims[a];
+    }
+  }
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.y * blockDim.x) {
+    long long off = i;
+    if (!ident) {
+      long long r = i;
+      off = 0;
+      for (int a = 0; a < J.m.nd; ++a) {
+        int d = J.m.dims[a];
+        long long q = r / d;
+        off += (r - q * d) * J.m.cstride[a];
+        r = q;
+      }
+    }
+    if (C) {
+      const double2 z = reinterpret_cast<const double2*>(in)[i];
+      out[off] = z.x;
+      out[n + off] = z.y;
     } else {
       out[off] = in[i];
     }
@@ -455,6 +491,7 @@ static void ctx_destroy_now(itn_ctx* ctx) {
     destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
     if (f) f(ctx->nccl);
   }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -573,6 +610,7 @@ extern "C" int itn_net_destroy(itn_net* net) {
   API_BEGIN
   if (!net) return ITN_OK;
   cudaSetDevice(net->ctx->device);
+  net->pending.clear();
   free_net_storage(net);
   itn_ctx* ctx = net->ctx;
   delete net;
@@ -584,6 +622,7 @@ extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
   API_BEGIN
   ITN_REQUIRE(src && out, ITN_EINVAL, "NULL argument");
   set_device(src->ctx);
+  itn_flush_pending(const_cast<itn_net*>(src));
   std::unique_ptr<itn_net> net(new itn_net(*src));
   net->fast = nullptr;
   net->dist = nullptr;
@@ -611,6 +650,7 @@ extern "C" int itn_sync(itn_net* net) {
   API_BEGIN
   ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
   set_device(net->ctx);
+  itn_flush_pending(net);
   CUDA_CHECK(cudaStreamSynchronize(net->ctx->stream));
   API_END
 }
@@ -674,6 +714,11 @@ extern "C" int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd,
   set_device(net->ctx);
   itn_ctx* ctx = net->ctx;
   Marshal m = make_marshal(net, v, nd, axis_edge);
+  for (size_t i = 0; i < net->pending.size(); ++i)
+    if (net->pending[i].v == v) {
+      net->pending.erase(net->pending.begin() + i);
+      break;
+    }
   const long long n = net->tensor_elems(v);
   const int P = net->planes();
   if (!net->T[v].p || net->T[v].n != n) {
@@ -691,6 +736,176 @@ extern "C" int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd,
   API_END
 }
 
+// ------------------------------------------------------------------------------------------------
+// pipelined host -> device upload of site tensors
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+cudaStream_t copy_stream(itn_ctx* ctx) {
+  if (!ctx->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  return ctx->copy_stream;
+}
+
+// Streams items[cuts[c] .. cuts[c+1]) chunk by chunk: the copy stream fills one of two staging slots while the main
+// stream imports (de-interleave + axis permutation) the other.  after_chunk(c) runs once the import of chunk c
+// has been enqueued on the main stream, so whatever it launches there overlaps the copy of chunk c + 1.
+// Host buffers are free again when the copy stream has drained (the caller synchronises it).
+template <class F>
+void upload_pipelined(itn_net* net, const std::vector<PendingUpload>& items, const std::vector<size_t>& cuts, F after_chunk) {
+  itn_ctx* ctx = net->ctx;
+  if (items.empty()) return;
+  const int P = net->planes();
+  cudaStream_t cs = copy_stream(ctx);
+  std::vector<ImportJob> jobs(items.size());
+  size_t slot_bytes = 0;
+  long long maxn = 0;
+  for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+    size_t off = 0;
+    for (size_t i = cuts[c]; i < cuts[c + 1]; ++i) {
+      const long long n = net->T[items[i].v].n;
+      jobs[i].src = (const double*)off;  // byte offset inside the slot for now
+      jobs[i].dst = net->T[items[i].v].p;
+      jobs[i].n = n;
+      jobs[i].m = items[i].m;
+      off += (size_t)n * P * sizeof(double);
+      maxn = std::max(maxn, n);
+    }
+    slot_bytes = std::max(slot_bytes, off);
+  }
+  DevBuf stage(ctx, 2 * slot_bytes), jb(ctx, jobs.size() * sizeof(ImportJob));
+  for (size_t c = 0; c + 1 < cuts.size(); ++c)
+    for (size_t i = cuts[c]; i < cuts[c + 1]; ++i)
+      jobs[i].src = (const double*)(stage.as<char>() + (c & 1) * slot_bytes + (size_t)jobs[i].src);
+  const ImportJob* dj = itn_upload(ctx, jobs, jb);
+  cudaEvent_t ready, copied[2], imported[2];
+  CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) {
+    CUDA_CHECK(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&imported[k], cudaEventDisableTiming));
+  }
+  auto cleanup = [&]() {
+    cudaEventDestroy(ready);
+    for (int k = 0; k < 2; ++k) {
+      cudaEventDestroy(copied[k]);
+      cudaEventDestroy(imported[k]);
+    }
+  };
+  try {
+    // the staging buffer and the destination tensors were allocated in main-stream order
+    CUDA_CHECK(cudaEventRecord(ready, ctx->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(cs, ready, 0));
+    unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + 2047) / 2048, 64));
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+      const int k = (int)(c & 1);
+      const size_t lo = cuts[c], hi = cuts[c + 1];
+      if (hi == lo) {
+        after_chunk(c);
+        continue;
+      }
+      if (c >= 2) CUDA_CHECK(cudaStreamWaitEvent(cs, imported[k], 0));
+      for (size_t i = lo; i < hi; ++i)
+        CUDA_CHECK(cudaMemcpyAsync((void*)jobs[i].src, items[i].host, (size_t)jobs[i].n * P * sizeof(double),
+                                   cudaMemcpyHostToDevice, cs));
+      CUDA_CHECK(cudaEventRecord(copied[k], cs));
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, copied[k], 0));
+      dim3 grid((unsigned)(hi - lo), gy);
+      if (net->cplx) k_import_batch<true><<<grid, 256, 0, ctx->stream>>>(dj + lo);
+      else k_import_batch<false><<<grid, 256, 0, ctx->stream>>>(dj + lo);
+      ITN_LAUNCH_CHECK(ctx);
+      CUDA_CHECK(cudaEventRecord(imported[k], ctx->stream));
+      after_chunk(c);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(cs));  // host buffers consumed
+  } catch (...) {
+    cudaStreamSynchronize(cs);
+    cleanup();
+    throw;
+  }
+  cleanup();
+}
+
+// chunk boundaries of roughly `target` bytes
+std::vector<size_t> cuts_by_bytes(const itn_net* net, const std::vector<PendingUpload>& items, size_t lo, size_t hi,
+                                  size_t target) {
+  std::vector<size_t> cuts{lo};
+  size_t acc = 0;
+  for (size_t i = lo; i < hi; ++i) {
+    acc += (size_t)net->T[items[i].v].n * net->planes() * sizeof(double);
+    if (acc >= target) {
+      cuts.push_back(i + 1);
+      acc = 0;
+    }
+  }
+  if (cuts.back() != hi) cuts.push_back(hi);
+  return cuts;
+}
+
+constexpr size_t kUploadChunkBytes = (size_t)256 << 20;
+
+}  // namespace
+
+// Copies every registered-but-deferred host tensor to the device (all consumers other than the pipelined first BP sweep).
+void itn_flush_pending(itn_net* net) {
+  if (net->pending.empty()) return;
+  std::vector<PendingUpload> items;
+  items.swap(net->pending);
+  upload_pipelined(net, items, cuts_by_bytes(net, items, 0, items.size(), kUploadChunkBytes), [](size_t) {});
+  net->topo_version++;  // tile-major copies planned while the tensors were pending are stale
+}
+
+/* BeliefPropagationCache(ptn) data path: every site tensor in one call (pipelined copy + import). */
+extern "C" int itn_net_set_tensors(itn_net* net, int n, const int32_t* verts, const void* const* hosts, const int32_t* nd,
+                                   const int32_t* axis_edge, int flags) {
+  API_BEGIN
+  ITN_REQUIRE(net && n >= 0 && (n == 0 || (verts && hosts)), ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE((flags & ~ITN_HOST_DEFERRED) == 0, ITN_EINVAL, "unknown flag");
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  const int P = net->planes();
+  std::vector<char> seen(net->nv, 0);
+  size_t aoff = 0;
+  std::vector<PendingUpload> items;
+  for (int i = 0; i < n; ++i) {
+    const int v = verts[i];
+    ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "vertex out of range");
+    ITN_REQUIRE(!seen[v], ITN_EINVAL, "vertex listed twice");
+    ITN_REQUIRE(hosts[i] != nullptr, ITN_EINVAL, "NULL host tensor");
+    seen[v] = 1;
+    const int ndv = nd ? nd[i] : (int)net->inc[v].size() + 1;
+    const int32_t* ax = axis_edge ? axis_edge + aoff : nullptr;
+    aoff += ndv;
+    if (!itn_is_local(net, v)) continue;  // another rank stores this vertex
+    PendingUpload pu;
+    pu.v = v;
+    pu.host = hosts[i];
+    pu.m = make_marshal(net, v, ndv, ax);
+    items.push_back(pu);
+  }
+  // a newer registration replaces an older pending one
+  if (!net->pending.empty()) {
+    std::vector<PendingUpload> keep;
+    for (const PendingUpload& pu : net->pending)
+      if (!seen[pu.v]) keep.push_back(pu);
+    net->pending.swap(keep);
+  }
+  for (const PendingUpload& pu : items) {
+    const int v = pu.v;
+    const long long nel = net->tensor_elems(v);
+    if (!net->T[v].p || net->T[v].n != nel || net->T[v].slab) {
+      if (net->T[v].p) itn_tensor_free(ctx, net->T[v]);
+      net->T[v].p = (double*)itn_dev_alloc(ctx, (size_t)nel * P * sizeof(double));
+      net->T[v].n = nel;
+    }
+  }
+  net->topo_version++;
+  if (flags & ITN_HOST_DEFERRED) {
+    net->pending.insert(net->pending.end(), items.begin(), items.end());
+  } else {
+    upload_pipelined(net, items, cuts_by_bytes(net, items, 0, items.size(), kUploadChunkBytes), [](size_t) {});
+  }
+  API_END
+}
+
 extern "C" int itn_net_get_tensor(const itn_net* net_, int v, void* host, int nd, const int32_t* axis_edge) {
   API_BEGIN
   itn_net* net = const_cast<itn_net*>(net_);
@@ -698,6 +913,7 @@ extern "C" int itn_net_get_tensor(const itn_net* net_, int v, void* host, int nd
   ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "vertex out of range");
   ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor is not set");
   set_device(net->ctx);
+  itn_flush_pending(net);
   itn_ctx* ctx = net->ctx;
   Marshal m = make_marshal(net, v, nd, axis_edge);
   const long long n = net->T[v].n;
@@ -903,6 +1119,7 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   if (last_mean_diff) *last_mean_diff = NAN;
   if (nseq == 0 || maxiter == 0) return ITN_OK;
   const bool sync_mode = group_ptr != nullptr;
+  if (!sync_mode) itn_flush_pending(net);  // only the synchronous sweep overlaps the upload (see below)
   if (sync_mode) {
     ITN_REQUIRE(ngroups == nseq && group_ptr[0] == 0, ITN_EUNSUPPORTED,
                 "grouped update supports single-edge groups only (ngroups must equal nseq)");
@@ -994,6 +1211,47 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   if (nfast > 0)
     for (int i = 0; i < nseq; ++i)
       if (!handled[i]) slow_specs.push_back({sjobs[i].v, 1u << (sjobs[i].k + 1), staged.ptr[i]});
+  // Deferred host tensors (itn_net_set_tensors, ITN_HOST_DEFERRED): in a synchronous sweep the outgoing messages of a
+  // vertex depend on its own tensor and the pre-sweep messages only, so the first sweep runs vertex chunk by vertex
+  // chunk behind the host -> device copy: copy(c + 1) overlaps import + relayout + DMMA phases of chunk c.
+  bool pipelined_first = false;
+  std::vector<PendingUpload> pl_items;
+  std::vector<size_t> pl_cuts;
+  std::vector<std::pair<int, int>> pl_ranges;  // sweep positions [lo, hi) completed by chunk c
+  if (!net->pending.empty()) {
+    bool contiguous = false;
+    if (nfast > 0) {
+      const std::vector<int>& sv = itn_fast_sweep_vertices(net, &contiguous);
+      if (contiguous) {
+        std::vector<int> pos(net->nv, -1);
+        for (size_t r = 0; r < sv.size(); ++r) pos[sv[r]] = (int)r;
+        std::vector<PendingUpload> others, bucket;
+        for (const PendingUpload& pu : net->pending) (pos[pu.v] >= 0 ? bucket : others).push_back(pu);
+        std::sort(bucket.begin(), bucket.end(), [&](const PendingUpload& a, const PendingUpload& b) { return pos[a.v] < pos[b.v]; });
+        // chunk 0: tensors outside the bucket (generic kernels run after the loop); then the bucket in sweep order
+        pl_items = others;
+        pl_cuts = {0, others.size()};
+        pl_ranges.push_back({0, 0});
+        pl_items.insert(pl_items.end(), bucket.begin(), bucket.end());
+        std::vector<size_t> bc = cuts_by_bytes(net, pl_items, others.size(), pl_items.size(), kUploadChunkBytes);
+        int done_pos = 0;
+        for (size_t c = 1; c < bc.size(); ++c) {
+          pl_cuts.push_back(bc[c]);
+          // sweep positions below the first still-pending bucket vertex are complete after this chunk
+          const int upto = bc[c] < pl_items.size() ? pos[pl_items[bc[c]].v] : (int)sv.size();
+          pl_ranges.push_back({done_pos, upto});
+          done_pos = upto;
+        }
+        if (bucket.empty()) pl_ranges.back().second = (int)sv.size();
+        pipelined_first = true;
+        net->pending.clear();
+      }
+    }
+    if (!pipelined_first) {
+      itn_flush_pending(net);
+      if (nfast > 0) itn_fast_bp_plan(net, all_dids, all_src, handled);  // rebuild the tile-major copies
+    }
+  }
 
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
@@ -1015,7 +1273,25 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
           cev.push_back(b);
           CUDA_CHECK(cudaEventRecord(a, ctx->stream));
         }
-        if (nfast > 0) {
+        if (nfast > 0 && pipelined_first && it == 0) {
+          itn_fast_bp_sweep_begin(net, all_dids, all_src, handled, staged.ptr.data());
+          int swept = 0;
+          upload_pipelined(net, pl_items, pl_cuts, [&](size_t c) {
+            const std::pair<int, int> r = pl_ranges[c];
+            if (r.second > r.first) {
+              itn_fast_relayout_range(net, r.first, r.second);
+              itn_fast_bp_sweep_range(net, r.first, r.second);
+              swept = r.second;
+            }
+          });
+          const int ns = (int)itn_fast_sweep_vertices(net, nullptr).size();
+          if (swept < ns) {  // bucket vertices that were already resident
+            itn_fast_relayout_range(net, swept, ns);
+            itn_fast_bp_sweep_range(net, swept, ns);
+          }
+          itn_fast_bp_sweep_end(net);
+          itn_run_vertex_jobs(net, slow_specs);
+        } else if (nfast > 0) {
           itn_fast_bp_sweep(net, all_dids, all_src, handled, staged.ptr.data());
           itn_run_vertex_jobs(net, slow_specs);
         } else {
@@ -1095,6 +1371,7 @@ extern "C" int itn_updated_message(itn_net* net, int src, int dst, int normalize
   API_BEGIN
   ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
   set_device(net->ctx);
+  itn_flush_pending(net);
   int32_t s = src, d = dst;
   std::vector<MsgJob> jobs = make_msg_jobs(net, &s, &d, 1);
   Staged staged(net, jobs), dest(net, jobs);
@@ -1109,6 +1386,7 @@ extern "C" int itn_message_residuals(itn_net* net, const int32_t* src, const int
   ITN_REQUIRE(net && out && (n == 0 || (src && dst)), ITN_EINVAL, "NULL argument");
   if (n == 0) return ITN_OK;
   set_device(net->ctx);
+  itn_flush_pending(net);
   std::vector<MsgJob> jobs = make_msg_jobs(net, src, dst, n);
   for (auto& J : jobs) ITN_REQUIRE(net->M[J.did].p, ITN_EINVAL, "message is not set");
   Staged staged(net, jobs), dest(net, jobs);
@@ -1174,6 +1452,7 @@ extern "C" int itn_region_scalars(itn_net* net, void* z_v, void* z_e) {
   API_BEGIN
   ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
   set_device(net->ctx);
+  itn_flush_pending(net);
   std::vector<std::complex<double>> zv, ze;
   region_scalars_host(net, zv, ze);
   if (net->cplx) {
@@ -1190,6 +1469,7 @@ extern "C" int itn_logscalar(itn_net* net, double out[2]) {
   API_BEGIN
   ITN_REQUIRE(net && out, ITN_EINVAL, "NULL argument");
   set_device(net->ctx);
+  itn_flush_pending(net);
   std::vector<std::complex<double>> zv, ze;
   region_scalars_host(net, zv, ze);
   // logscalar (abstractbeliefpropagationcache.jl:397-408): the O(nv + ne) log-sum over the device-computed scalars
@@ -1211,6 +1491,7 @@ extern "C" int itn_rescale(itn_net* net) {
   API_BEGIN
   ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
   set_device(net->ctx);
+  itn_flush_pending(net);
   itn_ctx* ctx = net->ctx;
   require_all_set(net);
   {
@@ -1271,6 +1552,7 @@ extern "C" int itn_expect1(itn_net* net, const int32_t* verts, int n, const void
   ITN_REQUIRE(net && verts && ops && out && n >= 0, ITN_EINVAL, "NULL argument");
   if (n == 0) return ITN_OK;
   set_device(net->ctx);
+  itn_flush_pending(net);
   itn_ctx* ctx = net->ctx;
   const int P = net->planes();
   // all ops must share the layout d_v x d_v; they are packed back to back with their own d
@@ -1321,6 +1603,7 @@ extern "C" int itn_rdm2(itn_net* net, const int32_t* eids, int n, void* out) {
   ITN_REQUIRE(net && eids && out && n >= 0, ITN_EINVAL, "NULL argument");
   if (n == 0) return ITN_OK;
   set_device(net->ctx);
+  itn_flush_pending(net);
   itn_ctx* ctx = net->ctx;
   const int P = net->planes();
   size_t env_elems = 0, out_elems = 0;
@@ -1392,6 +1675,7 @@ extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void*
   ITN_REQUIRE(net && verts && gates && n >= 0, ITN_EINVAL, "NULL argument");
   if (n == 0) return ITN_OK;
   set_device(net->ctx);
+  itn_flush_pending(net);
   itn_ctx* ctx = net->ctx;
   const int P = net->planes();
   size_t g_elems = 0;

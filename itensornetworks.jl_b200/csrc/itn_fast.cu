@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(256) k_fast_reduce(const double* __restrict__ 
 struct RelayoutJob {
   const double* src;  // canonical planar [s, a1, a2, a3, a4]
   long long n;
+  long long slot;     // bucket slot: the tile-major copies live at slot * d * 256 * TILE
 };
 // canonical planar [s, a1, a2, a3, a4] -> F1[s][a4][a3][tile(a1,a2)]: block (vertex, a4) streams one contiguous
 // d*4096 slab; a warp's stores land in d runs of 16 consecutive (swizzled) doubles.
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(256) k_fast_relayout_f1(const RelayoutJob* __r
   constexpr int TILE = C ? 512 : 256;
   const RelayoutJob J = jobs[blockIdx.x];
   const int a4 = blockIdx.y;
-  const size_t base = (size_t)blockIdx.x * d * 256 * TILE;
+  const size_t base = (size_t)J.slot * d * 256 * TILE;
   const double* src = J.src + (size_t)a4 * 4096 * d;
   for (int i = threadIdx.x; i < 4096 * d; i += blockDim.x) {
     const int s = i % d, r = i / d;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(256) k_fast_relayout_f2(const RelayoutJob* __r
   constexpr int TILE = C ? 512 : 256;
   const RelayoutJob J = jobs[blockIdx.x];
   const int a2 = blockIdx.y;
-  const size_t base = (size_t)blockIdx.x * d * 256 * TILE;
+  const size_t base = (size_t)J.slot * d * 256 * TILE;
   const int ntile = 16 * d;
   for (int plane = 0; plane < (C ? 2 : 1); ++plane) {
     const double* src = J.src + (size_t)plane * J.n;
@@ -513,6 +514,9 @@ struct FastCache {
   const double** d_tab = nullptr;  // 4 pointer tables of nb entries: F1, F2, P12, S34 of the sweep's vertices
   const double** d_msg = nullptr;
   double** d_staged = nullptr;
+  RelayoutJob* d_rjobs = nullptr;  // [nb] relayout descriptors, slot i at index i
+  std::vector<char> stale;         // [nb] tile-major copies not built yet (site tensor still on the host)
+  std::vector<int> sweep_verts;    // vertices of `sweep`, position order
 };
 
 void release(itn_net* net, FastCache* fc) {
@@ -521,6 +525,8 @@ void release(itn_net* net, FastCache* fc) {
   itn_dev_free(ctx, (void*)fc->d_tab);
   itn_dev_free(ctx, (void*)fc->d_msg);
   itn_dev_free(ctx, (void*)fc->d_staged);
+  itn_dev_free(ctx, (void*)fc->d_rjobs);
+  fc->d_rjobs = nullptr;
   fc->F1 = fc->F2 = fc->P12 = fc->S34 = fc->part = nullptr;
   fc->d_tab = nullptr;
   fc->d_msg = nullptr;
@@ -549,16 +555,19 @@ void launch_phase(itn_net* net, int nverts, const FastArgs& a) {
   ITN_LAUNCH_CHECK(net->ctx);
 }
 
+// The three phases for sweep positions [lo, hi).
 template <bool C>
-void sweep(itn_net* net, FastCache* fc) {
-  const int ns = (int)fc->sweep.size();
-  const double* const* tF1 = fc->d_tab;
-  const double* const* tF2 = fc->d_tab + fc->nb;
-  const double* const* tP12 = fc->d_tab + 2 * (size_t)fc->nb;
-  const double* const* tS34 = fc->d_tab + 3 * (size_t)fc->nb;
+void sweep_range(itn_net* net, FastCache* fc, int lo, int hi) {
+  constexpr int TILE = C ? 512 : 256;
+  const int ns = hi - lo;
+  if (ns <= 0) return;
+  const double* const* tF1 = fc->d_tab + lo;
+  const double* const* tF2 = fc->d_tab + fc->nb + lo;
+  const double* const* tP12 = fc->d_tab + 2 * (size_t)fc->nb + lo;
+  const double* const* tS34 = fc->d_tab + 3 * (size_t)fc->nb + lo;
   FastArgs a;
-  a.msg = fc->d_msg;
-  a.part = fc->part;
+  a.msg = fc->d_msg + 4 * (size_t)lo;
+  a.part = fc->part + (size_t)lo * 4 * 32 * fc->d * TILE;
   a.d = fc->d;
   // phase 1: P12 = M1^T X M2 on F1 tiles
   a.Xv = tF1; a.Pv = nullptr; a.Wv = (double* const*)tP12; a.kL = 0; a.kR = 1;
@@ -569,8 +578,34 @@ void sweep(itn_net* net, FastCache* fc) {
   // phase 3: out2 / out1 from S34 and F1 tiles
   a.Xv = tF1; a.Pv = tS34; a.Wv = nullptr; a.kL = 0; a.kR = 1;
   launch_phase<C, true, false>(net, ns, a);
-  k_fast_reduce<C><<<(unsigned)ns * 4, 256, 0, net->ctx->stream>>>(fc->part, fc->d_staged, 32 * fc->d);
+}
+
+template <bool C>
+void sweep_reduce(itn_net* net, FastCache* fc) {
+  k_fast_reduce<C><<<(unsigned)fc->sweep.size() * 4, 256, 0, net->ctx->stream>>>(fc->part, fc->d_staged, 32 * fc->d);
   ITN_LAUNCH_CHECK(net->ctx);
+}
+
+void relayout_launch(itn_net* net, FastCache* fc, int lo, int hi) {
+  if (hi <= lo) return;
+  itn_ctx* ctx = net->ctx;
+  const int d = fc->d;
+  const RelayoutJob* dj = fc->d_rjobs + lo;
+  dim3 grid(hi - lo, 16);
+  const size_t rsm = (size_t)16 * d * 257 * sizeof(double);
+  if (net->cplx) {
+    k_fast_relayout_f1<true><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, d);
+    ITN_LAUNCH_CHECK(ctx);
+    CUDA_CHECK(cudaFuncSetAttribute(k_fast_relayout_f2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+    k_fast_relayout_f2<true><<<grid, 256, rsm, ctx->stream>>>(dj, fc->F2, d);
+  } else {
+    k_fast_relayout_f1<false><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, d);
+    ITN_LAUNCH_CHECK(ctx);
+    CUDA_CHECK(cudaFuncSetAttribute(k_fast_relayout_f2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+    k_fast_relayout_f2<false><<<grid, 256, rsm, ctx->stream>>>(dj, fc->F2, d);
+  }
+  ITN_LAUNCH_CHECK(ctx);
+  for (int i = lo; i < hi; ++i) fc->stale[i] = 0;
 }
 
 // (Re)builds the tile-major copies of every eligible vertex when the network changed.
@@ -615,28 +650,28 @@ FastCache* ensure_cache(itn_net* net) {
       fc->d_tab = (const double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
       fc->d_msg = (const double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
       fc->d_staged = (double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
+      fc->d_rjobs = (RelayoutJob*)itn_dev_alloc(ctx, (size_t)fc->nb * sizeof(RelayoutJob));
     }
     std::vector<RelayoutJob> jobs(fc->nb);
-    for (int i = 0; i < fc->nb; ++i) jobs[i] = {net->T[verts[i]].p, net->T[verts[i]].n};
-    DevBuf jb(ctx, jobs.size() * sizeof(RelayoutJob));
-    const RelayoutJob* dj = itn_upload(ctx, jobs, jb);
-    dim3 grid(fc->nb, 16);
-    const size_t rsm = (size_t)16 * d * 257 * sizeof(double);
-    if (net->cplx) {
-      k_fast_relayout_f1<true><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, d);
-      ITN_LAUNCH_CHECK(ctx);
-      CUDA_CHECK(cudaFuncSetAttribute(k_fast_relayout_f2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-      k_fast_relayout_f2<true><<<grid, 256, rsm, ctx->stream>>>(dj, fc->F2, d);
-    } else {
-      k_fast_relayout_f1<false><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, d);
-      ITN_LAUNCH_CHECK(ctx);
-      CUDA_CHECK(cudaFuncSetAttribute(k_fast_relayout_f2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-      k_fast_relayout_f2<false><<<grid, 256, rsm, ctx->stream>>>(dj, fc->F2, d);
-    }
-    ITN_LAUNCH_CHECK(ctx);
-    fc->topo_version = net->topo_version;
+    for (int i = 0; i < fc->nb; ++i) jobs[i] = {net->T[verts[i]].p, net->T[verts[i]].n, (long long)i};
+    CUDA_CHECK(cudaMemcpyAsync(fc->d_rjobs, jobs.data(), jobs.size() * sizeof(RelayoutJob), cudaMemcpyHostToDevice, ctx->stream));
     fc->vslot.assign(net->nv, -1);
     for (int i = 0; i < fc->nb; ++i) fc->vslot[verts[i]] = i;
+    // tensors whose host buffer has not been copied yet are laid out by the upload pipeline (itn_fast_relayout_range)
+    fc->stale.assign(fc->nb, 0);
+    for (const PendingUpload& pu : net->pending)
+      if (fc->vslot[pu.v] >= 0) fc->stale[fc->vslot[pu.v]] = 1;
+    for (int lo = 0; lo < fc->nb;) {
+      if (fc->stale[lo]) {
+        ++lo;
+        continue;
+      }
+      int hi = lo;
+      while (hi < fc->nb && !fc->stale[hi]) ++hi;
+      relayout_launch(net, fc, lo, hi);
+      lo = hi;
+    }
+    fc->topo_version = net->topo_version;
   }
   return fc;
 }
@@ -667,6 +702,8 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
       rank_in_sweep[i] = (int)fc->sweep.size();
       fc->sweep.push_back(i);
     }
+  fc->sweep_verts.resize(fc->sweep.size());
+  for (size_t r = 0; r < fc->sweep.size(); ++r) fc->sweep_verts[r] = fc->verts[fc->sweep[r]];
   if (fc->sweep.empty()) return 0;
   std::vector<const double*> tab((size_t)fc->nb * 4, nullptr);
   for (size_t r = 0; r < fc->sweep.size(); ++r) {
@@ -689,8 +726,8 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
 }
 
 // Computes the un-normalised new messages of every job flagged by itn_fast_bp_plan into staged[i].
-void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
-                       const std::vector<char>& handled, double* const* staged) {
+void itn_fast_bp_sweep_begin(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
+                             const std::vector<char>& handled, double* const* staged) {
   FastCache* fc = (FastCache*)net->fast;
   ITN_REQUIRE(fc && !fc->sweep.empty(), ITN_EINVAL, "fast path is not prepared");
   itn_ctx* ctx = net->ctx;
@@ -715,8 +752,45 @@ void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::ve
   }
   CUDA_CHECK(cudaMemcpyAsync((void*)fc->d_msg, msg.data(), msg.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaMemcpyAsync((void*)fc->d_staged, st.data(), st.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
-  if (net->cplx) sweep<true>(net, fc);
-  else sweep<false>(net, fc);
+}
+
+void itn_fast_bp_sweep_range(itn_net* net, int lo, int hi) {
+  FastCache* fc = (FastCache*)net->fast;
+  ITN_REQUIRE(fc && lo >= 0 && hi <= (int)fc->sweep.size(), ITN_EINVAL, "bad sweep range");
+  for (int r = lo; r < hi; ++r)
+    ITN_REQUIRE(!fc->stale[fc->sweep[r]], ITN_EINVAL, "tile-major copy of a vertex in the sweep has not been built");
+  if (net->cplx) sweep_range<true>(net, fc, lo, hi);
+  else sweep_range<false>(net, fc, lo, hi);
+}
+
+void itn_fast_bp_sweep_end(itn_net* net) {
+  FastCache* fc = (FastCache*)net->fast;
+  if (net->cplx) sweep_reduce<true>(net, fc);
+  else sweep_reduce<false>(net, fc);
+}
+
+void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
+                       const std::vector<char>& handled, double* const* staged) {
+  itn_fast_bp_sweep_begin(net, dids, srcv, handled, staged);
+  itn_fast_bp_sweep_range(net, 0, (int)((FastCache*)net->fast)->sweep.size());
+  itn_fast_bp_sweep_end(net);
+}
+
+const std::vector<int>& itn_fast_sweep_vertices(itn_net* net, bool* contiguous) {
+  FastCache* fc = (FastCache*)net->fast;
+  ITN_REQUIRE(fc, ITN_EINVAL, "fast path is not prepared");
+  if (contiguous) {
+    bool c = (int)fc->sweep.size() == fc->nb;
+    for (size_t r = 0; c && r < fc->sweep.size(); ++r) c = fc->sweep[r] == (int)r;
+    *contiguous = c;
+  }
+  return fc->sweep_verts;
+}
+
+void itn_fast_relayout_range(itn_net* net, int lo, int hi) {
+  FastCache* fc = (FastCache*)net->fast;
+  ITN_REQUIRE(fc && lo >= 0 && hi <= fc->nb, ITN_EINVAL, "bad relayout range");
+  relayout_launch(net, fc, lo, hi);
 }
 
 // ------------------------------------------------------------------------------------------------

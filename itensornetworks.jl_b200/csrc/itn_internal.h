@@ -36,6 +36,7 @@ struct itn_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;  // host -> device staging copies that overlap kernels on `stream` (created on demand)
   int rank = 0, nranks = 1;
   void* nccl = nullptr;      // ncclComm_t
   void* nccl_lib = nullptr;  // dlopen handle
@@ -85,6 +86,20 @@ struct VJob {
   ModeStep steps[ITN_MAX_MODES];
 };
 
+// Axis description of a host tensor (any axis order, interleaved complex) relative to the canonical device layout.
+struct Marshal {
+  int nd;
+  int dims[ITN_MAX_MODES];           // host axis extents
+  long long cstride[ITN_MAX_MODES];  // canonical stride of host axis i
+};
+
+// A site tensor whose host buffer has been registered but not copied yet (itn_net_set_tensors, ITN_HOST_DEFERRED).
+struct PendingUpload {
+  int v;
+  const void* host;
+  Marshal m;
+};
+
 struct CommitJob {
   const double* staged;  // planar No x No
   double* dest;          // planar message (may be scratch)
@@ -104,6 +119,7 @@ struct itn_net {
   std::vector<DevTensor> M;  // per directed edge
   uint64_t topo_version = 0;  // bumped whenever a tensor pointer / bond dim changes
   double last_total_ms = 0, last_contract_ms = 0;
+  std::vector<PendingUpload> pending;  // deferred host tensors: device storage exists, contents arrive with the next consumer
   void* fast = nullptr;  // fast-path cache (owned by itn_fast.cu)
   void* dist = nullptr;  // halo exchange plan and buffers (owned by itn_dist.cu)
 
@@ -126,6 +142,9 @@ struct itn_net {
     return n;
   }
 };
+
+// copies every deferred host tensor (itn_net_set_tensors with ITN_HOST_DEFERRED) to the device; no-op when none is pending
+void itn_flush_pending(itn_net* net);
 
 // ---- device memory helpers (stream ordered) ----
 void* itn_dev_alloc(itn_ctx* ctx, size_t bytes);
@@ -180,6 +199,17 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
 void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
                        const std::vector<char>& handled, double* const* staged);
 void itn_fast_release(itn_net* net);
+// The same sweep in pieces, so that the first sweep can overlap the host -> device upload of the site tensors:
+// begin uploads the pointer tables, range runs the three phases for sweep positions [lo, hi), end reduces the
+// per-CTA partials into staged[].  itn_fast_bp_sweep = begin + range(0, n) + end.
+void itn_fast_bp_sweep_begin(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
+                             const std::vector<char>& handled, double* const* staged);
+void itn_fast_bp_sweep_range(itn_net* net, int lo, int hi);
+void itn_fast_bp_sweep_end(itn_net* net);
+// Vertices of the planned sweep in sweep-position order, and whether position r is bucket slot r for every r.
+const std::vector<int>& itn_fast_sweep_vertices(itn_net* net, bool* contiguous);
+// (Re)build the tile-major copies of bucket slots [lo, hi) from the canonical tensors (which must be complete).
+void itn_fast_relayout_range(itn_net* net, int lo, int hi);
 // simple update on the tile path (degree 4, all bonds 16, d = 2): bond environments and the rebuild A . T
 struct FastBenvJob {
   int v, slot;                 // vertex and bond slot of the gate bond

@@ -745,6 +745,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   ITN_REQUIRE(msg_mode == 0 || msg_mode == 1, ITN_EINVAL, "msg_mode must be 0 (identity) or 1 (singular values)");
   if (n == 0) return ITN_OK;
   CUDA_CHECK(cudaSetDevice(net->ctx->device));
+  itn_flush_pending(net);
   itn_ctx* ctx = net->ctx;
   const bool cplx = net->cplx;
   const int P = net->planes();

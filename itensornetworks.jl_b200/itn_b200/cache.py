@@ -72,9 +72,10 @@ class BeliefPropagationCache:
     """BP cache of <psi|psi> with the default one-site partition; state lives on the device."""
 
     def __init__(self, psi: ITensorNetwork = None, ctx: Context = None, messages="identity", owner=None, dist=None,
-                 _handle=None, _like=None):
+                 defer_upload=False, _handle=None, _like=None):
         if _handle is not None:  # clone
             self.ctx, self.graph, self.dtype, self.h = _like.ctx, _like.graph, _like.dtype, _handle
+            self._host_refs = None
             self.sdims = list(_like.sdims)
             self.owner, self.rank = _like.owner, _like.rank
             return
@@ -94,9 +95,11 @@ class BeliefPropagationCache:
         a4, p4 = i32(self.owner) if self.owner is not None else (None, None)
         check(lib().itn_net_create(self.ctx.h, _DTYPE_CODE[self.dtype], g.nv, g.ne, p0, p1, p2, p3, p4, C.byref(h)))
         self.h = h
-        for v in range(g.nv):
-            if self.owner is None or self.owner[v] == self.rank:
-                self.set_factor(v, psi.tensors[v])
+        # all site tensors in one call (pipelined copy + import).  defer_upload=True only registers the host arrays
+        # (kept alive in self._host_refs, and they must not be modified) and lets the first synchronous update()
+        # overlap the copy with its sweep (ITN_HOST_DEFERRED, include/itn_b200.h).
+        mine = [v for v in range(g.nv) if self.owner is None or self.owner[v] == self.rank]
+        self.set_factors(mine, [psi.tensors[v] for v in mine], defer=defer_upload)
         # initialize_cache (src/initialize_cache.jl:14-29): identity messages on loopy graphs, none on trees
         if messages == "identity" or (messages == "default" and not g.is_tree()):
             check(lib().itn_msg_set_identity(self.h))
@@ -123,6 +126,7 @@ class BeliefPropagationCache:
 
     def sync(self):
         check(lib().itn_sync(self.h))
+        self._host_refs = None
 
     # -- factors ------------------------------------------------------------------------------
     def edge_dim(self, e):
@@ -140,6 +144,20 @@ class BeliefPropagationCache:
             raise ITNError(2, f"tensor of vertex {v} has shape {t.shape}, expected {self._shape(v)}")
         f = np.asfortranarray(t)  # column-major bytes with axes [site, bonds...]
         check(lib().itn_net_set_tensor(self.h, int(v), f.ctypes.data_as(C.c_void_p), f.ndim, None))
+
+    def set_factors(self, verts, tensors, defer=False):
+        """itn_net_set_tensors: many site tensors in one pipelined upload (axes [site, bonds...])."""
+        hosts = []
+        for v, t in zip(verts, tensors):
+            t = np.asarray(t, dtype=self.dtype)
+            if t.shape != self._shape(v):
+                raise ITNError(2, f"tensor of vertex {v} has shape {t.shape}, expected {self._shape(v)}")
+            hosts.append(np.asfortranarray(t))
+        n = len(hosts)
+        _, pv = i32(list(verts))
+        ptrs = (C.c_void_p * max(n, 1))(*[h.ctypes.data for h in hosts])
+        check(lib().itn_net_set_tensors(self.h, n, pv, ptrs, None, None, 1 if defer else 0))
+        self._host_refs = hosts if defer else None
 
     def factor(self, v):
         shape = self._shape(v)
@@ -216,6 +234,7 @@ def update(bpc, maxiter="default", tol=None, edge_sequence=None, normalize=True,
     iters, diff = C.c_int32(), C.c_double()
     check(lib().itn_bp_update(out.h, ps, pd, len(flat), gp, ng, int(maxiter), -1.0 if tol is None else float(tol),
                               1 if normalize else 0, C.byref(iters), C.byref(diff)))
+    out._host_refs = None  # deferred host tensors have been consumed
     if info is not None:
         info["iterations"] = iters.value
         info["mean_diff"] = diff.value

@@ -223,3 +223,40 @@ def test_dmma_fast_path_chi16(dtype):
     ez = E.expect(bpc, "Z")
     for v in (0, 6, 12):
         assert abs(ez[v] - O.expect1(net, msgs, v, O.PAULI_Z)) < TOL
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dims,chi", [((6, 6), 16), ((4, 4), 3), ((9, 8), 16)], ids=["grid6_chi16", "grid4_chi3", "grid9x8_chi16"])
+def test_deferred_upload_first_sweep_overlaps_copy(dtype, dims, chi, monkeypatch):
+    # ITN_HOST_DEFERRED (include/itn_b200.h): the constructor only registers the host tensors, the first synchronous
+    # sweep runs vertex chunk by vertex chunk behind the host -> device copy.  Same messages as the eager path (bit for
+    # bit: identical kernels on identical data) and as the oracle.
+    g = O.grid_graph(dims)
+    net, psi = make_pair(g, chi, dtype)
+    seq = O.parallel_edge_sequence(g)
+    sync = [[e] for e in seq]
+    c = E.Context(0)
+    eager = E.BeliefPropagationCache(psi, ctx=c)
+    E.update(eager, maxiter=2, edge_sequence=sync, inplace=True)
+    lazy = E.BeliefPropagationCache(psi, ctx=c, defer_upload=True)
+    assert lazy._host_refs is not None
+    E.update(lazy, maxiter=2, edge_sequence=sync, inplace=True)
+    assert lazy._host_refs is None
+    for k in [(u, v) for (u, v) in g.edges] + [(v, u) for (u, v) in g.edges]:
+        assert np.array_equal(lazy.message(k), eager.message(k))
+    if g.nv <= 36:
+        msgs, _, _ = O.bp_update(net, O.identity_messages(net), seq=seq, groups=O.synchronous_groups(seq), maxiter=2)
+        assert_messages_close(lazy, msgs, TOL)
+    for v in range(g.nv):
+        assert np.array_equal(lazy.factor(v), net.tensors[v])
+    # consumers other than update() flush the pending tensors first
+    lazy2 = E.BeliefPropagationCache(psi, ctx=c, defer_upload=True)
+    assert np.array_equal(lazy2.factor(3), net.tensors[3])
+    ez = E.expect(E.update(lazy2, maxiter=2, edge_sequence=sync), "Z")
+    ez0 = E.expect(eager, "Z")
+    assert max(abs(ez[v] - ez0[v]) for v in range(g.nv)) < 1e-13
+    # sequential schedule on deferred tensors
+    lazy3 = E.BeliefPropagationCache(psi, ctx=c, defer_upload=True)
+    e3 = E.update(E.BeliefPropagationCache(psi, ctx=c), maxiter=1)
+    E.update(lazy3, maxiter=1, inplace=True)
+    assert np.array_equal(lazy3.message(g.edges[0]), e3.message(g.edges[0]))
