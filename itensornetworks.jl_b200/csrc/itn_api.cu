@@ -150,6 +150,17 @@ __global__ void k_export(const double* __restrict__ in, double* __restrict__ out
   }
 }
 
+struct CopyJob {
+  const double* src;
+  double* dst;
+  long long n;  // doubles
+};
+__global__ void __launch_bounds__(256) k_copy_batch(const CopyJob* __restrict__ jobs) {
+  const CopyJob J = jobs[blockIdx.x];
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < J.n; i += (long long)gridDim.y * blockDim.x)
+    J.dst[i] = J.src[i];
+}
+
 struct IdJob {
   double* p;
   int chi;
@@ -537,12 +548,47 @@ static void alloc_message(itn_net* net, int did) {
   net->M[did].n = n2;
 }
 
+// One shared, reference-counted allocation for a batch of tensors (a network has thousands of site tensors and tens
+// of thousands of messages: one cudaMallocAsync instead of one per object).  sizes in elements per plane.
+static void slab_alloc(itn_net* net, const std::vector<DevTensor*>& ts, const std::vector<long long>& elems) {
+  if (ts.empty()) return;
+  const int P = net->planes();
+  auto align32 = [](size_t x) { return (x + 31) & ~(size_t)31; };
+  size_t tot = 0;
+  for (long long n : elems) tot += align32((size_t)n * P);
+  DevSlab* slab = new DevSlab();
+  try {
+    slab->base = itn_dev_alloc(net->ctx, tot * sizeof(double));
+  } catch (...) {
+    delete slab;
+    throw;
+  }
+  size_t off = 0;
+  for (size_t i = 0; i < ts.size(); ++i) {
+    if (ts[i]->p) itn_tensor_free(net->ctx, *ts[i]);
+    ts[i]->p = (double*)slab->base + off;
+    ts[i]->n = elems[i];
+    ts[i]->slab = slab;
+    slab->refs++;
+    off += align32((size_t)elems[i] * P);
+  }
+}
+
 static void set_identity_messages(itn_net* net, const std::vector<int>& dids) {
   if (dids.empty()) return;
+  std::vector<DevTensor*> need;
+  std::vector<long long> need_n;
+  for (int did : dids) {
+    if (!msg_stored(net, did)) continue;
+    const long long n2 = (long long)net->edim[did / 2] * net->edim[did / 2];
+    if (net->M[did].p && net->M[did].n == n2) continue;
+    need.push_back(&net->M[did]);
+    need_n.push_back(n2);
+  }
+  slab_alloc(net, need, need_n);
   std::vector<IdJob> jobs;
   for (int did : dids) {
     if (!msg_stored(net, did)) continue;
-    alloc_message(net, did);
     jobs.push_back({net->M[did].p, net->edim[did / 2]});
   }
   if (jobs.empty()) return;
@@ -592,6 +638,7 @@ extern "C" int itn_net_create(itn_ctx* ctx, int dtype, int nv, int ne, const int
     ITN_REQUIRE((int)net->inc[v].size() + 1 <= ITN_MAX_MODES, ITN_EUNSUPPORTED, "vertex degree above 9 is not supported");
   net->T.assign(nv, DevTensor());
   net->M.assign(2 * (size_t)ne, DevTensor());
+  net->tver.assign(nv, 0);
   ctx->nets_alive++;
   *out = net.release();
   API_END
@@ -628,19 +675,41 @@ extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
   net->dist = nullptr;
   for (auto& t : net->T) t.p = nullptr, t.slab = nullptr;
   for (auto& m : net->M) m.p = nullptr, m.slab = nullptr;
+  // two shared allocations (site tensors, messages) and one batched copy kernel instead of ~20k cudaMallocAsync + memcpy
   const int P = src->planes();
+  std::vector<DevTensor*> ts, ms;
+  std::vector<long long> tn, mn;
+  std::vector<CopyJob> cj;
   for (int v = 0; v < src->nv; ++v)
     if (src->T[v].p) {
-      size_t b = (size_t)src->T[v].n * P * sizeof(double);
-      net->T[v].p = (double*)itn_dev_alloc(src->ctx, b);
-      CUDA_CHECK(cudaMemcpyAsync(net->T[v].p, src->T[v].p, b, cudaMemcpyDeviceToDevice, src->ctx->stream));
+      ts.push_back(&net->T[v]);
+      tn.push_back(src->T[v].n);
     }
   for (size_t d = 0; d < src->M.size(); ++d)
     if (src->M[d].p) {
-      size_t b = (size_t)src->M[d].n * P * sizeof(double);
-      net->M[d].p = (double*)itn_dev_alloc(src->ctx, b);
-      CUDA_CHECK(cudaMemcpyAsync(net->M[d].p, src->M[d].p, b, cudaMemcpyDeviceToDevice, src->ctx->stream));
+      ms.push_back(&net->M[d]);
+      mn.push_back(src->M[d].n);
     }
+  slab_alloc(net.get(), ts, tn);
+  slab_alloc(net.get(), ms, mn);
+  long long maxn = 0;
+  for (int v = 0; v < src->nv; ++v)
+    if (src->T[v].p) {
+      cj.push_back({src->T[v].p, net->T[v].p, src->T[v].n * P});
+      maxn = std::max<long long>(maxn, src->T[v].n * P);
+    }
+  for (size_t d = 0; d < src->M.size(); ++d)
+    if (src->M[d].p) {
+      cj.push_back({src->M[d].p, net->M[d].p, src->M[d].n * P});
+      maxn = std::max<long long>(maxn, src->M[d].n * P);
+    }
+  if (!cj.empty()) {
+    DevBuf jb(src->ctx, cj.size() * sizeof(CopyJob));
+    const CopyJob* dj = itn_upload(src->ctx, cj, jb);
+    unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn + 4095) / 4096, 64));
+    k_copy_batch<<<dim3((unsigned)cj.size(), gy), 256, 0, src->ctx->stream>>>(dj);
+    ITN_LAUNCH_CHECK(src->ctx);
+  }
   src->ctx->nets_alive++;
   *out = net.release();
   API_END
@@ -726,7 +795,7 @@ extern "C" int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd,
     net->T[v].p = (double*)itn_dev_alloc(ctx, (size_t)n * P * sizeof(double));
     net->T[v].n = n;
   }
-  net->topo_version++;
+  net->touch(v);
   DevBuf stage(ctx, (size_t)n * P * sizeof(double));
   CUDA_CHECK(cudaMemcpyAsync(stage.p, host, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   unsigned g = (unsigned)std::min<long long>((n + 255) / 256, 4096);
@@ -850,7 +919,7 @@ void itn_flush_pending(itn_net* net) {
   std::vector<PendingUpload> items;
   items.swap(net->pending);
   upload_pipelined(net, items, cuts_by_bytes(net, items, 0, items.size(), kUploadChunkBytes), [](size_t) {});
-  net->topo_version++;  // tile-major copies planned while the tensors were pending are stale
+  for (const PendingUpload& pu : items) net->touch(pu.v);  // tile-major copies planned while the tensors were pending are stale
 }
 
 /* BeliefPropagationCache(ptn) data path: every site tensor in one call (pipelined copy + import). */
@@ -888,14 +957,19 @@ extern "C" int itn_net_set_tensors(itn_net* net, int n, const int32_t* verts, co
       if (!seen[pu.v]) keep.push_back(pu);
     net->pending.swap(keep);
   }
-  for (const PendingUpload& pu : items) {
-    const int v = pu.v;
-    const long long nel = net->tensor_elems(v);
-    if (!net->T[v].p || net->T[v].n != nel || net->T[v].slab) {
-      if (net->T[v].p) itn_tensor_free(ctx, net->T[v]);
-      net->T[v].p = (double*)itn_dev_alloc(ctx, (size_t)nel * P * sizeof(double));
-      net->T[v].n = nel;
+  {
+    std::vector<DevTensor*> need;
+    std::vector<long long> need_n;
+    for (const PendingUpload& pu : items) {
+      const int v = pu.v;
+      const long long nel = net->tensor_elems(v);
+      if (!net->T[v].p || net->T[v].n != nel) {
+        need.push_back(&net->T[v]);
+        need_n.push_back(nel);
+      }
+      net->touch(v);
     }
+    slab_alloc(net, need, need_n);
   }
   net->topo_version++;
   if (flags & ITN_HOST_DEFERRED) {
@@ -1523,6 +1597,8 @@ extern "C" int itn_rescale(itn_net* net) {
     k_scale<<<dim3((unsigned)sj.size(), gy), 256, 0, ctx->stream>>>(dj);
     ITN_LAUNCH_CHECK(ctx);
   }
+  for (int v = 0; v < net->nv; ++v)
+    if (itn_is_local(net, v)) net->touch(v);
   net->topo_version++;
   API_END
 }
@@ -1715,6 +1791,7 @@ extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void*
     k_normalize<<<n, 256, 0, ctx->stream>>>(dn);
     ITN_LAUNCH_CHECK(ctx);
   }
+  for (int i = 0; i < n; ++i) net->touch(verts[i]);
   net->topo_version++;
   API_END
 }

@@ -425,6 +425,8 @@ struct RebJob {
   long long n_out;   // elements of the new tensor (offset of its imaginary plane)
   long long stI, stJ, stC, stQ;  // canonical strides of the tile's left / right index, the tile index and the CTA index
   int side, chi_new, inner_is_c;  // inner_is_c: the tile index c is the fastest bond (F2 tiles), else the left index is
+  double* Fown;      // chi_new == 16 only: the new tensor is also written tile-major, in place over X (same layout) ...
+  double* Foth;      // ... and into the other tile layout, so that no relayout pass is needed after the gate layer
 };
 
 template <bool C>
@@ -500,6 +502,27 @@ __global__ void __launch_bounds__(kThreads, 2) k_rebuild(const RebJob* __restric
     J.out[off] = src[0];
     if (C) J.out[J.n_out + off] = src[256];
   }
+  if (J.Fown) {
+    // own layout: tile (s', q, c) is this CTA's smem tile as it stands (same swizzle), 8 tiles contiguous per s'
+    for (int sp = 0; sp < D; ++sp) {
+      double* g = J.Fown + (((size_t)sp * 16 + q) * 16 + half * kTilesPerCta) * TILE;
+      for (int e = tid; e < kTilesPerCta * TILE; e += kThreads) {
+        const int w = e / TILE, r = e - w * TILE;
+        g[e] = Xs[(sp * kTilesPerCta + w) * TS + r];
+      }
+    }
+    // other layout: element (i, j) of tile c goes to tile (j, i) at position (c, q)  (the scatter of k_fast)
+    const int w = tid & 7;
+    const int c = half * kTilesPerCta + w;
+    const int pos = swz(c, q);
+    for (int sp = 0; sp < D; ++sp) {
+      double* wbase = J.Foth + (size_t)sp * 256 * TILE;
+      for (int e = tid >> 3; e < TILE; e += kThreads / 8) {
+        const int p = e >> 8, ij = e & 255, i = ij & 15, jj = ij >> 4;
+        wbase[((size_t)(jj * 16 + i)) * TILE + p * 256 + pos] = Xs[(sp * kTilesPerCta + w) * TS + p * 256 + swz(i, jj)];
+      }
+    }
+  }
 }
 
 struct FastCache {
@@ -516,7 +539,10 @@ struct FastCache {
   double** d_staged = nullptr;
   RelayoutJob* d_rjobs = nullptr;  // [nb] relayout descriptors, slot i at index i
   std::vector<char> stale;         // [nb] tile-major copies not built yet (site tensor still on the host)
+  std::vector<uint64_t> built;     // [nb] itn_net::tver of the tensor the tile-major copies were built from
+  std::vector<const double*> built_ptr;  // [nb] and its storage
   std::vector<int> sweep_verts;    // vertices of `sweep`, position order
+  std::vector<int> direct;         // slots whose tile-major copies were rewritten by k_rebuild (pending itn_fast_commit_direct)
 };
 
 void release(itn_net* net, FastCache* fc) {
@@ -605,7 +631,11 @@ void relayout_launch(itn_net* net, FastCache* fc, int lo, int hi) {
     k_fast_relayout_f2<false><<<grid, 256, rsm, ctx->stream>>>(dj, fc->F2, d);
   }
   ITN_LAUNCH_CHECK(ctx);
-  for (int i = lo; i < hi; ++i) fc->stale[i] = 0;
+  for (int i = lo; i < hi; ++i) {
+    fc->stale[i] = 0;
+    fc->built[i] = net->tver[fc->verts[i]];
+    fc->built_ptr[i] = net->T[fc->verts[i]].p;
+  }
 }
 
 // (Re)builds the tile-major copies of every eligible vertex when the network changed.
@@ -635,8 +665,10 @@ FastCache* ensure_cache(itn_net* net) {
   if (!fc) net->fast = fc = new FastCache();
   const int TILE = net->cplx ? 512 : 256;
   if (fc->topo_version != net->topo_version || fc->verts != verts) {
+    bool fresh = false;
     if (fc->verts != verts || fc->d != d || !fc->F1) {  // same bucket (e.g. after a gate layer): keep the buffers
       release(net, fc);
+      fresh = true;
       fc->verts = verts;
       fc->nb = (int)verts.size();
       fc->d = d;
@@ -651,23 +683,34 @@ FastCache* ensure_cache(itn_net* net) {
       fc->d_msg = (const double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
       fc->d_staged = (double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
       fc->d_rjobs = (RelayoutJob*)itn_dev_alloc(ctx, (size_t)fc->nb * sizeof(RelayoutJob));
+      fc->built.assign(fc->nb, ~0ull);
+      fc->built_ptr.assign(fc->nb, nullptr);
+      fc->stale.assign(fc->nb, 0);
     }
+    if (net->tver.size() != (size_t)net->nv) net->tver.assign(net->nv, 0);
     std::vector<RelayoutJob> jobs(fc->nb);
     for (int i = 0; i < fc->nb; ++i) jobs[i] = {net->T[verts[i]].p, net->T[verts[i]].n, (long long)i};
     CUDA_CHECK(cudaMemcpyAsync(fc->d_rjobs, jobs.data(), jobs.size() * sizeof(RelayoutJob), cudaMemcpyHostToDevice, ctx->stream));
     fc->vslot.assign(net->nv, -1);
     for (int i = 0; i < fc->nb; ++i) fc->vslot[verts[i]] = i;
-    // tensors whose host buffer has not been copied yet are laid out by the upload pipeline (itn_fast_relayout_range)
+    // only the slots whose tensor changed since their tile-major copies were built are laid out again; tensors whose
+    // host buffer has not been copied yet are left to the upload pipeline (itn_fast_relayout_range)
+    std::vector<char> todo(fc->nb, 0);
+    for (int i = 0; i < fc->nb; ++i)
+      todo[i] = fresh || fc->stale[i] || fc->built[i] != net->tver[verts[i]] || fc->built_ptr[i] != net->T[verts[i]].p;
     fc->stale.assign(fc->nb, 0);
     for (const PendingUpload& pu : net->pending)
-      if (fc->vslot[pu.v] >= 0) fc->stale[fc->vslot[pu.v]] = 1;
+      if (fc->vslot[pu.v] >= 0) {
+        fc->stale[fc->vslot[pu.v]] = 1;
+        todo[fc->vslot[pu.v]] = 0;
+      }
     for (int lo = 0; lo < fc->nb;) {
-      if (fc->stale[lo]) {
+      if (!todo[lo]) {
         ++lo;
         continue;
       }
       int hi = lo;
-      while (hi < fc->nb && !fc->stale[hi]) ++hi;
+      while (hi < fc->nb && todo[hi]) ++hi;
       relayout_launch(net, fc, lo, hi);
       lo = hi;
     }
@@ -882,10 +925,23 @@ void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs) {
 }
 
 // New site tensors after the gate: out (canonical layout, bond `slot` now chi_new <= 16) = A . T on the fused (s, l) index.
+// Called after the gate layer has committed its new tensors: the slots k_rebuild wrote tile-major are current.
+void itn_fast_commit_direct(itn_net* net) {
+  FastCache* fc = (FastCache*)net->fast;
+  if (!fc) return;
+  for (int slot : fc->direct) {
+    const int v = fc->verts[slot];
+    fc->built[slot] = net->tver[v];
+    fc->built_ptr[slot] = net->T[v].p;
+  }
+  fc->direct.clear();
+}
+
 void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs) {
   if (jobs.empty()) return;
   FastCache* fc = ensure_cache(net);
   ITN_REQUIRE(fc && fc->d == 2, ITN_EINVAL, "tile path is not available");
+  fc->direct.clear();
   itn_ctx* ctx = net->ctx;
   std::vector<RebJob> rj(jobs.size());
   for (size_t j = 0; j < jobs.size(); ++j) {
@@ -905,6 +961,10 @@ void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs) {
     R.n_out = acc;
     R.chi_new = J.chi_new;
     R.side = (J.slot & 1) ? 0 : 1;
+    const bool direct = J.chi_new == kChi;
+    R.Fown = direct ? (J.slot >= 2 ? fc->F2 : fc->F1) + off : nullptr;
+    R.Foth = direct ? (J.slot >= 2 ? fc->F1 : fc->F2) + off : nullptr;
+    if (direct) fc->direct.push_back(fc->vslot[J.v]);
     if (J.slot >= 2) {  // F2 tiles: (i, j) = (a3, a4), c = a1, q = a2
       R.X = fc->F2 + off;
       R.stI = st[2]; R.stJ = st[3]; R.stC = st[0]; R.stQ = st[1];

@@ -118,6 +118,12 @@ struct itn_net {
   std::vector<DevTensor> T;  // per vertex
   std::vector<DevTensor> M;  // per directed edge
   uint64_t topo_version = 0;  // bumped whenever a tensor pointer / bond dim changes
+  std::vector<uint64_t> tver;  // per vertex: bumped whenever the contents (or storage) of its site tensor change
+  void touch(int v) {
+    if (tver.size() != (size_t)nv) tver.assign(nv, 0);
+    tver[v]++;
+    topo_version++;
+  }
   double last_total_ms = 0, last_contract_ms = 0;
   std::vector<PendingUpload> pending;  // deferred host tensors: device storage exists, contents arrive with the next consumer
   void* fast = nullptr;  // fast-path cache (owned by itn_fast.cu)
@@ -224,6 +230,8 @@ struct FastRebuildJob {
 bool itn_fast_gate_site_ok(itn_net* net, int v);
 void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs);
 void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs);
+// after the new tensors are committed: marks the tile-major copies that itn_fast_rebuild wrote directly as current
+void itn_fast_commit_direct(itn_net* net);
 
 // ---- multi-GPU (itn_dist.cu) ----
 bool itn_is_local(const itn_net* net, int v);

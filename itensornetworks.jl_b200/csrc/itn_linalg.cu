@@ -39,56 +39,76 @@ __device__ __forceinline__ double wsum(double v) {
 
 // ------------------------------------------------------------------------------------------------
 // one-sided (Hestenes) Jacobi SVD, one CTA per matrix, planar storage, column-major
-//   in : A (m x n)                     out: A = U diag(sigma) (columns not normalised), V (n x n),
+//   in : A (m x n)                     out: us = A V = U diag(sigma) (columns not normalised), V (n x n, optional),
 //                                           sigma[n] sorted descending, perm[n] (sorted rank -> column)
+// A group of LP lanes owns one column pair of a round (32 / LP pairs per warp), so that a 64 x 64 matrix keeps
+// 16 warps busy and three matrices share an SM.  Column norms are recomputed exactly at the start of every sweep
+// and at the end (singular values); inside a sweep they follow the rotation identities a' = a - t|g|, b' = b + t|g|.
 // ------------------------------------------------------------------------------------------------
 struct SvdJob {
-  double* a;      // planar m x n (im plane at +m*n)
-  double* v;      // planar n x n (im plane at +n*n)
-  double* sigma;  // n
-  int* perm;      // n
+  double* a;       // planar m x n input (im plane at +m*n); overwritten with U*Sigma unless `us` is set
+  double* v;       // planar n x n (im plane at +n*n), or null: V is not accumulated
+  double* sigma;   // n
+  int* perm;       // n
   int m, n;
+  double* us;      // optional separate output for U*Sigma (a stays intact)
+  const int* skip; // optional device flag: non-zero -> this matrix needs no decomposition
 };
 
 constexpr int kSvdMaxThreads = 1024;
 constexpr int kSvdMaxSweeps = 30;
 
-// Block size: one warp per column pair of a round when possible (n/2 pairs), 4..32 warps.
-template <bool C>
+template <int LP>
+__device__ __forceinline__ double gsum(double v, unsigned mask) {
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+template <bool C, int LP>
 __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __restrict__ jobs, int smem_doubles) {
   extern __shared__ double sm[];
   __shared__ int s_rot;
-  __shared__ double s_norm[256];  // squared column norms, kept up to date across rotations
+  __shared__ double s_norm[256];  // squared column norms
   __shared__ double s_red[33];
   const SvdJob J = jobs[blockIdx.x];
+  if (J.skip && *J.skip) return;
   const int m = J.m, n = J.n;
   if (n == 0 || m == 0) return;
   const long long mn = (long long)m * n, nn = (long long)n * n;
   const int P = C ? 2 : 1;
-  const bool in_smem = (mn + nn) * P <= smem_doubles;
-  double* Ar = in_smem ? sm : J.a;
-  double* Ai = C ? (in_smem ? sm + mn : J.a + mn) : nullptr;
-  double* Vr = in_smem ? sm + P * mn : J.v;
-  double* Vi = C ? (in_smem ? sm + P * mn + nn : J.v + nn) : nullptr;
+  const bool has_v = J.v != nullptr;
+  double* dst = J.us ? J.us : J.a;
+  const bool in_smem = (mn + (has_v ? nn : 0)) * P <= smem_doubles;
+  double* Ar = in_smem ? sm : dst;
+  double* Ai = C ? Ar + mn : nullptr;
+  double* Vr = has_v ? (in_smem ? sm + P * mn : J.v) : nullptr;
+  double* Vi = (C && has_v) ? Vr + nn : nullptr;
   const int nthreads = blockDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-  if (in_smem)
-    for (long long i = tid; i < mn * P; i += nthreads) sm[i] = J.a[i];
-  for (long long i = tid; i < nn; i += nthreads) {
-    Vr[i] = (i % n == i / n) ? 1.0 : 0.0;
-    if (C) Vi[i] = 0.0;
-  }
-  __syncthreads();
-  // squared column norms
-  for (int j = warp; j < n; j += nwarps) {
-    double a2 = 0.0;
-    for (int i = lane; i < m; i += 32) {
-      const double r = Ar[(long long)j * m + i], im = C ? Ai[(long long)j * m + i] : 0.0;
-      a2 += r * r + im * im;
+  constexpr int PW = 32 / LP;
+  const int sub = lane / LP, sl = lane % LP;
+  const unsigned gmask = (LP == 32) ? 0xffffffffu : (((1u << LP) - 1u) << (sub * LP));
+  if (in_smem || dst != J.a)
+    for (long long i = tid; i < mn * P; i += nthreads) Ar[i] = J.a[i];
+  if (has_v)
+    for (long long i = tid; i < nn; i += nthreads) {
+      Vr[i] = (i % n == i / n) ? 1.0 : 0.0;
+      if (C) Vi[i] = 0.0;
     }
-    a2 = wsum(a2);
-    if (lane == 0) s_norm[j] = a2;
-  }
+  __syncthreads();
+  auto column_norms = [&]() {
+    for (int j = warp * PW + sub; j < n; j += nwarps * PW) {
+      double a2 = 0.0;
+      for (int i = sl; i < m; i += LP) {
+        const double r = Ar[(long long)j * m + i], im = C ? Ai[(long long)j * m + i] : 0.0;
+        a2 += r * r + im * im;
+      }
+      a2 = gsum<LP>(a2, gmask);
+      if (sl == 0) s_norm[j] = a2;
+    }
+  };
+  column_norms();
   __syncthreads();
   // columns whose norm is below ~1e-19 ||A||_F are numerically null: rotating them only amplifies underflow
   // noise (they appear whenever rank(A) < n, e.g. wide matrices and rank-deficient Gram matrices)
@@ -104,9 +124,10 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
   const double tol = sqrt((double)m) * 2.220446049250313e-16;
   for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
     if (tid == 0) s_rot = 0;
+    if (sweep > 0) column_norms();
     __syncthreads();
     for (int round = 0; round < ne - 1; ++round) {
-      for (int k = warp; k < ne / 2; k += nwarps) {
+      for (int k = warp * PW + sub; k < ne / 2; k += nwarps * PW) {
         int p, q;
         if (k == 0) {
           p = ne - 1;
@@ -128,58 +149,54 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
         double* api = C ? Ai + (long long)p * m : nullptr;
         double* aqi = C ? Ai + (long long)q * m : nullptr;
         double gr = 0, gi = 0;
-        for (int i = lane; i < m; i += 32) {
+        for (int i = sl; i < m; i += LP) {
           const double pr = apr[i], qr = aqr[i];
           const double pi = C ? api[i] : 0.0, qi = C ? aqi[i] : 0.0;
           gr += pr * qr + pi * qi;  // conj(a_p) . a_q
           gi += pr * qi - pi * qr;
         }
-        gr = wsum(gr);
-        gi = C ? wsum(gi) : 0.0;
+        gr = gsum<LP>(gr, gmask);
+        gi = C ? gsum<LP>(gi, gmask) : 0.0;
         const double g2 = gr * gr + gi * gi;
         if (g2 == 0.0 || !(g2 > tol * tol * alpha * beta)) continue;
-        const double gabs = sqrt(g2);
+        const double ginv = rsqrt(g2);
+        const double gabs = g2 * ginv;
         // phase e^{-i phi} applied to column q so that the inner product becomes real positive
-        const double er = gr / gabs, ei = -gi / gabs;
-        const double zeta = (beta - alpha) / (2.0 * gabs);
+        const double er = gr * ginv, ei = -gi * ginv;
+        const double zeta = (beta - alpha) * 0.5 * ginv;
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        double na = 0.0, nb = 0.0;
-        for (int i = lane; i < m; i += 32) {
+        const double c = rsqrt(1.0 + t * t), s = c * t;
+        for (int i = sl; i < m; i += LP) {
           const double pr = apr[i], qr0 = aqr[i];
           const double pi = C ? api[i] : 0.0, qi0 = C ? aqi[i] : 0.0;
           const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
-          const double npr = c * pr - s * qr, nqr = s * pr + c * qr;
-          const double npi = C ? c * pi - s * qi : 0.0, nqi = C ? s * pi + c * qi : 0.0;
-          apr[i] = npr;
-          aqr[i] = nqr;
+          apr[i] = c * pr - s * qr;
+          aqr[i] = s * pr + c * qr;
           if (C) {
-            api[i] = npi;
-            aqi[i] = nqi;
-          }
-          na += npr * npr + npi * npi;
-          nb += nqr * nqr + nqi * nqi;
-        }
-        double* vpr = Vr + (long long)p * n;
-        double* vqr = Vr + (long long)q * n;
-        double* vpi = C ? Vi + (long long)p * n : nullptr;
-        double* vqi = C ? Vi + (long long)q * n : nullptr;
-        for (int i = lane; i < n; i += 32) {
-          const double pr = vpr[i], qr0 = vqr[i];
-          const double pi = C ? vpi[i] : 0.0, qi0 = C ? vqi[i] : 0.0;
-          const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
-          vpr[i] = c * pr - s * qr;
-          vqr[i] = s * pr + c * qr;
-          if (C) {
-            vpi[i] = c * pi - s * qi;
-            vqi[i] = s * pi + c * qi;
+            api[i] = c * pi - s * qi;
+            aqi[i] = s * pi + c * qi;
           }
         }
-        na = wsum(na);
-        nb = wsum(nb);
-        if (lane == 0) {
-          s_norm[p] = na;  // recomputed, not updated by recurrence: no drift
-          s_norm[q] = nb;
+        if (has_v) {
+          double* vpr = Vr + (long long)p * n;
+          double* vqr = Vr + (long long)q * n;
+          double* vpi = C ? Vi + (long long)p * n : nullptr;
+          double* vqi = C ? Vi + (long long)q * n : nullptr;
+          for (int i = sl; i < n; i += LP) {
+            const double pr = vpr[i], qr0 = vqr[i];
+            const double pi = C ? vpi[i] : 0.0, qi0 = C ? vqi[i] : 0.0;
+            const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
+            vpr[i] = c * pr - s * qr;
+            vqr[i] = s * pr + c * qr;
+            if (C) {
+              vpi[i] = c * pi - s * qi;
+              vqi[i] = s * pi + c * qi;
+            }
+          }
+        }
+        if (sl == 0) {
+          s_norm[p] = fmax(alpha - t * gabs, 0.0);
+          s_norm[q] = beta + t * gabs;
           // rotations at the rounding level of the inner product are applied but do not keep the iteration alive
           if (g2 > 64.0 * tol * tol * alpha * beta) s_rot = 1;
         }
@@ -190,7 +207,9 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
     __syncthreads();
     if (!any) break;
   }
-  // singular values = column norms; stable descending order
+  // singular values = exact column norms; stable descending order
+  column_norms();
+  __syncthreads();
   for (int j = tid; j < n; j += nthreads) {
     const double sj = s_norm[j];
     int rank = 0;
@@ -202,30 +221,174 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
     J.perm[rank] = j;
   }
   if (in_smem) {
-    for (long long i = tid; i < mn * P; i += nthreads) J.a[i] = sm[i];
-    for (long long i = tid; i < nn * P; i += nthreads) J.v[i] = sm[P * mn + i];
+    for (long long i = tid; i < mn * P; i += nthreads) dst[i] = sm[i];
+    if (has_v)
+      for (long long i = tid; i < nn * P; i += nthreads) J.v[i] = sm[P * mn + i];
   }
+}
+
+template <bool C, int LP>
+void launch_jacobi(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int pairs, size_t smem) {
+  constexpr int PW = 32 / LP;
+  const int warps = std::min(32, std::max(1, (pairs + PW - 1) / PW));
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<C, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_jacobi_svd<C, LP><<<njobs, warps * 32, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
+  ITN_LAUNCH_CHECK(ctx);
 }
 
 void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
   if (jobs.empty()) return;
-  int maxn = 0;
+  int maxn = 0, maxm = 0;
   size_t need = 0;
   for (auto& j : jobs) {
     ITN_REQUIRE(j.n <= 256, ITN_EUNSUPPORTED, "Jacobi SVD supports at most 256 columns");
     maxn = std::max(maxn, j.n);
-    need = std::max(need, ((size_t)j.m * j.n + (size_t)j.n * j.n) * (cplx ? 2 : 1));
+    maxm = std::max(maxm, j.m);
+    need = std::max(need, ((size_t)j.m * j.n + (j.v ? (size_t)j.n * j.n : 0)) * (cplx ? 2 : 1));
   }
   size_t smem = std::min<size_t>(need * sizeof(double), 200 * 1024);
-  const int warps = std::min(32, std::max(4, (maxn + 1) / 2));
   DevBuf jb(ctx, jobs.size() * sizeof(SvdJob));
   const SvdJob* dj = itn_upload(ctx, jobs, jb);
-  if (cplx) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_jacobi_svd<true><<<(unsigned)jobs.size(), warps * 32, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
+  const int pairs = (maxn + 1) / 2;
+  const unsigned nj = (unsigned)jobs.size();
+  if (maxm <= 64) {
+    if (cplx) launch_jacobi<true, 16>(ctx, dj, nj, pairs, smem);
+    else launch_jacobi<false, 16>(ctx, dj, nj, pairs, smem);
   } else {
-    CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_jacobi_svd<false><<<(unsigned)jobs.size(), warps * 32, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
+    if (cplx) launch_jacobi<true, 32>(ctx, dj, nj, pairs, smem);
+    else launch_jacobi<false, 32>(ctx, dj, nj, pairs, smem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched Cholesky of small Hermitian matrices, one CTA (n <= 64 threads, thread i = row i) per matrix:
+//   K = conj(H) - shift_rel * trace(H) * 1,  H = (C + C^H) / 2;   K = L L^H
+// With R = L^H this is conj(C) = R^H R, i.e. C = R^T conj(R): the same R factor (up to the unitary freedom of its row
+// index) as the eigen route R = Lambda^1/2 V^T of k_su_build_R, at a fraction of the cost; R^+ = R^-1 = L^-H.
+// ok = 0 when a pivot falls below n eps max_i K_ii (numerically rank deficient): the caller's eigen route takes over.
+// With R == null the kernel is a definiteness test only (support test of the BP environments).
+// ------------------------------------------------------------------------------------------------
+struct CholJob {
+  const double* c;  // planar n x n
+  double* R;        // planar n x n, or null
+  double* Rp;       // planar n x n
+  int* ok;
+  int n;
+  double shift_rel;
+};
+
+template <bool C>
+__global__ void __launch_bounds__(64) k_chol(const CholJob* __restrict__ jobs) {
+  extern __shared__ double sm[];
+  __shared__ double s_piv, s_max, s_tr;
+  __shared__ int s_fail;
+  const CholJob J = jobs[blockIdx.x];
+  const int n = J.n, n2 = n * n;
+  const int i = threadIdx.x;
+  double* Kr = sm;
+  double* Ki = sm + n2;
+  // K = conj((C + C^H) / 2), lower triangle
+  if (i < n)
+    for (int j = 0; j <= i; ++j) {
+      Kr[i + n * j] = 0.5 * (J.c[i + n * j] + J.c[j + n * i]);
+      if (C) Ki[i + n * j] = -0.5 * (J.c[n2 + i + n * j] - J.c[n2 + j + n * i]);
+    }
+  __syncthreads();
+  if (i == 0) {
+    double mx = 0.0, tr = 0.0;
+    for (int k = 0; k < n; ++k) {
+      mx = fmax(mx, Kr[k + n * k]);
+      tr += Kr[k + n * k];
+    }
+    s_max = mx;
+    s_tr = tr;
+    s_fail = 0;
+  }
+  __syncthreads();
+  const double shift = J.shift_rel * s_tr;
+  const double thr = s_max * n * 2.220446049250313e-16;
+  if (i < n && shift != 0.0) Kr[i + n * i] -= shift;
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    if (i == k) {
+      const double d = Kr[k + n * k];
+      if (!(d > thr)) s_fail = 1;
+      s_piv = d;
+    }
+    __syncthreads();
+    if (s_fail) break;
+    const double rs = rsqrt(s_piv);
+    if (i == k) {
+      Kr[k + n * k] = s_piv * rs;
+      if (C) Ki[k + n * k] = 0.0;
+    } else if (i > k && i < n) {
+      Kr[i + n * k] *= rs;
+      if (C) Ki[i + n * k] *= rs;
+    }
+    __syncthreads();
+    if (i > k && i < n) {
+      const double lr = Kr[i + n * k], li = C ? Ki[i + n * k] : 0.0;
+      for (int j = k + 1; j <= i; ++j) {
+        const double mr = Kr[j + n * k], mi = C ? Ki[j + n * k] : 0.0;
+        // K[i,j] -= L[i,k] conj(L[j,k])
+        Kr[i + n * j] -= lr * mr + li * mi;
+        if (C) Ki[i + n * j] -= li * mr - lr * mi;
+      }
+    }
+    __syncthreads();
+  }
+  if (s_fail) {
+    if (i == 0) *J.ok = 0;
+    return;
+  }
+  if (i == 0) *J.ok = 1;
+  if (!J.R || i >= n) return;
+  // R[a, o] = conj(L[o, a]) (upper triangular)
+  for (int a = 0; a < n; ++a) {
+    const bool up = i >= a;  // thread i = column o
+    J.R[a + n * i] = up ? Kr[i + n * a] : 0.0;
+    if (C) J.R[n2 + a + n * i] = up ? -Ki[i + n * a] : 0.0;
+  }
+  // X = L^-1, column i computed by thread i;  R^+[o, a] = conj(X[a, o]): thread o = i writes its own column of X
+  // into row o of R^+ (coalesced across threads) and reads back only what it wrote itself
+  double* Pr = J.Rp;
+  double* Pi = J.Rp + n2;
+  for (int a = 0; a < n; ++a) {
+    double xr = 0.0, xi = 0.0;
+    if (a == i) {
+      xr = 1.0 / Kr[a + n * a];
+    } else if (a > i) {
+      double sr = 0.0, si = 0.0;
+      for (int k = i; k < a; ++k) {
+        const double lr = Kr[a + n * k], li = C ? Ki[a + n * k] : 0.0;
+        const double yr = Pr[i + n * k], yi = C ? -Pi[i + n * k] : 0.0;  // X[k, i] = conj(R^+[i, k])
+        sr += lr * yr - li * yi;
+        si += lr * yi + li * yr;
+      }
+      const double inv = 1.0 / Kr[a + n * a];
+      xr = -sr * inv;
+      xi = -si * inv;
+    }
+    Pr[i + n * a] = xr;
+    if (C) Pi[i + n * a] = -xi;
+  }
+}
+
+void run_chol(itn_ctx* ctx, bool cplx, const std::vector<CholJob>& jobs) {
+  if (jobs.empty()) return;
+  int maxn = 0;
+  for (auto& j : jobs) maxn = std::max(maxn, j.n);
+  ITN_REQUIRE(maxn <= 64, ITN_EINVAL, "batched Cholesky supports n <= 64");
+  const size_t smem = (size_t)maxn * maxn * (cplx ? 2 : 1) * sizeof(double);
+  DevBuf jb(ctx, jobs.size() * sizeof(CholJob));
+  const CholJob* dj = itn_upload(ctx, jobs, jb);
+  const int threads = maxn <= 32 ? 32 : 64;
+  if (cplx) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_chol<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chol<true><<<(unsigned)jobs.size(), threads, smem, ctx->stream>>>(dj);
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_chol<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_chol<false><<<(unsigned)jobs.size(), threads, smem, ctx->stream>>>(dj);
   }
   ITN_LAUNCH_CHECK(ctx);
 }
@@ -289,6 +452,7 @@ struct EigFnJob {
   double* out;        // planar chi x chi
   int chi;
   int* deficient;     // optional: set to 1 when eigenvalues were dropped by the cutoff
+  const int* skip;    // optional device flag: non-zero -> nothing to do (the Cholesky test proved full support)
 };
 // out = V_kept f(lambda) V_kept^H with lambda_j = sigma_j * sign(Re <v_j, (U Sigma)_j>); diagonal inputs
 // short-circuit to f(diag) (map_diag, apply.jl:22).  fn: 0 sqrt, 1 inv sqrt, 2 inv, 3 one (support projector).
@@ -298,6 +462,7 @@ __global__ void __launch_bounds__(256) k_eig_fn(const EigFnJob* __restrict__ job
   __shared__ double fr[256], fi[256];
   __shared__ int s_keep, s_diag;
   const EigFnJob J = jobs[blockIdx.x];
+  if (J.skip && *J.skip) return;
   const int n = J.chi, n2 = n * n;
   const int tid = threadIdx.x;
   if (tid == 0) s_diag = 1;
@@ -434,8 +599,10 @@ struct SuEdge {
   int d[2], n[2], r[2];
   int chi;                // current bond dimension
   const double* gate;     // planar d1 d2 d1 d2: g[s1' + d1*(s2' + d2*(s1 + d1*s2))]
-  double* theta;          // planar (r1 d1) x (r2 d2)
-  double* tv;             // V of theta
+  const int* rok[2];      // device flag: R / R^+ of this side already came from the Cholesky route
+  double* theta0;         // planar (r1 d1) x (r2 d2): theta' as built (input of the SVD, kept for V)
+  double* theta;          // planar (r1 d1) x (r2 d2): U Sigma after the SVD
+  double* tv;             // V of theta (kept columns only, rebuilt from theta0 and U Sigma)
   double* tsig;
   int* tperm;
   int newdim;             // filled on the host after truncation
@@ -446,6 +613,7 @@ template <bool C>
 __global__ void __launch_bounds__(256) k_su_build_R(const SuEdge* __restrict__ edges) {
   const SuEdge E = edges[blockIdx.x >> 1];
   const int side = blockIdx.x & 1;
+  if (E.rok[side] && *E.rok[side]) return;
   const int n = E.n[side], r = E.r[side];
   const long long n2 = (long long)n * n, rn = (long long)r * n;
   const double lmax = E.gsig[side][0];
@@ -499,8 +667,37 @@ __global__ void __launch_bounds__(256) k_su_theta(const SuEdge* __restrict__ edg
         accr += gr * tr - gim * ti;
         acci += gr * ti + gim * tr;
       }
-    E.theta[idx] = accr;
-    if (C) E.theta[mn + idx] = acci;
+    E.theta0[idx] = accr;
+    if (C) E.theta0[mn + idx] = acci;
+  }
+}
+
+// V of the kept singular triplets, rebuilt from theta' = U S V^H:  V[:, col] = theta'^H (U S)[:, col] / sigma^2.
+// (The Jacobi SVD of theta' does not accumulate V; for the kept columns sigma / sigma_max >= sqrt(cutoff), and
+// the product R1' R2' = U_k U_k^H theta' does not depend on the accuracy of the small-sigma rows at all.)
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_vrec(const SuEdge* __restrict__ edges) {
+  const SuEdge E = edges[blockIdx.x];
+  const int m = E.r[0] * E.d[0], nc = E.r[1] * E.d[1], nd = E.newdim;
+  const long long mn = (long long)m * nc, nn = (long long)nc * nc;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < nc * nd; idx += gridDim.y * blockDim.x) {
+    const int j = idx % nc, lp = idx / nc;
+    const int col = E.tperm[lp];
+    const double sig = E.tsig[lp];
+    const double f = sig > 0.0 ? 1.0 / (sig * sig) : 0.0;
+    double accr = 0.0, acci = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double ar = E.theta0[i + (long long)m * j], ur = E.theta[i + (long long)m * col];
+      if (C) {
+        const double ai = E.theta0[mn + i + (long long)m * j], ui = E.theta[mn + i + (long long)m * col];
+        accr += ar * ur + ai * ui;  // conj(a) * u
+        acci += ar * ui - ai * ur;
+      } else {
+        accr += ar * ur;
+      }
+    }
+    E.tv[j + (long long)nc * col] = f * accr;
+    if (C) E.tv[nn + j + (long long)nc * col] = f * acci;
   }
 }
 
@@ -798,7 +995,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     ITN_REQUIRE(g.nc <= 256 && g.m <= 512, ITN_EUNSUPPORTED, "simple update supports bond matrices up to 512 x 256");
     const int cand = std::min(g.m, g.nc);
     max_cand = std::max(max_cand, cand);
-    ws_doubles += (size_t)P * ((size_t)g.m * g.nc + (size_t)g.nc * g.nc);
+    ws_doubles += (size_t)P * (2 * (size_t)g.m * g.nc + (size_t)g.nc * g.nc);
     for (int s = 0; s < 2; ++s) ws_doubles += (size_t)P * g.nn[s] * g.d[s] * cand;
     sig_total += g.nc;
   }
@@ -819,6 +1016,12 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   DevBuf env_s(ctx, std::max<size_t>(env_sig, 1) * sizeof(double)), env_p(ctx, std::max<size_t>(env_sig, 1) * sizeof(int));
   DevBuf env_flag(ctx, std::max<size_t>(env_count, 1) * sizeof(int));
   CUDA_CHECK(cudaMemsetAsync(env_flag.p, 0, std::max<size_t>(env_count, 1) * sizeof(int), ctx->stream));
+  // Cholesky fast routes (run_chol): rok[2 i + s] = 1 when R / R^+ of that side came from the Cholesky factor of its
+  // bond environment, env_ok[k] = 1 when environment k is safely positive definite (nothing for the eigen cutoff to drop)
+  DevBuf rok(ctx, 2 * (size_t)n * sizeof(int)), env_ok(ctx, std::max<size_t>(env_count, 1) * sizeof(int));
+  CUDA_CHECK(cudaMemsetAsync(rok.p, 0, 2 * (size_t)n * sizeof(int), ctx->stream));
+  CUDA_CHECK(cudaMemsetAsync(env_ok.p, 0, std::max<size_t>(env_count, 1) * sizeof(int), ctx->stream));
+  std::vector<CholJob> chol_r, chol_env;
   struct EnvRef {
     int edge_i, side, slot;
     const double* pi;
@@ -887,7 +1090,12 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       E.d[s] = g.d[s];
       E.n[s] = g.nn[s];
       E.r[s] = g.r[s];
-      gj.push_back({Cm, Vm, sp, pp, g.nn[s], g.nn[s]});
+      {
+        SvdJob gjob = {Cm, Vm, sp, pp, g.nn[s], g.nn[s], nullptr, rok.as<int>() + 2 * (size_t)i + s};
+        gj.push_back(gjob);
+      }
+      E.rok[s] = rok.as<int>() + 2 * (size_t)i + s;
+      if (g.r[s] == g.nn[s] && g.nn[s] <= 64) chol_r.push_back({Cm, E.R[s], E.Rp[s], rok.as<int>() + 2 * (size_t)i + s, g.nn[s], 0.0});
       sp += g.nn[s];
       pp += g.nn[s];
       // hermitised environments (map_eigvals symmetrises its argument, apply.jl:9-15 with ishermitian = true)
@@ -904,9 +1112,13 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
           double* vv = env_v.as<double>() + off;
           double* pi = env_pi.as<double>() + off;
           const size_t k = env_refs.size();
-          ej_svd.push_back({us, vv, env_s.as<double>() + env_sig_off, env_p.as<int>() + env_sig_off, c, c});
+          SvdJob ejob = {us, vv, env_s.as<double>() + env_sig_off, env_p.as<int>() + env_sig_off, c, c, nullptr,
+                         env_ok.as<int>() + k};
+          ej_svd.push_back(ejob);
           ej_fn.push_back({envp, us, vv, env_s.as<double>() + env_sig_off, env_p.as<int>() + env_sig_off, pi, c,
-                           env_flag.as<int>() + k});
+                           env_flag.as<int>() + k, env_ok.as<int>() + k});
+          // E - 100 eps tr(E) positive definite => every eigenvalue exceeds the reference's relative cutoff 10 eps
+          if (c <= 64) chol_env.push_back({envp, nullptr, nullptr, env_ok.as<int>() + k, c, 100.0 * 2.220446049250313e-16});
           env_refs.push_back({i, s, (int)j, pi});
           env_sig_off += c;
         }
@@ -926,11 +1138,15 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       }
     }
     E.gate = d_gates.as<double>() + goff[i] * P;
+    E.theta0 = w; w += (size_t)P * g.m * g.nc;
     E.theta = w; w += (size_t)P * g.m * g.nc;
     E.tv = w; w += (size_t)P * g.nc * g.nc;
     E.tsig = sp;
     E.tperm = pp;
-    tj.push_back({E.theta, E.tv, sp, pp, g.m, g.nc});
+    {
+      SvdJob tjob = {E.theta0, nullptr, sp, pp, g.m, g.nc, E.theta, nullptr};
+      tj.push_back(tjob);
+    }
     sp += g.nc;
     pp += g.nc;
     const int cand = std::min(g.m, g.nc);
@@ -950,7 +1166,9 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   }
   itn_run_vertex_jobs(net, specs);
   itn_fast_bond_envs(net, fast_env);
-  run_jacobi(ctx, cplx, gj);
+  run_chol(ctx, cplx, chol_r);
+  run_jacobi(ctx, cplx, gj);  // only the sides the Cholesky route did not settle (r < n, or rank deficient)
+  run_chol(ctx, cplx, chol_env);
   if (!ej_svd.empty()) {
     // projector onto the support of every environment: eigenvalues below 10 eps (relative) are dropped, as in
     // map_eigvals(sqrt / inv o sqrt, env; cutoff = 10 eps) (apply.jl:36,40-69)
@@ -1022,6 +1240,9 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   // ---- 3. T factors and the new site tensors ----
   for (int i = 0; i < n; ++i) se[i].newdim = newdim[i];
   CUDA_CHECK(cudaMemcpyAsync((void*)dse, se.data(), se.size() * sizeof(SuEdge), cudaMemcpyHostToDevice, ctx->stream));
+  if (cplx) k_su_vrec<true><<<dim3(n, 4), 256, 0, ctx->stream>>>(dse);
+  else k_su_vrec<false><<<dim3(n, 4), 256, 0, ctx->stream>>>(dse);
+  ITN_LAUNCH_CHECK(ctx);
   if (cplx) k_su_T<true><<<dim3(2 * n, 4), 256, 0, ctx->stream>>>(dse);
   else k_su_T<false><<<dim3(2 * n, 4), 256, 0, ctx->stream>>>(dse);
   ITN_LAUNCH_CHECK(ctx);
@@ -1112,6 +1333,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       net->T[v].n = sites[si].n_new;
       net->T[v].slab = tslab;
       tslab->refs++;
+      net->touch(v);
     }
     net->edim[g.e] = newdim[i];
     for (int dd = 0; dd < 2; ++dd) {
@@ -1134,6 +1356,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     ITN_LAUNCH_CHECK(ctx);
   }
   net->topo_version++;
+  if (!normalize) itn_fast_commit_direct(net);  // k_normalize2 rescaled the canonical tensors only
   for (int i = 0; i < n; ++i) {
     if (newdim_out) newdim_out[i] = newdim[i];
     if (truncerr_out) truncerr_out[i] = terr[i];
