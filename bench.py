@@ -316,8 +316,8 @@ def run_ours(args):
 
     # ---- simple-update gates/s (second half of BASELINE.json's metric), single GPU ------------------------
     su = None
-    if world == 1 and args.gates:
-        su = bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch)
+    if args.gates:
+        su = bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch, dist if world > 1 else None)
 
     if rank != 0:
         if world > 1:
@@ -347,7 +347,7 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clocks,
     }
     if su is not None:
-        su["frac_of_fp64_peak"] = su["algorithmic_tflops"] / peak["sustained"]
+        su["frac_of_fp64_peak_per_gpu"] = su["algorithmic_tflops"] / peak["sustained"] / world
         line["simple_update"] = su
     if args.cpu_baseline:
         n, dt, sample = cpu_reference_sample(dims, chi, dtype, args.cpu_budget)
@@ -369,7 +369,7 @@ def gate_flops(graph, chi, d, cplx):
     return tot
 
 
-def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch):
+def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch, dist=None):
     """One Trotter step = one two-site gate on every edge, applied as vertex-disjoint colour layers
     (apply(o, psi; envs = BP messages, maxdim = chi, cutoff = nothing), src/apply.jl:97-146), in place on the device.
     Every bond is truncated from d^2 chi = 64 back to chi = 16 singular values, so the lattice stays on the chi = 16 kernels."""
@@ -385,20 +385,29 @@ def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch):
     for layer in layers:
         E.apply_layer([gate] * len(layer), work, [graph.edges[e] for e in layer], maxdim=chi, cutoff=None)
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     ngates = 0
     terr = 0.0
+    per_layer = []
     for layer in layers:
+        ta = time.perf_counter()
         info = E.apply_layer([gate] * len(layer), work, [graph.edges[e] for e in layer], maxdim=chi, cutoff=None)
+        per_layer.append(round(1e3 * (time.perf_counter() - ta), 2))  # apply_layer returns after the device is done
         ngates += len(layer)
         terr = max(terr, float(np.max(info["truncation_error"])))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if dist is not None:  # every rank applies the same layers to its part of the lattice: the slowest rank counts
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
     work.close()
     fl = gate_flops(graph, chi, d, np.dtype(dtype).kind == "c")
-    return {"gates_per_s": ngates / dt, "ms_per_trotter_step": 1e3 * dt, "gates": ngates, "colour_layers": len(layers),
+    return {"gates_per_s": ngates / dt, "ms_per_trotter_step": 1e3 * dt, "gates": ngates, "colour_layers": len(layers), "ms_per_layer": per_layer,
             "max_truncation_error": terr, "algorithmic_tflops": fl / dt / 1e12,
-            "note": "wall clock incl. the host round trip per layer (new bond dimensions are read back); "
+            "note": "wall clock (max over ranks) incl. the host round trip per layer (new bond dimensions are read back); "
                     "algorithmic flops = F_gemm + F_qr of SURVEY.md 8(d)"}
 
 

@@ -35,9 +35,55 @@ extern "C" int itn_version(void) { return 100; }
   }                                              \
   return ITN_OK;
 
+namespace {
+constexpr size_t kBigBlock = (size_t)32 << 20;    // blocks of at least 32 MiB are recycled by the context
+constexpr size_t kBigRound = (size_t)64 << 20;    // their sizes are rounded up to 64 MiB so that similar requests match
+constexpr size_t kBigCacheMax = (size_t)64 << 30; // parked bytes above this are returned to the driver
+
+void big_trim(itn_ctx* ctx, size_t keep) {
+  while (ctx->big_cached > keep && !ctx->big_free.empty()) {
+    auto it = std::prev(ctx->big_free.end());
+    cudaFreeAsync(it->second, ctx->stream);
+    ctx->big_cached -= it->first;
+    ctx->big_free.erase(it);
+  }
+}
+}  // namespace
+
 void* itn_dev_alloc(itn_ctx* ctx, size_t bytes) {
   void* p = nullptr;
+  if (bytes >= kBigBlock) {
+    const size_t want = (bytes + kBigRound - 1) / kBigRound * kBigRound;
+    auto it = ctx->big_free.lower_bound(want);
+    if (it != ctx->big_free.end() && it->first <= want + want / 4) {
+      p = it->second;
+      ctx->big_live[p] = it->first;
+      ctx->big_cached -= it->first;
+      ctx->big_free.erase(it);
+      return p;
+    }
+    cudaError_t e = cudaMallocAsync(&p, want, ctx->stream);
+    if (e != cudaSuccess) {  // give the parked blocks back and retry once
+      cudaGetLastError();
+      big_trim(ctx, 0);
+      cudaStreamSynchronize(ctx->stream);
+      e = cudaMallocAsync(&p, want, ctx->stream);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw ItnError(ITN_ENOMEM, std::string("device allocation of ") + std::to_string(bytes) +
+                                     " bytes failed: " + cudaGetErrorString(e));
+    }
+    ctx->big_live[p] = want;
+    return p;
+  }
   cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    big_trim(ctx, 0);
+    cudaStreamSynchronize(ctx->stream);
+    e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     throw ItnError(ITN_ENOMEM, std::string("device allocation of ") + std::to_string(bytes) +
@@ -46,7 +92,16 @@ void* itn_dev_alloc(itn_ctx* ctx, size_t bytes) {
   return p;
 }
 void itn_dev_free(itn_ctx* ctx, void* p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  auto it = ctx->big_live.find(p);
+  if (it != ctx->big_live.end()) {
+    ctx->big_free.emplace(it->second, p);
+    ctx->big_cached += it->second;
+    ctx->big_live.erase(it);
+    if (ctx->big_cached > kBigCacheMax) big_trim(ctx, kBigCacheMax * 3 / 4);
+    return;
+  }
+  cudaFreeAsync(p, ctx->stream);
 }
 
 void itn_tensor_free(itn_ctx* ctx, DevTensor& t) {
@@ -502,6 +557,8 @@ static void ctx_destroy_now(itn_ctx* ctx) {
     destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
     if (f) f(ctx->nccl);
   }
+  big_trim(ctx, 0);
+  cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

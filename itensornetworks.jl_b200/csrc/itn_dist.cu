@@ -112,6 +112,20 @@ void itn_dist_allreduce_sum(itn_ctx* ctx, double* dev, int n) {
   NCCL_CHECK(api().AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
 }
 
+void itn_dist_p2p(itn_ctx* ctx, const std::vector<P2PSeg>& segs) {
+  if (ctx->nranks == 1) return;
+  ITN_REQUIRE(ctx->nccl, ITN_ENCCL, "context is not initialised for multi-GPU use (itn_ctx_init_dist)");
+  bool any = false;
+  for (const P2PSeg& sg : segs) any = any || sg.sn || sg.rn;
+  if (!any) return;
+  NCCL_CHECK(api().GroupStart());
+  for (const P2PSeg& sg : segs) {
+    if (sg.sn) NCCL_CHECK(api().Send(sg.sbuf, sg.sn, ncclDouble, sg.rank, (ncclComm_t)ctx->nccl, ctx->stream));
+    if (sg.rn) NCCL_CHECK(api().Recv(sg.rbuf, sg.rn, ncclDouble, sg.rank, (ncclComm_t)ctx->nccl, ctx->stream));
+  }
+  NCCL_CHECK(api().GroupEnd());
+}
+
 void itn_dist_exchange(itn_net* net, const std::vector<int>& dids) {
   itn_ctx* ctx = net->ctx;
   if (ctx->nranks == 1) return;

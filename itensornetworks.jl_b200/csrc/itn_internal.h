@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -46,6 +47,13 @@ struct itn_ctx {
   int path_mode = 0;
   int sm_count = 148;
   size_t ws_budget = (size_t)6 << 30;  // scratch budget for the generic path (bytes)
+  // Large blocks (slabs of site tensors, tile-major copies, staging) are recycled here instead of going back to the
+  // driver's pool: every block is used on `stream` only (or on copy_stream between events that order it against
+  // `stream`), so a freed block can be handed to later work on the same stream without synchronising, and the
+  // multi-GB allocations of a gate layer or a fresh cache never wait for the driver to map new physical memory.
+  std::multimap<size_t, void*> big_free;        // size -> block
+  std::unordered_map<void*, size_t> big_live;   // block -> size
+  size_t big_cached = 0;                        // bytes parked in big_free
 };
 
 // Planar storage: re plane [0, n), im plane [n, 2n) (complex only).
@@ -239,6 +247,15 @@ bool itn_is_local(const itn_net* net, int v);
 // receives the matching ones (ordered by directed id on both sides); one grouped NCCL send/recv per peer.
 void itn_dist_exchange(itn_net* net, const std::vector<int>& dids);
 void itn_dist_allreduce_sum(itn_ctx* ctx, double* dev, int n);
+// One grouped point-to-point exchange on the context stream: per peer, sn doubles out of sbuf and rn doubles into rbuf.
+struct P2PSeg {
+  int rank;
+  const double* sbuf;
+  size_t sn;
+  double* rbuf;
+  size_t rn;
+};
+void itn_dist_p2p(itn_ctx* ctx, const std::vector<P2PSeg>& segs);
 void itn_dist_release(itn_net* net);
 
 // ---- small linear algebra (itn_linalg.cu) ----

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <numeric>
 
 #include "itn_internal.h"
@@ -703,10 +704,8 @@ __global__ void __launch_bounds__(256) k_su_vrec(const SuEdge* __restrict__ edge
 
 struct SuTrunc {
   const double* tsig;
-  int ncand;  // min(m, n)
-  int* newdim;
-  double* truncerr;
-  double* svals;  // stride entries
+  int ncand;    // min(m, n)
+  double* row;  // result row of the gate: [new bond dimension, truncation error, kept singular values (stride entries)]
 };
 __global__ void k_su_truncate(const SuTrunc* __restrict__ jobs, int n, int maxdim, double cutoff, int stride) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -717,9 +716,9 @@ __global__ void k_su_truncate(const SuTrunc* __restrict__ jobs, int n, int maxdi
   for (int i = 0; i < nc; ++i) p[i] = T.tsig[i] * T.tsig[i];
   double terr = 0.0;
   const int keep = truncate_spectrum(p, nc, maxdim, cutoff, &terr);
-  *T.newdim = keep;
-  *T.truncerr = terr;
-  for (int i = 0; i < stride; ++i) T.svals[i] = i < keep ? T.tsig[i] : 0.0;
+  T.row[0] = (double)keep;
+  T.row[1] = terr;
+  for (int i = 0; i < stride; ++i) T.row[2 + i] = i < keep ? T.tsig[i] : 0.0;
 }
 
 // T_side[(s, l), (s', l')] = sum_r R^+[(s, l), r] R'[r, s', l'],
@@ -933,6 +932,14 @@ extern "C" int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, 
 
 // ------------------------------------------------------------------------------------------------
 // apply2: simple update on a vertex-disjoint batch of edges
+//
+// Multi-GPU (graph-partitioned network, every rank calls with the same list): site-level work - hermitised
+// environments, the bond environment C of a side, the support projectors and the rebuild A' = A . T - runs on the rank
+// that owns the site; edge-level work - R factors of both sides, theta', its SVD, truncation and the T factors - runs
+// on the rank that owns esrc ("owner").  For an edge that crosses a cut the other rank ("guest") ships its C
+// (n x n, 16 KiB at chi = 16) to the owner and receives its T (n x d chi') back: two grouped ncclSend/ncclRecv
+// exchanges per layer plus one all-reduce that gives every rank the new bond dimensions, truncation errors and
+// singular values of all gates.
 // ------------------------------------------------------------------------------------------------
 extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* gates, int maxdim, double cutoff,
                           int normalize, int msg_mode, int32_t* newdim_out, double* truncerr_out, double* svals_out,
@@ -946,6 +953,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   itn_ctx* ctx = net->ctx;
   const bool cplx = net->cplx;
   const int P = net->planes();
+  const bool multi = ctx->nranks > 1;
   // ---- validation (errors mirror src/apply.jl:118-129,140-144) ----
   std::vector<char> used(net->nv, 0);
   for (int i = 0; i < n; ++i) {
@@ -954,7 +962,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     for (int v : {net->esrc[e], net->edst[e]}) {
       ITN_REQUIRE(!used[v], ITN_EINVAL, "a batch of two-site gates must be vertex-disjoint");
       used[v] = 1;
-      ITN_REQUIRE(itn_is_local(net, v), ITN_EUNSUPPORTED, "two-site gate on an edge that crosses a partition cut is not supported yet");
+      if (!itn_is_local(net, v)) continue;
       ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor is not set");
       for (int f : net->inc[v])
         if (f != e)
@@ -962,14 +970,17 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
                       "environment message into vertex " + std::to_string(v) + " is not set (update the BP cache first)");
     }
   }
-  // ---- sizes and workspace ----
+  // ---- geometry of every gate (global metadata), role of this rank ----
+  enum { NONE = 0, OWNER = 1, GUEST = 2 };
   struct Geo {
-    int e, v[2], k[2], d[2], nn[2], r[2], chi, m, nc;
+    int e, v[2], k[2], d[2], nn[2], r[2], chi, m, nc, cand;
     long long X[2];
+    bool loc[2];
+    int role, peer;  // peer: the other rank of a cut edge, -1 otherwise
+    int oi;          // index among the gates this rank owns
   };
   std::vector<Geo> geo(n);
-  size_t ws_doubles = 0, env_doubles = 0, sig_total = 0;
-  int max_cand = 1;
+  int max_cand = 1, n_own = 0;
   for (int i = 0; i < n; ++i) {
     Geo& g = geo[i];
     g.e = eids[i];
@@ -981,75 +992,120 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       g.k[s] = net->slot(v, g.e);
       g.d[s] = net->sdim[v];
       g.nn[s] = g.d[s] * g.chi;
-      g.X[s] = net->T[v].n / g.nn[s];
+      g.X[s] = net->tensor_elems(v) / g.nn[s];
       g.r[s] = (int)std::min<long long>(g.X[s], g.nn[s]);
+      g.loc[s] = itn_is_local(net, v);
       ITN_REQUIRE(g.nn[s] <= 256, ITN_EUNSUPPORTED, "simple update supports d*chi <= 256");
-      // C, V, R, R^+ ; T sized for the largest possible new bond
-      ws_doubles += (size_t)P * (2 * (size_t)g.nn[s] * g.nn[s] + 2 * (size_t)g.r[s] * g.nn[s]);
-      sig_total += g.nn[s];
-      for (int f : net->inc[v])
-        if (f != g.e) env_doubles += (size_t)P * net->edim[f] * net->edim[f];
     }
     g.m = g.r[0] * g.d[0];
     g.nc = g.r[1] * g.d[1];
     ITN_REQUIRE(g.nc <= 256 && g.m <= 512, ITN_EUNSUPPORTED, "simple update supports bond matrices up to 512 x 256");
-    const int cand = std::min(g.m, g.nc);
-    max_cand = std::max(max_cand, cand);
-    ws_doubles += (size_t)P * (2 * (size_t)g.m * g.nc + (size_t)g.nc * g.nc);
-    for (int s = 0; s < 2; ++s) ws_doubles += (size_t)P * g.nn[s] * g.d[s] * cand;
-    sig_total += g.nc;
+    g.cand = std::min(g.m, g.nc);
+    max_cand = std::max(max_cand, g.cand);
+    g.role = g.loc[0] ? OWNER : (g.loc[1] ? GUEST : NONE);
+    g.peer = -1;
+    if (g.role == OWNER && !g.loc[1]) g.peer = net->owner[g.v[1]];
+    if (g.role == GUEST) g.peer = net->owner[g.v[0]];
+    g.oi = g.role == OWNER ? n_own++ : -1;
   }
   ITN_REQUIRE(!svals_out || svals_stride >= 1, ITN_EINVAL, "svals_stride must be positive");
   const int stride = std::max(max_cand, 1);
-  DevBuf ws(ctx, ws_doubles * sizeof(double)), envs(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double));
-  // eigen-decomposition of the environments: only their support projectors are needed (see file header)
-  size_t env_count = 0, env_sig = 0;
-  for (int i = 0; i < n; ++i)
-    for (int s = 0; s < 2; ++s)
-      for (int f : net->inc[geo[i].v[s]])
-        if (f != geo[i].e) {
-          ++env_count;
-          env_sig += net->edim[f];
-        }
+  const int RS = 2 + stride;  // doubles per result row
+  // ---- communication segments of the cut edges (same gate order on both ranks) ----
+  struct Seg {
+    size_t sendC = 0, recvC = 0, sendT = 0, recvT = 0;        // doubles
+    size_t sendC_off = 0, recvC_off = 0, sendT_off = 0, recvT_off = 0;
+  };
+  std::map<int, Seg> segs;
+  auto csize = [&](const Geo& g) { return (size_t)P * g.nn[1] * g.nn[1]; };
+  auto tsize = [&](const Geo& g) { return (size_t)P * g.nn[1] * g.d[1] * g.cand; };
+  for (const Geo& g : geo) {
+    if (g.peer < 0) continue;
+    Seg& sg = segs[g.peer];
+    if (g.role == GUEST) {
+      sg.sendC += csize(g);
+      sg.recvT += tsize(g);
+    } else {
+      sg.recvC += csize(g);
+      sg.sendT += tsize(g);
+    }
+  }
+  size_t tot_sendC = 0, tot_recvC = 0, tot_sendT = 0, tot_recvT = 0;
+  for (auto& kv : segs) {
+    Seg& sg = kv.second;
+    sg.sendC_off = tot_sendC; tot_sendC += sg.sendC;
+    sg.recvC_off = tot_recvC; tot_recvC += sg.recvC;
+    sg.sendT_off = tot_sendT; tot_sendT += sg.sendT;
+    sg.recvT_off = tot_recvT; tot_recvT += sg.recvT;
+  }
+  DevBuf sendC(ctx, tot_sendC * sizeof(double)), recvC(ctx, tot_recvC * sizeof(double));
+  DevBuf sendT(ctx, tot_sendT * sizeof(double)), recvT(ctx, tot_recvT * sizeof(double));
+  std::map<int, Seg> cur = segs;  // running offsets while carving
+  for (auto& kv : cur) kv.second.sendC = kv.second.recvC = kv.second.sendT = kv.second.recvT = 0;
+  // ---- sizes and workspace ----
+  size_t ws_doubles = 0, env_doubles = 0, sig_total = 0, env_count = 0, env_sig = 0;
+  for (const Geo& g : geo) {
+    for (int s = 0; s < 2; ++s) {
+      if (g.role == OWNER) {
+        // C, V, R, R^+
+        ws_doubles += (size_t)P * (2 * (size_t)g.nn[s] * g.nn[s] + 2 * (size_t)g.r[s] * g.nn[s]);
+        sig_total += g.nn[s];
+        ws_doubles += (size_t)P * g.nn[s] * g.d[s] * g.cand;  // T
+      }
+      if (g.loc[s])
+        for (int f : net->inc[g.v[s]])
+          if (f != g.e) {
+            env_doubles += (size_t)P * net->edim[f] * net->edim[f];
+            ++env_count;
+            env_sig += net->edim[f];
+          }
+    }
+    if (g.role == OWNER) {
+      ws_doubles += (size_t)P * (2 * (size_t)g.m * g.nc + (size_t)g.nc * g.nc);
+      sig_total += g.nc;
+    }
+  }
+  DevBuf ws(ctx, std::max<size_t>(ws_doubles, 1) * sizeof(double)), envs(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double));
   DevBuf env_us(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double)), env_v(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double));
   DevBuf env_pi(ctx, std::max<size_t>(env_doubles, 1) * sizeof(double));
   DevBuf env_s(ctx, std::max<size_t>(env_sig, 1) * sizeof(double)), env_p(ctx, std::max<size_t>(env_sig, 1) * sizeof(int));
   DevBuf env_flag(ctx, std::max<size_t>(env_count, 1) * sizeof(int));
   CUDA_CHECK(cudaMemsetAsync(env_flag.p, 0, std::max<size_t>(env_count, 1) * sizeof(int), ctx->stream));
-  // Cholesky fast routes (run_chol): rok[2 i + s] = 1 when R / R^+ of that side came from the Cholesky factor of its
+  // Cholesky fast routes (run_chol): rok[2 oi + s] = 1 when R / R^+ of that side came from the Cholesky factor of its
   // bond environment, env_ok[k] = 1 when environment k is safely positive definite (nothing for the eigen cutoff to drop)
-  DevBuf rok(ctx, 2 * (size_t)n * sizeof(int)), env_ok(ctx, std::max<size_t>(env_count, 1) * sizeof(int));
-  CUDA_CHECK(cudaMemsetAsync(rok.p, 0, 2 * (size_t)n * sizeof(int), ctx->stream));
+  DevBuf rok(ctx, std::max<size_t>(2 * (size_t)n_own, 1) * sizeof(int)), env_ok(ctx, std::max<size_t>(env_count, 1) * sizeof(int));
+  CUDA_CHECK(cudaMemsetAsync(rok.p, 0, std::max<size_t>(2 * (size_t)n_own, 1) * sizeof(int), ctx->stream));
   CUDA_CHECK(cudaMemsetAsync(env_ok.p, 0, std::max<size_t>(env_count, 1) * sizeof(int), ctx->stream));
-  std::vector<CholJob> chol_r, chol_env;
-  struct EnvRef {
-    int edge_i, side, slot;
-    const double* pi;
-  };
-  std::vector<EnvRef> env_refs;
-  std::vector<SvdJob> ej_svd;
-  std::vector<EigFnJob> ej_fn;
-  DevBuf sigs(ctx, sig_total * sizeof(double)), perms(ctx, sig_total * sizeof(int));
-  DevBuf d_newdim(ctx, (size_t)n * sizeof(int)), d_terr(ctx, (size_t)n * sizeof(double)), d_sv(ctx, (size_t)n * stride * sizeof(double));
-  // gates: host interleaved -> planar
+  DevBuf sigs(ctx, std::max<size_t>(sig_total, 1) * sizeof(double)), perms(ctx, std::max<size_t>(sig_total, 1) * sizeof(int));
+  // result rows of all gates: filled by the owner of each gate, summed over ranks
+  DevBuf res(ctx, (size_t)n * RS * sizeof(double));
+  CUDA_CHECK(cudaMemsetAsync(res.p, 0, (size_t)n * RS * sizeof(double), ctx->stream));
+  // gates of the edges this rank owns: host interleaved -> planar
   size_t gate_elems = 0;
-  std::vector<size_t> goff(n);
-  for (int i = 0; i < n; ++i) {
-    goff[i] = gate_elems;
-    gate_elems += (size_t)geo[i].d[0] * geo[i].d[1] * geo[i].d[0] * geo[i].d[1];
-  }
-  DevBuf d_gates(ctx, gate_elems * P * sizeof(double));
+  std::vector<size_t> goff(n), gsrc(n);
   {
+    size_t src_off = 0;
+    for (int i = 0; i < n; ++i) {
+      const size_t ge = (size_t)geo[i].d[0] * geo[i].d[1] * geo[i].d[0] * geo[i].d[1];
+      gsrc[i] = src_off;
+      src_off += ge;
+      goff[i] = gate_elems;
+      if (geo[i].role == OWNER) gate_elems += ge;
+    }
+  }
+  DevBuf d_gates(ctx, std::max<size_t>(gate_elems, 1) * P * sizeof(double));
+  if (gate_elems) {
     std::vector<double> tmp(gate_elems * P);
     const double* h = (const double*)gates;
     for (int i = 0; i < n; ++i) {
+      if (geo[i].role != OWNER) continue;
       const size_t ge = (size_t)geo[i].d[0] * geo[i].d[1] * geo[i].d[0] * geo[i].d[1];
       for (size_t t = 0; t < ge; ++t) {
         if (cplx) {
-          tmp[goff[i] * 2 + t] = h[(goff[i] + t) * 2];
-          tmp[goff[i] * 2 + ge + t] = h[(goff[i] + t) * 2 + 1];
+          tmp[goff[i] * 2 + t] = h[(gsrc[i] + t) * 2];
+          tmp[goff[i] * 2 + ge + t] = h[(gsrc[i] + t) * 2 + 1];
         } else {
-          tmp[goff[i] + t] = h[goff[i] + t];
+          tmp[goff[i] + t] = h[gsrc[i] + t];
         }
       }
     }
@@ -1057,15 +1113,23 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // tmp dies at scope end
   }
   // ---- carve workspace, build jobs ----
-  std::vector<SuEdge> se(n);
+  struct EnvRef {
+    int gate, side, slot;
+    const double* pi;
+  };
+  std::vector<EnvRef> env_refs;
+  std::vector<SvdJob> ej_svd, gj, tj;
+  std::vector<EigFnJob> ej_fn;
+  std::vector<CholJob> chol_r, chol_env;
+  std::vector<SuEdge> se(n_own);
   std::vector<HermJob> hj;
   std::vector<JobSpec> specs;
-  std::vector<std::vector<const double*>> overrides;  // per spec: matrices per bond slot
+  std::vector<std::vector<const double*>> overrides;  // per local side: matrices per bond slot
   overrides.reserve(2 * (size_t)n);
-  std::vector<SvdJob> gj, tj;
   std::vector<FastBenvJob> fast_env;
   std::vector<char> fast_site(2 * (size_t)n, 0);
-  std::vector<SuTrunc> tr(n);
+  std::vector<SuTrunc> tr(n_own);
+  std::vector<double*> guestT(n, nullptr);  // guest gates: where the owner's T factor arrives
   double* w = ws.as<double>();
   double* envp = envs.as<double>();
   size_t env_sig_off = 0;
@@ -1073,31 +1137,49 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   int* pp = perms.as<int>();
   for (int i = 0; i < n; ++i) {
     const Geo& g = geo[i];
-    SuEdge& E = se[i];
-    memset(&E, 0, sizeof(E));
-    E.chi = g.chi;
+    if (g.role == NONE) continue;
+    SuEdge* E = g.role == OWNER ? &se[g.oi] : nullptr;
+    if (E) {
+      memset(E, 0, sizeof(*E));
+      E->chi = g.chi;
+    }
     for (int s = 0; s < 2; ++s) {
       const int v = g.v[s];
-      const size_t n2 = (size_t)g.nn[s] * g.nn[s], rn = (size_t)g.r[s] * g.nn[s];
-      double* Cm = w; w += P * n2;
-      double* Vm = w; w += P * n2;
-      E.R[s] = w; w += P * rn;
-      E.Rp[s] = w; w += P * rn;
-      E.gus[s] = Cm;
-      E.gv[s] = Vm;
-      E.gsig[s] = sp;
-      E.gperm[s] = pp;
-      E.d[s] = g.d[s];
-      E.n[s] = g.nn[s];
-      E.r[s] = g.r[s];
-      {
-        SvdJob gjob = {Cm, Vm, sp, pp, g.nn[s], g.nn[s], nullptr, rok.as<int>() + 2 * (size_t)i + s};
+      double* Cm = nullptr;
+      if (E) {
+        const size_t n2 = (size_t)g.nn[s] * g.nn[s], rn = (size_t)g.r[s] * g.nn[s];
+        if (g.loc[s]) {
+          Cm = w; w += P * n2;
+        } else {  // the guest's bond environment arrives here
+          Seg& sg = segs[g.peer];
+          Cm = recvC.as<double>() + sg.recvC_off + cur[g.peer].recvC;
+          cur[g.peer].recvC += csize(g);
+        }
+        double* Vm = w; w += P * n2;
+        E->R[s] = w; w += P * rn;
+        E->Rp[s] = w; w += P * rn;
+        E->gus[s] = Cm;
+        E->gv[s] = Vm;
+        E->gsig[s] = sp;
+        E->gperm[s] = pp;
+        E->d[s] = g.d[s];
+        E->n[s] = g.nn[s];
+        E->r[s] = g.r[s];
+        int* okp = rok.as<int>() + 2 * (size_t)g.oi + s;
+        SvdJob gjob = {Cm, Vm, sp, pp, g.nn[s], g.nn[s], nullptr, okp};
         gj.push_back(gjob);
+        E->rok[s] = okp;
+        if (g.r[s] == g.nn[s] && g.nn[s] <= 64) chol_r.push_back({Cm, E->R[s], E->Rp[s], okp, g.nn[s], 0.0});
+        sp += g.nn[s];
+        pp += g.nn[s];
+      } else if (s == 1) {  // guest: C of the local side goes to the owner
+        Seg& sg = segs[g.peer];
+        Cm = sendC.as<double>() + sg.sendC_off + cur[g.peer].sendC;
+        cur[g.peer].sendC += csize(g);
+        guestT[i] = recvT.as<double>() + sg.recvT_off + cur[g.peer].recvT;
+        cur[g.peer].recvT += tsize(g);
       }
-      E.rok[s] = rok.as<int>() + 2 * (size_t)i + s;
-      if (g.r[s] == g.nn[s] && g.nn[s] <= 64) chol_r.push_back({Cm, E.R[s], E.Rp[s], rok.as<int>() + 2 * (size_t)i + s, g.nn[s], 0.0});
-      sp += g.nn[s];
-      pp += g.nn[s];
+      if (!g.loc[s]) continue;
       // hermitised environments (map_eigvals symmetrises its argument, apply.jl:9-15 with ishermitian = true)
       overrides.emplace_back(net->inc[v].size(), nullptr);
       for (size_t j = 0; j < net->inc[v].size(); ++j) {
@@ -1137,26 +1219,32 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
         specs.push_back(spx);
       }
     }
-    E.gate = d_gates.as<double>() + goff[i] * P;
-    E.theta0 = w; w += (size_t)P * g.m * g.nc;
-    E.theta = w; w += (size_t)P * g.m * g.nc;
-    E.tv = w; w += (size_t)P * g.nc * g.nc;
-    E.tsig = sp;
-    E.tperm = pp;
+    if (!E) continue;
+    E->gate = d_gates.as<double>() + goff[i] * P;
+    E->theta0 = w; w += (size_t)P * g.m * g.nc;
+    E->theta = w; w += (size_t)P * g.m * g.nc;
+    E->tv = w; w += (size_t)P * g.nc * g.nc;
+    E->tsig = sp;
+    E->tperm = pp;
     {
-      SvdJob tjob = {E.theta0, nullptr, sp, pp, g.m, g.nc, E.theta, nullptr};
+      SvdJob tjob = {E->theta0, nullptr, sp, pp, g.m, g.nc, E->theta, nullptr};
       tj.push_back(tjob);
     }
     sp += g.nc;
     pp += g.nc;
-    const int cand = std::min(g.m, g.nc);
     for (int s = 0; s < 2; ++s) {
-      E.T[s] = w;
-      w += (size_t)P * g.nn[s] * g.d[s] * cand;
+      if (s == 1 && !g.loc[1]) {  // the guest's T factor is built in the send buffer
+        Seg& sg = segs[g.peer];
+        E->T[s] = sendT.as<double>() + sg.sendT_off + cur[g.peer].sendT;
+        cur[g.peer].sendT += tsize(g);
+      } else {
+        E->T[s] = w;
+        w += (size_t)P * g.nn[s] * g.d[s] * g.cand;
+      }
     }
-    tr[i] = {E.tsig, cand, d_newdim.as<int>() + i, d_terr.as<double>() + i, d_sv.as<double>() + (size_t)i * stride};
+    tr[g.oi] = {E->tsig, g.cand, res.as<double>() + (size_t)i * RS};
   }
-  // ---- 1. hermitise environments, bond environments C_side, eigen-decompose ----
+  // ---- 1. hermitise environments, bond environments C_side of the local sides ----
   if (!hj.empty()) {
     DevBuf hb(ctx, hj.size() * sizeof(HermJob));
     const HermJob* dh = itn_upload(ctx, hj, hb);
@@ -1166,8 +1254,16 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   }
   itn_run_vertex_jobs(net, specs);
   itn_fast_bond_envs(net, fast_env);
+  if (multi) {  // guests ship their bond environments to the owners
+    std::vector<P2PSeg> xs;
+    for (auto& kv : segs)
+      xs.push_back({kv.first, sendC.as<double>() + kv.second.sendC_off, kv.second.sendC,
+                    recvC.as<double>() + kv.second.recvC_off, kv.second.recvC});
+    itn_dist_p2p(ctx, xs);
+  }
+  // ---- 2. R factors (Cholesky; eigen route where r < n or C is rank deficient), environment support ----
   run_chol(ctx, cplx, chol_r);
-  run_jacobi(ctx, cplx, gj);  // only the sides the Cholesky route did not settle (r < n, or rank deficient)
+  run_jacobi(ctx, cplx, gj);
   run_chol(ctx, cplx, chol_env);
   if (!ej_svd.empty()) {
     // projector onto the support of every environment: eigenvalues below 10 eps (relative) are dropped, as in
@@ -1181,40 +1277,42 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     else k_eig_fn<false><<<(unsigned)ej_fn.size(), 256, 0, ctx->stream>>>(de, 3, eig_cutoff);
     ITN_LAUNCH_CHECK(ctx);
   }
-  // ---- 2. R factors, theta', SVD, truncation ----
-  DevBuf seb(ctx, se.size() * sizeof(SuEdge));
-  const SuEdge* dse = itn_upload(ctx, se, seb);
-  if (cplx) k_su_build_R<true><<<2 * n, 256, 0, ctx->stream>>>(dse);
-  else k_su_build_R<false><<<2 * n, 256, 0, ctx->stream>>>(dse);
-  ITN_LAUNCH_CHECK(ctx);
-  if (cplx) k_su_theta<true><<<dim3(n, 8), 256, 0, ctx->stream>>>(dse);
-  else k_su_theta<false><<<dim3(n, 8), 256, 0, ctx->stream>>>(dse);
-  ITN_LAUNCH_CHECK(ctx);
-  run_jacobi(ctx, cplx, tj);
-  DevBuf trb(ctx, tr.size() * sizeof(SuTrunc));
-  const SuTrunc* dtr = itn_upload(ctx, tr, trb);
-  k_su_truncate<<<(n + 31) / 32, 32, 0, ctx->stream>>>(dtr, n, maxdim, cutoff, stride);
-  ITN_LAUNCH_CHECK(ctx);
-  std::vector<int> newdim(n);
-  std::vector<double> terr(n), sv((size_t)n * stride);
-  CUDA_CHECK(cudaMemcpyAsync(newdim.data(), d_newdim.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(terr.data(), d_terr.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaMemcpyAsync(sv.data(), d_sv.p, sv.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // ---- 3. theta', SVD, truncation (owned gates) ----
+  DevBuf seb(ctx, std::max<size_t>(se.size(), 1) * sizeof(SuEdge));
+  const SuEdge* dse = n_own ? itn_upload(ctx, se, seb) : nullptr;
+  if (n_own) {
+    if (cplx) k_su_build_R<true><<<2 * n_own, 256, 0, ctx->stream>>>(dse);
+    else k_su_build_R<false><<<2 * n_own, 256, 0, ctx->stream>>>(dse);
+    ITN_LAUNCH_CHECK(ctx);
+    if (cplx) k_su_theta<true><<<dim3(n_own, 8), 256, 0, ctx->stream>>>(dse);
+    else k_su_theta<false><<<dim3(n_own, 8), 256, 0, ctx->stream>>>(dse);
+    ITN_LAUNCH_CHECK(ctx);
+    run_jacobi(ctx, cplx, tj);
+    DevBuf trb(ctx, tr.size() * sizeof(SuTrunc));
+    const SuTrunc* dtr = itn_upload(ctx, tr, trb);
+    k_su_truncate<<<(n_own + 31) / 32, 32, 0, ctx->stream>>>(dtr, n_own, maxdim, cutoff, stride);
+    ITN_LAUNCH_CHECK(ctx);
+  }
+  itn_dist_allreduce_sum(ctx, res.as<double>(), n * RS);  // every rank learns the outcome of every gate
+  std::vector<double> hres((size_t)n * RS);
+  CUDA_CHECK(cudaMemcpyAsync(hres.data(), res.p, hres.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<int> eflag(std::max<size_t>(env_count, 1), 0);
   CUDA_CHECK(cudaMemcpyAsync(eflag.data(), env_flag.p, eflag.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> newdim(n);
+  for (int i = 0; i < n; ++i) newdim[i] = (int)(hres[(size_t)i * RS] + 0.5);
   // sites with a rank-deficient environment: A <- A x_j P_j before the rebuild
   std::vector<ModeProdSpec> pspecs;
-  std::vector<std::pair<int, int>> pspec_site;  // (edge_i, side)
+  std::vector<std::pair<int, int>> pspec_site;  // (gate, side)
   std::vector<double*> pscratch;
   std::vector<const double*> presult;
   for (size_t k = 0; k < env_refs.size(); ++k) {
     if (!eflag[k]) continue;
     const EnvRef& r = env_refs[k];
-    const int v = geo[r.edge_i].v[r.side];
+    const int v = geo[r.gate].v[r.side];
     int idx = -1;
     for (size_t q = 0; q < pspec_site.size(); ++q)
-      if (pspec_site[q] == std::make_pair(r.edge_i, r.side)) idx = (int)q;
+      if (pspec_site[q] == std::make_pair(r.gate, r.side)) idx = (int)q;
     if (idx < 0) {
       ModeProdSpec sp;
       memset(&sp, 0, sizeof(sp));
@@ -1228,7 +1326,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       sp.w1 = (double*)itn_dev_alloc(ctx, (size_t)sp.n * P * sizeof(double));
       pscratch.push_back(sp.w1);
       pspecs.push_back(sp);
-      pspec_site.push_back({r.edge_i, r.side});
+      pspec_site.push_back({r.gate, r.side});
       idx = (int)pspecs.size() - 1;
     }
     ModeProdSpec& sp = pspecs[idx];
@@ -1237,34 +1335,46 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     sp.nsteps++;
   }
   itn_run_modeprods(ctx, cplx, pspecs, presult);
-  // ---- 3. T factors and the new site tensors ----
-  for (int i = 0; i < n; ++i) se[i].newdim = newdim[i];
-  CUDA_CHECK(cudaMemcpyAsync((void*)dse, se.data(), se.size() * sizeof(SuEdge), cudaMemcpyHostToDevice, ctx->stream));
-  if (cplx) k_su_vrec<true><<<dim3(n, 4), 256, 0, ctx->stream>>>(dse);
-  else k_su_vrec<false><<<dim3(n, 4), 256, 0, ctx->stream>>>(dse);
-  ITN_LAUNCH_CHECK(ctx);
-  if (cplx) k_su_T<true><<<dim3(2 * n, 4), 256, 0, ctx->stream>>>(dse);
-  else k_su_T<false><<<dim3(2 * n, 4), 256, 0, ctx->stream>>>(dse);
-  ITN_LAUNCH_CHECK(ctx);
+  // ---- 4. T factors (owner), shipped to the guests; new site tensors of the local sides ----
+  if (n_own) {
+    for (int i = 0; i < n; ++i)
+      if (geo[i].role == OWNER) se[geo[i].oi].newdim = newdim[i];
+    CUDA_CHECK(cudaMemcpyAsync((void*)dse, se.data(), se.size() * sizeof(SuEdge), cudaMemcpyHostToDevice, ctx->stream));
+    if (cplx) k_su_vrec<true><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+    else k_su_vrec<false><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+    ITN_LAUNCH_CHECK(ctx);
+    if (cplx) k_su_T<true><<<dim3(2 * n_own, 4), 256, 0, ctx->stream>>>(dse);
+    else k_su_T<false><<<dim3(2 * n_own, 4), 256, 0, ctx->stream>>>(dse);
+    ITN_LAUNCH_CHECK(ctx);
+  }
+  if (multi) {
+    std::vector<P2PSeg> xs;
+    for (auto& kv : segs)
+      xs.push_back({kv.first, sendT.as<double>() + kv.second.sendT_off, kv.second.sendT,
+                    recvT.as<double>() + kv.second.recvT_off, kv.second.recvT});
+    itn_dist_p2p(ctx, xs);
+  }
   std::vector<SuSite> sites, slow_sites;
+  std::vector<int> site_v;
   std::vector<FastRebuildJob> fast_reb;
   std::vector<NormJob2> nj;
   long long maxn = 0;
   // one allocation for all new site tensors of the layer, one for the new messages (shared, reference counted)
   auto align32 = [](size_t x) { return (x + 31) & ~(size_t)31; };
   size_t slab_doubles = 0, mslab_doubles = 0;
-  for (int i = 0; i < n; ++i)
-    for (int s = 0; s < 2; ++s) {
-      slab_doubles += align32((size_t)(net->T[geo[i].v[s]].n / geo[i].chi * newdim[i]) * P);
-      mslab_doubles += align32((size_t)newdim[i] * newdim[i] * P);
-    }
-  DevSlab* tslab = new DevSlab();
-  DevSlab* mslab = new DevSlab();
+  for (int i = 0; i < n; ++i) {
+    const Geo& g = geo[i];
+    for (int s = 0; s < 2; ++s)
+      if (g.loc[s]) slab_doubles += align32((size_t)(net->T[g.v[s]].n / g.chi * newdim[i]) * P);
+    if (g.role != NONE) mslab_doubles += 2 * align32((size_t)newdim[i] * newdim[i] * P);
+  }
+  DevSlab* tslab = slab_doubles ? new DevSlab() : nullptr;
+  DevSlab* mslab = mslab_doubles ? new DevSlab() : nullptr;
   try {
-    tslab->base = itn_dev_alloc(ctx, slab_doubles * sizeof(double));
-    mslab->base = itn_dev_alloc(ctx, mslab_doubles * sizeof(double));
+    if (tslab) tslab->base = itn_dev_alloc(ctx, slab_doubles * sizeof(double));
+    if (mslab) mslab->base = itn_dev_alloc(ctx, mslab_doubles * sizeof(double));
   } catch (...) {
-    if (tslab->base) itn_dev_free(ctx, tslab->base);
+    if (tslab && tslab->base) itn_dev_free(ctx, tslab->base);
     delete tslab;
     delete mslab;
     for (double* p : pscratch) itn_dev_free(ctx, p);
@@ -1275,12 +1385,13 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     for (int i = 0; i < n; ++i) {
       const Geo& g = geo[i];
       for (int s = 0; s < 2; ++s) {
+        if (!g.loc[s]) continue;
         const int v = g.v[s];
         SuSite S;
         S.a = net->T[v].p;
         for (size_t q = 0; q < pspec_site.size(); ++q)
           if (pspec_site[q] == std::make_pair(i, s)) S.a = presult[q];
-        S.T = se[i].T[s];
+        S.T = g.role == OWNER ? se[g.oi].T[s] : guestT[i];
         S.d = g.d[s];
         S.chi = g.chi;
         S.chi_new = newdim[i];
@@ -1293,6 +1404,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
         S.out = (double*)tslab->base + toff;
         toff += align32((size_t)S.n_new * P);
         sites.push_back(S);
+        site_v.push_back(v);
         if (fast_site[2 * (size_t)i + s] && S.a == net->T[v].p && newdim[i] <= 16)
           fast_reb.push_back({v, g.k[s], newdim[i], S.T, S.out});
         else
@@ -1313,7 +1425,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       else k_su_rebuild<false><<<dim3((unsigned)slow_sites.size(), gy), 256, 0, ctx->stream>>>(ds);
       ITN_LAUNCH_CHECK(ctx);
     }
-    if (normalize) {
+    if (normalize && !nj.empty()) {
       DevBuf nb(ctx, nj.size() * sizeof(NormJob2));
       const NormJob2* dn = itn_upload(ctx, nj, nb);
       k_normalize2<<<(unsigned)nj.size(), 256, 0, ctx->stream>>>(dn);
@@ -1321,21 +1433,22 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     }
   }
   for (double* p : pscratch) itn_dev_free(ctx, p);  // stream ordered: freed after the rebuild kernel
-  // ---- 4. commit: swap tensors, new bond dimensions, reset the messages on the gated edges ----
+  // ---- 5. commit: swap tensors, new bond dimensions, reset the messages on the gated edges ----
   std::vector<DiagMsgJob> dj;
-  size_t si = 0, moff = 0;
+  size_t moff = 0;
+  for (size_t si = 0; si < sites.size(); ++si) {
+    const int v = site_v[si];
+    itn_tensor_free(ctx, net->T[v]);
+    net->T[v].p = sites[si].out;
+    net->T[v].n = sites[si].n_new;
+    net->T[v].slab = tslab;
+    tslab->refs++;
+    net->touch(v);
+  }
   for (int i = 0; i < n; ++i) {
     const Geo& g = geo[i];
-    for (int s = 0; s < 2; ++s, ++si) {
-      const int v = g.v[s];
-      itn_tensor_free(ctx, net->T[v]);
-      net->T[v].p = sites[si].out;
-      net->T[v].n = sites[si].n_new;
-      net->T[v].slab = tslab;
-      tslab->refs++;
-      net->touch(v);
-    }
-    net->edim[g.e] = newdim[i];
+    net->edim[g.e] = newdim[i];  // every rank keeps the bond dimensions of the whole graph
+    if (g.role == NONE) continue;
     for (int dd = 0; dd < 2; ++dd) {
       DevTensor& m = net->M[2 * g.e + dd];
       const long long n2 = (long long)newdim[i] * newdim[i];
@@ -1345,10 +1458,10 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       m.n = n2;
       m.slab = mslab;
       mslab->refs++;
-      dj.push_back({m.p, msg_mode == 1 ? d_sv.as<double>() + (size_t)i * stride : nullptr, newdim[i]});
+      dj.push_back({m.p, msg_mode == 1 ? res.as<double>() + (size_t)i * RS + 2 : nullptr, newdim[i]});
     }
   }
-  {
+  if (!dj.empty()) {
     DevBuf db(ctx, dj.size() * sizeof(DiagMsgJob));
     const DiagMsgJob* dd = itn_upload(ctx, dj, db);
     if (cplx) k_diag_msg<true><<<(unsigned)dj.size(), 128, 0, ctx->stream>>>(dd);
@@ -1359,9 +1472,9 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   if (!normalize) itn_fast_commit_direct(net);  // k_normalize2 rescaled the canonical tensors only
   for (int i = 0; i < n; ++i) {
     if (newdim_out) newdim_out[i] = newdim[i];
-    if (truncerr_out) truncerr_out[i] = terr[i];
+    if (truncerr_out) truncerr_out[i] = hres[(size_t)i * RS + 1];
     if (svals_out)
-      for (int t = 0; t < svals_stride; ++t) svals_out[(size_t)i * svals_stride + t] = t < stride ? sv[(size_t)i * stride + t] : 0.0;
+      for (int t = 0; t < svals_stride; ++t) svals_out[(size_t)i * svals_stride + t] = t < stride ? hres[(size_t)i * RS + 2 + t] : 0.0;
   }
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   API_END

@@ -7,4 +7,4 @@ from .cache import (BeliefPropagationCache, Context, apply, apply_layer, default
 from .graphs import (NamedGraph, default_edge_sequence, edge_coloring, forest_cover, heavy_hex_eagle,
                      named_comb_tree, named_grid, named_path_graph, parallel_edge_sequence)
 from .network import ITensorNetwork, productstate, random_tensornetwork
-from .dist import directed_id, halo_bytes_per_sweep, halo_plan, init_distributed, partition_vertices
+from .dist import directed_id, gate_exchange_plan, halo_bytes_per_sweep, halo_plan, init_distributed, partition_vertices

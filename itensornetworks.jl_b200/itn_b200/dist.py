@@ -66,6 +66,44 @@ def halo_bytes_per_sweep(graph, owner, edge_dims, itemsize):
     return out
 
 
+def gate_exchange_plan(graph, owner, rank, pairs, edge_dims, sdims, planes=2):
+    """What itn_apply2 exchanges for a vertex-disjoint layer of two-site gates on a partitioned network, as seen from
+    `rank` (csrc/itn_linalg.cu): site-level work runs where the site lives, edge-level work on the rank that owns esrc
+    (the "owner"); for an edge crossing a cut the other rank (the "guest") sends its bond environment C (n x n,
+    n = d chi) and receives its T factor (n x d cand, cand = largest possible new bond dimension).
+    Returns {peer: {"send_C": [(gate index, doubles)], "recv_C": [...], "send_T": [...], "recv_T": [...]}}; every list is
+    in gate order, which is the order of the segments inside the NCCL buffers on both sides."""
+    plan = {}
+    for i, (a, b) in enumerate(pairs):
+        e = graph.eid[(a, b)]
+        u, v = graph.edges[e]  # engine orientation (esrc, edst)
+        ou, ov = owner[u], owner[v]
+        if ou == ov or rank not in (ou, ov):
+            continue
+        chi = int(edge_dims[e])
+
+        def outer(x):
+            n = 1
+            for f in graph.inc[x]:
+                if f != e:
+                    n *= int(edge_dims[f])
+            return n
+        r = [min(outer(x), sdims[x] * chi) for x in (u, v)]
+        cand = min(r[0] * sdims[u], r[1] * sdims[v])
+        nn = sdims[v] * chi  # the guest always holds edst
+        csize = planes * nn * nn
+        tsize = planes * nn * sdims[v] * cand
+        if rank == ou:  # owner: receives C, sends T
+            pl = plan.setdefault(ov, {"send_C": [], "recv_C": [], "send_T": [], "recv_T": []})
+            pl["recv_C"].append((i, csize))
+            pl["send_T"].append((i, tsize))
+        else:           # guest
+            pl = plan.setdefault(ou, {"send_C": [], "recv_C": [], "send_T": [], "recv_T": []})
+            pl["send_C"].append((i, csize))
+            pl["recv_T"].append((i, tsize))
+    return plan
+
+
 def init_distributed(ctx, rank, world):
     """Create the library's NCCL communicator: rank 0 draws the id, torch.distributed (any backend) broadcasts
     its 128 bytes, every rank calls itn_ctx_init_dist."""

@@ -51,6 +51,25 @@ def main():
         r = E.rescale(bpc)
         zv2, ze2 = E.scalar_factors_quotient(r)
         worst = max(worst, float(np.max(np.abs(zv2 - 1))), float(np.max(np.abs(ze2 - 1))))
+        # simple-update gate layers on the partitioned network (src/apply.jl:33-95): interior edges and edges that cross
+        # the cut (the guest rank ships its bond environment, the owner returns the T factor); then BP again and <Z>
+        gate = O.random_unitary(4, seed=11, dtype=dtype).reshape(2, 2, 2, 2)
+        gate = (gate + 0.5 * np.eye(4, dtype=dtype).reshape(2, 2, 2, 2)).astype(dtype)  # non-unitary: truncation error > 0
+        maxdim = max(2, chi - 1) if chi <= 3 else chi
+        msgs = ref
+        for layer in O.edge_coloring(g):
+            info2 = E.apply_layer([gate] * len(layer), bpc, [g.edges[e] for e in layer], maxdim=maxdim, cutoff=1e-13)
+            for i, e in enumerate(layer):
+                net, inf = O.simple_update_bp(net, msgs, e, gate, maxdim=maxdim, cutoff=1e-13)
+                msgs = O.reset_edge_messages(net, msgs, e)
+                assert info2["newdim"][i] == inf["newdim"], (dims, e, info2["newdim"][i], inf["newdim"])
+                worst = max(worst, abs(info2["truncation_error"][i] - inf["truncerr"]))
+                sv = inf["svals"][:inf["newdim"]]
+                worst = max(worst, float(np.max(np.abs(info2["singular_values"][i] - sv)) / sv[0]))
+            msgs, _, _ = O.bp_update(net, msgs, seq=seq, groups=O.synchronous_groups(seq), maxiter=2)
+            E.update(bpc, maxiter=2, edge_sequence=[[e] for e in seq], inplace=True)
+        ez = E.expect(bpc, "Z")
+        worst = max(worst, max(abs(ez[v] - O.expect1(net, msgs, v, O.PAULI_Z)) for v in range(g.nv)))
     t = torch.tensor([worst], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -118,3 +118,85 @@ def test_halo_plan_is_symmetric():
         assert sum(len(pl["send"]) for p in plans for pl in p.values()) == 2 * ncut
     b = E.halo_bytes_per_sweep(E.named_grid((64, 64)), E.partition_vertices(E.named_grid((64, 64)), 8), [16] * 8064, 16)
     assert b[0] == 64 * 256 * 16 and b[3] == 2 * 64 * 256 * 16  # 256 KiB per cut and direction
+
+
+def test_gate_exchange_plan_is_symmetric():
+    # cut-edge two-site gates (itn_apply2 on a partitioned network): what one rank sends is what its peer expects
+    sys.path.insert(0, os.path.join(ROOT, "itensornetworks.jl_b200"))
+    import itn_b200 as E
+    for dims, world, chi in (((8, 8), 4, 16), ((6, 5), 3, 4), ((4, 4, 4), 2, 2), ((64, 64), 8, 16)):
+        g = E.named_grid(dims)
+        owner = E.partition_vertices(g, world)
+        sd = [2] * g.nv
+        ed = [chi] * g.ne
+        for layer in E.edge_coloring(g):
+            pairs = [g.edges[e] for e in layer]
+            plans = [E.gate_exchange_plan(g, owner, r, pairs, ed, sd) for r in range(world)]
+            ncut = sum(1 for (u, v) in pairs if owner[u] != owner[v])
+            assert sum(len(pl["send_C"]) for p in plans for pl in p.values()) == ncut
+            for r in range(world):
+                for peer, pl in plans[r].items():
+                    assert pl["send_C"] == plans[peer][r]["recv_C"] and pl["recv_C"] == plans[peer][r]["send_C"]
+                    assert pl["send_T"] == plans[peer][r]["recv_T"] and pl["recv_T"] == plans[peer][r]["send_T"]
+    # 64x64 chi=16 d=2 ComplexF64: C is 32 x 32 (16 KiB), T is 32 x (2 * 64) (64 KiB) per cut gate
+    g = E.named_grid((64, 64))
+    owner = E.partition_vertices(g, 8)
+    lay = max(E.edge_coloring(g), key=lambda l: sum(owner[g.edges[e][0]] != owner[g.edges[e][1]] for e in l))
+    pl = E.gate_exchange_plan(g, owner, 3, [g.edges[e] for e in lay], [16] * g.ne, [2] * g.nv)
+    sizes = {c for p in pl.values() for (_, c) in p["send_C"] + p["recv_C"]}
+    assert sizes == {2 * 32 * 32}
+
+
+def _gate_worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "itensornetworks.jl_b200"))
+        import torch
+        import torch.distributed as dist
+
+        import itn_b200 as E
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        g = E.named_grid((6, 4))
+        owner = E.partition_vertices(g, world)
+        ok = True
+        for layer in E.edge_coloring(g):
+            pairs = [g.edges[e] for e in layer]
+            plan = E.gate_exchange_plan(g, owner, rank, pairs, [3] * g.ne, [2] * g.nv)
+            for what_s, what_r in (("send_C", "recv_C"), ("send_T", "recv_T")):
+                reqs, bufs = [], []
+                for peer, pl in sorted(plan.items()):
+                    if pl[what_s]:  # segment of gate i is filled with the marker 1000 * i + sender rank
+                        sb = torch.cat([torch.full((n,), 1000.0 * i + rank, dtype=torch.float64) for i, n in pl[what_s]])
+                        reqs.append(dist.isend(sb, peer))
+                    if pl[what_r]:
+                        rb = torch.empty(sum(n for _, n in pl[what_r]), dtype=torch.float64)
+                        reqs.append(dist.irecv(rb, peer))
+                        bufs.append((peer, pl[what_r], rb))
+                for r in reqs:
+                    r.wait()
+                for peer, segs, rb in bufs:
+                    off = 0
+                    for i, n in segs:
+                        ok = ok and bool((rb[off:off + n] == 1000.0 * i + peer).all())
+                        off += n
+        q.put((rank, ok))
+        dist.destroy_process_group()
+    except Exception as ex:  # pragma: no cover
+        q.put((rank, repr(ex)))
+
+
+def test_gate_exchange_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_gate_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=240) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    for rank, ok in res:
+        assert ok is True, (rank, ok)
