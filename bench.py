@@ -58,6 +58,18 @@ def algorithmic_flops_per_sweep(graph, chi, d, cplx):
     return tot
 
 
+def measured_traffic(workload, world):
+    """DRAM bytes of the sweep's contraction kernels from the committed ncu --set full capture (profiles/r1_traffic.json),
+    per sweep and GPU; None for workloads that were not captured."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if j.get("workload") == workload:
+            return float(j["dram_bytes_per_sweep"]) / world
+    except Exception:
+        pass
+    return None
+
+
 def fp64_peak():
     """FP64 roofline denominator: measured cuBLAS ZGEMM burst on this pool (tools/fp64_peak.cu)."""
     path = os.path.join(ROOT, "profiles", "r1_fp64_peak.json")
@@ -338,7 +350,8 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (psi %.2f GB per sweep)" % (h2d / 1e9) if h2d > 2e8 else "working set fits L2; no flush (latency-bound config)",
                    "parallelism": "graph partition x%d, NCCL boundary messages" % world if world > 1 else "single GPU"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak["sustained"], "unit": "TFLOP/s",
-                     "frac": (achieved / peak["sustained"]) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak["sustained"]) if achieved else None,
+                     "traffic": measured_traffic(args.workload, world), "traffic_unit": "bytes per sweep and GPU (ncu dram__bytes_read+write of the three DMMA phases, profiles/r1c_k_fast_ncu_grid64.txt)",
                      "kernel": "message-update contraction kernels (per sweep, per GPU)", "peak_source": peak["source"],
                      "contract_ms_per_sweep": contract_ms_per_sweep,
                      "note": "achieved = algorithmic flops (8*z*d*chi^(z+1) per message) / device time; FP64 DMMA peak, not bf16"},
@@ -380,10 +393,11 @@ def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch, dist=None):
     gate = ((v * np.exp(-0.05 * w)) @ v.conj().T).astype(dtype).reshape(d, d, d, d)  # exp(-tau H): imaginary-time step
     layers = E.edge_coloring(graph)
     work = bpc.copy()
-    # warm-up: one full untimed Trotter step (grows the stream-ordered memory pool to its steady state: every layer
+    # warm-up: full untimed Trotter steps (grow the stream-ordered memory pool to its steady state: every layer
     # allocates the new site tensors of its 2 x |layer| vertices in one slab and releases the old ones)
-    for layer in layers:
-        E.apply_layer([gate] * len(layer), work, [graph.edges[e] for e in layer], maxdim=chi, cutoff=None)
+    for _ in range(3):  # three untimed steps: the slab ping-pong of the layers needs three slabs before it stops allocating
+        for layer in layers:
+            E.apply_layer([gate] * len(layer), work, [graph.edges[e] for e in layer], maxdim=chi, cutoff=None)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
