@@ -67,9 +67,19 @@ function B200BeliefPropagationCache(psi::ITensorNetwork{V}; ctx::Context=Context
     ctx.h, dtype_code(elt), length(verts), length(eds), esrc, edst, edim, sdim, C_NULL, out))
   bpc = B200BeliefPropagationCache{V}(out[], ctx, psi, verts, vid, eds, elt)
   finalizer(b -> ccall((:itn_net_destroy, LIB), Cint, (Ptr{Cvoid},), b.h), bpc)
-  for v in verts
-    set_factor!(bpc, v, psi[v])
-  end
+  # all site tensors in one pipelined upload (itn_net_set_tensors): column-major `array(t)`, axis_edge maps the ITensor
+  # index order to edges so nothing is permuted on the host.  flags = 1 (ITN_HOST_DEFERRED) would only register the
+  # arrays and let the first synchronous update() overlap the copy with its sweep; the arrays must then stay rooted
+  # (keep `arrs` in the cache object) until that call returns.
+  arrs = [array(psi[v]) for v in verts]
+  axes = [axis_edges(bpc, v, psi[v]) for v in verts]
+  ids = Int32[vid[v] for v in verts]
+  nds = Int32[ndims(a) for a in arrs]
+  ptrs = Ptr{Cvoid}[pointer(a) for a in arrs]
+  flat = reduce(vcat, axes; init=Int32[])
+  GC.@preserve arrs check(ccall((:itn_net_set_tensors, LIB), Cint,
+    (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{Int32}, Ptr{Int32}, Cint),
+    bpc.h, length(verts), ids, ptrs, nds, flat, 0))
   # initialize_cache (src/initialize_cache.jl:14-29): identity messages on loopy graphs only
   if messages === :identity || (messages === :default && !NamedGraphs.is_tree(psi))
     check(ccall((:itn_msg_set_identity, LIB), Cint, (Ptr{Cvoid},), bpc.h))
