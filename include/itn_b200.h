@@ -159,6 +159,18 @@ int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* gates, int 
                double cutoff, int normalize, int msg_mode, int32_t* newdim_n, double* truncerr_n,
                double* svals, int svals_stride);
 
+/* The gauged simple-update loop as one call (`apply(o, psi; cache_update_kwargs, maxdim, cutoff)` of
+ * north_star): for each colour layer l = 0 .. nlayers-1, itn_apply2 on eids[layer_ptr[l] .. layer_ptr[l+1]) (gates
+ * concatenated in the same order, outputs indexed like eids), followed - when bp_maxiter > 0 - by itn_bp_update with
+ * the given sequence (same meaning of seq / group_ptr / tol / normalize as itn_bp_update), so that the next layer sees
+ * refreshed environments.  This is the host loop `for layer: psi = apply(gates, psi; envs); bpc = update(bpc)` of a
+ * TEBD driver without returning to the host language between its parts.  bp_iters_total (nullable): sweeps run. */
+int itn_apply_layers(itn_net* net, int nlayers, const int32_t* layer_ptr, const int32_t* eids, const void* gates,
+                     int maxdim, double cutoff, int normalize, int msg_mode, const int32_t* seq_src,
+                     const int32_t* seq_dst, int nseq, const int32_t* group_ptr, int ngroups, int bp_maxiter,
+                     double bp_tol, int bp_normalize, int32_t* newdim_n, double* truncerr_n, double* svals,
+                     int svals_stride, int32_t* bp_iters_total);
+
 /* map_eigvals(f, A, ...; ishermitian = true, cutoff) (src/apply.jl:21-25) for a batch of n
  * Hermitian chi x chi host matrices; fn: 0 = sqrt, 1 = inv o sqrt, 2 = inv.  cutoff < 0: none. */
 int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, const void* host_in,
@@ -168,8 +180,9 @@ int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, const void*
 
 /* Number of kernels this library has launched on ctx since creation (bench.py "gpu_launches"). */
 int itn_ctx_launch_count(const itn_ctx* ctx, int64_t* out);
-/* Select the message-update implementation: 0 = auto (DMMA fast path where a bucket qualifies,
- * generic otherwise), 1 = force the generic kernels (used by the parity tests as a second opinion). */
+/* Select the message-update implementation: 0 = auto (DMMA tile path where a bucket qualifies, the shape-generic
+ * DMMA kernels otherwise), 1 = shape-generic DMMA kernels only, 2 = plain FMA kernels only (the parity tests use
+ * 1 and 2 as second and third opinions on the device). */
 int itn_ctx_set_path(itn_ctx* ctx, int mode);
 /* Device time of the last itn_bp_update in milliseconds (CUDA events on the context stream) and
  * the share spent in the dominant contraction kernels. */

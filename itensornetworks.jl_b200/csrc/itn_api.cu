@@ -582,7 +582,7 @@ extern "C" int itn_ctx_launch_count(const itn_ctx* ctx, int64_t* out) {
 extern "C" int itn_ctx_set_path(itn_ctx* ctx, int mode) {
   API_BEGIN
   ITN_REQUIRE(ctx, ITN_EINVAL, "ctx is NULL");
-  ITN_REQUIRE(mode == 0 || mode == 1, ITN_EINVAL, "mode must be 0 (auto) or 1 (generic)");
+  ITN_REQUIRE(mode >= 0 && mode <= 2, ITN_EINVAL, "mode must be 0 (auto), 1 (shape-generic DMMA kernels only) or 2 (FMA kernels only)");
   ctx->path_mode = mode;
   API_END
 }
@@ -1338,10 +1338,46 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   // synchronous sweeps: vertices that qualify go to the DMMA kernels, the rest to the generic kernels
   std::vector<char> handled;
   const int nfast = sync_mode ? itn_fast_bp_plan(net, all_dids, all_src, handled) : 0;
+  // the rest of a synchronous sweep: vertices whose outgoing messages are all part of it go to the vertex-level DMMA
+  // sweep (shared partial absorptions, itn_run_vertex_sweeps), whatever is left to the per-message kernels
   std::vector<JobSpec> slow_specs;
-  if (nfast > 0)
+  std::vector<SweepSpec> vsweeps;
+  if (sync_mode) {
+    if (handled.size() != (size_t)nseq) handled.assign(nseq, 0);
+    std::vector<int> cnt(net->nv, 0), first(net->nv, -1);
     for (int i = 0; i < nseq; ++i)
-      if (!handled[i]) slow_specs.push_back({sjobs[i].v, 1u << (sjobs[i].k + 1), staged.ptr[i]});
+      if (!handled[i]) cnt[sjobs[i].v]++;
+    std::vector<int> vs_index(net->nv, -1);
+    for (int i = 0; i < nseq; ++i) {
+      if (handled[i]) continue;
+      const int v = sjobs[i].v;
+      if (cnt[v] == (int)net->inc[v].size() && itn_vertex_sweep_ok(net, v) && net->T[v].p) {
+        if (vs_index[v] < 0) {
+          vs_index[v] = (int)vsweeps.size();
+          SweepSpec sp;
+          memset(&sp, 0, sizeof(sp));
+          sp.v = v;
+          vsweeps.push_back(sp);
+        }
+        vsweeps[vs_index[v]].out[sjobs[i].k] = staged.ptr[i];
+      } else {
+        slow_specs.push_back({v, 1u << (sjobs[i].k + 1), staged.ptr[i]});
+      }
+    }
+    // a sequence that lists a directed edge twice leaves a slot of the vertex sweep unset: fall back for that vertex
+    for (size_t q = 0; q < vsweeps.size();) {
+      const int v = vsweeps[q].v;
+      bool full = true;
+      for (size_t k = 0; k < net->inc[v].size(); ++k) full = full && vsweeps[q].out[k] != nullptr;
+      if (full) {
+        ++q;
+        continue;
+      }
+      for (int i = 0; i < nseq; ++i)
+        if (!handled[i] && sjobs[i].v == v) slow_specs.push_back({v, 1u << (sjobs[i].k + 1), staged.ptr[i]});
+      vsweeps.erase(vsweeps.begin() + q);
+    }
+  }
   // Deferred host tensors (itn_net_set_tensors, ITN_HOST_DEFERRED): in a synchronous sweep the outgoing messages of a
   // vertex depend on its own tensor and the pre-sweep messages only, so the first sweep runs vertex chunk by vertex
   // chunk behind the host -> device copy: copy(c + 1) overlaps import + relayout + DMMA phases of chunk c.
@@ -1421,9 +1457,11 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
             itn_fast_bp_sweep_range(net, swept, ns);
           }
           itn_fast_bp_sweep_end(net);
+          itn_run_vertex_sweeps(net, vsweeps);
           itn_run_vertex_jobs(net, slow_specs);
-        } else if (nfast > 0) {
-          itn_fast_bp_sweep(net, all_dids, all_src, handled, staged.ptr.data());
+        } else if (sync_mode) {
+          if (nfast > 0) itn_fast_bp_sweep(net, all_dids, all_src, handled, staged.ptr.data());
+          itn_run_vertex_sweeps(net, vsweeps);
           itn_run_vertex_jobs(net, slow_specs);
         } else {
           compute_messages(net, sjobs, lo, hi, staged.ptr);

@@ -324,79 +324,103 @@ struct BenvArgs {
   const double* const* Pv;  // [n] tensor with the other pair's two messages absorbed (same layout)
   const double* const* Mv;  // [n] message on the partner bond of the gate bond (planar 16 x 16)
   const int* side;          // [n]
-  double* part;             // [n][d*d][32][TILE]
+  double* part;             // [n][3][32][TILE]: pairs (s, s') = (0,0), (0,1), (1,1)
   int d;
 };
 
+// d = 2.  One CTA per (site, q, half) handles BOTH ket copies s and BOTH bra copies s' of its 8 tile positions:
+// the third absorption T_s = M^T P_s (or P_s M) is computed once per s and reused for every s', and only the pairs
+// s <= s' are closed (C is Hermitian: block (s', s) is the conjugate transpose of block (s, s')):
+// 2 + 3 = 5 tile products and 4 tile loads per position instead of 8 and 8.
+// Shared memory: P_0, P_1 (overwritten by T_s, then by the outputs), one X buffer (X_0, then X_1), M  =  103 KB, 2 CTAs / SM.
 template <bool C>
 __global__ void __launch_bounds__(kThreads, 2) k_benv(const BenvArgs a) {
   extern __shared__ __align__(16) double sm[];
   constexpr int TILE = C ? 512 : 256;
   constexpr int TS = TILE + 2;
-  double* Xs = sm;
-  double* Ps = Xs + kTilesPerCta * TS;
-  double* Ss = Ps + kTilesPerCta * TS;
-  double* Ms = Ss + kTilesPerCta * TS;
+  constexpr int D = 2;
+  double* Ps = sm;                           // [D][8] tiles
+  double* Xs = Ps + D * kTilesPerCta * TS;   // [8] tiles
+  double* Ms = Xs + kTilesPerCta * TS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
   const int half = b & 1, q = (b >> 1) & 15;
-  const int rest = b >> 5;
-  const int dd = a.d * a.d;
-  const int j = rest / dd, ss = rest - j * dd;
-  const int s = ss % a.d, sp = ss / a.d;  // s: ket copy (P), sp: bra copy (X)
+  const int j = b >> 5;
   const int side = a.side[j];
-  {
-    const double* gp = a.Pv[j] + (((size_t)s * 16 + q) * 16 + half * kTilesPerCta) * TILE;
-    const double* gx = a.Xv[j] + (((size_t)sp * 16 + q) * 16 + half * kTilesPerCta) * TILE;
+  auto load_tiles = [&](double* dst, const double* g) {
     for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
       const int w = i / (TILE / 2), r = i - w * (TILE / 2);
-      cp_async16(Xs + w * TS + 2 * r, gx + 2 * i);
-      cp_async16(Ps + w * TS + 2 * r, gp + 2 * i);
+      cp_async16(dst + w * TS + 2 * r, g + 2 * i);
     }
+  };
+  for (int s = 0; s < D; ++s)
+    load_tiles(Ps + s * kTilesPerCta * TS, a.Pv[j] + (((size_t)s * 16 + q) * 16 + half * kTilesPerCta) * TILE);
+  load_tiles(Xs, a.Xv[j] + (((size_t)0 * 16 + q) * 16 + half * kTilesPerCta) * TILE);
+  {
     const double* m = a.Mv[j];
     const int o = swz(tid & 15, tid >> 4);
     Ms[o] = m[tid];
     if (C) Ms[256 + o] = m[256 + tid];
-    cp_async_commit_wait_all();
   }
+  cp_async_commit_wait_all();
   __syncthreads();
   double* X = Xs + warp * TS;
-  double* S = Ss + warp * TS;
-  double* P = Ps + warp * TS;
+  double* P0 = Ps + warp * TS;
+  double* P1 = Ps + (kTilesPerCta + warp) * TS;
   double cre[2][4], cim[2][4];
-  zero_acc<C>(cre, cim);
-  if (side == 0) {
-    tile_mm<C, true, false, false>(Ms, P, cre, cim, lane);  // T = M^T P
-    store_acc<C>(S, cre, cim, lane);
-    __syncwarp();
+  // third absorption, in place over P_s
+  for (int s = 0; s < D; ++s) {
+    double* P = s ? P1 : P0;
     zero_acc<C>(cre, cim);
-    tile_mm<C, true, false, true>(S, X, cre, cim, lane);    // O[l,l'] = sum_k T[k,l] conj(X[k,l'])
-  } else {
-    tile_mm<C, false, false, false>(P, Ms, cre, cim, lane); // U = P M
-    store_acc<C>(S, cre, cim, lane);
+    if (side == 0) tile_mm<C, true, false, false>(Ms, P, cre, cim, lane);   // T = M^T P
+    else tile_mm<C, false, false, false>(P, Ms, cre, cim, lane);            // U = P M
     __syncwarp();
-    zero_acc<C>(cre, cim);
-    tile_mm<C, false, true, true>(S, X, cre, cim, lane);    // O[a,a''] = sum_k U[a,k] conj(X[a'',k])
+    store_acc<C>(P, cre, cim, lane);
   }
   __syncwarp();
-  store_acc<C>(S, cre, cim, lane);
-  __syncthreads();
-  double* pr = a.part + (((size_t)j * dd + ss) * 32 + (q * 2 + half)) * TILE;
-  for (int o = tid; o < TILE; o += kThreads) {
-    double acc = 0.0;
+  auto close = [&](const double* Tt, double (&re)[2][4], double (&im)[2][4]) {
+    zero_acc<C>(re, im);
+    if (side == 0) tile_mm<C, true, false, true>(Tt, X, re, im, lane);     // O[l,l'] = sum_k T[k,l] conj(X[k,l'])
+    else tile_mm<C, false, true, true>(Tt, X, re, im, lane);               // O[a,a''] = sum_k U[a,k] conj(X[a'',k])
+  };
+  auto reduce_to = [&](const double* tiles, int pair) {
+    double* pr = a.part + (((size_t)j * 3 + pair) * 32 + (q * 2 + half)) * TILE;
+    for (int o = tid; o < TILE; o += kThreads) {
+      double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < kTilesPerCta; ++w) acc += Ss[w * TS + o];
-    pr[o] = acc;
-  }
+      for (int w = 0; w < kTilesPerCta; ++w) acc += tiles[w * TS + o];
+      pr[o] = acc;
+    }
+  };
+  // s' = 0: pair (0, 0); the output overwrites the X_0 tile
+  close(P0, cre, cim);
+  __syncwarp();
+  store_acc<C>(X, cre, cim, lane);
+  __syncthreads();
+  reduce_to(Xs, 0);
+  __syncthreads();
+  // s' = 1: pairs (0, 1) and (1, 1); the outputs overwrite T_0 and T_1
+  load_tiles(Xs, a.Xv[j] + (((size_t)1 * 16 + q) * 16 + half * kTilesPerCta) * TILE);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  close(P0, cre, cim);
+  __syncwarp();
+  store_acc<C>(P0, cre, cim, lane);
+  close(P1, cre, cim);
+  __syncwarp();
+  store_acc<C>(P1, cre, cim, lane);
+  __syncthreads();
+  reduce_to(Ps, 1);
+  reduce_to(Ps + kTilesPerCta * TS, 2);
 }
 
-// C[(s + d l) + n (s' + d l')] = sum over the 32 per-CTA partials, un-swizzled; n = 16 d
+// C[(s + d l) + n (s' + d l')] = sum over the 32 per-CTA partials of pair (s, s'), un-swizzled; n = 16 d, d = 2.
+// pair 0 = (0, 0), 1 = (0, 1), 2 = (1, 1); block (1, 0) is the conjugate transpose of block (0, 1).
 template <bool C>
 __global__ void __launch_bounds__(256) k_benv_reduce(const double* __restrict__ part, double* const* __restrict__ Cout, int d) {
   constexpr int TILE = C ? 512 : 256;
-  const int dd = d * d;
-  const int j = blockIdx.x / dd, ss = blockIdx.x - j * dd;
-  const int s = ss % d, sp = ss / d;
+  const int j = blockIdx.x / 3, pair = blockIdx.x - j * 3;
+  const int s = pair == 2 ? 1 : 0, sp = pair == 0 ? 0 : 1;
   const double* p = part + (size_t)blockIdx.x * 32 * TILE;
   const int tid = threadIdx.x, l = tid & 15, lp = tid >> 4;
   const int o = swz(l, lp);
@@ -410,6 +434,11 @@ __global__ void __launch_bounds__(256) k_benv_reduce(const double* __restrict__ 
   const size_t idx = (size_t)(s + d * l) + (size_t)n * (sp + d * lp);
   out[idx] = sr;
   if (C) out[(size_t)n * n + idx] = si;
+  if (s != sp) {
+    const size_t idt = (size_t)(sp + d * lp) + (size_t)n * (s + d * l);
+    out[idt] = sr;
+    if (C) out[(size_t)n * n + idt] = -si;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -640,7 +669,7 @@ void relayout_launch(itn_net* net, FastCache* fc, int lo, int hi) {
 
 // (Re)builds the tile-major copies of every eligible vertex when the network changed.
 FastCache* ensure_cache(itn_net* net) {
-  if (net->ctx->path_mode == 1) return nullptr;
+  if (net->ctx->path_mode != 0) return nullptr;
   {
     FastCache* cur = (FastCache*)net->fast;
     if (cur && cur->nb > 0 && cur->topo_version == net->topo_version) return cur;
@@ -897,7 +926,8 @@ void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs) {
   DevBuf tb(ctx, tabs.size() * sizeof(double*)), sb(ctx, nj * sizeof(int));
   const double** dt = (const double**)itn_upload(ctx, tabs, tb);
   const int* ds = itn_upload(ctx, side, sb);
-  DevBuf part(ctx, nj * d * d * 32 * TILE * sizeof(double));
+  ITN_REQUIRE(d == 2, ITN_EINVAL, "tile bond environments need d = 2");
+  DevBuf part(ctx, nj * 3 * 32 * TILE * sizeof(double));
   BenvArgs b;
   b.Xv = dt;
   b.Pv = dt + nj;
@@ -905,21 +935,21 @@ void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs) {
   b.side = ds;
   b.part = part.as<double>();
   b.d = d;
-  const unsigned grid = (unsigned)(nj * d * d * 32);
+  const unsigned grid = (unsigned)(nj * 32);
   if (net->cplx) {
     const size_t smem = (size_t)(3 * kTilesPerCta + 1) * (512 + 2) * sizeof(double);
     CUDA_CHECK(cudaFuncSetAttribute(k_benv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_benv<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     k_benv<true><<<grid, kThreads, smem, ctx->stream>>>(b);
     ITN_LAUNCH_CHECK(ctx);
-    k_benv_reduce<true><<<(unsigned)(nj * d * d), 256, 0, ctx->stream>>>(part.as<double>(), (double* const*)(dt + 3 * nj), d);
+    k_benv_reduce<true><<<(unsigned)(nj * 3), 256, 0, ctx->stream>>>(part.as<double>(), (double* const*)(dt + 3 * nj), d);
   } else {
     const size_t smem = (size_t)(3 * kTilesPerCta + 1) * (256 + 2) * sizeof(double);
     CUDA_CHECK(cudaFuncSetAttribute(k_benv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_benv<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     k_benv<false><<<grid, kThreads, smem, ctx->stream>>>(b);
     ITN_LAUNCH_CHECK(ctx);
-    k_benv_reduce<false><<<(unsigned)(nj * d * d), 256, 0, ctx->stream>>>(part.as<double>(), (double* const*)(dt + 3 * nj), d);
+    k_benv_reduce<false><<<(unsigned)(nj * 3), 256, 0, ctx->stream>>>(part.as<double>(), (double* const*)(dt + 3 * nj), d);
   }
   ITN_LAUNCH_CHECK(ctx);
 }

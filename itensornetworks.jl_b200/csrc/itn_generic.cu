@@ -16,6 +16,7 @@
 // second opinion for the DMMA fast path (itn_fast.cu); FP64 FMA pipe, not tensor cores.
 #include <algorithm>
 #include <cstring>
+#include <functional>
 
 #include "itn_internal.h"
 
@@ -192,6 +193,388 @@ __global__ void __launch_bounds__(kThreads) k_gram(const VJob* __restrict__ jobs
       out[oi] = vr;
       if (C) out[n2 + oi] = vi;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMMA versions of the two kernels above (FP64 mma.sync m16n8k8, ComplexF64 as four real products on the planes).
+// Fragments are loaded straight from global memory: every element of the big operand is used by exactly one warp,
+// so there is nothing to share through shared memory except the small message matrix.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_16x8x8(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+
+// out[l, b, r] = sum_a in[l, a, r] * M[a + K b].  Rows of the product are the flattened (l, r) pairs, 16 per warp tile;
+// the message matrix sits in shared memory, zero padded to multiples of 8 (row stride K8 + 4: conflict-free fragments).
+template <bool C>
+__global__ void __launch_bounds__(kThreads) k_modeprod_mma(const VJob* __restrict__ jobs, int step) {
+  extern __shared__ double sm[];
+  const VJob& J = jobs[blockIdx.x];
+  if (step >= J.nsteps) return;
+  const ModeStep S = J.steps[step];
+  const double* __restrict__ src = (step == 0) ? J.ap : J.w[(step - 1) & 1];
+  double* __restrict__ dst = J.w[step & 1];
+  const long long L = S.L, R = S.R;
+  const int K = S.K, N = S.N;
+  const int K8 = (K + 7) & ~7, N8 = (N + 7) & ~7, ld = K8 + 4;
+  const long long n_in = L * K * R, n_out = L * N * R;
+  double* Mr = sm;
+  double* Mi = sm + (size_t)ld * N8;
+  for (int i = threadIdx.x; i < ld * N8; i += blockDim.x) {
+    const int k = i % ld, b = i / ld;
+    const bool ok = k < K && b < N;
+    Mr[i] = ok ? S.m[k + K * b] : 0.0;
+    if (C) Mi[i] = ok ? S.m[S.mplane + k + K * b] : 0.0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const long long rows = L * R;
+  const long long ntiles = (rows + 15) >> 4;
+  for (long long tile = (long long)blockIdx.y * (kThreads / 32) + warp; tile < ntiles;
+       tile += (long long)gridDim.y * (kThreads / 32)) {
+    long long ib[2], ob[2];
+    bool ok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long rho = tile * 16 + g + 8 * h;
+      ok[h] = rho < rows;
+      const long long l = ok[h] ? rho % L : 0, r = ok[h] ? rho / L : 0;
+      ib[h] = l + L * K * r;
+      ob[h] = l + L * N * r;
+    }
+    for (int n0 = 0; n0 < N8; n0 += 16) {
+      const int nbs = (N8 - n0) >= 16 ? 2 : 1;
+      double cr[2][4], ci[2][4];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) cr[nb][v] = ci[nb][v] = 0.0;
+      for (int k0 = 0; k0 < K8; k0 += 8) {
+        double ar[4], ai[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int h = v & 1, k = k0 + t + 4 * (v >> 1);
+          const bool lo = ok[h] && k < K;
+          const long long a = ib[h] + L * k;
+          ar[v] = lo ? src[a] : 0.0;
+          ai[v] = (C && lo) ? src[n_in + a] : 0.0;
+        }
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          if (nb >= nbs) break;
+          double br[2], bi[2], nbi[2];
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int o = (k0 + t + 4 * v) + ld * (n0 + 8 * nb + g);
+            br[v] = Mr[o];
+            bi[v] = C ? Mi[o] : 0.0;
+            nbi[v] = -bi[v];
+          }
+          dmma_16x8x8(cr[nb], ar, br);
+          if (C) {
+            dmma_16x8x8(ci[nb], ar, bi);
+            dmma_16x8x8(cr[nb], ai, nbi);
+            dmma_16x8x8(ci[nb], ai, br);
+          }
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        if (nb >= nbs) break;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int h = v >> 1, b = n0 + 8 * nb + 2 * t + (v & 1);
+          if (ok[h] && b < N) {
+            const long long o = ob[h] + L * b;
+            dst[o] = cr[nb][v];
+            if (C) dst[n_out + o] = ci[nb][v];
+          }
+        }
+      }
+    }
+  }
+}
+
+// out[o + No*o'] = sum_x B[x + X*o] * conj(A'[x + X*o']).  Work items are (16-row tile, pair of 8-column blocks, split of x);
+// a warp owns one item at a time, partial sums of the splits meet in shared memory in a fixed order.
+template <bool C>
+__global__ void __launch_bounds__(kThreads) k_gram_mma(const VJob* __restrict__ jobs) {
+  extern __shared__ double sm[];  // [S][2][No16 * No16]
+  const VJob& J = jobs[blockIdx.x];
+  const long long X = J.X;
+  const int No = J.No;
+  const long long n = J.n;
+  const double* __restrict__ B = (J.nsteps == 0) ? J.ap : J.w[(J.nsteps - 1) & 1];
+  const double* __restrict__ A = J.ap;
+  double* __restrict__ out = J.out;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int No16 = (No + 15) & ~15;
+  const int mt = No16 >> 4, np = No16 >> 4;  // 16-row tiles, pairs of 8-column blocks
+  const int T = mt * np;
+  const int S = (T >= nwarps) ? 1 : (nwarps / T);
+  const int n2 = No * No, p2 = No16 * No16;
+  for (int item = warp; item < T * S; item += nwarps) {
+    const int tile = item / S, split = item % S;
+    const int o0 = (tile % mt) * 16, p0 = (tile / mt) * 16;
+    const long long xlo = (X * split / S) & ~7ll, xhi = (split == S - 1) ? X : ((X * (split + 1) / S) & ~7ll);
+    double cr[2][4], ci[2][4];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) cr[nb][v] = ci[nb][v] = 0.0;
+    for (long long x0 = xlo; x0 < xhi; x0 += 8) {
+      double ar[4], ai[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int o = o0 + g + 8 * (v & 1);
+        const long long x = x0 + t + 4 * (v >> 1);
+        const bool ok = o < No && x < xhi;
+        ar[v] = ok ? B[x + X * o] : 0.0;
+        ai[v] = (C && ok) ? B[n + x + X * o] : 0.0;
+      }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        double br[2], bi[2], nbi[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int p = p0 + 8 * nb + g;
+          const long long x = x0 + t + 4 * v;
+          const bool ok = p < No && x < xhi;
+          br[v] = ok ? A[x + X * p] : 0.0;
+          bi[v] = (C && ok) ? A[n + x + X * p] : 0.0;
+          nbi[v] = -bi[v];
+        }
+        // b conj(a): re += br_B ar_A + bi_B ai_A ; im += bi_B ar_A - br_B ai_A   (ar/ai = B fragment, br/bi = A' fragment)
+        dmma_16x8x8(cr[nb], ar, br);
+        if (C) {
+          dmma_16x8x8(cr[nb], ai, bi);
+          dmma_16x8x8(ci[nb], ai, br);
+          dmma_16x8x8(ci[nb], ar, nbi);
+        }
+      }
+    }
+    double* pr = sm + (size_t)split * 2 * p2;
+    double* pi = pr + p2;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int o = o0 + g + 8 * (v >> 1), p = p0 + 8 * nb + 2 * t + (v & 1);
+        pr[o + No16 * p] = cr[nb][v];
+        if (C) pi[o + No16 * p] = ci[nb][v];
+      }
+  }
+  __syncthreads();
+  for (int oi = threadIdx.x; oi < n2; oi += blockDim.x) {
+    const int o = oi % No, p = oi / No;
+    double vr = 0.0, vi = 0.0;
+    for (int s2 = 0; s2 < S; ++s2) {
+      vr += sm[(size_t)s2 * 2 * p2 + o + No16 * p];
+      if (C) vi += sm[(size_t)s2 * 2 * p2 + p2 + o + No16 * p];
+    }
+    out[oi] = vr;
+    if (C) out[n2 + oi] = vi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vertex-level synchronous sweep on the canonical layout (no permutation): all z outgoing messages of a vertex with the
+// partial absorptions shared between them (divide and conquer over the bond set: z = 3 -> 5 mode products instead of 6,
+// z = 4 -> 8 instead of 12, z = 6 -> 16 instead of 30), every step on DMMA.
+//   mode product   dst[l, b, r] = sum_a src[l, a, r] M[a + K b]                      (MpOp)
+//   close          out[o + chi o'] = sum_{l, r} B[l, o, r] conj(A[l, o', r])          (GrOp, any position of the open bond)
+// ------------------------------------------------------------------------------------------------
+struct MpOp {
+  const double* src;
+  double* dst;
+  const double* m;  // planar K x K
+  long long L, R;
+  int K;
+};
+struct GrOp {
+  const double* B;
+  const double* A;
+  double* out;  // planar chi x chi
+  long long L, R;
+  int chi;
+};
+
+template <bool C>
+__global__ void __launch_bounds__(kThreads) k_mp_mma(const MpOp* __restrict__ ops) {
+  extern __shared__ double sm[];
+  const MpOp S = ops[blockIdx.x];
+  const double* __restrict__ src = S.src;
+  double* __restrict__ dst = S.dst;
+  const long long L = S.L, R = S.R;
+  const int K = S.K;
+  const int K8 = (K + 7) & ~7, ld = K8 + 4;
+  const long long nel = L * K * R;
+  double* Mr = sm;
+  double* Mi = sm + (size_t)ld * K8;
+  for (int i = threadIdx.x; i < ld * K8; i += blockDim.x) {
+    const int k = i % ld, b = i / ld;
+    const bool ok = k < K && b < K;
+    Mr[i] = ok ? S.m[k + K * b] : 0.0;
+    if (C) Mi[i] = ok ? S.m[(long long)K * K + k + K * b] : 0.0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const long long rows = L * R;
+  const long long ntiles = (rows + 15) >> 4;
+  for (long long tile = (long long)blockIdx.y * (kThreads / 32) + warp; tile < ntiles;
+       tile += (long long)gridDim.y * (kThreads / 32)) {
+    long long ib[2];
+    bool ok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long rho = tile * 16 + g + 8 * h;
+      ok[h] = rho < rows;
+      const long long l = ok[h] ? rho % L : 0, r = ok[h] ? rho / L : 0;
+      ib[h] = l + L * K * r;
+    }
+    for (int n0 = 0; n0 < K8; n0 += 16) {
+      const int nbs = (K8 - n0) >= 16 ? 2 : 1;
+      double cr[2][4], ci[2][4];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) cr[nb][v] = ci[nb][v] = 0.0;
+      for (int k0 = 0; k0 < K8; k0 += 8) {
+        double ar[4], ai[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int h = v & 1, k = k0 + t + 4 * (v >> 1);
+          const bool lo = ok[h] && k < K;
+          const long long a = ib[h] + L * k;
+          ar[v] = lo ? src[a] : 0.0;
+          ai[v] = (C && lo) ? src[nel + a] : 0.0;
+        }
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          if (nb >= nbs) break;
+          double br[2], bi[2], nbi[2];
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int o = (k0 + t + 4 * v) + ld * (n0 + 8 * nb + g);
+            br[v] = Mr[o];
+            bi[v] = C ? Mi[o] : 0.0;
+            nbi[v] = -bi[v];
+          }
+          dmma_16x8x8(cr[nb], ar, br);
+          if (C) {
+            dmma_16x8x8(ci[nb], ar, bi);
+            dmma_16x8x8(cr[nb], ai, nbi);
+            dmma_16x8x8(ci[nb], ai, br);
+          }
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        if (nb >= nbs) break;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int h = v >> 1, b = n0 + 8 * nb + 2 * t + (v & 1);
+          if (ok[h] && b < K) {
+            const long long o = ib[h] + L * b;
+            dst[o] = cr[nb][v];
+            if (C) dst[nel + o] = ci[nb][v];
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool C>
+__global__ void __launch_bounds__(kThreads) k_gr_mma(const GrOp* __restrict__ ops) {
+  extern __shared__ double sm[];  // [S][2][No16 * No16]
+  const GrOp J = ops[blockIdx.x];
+  const long long L = J.L, X = J.L * J.R;
+  const int No = J.chi;
+  const long long n = X * No, LK = L * No;
+  const double* __restrict__ B = J.B;
+  const double* __restrict__ A = J.A;
+  double* __restrict__ out = J.out;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int No16 = (No + 15) & ~15;
+  const int mt = No16 >> 4;
+  const int T = mt * mt;
+  const int S = (T >= nwarps) ? 1 : (nwarps / T);
+  const int n2 = No * No, p2 = No16 * No16;
+  for (int item = warp; item < T * S; item += nwarps) {
+    const int tile = item / S, split = item % S;
+    const int o0 = (tile % mt) * 16, p0 = (tile / mt) * 16;
+    const long long xlo = (X * split / S) & ~7ll, xhi = (split == S - 1) ? X : ((X * (split + 1) / S) & ~7ll);
+    double cr[2][4], ci[2][4];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) cr[nb][v] = ci[nb][v] = 0.0;
+    for (long long x0 = xlo; x0 < xhi; x0 += 8) {
+      // element (x, o) lives at (x mod L) + L chi (x div L) + L o
+      long long xb[2];
+      bool xok[2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const long long x = x0 + t + 4 * v;
+        xok[v] = x < xhi;
+        const long long r = x / L;
+        xb[v] = (x - r * L) + LK * r;
+      }
+      double ar[4], ai[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int o = o0 + g + 8 * (v & 1);
+        const bool ok = o < No && xok[v >> 1];
+        const long long a = xb[v >> 1] + L * o;
+        ar[v] = ok ? B[a] : 0.0;
+        ai[v] = (C && ok) ? B[n + a] : 0.0;
+      }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        double br[2], bi[2], nbi[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int p = p0 + 8 * nb + g;
+          const bool ok = p < No && xok[v];
+          const long long a = xb[v] + L * p;
+          br[v] = ok ? A[a] : 0.0;
+          bi[v] = (C && ok) ? A[n + a] : 0.0;
+          nbi[v] = -bi[v];
+        }
+        dmma_16x8x8(cr[nb], ar, br);
+        if (C) {
+          dmma_16x8x8(cr[nb], ai, bi);
+          dmma_16x8x8(ci[nb], ai, br);
+          dmma_16x8x8(ci[nb], ar, nbi);
+        }
+      }
+    }
+    double* pr = sm + (size_t)split * 2 * p2;
+    double* pi = pr + p2;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int o = o0 + g + 8 * (v >> 1), p = p0 + 8 * nb + 2 * t + (v & 1);
+        pr[o + No16 * p] = cr[nb][v];
+        if (C) pi[o + No16 * p] = ci[nb][v];
+      }
+  }
+  __syncthreads();
+  for (int oi = threadIdx.x; oi < n2; oi += blockDim.x) {
+    const int o = oi % No, p = oi / No;
+    double vr = 0.0, vi = 0.0;
+    for (int s2 = 0; s2 < S; ++s2) {
+      vr += sm[(size_t)s2 * 2 * p2 + o + No16 * p];
+      if (C) vi += sm[(size_t)s2 * 2 * p2 + p2 + o + No16 * p];
+    }
+    out[oi] = vr;
+    if (C) out[n2 + oi] = vi;
   }
 }
 
@@ -393,6 +776,48 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
       else k_permute<false><<<grid, kThreads, 0, ctx->stream>>>(dj);
       ITN_LAUNCH_CHECK(ctx);
     }
+    int maxK = 0, maxNo = 0;
+    bool plain = true;
+    for (const VJob& J : batch) {
+      maxNo = std::max(maxNo, J.No);
+      for (int s = 0; s < J.nsteps; ++s) {
+        maxK = std::max(maxK, std::max(J.steps[s].K, J.steps[s].N));
+        plain = plain && !J.steps[s].trans && !J.steps[s].conj;
+      }
+    }
+    const bool use_mma = ctx->path_mode != 2 && plain && maxK <= 64 && maxNo <= 64;
+    if (use_mma) {
+      // DMMA kernels: the message matrix padded to multiples of 8 in shared memory; 16-row tiles of flattened (l, r)
+      const int K8 = (maxK + 7) & ~7;
+      const size_t msm = (size_t)(K8 + 4) * K8 * 2 * sizeof(double);
+      if (msm > 48 * 1024) {
+        if (net->cplx) CUDA_CHECK(cudaFuncSetAttribute(k_modeprod_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+        else CUDA_CHECK(cudaFuncSetAttribute(k_modeprod_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+      }
+      unsigned gym = (unsigned)std::max<long long>(1, std::min<long long>(maxn / std::max(maxK, 1) / 128 + 1, 148));
+      while (gym > 1 && (unsigned long long)gym * nb > 148ull * 32ull) gym = (gym + 1) / 2;
+      dim3 gridm(nb, gym);
+      for (int s = 0; s < maxsteps; ++s) {
+        if (net->cplx) k_modeprod_mma<true><<<gridm, kThreads, msm, ctx->stream>>>(dj, s);
+        else k_modeprod_mma<false><<<gridm, kThreads, msm, ctx->stream>>>(dj, s);
+        ITN_LAUNCH_CHECK(ctx);
+      }
+      size_t gsm = 0;
+      for (const VJob& J : batch) {
+        const int No16 = (J.No + 15) & ~15;
+        const int T = (No16 / 16) * (No16 / 16), S = T >= kThreads / 32 ? 1 : (kThreads / 32) / T;
+        gsm = std::max(gsm, (size_t)S * 2 * No16 * No16 * sizeof(double));
+      }
+      if (gsm > 48 * 1024) {
+        if (net->cplx) CUDA_CHECK(cudaFuncSetAttribute(k_gram_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+        else CUDA_CHECK(cudaFuncSetAttribute(k_gram_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+      }
+      if (net->cplx) k_gram_mma<true><<<nb, kThreads, gsm, ctx->stream>>>(dj);
+      else k_gram_mma<false><<<nb, kThreads, gsm, ctx->stream>>>(dj);
+      ITN_LAUNCH_CHECK(ctx);
+      lo = hi;
+      continue;
+    }
     int smem_elems = maxkn;
     size_t smem_bytes = (size_t)smem_elems * P * sizeof(double);
     if (smem_bytes > 96 * 1024) {  // too large to stage: kernels read the matrix from global memory
@@ -474,5 +899,151 @@ void itn_run_modeprods(itn_ctx* ctx, bool cplx, const std::vector<ModeProdSpec>&
     if (cplx) k_modeprod<true><<<grid, kThreads, smem_bytes, ctx->stream>>>(dj, t, smem_elems);
     else k_modeprod<false><<<grid, kThreads, smem_bytes, ctx->stream>>>(dj, t, smem_elems);
     ITN_LAUNCH_CHECK(ctx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertex-level synchronous sweeps (k_mp_mma / k_gr_mma)
+// ------------------------------------------------------------------------------------------------
+bool itn_vertex_sweep_ok(const itn_net* net, int v) {
+  if (net->ctx->path_mode == 2) return false;
+  const int z = (int)net->inc[v].size();
+  if (z < 2) return false;
+  for (int e : net->inc[v])
+    if (net->edim[e] > 64) return false;
+  return true;
+}
+
+void itn_run_vertex_sweeps(itn_net* net, const std::vector<SweepSpec>& specs) {
+  if (specs.empty()) return;
+  itn_ctx* ctx = net->ctx;
+  const int P = net->planes();
+  size_t lo = 0;
+  while (lo < specs.size()) {
+    // batch bounded by the scratch budget: a vertex of degree z needs at most z temporaries
+    size_t hi = lo, bytes = 0;
+    while (hi < specs.size()) {
+      const int v = specs[hi].v;
+      const size_t need = (size_t)net->T[v].n * P * sizeof(double) * net->inc[v].size();
+      if (hi > lo && bytes + need > ctx->ws_budget) break;
+      bytes += need;
+      ++hi;
+    }
+    DevBuf ws(ctx, std::max<size_t>(bytes, 16));
+    // rounds[i]: the i-th operation of every vertex of the batch (operations of one vertex run in order)
+    std::vector<std::vector<MpOp>> mp_rounds;
+    std::vector<std::vector<GrOp>> gr_rounds;
+    int maxK = 1;
+    long long maxn = 0;
+    size_t woff = 0;
+    for (size_t si = lo; si < hi; ++si) {
+      const SweepSpec& sp = specs[si];
+      const int v = sp.v;
+      const int z = (int)net->inc[v].size();
+      ITN_REQUIRE(net->T[v].p != nullptr, ITN_EINVAL, "site tensor of vertex " + std::to_string(v) + " is not set");
+      const long long n = net->T[v].n;
+      maxn = std::max(maxn, n);
+      std::vector<long long> Ls(z), Rs(z);
+      std::vector<int> chis(z);
+      std::vector<const double*> msg(z);
+      long long acc = net->sdim[v];
+      for (int k = 0; k < z; ++k) {
+        const int e = net->inc[v][k];
+        chis[k] = net->edim[e];
+        Ls[k] = acc;
+        acc *= chis[k];
+        maxK = std::max(maxK, chis[k]);
+        const DevTensor& m = net->M[net->msg_into(v, e)];
+        ITN_REQUIRE(m.p != nullptr, ITN_EINVAL,
+                    "message into vertex " + std::to_string(v) + " on edge " + std::to_string(e) + " is not set");
+        msg[k] = m.p;
+      }
+      for (int k = 0; k < z; ++k) Rs[k] = n / (Ls[k] * chis[k]);
+      std::vector<double*> slots(z);
+      for (int k = 0; k < z; ++k) {
+        slots[k] = (double*)(ws.as<char>() + woff);
+        woff += (size_t)n * P * sizeof(double);
+      }
+      int round = 0, top = 0;
+      auto put_mp = [&](const MpOp& op) {
+        if ((int)mp_rounds.size() <= round) mp_rounds.resize(round + 1), gr_rounds.resize(round + 1);
+        mp_rounds[round++].push_back(op);
+      };
+      auto put_gr = [&](const GrOp& op) {
+        if ((int)gr_rounds.size() <= round) mp_rounds.resize(round + 1), gr_rounds.resize(round + 1);
+        gr_rounds[round++].push_back(op);
+      };
+      // solve(T, S): T has every bond outside S absorbed; emits the outgoing message of every bond in S
+      std::function<void(const double*, int, int)> solve = [&](const double* Tn, int s_lo, int s_hi) {
+        if (s_hi - s_lo == 1) {
+          const int k = s_lo;
+          put_gr({Tn, net->T[v].p, sp.out[k], Ls[k], Rs[k], chis[k]});
+          return;
+        }
+        const int mid = (s_lo + s_hi) / 2;
+        const int saved = top;
+        auto absorb = [&](int a_lo, int a_hi) {
+          const double* cur = Tn;
+          for (int k = a_lo; k < a_hi; ++k) {
+            double* dst = slots[top++];
+            put_mp({cur, dst, msg[k], Ls[k], Rs[k], chis[k]});
+            cur = dst;
+          }
+          return cur;
+        };
+        const double* T1 = absorb(mid, s_hi);  // absorb the upper half, emit the lower half
+        solve(T1, s_lo, mid);
+        top = saved;
+        const double* T2 = absorb(s_lo, mid);
+        solve(T2, mid, s_hi);
+        top = saved;
+      };
+      solve(net->T[v].p, 0, z);
+    }
+    const int K8 = (maxK + 7) & ~7;
+    const size_t msm = (size_t)(K8 + 4) * K8 * 2 * sizeof(double);
+    const int No16 = (maxK + 15) & ~15;
+    const int Tt = (No16 / 16) * (No16 / 16), Ss = Tt >= kThreads / 32 ? 1 : (kThreads / 32) / Tt;
+    size_t gsm = (size_t)Ss * 2 * No16 * No16 * sizeof(double);
+    gsm = std::max(gsm, (size_t)(kThreads / 32) * 2 * 256 * sizeof(double));
+    if (net->cplx) {
+      if (msm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_mp_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+      if (gsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_gr_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    } else {
+      if (msm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_mp_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+      if (gsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_gr_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    }
+    // one upload for all operation tables
+    size_t nmp = 0, ngr = 0;
+    for (auto& r : mp_rounds) nmp += r.size();
+    for (auto& r : gr_rounds) ngr += r.size();
+    std::vector<MpOp> all_mp;
+    std::vector<GrOp> all_gr;
+    all_mp.reserve(nmp);
+    all_gr.reserve(ngr);
+    for (auto& r : mp_rounds) all_mp.insert(all_mp.end(), r.begin(), r.end());
+    for (auto& r : gr_rounds) all_gr.insert(all_gr.end(), r.begin(), r.end());
+    DevBuf mb(ctx, std::max<size_t>(nmp, 1) * sizeof(MpOp)), gb(ctx, std::max<size_t>(ngr, 1) * sizeof(GrOp));
+    const MpOp* dmp = itn_upload(ctx, all_mp, mb);
+    const GrOp* dgr = itn_upload(ctx, all_gr, gb);
+    size_t mo = 0, go = 0;
+    for (size_t r = 0; r < mp_rounds.size(); ++r) {
+      const unsigned nm = (unsigned)mp_rounds[r].size(), ng = (unsigned)gr_rounds[r].size();
+      if (nm) {
+        unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>(maxn / std::max(maxK, 1) / 128 + 1, 148));
+        while (gy > 1 && (unsigned long long)gy * nm > 148ull * 32ull) gy = (gy + 1) / 2;
+        if (net->cplx) k_mp_mma<true><<<dim3(nm, gy), kThreads, msm, ctx->stream>>>(dmp + mo);
+        else k_mp_mma<false><<<dim3(nm, gy), kThreads, msm, ctx->stream>>>(dmp + mo);
+        ITN_LAUNCH_CHECK(ctx);
+        mo += nm;
+      }
+      if (ng) {
+        if (net->cplx) k_gr_mma<true><<<ng, kThreads, gsm, ctx->stream>>>(dgr + go);
+        else k_gr_mma<false><<<ng, kThreads, gsm, ctx->stream>>>(dgr + go);
+        ITN_LAUNCH_CHECK(ctx);
+        go += ng;
+      }
+    }
+    lo = hi;
   }
 }

@@ -190,6 +190,13 @@ struct JobSpec {
 };
 // Runs all specs in [lo, hi) batches bounded by the workspace budget. Results in spec.out.
 void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs);
+// All outgoing messages of a vertex in one go (synchronous sweeps), partial absorptions shared between the outputs.
+struct SweepSpec {
+  int v;
+  double* out[ITN_MAX_MODES];  // staged (un-normalised) message leaving along bond slot k, planar chi_k x chi_k
+};
+bool itn_vertex_sweep_ok(const itn_net* net, int v);
+void itn_run_vertex_sweeps(itn_net* net, const std::vector<SweepSpec>& specs);
 void itn_run_commit(itn_net* net, const std::vector<CommitJob>& jobs, int normalize, double* d_diffs);
 int itn_open_extent(const itn_net* net, int v, uint32_t open_mask);
 

@@ -1480,6 +1480,43 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   API_END
 }
 
+extern "C" int itn_apply_layers(itn_net* net, int nlayers, const int32_t* layer_ptr, const int32_t* eids, const void* gates,
+                                int maxdim, double cutoff, int normalize, int msg_mode, const int32_t* seq_src,
+                                const int32_t* seq_dst, int nseq, const int32_t* group_ptr, int ngroups, int bp_maxiter,
+                                double bp_tol, int bp_normalize, int32_t* newdim_n, double* truncerr_n, double* svals,
+                                int svals_stride, int32_t* bp_iters_total) {
+  if (!net || nlayers < 0 || (nlayers > 0 && (!layer_ptr || !eids || !gates))) {
+    itn_set_error("NULL argument");
+    return ITN_EINVAL;
+  }
+  if (bp_iters_total) *bp_iters_total = 0;
+  const size_t item = (net->cplx ? 2 : 1) * sizeof(double);
+  size_t goff = 0;  // bytes into `gates`
+  for (int l = 0; l < nlayers; ++l) {
+    const int lo = layer_ptr[l], hi = layer_ptr[l + 1];
+    if (hi < lo) {
+      itn_set_error("layer_ptr must be non-decreasing");
+      return ITN_EINVAL;
+    }
+    int st = itn_apply2(net, eids + lo, hi - lo, (const char*)gates + goff, maxdim, cutoff, normalize, msg_mode,
+                        newdim_n ? newdim_n + lo : nullptr, truncerr_n ? truncerr_n + lo : nullptr,
+                        svals ? svals + (size_t)lo * svals_stride : nullptr, svals_stride);
+    if (st != ITN_OK) return st;
+    for (int i = lo; i < hi; ++i) {
+      const int e = eids[i];
+      const size_t d1 = net->sdim[net->esrc[e]], d2 = net->sdim[net->edst[e]];
+      goff += d1 * d2 * d1 * d2 * item;
+    }
+    if (bp_maxiter > 0 && nseq > 0) {
+      int32_t it = 0;
+      st = itn_bp_update(net, seq_src, seq_dst, nseq, group_ptr, ngroups, bp_maxiter, bp_tol, bp_normalize, &it, nullptr);
+      if (st != ITN_OK) return st;
+      if (bp_iters_total) *bp_iters_total += it;
+    }
+  }
+  return ITN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // multi-GPU plumbing lives in itn_dist.cu
 // ------------------------------------------------------------------------------------------------

@@ -44,7 +44,7 @@ class Context:
         return n.value
 
     def set_path(self, mode):
-        """0 = auto (DMMA fast path where it applies), 1 = generic kernels only."""
+        """0 = auto (DMMA tile path where it applies), 1 = shape-generic DMMA kernels only, 2 = FMA kernels only."""
         check(lib().itn_ctx_set_path(self.h, int(mode)))
 
     def close(self):
@@ -488,6 +488,73 @@ def apply_layer(gates, bpc, pairs, maxdim=None, cutoff=None, normalize=False, ms
                            newdim.ctypes.data_as(C.POINTER(C.c_int32)), terr.ctypes.data_as(C.POINTER(C.c_double)),
                            sv.ctypes.data_as(C.POINTER(C.c_double)), stride))
     return {"newdim": newdim, "truncation_error": terr,
+            "singular_values": [sv[i, :newdim[i]].copy() for i in range(n)]}
+
+
+def _pack_gates(bpc, gates, pairs):
+    g = bpc.graph
+    eids, packed, memo = [], [], {}
+    for gate, (v1, v2) in zip(gates, pairs):
+        e = g.eid.get((v1, v2))
+        if e is None:
+            raise ITNError(1, "Vertices where the gates are being applied must be neighbors for now.")
+        d1, d2 = bpc.sdims[v1], bpc.sdims[v2]
+        flip = g.edges[e] != (v1, v2)
+        key = (id(gate), d1, d2, flip)
+        if key not in memo:
+            gt = np.asarray(gate, dtype=bpc.dtype).reshape(d1, d2, d1, d2)
+            if flip:
+                gt = gt.transpose(1, 0, 3, 2)
+            memo[key] = np.asfortranarray(gt).ravel(order="F")
+        eids.append(e)
+        packed.append(memo[key])
+    return eids, packed
+
+
+def tebd_step(bpc, layers, maxdim=None, cutoff=None, normalize=False, msg_mode=0, bp_maxiter=0, bp_tol=None,
+              edge_sequence=None, info=None):
+    """One Trotter step in ONE library call (itn_apply_layers): `layers` is a list of (gates, pairs) colour layers, each a
+    vertex-disjoint batch of two-site gates; after every layer `bp_maxiter` BP sweeps over `edge_sequence` (list of
+    single-edge groups = synchronous sweep, list of edges = sequential) refresh the environments of the next layer.
+    Mirrors the host loop `psi = apply(o, psi; envs...); bpc = update(bpc; cache_update_kwargs...)` of a TEBD driver
+    (src/apply.jl:97-160 with the cache protocol of src/expect.jl:21-41).  In place; returns per-gate results."""
+    all_e, all_g, ptr = [], [], [0]
+    for gates, pairs in layers:
+        e, g = _pack_gates(bpc, gates, pairs)
+        all_e += e
+        all_g += g
+        ptr.append(len(all_e))
+    n = len(all_e)
+    packed = np.ascontiguousarray(np.concatenate(all_g)) if n else np.zeros(0, dtype=bpc.dtype)
+    dmax = max(bpc.sdims) if bpc.sdims else 1
+    stride = max([dmax * dmax * bpc.edge_dim(e) for e in set(all_e)] + [1])
+    if maxdim is not None:
+        stride = max(stride, dmax * dmax * int(maxdim))  # bonds may grow between the layers of the step
+    newdim = np.zeros(n, dtype=np.int32)
+    terr = np.zeros(n, dtype=np.float64)
+    sv = np.zeros((n, stride), dtype=np.float64)
+    if edge_sequence is None:
+        edge_sequence = []
+    grouped = len(edge_sequence) > 0 and isinstance(edge_sequence[0], list)
+    flat = [e for grp in edge_sequence for e in grp] if grouped else list(edge_sequence)
+    _, ps = i32([u for u, _ in flat])
+    _, pd = i32([v for _, v in flat])
+    gp = None
+    if grouped:
+        _, gp = i32(np.cumsum([0] + [len(grp) for grp in edge_sequence]))
+    _, pe = i32(all_e)
+    _, pl = i32(ptr)
+    iters = C.c_int32()
+    check(lib().itn_apply_layers(bpc.h, len(layers), pl, pe, packed.ctypes.data_as(C.c_void_p),
+                                 0 if maxdim is None else int(maxdim), -1.0 if cutoff is None else float(cutoff),
+                                 1 if normalize else 0, int(msg_mode), ps, pd, len(flat), gp,
+                                 len(edge_sequence) if grouped else 0, int(bp_maxiter), -1.0 if bp_tol is None else float(bp_tol),
+                                 1, newdim.ctypes.data_as(C.POINTER(C.c_int32)), terr.ctypes.data_as(C.POINTER(C.c_double)),
+                                 sv.ctypes.data_as(C.POINTER(C.c_double)), stride, C.byref(iters)))
+    bpc._host_refs = None
+    if info is not None:
+        info["bp_iterations"] = iters.value
+    return {"newdim": newdim, "truncation_error": terr, "layer_ptr": ptr,
             "singular_values": [sv[i, :newdim[i]].copy() for i in range(n)]}
 
 

@@ -15,7 +15,7 @@ DTYPES = [np.float64, np.complex128]
 EPS = np.finfo(np.float64).eps
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["auto", "generic"])
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=["auto", "generic_dmma", "generic_fma"])
 def ctx(request):
     c = E.Context(0)
     c.set_path(request.param)
@@ -74,9 +74,18 @@ def test_sequential_sweeps_match_oracle_every_iteration(ctx, dtype, name, mk, ch
     seq = O.default_edge_sequence(g)
     bpc = E.BeliefPropagationCache(psi, ctx=ctx)
     _, _, _, hist = O.bp_update(net, O.identity_messages(net), seq=seq, maxiter=3, return_history=True)
+    msgs = O.identity_messages(net)
     for it in range(3):
+        # one Gauss-Seidel sweep of the oracle from the engine's current messages: BP on these random networks is not
+        # contractive (on cubic3_chi2 complex a rounding-level difference grows ~300x per sweep, measured with three
+        # different kernel families, tools/dbg_cubic.py), so every iteration is compared from identical inputs ...
+        ref, _, _ = O.bp_update(net, msgs, seq=seq, maxiter=1)
         E.update(bpc, maxiter=1, edge_sequence=seq, inplace=True)
-        assert_messages_close(bpc, hist[it], TOL)
+        assert_messages_close(bpc, ref, TOL)
+        msgs = {k: bpc.message(k) for k in ref}
+        # ... and against the oracle's own history while the amplification leaves room (first two sweeps)
+        if it < 2:
+            assert_messages_close(bpc, hist[it], 1e-9)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -213,12 +222,13 @@ def test_dmma_fast_path_chi16(dtype):
     assert_messages_close(bpc, msgs, TOL)
     assert abs(info["mean_diff"] - diff_o) < 1e-12
     # the generic kernels give the same answer (second opinion on the device)
-    c2 = E.Context(0)
-    c2.set_path(1)
-    b2 = E.BeliefPropagationCache(psi, ctx=c2)
-    E.update(b2, maxiter=3, edge_sequence=[[e] for e in seq], inplace=True)
-    for k in msgs:
-        assert rel_err(bpc.message(k), b2.message(k)) < 1e-12
+    for mode in (1, 2):  # shape-generic DMMA kernels, plain FMA kernels
+        c2 = E.Context(0)
+        c2.set_path(mode)
+        b2 = E.BeliefPropagationCache(psi, ctx=c2)
+        E.update(b2, maxiter=3, edge_sequence=[[e] for e in seq], inplace=True)
+        for k in msgs:
+            assert rel_err(bpc.message(k), b2.message(k)) < 1e-12
     # observables downstream of the fast path
     ez = E.expect(bpc, "Z")
     for v in (0, 6, 12):

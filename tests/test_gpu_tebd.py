@@ -60,3 +60,38 @@ def test_kicked_ising_heavy_hex():
     worst = max(abs(ez[v] - O.expect1(net, msgs, v, O.PAULI_Z)) for v in range(g.nv))
     assert worst < 1e-8, worst
     assert max(bpc.edge_dim(e) for e in range(g.ne)) == maxdim
+
+
+def test_tebd_step_single_call_equals_host_loop():
+    # itn_apply_layers (include/itn_b200.h): gate layers + BP sweeps in one library call = the same calls made one by one
+    g = O.grid_graph((5, 4))
+    eg = E.named_grid((5, 4))
+    psi = E.random_tensornetwork(5, np.complex128, eg, link_space=3)
+    ctx = E.Context(0)
+    seq = [[e] for e in O.parallel_edge_sequence(g)]
+    a = E.update(E.BeliefPropagationCache(psi, ctx=ctx), maxiter=5, edge_sequence=seq)
+    b = a.copy()
+    gate = rzz(-0.9)
+    kick = O.random_unitary(4, seed=5).reshape(2, 2, 2, 2)
+    layers = []
+    for li, layer in enumerate(O.edge_coloring(g)):
+        layers.append(([gate if li % 2 == 0 else kick] * len(layer), [g.edges[e] for e in layer]))
+    infos = []
+    for gates, pairs in layers:
+        infos.append(E.apply_layer(gates, a, pairs, maxdim=4, cutoff=1e-11))
+        E.update(a, maxiter=3, edge_sequence=seq, inplace=True)
+    info = {}
+    res = E.tebd_step(b, layers, maxdim=4, cutoff=1e-11, bp_maxiter=3, edge_sequence=seq, info=info)
+    assert info["bp_iterations"] == 3 * len(layers)
+    off = 0
+    for li, inf in enumerate(infos):
+        n = len(inf["newdim"])
+        assert np.array_equal(res["newdim"][off:off + n], inf["newdim"])
+        assert np.array_equal(res["truncation_error"][off:off + n], inf["truncation_error"])
+        for i in range(n):
+            assert np.array_equal(res["singular_values"][off + i], inf["singular_values"][i])
+        off += n
+    for v in range(g.nv):
+        assert np.array_equal(a.factor(v), b.factor(v))
+    for (u, v) in g.edges:
+        assert np.array_equal(a.message((u, v)), b.message((u, v)))
