@@ -130,7 +130,7 @@ struct FastArgs {
 };
 
 template <bool C, bool HAS_P, bool DO_W>
-__global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
+__global__ void __launch_bounds__(kThreads, HAS_P ? 2 : 3) k_fast(const FastArgs a) {
   extern __shared__ __align__(16) double sm[];
   constexpr int TILE = C ? 512 : 256;
   constexpr int TS = TILE + 2;  // shared-memory tile stride: +2 doubles rotates the banks from tile to tile
@@ -148,18 +148,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
   const size_t cube = (((size_t)s_site * 16 + q) * 16 + half * kTilesPerCta) * TILE;
 
   {
-    const double* gx = a.Xv[vi] + cube;
-    for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
-      const int w = i / (TILE / 2), r = i - w * (TILE / 2);
-      cp_async16(Xs + w * TS + 2 * r, gx + 2 * i);
-    }
+    // two cp.async groups: the partially absorbed tiles P first (the products M_L^T P and P M_R need nothing else),
+    // the site-tensor tiles X second, so that the copy of X overlaps the first two tile products
     if (HAS_P) {
       const double* gp = a.Pv[vi] + cube;
       for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
         const int w = i / (TILE / 2), r = i - w * (TILE / 2);
         cp_async16(Ps + w * TS + 2 * r, gp + 2 * i);
       }
+      asm volatile("cp.async.commit_group;\n" ::);
     }
+    const double* gx = a.Xv[vi] + cube;
+    for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
+      const int w = i / (TILE / 2), r = i - w * (TILE / 2);
+      cp_async16(Xs + w * TS + 2 * r, gx + 2 * i);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
     const double* ml = a.msg[vi * 4 + a.kL];
     const double* mr = a.msg[vi * 4 + a.kR];
     const int o = swz(tid & 15, tid >> 4);
@@ -169,7 +173,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
       MLs[256 + o] = ml[256 + tid];
       MRs[256 + o] = mr[256 + tid];
     }
-    cp_async_commit_wait_all();
+    if (HAS_P) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   }
   __syncthreads();
 
@@ -183,18 +188,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_fast(const FastArgs a) {
     zero_acc<C>(cre, cim);
     tile_mm<C, true, false, false>(MLs, P, cre, cim, lane);
     store_acc<C>(S, cre, cim, lane);
-    __syncwarp();
-    // right output: O[l,l'] = sum_k T[k,l] conj(X[k,l'])
-    zero_acc<C>(cre, cim);
-    tile_mm<C, true, false, true>(S, X, cre, cim, lane);
-    __syncwarp();
-    store_acc<C>(S, cre, cim, lane);
     // U = P MR   (U overwrites P: every lane holds its P fragments in registers before the store)
     zero_acc<C>(cre, cim);
     tile_mm<C, false, false, false>(P, MRs, cre, cim, lane);
     __syncwarp();
     store_acc<C>(P, cre, cim, lane);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();  // X has landed (copied by all threads of the CTA)
+    // right output: O[l,l'] = sum_k T[k,l] conj(X[k,l'])
+    zero_acc<C>(cre, cim);
+    tile_mm<C, true, false, true>(S, X, cre, cim, lane);
     __syncwarp();
+    store_acc<C>(S, cre, cim, lane);
     // left output: O[a,a''] = sum_k U[a,k] conj(X[a'',k])   (kept in registers; stored once P is free)
     zero_acc<C>(lre, lim);
     tile_mm<C, false, true, true>(P, X, lre, lim, lane);

@@ -167,15 +167,22 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
         const double zeta = (beta - alpha) * 0.5 * ginv;
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         const double c = rsqrt(1.0 + t * t), s = c * t;
+        // de Rijk's ordering: the column that ends up with the larger norm is stored at the lower index p, so the
+        // columns sort themselves by decreasing norm as the sweeps proceed (fewer sweeps to convergence)
+        const bool swap = alpha < beta;
+        double* wpr = swap ? aqr : apr;
+        double* wqr = swap ? apr : aqr;
+        double* wpi = swap ? aqi : api;
+        double* wqi = swap ? api : aqi;
         for (int i = sl; i < m; i += LP) {
           const double pr = apr[i], qr0 = aqr[i];
           const double pi = C ? api[i] : 0.0, qi0 = C ? aqi[i] : 0.0;
           const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
-          apr[i] = c * pr - s * qr;
-          aqr[i] = s * pr + c * qr;
+          wpr[i] = c * pr - s * qr;
+          wqr[i] = s * pr + c * qr;
           if (C) {
-            api[i] = c * pi - s * qi;
-            aqi[i] = s * pi + c * qi;
+            wpi[i] = c * pi - s * qi;
+            wqi[i] = s * pi + c * qi;
           }
         }
         if (has_v) {
@@ -183,21 +190,25 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
           double* vqr = Vr + (long long)q * n;
           double* vpi = C ? Vi + (long long)p * n : nullptr;
           double* vqi = C ? Vi + (long long)q * n : nullptr;
+          double* xpr = swap ? vqr : vpr;
+          double* xqr = swap ? vpr : vqr;
+          double* xpi = swap ? vqi : vpi;
+          double* xqi = swap ? vpi : vqi;
           for (int i = sl; i < n; i += LP) {
             const double pr = vpr[i], qr0 = vqr[i];
             const double pi = C ? vpi[i] : 0.0, qi0 = C ? vqi[i] : 0.0;
             const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
-            vpr[i] = c * pr - s * qr;
-            vqr[i] = s * pr + c * qr;
+            xpr[i] = c * pr - s * qr;
+            xqr[i] = s * pr + c * qr;
             if (C) {
-              vpi[i] = c * pi - s * qi;
-              vqi[i] = s * pi + c * qi;
+              xpi[i] = c * pi - s * qi;
+              xqi[i] = s * pi + c * qi;
             }
           }
         }
         if (sl == 0) {
-          s_norm[p] = fmax(alpha - t * gabs, 0.0);
-          s_norm[q] = beta + t * gabs;
+          s_norm[swap ? q : p] = fmax(alpha - t * gabs, 0.0);
+          s_norm[swap ? p : q] = beta + t * gabs;
           // rotations at the rounding level of the inner product are applied but do not keep the iteration alive
           if (g2 > 64.0 * tol * tol * alpha * beta) s_rot = 1;
         }

@@ -71,3 +71,40 @@ def test_config4_grid64_chi16_dmma_sweep_equals_generic_updates():
     assert 0.0 <= info["mean_diff"] < 1.0
     tm = bpc.last_timing()
     assert tm["contract_ms"] < 200.0  # the DMMA path ran (the generic kernels need ~350 ms per sweep)
+
+
+def test_config3_heavyhex_chi32_bp_and_gate_layer_match_oracle():
+    # BASELINE config 3 at its full bond dimension: 127-qubit heavy-hex, chi = 32, ComplexF64.  Bond matrices of the
+    # simple update are 128 x 128 (interior) down to 2 x 64 (leaves); the oracle still runs this size in seconds.
+    from oracle import itn_oracle as O
+    g = O.heavy_hex_eagle_graph()
+    eg = E.heavy_hex_eagle()
+    net = O.random_network(g, 32, dtype=np.complex128, seed=77)
+    psi = E.ITensorNetwork(eg, [t.copy() for t in net.tensors], np.complex128)
+    ctx = E.Context(0)
+    seq = O.parallel_edge_sequence(g)
+    sync = [[e] for e in seq]
+    msgs, _, _ = O.bp_update(net, O.identity_messages(net), seq=seq, groups=O.synchronous_groups(seq), maxiter=3)
+    bpc = E.BeliefPropagationCache(psi, ctx=ctx)
+    E.update(bpc, maxiter=3, edge_sequence=sync, inplace=True)
+    worst = max(np.linalg.norm(bpc.message(k) - m) / np.linalg.norm(m) for k, m in msgs.items())
+    assert worst < 1e-10, worst
+    layer = O.edge_coloring(g)[0]
+    rng = np.random.default_rng(9)
+    h = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    h = (h + h.conj().T) / 2
+    w, v = np.linalg.eigh(h)
+    gate = ((v * np.exp(-0.3j * w)) @ v.conj().T).reshape(2, 2, 2, 2)
+    info = E.apply_layer([gate] * len(layer), bpc, [g.edges[e] for e in layer], maxdim=32, cutoff=1e-12)
+    for i, e in enumerate(layer):
+        new, inf = O.simple_update_bp(net, msgs, e, gate, maxdim=32, cutoff=1e-12)
+        assert info["newdim"][i] == inf["newdim"], (e, info["newdim"][i], inf["newdim"])
+        assert abs(info["truncation_error"][i] - inf["truncerr"]) < 1e-10
+        sv = inf["svals"][:inf["newdim"]]
+        assert np.max(np.abs(info["singular_values"][i] - sv)) < 1e-10 * sv[0]
+        if i < 6:  # the updated pair (gauge invariant): A1' . A2' contracted over the new bond
+            v1, v2 = g.edges[e]
+            k1, k2 = g.slot(v1, e), g.slot(v2, e)
+            pair_o = np.tensordot(new.tensors[v1], new.tensors[v2], axes=([1 + k1], [1 + k2]))
+            pair_e = np.tensordot(bpc.factor(v1), bpc.factor(v2), axes=([1 + k1], [1 + k2]))
+            assert np.linalg.norm(pair_e - pair_o) < 1e-9 * np.linalg.norm(pair_o)
