@@ -66,8 +66,8 @@ __device__ __forceinline__ double gsum(double v, unsigned mask) {
   return v;
 }
 
-template <bool C, int LP>
-__global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __restrict__ jobs, int smem_doubles) {
+template <bool C, int LP, bool CACHE>
+__global__ void __launch_bounds__(CACHE ? 512 : kSvdMaxThreads) k_jacobi_svd(const SvdJob* __restrict__ jobs, int smem_doubles) {
   extern __shared__ double sm[];
   __shared__ int s_rot;
   __shared__ double s_norm[256];  // squared column norms
@@ -150,11 +150,26 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
         double* api = C ? Ai + (long long)p * m : nullptr;
         double* aqi = C ? Ai + (long long)q * m : nullptr;
         double gr = 0, gi = 0;
-        for (int i = sl; i < m; i += LP) {
-          const double pr = apr[i], qr = aqr[i];
-          const double pi = C ? api[i] : 0.0, qi = C ? aqi[i] : 0.0;
-          gr += pr * qr + pi * qi;  // conj(a_p) . a_q
-          gi += pr * qi - pi * qr;
+        double rpr[4], rpi[4], rqr[4], rqi[4];
+        if (CACHE) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = sl + LP * j;
+            const bool ok = i < m;
+            rpr[j] = ok ? apr[i] : 0.0;
+            rqr[j] = ok ? aqr[i] : 0.0;
+            rpi[j] = (C && ok) ? api[i] : 0.0;
+            rqi[j] = (C && ok) ? aqi[i] : 0.0;
+            gr += rpr[j] * rqr[j] + rpi[j] * rqi[j];  // conj(a_p) . a_q
+            gi += rpr[j] * rqi[j] - rpi[j] * rqr[j];
+          }
+        } else {
+          for (int i = sl; i < m; i += LP) {
+            const double pr = apr[i], qr = aqr[i];
+            const double pi = C ? api[i] : 0.0, qi = C ? aqi[i] : 0.0;
+            gr += pr * qr + pi * qi;  // conj(a_p) . a_q
+            gi += pr * qi - pi * qr;
+          }
         }
         gr = gsum<LP>(gr, gmask);
         gi = C ? gsum<LP>(gi, gmask) : 0.0;
@@ -167,22 +182,34 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
         const double zeta = (beta - alpha) * 0.5 * ginv;
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         const double c = rsqrt(1.0 + t * t), s = c * t;
-        // de Rijk's ordering: the column that ends up with the larger norm is stored at the lower index p, so the
-        // columns sort themselves by decreasing norm as the sweeps proceed (fewer sweeps to convergence)
-        const bool swap = alpha < beta;
-        double* wpr = swap ? aqr : apr;
-        double* wqr = swap ? apr : aqr;
-        double* wpi = swap ? aqi : api;
-        double* wqi = swap ? api : aqi;
-        for (int i = sl; i < m; i += LP) {
-          const double pr = apr[i], qr0 = aqr[i];
-          const double pi = C ? api[i] : 0.0, qi0 = C ? aqi[i] : 0.0;
-          const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
-          wpr[i] = c * pr - s * qr;
-          wqr[i] = s * pr + c * qr;
-          if (C) {
-            wpi[i] = c * pi - s * qi;
-            wqi[i] = s * pi + c * qi;
+        if (CACHE) {
+          // m <= 4 LP: the rows of this lane group are still in registers from the inner product
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = sl + LP * j;
+            if (i < m) {
+              const double pr = rpr[j], qr0 = rqr[j];
+              const double pi = C ? rpi[j] : 0.0, qi0 = C ? rqi[j] : 0.0;
+              const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
+              apr[i] = c * pr - s * qr;
+              aqr[i] = s * pr + c * qr;
+              if (C) {
+                api[i] = c * pi - s * qi;
+                aqi[i] = s * pi + c * qi;
+              }
+            }
+          }
+        } else {
+          for (int i = sl; i < m; i += LP) {
+            const double pr = apr[i], qr0 = aqr[i];
+            const double pi = C ? api[i] : 0.0, qi0 = C ? aqi[i] : 0.0;
+            const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
+            apr[i] = c * pr - s * qr;
+            aqr[i] = s * pr + c * qr;
+            if (C) {
+              api[i] = c * pi - s * qi;
+              aqi[i] = s * pi + c * qi;
+            }
           }
         }
         if (has_v) {
@@ -190,25 +217,21 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
           double* vqr = Vr + (long long)q * n;
           double* vpi = C ? Vi + (long long)p * n : nullptr;
           double* vqi = C ? Vi + (long long)q * n : nullptr;
-          double* xpr = swap ? vqr : vpr;
-          double* xqr = swap ? vpr : vqr;
-          double* xpi = swap ? vqi : vpi;
-          double* xqi = swap ? vpi : vqi;
           for (int i = sl; i < n; i += LP) {
             const double pr = vpr[i], qr0 = vqr[i];
             const double pi = C ? vpi[i] : 0.0, qi0 = C ? vqi[i] : 0.0;
             const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
-            xpr[i] = c * pr - s * qr;
-            xqr[i] = s * pr + c * qr;
+            vpr[i] = c * pr - s * qr;
+            vqr[i] = s * pr + c * qr;
             if (C) {
-              xpi[i] = c * pi - s * qi;
-              xqi[i] = s * pi + c * qi;
+              vpi[i] = c * pi - s * qi;
+              vqi[i] = s * pi + c * qi;
             }
           }
         }
         if (sl == 0) {
-          s_norm[swap ? q : p] = fmax(alpha - t * gabs, 0.0);
-          s_norm[swap ? p : q] = beta + t * gabs;
+          s_norm[p] = fmax(alpha - t * gabs, 0.0);
+          s_norm[q] = beta + t * gabs;
           // rotations at the rounding level of the inner product are applied but do not keep the iteration alive
           if (g2 > 64.0 * tol * tol * alpha * beta) s_rot = 1;
         }
@@ -239,12 +262,13 @@ __global__ void __launch_bounds__(kSvdMaxThreads) k_jacobi_svd(const SvdJob* __r
   }
 }
 
-template <bool C, int LP>
+template <bool C, int LP, bool CACHE>
 void launch_jacobi(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int pairs, size_t smem) {
   constexpr int PW = 32 / LP;
-  const int warps = std::min(32, std::max(1, (pairs + PW - 1) / PW));
-  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<C, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_jacobi_svd<C, LP><<<njobs, warps * 32, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
+  const int warps = std::min(CACHE ? 16 : 32, std::max(1, (pairs + PW - 1) / PW));
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<C, LP, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_svd<C, LP, CACHE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  k_jacobi_svd<C, LP, CACHE><<<njobs, warps * 32, smem, ctx->stream>>>(dj, (int)(smem / sizeof(double)));
   ITN_LAUNCH_CHECK(ctx);
 }
 
@@ -264,11 +288,13 @@ void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
   const int pairs = (maxn + 1) / 2;
   const unsigned nj = (unsigned)jobs.size();
   if (maxm <= 64) {
-    if (cplx) launch_jacobi<true, 16>(ctx, dj, nj, pairs, smem);
-    else launch_jacobi<false, 16>(ctx, dj, nj, pairs, smem);
+    // (CACHE = true keeps the rows of a column pair in registers between the inner product and the rotation; at 126
+    //  registers per thread it halves the occupancy and is slower than re-reading shared memory, so it is not selected)
+    if (cplx) launch_jacobi<true, 16, false>(ctx, dj, nj, pairs, smem);
+    else launch_jacobi<false, 16, false>(ctx, dj, nj, pairs, smem);
   } else {
-    if (cplx) launch_jacobi<true, 32>(ctx, dj, nj, pairs, smem);
-    else launch_jacobi<false, 32>(ctx, dj, nj, pairs, smem);
+    if (cplx) launch_jacobi<true, 32, false>(ctx, dj, nj, pairs, smem);
+    else launch_jacobi<false, 32, false>(ctx, dj, nj, pairs, smem);
   }
 }
 

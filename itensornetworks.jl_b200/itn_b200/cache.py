@@ -23,6 +23,11 @@ from .graphs import default_edge_sequence
 from .network import ITensorNetwork
 
 _DTYPE_CODE = {np.dtype(np.float64): 0, np.dtype(np.complex128): 1}
+# The engine computes in Float64 / ComplexF64.  The reference's tests also run Float32 / ComplexF32 networks and pin that
+# the element type is preserved (test_belief_propagation.jl:54, test_normalize.jl:59): single-precision inputs are widened
+# at the boundary and everything handed back (messages, factors, scalars, observables) is narrowed to the input's type.
+_COMPUTE = {np.dtype(np.float32): np.dtype(np.float64), np.dtype(np.complex64): np.dtype(np.complex128),
+            np.dtype(np.float64): np.dtype(np.float64), np.dtype(np.complex128): np.dtype(np.complex128)}
 
 
 class Context:
@@ -75,13 +80,15 @@ class BeliefPropagationCache:
                  defer_upload=False, _handle=None, _like=None):
         if _handle is not None:  # clone
             self.ctx, self.graph, self.dtype, self.h = _like.ctx, _like.graph, _like.dtype, _handle
+            self.eltype = _like.eltype
             self._host_refs = None
             self.sdims = list(_like.sdims)
             self.owner, self.rank = _like.owner, _like.rank
             return
         self.ctx = ctx or default_context()
         self.graph = psi.graph
-        self.dtype = psi.dtype
+        self.eltype = np.dtype(psi.dtype)      # what the caller sees
+        self.dtype = _COMPUTE[self.eltype]     # what the device computes in
         g = self.graph
         self.sdims = [t.shape[0] for t in psi.tensors]
         # multi-GPU: owner[v] = rank that stores vertex v; dist = (rank, nranks) of this process
@@ -163,10 +170,10 @@ class BeliefPropagationCache:
         shape = self._shape(v)
         out = np.empty(shape, dtype=self.dtype, order="F")
         check(lib().itn_net_get_tensor(self.h, int(v), out.ctypes.data_as(C.c_void_p), len(shape), None))
-        return np.ascontiguousarray(out)
+        return np.ascontiguousarray(out).astype(self.eltype, copy=False)
 
     def tensornetwork(self):
-        return ITensorNetwork(self.graph, [self.factor(v) for v in range(self.graph.nv)], self.dtype)
+        return ITensorNetwork(self.graph, [self.factor(v) for v in range(self.graph.nv)], self.eltype)
 
     # -- messages -----------------------------------------------------------------------------
     def message(self, edge):
@@ -174,7 +181,7 @@ class BeliefPropagationCache:
         chi = self.edge_dim(self.graph.eid[(u, v)])
         out = np.empty((chi, chi), dtype=self.dtype, order="F")
         check(lib().itn_msg_get(self.h, int(u), int(v), out.ctypes.data_as(C.c_void_p)))
-        return np.ascontiguousarray(out)
+        return np.ascontiguousarray(out).astype(self.eltype, copy=False)
 
     def set_message(self, edge, m):
         u, v = edge
@@ -246,7 +253,7 @@ def updated_message(bpc, edge, normalize=True):
     chi = bpc.edge_dim(bpc.graph.eid[(u, v)])
     out = np.empty((chi, chi), dtype=bpc.dtype, order="F")
     check(lib().itn_updated_message(bpc.h, int(u), int(v), 1 if normalize else 0, out.ctypes.data_as(C.c_void_p)))
-    return np.ascontiguousarray(out)
+    return np.ascontiguousarray(out).astype(bpc.eltype, copy=False)
 
 
 def update_message(bpc, edge, normalize=True):
@@ -299,7 +306,7 @@ def scalar_factors_quotient(bpc):
     zv = np.empty(bpc.graph.nv, dtype=bpc.dtype)
     ze = np.empty(max(bpc.graph.ne, 1), dtype=bpc.dtype)
     check(lib().itn_region_scalars(bpc.h, zv.ctypes.data_as(C.c_void_p), ze.ctypes.data_as(C.c_void_p)))
-    return zv, ze[: bpc.graph.ne]
+    return zv.astype(bpc.eltype, copy=False), ze[: bpc.graph.ne].astype(bpc.eltype, copy=False)
 
 
 def vertex_scalars(bpc):
@@ -396,6 +403,7 @@ def expect(psi, operator, vertices=None, alg="bp", cache=None, update_cache=None
     out = np.empty(len(vertices), dtype=cache.dtype)
     _, pv = i32(vertices)
     check(lib().itn_expect1(cache.h, pv, len(vertices), ops.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    out = out.astype(cache.eltype, copy=False)
     return {int(v): out[i] for i, v in enumerate(vertices)}
 
 
@@ -409,7 +417,7 @@ def rdm2(bpc, edges):
     check(lib().itn_rdm2(bpc.h, pe, len(eids), out.ctypes.data_as(C.c_void_p)))
     res, off = [], 0
     for d in ds:
-        res.append(out[off:off + d * d].reshape(d, d, order="F").copy())
+        res.append(out[off:off + d * d].reshape(d, d, order="F").astype(bpc.eltype))
         off += d * d
     return res
 

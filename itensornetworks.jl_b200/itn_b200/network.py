@@ -14,7 +14,8 @@ class ITensorNetwork:
     def __init__(self, graph: NamedGraph, tensors, dtype=None):
         self.graph = graph
         self.dtype = np.dtype(dtype if dtype is not None else tensors[0].dtype)
-        assert self.dtype in (np.dtype(np.float64), np.dtype(np.complex128)), "Float64 / ComplexF64 only"
+        assert self.dtype in (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.complex64), np.dtype(np.complex128)), \
+            "Float32 / Float64 / ComplexF32 / ComplexF64 only"
         self.tensors = [np.asarray(t, dtype=self.dtype) for t in tensors]
         for v, t in enumerate(self.tensors):
             assert t.ndim == 1 + graph.degree(v), f"tensor {v} must have axes [site, bonds...]"

@@ -270,3 +270,26 @@ def test_deferred_upload_first_sweep_overlaps_copy(dtype, dims, chi, monkeypatch
     e3 = E.update(E.BeliefPropagationCache(psi, ctx=c), maxiter=1)
     E.update(lazy3, maxiter=1, inplace=True)
     assert np.array_equal(lazy3.message(g.edges[0]), e3.message(g.edges[0]))
+
+
+@pytest.mark.parametrize("eltype", [np.float32, np.complex64])
+def test_single_precision_element_types_are_preserved(eltype):
+    # test_belief_propagation.jl:18-55 and test_normalize.jl:52-66 run Float32 / ComplexF32 networks and pin that the
+    # element type survives; the engine widens at the boundary, computes in double and narrows what it hands back
+    g = O.grid_graph((3, 3))
+    net = O.random_network(g, 2, dtype=np.complex128 if np.dtype(eltype).kind == "c" else np.float64, seed=1234)
+    eg = E.NamedGraph(g.nv, g.edges)
+    psi = E.ITensorNetwork(eg, [t.astype(eltype) for t in net.tensors], eltype)
+    bpc = E.BeliefPropagationCache(psi, ctx=E.Context(0))
+    seq = [[e] for e in O.parallel_edge_sequence(g)]
+    bpc = E.update(bpc, maxiter=25, tol=float(np.finfo(eltype).eps), edge_sequence=seq)
+    for e in g.edges:
+        assert bpc.message(e).dtype == np.dtype(eltype)
+        assert E.message_diff(E.updated_message(bpc, e), bpc.message(e)) < 10 * np.finfo(eltype).eps
+    assert bpc.factor(0).dtype == np.dtype(eltype)
+    r = E.rescale(bpc)
+    zv, ze = E.scalar_factors_quotient(r)
+    assert zv.dtype == np.dtype(eltype)
+    assert np.allclose(zv, 1.0, atol=1e-5) and np.allclose(ze, 1.0, atol=1e-5)
+    out = E.normalize(psi, cache=bpc)
+    assert out.dtype == np.dtype(eltype)
