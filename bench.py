@@ -419,7 +419,7 @@ def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch, dist=None):
     for layer in layers:
         ta = time.perf_counter()
         info = E.apply_layer([gate] * len(layer), work, [graph.edges[e] for e in layer], maxdim=chi, cutoff=None)
-        per_layer.append(round(1e3 * (time.perf_counter() - ta), 2))  # apply_layer returns after the device is done
+        per_layer.append(round(1e3 * (time.perf_counter() - ta), 2))  # host-side time of the call: the rebuild of a layer overlaps the next call, the step total is synchronised
         ngates += len(layer)
         terr = max(terr, float(np.max(info["truncation_error"])))
     torch.cuda.synchronize()

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <complex>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <numeric>
 
@@ -1777,46 +1778,99 @@ extern "C" int itn_rdm2(itn_net* net, const int32_t* eids, int n, void* out) {
   itn_flush_pending(net);
   itn_ctx* ctx = net->ctx;
   const int P = net->planes();
-  size_t env_elems = 0, out_elems = 0;
+  const bool multi = ctx->nranks > 1;
+  // Partitioned network: every rank is called with the same list.  The bond environment of a site is computed where the
+  // site lives; the rank that owns esrc combines the two environments of an edge (for an edge that crosses a cut the
+  // other rank ships its (d chi)^2 environment, as itn_apply2 does), and one all-reduce hands every rank every matrix.
   int maxD2 = 0;
+  std::map<int, std::pair<size_t, size_t>> seg;  // peer -> (doubles to send, doubles to receive)
   for (int i = 0; i < n; ++i) {
     int e = eids[i];
     ITN_REQUIRE(e >= 0 && e < net->ne, ITN_EINVAL, "edge id out of range");
     int u = net->esrc[e], v = net->edst[e];
-    ITN_REQUIRE(itn_is_local(net, u) && itn_is_local(net, v), ITN_EUNSUPPORTED,
-                "rdm2 on an edge that crosses a partition cut is not supported yet");
-    long long nu = (long long)net->sdim[u] * net->edim[e], nv_ = (long long)net->sdim[v] * net->edim[e];
-    env_elems += (size_t)(nu * nu + nv_ * nv_);
     int D = net->sdim[u] * net->sdim[v];
     ITN_REQUIRE(D * D <= 256, ITN_EUNSUPPORTED, "rdm2 supports d_u*d_v <= 16");
     maxD2 = std::max(maxD2, D * D);
-    out_elems += (size_t)D * D;
+    const bool lu = itn_is_local(net, u), lv = itn_is_local(net, v);
+    const size_t nv2 = (size_t)P * net->sdim[v] * net->edim[e] * net->sdim[v] * net->edim[e];
+    if (lu && !lv) seg[net->owner[v]].second += nv2;
+    if (!lu && lv) seg[net->owner[u]].first += nv2;
   }
-  DevBuf denv(ctx, env_elems * P * sizeof(double));
-  DevBuf dout(ctx, (size_t)n * maxD2 * 2 * sizeof(double));
-  std::vector<JobSpec> specs;
-  std::vector<Rdm2Job> rj(n);
-  size_t off = 0;
+  size_t tot_s = 0, tot_r = 0;
+  std::map<int, std::pair<size_t, size_t>> segoff, cur;
+  for (auto& kv : seg) {
+    segoff[kv.first] = {tot_s, tot_r};
+    cur[kv.first] = {0, 0};
+    tot_s += kv.second.first;
+    tot_r += kv.second.second;
+  }
+  DevBuf sbuf(ctx, tot_s * sizeof(double)), rbuf(ctx, tot_r * sizeof(double));
+  size_t env_elems = 0;
   for (int i = 0; i < n; ++i) {
     int e = eids[i], u = net->esrc[e], v = net->edst[e];
     long long nu = (long long)net->sdim[u] * net->edim[e], nv_ = (long long)net->sdim[v] * net->edim[e];
-    double* eu = denv.as<double>() + off * P;
-    off += (size_t)(nu * nu);
-    double* ev = denv.as<double>() + off * P;
-    off += (size_t)(nv_ * nv_);
+    if (itn_is_local(net, u)) env_elems += (size_t)(nu * nu);
+    if (itn_is_local(net, u) && itn_is_local(net, v)) env_elems += (size_t)(nv_ * nv_);
+  }
+  DevBuf denv(ctx, std::max<size_t>(env_elems, 1) * P * sizeof(double));
+  DevBuf dout(ctx, (size_t)n * maxD2 * 2 * sizeof(double));
+  CUDA_CHECK(cudaMemsetAsync(dout.p, 0, (size_t)n * maxD2 * 2 * sizeof(double), ctx->stream));
+  std::vector<JobSpec> specs;
+  std::vector<Rdm2Job> rj;
+  std::vector<int> rj_gate;
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    int e = eids[i], u = net->esrc[e], v = net->edst[e];
+    const bool lu = itn_is_local(net, u), lv = itn_is_local(net, v);
+    if (!lu && !lv) continue;
+    long long nu = (long long)net->sdim[u] * net->edim[e], nv_ = (long long)net->sdim[v] * net->edim[e];
     for (int w : {u, v})
-      for (int f : net->inc[w])
-        if (f != e) ITN_REQUIRE(net->M[net->msg_into(w, f)].p, ITN_EINVAL, "an incoming message is not set");
-    specs.push_back({u, 1u | (1u << (net->slot(u, e) + 1)), eu});
-    specs.push_back({v, 1u | (1u << (net->slot(v, e) + 1)), ev});
-    rj[i] = {eu, ev, net->sdim[u], net->sdim[v], net->edim[e]};
+      if (itn_is_local(net, w))
+        for (int f : net->inc[w])
+          if (f != e) ITN_REQUIRE(net->M[net->msg_into(w, f)].p, ITN_EINVAL, "an incoming message is not set");
+    double *eu = nullptr, *ev = nullptr;
+    if (lu) {
+      eu = denv.as<double>() + off * P;
+      off += (size_t)(nu * nu);
+      specs.push_back({u, 1u | (1u << (net->slot(u, e) + 1)), eu});
+      if (lv) {
+        ev = denv.as<double>() + off * P;
+        off += (size_t)(nv_ * nv_);
+        specs.push_back({v, 1u | (1u << (net->slot(v, e) + 1)), ev});
+      } else {  // arrives from the rank that owns v
+        const int peer = net->owner[v];
+        ev = rbuf.as<double>() + segoff[peer].second + cur[peer].second;
+        cur[peer].second += (size_t)P * nv_ * nv_;
+      }
+      rj.push_back({eu, ev, net->sdim[u], net->sdim[v], net->edim[e]});
+      rj_gate.push_back(i);
+    } else {  // guest: the environment of v goes to the owner of u
+      const int peer = net->owner[u];
+      ev = sbuf.as<double>() + segoff[peer].first + cur[peer].first;
+      cur[peer].first += (size_t)P * nv_ * nv_;
+      specs.push_back({v, 1u | (1u << (net->slot(v, e) + 1)), ev});
+    }
   }
   itn_run_vertex_jobs(net, specs);
-  DevBuf jb(ctx, rj.size() * sizeof(Rdm2Job));
-  const Rdm2Job* dj = itn_upload(ctx, rj, jb);
-  if (net->cplx) k_rdm2_finalize<true><<<n, 256, 0, ctx->stream>>>(dj, dout.as<double>(), maxD2 * 2);
-  else k_rdm2_finalize<false><<<n, 256, 0, ctx->stream>>>(dj, dout.as<double>(), maxD2 * 2);
-  ITN_LAUNCH_CHECK(ctx);
+  if (multi) {
+    std::vector<P2PSeg> xs;
+    for (auto& kv : seg)
+      xs.push_back({kv.first, sbuf.as<double>() + segoff[kv.first].first, kv.second.first,
+                    rbuf.as<double>() + segoff[kv.first].second, kv.second.second});
+    itn_dist_p2p(ctx, xs);
+  }
+  if (!rj.empty()) {
+    // the finalize kernel writes row blockIdx.x of its output: give every owned gate its own row of dout
+    DevBuf jb(ctx, rj.size() * sizeof(Rdm2Job)), tmp(ctx, rj.size() * (size_t)maxD2 * 2 * sizeof(double));
+    const Rdm2Job* dj = itn_upload(ctx, rj, jb);
+    if (net->cplx) k_rdm2_finalize<true><<<(unsigned)rj.size(), 256, 0, ctx->stream>>>(dj, tmp.as<double>(), maxD2 * 2);
+    else k_rdm2_finalize<false><<<(unsigned)rj.size(), 256, 0, ctx->stream>>>(dj, tmp.as<double>(), maxD2 * 2);
+    ITN_LAUNCH_CHECK(ctx);
+    for (size_t k = 0; k < rj.size(); ++k)
+      CUDA_CHECK(cudaMemcpyAsync(dout.as<double>() + (size_t)rj_gate[k] * maxD2 * 2, tmp.as<double>() + k * (size_t)maxD2 * 2,
+                                 (size_t)maxD2 * 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  itn_dist_allreduce_sum(ctx, dout.as<double>(), n * maxD2 * 2);
   std::vector<double> h((size_t)n * maxD2 * 2);
   CUDA_CHECK(cudaMemcpyAsync(h.data(), dout.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -1131,8 +1131,9 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     }
   }
   DevBuf d_gates(ctx, std::max<size_t>(gate_elems, 1) * P * sizeof(double));
+  std::vector<double> tmp;  // lives until the results have been read back (the stream is synchronised there)
   if (gate_elems) {
-    std::vector<double> tmp(gate_elems * P);
+    tmp.resize(gate_elems * P);
     const double* h = (const double*)gates;
     for (int i = 0; i < n; ++i) {
       if (geo[i].role != OWNER) continue;
@@ -1147,7 +1148,6 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       }
     }
     CUDA_CHECK(cudaMemcpyAsync(d_gates.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // tmp dies at scope end
   }
   // ---- carve workspace, build jobs ----
   struct EnvRef {
@@ -1513,7 +1513,8 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     if (svals_out)
       for (int t = 0; t < svals_stride; ++t) svals_out[(size_t)i * svals_stride + t] = t < stride ? hres[(size_t)i * RS + 2 + t] : 0.0;
   }
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  // no synchronisation here: everything destined for host pointers was complete at the read-back above; the rebuild of
+  // the site tensors finishes in stream order while the host prepares the next call
   API_END
 }
 

@@ -48,6 +48,10 @@ def main():
         worst = max(worst, abs(E.logscalar(bpc) - O.logscalar(net, ref)) * 1e-1)
         ez = E.expect(bpc, "Z")
         worst = max(worst, max(abs(ez[v] - O.expect1(net, ref, v, O.PAULI_Z)) for v in range(g.nv)))
+        # two-site RDMs on interior and cut edges (test_belief_propagation.jl:64-91): every rank gets every matrix
+        pick = [e for e, (u, v) in enumerate(g.edges) if owner[u] != owner[v]][:3] + [0, g.ne - 1]
+        for m, e in zip(E.rdm2(bpc, pick), pick):
+            worst = max(worst, np.linalg.norm(m - O.rdm2(net, ref, e)))
         r = E.rescale(bpc)
         zv2, ze2 = E.scalar_factors_quotient(r)
         worst = max(worst, float(np.max(np.abs(zv2 - 1))), float(np.max(np.abs(ze2 - 1))))
