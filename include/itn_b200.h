@@ -178,6 +178,13 @@ int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, const void*
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 
+/* Singular values (sorted descending, n per matrix) and optionally U*Sigma (columns in the kernel's internal order, not
+ * sorted) of `batch` host matrices m x n, column-major, through the batched one-sided Jacobi kernels that
+ * simple_update_bp's `factorize_svd` (src/apply.jl:81-88) runs on.  variant: 0 = the kernel the gate path selects,
+ * 1 = the shape-generic kernel (second opinion).  device_ms (nullable): CUDA-event time of the decomposition alone. */
+int itn_svd_batch(itn_ctx* ctx, int dtype, int m, int n, int batch, const void* host_in, double* host_sigma,
+                  void* host_us, int variant, double* device_ms);
+
 /* Number of kernels this library has launched on ctx since creation (bench.py "gpu_launches"). */
 int itn_ctx_launch_count(const itn_ctx* ctx, int64_t* out);
 /* Select the message-update implementation: 0 = auto (DMMA tile path where a bucket qualifies, the shape-generic

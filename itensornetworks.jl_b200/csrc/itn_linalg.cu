@@ -272,15 +272,247 @@ void launch_jacobi(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int pairs, si
   ITN_LAUNCH_CHECK(ctx);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_jacobi64: the same one-sided Jacobi iteration (same pair ordering, thresholds and norm updates as k_jacobi_svd)
+// specialised for the bond matrix of a gate: m, n <= 64, no V.  The matrix sits in shared memory as 64 x n with the rows
+// zero-padded to 64 (a zero row changes no inner product).  Eight lanes own one column pair of a round (four pairs per
+// warp, eight warps for 32 pairs); lane sl holds rows {2 sl, 2 sl + 1} + 16 j, j = 0..3, of both columns in registers
+// from the inner product to the rotation, so a round moves every column through shared memory exactly once in each
+// direction with 16-byte accesses (each 8-lane group touches 128 contiguous bytes: conflict free).  Control flow is
+// uniform inside a warp up to the shuffles (full-mask butterflies over offsets 4, 2, 1 stay inside a group); pair
+// indices need no division; shared memory is addressed directly (no generic loads).
+// ------------------------------------------------------------------------------------------------
+template <bool C>
+__global__ void __launch_bounds__(256, 2) k_jacobi64(const SvdJob* __restrict__ jobs) {
+  extern __shared__ double sm[];  // [planes][n cols][64 rows]
+  __shared__ double s_norm[64];
+  __shared__ double s_tiny;
+  __shared__ int s_rot;
+  const SvdJob J = jobs[blockIdx.x];
+  if (J.skip && *J.skip) return;
+  const int m = J.m, n = J.n;
+  if (n == 0 || m == 0) return;
+  double* dst = J.us ? J.us : J.a;
+  const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  const int sub = lane >> 3, sl = lane & 7;
+  double* Ar = sm;
+  double* Ai = sm + 64 * 64;
+  {
+    const double* src_r = J.a;
+    const double* src_i = J.a + (size_t)m * n;
+    for (int idx = tid; idx < n * 64; idx += nthreads) {
+      const int j = idx >> 6, i = idx & 63;
+      const bool ok = i < m;
+      Ar[idx] = ok ? src_r[(size_t)j * m + i] : 0.0;
+      if (C) Ai[idx] = ok ? src_i[(size_t)j * m + i] : 0.0;
+    }
+  }
+  __syncthreads();
+  auto column_norms = [&]() {
+    for (int jb = warp * 4; jb < n; jb += nwarps * 4) {  // uniform trip count inside a warp
+      const int j = jb + sub;
+      double a2 = 0.0;
+      if (j < n) {
+        const double2* cr = reinterpret_cast<const double2*>(Ar + j * 64) + sl;
+        const double2* ci = reinterpret_cast<const double2*>(Ai + j * 64) + sl;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const double2 r = cr[8 * t];
+          a2 += r.x * r.x + r.y * r.y;
+          if (C) {
+            const double2 im = ci[8 * t];
+            a2 += im.x * im.x + im.y * im.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      if (j < n && sl == 0) s_norm[j] = a2;
+    }
+  };
+  column_norms();
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int j = 0; j < n; ++j) t += s_norm[j];
+    s_tiny = t * (2.220446049250313e-19 * 2.220446049250313e-19);
+  }
+  __syncthreads();
+  const double tiny = s_tiny;
+  const int ne = n + (n & 1), npairs = ne >> 1;
+  const int k = warp * 4 + sub;  // pair slot of this lane group (the launch provides >= npairs groups)
+  const double tol = sqrt((double)m) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+  for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    if (sweep > 0) column_norms();
+    __syncthreads();
+    for (int round = 0; round < ne - 1; ++round) {
+      int p, q;
+      if (k == 0) {
+        p = ne - 1;
+        q = round;
+      } else {
+        p = round + k;
+        if (p >= ne - 1) p -= ne - 1;
+        q = round - k;
+        if (q < 0) q += ne - 1;
+      }
+      const bool valid = k < npairs && p < n && q < n;
+      if (!valid) p = q = 0;  // addresses stay in range; nothing is loaded or stored for a bye
+      if (p > q) {
+        const int t = p;
+        p = q;
+        q = t;
+      }
+      const double alpha = s_norm[p], beta = s_norm[q];
+      double2* cpr = reinterpret_cast<double2*>(Ar + p * 64) + sl;
+      double2* cqr = reinterpret_cast<double2*>(Ar + q * 64) + sl;
+      double2* cpi = reinterpret_cast<double2*>(Ai + p * 64) + sl;
+      double2* cqi = reinterpret_cast<double2*>(Ai + q * 64) + sl;
+      double2 pr[4], qr[4], pi[4], qi[4];
+      double gr = 0.0, gi = 0.0;
+      if (valid) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          pr[t] = cpr[8 * t];
+          qr[t] = cqr[8 * t];
+          if (C) {
+            pi[t] = cpi[8 * t];
+            qi[t] = cqi[8 * t];
+          }
+        }
+        double gr1 = 0.0, gi1 = 0.0;  // two accumulators per part: shorter dependent FMA chains
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // conj(a_p) . a_q
+          gr = fma(pr[t].x, qr[t].x, gr);
+          gr1 = fma(pr[t].y, qr[t].y, gr1);
+          if (C) {
+            gr = fma(pi[t].x, qi[t].x, gr);
+            gr1 = fma(pi[t].y, qi[t].y, gr1);
+            gi = fma(pr[t].x, qi[t].x, gi);
+            gi1 = fma(pr[t].y, qi[t].y, gi1);
+            gi = fma(-pi[t].x, qr[t].x, gi);
+            gi1 = fma(-pi[t].y, qr[t].y, gi1);
+          }
+        }
+        gr += gr1;
+        gi += gi1;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        gr += __shfl_xor_sync(0xffffffffu, gr, o);
+        if (C) gi += __shfl_xor_sync(0xffffffffu, gi, o);
+      }
+      const double g2 = gr * gr + gi * gi;
+      const double thr = tol2 * alpha * beta;
+      if (valid && alpha > tiny && beta > tiny && g2 > thr && g2 > 0.0) {
+        const double ginv = rsqrt(g2);
+        const double gabs = g2 * ginv;
+        // phase e^{-i phi} applied to column q so that the inner product becomes real positive
+        const double er = gr * ginv, ei = -gi * ginv;
+        const double zeta = (beta - alpha) * 0.5 * ginv;
+        const double w = fma(zeta, zeta, 1.0);
+        const double den = fabs(zeta) + w * rsqrt(w);  // >= 1
+        const double rden = rsqrt(den);
+        const double t = copysign(rden * rden, zeta);  // sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), sign(0) = +
+        const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          double2 npr, nqr, npi, nqi;
+          {
+            const double a = pr[u].x, ai = C ? pi[u].x : 0.0, b0 = qr[u].x, b0i = C ? qi[u].x : 0.0;
+            const double b = C ? (b0 * er - b0i * ei) : b0 * er, bi = C ? (b0 * ei + b0i * er) : 0.0;
+            npr.x = c * a - s * b;
+            nqr.x = s * a + c * b;
+            npi.x = c * ai - s * bi;
+            nqi.x = s * ai + c * bi;
+          }
+          {
+            const double a = pr[u].y, ai = C ? pi[u].y : 0.0, b0 = qr[u].y, b0i = C ? qi[u].y : 0.0;
+            const double b = C ? (b0 * er - b0i * ei) : b0 * er, bi = C ? (b0 * ei + b0i * er) : 0.0;
+            npr.y = c * a - s * b;
+            nqr.y = s * a + c * b;
+            npi.y = c * ai - s * bi;
+            nqi.y = s * ai + c * bi;
+          }
+          cpr[8 * u] = npr;
+          cqr[8 * u] = nqr;
+          if (C) {
+            cpi[8 * u] = npi;
+            cqi[8 * u] = nqi;
+          }
+        }
+        if (sl == 0) {
+          s_norm[p] = fmax(alpha - t * gabs, 0.0);
+          s_norm[q] = beta + t * gabs;
+          // rotations at the rounding level of the inner product are applied but do not keep the iteration alive
+          if (g2 > 64.0 * thr) s_rot = 1;
+        }
+      }
+      __syncthreads();
+    }
+    const int any = s_rot;
+    __syncthreads();
+    if (!any) break;
+  }
+  // singular values = exact column norms; stable descending order
+  column_norms();
+  __syncthreads();
+  for (int j = tid; j < n; j += nthreads) {
+    const double sj = s_norm[j];
+    int rank = 0;
+    for (int kk = 0; kk < n; ++kk) {
+      const double sk = s_norm[kk];
+      rank += (sk > sj) || (sk == sj && kk < j);
+    }
+    J.sigma[rank] = sqrt(sj);
+    J.perm[rank] = j;
+  }
+  {
+    double* dst_r = dst;
+    double* dst_i = dst + (size_t)m * n;
+    for (int idx = tid; idx < n * 64; idx += nthreads) {
+      const int j = idx >> 6, i = idx & 63;
+      if (i < m) {
+        dst_r[(size_t)j * m + i] = Ar[idx];
+        if (C) dst_i[(size_t)j * m + i] = Ai[idx];
+      }
+    }
+  }
+}
+
+template <bool C>
+void launch_jacobi64(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int maxn) {
+  const int npairs = (maxn + 1) / 2;
+  const int warps = std::max(1, (npairs + 3) / 4);
+  const size_t smem = (size_t)(C ? 2 : 1) * 64 * 64 * sizeof(double);
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi64<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi64<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  k_jacobi64<C><<<njobs, warps * 32, smem, ctx->stream>>>(dj);
+  ITN_LAUNCH_CHECK(ctx);
+}
+
+int g_jacobi_variant = 0;  // 0 = auto, 1 = generic kernel only (itn_svd_batch's second opinion)
+
 void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
   if (jobs.empty()) return;
   int maxn = 0, maxm = 0;
   size_t need = 0;
+  bool any_v = false;
   for (auto& j : jobs) {
     ITN_REQUIRE(j.n <= 256, ITN_EUNSUPPORTED, "Jacobi SVD supports at most 256 columns");
     maxn = std::max(maxn, j.n);
     maxm = std::max(maxm, j.m);
+    any_v = any_v || j.v != nullptr;
     need = std::max(need, ((size_t)j.m * j.n + (j.v ? (size_t)j.n * j.n : 0)) * (cplx ? 2 : 1));
+  }
+  if (!any_v && maxm <= 64 && maxn <= 64 && maxn >= 2 && g_jacobi_variant == 0) {
+    DevBuf jb(ctx, jobs.size() * sizeof(SvdJob));
+    const SvdJob* dj = itn_upload(ctx, jobs, jb);
+    if (cplx) launch_jacobi64<true>(ctx, dj, (unsigned)jobs.size(), maxn);
+    else launch_jacobi64<false>(ctx, dj, (unsigned)jobs.size(), maxn);
+    return;
   }
   size_t smem = std::min<size_t>(need * sizeof(double), 200 * 1024);
   DevBuf jb(ctx, jobs.size() * sizeof(SvdJob));
@@ -964,6 +1196,64 @@ extern "C" int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, 
   ITN_LAUNCH_CHECK(ctx);
   CUDA_CHECK(cudaMemcpyAsync(host_out, raw.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END
+}
+
+// Batched singular values (and U*Sigma) of host matrices through the same Jacobi kernels the gate path uses:
+// instrumentation for tests/test_gpu_linalg.py and tools/svd_bench.py.
+extern "C" int itn_svd_batch(itn_ctx* ctx, int dtype, int m, int n, int batch, const void* host_in, double* host_sigma,
+                             void* host_us, int variant, double* device_ms) {
+  API_BEGIN
+  ITN_REQUIRE(ctx && host_in && host_sigma, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(dtype == ITN_F64 || dtype == ITN_C128, ITN_EUNSUPPORTED, "dtype must be 0 (Float64) or 1 (ComplexF64)");
+  ITN_REQUIRE(m >= 1 && n >= 1 && n <= 256 && batch >= 0, ITN_EINVAL, "bad batch shape");
+  ITN_REQUIRE(variant == 0 || variant == 1, ITN_EINVAL, "variant must be 0 (auto) or 1 (generic kernel)");
+  if (batch == 0) return ITN_OK;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  const bool cplx = dtype == ITN_C128;
+  const int P = cplx ? 2 : 1;
+  const size_t mn = (size_t)m * n, bytes = (size_t)batch * mn * P * sizeof(double);
+  DevBuf raw(ctx, bytes), in(ctx, bytes), us(ctx, bytes);
+  DevBuf sig(ctx, (size_t)batch * n * sizeof(double)), perm(ctx, (size_t)batch * n * sizeof(int));
+  CUDA_CHECK(cudaMemcpyAsync(raw.p, host_in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned g = (unsigned)std::min<size_t>((batch * mn + 255) / 256, 2048);
+  if (cplx) k_split<true><<<g, 256, 0, ctx->stream>>>(raw.as<double>(), in.as<double>(), (int)mn, batch);
+  else k_split<false><<<g, 256, 0, ctx->stream>>>(raw.as<double>(), in.as<double>(), (int)mn, batch);
+  ITN_LAUNCH_CHECK(ctx);
+  std::vector<SvdJob> jobs(batch);
+  for (int i = 0; i < batch; ++i)
+    jobs[i] = {in.as<double>() + i * mn * P, nullptr, sig.as<double>() + (size_t)i * n, perm.as<int>() + (size_t)i * n, m, n,
+               us.as<double>() + i * mn * P, nullptr};
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  const int saved = g_jacobi_variant;
+  g_jacobi_variant = variant;
+  try {
+    CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+    run_jacobi(ctx, cplx, jobs);
+    CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
+  } catch (...) {
+    g_jacobi_variant = saved;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    throw;
+  }
+  g_jacobi_variant = saved;
+  CUDA_CHECK(cudaMemcpyAsync(host_sigma, sig.p, (size_t)batch * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (host_us) {
+    if (cplx) k_merge<true><<<g, 256, 0, ctx->stream>>>(us.as<double>(), raw.as<double>(), (int)mn, batch);
+    else k_merge<false><<<g, 256, 0, ctx->stream>>>(us.as<double>(), raw.as<double>(), (int)mn, batch);
+    ITN_LAUNCH_CHECK(ctx);
+    CUDA_CHECK(cudaMemcpyAsync(host_us, raw.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  float ms = 0.f;
+  if (se == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CUDA_CHECK(se);
+  if (device_ms) *device_ms = ms;
   API_END
 }
 

@@ -582,3 +582,23 @@ def map_eigvals(f, mats, cutoff=None, ctx=None):
                                 out.ctypes.data_as(C.c_void_p), -1.0 if cutoff is None else float(cutoff)))
     res = np.stack([o.reshape(chi, chi, order="F") for o in out])
     return res[0] if single else res
+
+
+def svd_batch(mats, variant=0, want_us=False, ctx=None):
+    """Singular values of a batch of matrices through the engine's batched Jacobi kernels (the `factorize_svd` step of
+    simple_update_bp, src/apply.jl:81-88).  Returns (sigma[batch, n] descending, U*Sigma or None, device milliseconds);
+    variant 1 forces the shape-generic kernel."""
+    ctx = ctx or default_context()
+    mats = np.asarray(mats)
+    dtype = np.dtype(np.complex128 if mats.dtype.kind == "c" else np.float64)
+    b, m, n = mats.shape
+    inp = np.ascontiguousarray(np.stack([np.asfortranarray(x.astype(dtype)).ravel(order="F") for x in mats]))
+    sig = np.zeros((b, n), dtype=np.float64)
+    us = np.empty_like(inp) if want_us else None
+    ms = C.c_double(0.0)
+    check(lib().itn_svd_batch(ctx.h, _DTYPE_CODE[dtype], m, n, b, inp.ctypes.data_as(C.c_void_p),
+                              sig.ctypes.data_as(C.POINTER(C.c_double)),
+                              us.ctypes.data_as(C.c_void_p) if want_us else None, int(variant), C.byref(ms)))
+    if want_us:
+        us = np.stack([u.reshape(m, n, order="F") for u in us])
+    return sig, us, ms.value
