@@ -83,6 +83,20 @@ int itn_net_tensor_size(const itn_net* net, int v, int64_t* out_elems);
 int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd, const int32_t* axis_edge);
 int itn_net_get_tensor(const itn_net* net, int v, void* host, int nd, const int32_t* axis_edge);
 
+/* Bra layer of a bilinear form <phi|psi>: BilinearFormNetwork(phi, psi) with the identity operator layer
+ * (src/formnetworks/bilinearformnetwork.jl:23-42, inner_network src/inner.jl:139-171), the network behind
+ * inner(phi, psi; alg = "bp") and loginner (src/inner.jl:100-171).  phi_v is passed as given (NOT conjugated: the engine
+ * applies `dag`), with the axis description of itn_net_set_tensor and the same extents as the ket; hosts holding
+ * different bond dimensions zero-pad the smaller tensor.  Vertices without a bra tensor keep bra = conj(ket).
+ * While a bra layer is set, messages are general (not Hermitian) matrices M[a_ket, a_bra] and only itn_bp_update,
+ * itn_updated_message, itn_message_residuals, itn_region_scalars, itn_logscalar, the message accessors and
+ * itn_net_clone are defined; observables, rescale and gates return ITN_EUNSUPPORTED (as in the reference, where
+ * expect / apply / normalize take a QuadraticFormNetwork).  <phi|A|psi> (src/inner.jl:154-171) enters as
+ * <phi|(A psi)> with the operator layer contracted into the ket site by site on the host (fused bond indices).
+ * itn_net_clear_bra returns to the quadratic form <psi|psi>. */
+int itn_net_set_bra_tensor(itn_net* net, int v, const void* host, int nd, const int32_t* axis_edge);
+int itn_net_clear_bra(itn_net* net);
+
 /* The constructor's data path, BeliefPropagationCache(ptn) over the whole network
  * (src/caches/beliefpropagationcache.jl:20-35): n site tensors in one call.  hosts[i] is the column-major
  * tensor of vertex verts[i]; nd / axis_edge (nullable = canonical [site, bonds...]) are the per-tensor axis

@@ -705,6 +705,9 @@ extern "C" int itn_net_create(itn_ctx* ctx, int dtype, int nv, int ne, const int
 static void free_net_storage(itn_net* net) {
   for (auto& t : net->T)
     if (t.p) itn_tensor_free(net->ctx, t);
+  for (auto& t : net->Tb)
+    if (t.p) itn_tensor_free(net->ctx, t);
+  net->nbra = 0;
   for (auto& m : net->M)
     if (m.p) itn_tensor_free(net->ctx, m);
   itn_fast_release(net);
@@ -732,6 +735,7 @@ extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
   net->fast = nullptr;
   net->dist = nullptr;
   for (auto& t : net->T) t.p = nullptr, t.slab = nullptr;
+  for (auto& t : net->Tb) t.p = nullptr, t.slab = nullptr;
   for (auto& m : net->M) m.p = nullptr, m.slab = nullptr;
   // two shared allocations (site tensors, messages) and one batched copy kernel instead of ~20k cudaMallocAsync + memcpy
   const int P = src->planes();
@@ -748,9 +752,19 @@ extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
       ms.push_back(&net->M[d]);
       mn.push_back(src->M[d].n);
     }
+  for (size_t v = 0; v < src->Tb.size(); ++v)
+    if (src->Tb[v].p) {
+      ts.push_back(&net->Tb[v]);
+      tn.push_back(src->Tb[v].n);
+    }
   slab_alloc(net.get(), ts, tn);
   slab_alloc(net.get(), ms, mn);
   long long maxn = 0;
+  for (size_t v = 0; v < src->Tb.size(); ++v)
+    if (src->Tb[v].p) {
+      cj.push_back({src->Tb[v].p, net->Tb[v].p, src->Tb[v].n * P});
+      maxn = std::max<long long>(maxn, src->Tb[v].n * P);
+    }
   for (int v = 0; v < src->nv; ++v)
     if (src->T[v].p) {
       cj.push_back({src->T[v].p, net->T[v].p, src->T[v].n * P});
@@ -860,6 +874,51 @@ extern "C" int itn_net_set_tensor(itn_net* net, int v, const void* host, int nd,
   if (net->cplx) k_import<true><<<g, 256, 0, ctx->stream>>>(stage.as<double>(), net->T[v].p, n, m);
   else k_import<false><<<g, 256, 0, ctx->stream>>>(stage.as<double>(), net->T[v].p, n, m);
   ITN_LAUNCH_CHECK(ctx);
+  API_END
+}
+
+// Bra layer of a bilinear form <phi|psi> (BilinearFormNetwork, src/formnetworks/bilinearformnetwork.jl:23-42; built by
+// inner_network, src/inner.jl:139-171).  The quadratic form keeps bra = conj(ket) implicit; here phi_v is stored as given
+// and conjugated by the closing kernels exactly where they conjugate the ket.  Same extents as the ket (a host that
+// holds different bond dimensions zero-pads the smaller tensor, which changes no contraction).
+extern "C" int itn_net_set_bra_tensor(itn_net* net, int v, const void* host, int nd, const int32_t* axis_edge) {
+  API_BEGIN
+  ITN_REQUIRE(net && host, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "vertex out of range");
+  if (!itn_is_local(net, v)) return ITN_OK;
+  set_device(net->ctx);
+  itn_ctx* ctx = net->ctx;
+  Marshal m = make_marshal(net, v, nd, axis_edge);
+  const long long n = net->tensor_elems(v);
+  const int P = net->planes();
+  if (net->Tb.size() != (size_t)net->nv) net->Tb.resize(net->nv);
+  DevTensor& t = net->Tb[v];
+  if (!t.p || t.n != n) {
+    if (t.p) itn_tensor_free(ctx, t);
+    else net->nbra++;
+    t.p = (double*)itn_dev_alloc(ctx, (size_t)n * P * sizeof(double));
+    t.n = n;
+  }
+  net->touch(v);
+  DevBuf stage(ctx, (size_t)n * P * sizeof(double));
+  CUDA_CHECK(cudaMemcpyAsync(stage.p, host, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  unsigned g = (unsigned)std::min<long long>((n + 255) / 256, 4096);
+  if (net->cplx) k_import<true><<<g, 256, 0, ctx->stream>>>(stage.as<double>(), t.p, n, m);
+  else k_import<false><<<g, 256, 0, ctx->stream>>>(stage.as<double>(), t.p, n, m);
+  ITN_LAUNCH_CHECK(ctx);
+  API_END
+}
+
+extern "C" int itn_net_clear_bra(itn_net* net) {
+  API_BEGIN
+  ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  set_device(net->ctx);
+  for (size_t v = 0; v < net->Tb.size(); ++v)
+    if (net->Tb[v].p) {
+      itn_tensor_free(net->ctx, net->Tb[v]);
+      net->touch((int)v);
+    }
+  net->nbra = 0;
   API_END
 }
 
@@ -1660,6 +1719,7 @@ extern "C" int itn_logscalar(itn_net* net, double out[2]) {
 extern "C" int itn_rescale(itn_net* net) {
   API_BEGIN
   ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  ITN_REQUIRE(!net->has_bra(), ITN_EUNSUPPORTED, "not defined for a bilinear form network (a bra layer is set): only BP updates, region scalars and logscalar are");
   set_device(net->ctx);
   itn_flush_pending(net);
   itn_ctx* ctx = net->ctx;
@@ -1722,6 +1782,7 @@ static void upload_planar(itn_net* net, const void* host, long long n_each, int 
 extern "C" int itn_expect1(itn_net* net, const int32_t* verts, int n, const void* ops, void* out) {
   API_BEGIN
   ITN_REQUIRE(net && verts && ops && out && n >= 0, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(!net->has_bra(), ITN_EUNSUPPORTED, "not defined for a bilinear form network (a bra layer is set): only BP updates, region scalars and logscalar are");
   if (n == 0) return ITN_OK;
   set_device(net->ctx);
   itn_flush_pending(net);
@@ -1773,6 +1834,7 @@ extern "C" int itn_expect1(itn_net* net, const int32_t* verts, int n, const void
 extern "C" int itn_rdm2(itn_net* net, const int32_t* eids, int n, void* out) {
   API_BEGIN
   ITN_REQUIRE(net && eids && out && n >= 0, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(!net->has_bra(), ITN_EUNSUPPORTED, "not defined for a bilinear form network (a bra layer is set): only BP updates, region scalars and logscalar are");
   if (n == 0) return ITN_OK;
   set_device(net->ctx);
   itn_flush_pending(net);
@@ -1898,6 +1960,7 @@ extern "C" int itn_rdm2(itn_net* net, const int32_t* eids, int n, void* out) {
 extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void* gates, int normalize) {
   API_BEGIN
   ITN_REQUIRE(net && verts && gates && n >= 0, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(!net->has_bra(), ITN_EUNSUPPORTED, "not defined for a bilinear form network (a bra layer is set): only BP updates, region scalars and logscalar are");
   if (n == 0) return ITN_OK;
   set_device(net->ctx);
   itn_flush_pending(net);

@@ -674,7 +674,7 @@ void relayout_launch(itn_net* net, FastCache* fc, int lo, int hi) {
 
 // (Re)builds the tile-major copies of every eligible vertex when the network changed.
 FastCache* ensure_cache(itn_net* net) {
-  if (net->ctx->path_mode != 0) return nullptr;
+  if (net->ctx->path_mode != 0 || net->has_bra()) return nullptr;  // the tile kernels close with conj(ket)
   {
     FastCache* cur = (FastCache*)net->fast;
     if (cur && cur->nb > 0 && cur->topo_version == net->topo_version) return cur;

@@ -25,12 +25,13 @@ namespace {
 constexpr int kThreads = 256;
 
 template <bool C>
-__global__ void __launch_bounds__(kThreads) k_permute(const VJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(kThreads) k_permute(const VJob* __restrict__ jobs, int bra) {
   const VJob& J = jobs[blockIdx.x];
   if (J.identity_perm) return;
+  if (bra && !J.b) return;
   const long long n = J.n;
-  const double* __restrict__ a = J.a;
-  double* __restrict__ ap = J.ap;
+  const double* __restrict__ a = bra ? J.b : J.a;
+  double* __restrict__ ap = bra ? J.bp : J.ap;
   for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.y * blockDim.x) {
     long long r = i, off = 0;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kThreads) k_gram(const VJob* __restrict__ jobs
   const int No = J.No;
   const long long n = J.n;
   const double* __restrict__ B = (J.nsteps == 0) ? J.ap : J.w[(J.nsteps - 1) & 1];
-  const double* __restrict__ A = J.ap;
+  const double* __restrict__ A = J.b ? J.bp : J.ap;  // bilinear form: close with the bra layer
   double* __restrict__ out = J.out;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t1 = (No + 3) >> 2, T = t1 * t1;
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kThreads) k_gram_mma(const VJob* __restrict__ 
   const int No = J.No;
   const long long n = J.n;
   const double* __restrict__ B = (J.nsteps == 0) ? J.ap : J.w[(J.nsteps - 1) & 1];
-  const double* __restrict__ A = J.ap;
+  const double* __restrict__ A = J.b ? J.bp : J.ap;  // bilinear form: close with the bra layer
   double* __restrict__ out = J.out;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int No16 = (No + 15) & ~15;
@@ -675,6 +676,7 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
     VJob J;
     memset(&J, 0, sizeof(J));
     J.a = net->T[v].p;
+    J.b = (net->has_bra() && net->Tb[v].p) ? net->Tb[v].p : nullptr;
     J.n = net->T[v].n;
     J.nm = z + 1;
     J.dims[0] = net->sdim[v];
@@ -736,7 +738,7 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
     int maxsteps = 0, maxkn = 0;
     while (hi < N) {
       const VJob& J = jobs[hi];
-      size_t need = (size_t)J.n * P * sizeof(double) * ((J.identity_perm ? 0 : 1) + (J.nsteps >= 2 ? 2 : J.nsteps));
+      size_t need = (size_t)J.n * P * sizeof(double) * ((J.identity_perm ? 0 : (J.b ? 2 : 1)) + (J.nsteps >= 2 ? 2 : J.nsteps));
       if (hi > lo && bytes + need > ctx->ws_budget) break;
       bytes += need;
       ++hi;
@@ -749,9 +751,14 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
       size_t tb = (size_t)J.n * P * sizeof(double);
       if (J.identity_perm) {
         J.ap = const_cast<double*>(J.a);
+        J.bp = const_cast<double*>(J.b);
       } else {
         J.ap = (double*)(base + off);
         off += tb;
+        if (J.b) {
+          J.bp = (double*)(base + off);
+          off += tb;
+        }
       }
       for (int i = 0; i < std::min(J.nsteps, 2); ++i) {
         J.w[i] = (double*)(base + off);
@@ -769,11 +776,19 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
     // keep the total grid reasonable for huge batches
     while (gy > 1 && (unsigned long long)gy * nb > 148ull * 64ull) gy = (gy + 1) / 2;
     dim3 grid(nb, gy);
-    bool any_perm = false;
-    for (const VJob& J : batch) any_perm |= !J.identity_perm;
+    bool any_perm = false, any_bra_perm = false;
+    for (const VJob& J : batch) {
+      any_perm |= !J.identity_perm;
+      any_bra_perm |= !J.identity_perm && J.b;
+    }
     if (any_perm) {
-      if (net->cplx) k_permute<true><<<grid, kThreads, 0, ctx->stream>>>(dj);
-      else k_permute<false><<<grid, kThreads, 0, ctx->stream>>>(dj);
+      if (net->cplx) k_permute<true><<<grid, kThreads, 0, ctx->stream>>>(dj, 0);
+      else k_permute<false><<<grid, kThreads, 0, ctx->stream>>>(dj, 0);
+      ITN_LAUNCH_CHECK(ctx);
+    }
+    if (any_bra_perm) {
+      if (net->cplx) k_permute<true><<<grid, kThreads, 0, ctx->stream>>>(dj, 1);
+      else k_permute<false><<<grid, kThreads, 0, ctx->stream>>>(dj, 1);
       ITN_LAUNCH_CHECK(ctx);
     }
     int maxK = 0, maxNo = 0;
@@ -977,7 +992,7 @@ void itn_run_vertex_sweeps(itn_net* net, const std::vector<SweepSpec>& specs) {
       std::function<void(const double*, int, int)> solve = [&](const double* Tn, int s_lo, int s_hi) {
         if (s_hi - s_lo == 1) {
           const int k = s_lo;
-          put_gr({Tn, net->T[v].p, sp.out[k], Ls[k], Rs[k], chis[k]});
+          put_gr({Tn, net->bra(v), sp.out[k], Ls[k], Rs[k], chis[k]});
           return;
         }
         const int mid = (s_lo + s_hi) / 2;

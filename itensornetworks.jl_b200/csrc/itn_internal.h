@@ -82,6 +82,8 @@ struct VJob {
   const double* a;   // source tensor, planar, canonical order [site, bonds...]
   double* ap;        // permuted copy: closed modes first, open modes last (== a if identity)
   double* w[2];      // ping-pong scratch (planar, n each)
+  const double* b;   // bra tensor when the network is a bilinear form <phi|psi> (null: bra = ket)
+  double* bp;        // permuted copy of b (== b if identity), the A' of the close below when b is set
   double* out;       // staged result, planar No x No:  out[o + No*o'] = sum_x B[x,o] conj(A'[x,o'])
   long long n;       // elements of the tensor
   long long X;       // product of closed extents
@@ -124,6 +126,12 @@ struct itn_net {
   std::vector<std::vector<int>> inc;  // incident edge ids, ascending
   std::unordered_map<uint64_t, int> dmap;  // (src,dst) -> directed id (2e: esrc->edst, 2e+1: reverse)
   std::vector<DevTensor> T;  // per vertex
+  // bra layer of a BilinearFormNetwork <phi|psi> (src/formnetworks/bilinearformnetwork.jl:23-42): phi_v as given
+  // (conjugated on use); empty / null entries mean bra = ket (QuadraticFormNetwork)
+  std::vector<DevTensor> Tb;
+  int nbra = 0;
+  bool has_bra() const { return nbra > 0; }
+  const double* bra(int v) const { return (nbra > 0 && Tb[v].p) ? Tb[v].p : T[v].p; }
   std::vector<DevTensor> M;  // per directed edge
   uint64_t topo_version = 0;  // bumped whenever a tensor pointer / bond dim changes
   std::vector<uint64_t> tver;  // per vertex: bumped whenever the contents (or storage) of its site tensor change

@@ -23,7 +23,10 @@
 //
 // map_eigvals (apply.jl:21-25) runs on the same Jacobi kernel.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -57,6 +60,7 @@ struct SvdJob {
 };
 
 constexpr int kSvdMaxThreads = 1024;
+constexpr size_t kGlueSmemMax = 200 * 1024;  // dynamic shared memory the staged glue kernels may ask for
 constexpr int kSvdMaxSweeps = 30;
 
 template <int LP>
@@ -1029,6 +1033,164 @@ __global__ void __launch_bounds__(256) k_su_T(const SuEdge* __restrict__ edges) 
   }
 }
 
+// ---- shared-memory versions of the three glue kernels (one CTA per gate / gate side; operands staged once) ----------
+// The plain kernels above read every operand element from global memory once per output element; at 2048 gates per
+// layer they cost ~1 ms each although they move < 0.3 GB.  Selected when the operands of every gate of the batch fit.
+
+// theta': thread per (a, b) computes t[s1][s2] = sum_l R1[a,(s1,l)] R2[b,(s2,l)] once, then all d1 d2 gate outputs.
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_theta_s(const SuEdge* __restrict__ edges) {
+  extern __shared__ double sm[];
+  const SuEdge E = edges[blockIdx.x];
+  const int d1 = E.d[0], d2 = E.d[1], r1 = E.r[0], r2 = E.r[1], chi = E.chi;
+  const int m = r1 * d1, nc = r2 * d2;
+  const long long mn = (long long)m * nc;
+  const int p1 = r1 * E.n[0], p2 = r2 * E.n[1];
+  const int gsz = d1 * d2 * d1 * d2;
+  constexpr int P = C ? 2 : 1;
+  double* R1 = sm;              // [P][p1]
+  double* R2 = R1 + P * p1;     // [P][p2]
+  double* G = R2 + P * p2;      // [P][gsz]
+  for (int i = threadIdx.x; i < P * p1; i += blockDim.x) R1[i] = E.R[0][i];
+  for (int i = threadIdx.x; i < P * p2; i += blockDim.x) R2[i] = E.R[1][i];
+  for (int i = threadIdx.x; i < P * gsz; i += blockDim.x) G[i] = E.gate[i];
+  __syncthreads();
+  for (int ab = threadIdx.x; ab < r1 * r2; ab += blockDim.x) {
+    const int a = ab % r1, b = ab / r1;
+    double tr[16], ti[16];
+    for (int s2 = 0; s2 < d2; ++s2)
+      for (int s1 = 0; s1 < d1; ++s1) {
+        double xr_ = 0.0, xi_ = 0.0;
+        for (int l = 0; l < chi; ++l) {
+          const int i1 = a + r1 * (s1 + d1 * l), i2 = b + r2 * (s2 + d2 * l);
+          const double xr = R1[i1], yr = R2[i2];
+          if (C) {
+            const double xi = R1[p1 + i1], yi = R2[p2 + i2];
+            xr_ += xr * yr - xi * yi;
+            xi_ += xr * yi + xi * yr;
+          } else {
+            xr_ += xr * yr;
+          }
+        }
+        tr[s1 + d1 * s2] = xr_;
+        ti[s1 + d1 * s2] = xi_;
+      }
+    for (int s2p = 0; s2p < d2; ++s2p)
+      for (int s1p = 0; s1p < d1; ++s1p) {
+        double accr = 0.0, acci = 0.0;
+        for (int s2 = 0; s2 < d2; ++s2)
+          for (int s1 = 0; s1 < d1; ++s1) {
+            const int gi = s1p + d1 * (s2p + d2 * (s1 + d1 * s2));
+            const double gr = G[gi], gim = C ? G[gsz + gi] : 0.0;
+            const double xr = tr[s1 + d1 * s2], xi = ti[s1 + d1 * s2];
+            accr += gr * xr - gim * xi;
+            acci += gr * xi + gim * xr;
+          }
+        const long long idx = (a + (long long)r1 * s1p) + (long long)m * (b + (long long)r2 * s2p);
+        E.theta0[idx] = accr;
+        if (C) E.theta0[mn + idx] = acci;
+      }
+  }
+}
+
+// V[:, col] = theta'^H (U S)[:, col] / sigma^2 for the kept columns; theta' staged with a padded column stride
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_vrec_s(const SuEdge* __restrict__ edges) {
+  extern __shared__ double sm[];
+  const SuEdge E = edges[blockIdx.x];
+  const int m = E.r[0] * E.d[0], nc = E.r[1] * E.d[1], nd = E.newdim;
+  const long long mn = (long long)m * nc, nn = (long long)nc * nc;
+  constexpr int P = C ? 2 : 1;
+  const int ms = m + 1;            // padded stride: lanes walk j, rows of one column stay contiguous
+  double* Th = sm;                 // [P][nc][ms]
+  double* Us = Th + P * nc * ms;   // [P][nd][m]   kept columns of U S, in sorted order
+  for (int idx = threadIdx.x; idx < m * nc; idx += blockDim.x) {
+    const int i = idx % m, j = idx / m;
+    Th[j * ms + i] = E.theta0[idx];
+    if (C) Th[nc * ms + j * ms + i] = E.theta0[mn + idx];
+  }
+  for (int idx = threadIdx.x; idx < m * nd; idx += blockDim.x) {
+    const int i = idx % m, lp = idx / m;
+    const long long src = i + (long long)m * E.tperm[lp];
+    Us[idx] = E.theta[src];
+    if (C) Us[nd * m + idx] = E.theta[mn + src];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nc * nd; idx += blockDim.x) {
+    const int j = idx % nc, lp = idx / nc;
+    const int col = E.tperm[lp];
+    const double sig = E.tsig[lp];
+    const double f = sig > 0.0 ? 1.0 / (sig * sig) : 0.0;
+    const double* tr = Th + j * ms;
+    const double* ti = Th + nc * ms + j * ms;
+    const double* ur = Us + lp * m;
+    const double* ui = Us + nd * m + lp * m;
+    double accr = 0.0, acci = 0.0;
+    for (int i = 0; i < m; ++i) {
+      if (C) {
+        accr += tr[i] * ur[i] + ti[i] * ui[i];  // conj(a) * u
+        acci += tr[i] * ui[i] - ti[i] * ur[i];
+      } else {
+        accr += tr[i] * ur[i];
+      }
+    }
+    E.tv[j + (long long)nc * col] = f * accr;
+    if (C) E.tv[nn + j + (long long)nc * col] = f * acci;
+  }
+}
+
+// T_side = R^+ R' with R^+ and the kept, scaled columns of R' staged
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_T_s(const SuEdge* __restrict__ edges) {
+  extern __shared__ double sm[];
+  const SuEdge E = edges[blockIdx.x >> 1];
+  const int side = blockIdx.x & 1;
+  const int n = E.n[side], r = E.r[side], d = E.d[side], nd = E.newdim;
+  const int m = E.r[0] * E.d[0], nc = E.r[1] * E.d[1];
+  const long long mn = (long long)m * nc, nn = (long long)nc * nc;
+  const int rn = r * n, q = d * nd, rq = r * q;
+  constexpr int P = C ? 2 : 1;
+  double* Rp = sm;            // [P][n x r]
+  double* Rn = Rp + P * rn;   // [P][r x (d nd)]:  R'[a, sp, lp]
+  for (int i = threadIdx.x; i < P * rn; i += blockDim.x) Rp[i] = E.Rp[side][i];
+  for (int idx = threadIdx.x; idx < rq; idx += blockDim.x) {
+    const int a = idx % r, sq = idx / r, sp = sq % d, lp = sq / d;
+    const int col = E.tperm[lp];
+    const double sig = E.tsig[lp];
+    const double f = side == 0 ? (sig > 0.0 ? 1.0 / sqrt(sig) : 0.0) : sqrt(sig);
+    double xr, xi;
+    if (side == 0) {
+      const long long i = (a + (long long)r * sp) + (long long)m * col;
+      xr = E.theta[i];
+      xi = C ? E.theta[mn + i] : 0.0;
+    } else {
+      const long long i = (a + (long long)r * sp) + (long long)nc * col;
+      xr = E.tv[i];
+      xi = C ? -E.tv[nn + i] : 0.0;
+    }
+    Rn[idx] = f * xr;
+    if (C) Rn[rq + idx] = f * xi;
+  }
+  __syncthreads();
+  const long long tot = (long long)n * q;
+  for (int idx = threadIdx.x; idx < n * q; idx += blockDim.x) {
+    const int o = idx % n, sq = idx / n;
+    double accr = 0.0, acci = 0.0;
+    for (int a = 0; a < r; ++a) {
+      const double pr = Rp[o + n * a], xr = Rn[a + r * sq];
+      if (C) {
+        const double pi = Rp[rn + o + n * a], xi = Rn[rq + a + r * sq];
+        accr += pr * xr - pi * xi;
+        acci += pr * xi + pi * xr;
+      } else {
+        accr += pr * xr;
+      }
+    }
+    E.T[side][idx] = accr;
+    if (C) E.T[side][tot + idx] = acci;
+  }
+}
+
 struct SuSite {
   const double* a;   // old tensor, canonical planar [s, bonds...]
   double* out;       // new tensor
@@ -1148,6 +1310,25 @@ void itn_dev_map_eigvals(itn_ctx* ctx, bool cplx, int fn, int chi, int n, const 
   else k_eig_fn<false><<<n, 256, 0, ctx->stream>>>(de, fn, cutoff);
   ITN_LAUNCH_CHECK(ctx);
 }
+
+// ITN_TRACE=1: host-side phase times of itn_apply2 on stderr (where the host keeps the GPU waiting)
+struct HostTrace {
+  bool on;
+  std::chrono::steady_clock::time_point last;
+  std::string line;
+  HostTrace() : on(getenv("ITN_TRACE") != nullptr), last(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof buf, " %s %.2f", what, std::chrono::duration<double, std::milli>(now - last).count());
+    line += buf;
+    last = now;
+  }
+  ~HostTrace() {
+    if (on) fprintf(stderr, "[itn trace] apply2 host ms:%s\n", line.c_str());
+  }
+};
 
 #define API_BEGIN try {
 #define API_END                              \
@@ -1274,6 +1455,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   API_BEGIN
   ITN_REQUIRE(net && eids && gates && n >= 0, ITN_EINVAL, "NULL argument");
   ITN_REQUIRE(msg_mode == 0 || msg_mode == 1, ITN_EINVAL, "msg_mode must be 0 (identity) or 1 (singular values)");
+  ITN_REQUIRE(!net->has_bra(), ITN_EUNSUPPORTED, "gates are not defined for a bilinear form network (a bra layer is set)");
   if (n == 0) return ITN_OK;
   CUDA_CHECK(cudaSetDevice(net->ctx->device));
   itn_flush_pending(net);
@@ -1297,6 +1479,8 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
                       "environment message into vertex " + std::to_string(v) + " is not set (update the BP cache first)");
     }
   }
+  HostTrace trace;
+  trace.mark("validate");
   // ---- geometry of every gate (global metadata), role of this rank ----
   enum { NONE = 0, OWNER = 1, GUEST = 2 };
   struct Geo {
@@ -1571,6 +1755,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     }
     tr[g.oi] = {E->tsig, g.cand, res.as<double>() + (size_t)i * RS};
   }
+  trace.mark("plan");
   // ---- 1. hermitise environments, bond environments C_side of the local sides ----
   if (!hj.empty()) {
     DevBuf hb(ctx, hj.size() * sizeof(HermJob));
@@ -1588,6 +1773,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
                     recvC.as<double>() + kv.second.recvC_off, kv.second.recvC});
     itn_dist_p2p(ctx, xs);
   }
+  trace.mark("launch_env");
   // ---- 2. R factors (Cholesky; eigen route where r < n or C is rank deficient), environment support ----
   run_chol(ctx, cplx, chol_r);
   run_jacobi(ctx, cplx, gj);
@@ -1604,15 +1790,37 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     else k_eig_fn<false><<<(unsigned)ej_fn.size(), 256, 0, ctx->stream>>>(de, 3, eig_cutoff);
     ITN_LAUNCH_CHECK(ctx);
   }
+  trace.mark("launch_R");
   // ---- 3. theta', SVD, truncation (owned gates) ----
+  // staged-operand version of k_su_theta when R1, R2 and the gate of every owned edge fit (0: plain kernel)
+  size_t theta_smem = 0;
+  for (const Geo& g : geo) {
+    if (g.role != OWNER) continue;
+    const size_t need = (size_t)P * ((size_t)g.r[0] * g.nn[0] + (size_t)g.r[1] * g.nn[1] + (size_t)g.d[0] * g.d[1] * g.d[0] * g.d[1]) * sizeof(double);
+    if (g.d[0] * g.d[1] > 16 || need > kGlueSmemMax) {
+      theta_smem = 0;
+      break;
+    }
+    theta_smem = std::max(theta_smem, need);
+  }
   DevBuf seb(ctx, std::max<size_t>(se.size(), 1) * sizeof(SuEdge));
   const SuEdge* dse = n_own ? itn_upload(ctx, se, seb) : nullptr;
   if (n_own) {
     if (cplx) k_su_build_R<true><<<2 * n_own, 256, 0, ctx->stream>>>(dse);
     else k_su_build_R<false><<<2 * n_own, 256, 0, ctx->stream>>>(dse);
     ITN_LAUNCH_CHECK(ctx);
-    if (cplx) k_su_theta<true><<<dim3(n_own, 8), 256, 0, ctx->stream>>>(dse);
-    else k_su_theta<false><<<dim3(n_own, 8), 256, 0, ctx->stream>>>(dse);
+    if (theta_smem) {
+      if (cplx) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_su_theta_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)theta_smem));
+        k_su_theta_s<true><<<n_own, 256, theta_smem, ctx->stream>>>(dse);
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_su_theta_s<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)theta_smem));
+        k_su_theta_s<false><<<n_own, 256, theta_smem, ctx->stream>>>(dse);
+      }
+    } else {
+      if (cplx) k_su_theta<true><<<dim3(n_own, 8), 256, 0, ctx->stream>>>(dse);
+      else k_su_theta<false><<<dim3(n_own, 8), 256, 0, ctx->stream>>>(dse);
+    }
     ITN_LAUNCH_CHECK(ctx);
     run_jacobi(ctx, cplx, tj);
     DevBuf trb(ctx, tr.size() * sizeof(SuTrunc));
@@ -1620,12 +1828,14 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     k_su_truncate<<<(n_own + 31) / 32, 32, 0, ctx->stream>>>(dtr, n_own, maxdim, cutoff, stride);
     ITN_LAUNCH_CHECK(ctx);
   }
+  trace.mark("launch_svd");
   itn_dist_allreduce_sum(ctx, res.as<double>(), n * RS);  // every rank learns the outcome of every gate
   std::vector<double> hres((size_t)n * RS);
   CUDA_CHECK(cudaMemcpyAsync(hres.data(), res.p, hres.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<int> eflag(std::max<size_t>(env_count, 1), 0);
   CUDA_CHECK(cudaMemcpyAsync(eflag.data(), env_flag.p, eflag.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  trace.mark("sync_wait");
   std::vector<int> newdim(n);
   for (int i = 0; i < n; ++i) newdim[i] = (int)(hres[(size_t)i * RS] + 0.5);
   // sites with a rank-deficient environment: A <- A x_j P_j before the rebuild
@@ -1662,16 +1872,46 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     sp.nsteps++;
   }
   itn_run_modeprods(ctx, cplx, pspecs, presult);
+  trace.mark("projectors");
   // ---- 4. T factors (owner), shipped to the guests; new site tensors of the local sides ----
   if (n_own) {
     for (int i = 0; i < n; ++i)
       if (geo[i].role == OWNER) se[geo[i].oi].newdim = newdim[i];
     CUDA_CHECK(cudaMemcpyAsync((void*)dse, se.data(), se.size() * sizeof(SuEdge), cudaMemcpyHostToDevice, ctx->stream));
-    if (cplx) k_su_vrec<true><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
-    else k_su_vrec<false><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+    // staged operand sizes with the bond dimensions kept by this layer
+    size_t vrec_smem = 0, T_smem = 0;
+    for (int i = 0; i < n; ++i) {
+      const Geo& g = geo[i];
+      if (g.role != OWNER) continue;
+      vrec_smem = std::max(vrec_smem, (size_t)P * ((size_t)(g.m + 1) * g.nc + (size_t)g.m * newdim[i]) * sizeof(double));
+      for (int s = 0; s < 2; ++s)
+        T_smem = std::max(T_smem, (size_t)P * ((size_t)g.r[s] * g.nn[s] + (size_t)g.r[s] * g.d[s] * newdim[i]) * sizeof(double));
+    }
+    if (vrec_smem <= kGlueSmemMax) {
+      if (cplx) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_su_vrec_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vrec_smem));
+        k_su_vrec_s<true><<<n_own, 256, vrec_smem, ctx->stream>>>(dse);
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_su_vrec_s<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vrec_smem));
+        k_su_vrec_s<false><<<n_own, 256, vrec_smem, ctx->stream>>>(dse);
+      }
+    } else {
+      if (cplx) k_su_vrec<true><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+      else k_su_vrec<false><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+    }
     ITN_LAUNCH_CHECK(ctx);
-    if (cplx) k_su_T<true><<<dim3(2 * n_own, 4), 256, 0, ctx->stream>>>(dse);
-    else k_su_T<false><<<dim3(2 * n_own, 4), 256, 0, ctx->stream>>>(dse);
+    if (T_smem <= kGlueSmemMax) {
+      if (cplx) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_su_T_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_smem));
+        k_su_T_s<true><<<2 * n_own, 256, T_smem, ctx->stream>>>(dse);
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_su_T_s<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_smem));
+        k_su_T_s<false><<<2 * n_own, 256, T_smem, ctx->stream>>>(dse);
+      }
+    } else {
+      if (cplx) k_su_T<true><<<dim3(2 * n_own, 4), 256, 0, ctx->stream>>>(dse);
+      else k_su_T<false><<<dim3(2 * n_own, 4), 256, 0, ctx->stream>>>(dse);
+    }
     ITN_LAUNCH_CHECK(ctx);
   }
   if (multi) {
@@ -1760,6 +2000,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     }
   }
   for (double* p : pscratch) itn_dev_free(ctx, p);  // stream ordered: freed after the rebuild kernel
+  trace.mark("launch_rebuild");
   // ---- 5. commit: swap tensors, new bond dimensions, reset the messages on the gated edges ----
   std::vector<DiagMsgJob> dj;
   size_t moff = 0;
@@ -1803,6 +2044,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     if (svals_out)
       for (int t = 0; t < svals_stride; ++t) svals_out[(size_t)i * svals_stride + t] = t < stride ? hres[(size_t)i * RS + 2 + t] : 0.0;
   }
+  trace.mark("commit");
   // no synchronisation here: everything destined for host pointers was complete at the read-back above; the rebuild of
   // the site tensors finishes in stream order while the host prepares the next call
   API_END

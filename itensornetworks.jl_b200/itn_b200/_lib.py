@@ -39,6 +39,8 @@ _SIGS = {
     "itn_net_edge_dim": (C.c_int, [_vp, C.c_int, _i32p]),
     "itn_net_tensor_size": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "itn_net_set_tensor": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i32p]),
+    "itn_net_set_bra_tensor": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i32p]),
+    "itn_net_clear_bra": (C.c_int, [_vp]),
     "itn_net_set_tensors": (C.c_int, [_vp, C.c_int, _i32p, C.POINTER(_vp), _i32p, _i32p, C.c_int]),
     "itn_net_get_tensor": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i32p]),
     "itn_msg_set_identity": (C.c_int, [_vp]),

@@ -77,13 +77,14 @@ class BeliefPropagationCache:
     """BP cache of <psi|psi> with the default one-site partition; state lives on the device."""
 
     def __init__(self, psi: ITensorNetwork = None, ctx: Context = None, messages="identity", owner=None, dist=None,
-                 defer_upload=False, _handle=None, _like=None):
+                 defer_upload=False, bra: ITensorNetwork = None, _handle=None, _like=None):
         if _handle is not None:  # clone
             self.ctx, self.graph, self.dtype, self.h = _like.ctx, _like.graph, _like.dtype, _handle
             self.eltype = _like.eltype
             self._host_refs = None
             self.sdims = list(_like.sdims)
             self.owner, self.rank = _like.owner, _like.rank
+            self.bilinear = getattr(_like, "bilinear", False)
             return
         self.ctx = ctx or default_context()
         self.graph = psi.graph
@@ -107,6 +108,11 @@ class BeliefPropagationCache:
         # overlap the copy with its sweep (ITN_HOST_DEFERRED, include/itn_b200.h).
         mine = [v for v in range(g.nv) if self.owner is None or self.owner[v] == self.rank]
         self.set_factors(mine, [psi.tensors[v] for v in mine], defer=defer_upload)
+        # BilinearFormNetwork <bra|psi> (src/formnetworks/bilinearformnetwork.jl:23-42): explicit bra layer, same shapes
+        self.bilinear = bra is not None
+        if bra is not None:
+            for v in mine:
+                self.set_bra_factor(v, bra.tensors[v])
         # initialize_cache (src/initialize_cache.jl:14-29): identity messages on loopy graphs, none on trees
         if messages == "identity" or (messages == "default" and not g.is_tree()):
             check(lib().itn_msg_set_identity(self.h))
@@ -151,6 +157,13 @@ class BeliefPropagationCache:
             raise ITNError(2, f"tensor of vertex {v} has shape {t.shape}, expected {self._shape(v)}")
         f = np.asfortranarray(t)  # column-major bytes with axes [site, bonds...]
         check(lib().itn_net_set_tensor(self.h, int(v), f.ctypes.data_as(C.c_void_p), f.ndim, None))
+
+    def set_bra_factor(self, v, t):
+        """bra tensor phi_v of a bilinear form (passed un-conjugated; the engine applies `dag`)."""
+        t = np.asfortranarray(np.asarray(t, dtype=self.dtype))
+        assert t.shape == self._shape(v), f"bra tensor {v} has shape {t.shape}, expected {self._shape(v)}"
+        check(lib().itn_net_set_bra_tensor(self.h, v, t.ctypes.data_as(C.c_void_p), t.ndim, None))
+        self.bilinear = True
 
     def set_factors(self, verts, tensors, defer=False):
         """itn_net_set_tensors: many site tensors in one pipelined upload (axes [site, bonds...])."""
@@ -360,6 +373,62 @@ def normalize(psi, alg="bp", cache=None, update_cache=None, cache_update_kwargs=
     cache = _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx)
     check(lib().itn_rescale(cache.h))
     return cache.tensornetwork()
+
+
+def _pad_to(t, shape, dtype):
+    out = np.zeros(shape, dtype=dtype)
+    out[tuple(slice(0, n) for n in t.shape)] = t
+    return out
+
+
+def inner_network(phi: ITensorNetwork, psi: ITensorNetwork, operator: ITensorNetwork = None):
+    """inner_network(phi, psi) / inner_network(phi, A, psi) (src/inner.jl:139-171): returns (ket, bra) host networks of
+    equal shapes for BeliefPropagationCache(ket, bra=bra).  The operator layer (a list of arrays A_v[s', s, b_1..b_z] with
+    the bond order of the state) is contracted into
+    the ket site by site (fused bonds a_k + chi_k b_k); differing bond dimensions are zero-padded.  This is host-side
+    layout work (one small tensordot per site), the contractions of BP itself all run on the device."""
+    g = psi.graph
+    ops = None if operator is None else [np.asarray(a) for a in getattr(operator, "tensors", operator)]
+    dtype = np.result_type(phi.dtype, psi.dtype, *([a.dtype for a in ops] if ops else []))
+    kets = []
+    for v in range(g.nv):
+        t = psi.tensors[v]
+        if ops is not None:
+            a = ops[v]
+            z = t.ndim - 1
+            r = np.tensordot(a, t, axes=([1], [0]))  # [s', b_1..b_z, a_1..a_z]
+            r = np.transpose(r, [0] + [i for k in range(z) for i in (1 + k, 1 + z + k)])  # [s', b_1, a_1, b_2, a_2, ..]
+            t = r.reshape([r.shape[0]] + [r.shape[1 + 2 * k] * r.shape[2 + 2 * k] for k in range(z)])  # C order: a fastest
+        kets.append(t)
+    ks, bs = [], []
+    for v in range(g.nv):
+        shape = tuple(max(x, y) for x, y in zip(kets[v].shape, phi.tensors[v].shape))
+        ks.append(_pad_to(kets[v], shape, dtype))
+        bs.append(_pad_to(phi.tensors[v], shape, dtype))
+    return ITensorNetwork(g, ks, dtype), ITensorNetwork(g, bs, dtype)
+
+
+def loginner(phi, psi, operator=None, alg="bp", cache=None, update_cache=None, cache_update_kwargs=None, ctx=None,
+             messages="default_bilinear"):
+    """loginner(phi, psi; alg = "bp") / loginner(phi, A, psi; alg = "bp") (src/inner.jl:100-137) = logscalar of the BP
+    cache of the bilinear form network (src/contract.jl:41-58).  As in the reference the cache of a bilinear form has no
+    default messages (initialize_cache fallback, src/initialize_cache.jl:10-12): on trees the forest-cover sequence
+    creates them; on loopy graphs pass `messages="identity"` or a dict, and `maxiter` in cache_update_kwargs."""
+    assert alg == "bp", "only alg=\"bp\" runs on the engine"
+    if cache is None:
+        ket, bra = inner_network(phi, psi, operator)
+        cache = BeliefPropagationCache(ket, ctx=ctx, bra=bra, messages=None if messages == "default_bilinear" else messages)
+        update_cache = True if update_cache is None else update_cache
+    elif update_cache is None:
+        update_cache = False
+    if update_cache:
+        cache = update(cache, inplace=True, **(cache_update_kwargs or {}))
+    return logscalar(cache)
+
+
+def inner(phi, psi, operator=None, **kwargs):
+    """inner(phi, psi; alg = "bp") / inner(phi, A, psi; alg = "bp") (src/inner.jl:139-171): exp(loginner)."""
+    return np.exp(loginner(phi, psi, operator, **kwargs))
 
 
 def norm_sqr(psi, cache=None, update_cache=None, cache_update_kwargs=None, ctx=None):

@@ -20,6 +20,7 @@ This is a dense NumPy restatement (float64 / complex128) of
   src/formnetworks/quadraticformnetwork.jl:96-124, src/initialize_cache.jl:14-29
   src/edge_sequences.jl:32-51
   src/expect.jl:5-19, src/normalize.jl:13-34,63-80, src/apply.jl:9-146
+  src/inner.jl:100-171, src/formnetworks/bilinearformnetwork.jl:23-94 (bilinear forms <phi|psi>, <phi|A|psi>)
   test/utils.jl:23-38 (input generator)
 with the index conventions of SURVEY.md Appendix A:
   site tensor  A_v[s, a_1..a_z]   (s = physical index, a_k = bond to the k-th incident edge)
@@ -260,9 +261,18 @@ class Network:
     graph: Graph
     tensors: list  # tensors[v].shape == (d_v, chi_{inc[v][0]}, chi_{inc[v][1]}, ...)
     dtype: type = np.complex128
+    # bra layer of a BilinearFormNetwork <phi|psi> (formnetworks/bilinearformnetwork.jl:23-42): bra[v] = phi_v as given
+    # (conjugated on use, `dag`); None = QuadraticFormNetwork, bra = ket
+    bra: list | None = None
 
     def copy(self):
-        return Network(self.graph, [t.copy() for t in self.tensors], self.dtype)
+        return Network(self.graph, [t.copy() for t in self.tensors], self.dtype,
+                       None if self.bra is None else [None if t is None else t.copy() for t in self.bra])
+
+    def bra_tensor(self, v):
+        if self.bra is None or self.bra[v] is None:
+            return self.tensors[v]
+        return self.bra[v]
 
     def edge_dim(self, e):
         u, _ = self.graph.edges[e]
@@ -321,7 +331,7 @@ def updated_message(net, msgs, v, w, normalize=True):
     g = net.graph
     e = g.eid[(v, w)]
     k = g.slot(v, e)
-    a = net.tensors[v]
+    a = net.bra_tensor(v)
     b = absorbed_ket(net, msgs, v, skip_edges=(e,))
     axes = [i for i in range(a.ndim) if i != 1 + k]
     m = np.tensordot(b, a.conj(), axes=(axes, axes))
@@ -399,7 +409,7 @@ def synchronous_groups(seq):
 
 def vertex_scalar(net, msgs, v):
     b = absorbed_ket(net, msgs, v)
-    return np.vdot(net.tensors[v], b)  # sum conj(A) * B
+    return np.vdot(net.bra_tensor(v), b)  # sum conj(A) * B
 
 
 def edge_scalar(net, msgs, e):
@@ -675,6 +685,59 @@ def _state_vector(net):
         subs.append(site[v] + "".join(bond[e] for e in g.inc[v]))
     expr = ",".join(subs) + "->" + "".join(site)
     return np.einsum(expr, *net.tensors, optimize="greedy")
+
+
+def bilinear_network(phi: Network, psi: Network):
+    """inner_network(phi, psi) (src/inner.jl:139-152 -> BilinearFormNetwork with the identity operator layer,
+    formnetworks/bilinearformnetwork.jl:23-42,74-94): ket = psi, bra = dag(phi).  Bond dimensions may differ: the smaller
+    tensor is zero-padded, which changes no contraction."""
+    g = psi.graph
+    dtype = np.result_type(phi.dtype, psi.dtype)
+    kets, bras = [], []
+    for v in range(g.nv):
+        a, b = psi.tensors[v].astype(dtype), phi.tensors[v].astype(dtype)
+        shape = tuple(max(x, y) for x, y in zip(a.shape, b.shape))
+        pa = np.zeros(shape, dtype=dtype)
+        pa[tuple(slice(0, n) for n in a.shape)] = a
+        pb = np.zeros(shape, dtype=dtype)
+        pb[tuple(slice(0, n) for n in b.shape)] = b
+        kets.append(pa)
+        bras.append(pb)
+    return Network(g, kets, dtype, bras)
+
+
+def apply_operator_network(op: Network, psi: Network):
+    """A|psi> for an operator network A_v[s', s, b_1..b_z] on the same graph: the operator and ket layers of
+    inner_network(phi, A, psi) (src/inner.jl:154-171) contracted site by site, bonds fused as a_k + chi_k * b_k."""
+    g = psi.graph
+    out = []
+    for v in range(g.nv):
+        a, t = op.tensors[v], psi.tensors[v]
+        z = t.ndim - 1
+        r = np.tensordot(a, t, axes=([1], [0]))  # [s', b_1..b_z, a_1..a_z]
+        r = np.transpose(r, [0] + [i for k in range(z) for i in (1 + k, 1 + z + k)])  # [s', b_1, a_1, b_2, a_2, ...]
+        # C-order reshape of each (b_k, a_k) pair: a_k fastest
+        out.append(np.ascontiguousarray(r.reshape([r.shape[0]] + [r.shape[1 + 2 * k] * r.shape[2 + 2 * k] for k in range(z)])))
+    return Network(g, out, np.result_type(op.dtype, psi.dtype))
+
+
+def exact_inner_operator(phi: Network, op: Network, psi: Network):
+    """<phi|A|psi> by brute force (inner(phi, A, psi; alg = "exact"), src/inner.jl:77-98); tiny networks only."""
+    import string
+    g = psi.graph
+    letters = iter(string.ascii_letters)
+    so = [next(letters) for _ in range(g.nv)]
+    si = [next(letters) for _ in range(g.nv)]
+    b = [next(letters) for _ in range(g.ne)]
+    subs = [so[v] + si[v] + "".join(b[e] for e in g.inc[v]) for v in range(g.nv)]
+    full = np.einsum(",".join(subs) + "->" + "".join(so) + "".join(si), *op.tensors, optimize="greedy")
+    apsi = np.tensordot(full, _state_vector(psi), axes=(list(range(g.nv, 2 * g.nv)), list(range(g.nv))))
+    return np.vdot(_state_vector(phi), apsi)
+
+
+def exact_inner(phi: Network, psi: Network):
+    """<phi|psi> by brute force (inner(phi, psi; alg = "exact"), src/inner.jl:60-75)."""
+    return np.vdot(_state_vector(phi), _state_vector(psi))
 
 
 def exact_norm_sqr(net):

@@ -202,3 +202,33 @@ def test_synchronous_vs_sequential_same_fixed_point():
     m_syn, _, _ = O.bp_update(net, O.identity_messages(net), seq=seq, groups=O.synchronous_groups(seq), maxiter=400, tol=1e-30)
     for k in m_seq:
         assert O.message_diff(m_seq[k], m_syn[k]) < 1e-12
+
+
+# ---- bilinear forms: test/test_inner.jl:12-48 ("Inner products, BP vs exact comparison") ----
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_inner_bp_equals_exact_on_trees(dtype):
+    g = O.random_tree_graph(7, seed=4)
+    x = O.random_network(g, 2, dtype=dtype, seed=1234)
+    y = O.random_network(g, [2, 3, 2, 3, 2, 3], dtype=dtype, seed=4321)
+    net = O.bilinear_network(x, y)
+    msgs, _, _ = O.bp_update(net, {}, seq=O.default_edge_sequence(g), maxiter=1)
+    exact = O.exact_inner(x, y)
+    assert abs(O.scalar(net, msgs) - exact) < 1e-10 * abs(exact)
+    # three layers <x|A|y> (test_inner.jl:41-48) with a random operator network of bond dimension 2
+    rng = np.random.default_rng(9)
+    ops = [rng.standard_normal((2, 2) + (2,) * len(g.inc[v])).astype(dtype) for v in range(g.nv)]
+    a = O.Network(g, ops, dtype)
+    net3 = O.bilinear_network(x, O.apply_operator_network(a, y))
+    msgs3, _, _ = O.bp_update(net3, {}, seq=O.default_edge_sequence(g), maxiter=1)
+    exact3 = O.exact_inner_operator(x, a, y)
+    assert abs(O.scalar(net3, msgs3) - exact3) < 1e-10 * abs(exact3)
+
+
+def test_bilinear_with_equal_layers_is_the_quadratic_form():
+    g = O.grid_graph((3, 3))
+    psi = O.random_network(g, 2, dtype=np.complex128, seed=3)
+    seq = O.parallel_edge_sequence(g)
+    m_q, _, _ = O.bp_update(psi, O.identity_messages(psi), seq=seq, groups=O.synchronous_groups(seq), maxiter=4)
+    both = O.bilinear_network(psi, psi)
+    m_b, _, _ = O.bp_update(both, O.identity_messages(both), seq=seq, groups=O.synchronous_groups(seq), maxiter=4)
+    assert max(np.abs(m_q[k] - m_b[k]).max() for k in m_q) < 1e-14
