@@ -195,7 +195,7 @@ int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, const void*
 /* Singular values (sorted descending, n per matrix) and optionally U*Sigma (columns in the kernel's internal order, not
  * sorted) of `batch` host matrices m x n, column-major, through the batched one-sided Jacobi kernels that
  * simple_update_bp's `factorize_svd` (src/apply.jl:81-88) runs on.  variant: 0 = the kernel the gate path selects,
- * 1 = the shape-generic kernel (second opinion).  device_ms (nullable): CUDA-event time of the decomposition alone. */
+ * 1 = the shape-generic kernel, 2 = the round-robin m, n <= 64 kernel (second opinions).  device_ms (nullable): CUDA-event time of the decomposition alone. */
 int itn_svd_batch(itn_ctx* ctx, int dtype, int m, int n, int batch, const void* host_in, double* host_sigma,
                   void* host_us, int variant, double* device_ms);
 

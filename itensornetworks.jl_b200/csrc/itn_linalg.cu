@@ -486,6 +486,263 @@ __global__ void __launch_bounds__(256, 2) k_jacobi64(const SvdJob* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_jacobi64oe: k_jacobi64 with the odd-even transposition ordering (Brent-Luk): the columns sit on a line of n
+// positions, steps alternate between the pairs (2k, 2k+1) and (2k+1, 2k+2), and the two columns of a pair exchange
+// positions after their rotation, so that n consecutive steps bring every pair of columns together exactly once.
+// Lane group k keeps the column at position 2k+1 in REGISTERS for the whole decomposition: in every step it loads only
+// its partner (position 2k or 2k+2) from shared memory, and after the rotation it keeps the rotated partner (which now
+// sits at position 2k+1) and stores its own rotated column into the partner's slot.  Shared memory therefore holds the
+// even positions only (32 KB for 64 ComplexF64 columns) and a step moves ONE column per pair in each direction, half
+// the traffic of k_jacobi64, whose ncu profile is shared-memory bound (profiles/r1r_k_jacobi64_ncu.txt).
+// Thresholds, rotation formulas and norm updates are those of k_jacobi_svd / k_jacobi64.
+// ------------------------------------------------------------------------------------------------
+// OCC = resident CTAs per SM asked for: 2 keeps the partner column in registers between the inner product and the
+// rotation (128 registers); 3 reads it again from shared memory (<= 85 registers, one more matrix in flight per SM).
+template <bool C, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restrict__ jobs) {
+  extern __shared__ double sm[];  // [planes][32 slots][64 rows]: the columns at the even positions
+  __shared__ double s_norm[64];   // squared column norms by position
+  __shared__ double s_tiny;
+  __shared__ int s_rot;
+  const SvdJob J = jobs[blockIdx.x];
+  if (J.skip && *J.skip) return;
+  const int m = J.m, n = J.n;
+  if (n == 0 || m == 0) return;
+  double* dst = J.us ? J.us : J.a;
+  const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane >> 3, sl = lane & 7;
+  const int k = warp * 4 + sub;        // lane group: owns position 2k+1 (registers) and loads / stores slots k, k+1
+  const bool has_reg = 2 * k + 1 < n;  // this group holds a column
+  double* Ar = sm;
+  double* Ai = sm + 32 * 64;
+  const size_t mn = (size_t)m * n;
+  for (int idx = tid; idx < ((n + 1) >> 1) * 64; idx += nthreads) {  // even positions -> shared memory
+    const int slot = idx >> 6, i = idx & 63;
+    const bool ok = i < m;
+    Ar[idx] = ok ? J.a[(size_t)(2 * slot) * m + i] : 0.0;
+    if (C) Ai[idx] = ok ? J.a[mn + (size_t)(2 * slot) * m + i] : 0.0;
+  }
+  double2 pr[4], pi[4];  // the column at position 2k+1: rows {2 sl, 2 sl + 1} + 16 t
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int i0 = 2 * sl + 16 * t;
+    const size_t base = (size_t)(2 * k + 1) * m;
+    pr[t].x = (has_reg && i0 < m) ? J.a[base + i0] : 0.0;
+    pr[t].y = (has_reg && i0 + 1 < m) ? J.a[base + i0 + 1] : 0.0;
+    pi[t].x = (C && has_reg && i0 < m) ? J.a[mn + base + i0] : 0.0;
+    pi[t].y = (C && has_reg && i0 + 1 < m) ? J.a[mn + base + i0 + 1] : 0.0;
+  }
+  __syncthreads();
+  auto column_norms = [&]() {  // uniform control flow: every lane takes part in both reductions
+    double a2 = 0.0, b2 = 0.0;
+    if (2 * k < n) {
+      const double2* cr = reinterpret_cast<const double2*>(Ar + k * 64) + sl;
+      const double2* ci = reinterpret_cast<const double2*>(Ai + k * 64) + sl;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const double2 r = cr[8 * t];
+        a2 += r.x * r.x + r.y * r.y;
+        if (C) {
+          const double2 im = ci[8 * t];
+          a2 += im.x * im.x + im.y * im.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      b2 += pr[t].x * pr[t].x + pr[t].y * pr[t].y;
+      if (C) b2 += pi[t].x * pi[t].x + pi[t].y * pi[t].y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    }
+    if (sl == 0) {
+      if (2 * k < n) s_norm[2 * k] = a2;
+      if (has_reg) s_norm[2 * k + 1] = b2;
+    }
+  };
+  column_norms();
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int j = 0; j < n; ++j) t += s_norm[j];
+    s_tiny = t * (2.220446049250313e-19 * 2.220446049250313e-19);
+  }
+  __syncthreads();
+  const double tiny = s_tiny;
+  const double tol = sqrt((double)m) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+  int step = 0;  // parity continues across sweeps: any n consecutive steps visit every pair once
+  for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    if (sweep > 0) column_norms();
+    __syncthreads();
+    for (int it = 0; it < n; ++it, ++step) {
+      const int slot = k + (step & 1);  // even step: pair (2k, 2k+1); odd step: pair (2k+1, 2k+2)
+      const int ppos = 2 * slot;
+      const bool valid = has_reg && ppos < n;
+      double2* cqr = reinterpret_cast<double2*>(Ar + (valid ? slot : 0) * 64) + sl;
+      double2* cqi = reinterpret_cast<double2*>(Ai + (valid ? slot : 0) * 64) + sl;
+      double2 qr[4], qi[4];
+      double gr = 0.0, gi = 0.0;
+      if (valid) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          qr[t] = cqr[8 * t];
+          if (C) qi[t] = cqi[8 * t];
+        }
+        double gr1 = 0.0, gi1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // conj(a_p) . a_q
+          gr = fma(pr[t].x, qr[t].x, gr);
+          gr1 = fma(pr[t].y, qr[t].y, gr1);
+          if (C) {
+            gr = fma(pi[t].x, qi[t].x, gr);
+            gr1 = fma(pi[t].y, qi[t].y, gr1);
+            gi = fma(pr[t].x, qi[t].x, gi);
+            gi1 = fma(pr[t].y, qi[t].y, gi1);
+            gi = fma(-pi[t].x, qr[t].x, gi);
+            gi1 = fma(-pi[t].y, qr[t].y, gi1);
+          }
+        }
+        gr += gr1;
+        gi += gi1;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        gr += __shfl_xor_sync(0xffffffffu, gr, o);
+        if (C) gi += __shfl_xor_sync(0xffffffffu, gi, o);
+      }
+      if (valid) {
+        const double alpha = s_norm[2 * k + 1], beta = s_norm[ppos];  // p = the register column, q = the partner
+        const double g2 = gr * gr + gi * gi;
+        const double thr = tol2 * alpha * beta;
+        double na = alpha, nb = beta;
+        if (alpha > tiny && beta > tiny && g2 > thr && g2 > 0.0) {
+          // Rotation angle without chained reciprocal square roots: with delta = beta - alpha and
+          // h = (4 |g|^2 + delta^2)^-1/2:  cos(2 theta) = |delta| h,  sin(2 theta) = 2 |g| h, hence
+          // c^2 = (1 + |delta| h) / 2,  s = sign(delta) |g| h / c,  t |g| = sign(delta) |g|^2 h / c^2
+          // (the same smaller-angle rotation as t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = delta / (2 |g|));
+          // rsqrt(g2) and h are independent, only rsqrt(c^2) waits for h.
+          const double delta = beta - alpha;
+          const double ginv = rsqrt(g2);
+          const double h = rsqrt(fma(delta, delta, 4.0 * g2));
+          const double er = gr * ginv, ei = -gi * ginv;
+          const double cc = fma(0.5 * fabs(delta), h, 0.5);
+          const double rc = rsqrt(cc);
+          const double c = cc * rc;
+          const double s = copysign(g2 * ginv * h * rc, delta);
+          const double tg = copysign(g2 * h * rc * rc, delta);  // t |g|
+          na = fmax(alpha - tg, 0.0);
+          nb = beta + tg;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            double2 npr, nqr, npi, nqi;
+            if (OCC > 2) {  // the partner was not kept in registers
+              qr[u] = cqr[8 * u];
+              if (C) qi[u] = cqi[8 * u];
+            }
+            {
+              const double a = pr[u].x, ai = C ? pi[u].x : 0.0, b0 = qr[u].x, b0i = C ? qi[u].x : 0.0;
+              const double b = C ? (b0 * er - b0i * ei) : b0 * er, bi = C ? (b0 * ei + b0i * er) : 0.0;
+              npr.x = c * a - s * b;
+              nqr.x = s * a + c * b;
+              npi.x = c * ai - s * bi;
+              nqi.x = s * ai + c * bi;
+            }
+            {
+              const double a = pr[u].y, ai = C ? pi[u].y : 0.0, b0 = qr[u].y, b0i = C ? qi[u].y : 0.0;
+              const double b = C ? (b0 * er - b0i * ei) : b0 * er, bi = C ? (b0 * ei + b0i * er) : 0.0;
+              npr.y = c * a - s * b;
+              nqr.y = s * a + c * b;
+              npi.y = c * ai - s * bi;
+              nqi.y = s * ai + c * bi;
+            }
+            // position exchange: the rotated register column goes to the partner's slot, the rotated partner stays
+            cqr[8 * u] = npr;
+            pr[u] = nqr;
+            if (C) {
+              cqi[8 * u] = npi;
+              pi[u] = nqi;
+            }
+          }
+          if (sl == 0 && g2 > 64.0 * thr) s_rot = 1;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {  // no rotation: the two columns still exchange positions
+            if (OCC > 2) {
+              qr[u] = cqr[8 * u];
+              if (C) qi[u] = cqi[8 * u];
+            }
+            cqr[8 * u] = pr[u];
+            pr[u] = qr[u];
+            if (C) {
+              cqi[8 * u] = pi[u];
+              pi[u] = qi[u];
+            }
+          }
+        }
+        if (sl == 0) {
+          s_norm[ppos] = na;       // the former register column now sits in the slot
+          s_norm[2 * k + 1] = nb;  // the former partner is the register column
+        }
+      }
+      __syncthreads();
+    }
+    const int any = s_rot;
+    __syncthreads();
+    if (!any) break;
+  }
+  column_norms();
+  __syncthreads();
+  for (int j = tid; j < n; j += nthreads) {
+    const double sj = s_norm[j];
+    int rank = 0;
+    for (int kk = 0; kk < n; ++kk) {
+      const double sk = s_norm[kk];
+      rank += (sk > sj) || (sk == sj && kk < j);
+    }
+    J.sigma[rank] = sqrt(sj);
+    J.perm[rank] = j;
+  }
+  for (int idx = tid; idx < ((n + 1) >> 1) * 64; idx += nthreads) {
+    const int slot = idx >> 6, i = idx & 63;
+    if (i < m) {
+      dst[(size_t)(2 * slot) * m + i] = Ar[idx];
+      if (C) dst[mn + (size_t)(2 * slot) * m + i] = Ai[idx];
+    }
+  }
+  if (has_reg) {
+    const size_t base = (size_t)(2 * k + 1) * m;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i0 = 2 * sl + 16 * t;
+      if (i0 < m) {
+        dst[base + i0] = pr[t].x;
+        if (C) dst[mn + base + i0] = pi[t].x;
+      }
+      if (i0 + 1 < m) {
+        dst[base + i0 + 1] = pr[t].y;
+        if (C) dst[mn + base + i0 + 1] = pi[t].y;
+      }
+    }
+  }
+}
+
+template <bool C, int OCC>
+void launch_jacobi64oe(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int maxn) {
+  const int groups = (maxn + 1) / 2;
+  const int warps = std::max(1, (groups + 3) / 4);
+  const size_t smem = (size_t)(C ? 2 : 1) * 32 * 64 * sizeof(double);
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi64oe<C, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi64oe<C, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  k_jacobi64oe<C, OCC><<<njobs, warps * 32, smem, ctx->stream>>>(dj);
+  ITN_LAUNCH_CHECK(ctx);
+}
+
 template <bool C>
 void launch_jacobi64(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int maxn) {
   const int npairs = (maxn + 1) / 2;
@@ -497,7 +754,7 @@ void launch_jacobi64(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int maxn) {
   ITN_LAUNCH_CHECK(ctx);
 }
 
-int g_jacobi_variant = 0;  // 0 = auto, 1 = generic kernel only (itn_svd_batch's second opinion)
+int g_jacobi_variant = 0;  // 0 = auto, 1 = generic kernel only, 2 = round-robin k_jacobi64 (itn_svd_batch's second opinions)
 
 void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
   if (jobs.empty()) return;
@@ -511,11 +768,19 @@ void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
     any_v = any_v || j.v != nullptr;
     need = std::max(need, ((size_t)j.m * j.n + (j.v ? (size_t)j.n * j.n : 0)) * (cplx ? 2 : 1));
   }
-  if (!any_v && maxm <= 64 && maxn <= 64 && maxn >= 2 && g_jacobi_variant == 0) {
+  if (!any_v && maxm <= 64 && maxn <= 64 && maxn >= 2 && g_jacobi_variant != 1) {
     DevBuf jb(ctx, jobs.size() * sizeof(SvdJob));
     const SvdJob* dj = itn_upload(ctx, jobs, jb);
-    if (cplx) launch_jacobi64<true>(ctx, dj, (unsigned)jobs.size(), maxn);
-    else launch_jacobi64<false>(ctx, dj, (unsigned)jobs.size(), maxn);
+    if (g_jacobi_variant == 2) {
+      if (cplx) launch_jacobi64<true>(ctx, dj, (unsigned)jobs.size(), maxn);
+      else launch_jacobi64<false>(ctx, dj, (unsigned)jobs.size(), maxn);
+    } else if (g_jacobi_variant == 3) {
+      if (cplx) launch_jacobi64oe<true, 3>(ctx, dj, (unsigned)jobs.size(), maxn);
+      else launch_jacobi64oe<false, 3>(ctx, dj, (unsigned)jobs.size(), maxn);
+    } else {
+      if (cplx) launch_jacobi64oe<true, 2>(ctx, dj, (unsigned)jobs.size(), maxn);
+      else launch_jacobi64oe<false, 2>(ctx, dj, (unsigned)jobs.size(), maxn);
+    }
     return;
   }
   size_t smem = std::min<size_t>(need * sizeof(double), 200 * 1024);
@@ -1388,7 +1653,7 @@ extern "C" int itn_svd_batch(itn_ctx* ctx, int dtype, int m, int n, int batch, c
   ITN_REQUIRE(ctx && host_in && host_sigma, ITN_EINVAL, "NULL argument");
   ITN_REQUIRE(dtype == ITN_F64 || dtype == ITN_C128, ITN_EUNSUPPORTED, "dtype must be 0 (Float64) or 1 (ComplexF64)");
   ITN_REQUIRE(m >= 1 && n >= 1 && n <= 256 && batch >= 0, ITN_EINVAL, "bad batch shape");
-  ITN_REQUIRE(variant == 0 || variant == 1, ITN_EINVAL, "variant must be 0 (auto) or 1 (generic kernel)");
+  ITN_REQUIRE(variant >= 0 && variant <= 3, ITN_EINVAL, "variant must be 0 (auto), 1 (generic kernel), 2 (round-robin m, n <= 64 kernel) or 3 (odd-even kernel, 3 CTAs per SM)");
   if (batch == 0) return ITN_OK;
   CUDA_CHECK(cudaSetDevice(ctx->device));
   const bool cplx = dtype == ITN_C128;

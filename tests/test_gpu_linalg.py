@@ -1,8 +1,9 @@
 """GPU checks of the batched one-sided Jacobi SVD behind `factorize_svd` in simple_update_bp (src/apply.jl:81-88).
 
 Reference for the numbers: LAPACK through NumPy (the reference calls LAPACK through NDTensors' `svd`).  Singular values
-must agree to 1e-12 relative to the largest one (the gate path's tolerance is 1e-10); the specialised m, n <= 64 kernel
-(variant 0) is also compared with the shape-generic kernel (variant 1) on the same bytes."""
+must agree to 1e-12 relative to the largest one (the gate path's tolerance is 1e-10); the specialised m, n <= 64 kernels
+(variant 0: odd-even ordering, variant 2: round-robin) are also compared with the shape-generic kernel (variant 1) on the
+same bytes."""
 import numpy as np
 import pytest
 
@@ -32,7 +33,7 @@ def test_singular_values_match_lapack(ctx, dtype, shape):
     rng = np.random.default_rng(100 * m + n)
     a = random_batch(rng, 5, m, n, dtype)
     ref = np.stack([np.concatenate([np.linalg.svd(x, compute_uv=False), np.zeros(max(0, n - m))]) for x in a])
-    for variant in (0, 1):
+    for variant in (0, 1, 2, 3):
         sig, us, _ = E.svd_batch(a, variant=variant, want_us=True, ctx=ctx)
         scale = ref[:, :1]
         assert np.max(np.abs(sig - ref) / scale) < 1e-12, (variant, np.max(np.abs(sig - ref) / scale))
@@ -55,9 +56,11 @@ def test_graded_and_rank_deficient(ctx, dtype):
     ref = np.stack([np.linalg.svd(x, compute_uv=False) for x in a])
     s0, _, _ = E.svd_batch(a, variant=0, ctx=ctx)
     s1, _, _ = E.svd_batch(a, variant=1, ctx=ctx)
+    s2, _, _ = E.svd_batch(a, variant=2, ctx=ctx)
     scale = np.maximum(ref[:, :1], 1e-300)
     assert np.max(np.abs(s0 - ref) / scale) < 1e-12
     assert np.max(np.abs(s0 - s1) / scale) < 1e-12
+    assert np.max(np.abs(s0 - s2) / scale) < 1e-12
 
 
 def test_gate_sized_batch_matches_generic_kernel(ctx):
@@ -65,7 +68,9 @@ def test_gate_sized_batch_matches_generic_kernel(ctx):
     a = random_batch(rng, 300, 64, 64, np.complex128)
     s0, _, t0 = E.svd_batch(a, variant=0, ctx=ctx)
     s1, _, t1 = E.svd_batch(a, variant=1, ctx=ctx)
+    s2, _, t2 = E.svd_batch(a, variant=2, ctx=ctx)
     assert np.max(np.abs(s0 - s1)) < 1e-12 * np.max(s1)
+    assert np.max(np.abs(s0 - s2)) < 1e-12 * np.max(s1)
     ref = np.linalg.svd(a[:8], compute_uv=False)
     assert np.max(np.abs(s0[:8] - ref)) < 1e-12 * np.max(ref)
-    print(f"\n300 x (64 x 64 c128): specialised {t0:.3f} ms, generic {t1:.3f} ms")
+    print(f"\n300 x (64 x 64 c128): odd-even {t0:.3f} ms, round-robin {t2:.3f} ms, generic {t1:.3f} ms")
