@@ -85,6 +85,7 @@ class BeliefPropagationCache:
             self.sdims = list(_like.sdims)
             self.owner, self.rank = _like.owner, _like.rank
             self.bilinear = getattr(_like, "bilinear", False)
+            self._edims = None if _like._edims is None else list(_like._edims)
             return
         self.ctx = ctx or default_context()
         self.graph = psi.graph
@@ -92,12 +93,13 @@ class BeliefPropagationCache:
         self.dtype = _COMPUTE[self.eltype]     # what the device computes in
         g = self.graph
         self.sdims = [t.shape[0] for t in psi.tensors]
+        self._edims = [psi.edge_dim(e) for e in range(g.ne)]
         # multi-GPU: owner[v] = rank that stores vertex v; dist = (rank, nranks) of this process
         self.owner = None if owner is None else [int(x) for x in owner]
         self.rank = self.ctx.rank if dist is None else int(dist[0])
         a0, p0 = i32([u for u, _ in g.edges])
         a1, p1 = i32([v for _, v in g.edges])
-        a2, p2 = i32([psi.edge_dim(e) for e in range(g.ne)])
+        a2, p2 = i32(self._edims)
         a3, p3 = i32(self.sdims)
         h = C.c_void_p()
         a4, p4 = i32(self.owner) if self.owner is not None else (None, None)
@@ -143,9 +145,20 @@ class BeliefPropagationCache:
 
     # -- factors ------------------------------------------------------------------------------
     def edge_dim(self, e):
-        d = C.c_int32()
-        check(lib().itn_net_edge_dim(self.h, int(e), C.byref(d)))
-        return d.value
+        # host copy of the library's edge dims (they change only through the gate calls below, which return them)
+        ed = self._edims
+        if ed is None:
+            ed = self._edims = [0] * self.graph.ne
+            d = C.c_int32()
+            for f in range(self.graph.ne):
+                check(lib().itn_net_edge_dim(self.h, f, C.byref(d)))
+                ed[f] = d.value
+        return ed[int(e)]
+
+    def _note_newdims(self, eids, newdim):
+        if self._edims is not None:
+            for e, k in zip(eids, newdim):
+                self._edims[e] = int(k)
 
     def _shape(self, v):
         return (self.sdims[v],) + tuple(self.edge_dim(e) for e in self.graph.inc[v])
@@ -529,33 +542,11 @@ def apply(gate, bpc, verts, maxdim=None, cutoff=None, normalize=False, callback=
 def apply_layer(gates, bpc, pairs, maxdim=None, cutoff=None, normalize=False, msg_mode=0):
     """A vertex-disjoint layer of two-site gates in one batched call (in place).
     gates[i][s1', s2', s1, s2] acts on pairs[i] = (v1, v2)."""
-    g = bpc.graph
-    eids, packed = [], []
-    memo = {}  # the same gate object on many edges (a Trotter layer) is packed once per orientation
-    for gate, (v1, v2) in zip(gates, pairs):
-        e = g.eid.get((v1, v2))
-        if e is None:
-            raise ITNError(1, "Vertices where the gates are being applied must be neighbors for now.")
-        d1, d2 = bpc.sdims[v1], bpc.sdims[v2]
-        flip = g.edges[e] != (v1, v2)  # engine orientation is (esrc, edst)
-        key = (id(gate), d1, d2, flip)
-        if key not in memo:
-            gt = np.asarray(gate, dtype=bpc.dtype).reshape(d1, d2, d1, d2)
-            if flip:
-                gt = gt.transpose(1, 0, 3, 2)
-            memo[key] = np.asfortranarray(gt).ravel(order="F")
-        eids.append(e)
-        packed.append(memo[key])
+    eids, packed = _pack_gates(bpc, gates, pairs)
     n = len(eids)
-    packed = np.ascontiguousarray(np.concatenate(packed)) if n else np.zeros(0, dtype=bpc.dtype)
+    packed = np.concatenate(packed) if n else np.zeros(0, dtype=bpc.dtype)
     dmax = max(bpc.sdims) if bpc.sdims else 1
-    stride = 1
-    if n:
-        chis = {}
-        for e in eids:
-            if e not in chis:
-                chis[e] = bpc.edge_dim(e)
-        stride = max(dmax * dmax * c for c in chis.values())
+    stride = max([dmax * dmax * bpc.edge_dim(e) for e in eids] + [1])
     newdim = np.zeros(n, dtype=np.int32)
     terr = np.zeros(n, dtype=np.float64)
     sv = np.zeros((n, stride), dtype=np.float64)
@@ -564,8 +555,25 @@ def apply_layer(gates, bpc, pairs, maxdim=None, cutoff=None, normalize=False, ms
                            -1.0 if cutoff is None else float(cutoff), 1 if normalize else 0, int(msg_mode),
                            newdim.ctypes.data_as(C.POINTER(C.c_int32)), terr.ctypes.data_as(C.POINTER(C.c_double)),
                            sv.ctypes.data_as(C.POINTER(C.c_double)), stride))
-    return {"newdim": newdim, "truncation_error": terr,
-            "singular_values": [sv[i, :newdim[i]].copy() for i in range(n)]}
+    bpc._note_newdims(eids, newdim)
+    return {"newdim": newdim, "truncation_error": terr, "singular_values": _SvalRows(sv, newdim)}
+
+
+class _SvalRows:
+    """singular_values[i] = the kept singular values of gate i (a view into the padded result rows, sliced on access:
+    a colour layer of the 64 x 64 lattice has 2048 gates and most callers read a few of them)."""
+
+    def __init__(self, sv, newdim):
+        self.sv, self.newdim = sv, newdim
+
+    def __len__(self):
+        return len(self.newdim)
+
+    def __getitem__(self, i):
+        return self.sv[i, :self.newdim[i]]
+
+    def __iter__(self):
+        return (self.sv[i, :k] for i, k in enumerate(self.newdim))
 
 
 def _pack_gates(bpc, gates, pairs):
@@ -604,7 +612,7 @@ def tebd_step(bpc, layers, maxdim=None, cutoff=None, normalize=False, msg_mode=0
     n = len(all_e)
     packed = np.ascontiguousarray(np.concatenate(all_g)) if n else np.zeros(0, dtype=bpc.dtype)
     dmax = max(bpc.sdims) if bpc.sdims else 1
-    stride = max([dmax * dmax * bpc.edge_dim(e) for e in set(all_e)] + [1])
+    stride = max([dmax * dmax * bpc.edge_dim(e) for e in all_e] + [1])
     if maxdim is not None:
         stride = max(stride, dmax * dmax * int(maxdim))  # bonds may grow between the layers of the step
     newdim = np.zeros(n, dtype=np.int32)
@@ -629,10 +637,10 @@ def tebd_step(bpc, layers, maxdim=None, cutoff=None, normalize=False, msg_mode=0
                                  1, newdim.ctypes.data_as(C.POINTER(C.c_int32)), terr.ctypes.data_as(C.POINTER(C.c_double)),
                                  sv.ctypes.data_as(C.POINTER(C.c_double)), stride, C.byref(iters)))
     bpc._host_refs = None
+    bpc._note_newdims(all_e, newdim)  # layers in order: the last gate on an edge wins
     if info is not None:
         info["bp_iterations"] = iters.value
-    return {"newdim": newdim, "truncation_error": terr, "layer_ptr": ptr,
-            "singular_values": [sv[i, :newdim[i]].copy() for i in range(n)]}
+    return {"newdim": newdim, "truncation_error": terr, "layer_ptr": ptr, "singular_values": _SvalRows(sv, newdim)}
 
 
 def map_eigvals(f, mats, cutoff=None, ctx=None):
