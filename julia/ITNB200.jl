@@ -183,4 +183,29 @@ function apply_gate!(bpc::B200BeliefPropagationCache, gate::AbstractArray, v1, v
   return bpc
 end
 
+# inner(phi, psi; alg = "bp") / loginner (src/inner.jl:100-171): BilinearFormNetwork(phi, psi) with an explicit bra layer.
+# phi must live on the same graph with the same link dimensions as psi (pad the smaller tensor with zeros otherwise;
+# for inner(phi, A, psi) contract A[v] into psi[v] first and fuse the link pairs with combiners).  The link indices of
+# phi[v] are matched to those of psi[v] edge by edge; phi is passed un-conjugated, the engine applies `dag`.
+function set_bra_factor!(bpc::B200BeliefPropagationCache, phi::ITensorNetwork, v)
+  t = phi[v]
+  s = only(siteinds(phi, v))
+  ax = Int32[i == s ? -1 : findfirst(e -> (src(e) == v || dst(e) == v) &&
+                                      i == commonind(phi[src(e)], phi[dst(e)]), bpc.eds) - 1 for i in inds(t)]
+  a = Array{bpc.elt}(array(t))
+  GC.@preserve a ax check(ccall((:itn_net_set_bra_tensor, LIB), Cint,
+    (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Int32}), bpc.h, bpc.vid[v], a, ndims(a), ax))
+  return bpc
+end
+
+function loginner_bp(phi::ITensorNetwork, psi::ITensorNetwork; ctx::Context=Context(), messages=:none, update_kwargs...)
+  # the fallback initialize_cache of the reference gives a bilinear form no default messages (src/initialize_cache.jl:10-12)
+  bpc = B200BeliefPropagationCache(psi; ctx, messages)
+  for v in bpc.verts
+    set_bra_factor!(bpc, phi, v)
+  end
+  return ITensorNetworks.logscalar(ITensorNetworks.update(bpc; update_kwargs...))
+end
+inner_bp(phi, psi; kwargs...) = exp(loginner_bp(phi, psi; kwargs...))
+
 end # module
