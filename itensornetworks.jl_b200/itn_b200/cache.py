@@ -539,24 +539,42 @@ def apply(gate, bpc, verts, maxdim=None, cutoff=None, normalize=False, callback=
     raise ITNError(1, "Gates with more than 2 sites is not supported yet.")
 
 
-def apply_layer(gates, bpc, pairs, maxdim=None, cutoff=None, normalize=False, msg_mode=0):
+def apply_layer(gates, bpc, pairs=None, maxdim=None, cutoff=None, normalize=False, msg_mode=0):
     """A vertex-disjoint layer of two-site gates in one batched call (in place).
     gates[i][s1', s2', s1, s2] acts on pairs[i] = (v1, v2)."""
-    eids, packed = _pack_gates(bpc, gates, pairs)
+    if isinstance(gates, GateLayer):  # packed once by prepare_layer (a Trotter driver applies the same layers every step)
+        eids, packed, pe = gates.eids, gates.packed, gates.pe
+    else:
+        eids, packed = _pack_gates(bpc, gates, pairs)
+        packed = np.concatenate(packed) if eids else np.zeros(0, dtype=bpc.dtype)
+        _, pe = i32(eids)
     n = len(eids)
-    packed = np.concatenate(packed) if n else np.zeros(0, dtype=bpc.dtype)
     dmax = max(bpc.sdims) if bpc.sdims else 1
     stride = max([dmax * dmax * bpc.edge_dim(e) for e in eids] + [1])
     newdim = np.zeros(n, dtype=np.int32)
     terr = np.zeros(n, dtype=np.float64)
     sv = np.zeros((n, stride), dtype=np.float64)
-    _, pe = i32(eids)
     check(lib().itn_apply2(bpc.h, pe, n, packed.ctypes.data_as(C.c_void_p), 0 if maxdim is None else int(maxdim),
                            -1.0 if cutoff is None else float(cutoff), 1 if normalize else 0, int(msg_mode),
                            newdim.ctypes.data_as(C.POINTER(C.c_int32)), terr.ctypes.data_as(C.POINTER(C.c_double)),
                            sv.ctypes.data_as(C.POINTER(C.c_double)), stride))
     bpc._note_newdims(eids, newdim)
     return {"newdim": newdim, "truncation_error": terr, "singular_values": _SvalRows(sv, newdim)}
+
+
+class GateLayer:
+    """A vertex-disjoint layer of two-site gates in the engine's wire format (edge ids + gates packed in (esrc, edst)
+    orientation), built once by prepare_layer and passed to apply_layer in place of the gate list."""
+
+    def __init__(self, eids, packed):
+        self.eids = list(eids)
+        self.packed = np.ascontiguousarray(packed)
+        self._ids, self.pe = i32(self.eids)
+
+
+def prepare_layer(bpc, gates, pairs):
+    eids, packed = _pack_gates(bpc, gates, pairs)
+    return GateLayer(eids, np.concatenate(packed) if eids else np.zeros(0, dtype=bpc.dtype))
 
 
 class _SvalRows:

@@ -223,3 +223,20 @@ def test_apply2_dmma_tile_path(dtype, e, maxdim):
         for k, m in m2.items():
             if g.eid[k] != e:
                 assert rel_err(out.message(k), m) < 1e-9
+
+
+def test_prepared_layer_equals_gate_list(ctx):
+    # prepare_layer packs a layer once (edge ids + gates in (esrc, edst) orientation); applying it equals the list form
+    g = O.grid_graph((4, 3))
+    net, psi = make_pair(g, 3, np.complex128)
+    msgs, bpc = bp_both(net, psi, ctx, 4)
+    layer = O.edge_coloring(g)[1]
+    gate = O.random_unitary(4, seed=21).reshape(2, 2, 2, 2)
+    pairs = [g.edges[e][::-1] if i % 2 else g.edges[e] for i, e in enumerate(layer)]  # both orientations
+    a, b = bpc.copy(), bpc.copy()
+    ia = E.apply_layer([gate] * len(layer), a, pairs, maxdim=3, cutoff=1e-12)
+    ib = E.apply_layer(E.prepare_layer(b, [gate] * len(layer), pairs), b, maxdim=3, cutoff=1e-12)
+    assert np.array_equal(ia["newdim"], ib["newdim"]) and np.array_equal(ia["truncation_error"], ib["truncation_error"])
+    for v in range(g.nv):
+        assert np.array_equal(a.factor(v), b.factor(v))
+    assert a.edge_dim(layer[0]) == int(ia["newdim"][0])

@@ -47,6 +47,22 @@ def test_singular_values_match_lapack(ctx, dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("shape", [(128, 64), (64, 128), (100, 50), (33, 100), (128, 7), (128, 128), (70, 70)])
+def test_bond_matrices_up_to_128(ctx, dtype, shape):
+    # heavy-hex chi = 32 bond matrices: 128 x 64 and 64 x 128 run on the m <= 128 / n <= 128 instances of the odd-even
+    # kernel (a wide matrix has n - m null columns), anything larger in both directions on the shape-generic kernel
+    m, n = shape
+    rng = np.random.default_rng(7 * m + n)
+    a = random_batch(rng, 3, m, n, dtype)
+    ref = np.stack([np.concatenate([np.linalg.svd(x, compute_uv=False), np.zeros(max(0, n - m))]) for x in a])
+    for variant in (0, 1):
+        sig, us, _ = E.svd_batch(a, variant=variant, want_us=True, ctx=ctx)
+        assert np.max(np.abs(sig - ref) / ref[:, :1]) < 1e-12, (variant, np.max(np.abs(sig - ref) / ref[:, :1]))
+        for x, u in zip(a, us):
+            assert np.linalg.norm(u @ u.conj().T - x @ x.conj().T) < 1e-11 * np.linalg.norm(x) ** 2
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_graded_and_rank_deficient(ctx, dtype):
     rng = np.random.default_rng(5)
     a = random_batch(rng, 4, 64, 64, dtype, decay=0.6)  # sigma_max / sigma_min ~ 1e14
