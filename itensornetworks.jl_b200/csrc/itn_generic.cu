@@ -886,7 +886,7 @@ void itn_run_modeprods(itn_ctx* ctx, bool cplx, const std::vector<ModeProdSpec>&
       S.R = sp.n / (L * sp.dims[m]);
       S.m = sp.mat[t];
       S.mplane = (long long)sp.dims[m] * sp.dims[m];
-      S.trans = 0;
+      S.trans = sp.trans[t] ? 1 : 0;
       S.conj = 0;
       maxkn = std::max(maxkn, S.K * S.N);
     }

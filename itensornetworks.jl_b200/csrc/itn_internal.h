@@ -216,6 +216,7 @@ struct ModeProdSpec {
   int nsteps;
   int mode[ITN_MAX_MODES];          // which mode each step acts on
   const double* mat[ITN_MAX_MODES];  // planar dims[mode] x dims[mode]: out[.., b, ..] = sum_a in[.., a, ..] mat[a + K b]
+  int trans[ITN_MAX_MODES];          // non-zero: use mat[b + K a] instead
   double *w0, *w1;                   // ping-pong outputs, n * planes doubles each
 };
 void itn_run_modeprods(itn_ctx* ctx, bool cplx, const std::vector<ModeProdSpec>& specs, std::vector<const double*>& result);

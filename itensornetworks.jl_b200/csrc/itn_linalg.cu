@@ -1337,6 +1337,122 @@ __global__ void __launch_bounds__(256) k_su_T(const SuEdge* __restrict__ edges) 
   }
 }
 
+// ---- thin sides: fewer outer-bond states than (site, gate bond) states, X < n (degree <= 2 sites at d chi > chi^(z-1)) ----
+// The bond environment C = A~^T conj(A~) (n x n) then has rank X, and the reference's QR of the X x n matrix A~ returns
+// an X x n R factor (apply.jl:74-75 with rows = outer bonds).  Any square-root factor of the outer messages serves as
+// well as the Hermitian one: with M_j = S_j S_j^H (Cholesky, S_j = R_j^T of k_chol) the tensor A x_j S_j, read as an
+// X x n matrix, IS such an R (R^T conj(R) = C), and R^+ = R^H (R R^H)^-1 with one X x X Cholesky.  No eigen-
+// decomposition of the rank-deficient C is needed; if a Cholesky meets a non-positive pivot the flag stays 0 and the
+// eigen route (k_jacobi_svd + k_su_build_R) takes over as before.
+struct ThinJob {
+  const double* at;  // A x_j S_j over the outer bonds, canonical planar [s, bonds...]
+  long long n_t;     // its element count (offset of the imaginary plane)
+  double* R;         // planar X x n:  R[i + X o], i = outer multi-index, o = s + d l
+  double* Rp;        // planar n x X:  R^+[o + n i]
+  double* G;         // planar X x X:  R R^H
+  const double* Gp;  // planar X x X:  k_chol's R^+ output for G  (conj(G)^-1 = Gp Gp^H)
+  const int* okG;    // k_chol flag of G
+  const int* ok_env; // k_chol flags of the outer messages (n_env of them, contiguous)
+  int n_env;
+  int* ok;           // out: 1 when R / R^+ are valid
+  int d, chi, X, n;
+  long long lo;      // canonical stride of the gate bond (product of the extents below it, site included)
+};
+
+template <bool C>
+__global__ void __launch_bounds__(256) k_thin_R(const ThinJob* __restrict__ jobs) {
+  const ThinJob J = jobs[blockIdx.x];
+  const long long lo_rest = J.lo / J.d, rn = (long long)J.X * J.n;
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < J.n_t; idx += (long long)gridDim.y * blockDim.x) {
+    const int s = (int)(idx % J.d);
+    long long r = idx / J.d;
+    const long long below = r % lo_rest;
+    r /= lo_rest;
+    const int l = (int)(r % J.chi);
+    const long long above = r / J.chi;
+    const long long i = below + lo_rest * above;
+    const int o = s + J.d * l;
+    J.R[i + (long long)J.X * o] = J.at[idx];
+    if (C) J.R[rn + i + (long long)J.X * o] = J.at[J.n_t + idx];
+  }
+}
+
+template <bool C>
+__global__ void __launch_bounds__(256) k_thin_gram(const ThinJob* __restrict__ jobs) {
+  const ThinJob J = jobs[blockIdx.x];
+  const int X = J.X, n = J.n;
+  const long long rn = (long long)X * n;
+  for (int idx = threadIdx.x; idx < X * X; idx += blockDim.x) {
+    const int i = idx % X, ip = idx / X;
+    double ar = 0.0, ai = 0.0;
+    for (int o = 0; o < n; ++o) {
+      const double xr = J.R[i + (long long)X * o], yr = J.R[ip + (long long)X * o];
+      if (C) {
+        const double xi = J.R[rn + i + (long long)X * o], yi = J.R[rn + ip + (long long)X * o];
+        ar += xr * yr + xi * yi;  // x conj(y)
+        ai += xi * yr - xr * yi;
+      } else {
+        ar += xr * yr;
+      }
+    }
+    J.G[idx] = ar;
+    if (C) J.G[(long long)X * X + idx] = ai;
+  }
+}
+
+// R^+ = R^H G^-1,  G^-1 = conj(Gp Gp^H)
+template <bool C>
+__global__ void __launch_bounds__(256) k_thin_pinv(const ThinJob* __restrict__ jobs) {
+  extern __shared__ double sm[];  // [planes][X x X]: G^-1
+  __shared__ int s_ok;
+  const ThinJob J = jobs[blockIdx.x];
+  const int X = J.X, n = J.n, x2 = X * X;
+  if (threadIdx.x == 0) {
+    int ok = *J.okG;
+    for (int q = 0; q < J.n_env; ++q) ok = ok && J.ok_env[q];
+    s_ok = ok;
+  }
+  __syncthreads();
+  if (!s_ok) return;  // *J.ok stays 0: eigen route
+  double* Wr = sm;
+  double* Wi = sm + x2;
+  for (int idx = threadIdx.x; idx < x2; idx += blockDim.x) {
+    const int a = idx % X, b = idx / X;  // W[a, b] = sum_k Gp[a, k] conj(Gp[b, k]);  G^-1 = conj(W)
+    double wr = 0.0, wi = 0.0;
+    for (int k = 0; k < X; ++k) {
+      const double pr = J.Gp[a + X * k], qr = J.Gp[b + X * k];
+      if (C) {
+        const double pi = J.Gp[x2 + a + X * k], qi = J.Gp[x2 + b + X * k];
+        wr += pr * qr + pi * qi;
+        wi += pi * qr - pr * qi;
+      } else {
+        wr += pr * qr;
+      }
+    }
+    Wr[idx] = wr;
+    if (C) Wi[idx] = -wi;
+  }
+  __syncthreads();
+  const long long rn = (long long)X * n;
+  for (int idx = threadIdx.x; idx < n * X; idx += blockDim.x) {
+    const int o = idx % n, i = idx / n;
+    double ar = 0.0, ai = 0.0;
+    for (int k = 0; k < X; ++k) {  // sum_k conj(R[k, o]) Ginv[k, i]
+      const double xr = J.R[k + (long long)X * o], gr = Wr[k + X * i];
+      if (C) {
+        const double xi = -J.R[rn + k + (long long)X * o], gi = Wi[k + X * i];
+        ar += xr * gr - xi * gi;
+        ai += xr * gi + xi * gr;
+      } else {
+        ar += xr * gr;
+      }
+    }
+    J.Rp[o + (long long)n * i] = ar;
+    if (C) J.Rp[rn + o + (long long)n * i] = ai;
+  }
+  if (threadIdx.x == 0) *J.ok = 1;
+}
+
 // ---- shared-memory versions of the three glue kernels (one CTA per gate / gate side; operands staged once) ----------
 // The plain kernels above read every operand element from global memory once per output element; at 2048 gates per
 // layer they cost ~1 ms each although they move < 0.3 GB.  Selected when the operands of every gate of the batch fit.
@@ -1936,6 +2052,20 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   std::vector<SvdJob> ej_svd, gj, tj;
   std::vector<EigFnJob> ej_fn;
   std::vector<CholJob> chol_r, chol_env;
+  // thin sides (X < n): R = A x_j S_j from the Cholesky factors of the outer messages (see k_thin_R)
+  std::vector<ThinJob> thin;
+  std::vector<CholJob> thin_chol_env, thin_chol_G;
+  std::vector<ModeProdSpec> thin_specs;
+  std::vector<double*> thin_scratch;
+  size_t thin_flags_n = 0;
+  for (const Geo& g : geo)
+    if (g.role == OWNER)
+      for (int s = 0; s < 2; ++s)
+        if (g.loc[s] && g.r[s] < g.nn[s]) thin_flags_n += net->inc[g.v[s]].size() + 1;
+  DevBuf thin_flags(ctx, std::max<size_t>(thin_flags_n, 1) * sizeof(int));
+  CUDA_CHECK(cudaMemsetAsync(thin_flags.p, 0, std::max<size_t>(thin_flags_n, 1) * sizeof(int), ctx->stream));
+  size_t thin_flag_off = 0;
+  int thin_maxX = 1;
   std::vector<SuEdge> se(n_own);
   std::vector<HermJob> hj;
   std::vector<JobSpec> specs;
@@ -2021,6 +2151,57 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
         }
         envp += (size_t)P * c * c;
       }
+      if (E && g.r[s] < g.nn[s] && g.X[s] <= 64) {
+        bool ok = true;
+        for (int f : net->inc[v])
+          if (f != g.e) ok = ok && net->edim[f] <= 64;
+        if (ok) {
+          const int X = (int)g.X[s], nn = g.nn[s];
+          const size_t x2 = (size_t)X * X;
+          ModeProdSpec sp;
+          memset(&sp, 0, sizeof(sp));
+          sp.src = net->T[v].p;
+          sp.n = net->T[v].n;
+          sp.nm = (int)net->inc[v].size() + 1;
+          sp.dims[0] = net->sdim[v];
+          for (size_t j = 0; j < net->inc[v].size(); ++j) sp.dims[j + 1] = net->edim[net->inc[v][j]];
+          int* flags = thin_flags.as<int>() + thin_flag_off;
+          int n_env = 0;
+          for (size_t j = 0; j < net->inc[v].size(); ++j) {
+            const int f = net->inc[v][j];
+            if (f == g.e) continue;
+            const int c = net->edim[f];
+            double* fac = (double*)itn_dev_alloc(ctx, (size_t)2 * c * c * P * sizeof(double));  // R_j and its inverse
+            thin_scratch.push_back(fac);
+            thin_chol_env.push_back({overrides.back()[j], fac, fac + (size_t)c * c * P, flags + n_env, c, 0.0});
+            sp.mode[sp.nsteps] = (int)j + 1;
+            sp.mat[sp.nsteps] = fac;
+            sp.trans[sp.nsteps] = 1;  // S_j = R_j^T
+            sp.nsteps++;
+            ++n_env;
+          }
+          if (sp.nsteps > 0) {
+            sp.w0 = (double*)itn_dev_alloc(ctx, (size_t)sp.n * P * sizeof(double));
+            thin_scratch.push_back(sp.w0);
+          }
+          if (sp.nsteps > 1) {
+            sp.w1 = (double*)itn_dev_alloc(ctx, (size_t)sp.n * P * sizeof(double));
+            thin_scratch.push_back(sp.w1);
+          }
+          thin_specs.push_back(sp);
+          double* gb = (double*)itn_dev_alloc(ctx, 3 * x2 * P * sizeof(double));  // G, its Cholesky factor, the inverse factor
+          thin_scratch.push_back(gb);
+          int* okG = flags + n_env;
+          thin_chol_G.push_back({gb, gb + x2 * P, gb + 2 * x2 * P, okG, X, 0.0});
+          long long lo = g.d[s];
+          for (int j = 0; j < g.k[s]; ++j) lo *= net->edim[net->inc[v][j]];
+          ThinJob tj = {nullptr, net->T[v].n, E->R[s], E->Rp[s], gb, gb + 2 * x2 * P, okG, flags, n_env,
+                        rok.as<int>() + 2 * (size_t)g.oi + s, g.d[s], g.chi, X, nn, lo};
+          thin.push_back(tj);
+          thin_flag_off += (size_t)n_env + 1;
+          thin_maxX = std::max(thin_maxX, X);
+        }
+      }
       if (itn_fast_gate_site_ok(net, v)) {
         // degree 4, all bonds 16, d = 2: bond environment on the DMMA tile path
         fast_env.push_back({v, g.k[s], overrides.back().data(), Cm});
@@ -2079,6 +2260,38 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   }
   trace.mark("launch_env");
   // ---- 2. R factors (Cholesky; eigen route where r < n or C is rank deficient), environment support ----
+  if (!thin.empty()) {
+    run_chol(ctx, cplx, thin_chol_env);
+    std::vector<const double*> tres;
+    itn_run_modeprods(ctx, cplx, thin_specs, tres);
+    long long tmax = 0;
+    for (size_t q = 0; q < thin.size(); ++q) {
+      thin[q].at = tres[q];
+      tmax = std::max(tmax, thin[q].n_t);
+    }
+    DevBuf tb(ctx, thin.size() * sizeof(ThinJob));
+    const ThinJob* dt = itn_upload(ctx, thin, tb);
+    const unsigned nt = (unsigned)thin.size();
+    const unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((tmax + 1023) / 1024, 32));
+    if (cplx) k_thin_R<true><<<dim3(nt, gy), 256, 0, ctx->stream>>>(dt);
+    else k_thin_R<false><<<dim3(nt, gy), 256, 0, ctx->stream>>>(dt);
+    ITN_LAUNCH_CHECK(ctx);
+    if (cplx) k_thin_gram<true><<<nt, 256, 0, ctx->stream>>>(dt);
+    else k_thin_gram<false><<<nt, 256, 0, ctx->stream>>>(dt);
+    ITN_LAUNCH_CHECK(ctx);
+    run_chol(ctx, cplx, thin_chol_G);
+    const size_t psm = (size_t)P * thin_maxX * thin_maxX * sizeof(double);
+    if (cplx) {
+      CUDA_CHECK(cudaFuncSetAttribute(k_thin_pinv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+      k_thin_pinv<true><<<nt, 256, psm, ctx->stream>>>(dt);
+    } else {
+      CUDA_CHECK(cudaFuncSetAttribute(k_thin_pinv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+      k_thin_pinv<false><<<nt, 256, psm, ctx->stream>>>(dt);
+    }
+    ITN_LAUNCH_CHECK(ctx);
+    for (double* p : thin_scratch) itn_dev_free(ctx, p);  // stream ordered
+    thin_scratch.clear();
+  }
   run_chol(ctx, cplx, chol_r);
   run_jacobi(ctx, cplx, gj);
   run_chol(ctx, cplx, chol_env);

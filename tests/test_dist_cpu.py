@@ -200,3 +200,27 @@ def test_gate_exchange_two_ranks_gloo():
         p.join(timeout=60)
     for rank, ok in res:
         assert ok is True, (rank, ok)
+
+
+def test_inner_network_host_layout_matches_oracle():
+    """inner_network (host mirror): zero-padding of unequal bond dimensions and the operator layer fused into the ket
+    (src/inner.jl:139-171) agree with the oracle's restatement; no device call is involved."""
+    import numpy as np
+
+    import itn_b200 as E
+    from oracle import itn_oracle as O
+    g = O.random_tree_graph(7, seed=3)
+    phi = O.random_network(g, [2, 3, 2, 1, 2, 3], dtype=np.complex128, seed=1)
+    psi = O.random_network(g, [3, 2, 3, 2, 2, 1], dtype=np.complex128, seed=2)
+    rng = np.random.default_rng(0)
+    ops = [rng.standard_normal((2, 2) + (2,) * len(g.inc[v])) + 0j for v in range(g.nv)]
+    eg = E.NamedGraph(g.nv, g.edges)
+    ket, bra = E.inner_network(E.ITensorNetwork(eg, phi.tensors), E.ITensorNetwork(eg, psi.tensors), ops)
+    ref = O.bilinear_network(phi, O.apply_operator_network(O.Network(g, ops, np.complex128), psi))
+    for v in range(g.nv):
+        assert ket.tensors[v].shape == bra.tensors[v].shape == ref.tensors[v].shape
+        assert np.array_equal(ket.tensors[v], ref.tensors[v]) and np.array_equal(bra.tensors[v], ref.bra[v])
+    # BP on the tree (oracle) reproduces the brute-force <phi|A|psi>
+    msgs, _, _ = O.bp_update(ref, {}, seq=O.default_edge_sequence(g), maxiter=1)
+    exact = O.exact_inner_operator(phi, O.Network(g, ops, np.complex128), psi)
+    assert abs(O.scalar(ref, msgs) - exact) < 1e-10 * abs(exact)
