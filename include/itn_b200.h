@@ -190,6 +190,17 @@ int itn_apply_layers(itn_net* net, int nlayers, const int32_t* layer_ptr, const 
 int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, const void* host_in,
                     void* host_out, double cutoff);
 
+/* ---- generalised partitions ------------------------------------------------------------------ */
+
+/* Contraction of two host tensors over `npairs` axis pairs (numpy.tensordot convention: the result carries the free axes
+ * of a, then the free axes of b), column-major, on the device.  This is the `contract` of the tensors inside one
+ * multi-site partition (src/caches/abstractbeliefpropagationcache.jl:232-233 for partitioned_vertices with several sites
+ * per partition, test/test_expect.jl:22-39): the host merges the site tensors of a partition into one super-site tensor
+ * (fused site and bond indices) with it and hands the resulting network to itn_net_create; BP, scalars and expect then
+ * run on the existing kernels.  Small tensors, set-up work. */
+int itn_tensordot(itn_ctx* ctx, int dtype, const void* a_host, int nda, const int32_t* dims_a, const void* b_host, int ndb,
+                  const int32_t* dims_b, int npairs, const int32_t* axes_a, const int32_t* axes_b, void* out_host);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 
 /* Singular values (sorted descending, n per matrix) and optionally U*Sigma (columns in the kernel's internal order, not

@@ -681,7 +681,8 @@ extern "C" int itn_net_create(itn_ctx* ctx, int dtype, int nv, int ne, const int
     ITN_REQUIRE(net->owner[v] >= 0 && net->owner[v] < ctx->nranks, ITN_EINVAL,
                 "owner[v] must be a rank of the context (call itn_ctx_init_dist before itn_net_create)");
   net->inc.assign(nv, {});
-  for (int v = 0; v < nv; ++v) ITN_REQUIRE(sdim[v] >= 1 && sdim[v] <= 8, ITN_EUNSUPPORTED, "site dimension must be in 1..8");
+  // site dimensions above 8 are super-sites of multi-site partitions (fused site indices): BP, scalars and expect only
+  for (int v = 0; v < nv; ++v) ITN_REQUIRE(sdim[v] >= 1 && sdim[v] <= 64, ITN_EUNSUPPORTED, "site dimension must be in 1..64");
   for (int e = 0; e < ne; ++e) {
     int s = esrc[e], d = edst[e];
     ITN_REQUIRE(s >= 0 && s < nv && d >= 0 && d < nv && s != d, ITN_EINVAL, "edge endpoint out of range or self loop");
@@ -1984,6 +1985,7 @@ extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void*
   long long maxn = 0;
   for (int i = 0; i < n; ++i) {
     int v = verts[i], d = net->sdim[v];
+    ITN_REQUIRE(d <= 8, ITN_EUNSUPPORTED, "one-site gates support site dimensions up to 8");
     double* g = dg.as<double>() + off * P;
     upload_planar(net, (const char*)gates + off * P * sizeof(double), (long long)d * d, 1, g);
     jobs[i] = {net->T[v].p, net->T[v].n, g, d, normalize};
@@ -2005,5 +2007,123 @@ extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void*
   }
   for (int i = 0; i < n; ++i) net->touch(verts[i]);
   net->topo_version++;
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pairwise contraction of two host tensors on the device: the `contract` of the tensors inside one partition
+// (NDTensors contract called from src/caches/abstractbeliefpropagationcache.jl:232-233 on a multi-site partition).
+// The host mirror uses it to merge the site tensors of a partition into one super-site tensor (generalised
+// partitions); this is set-up work on small tensors, not a tuned kernel: one thread per output
+// element, a serial loop over the contracted multi-index.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DotSpec {
+  int nfa, nfb, nc;
+  int fa_dim[16], fb_dim[16], c_dim[16];
+  long long fa_str[16], fb_str[16], ca_str[16], cb_str[16];
+  long long nout, ncon;
+};
+
+template <bool C>
+__global__ void __launch_bounds__(256) k_tensordot(const double* __restrict__ a, const double* __restrict__ b,
+                                                   double* __restrict__ out, DotSpec S) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < S.nout; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx, oa = 0, ob = 0;
+    for (int q = 0; q < S.nfa; ++q) {
+      oa += (r % S.fa_dim[q]) * S.fa_str[q];
+      r /= S.fa_dim[q];
+    }
+    for (int q = 0; q < S.nfb; ++q) {
+      ob += (r % S.fb_dim[q]) * S.fb_str[q];
+      r /= S.fb_dim[q];
+    }
+    double accr = 0.0, acci = 0.0;
+    for (long long c = 0; c < S.ncon; ++c) {
+      long long rc = c, pa = oa, pb = ob;
+      for (int q = 0; q < S.nc; ++q) {
+        const long long k = rc % S.c_dim[q];
+        rc /= S.c_dim[q];
+        pa += k * S.ca_str[q];
+        pb += k * S.cb_str[q];
+      }
+      if (C) {
+        const double xr = a[2 * pa], xi = a[2 * pa + 1], yr = b[2 * pb], yi = b[2 * pb + 1];
+        accr += xr * yr - xi * yi;
+        acci += xr * yi + xi * yr;
+      } else {
+        accr += a[pa] * b[pb];
+      }
+    }
+    if (C) {
+      out[2 * idx] = accr;
+      out[2 * idx + 1] = acci;
+    } else {
+      out[idx] = accr;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int itn_tensordot(itn_ctx* ctx, int dtype, const void* a_host, int nda, const int32_t* dims_a, const void* b_host,
+                             int ndb, const int32_t* dims_b, int npairs, const int32_t* axes_a, const int32_t* axes_b,
+                             void* out_host) {
+  API_BEGIN
+  ITN_REQUIRE(ctx && a_host && b_host && out_host && dims_a && dims_b, ITN_EINVAL, "NULL argument");
+  ITN_REQUIRE(dtype == ITN_F64 || dtype == ITN_C128, ITN_EUNSUPPORTED, "dtype must be 0 (Float64) or 1 (ComplexF64)");
+  ITN_REQUIRE(nda >= 0 && ndb >= 0 && nda <= 16 && ndb <= 16 && npairs >= 0 && npairs <= nda && npairs <= ndb, ITN_EINVAL,
+              "bad tensor ranks");
+  ITN_REQUIRE(npairs == 0 || (axes_a && axes_b), ITN_EINVAL, "NULL argument");
+  set_device(ctx);
+  DotSpec S;
+  memset(&S, 0, sizeof(S));
+  std::vector<long long> sa(nda), sb(ndb);
+  long long na = 1, nb = 1;
+  for (int i = 0; i < nda; ++i) {
+    ITN_REQUIRE(dims_a[i] >= 1, ITN_ESHAPE, "extents must be positive");
+    sa[i] = na;
+    na *= dims_a[i];
+  }
+  for (int i = 0; i < ndb; ++i) {
+    ITN_REQUIRE(dims_b[i] >= 1, ITN_ESHAPE, "extents must be positive");
+    sb[i] = nb;
+    nb *= dims_b[i];
+  }
+  std::vector<char> ca(nda, 0), cb(ndb, 0);
+  S.ncon = 1;
+  for (int q = 0; q < npairs; ++q) {
+    const int x = axes_a[q], y = axes_b[q];
+    ITN_REQUIRE(x >= 0 && x < nda && y >= 0 && y < ndb && !ca[x] && !cb[y], ITN_EINVAL, "bad contraction axes");
+    ITN_REQUIRE(dims_a[x] == dims_b[y], ITN_ESHAPE, "contracted extents differ");
+    ca[x] = cb[y] = 1;
+    S.c_dim[q] = dims_a[x];
+    S.ca_str[q] = sa[x];
+    S.cb_str[q] = sb[y];
+    S.ncon *= dims_a[x];
+  }
+  S.nc = npairs;
+  S.nout = 1;
+  for (int i = 0; i < nda; ++i)
+    if (!ca[i]) {
+      S.fa_dim[S.nfa] = dims_a[i];
+      S.fa_str[S.nfa++] = sa[i];
+      S.nout *= dims_a[i];
+    }
+  for (int i = 0; i < ndb; ++i)
+    if (!cb[i]) {
+      S.fb_dim[S.nfb] = dims_b[i];
+      S.fb_str[S.nfb++] = sb[i];
+      S.nout *= dims_b[i];
+    }
+  const size_t item = (dtype == ITN_C128 ? 2 : 1) * sizeof(double);
+  DevBuf da(ctx, (size_t)na * item), db(ctx, (size_t)nb * item), dout(ctx, (size_t)S.nout * item);
+  CUDA_CHECK(cudaMemcpyAsync(da.p, a_host, (size_t)na * item, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(db.p, b_host, (size_t)nb * item, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((S.nout + 255) / 256, 148 * 8));
+  if (dtype == ITN_C128) k_tensordot<true><<<grid, 256, 0, ctx->stream>>>(da.as<double>(), db.as<double>(), dout.as<double>(), S);
+  else k_tensordot<false><<<grid, 256, 0, ctx->stream>>>(da.as<double>(), db.as<double>(), dout.as<double>(), S);
+  ITN_LAUNCH_CHECK(ctx);
+  CUDA_CHECK(cudaMemcpyAsync(out_host, dout.p, (size_t)S.nout * item, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   API_END
 }

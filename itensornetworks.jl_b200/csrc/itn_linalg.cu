@@ -1926,7 +1926,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       g.X[s] = net->tensor_elems(v) / g.nn[s];
       g.r[s] = (int)std::min<long long>(g.X[s], g.nn[s]);
       g.loc[s] = itn_is_local(net, v);
-      ITN_REQUIRE(g.nn[s] <= 256, ITN_EUNSUPPORTED, "simple update supports d*chi <= 256");
+      ITN_REQUIRE(g.nn[s] <= 256 && g.d[s] <= 8, ITN_EUNSUPPORTED, "simple update supports d <= 8 and d*chi <= 256");
     }
     g.m = g.r[0] * g.d[0];
     g.nc = g.r[1] * g.d[1];

@@ -8,3 +8,4 @@ from .graphs import (NamedGraph, default_edge_sequence, edge_coloring, forest_co
                      named_comb_tree, named_grid, named_path_graph, parallel_edge_sequence)
 from .network import ITensorNetwork, productstate, random_tensornetwork
 from .dist import directed_id, gate_exchange_plan, halo_bytes_per_sweep, halo_plan, init_distributed, partition_vertices
+from .partitions import PartitionMap, partition_plan, partitioned_network, tensordot

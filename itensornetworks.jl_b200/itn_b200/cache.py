@@ -77,7 +77,7 @@ class BeliefPropagationCache:
     """BP cache of <psi|psi> with the default one-site partition; state lives on the device."""
 
     def __init__(self, psi: ITensorNetwork = None, ctx: Context = None, messages="identity", owner=None, dist=None,
-                 defer_upload=False, bra: ITensorNetwork = None, _handle=None, _like=None):
+                 defer_upload=False, bra: ITensorNetwork = None, partitioned_vertices=None, _handle=None, _like=None):
         if _handle is not None:  # clone
             self.ctx, self.graph, self.dtype, self.h = _like.ctx, _like.graph, _like.dtype, _handle
             self.eltype = _like.eltype
@@ -86,8 +86,17 @@ class BeliefPropagationCache:
             self.owner, self.rank = _like.owner, _like.rank
             self.bilinear = getattr(_like, "bilinear", False)
             self._edims = None if _like._edims is None else list(_like._edims)
+            self.partition = _like.partition
             return
         self.ctx = ctx or default_context()
+        # partitioned_vertices (src/caches/beliefpropagationcache.jl:20-35): several sites per partition.  The sites of a
+        # partition are merged into one super-site (device contractions, partitions.py); everything below then sees the
+        # super-site network, self.partition maps original vertices to (partition, position).
+        self.partition = None
+        if partitioned_vertices is not None and any(len(grp) > 1 for grp in partitioned_vertices):
+            from .partitions import partitioned_network
+            assert bra is None and owner is None, "multi-site partitions: single GPU, quadratic form"
+            psi, self.partition = partitioned_network(psi, partitioned_vertices, self.ctx)
         self.graph = psi.graph
         self.eltype = np.dtype(psi.dtype)      # what the caller sees
         self.dtype = _COMPUTE[self.eltype]     # what the device computes in
@@ -314,6 +323,8 @@ def environment(bpc, verts):
     """environment(bpc, verts) for whole-site vertex sets: the incoming messages on the boundary
     of `verts` (edges inside the set are excluded).  Returns [((u, v), M_{u->v}), ...]."""
     vs = set(int(v) for v in verts)
+    if bpc.partition is not None:  # messages into the partitions that contain `verts` (fused bond indices)
+        vs = set(bpc.partition.group_of[v] for v in vs)
     out = []
     for v in sorted(vs):
         for e in bpc.graph.inc[v]:
@@ -365,13 +376,13 @@ def rescale(bpc, inplace=False):
     return out
 
 
-def _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx=None):
+def _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx=None, cache_construction_kwargs=None):
     """The `cache!` / `update_cache` / `cache_update_kwargs` protocol (src/expect.jl:21-41)."""
     if isinstance(psi, BeliefPropagationCache):
         cache, psi = psi, None
         update_cache = False if update_cache is None else update_cache
     if cache is None:
-        cache = BeliefPropagationCache(psi, ctx=ctx, messages="default")
+        cache = BeliefPropagationCache(psi, ctx=ctx, messages="default", **(cache_construction_kwargs or {}))
         update_cache = True if update_cache is None else update_cache
     elif update_cache is None:
         update_cache = False
@@ -471,15 +482,31 @@ def op(name, dtype=np.complex128):
     return m.astype(dtype)
 
 
-def expect(psi, operator, vertices=None, alg="bp", cache=None, update_cache=None, cache_update_kwargs=None, ctx=None):
-    """expect(psi, op, vertices; alg="bp", cache!, update_cache, cache_update_kwargs) (src/expect.jl:58-109).
+def expect(psi, operator, vertices=None, alg="bp", cache=None, update_cache=None, cache_update_kwargs=None, ctx=None,
+           cache_construction_kwargs=None):
+    """expect(psi, op, vertices; alg="bp", cache!, update_cache, cache_update_kwargs, cache_construction_kwargs)
+    (src/expect.jl:58-109); cache_construction_kwargs = {"partitioned_vertices": [[v, ...], ...]} groups several sites
+    per BP partition (test/test_expect.jl:22-39).
 
     `operator` is a name ("Sz", "Z", ...) or a d x d matrix O[s_out, s_in]. Returns {vertex: value}."""
     assert alg == "bp", "only alg=\"bp\" runs on the engine"
-    cache = _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx)
+    cache = _cache_for(psi, cache, update_cache, cache_update_kwargs, ctx, cache_construction_kwargs)
+    o = op(operator, cache.dtype) if isinstance(operator, str) else np.asarray(operator, dtype=cache.dtype)
+    if cache.partition is not None:
+        # the operator acts on one factor of the fused site index of its partition
+        pm = cache.partition
+        if vertices is None:
+            vertices = sorted(pm.group_of)
+        vertices = [int(v) for v in vertices]
+        packed = [np.asfortranarray(pm.lift_operator(v, o).astype(cache.dtype)).ravel(order="F") for v in vertices]
+        ops = np.ascontiguousarray(np.concatenate(packed)) if packed else np.zeros(0, dtype=cache.dtype)
+        out = np.empty(len(vertices), dtype=cache.dtype)
+        _, pv = i32([pm.group_of[v] for v in vertices])
+        check(lib().itn_expect1(cache.h, pv, len(vertices), ops.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        out = out.astype(cache.eltype, copy=False)
+        return {v: out[i] for i, v in enumerate(vertices)}
     if vertices is None:
         vertices = list(range(cache.graph.nv))
-    o = op(operator, cache.dtype) if isinstance(operator, str) else np.asarray(operator, dtype=cache.dtype)
     ops = np.stack([np.asfortranarray(o).ravel(order="F")] * len(vertices)) if len(vertices) else np.zeros((0, 4))
     ops = np.ascontiguousarray(ops, dtype=cache.dtype)
     out = np.empty(len(vertices), dtype=cache.dtype)
@@ -521,6 +548,9 @@ def apply(gate, bpc, verts, maxdim=None, cutoff=None, normalize=False, callback=
     """apply(o, psi; envs, maxdim, cutoff, normalize, callback) (src/apply.jl:97-146) on a BP cache:
     the product environment is the cache's current messages.  `verts` = (v,) or (v1, v2)."""
     verts = tuple(int(v) for v in verts)
+    if bpc.partition is not None:
+        raise ITNError(1, "`apply` requires a product environment (`envs` with no shared edges); the cache groups several "
+                          "sites per partition. Contract `envs` to product form before calling.")
     out = bpc if inplace else bpc.copy()
     if len(verts) == 1:
         g = np.asfortranarray(np.asarray(gate, dtype=bpc.dtype))

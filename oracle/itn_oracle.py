@@ -735,6 +735,51 @@ def exact_inner_operator(phi: Network, op: Network, psi: Network):
     return np.vdot(_state_vector(phi), apsi)
 
 
+def partition_network(net: Network, groups):
+    """Super-site network of `net` for a partition of its vertices into `groups` (partitioned_vertices of
+    BeliefPropagationCache, src/caches/beliefpropagationcache.jl:20-35; column grouping in test/test_expect.jl:22-39).
+    One einsum per partition: internal edges are summed, the site indices of the members fuse into one site index
+    (first member fastest) and the edges to each neighbouring partition fuse into one bond (ascending edge id, first
+    fastest).  Returns (Network on the quotient graph, group_of)."""
+    import string
+    g = net.graph
+    group_of = {int(v): gi for gi, grp in enumerate(groups) for v in grp}
+    bundles = {}
+    for e, (u, v) in enumerate(g.edges):
+        a, b = group_of[u], group_of[v]
+        if a != b:
+            bundles.setdefault((min(a, b), max(a, b)), []).append(e)
+    qedges = sorted(bundles)
+    qg = Graph(len(groups), qedges)
+    tensors = []
+    for gi, grp in enumerate(groups):
+        letters = iter(string.ascii_letters)
+        site = {v: next(letters) for v in grp}
+        bond = {}
+        for v in grp:
+            for e in g.inc[v]:
+                if e not in bond:
+                    bond[e] = next(letters)
+        subs = [site[v] + "".join(bond[e] for e in g.inc[v]) for v in grp]
+        out = "".join(site[v] for v in grp)
+        shape = [int(np.prod([net.tensors[v].shape[0] for v in grp]))]
+        for qe in qg.inc[gi]:
+            es = bundles[qedges[qe]]
+            out += "".join(bond[e] for e in es)
+            shape.append(int(np.prod([net.edge_dim(e) for e in es])))
+        t = np.einsum(",".join(subs) + "->" + out, *[net.tensors[v] for v in grp])
+        tensors.append(np.ascontiguousarray(t.reshape(shape, order="F")))
+    return Network(qg, tensors, net.dtype), group_of
+
+
+def lift_operator(site_dims, pos, o):
+    """Operator on member `pos` of a partition as an operator on the fused site index (first member fastest)."""
+    out = np.ones((1, 1), dtype=np.asarray(o).dtype)
+    for q, d in enumerate(site_dims):
+        out = np.kron(np.asarray(o) if q == pos else np.eye(d), out)
+    return out
+
+
 def exact_inner(phi: Network, psi: Network):
     """<phi|psi> by brute force (inner(phi, psi; alg = "exact"), src/inner.jl:60-75)."""
     return np.vdot(_state_vector(phi), _state_vector(psi))

@@ -232,3 +232,22 @@ def test_bilinear_with_equal_layers_is_the_quadratic_form():
     both = O.bilinear_network(psi, psi)
     m_b, _, _ = O.bp_update(both, O.identity_messages(both), seq=seq, groups=O.synchronous_groups(seq), maxiter=4)
     assert max(np.abs(m_q[k] - m_b[k]).max() for k in m_q) < 1e-14
+
+
+# ---- multi-site partitions: test/test_expect.jl:22-39 (group by column to make BP exact) ----
+@pytest.mark.parametrize("dims", [(2, 2), (3, 3), (3, 2)])
+def test_column_partition_makes_bp_exact(dims):
+    g = O.grid_graph(dims)
+    net = O.random_network(g, 2, dtype=np.complex128, seed=1234)
+    cols = {}
+    for v, c in enumerate(g.coords):
+        cols.setdefault(c[0], []).append(v)
+    groups = [cols[k] for k in sorted(cols)]
+    coarse, group_of = O.partition_network(net, groups)
+    assert coarse.graph.is_tree()
+    msgs, _, _ = O.bp_update(coarse, {}, seq=O.default_edge_sequence(coarse.graph), maxiter=1)
+    sz = 0.5 * O.PAULI_Z
+    for v in range(g.nv):
+        gi = group_of[v]
+        lifted = O.lift_operator([2] * len(groups[gi]), groups[gi].index(v), sz)
+        assert abs(O.expect1(coarse, msgs, gi, lifted) - O.exact_expect1(net, v, sz)) < 1e-12
