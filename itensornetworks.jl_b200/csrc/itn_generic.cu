@@ -15,6 +15,7 @@
 // Storage is planar (re plane, im plane).  These kernels are the shape-agnostic path and the on-GPU
 // second opinion for the DMMA fast path (itn_fast.cu); FP64 FMA pipe, not tensor cores.
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <functional>
 
@@ -402,6 +403,7 @@ struct GrOp {
   double* out;  // planar chi x chi
   long long L, R;
   int chi;
+  double* part;  // gridDim.y > 1: gridDim.y partial results (planar chi x chi each), summed in order by k_gr_reduce
 };
 
 template <bool C>
@@ -506,10 +508,15 @@ __global__ void __launch_bounds__(kThreads) k_gr_mma(const GrOp* __restrict__ op
   const int T = mt * mt;
   const int S = (T >= nwarps) ? 1 : (nwarps / T);
   const int n2 = No * No, p2 = No16 * No16;
+  // small graphs: the closed index range is also split across gridDim.y CTAs (partials, fixed-order reduction)
+  const int Y = gridDim.y, yb = blockIdx.y;
+  const long long Xlo = (X * yb / Y) & ~7ll, Xhi = (yb == Y - 1) ? X : ((X * (yb + 1) / Y) & ~7ll);
+  const long long Xc = Xhi - Xlo;
+  if (Y > 1) out = J.part + (size_t)yb * (C ? 2 : 1) * n2;
   for (int item = warp; item < T * S; item += nwarps) {
     const int tile = item / S, split = item % S;
     const int o0 = (tile % mt) * 16, p0 = (tile / mt) * 16;
-    const long long xlo = (X * split / S) & ~7ll, xhi = (split == S - 1) ? X : ((X * (split + 1) / S) & ~7ll);
+    const long long xlo = Xlo + ((Xc * split / S) & ~7ll), xhi = (split == S - 1) ? Xhi : (Xlo + ((Xc * (split + 1) / S) & ~7ll));
     double cr[2][4], ci[2][4];
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb)
@@ -576,6 +583,18 @@ __global__ void __launch_bounds__(kThreads) k_gr_mma(const GrOp* __restrict__ op
     }
     out[oi] = vr;
     if (C) out[n2 + oi] = vi;
+  }
+}
+
+// out = sum over the Y partials of an operation, in index order
+template <bool C>
+__global__ void __launch_bounds__(256) k_gr_reduce(const GrOp* __restrict__ ops, int Y) {
+  const GrOp J = ops[blockIdx.x];
+  const int tot = (C ? 2 : 1) * J.chi * J.chi;
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    double acc = 0.0;
+    for (int y = 0; y < Y; ++y) acc += J.part[(size_t)y * tot + i];
+    J.out[i] = acc;
   }
 }
 
@@ -1028,6 +1047,32 @@ void itn_run_vertex_sweeps(itn_net* net, const std::vector<SweepSpec>& specs) {
       if (msm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_mp_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
       if (gsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_gr_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
     }
+    // rounds with few closes (small graphs: heavy-hex has 127 vertices) split the closed index range of every close
+    // over Y CTAs so that the launch covers the SMs; partial results are summed in a fixed order
+    std::vector<int> ysplit(gr_rounds.size(), 1);
+    size_t part_doubles = 0;
+    for (size_t r = 0; r < gr_rounds.size(); ++r) {
+      const size_t ng = gr_rounds[r].size();
+      if (ng == 0 || ng >= 148) continue;
+      long long xmin = LLONG_MAX;
+      for (const GrOp& op : gr_rounds[r]) xmin = std::min(xmin, op.L * op.R);
+      const int y = (int)std::min<long long>(std::min<long long>(8, 296 / (long long)ng), xmin / 512);
+      if (y < 2) continue;
+      ysplit[r] = y;
+      for (const GrOp& op : gr_rounds[r]) part_doubles += (size_t)y * P * op.chi * op.chi;
+    }
+    DevBuf partb(ctx, std::max<size_t>(part_doubles, 1) * sizeof(double));
+    {
+      double* pp = partb.as<double>();
+      for (size_t r = 0; r < gr_rounds.size(); ++r)
+        for (GrOp& op : gr_rounds[r]) {
+          op.part = nullptr;
+          if (ysplit[r] > 1) {
+            op.part = pp;
+            pp += (size_t)ysplit[r] * P * op.chi * op.chi;
+          }
+        }
+    }
     // one upload for all operation tables
     size_t nmp = 0, ngr = 0;
     for (auto& r : mp_rounds) nmp += r.size();
@@ -1053,9 +1098,15 @@ void itn_run_vertex_sweeps(itn_net* net, const std::vector<SweepSpec>& specs) {
         mo += nm;
       }
       if (ng) {
-        if (net->cplx) k_gr_mma<true><<<ng, kThreads, gsm, ctx->stream>>>(dgr + go);
-        else k_gr_mma<false><<<ng, kThreads, gsm, ctx->stream>>>(dgr + go);
+        const unsigned Y = (unsigned)ysplit[r];
+        if (net->cplx) k_gr_mma<true><<<dim3(ng, Y), kThreads, gsm, ctx->stream>>>(dgr + go);
+        else k_gr_mma<false><<<dim3(ng, Y), kThreads, gsm, ctx->stream>>>(dgr + go);
         ITN_LAUNCH_CHECK(ctx);
+        if (Y > 1) {
+          if (net->cplx) k_gr_reduce<true><<<ng, 256, 0, ctx->stream>>>(dgr + go, (int)Y);
+          else k_gr_reduce<false><<<ng, 256, 0, ctx->stream>>>(dgr + go, (int)Y);
+          ITN_LAUNCH_CHECK(ctx);
+        }
         go += ng;
       }
     }
