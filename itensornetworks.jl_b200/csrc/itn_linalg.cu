@@ -1184,6 +1184,11 @@ struct SuEdge {
   double* tsig;
   int* tperm;
   int newdim;             // filled on the host after truncation
+  // wide theta' (m < n columns): the Jacobi kernel decomposes theta'^H (n x m, no null columns); tt0 = theta'^H,
+  // tt = theta'^H U = V Sigma (columns in the kernel's order); k_su_urec turns them into theta (U Sigma) and tv (V)
+  double* tt0;
+  double* tt;
+  int transposed;
 };
 
 // R[i, o] = sqrt(lambda_i) V[o, i];  R^+[o, i] = conj(V[o, i]) / sqrt(lambda_i)   (C = V L V^H = conj(A~^H A~))
@@ -1256,6 +1261,7 @@ __global__ void __launch_bounds__(256) k_su_theta(const SuEdge* __restrict__ edg
 template <bool C>
 __global__ void __launch_bounds__(256) k_su_vrec(const SuEdge* __restrict__ edges) {
   const SuEdge E = edges[blockIdx.x];
+  if (E.transposed) return;  // k_su_urec
   const int m = E.r[0] * E.d[0], nc = E.r[1] * E.d[1], nd = E.newdim;
   const long long mn = (long long)m * nc, nn = (long long)nc * nc;
   for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < nc * nd; idx += gridDim.y * blockDim.x) {
@@ -1276,6 +1282,55 @@ __global__ void __launch_bounds__(256) k_su_vrec(const SuEdge* __restrict__ edge
     }
     E.tv[j + (long long)nc * col] = f * accr;
     if (C) E.tv[nn + j + (long long)nc * col] = f * acci;
+  }
+}
+
+// wide theta': tt0 = theta'^H (conjugate transpose, n x m)
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_transpose(const SuEdge* __restrict__ edges) {
+  const SuEdge E = edges[blockIdx.x];
+  if (!E.transposed) return;
+  const int m = E.r[0] * E.d[0], nc = E.r[1] * E.d[1];
+  const long long mn = (long long)m * nc;
+  for (long long idx = (long long)blockIdx.y * blockDim.x + threadIdx.x; idx < mn; idx += (long long)gridDim.y * blockDim.x) {
+    const int i = (int)(idx % m), j = (int)(idx / m);
+    E.tt0[j + (long long)nc * i] = E.theta0[idx];
+    if (C) E.tt0[mn + j + (long long)nc * i] = -E.theta0[mn + idx];
+  }
+}
+
+// wide theta' after the decomposition of theta'^H:  V[:, col] = tt[:, col] / sigma,  (U Sigma)[:, col] = theta' V[:, col]
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_urec(const SuEdge* __restrict__ edges) {
+  const SuEdge E = edges[blockIdx.x];
+  if (!E.transposed) return;
+  const int m = E.r[0] * E.d[0], nc = E.r[1] * E.d[1], nd = E.newdim;
+  const long long mn = (long long)m * nc, nn = (long long)nc * nc;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < (m + nc) * nd; idx += gridDim.y * blockDim.x) {
+    const int lp = idx / (m + nc), q = idx % (m + nc);
+    const int col = E.tperm[lp];
+    const double sig = E.tsig[lp];
+    const double f = sig > 0.0 ? 1.0 / sig : 0.0;
+    if (q < nc) {  // V
+      const int j = q;
+      E.tv[j + (long long)nc * col] = f * E.tt[j + (long long)nc * col];
+      if (C) E.tv[nn + j + (long long)nc * col] = f * E.tt[mn + j + (long long)nc * col];
+    } else {       // U Sigma
+      const int i = q - nc;
+      double accr = 0.0, acci = 0.0;
+      for (int j = 0; j < nc; ++j) {
+        const double ar = E.theta0[i + (long long)m * j], wr = E.tt[j + (long long)nc * col];
+        if (C) {
+          const double ai = E.theta0[mn + i + (long long)m * j], wi = E.tt[mn + j + (long long)nc * col];
+          accr += ar * wr - ai * wi;
+          acci += ar * wi + ai * wr;
+        } else {
+          accr += ar * wr;
+        }
+      }
+      E.theta[i + (long long)m * col] = f * accr;
+      if (C) E.theta[mn + i + (long long)m * col] = f * acci;
+    }
   }
 }
 
@@ -1518,6 +1573,7 @@ template <bool C>
 __global__ void __launch_bounds__(256) k_su_vrec_s(const SuEdge* __restrict__ edges) {
   extern __shared__ double sm[];
   const SuEdge E = edges[blockIdx.x];
+  if (E.transposed) return;  // k_su_urec
   const int m = E.r[0] * E.d[0], nc = E.r[1] * E.d[1], nd = E.newdim;
   const long long mn = (long long)m * nc, nn = (long long)nc * nc;
   constexpr int P = C ? 2 : 1;
@@ -1992,7 +2048,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
           }
     }
     if (g.role == OWNER) {
-      ws_doubles += (size_t)P * (2 * (size_t)g.m * g.nc + (size_t)g.nc * g.nc);
+      ws_doubles += (size_t)P * (4 * (size_t)g.m * g.nc + (size_t)g.nc * g.nc);  // theta0, theta, (tt0, tt), tv
       sig_total += g.nc;
     }
   }
@@ -2075,6 +2131,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   std::vector<char> fast_site(2 * (size_t)n, 0);
   std::vector<SuTrunc> tr(n_own);
   std::vector<double*> guestT(n, nullptr);  // guest gates: where the owner's T factor arrives
+  bool any_transposed = false;
   double* w = ws.as<double>();
   double* envp = envs.as<double>();
   size_t env_sig_off = 0;
@@ -2222,8 +2279,14 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     E->tv = w; w += (size_t)P * g.nc * g.nc;
     E->tsig = sp;
     E->tperm = pp;
+    E->tt0 = w; w += (size_t)P * g.m * g.nc;
+    E->tt = w; w += (size_t)P * g.m * g.nc;
+    // wide theta' (every heavy-hex edge whose esrc is the degree-2 site): decompose theta'^H, which has no null columns
+    E->transposed = (g.m < g.nc && g.nc <= 128 && g.m <= 64) ? 1 : 0;
+    any_transposed = any_transposed || E->transposed;
     {
       SvdJob tjob = {E->theta0, nullptr, sp, pp, g.m, g.nc, E->theta, nullptr};
+      if (E->transposed) tjob = {E->tt0, nullptr, sp, pp, g.nc, g.m, E->tt, nullptr};
       tj.push_back(tjob);
     }
     sp += g.nc;
@@ -2260,8 +2323,15 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   }
   trace.mark("launch_env");
   // ---- 2. R factors (Cholesky; eigen route where r < n or C is rank deficient), environment support ----
+  {
+    // the three independent Cholesky batches (outer messages of thin sides, full-rank bond environments, support tests)
+    // in one launch
+    std::vector<CholJob> all(thin_chol_env);
+    all.insert(all.end(), chol_r.begin(), chol_r.end());
+    all.insert(all.end(), chol_env.begin(), chol_env.end());
+    run_chol(ctx, cplx, all);
+  }
   if (!thin.empty()) {
-    run_chol(ctx, cplx, thin_chol_env);
     std::vector<const double*> tres;
     itn_run_modeprods(ctx, cplx, thin_specs, tres);
     long long tmax = 0;
@@ -2292,9 +2362,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     for (double* p : thin_scratch) itn_dev_free(ctx, p);  // stream ordered
     thin_scratch.clear();
   }
-  run_chol(ctx, cplx, chol_r);
   run_jacobi(ctx, cplx, gj);
-  run_chol(ctx, cplx, chol_env);
   if (!ej_svd.empty()) {
     // projector onto the support of every environment: eigenvalues below 10 eps (relative) are dropped, as in
     // map_eigvals(sqrt / inv o sqrt, env; cutoff = 10 eps) (apply.jl:36,40-69)
@@ -2339,6 +2407,11 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       else k_su_theta<false><<<dim3(n_own, 8), 256, 0, ctx->stream>>>(dse);
     }
     ITN_LAUNCH_CHECK(ctx);
+    if (any_transposed) {
+      if (cplx) k_su_transpose<true><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+      else k_su_transpose<false><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+      ITN_LAUNCH_CHECK(ctx);
+    }
     run_jacobi(ctx, cplx, tj);
     DevBuf trb(ctx, tr.size() * sizeof(SuTrunc));
     const SuTrunc* dtr = itn_upload(ctx, tr, trb);
@@ -2417,6 +2490,11 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       else k_su_vrec<false><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
     }
     ITN_LAUNCH_CHECK(ctx);
+    if (any_transposed) {
+      if (cplx) k_su_urec<true><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+      else k_su_urec<false><<<dim3(n_own, 4), 256, 0, ctx->stream>>>(dse);
+      ITN_LAUNCH_CHECK(ctx);
+    }
     if (T_smem <= kGlueSmemMax) {
       if (cplx) {
         CUDA_CHECK(cudaFuncSetAttribute(k_su_T_s<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_smem));
