@@ -760,7 +760,7 @@ void launch_jacobi64(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int maxn) {
   ITN_LAUNCH_CHECK(ctx);
 }
 
-int g_jacobi_variant = 0;  // 0 = auto, 1 = generic kernel only, 2 = round-robin k_jacobi64 (itn_svd_batch's second opinions)
+thread_local int g_jacobi_variant = 0;  // 0 = auto, 1 = generic kernel only, 2 = round-robin k_jacobi64 (itn_svd_batch's second opinions)
 
 void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
   if (jobs.empty()) return;
