@@ -1996,7 +1996,8 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     g.oi = g.role == OWNER ? n_own++ : -1;
   }
   ITN_REQUIRE(!svals_out || svals_stride >= 1, ITN_EINVAL, "svals_stride must be positive");
-  const int stride = std::max(max_cand, 1);
+  // result row of a gate: kept dimension, truncation error, kept singular values (never more than maxdim of them)
+  const int stride = std::max(maxdim > 0 ? std::min(max_cand, maxdim) : max_cand, 1);
   const int RS = 2 + stride;  // doubles per result row
   // ---- communication segments of the cut edges (same gate order on both ranks) ----
   struct Seg {
