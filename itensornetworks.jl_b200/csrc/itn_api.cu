@@ -990,9 +990,16 @@ void upload_pipelined(itn_net* net, const std::vector<PendingUpload>& items, con
         continue;
       }
       if (c >= 2) CUDA_CHECK(cudaStreamWaitEvent(cs, imported[k], 0));
-      for (size_t i = lo; i < hi; ++i)
-        CUDA_CHECK(cudaMemcpyAsync((void*)jobs[i].src, items[i].host, (size_t)jobs[i].n * P * sizeof(double),
-                                   cudaMemcpyHostToDevice, cs));
+      // tensors that follow each other in host memory (one big pinned buffer in vertex order is the common case) land
+      // next to each other in the slot too: one copy per contiguous run instead of one per tensor
+      for (size_t i = lo; i < hi;) {
+        size_t bytes = (size_t)jobs[i].n * P * sizeof(double), j = i + 1;
+        while (j < hi && (const char*)items[j].host == (const char*)items[i].host + bytes &&
+               (const char*)jobs[j].src == (const char*)jobs[i].src + bytes)
+          bytes += (size_t)jobs[j++].n * P * sizeof(double);
+        CUDA_CHECK(cudaMemcpyAsync((void*)jobs[i].src, items[i].host, bytes, cudaMemcpyHostToDevice, cs));
+        i = j;
+      }
       CUDA_CHECK(cudaEventRecord(copied[k], cs));
       CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, copied[k], 0));
       dim3 grid((unsigned)(hi - lo), gy);
