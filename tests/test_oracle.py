@@ -251,3 +251,51 @@ def test_column_partition_makes_bp_exact(dims):
         gi = group_of[v]
         lifted = O.lift_operator([2] * len(groups[gi]), groups[gi].index(v), sz)
         assert abs(O.expect1(coarse, msgs, gi, lifted) - O.exact_expect1(net, v, sz)) < 1e-12
+
+
+# ---- test/test_forms.jl:62-75: on a tree the BP environment of a site equals the exact one ----
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_bp_environment_of_a_site_is_exact_on_a_tree(dtype):
+    import string
+    g = O.grid_graph((1, 4))  # the 1 x 4 chain of test_forms.jl
+    net = O.random_network(g, [2, 3, 2], dtype=dtype, seed=1234)
+    msgs, _, _ = O.bp_update(net, {}, seq=O.default_edge_sequence(g), maxiter=1)
+    v = 1
+    # exact environment of v in <psi|psi>: every other ket and bra tensor contracted, the bonds of v left open
+    letters = iter(string.ascii_letters)
+    site = [next(letters) for _ in range(g.nv)]
+    kb = [next(letters) for _ in range(g.ne)]
+    bb = [next(letters) for _ in range(g.ne)]
+    ops, subs = [], []
+    for u in range(g.nv):
+        if u == v:
+            continue
+        ops += [net.tensors[u], net.tensors[u].conj()]
+        subs += [site[u] + "".join(kb[e] for e in g.inc[u]), site[u] + "".join(bb[e] for e in g.inc[u])]
+    out = "".join(kb[e] + bb[e] for e in g.inc[v])
+    exact = np.einsum(",".join(subs) + "->" + out, *ops)
+    # BP environment = outer product of the incoming messages M_{u->v}[a, a']
+    bp = np.ones(())
+    for e in g.inc[v]:
+        bp = np.multiply.outer(bp, msgs[(g.other(e, v), v)])
+    exact = exact / np.linalg.norm(exact)
+    bp = bp / np.linalg.norm(bp)
+    phase = np.vdot(bp, exact)  # BP messages are normalised individually: compare up to one scalar
+    assert abs(abs(phase) - 1) < 1e-12 and np.linalg.norm(exact - phase * bp) < 1e-12
+
+
+def test_partition_plan_quotient_graph():
+    # host bookkeeping of multi-site partitions: a 3 x 3 grid grouped by column is a 3-vertex chain whose bonds fuse
+    # the three horizontal edges between neighbouring columns (ascending edge id on both sides)
+    import itn_b200 as E
+    g = E.named_grid((3, 3))
+    cols = {}
+    for v, c in enumerate(g.names):
+        cols.setdefault(c[0], []).append(v)
+    groups = [cols[k] for k in sorted(cols)]
+    group_of, qedges, bundles = E.partition_plan(g, groups)
+    assert qedges == [(0, 1), (1, 2)]
+    assert all(len(bundles[q]) == 3 and bundles[q] == sorted(bundles[q]) for q in qedges)
+    assert sorted(group_of) == list(range(9)) and [group_of[v] for v in groups[2]] == [2, 2, 2]
+    with pytest.raises(AssertionError):
+        E.partition_plan(g, [[0, 1], [1, 2, 3, 4, 5, 6, 7, 8]])
