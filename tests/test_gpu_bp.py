@@ -293,3 +293,21 @@ def test_single_precision_element_types_are_preserved(eltype):
     assert np.allclose(zv, 1.0, atol=1e-5) and np.allclose(ze, 1.0, atol=1e-5)
     out = E.normalize(psi, cache=bpc)
     assert out.dtype == np.dtype(eltype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_environment_on_a_tree_matches_the_exact_environment(ctx, dtype):
+    # test/test_forms.jl:62-75: environment(qf, state_vertices(qf, [v]); alg = "bp", update_cache = true) on a tree
+    from util import exact_site_environment
+    g = O.comb_tree_graph(3, 3)
+    net, psi = make_pair(g, 2, dtype)
+    bpc = E.update(E.BeliefPropagationCache(psi, ctx=ctx, messages="default"))  # tree: no initial messages, one sweep
+    for v in (0, 4, 8):
+        env = dict(E.environment(bpc, [v]))
+        bp = np.ones(())
+        for e in g.inc[v]:
+            bp = np.multiply.outer(bp, env[(g.other(e, v), v)])
+        exact = exact_site_environment(net, v)
+        exact, bp = exact / np.linalg.norm(exact), bp / np.linalg.norm(bp)
+        phase = np.vdot(bp, exact)
+        assert abs(abs(phase) - 1) < TOL and np.linalg.norm(exact - phase * bp) < TOL
