@@ -66,3 +66,19 @@ def test_host_schedules():
         assert len(vs) == len(set(vs))
     g3 = itn_b200.named_grid((3, 3, 3))
     assert g3.ne == 54 and max(g3.degree(v) for v in range(g3.nv)) == 6
+
+
+def test_binding_arity_matches_the_prototypes():
+    # every ctypes signature of the host mirror has as many arguments as the C prototype it binds, and pointer / scalar
+    # kinds agree position by position (a drifted signature would corrupt the stack silently)
+    txt = open(os.path.join(ROOT, "include", "itn_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = dict(re.findall(r"\b(itn_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt))
+    assert set(protos) == set(_lib.EXPORTED_SYMBOLS)
+    for name, (_, argtypes) in _lib._SIGS.items():
+        params = [p.strip() for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, binding {len(argtypes)}"
+        for p, a in zip(params, argtypes):
+            is_ptr_c = "*" in p or "[" in p
+            is_ptr_py = a in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(a, "contents") or a.__name__.startswith("LP_")
+            assert is_ptr_c == is_ptr_py, f"{name}: parameter `{p}` vs binding {a}"
