@@ -82,3 +82,21 @@ def test_binding_arity_matches_the_prototypes():
             is_ptr_c = "*" in p or "[" in p
             is_ptr_py = a in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(a, "contents") or a.__name__.startswith("LP_")
             assert is_ptr_c == is_ptr_py, f"{name}: parameter `{p}` vs binding {a}"
+
+
+def test_julia_shim_ccalls_match_the_prototypes():
+    # julia/ITNB200.jl cannot be executed here (no Julia runtime); at least every ccall in it names an exported symbol and
+    # passes as many argument types as the C prototype has parameters, pointers where the prototype has pointers
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "itn_b200.h")).read(), flags=re.S)
+    protos = dict(re.findall(r"\b(itn_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr))
+    jl = open(os.path.join(ROOT, "julia", "ITNB200.jl")).read()
+    calls = re.findall(r"ccall\(\(:(itn_[a-z0-9_]+),\s*LIB\),\s*(\w+),\s*\(([^)]*)\)", jl, flags=re.S)
+    assert len(calls) >= 15
+    for name, ret, args in calls:
+        assert name in protos, f"{name} is not declared in include/itn_b200.h"
+        params = [p.strip() for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
+        types = [t.strip() for t in args.split(",") if t.strip()]
+        assert len(types) == len(params), f"{name}: ccall passes {len(types)} arguments, the prototype takes {len(params)}"
+        assert ret == ("Cstring" if name == "itn_last_error" else "Cint")
+        for p, t in zip(params, types):
+            assert ("*" in p or "[" in p) == t.startswith("Ptr"), f"{name}: `{p}` vs {t}"
