@@ -183,6 +183,103 @@ function apply_gate!(bpc::B200BeliefPropagationCache, gate::AbstractArray, v1, v
   return bpc
 end
 
+# set_message!(bpc, edge, M) (abstract...cache.jl:197-200): M[a, a'] on the directed edge src(e) -> dst(e)
+function set_message_matrix!(bpc::B200BeliefPropagationCache, e, m::AbstractMatrix)
+  a = Matrix{bpc.elt}(m)
+  GC.@preserve a check(ccall((:itn_msg_set, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}),
+    bpc.h, bpc.vid[src(e)], bpc.vid[dst(e)], a))
+  return bpc
+end
+
+# updated_message(bpc, edge; normalize) without storing it (abstract...cache.jl:225-239, test_belief_propagation.jl:51)
+function updated_message_matrix(bpc::B200BeliefPropagationCache, e; normalize=true)
+  chi = size(message_matrix(bpc, e), 1)
+  m = Matrix{bpc.elt}(undef, chi, chi)
+  GC.@preserve m check(ccall((:itn_updated_message, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}),
+    bpc.h, bpc.vid[src(e)], bpc.vid[dst(e)], normalize, m))
+  return m
+end
+
+# message_diff(updated_message(bpc, e), message(bpc, e)) for a list of directed edges (abstract...cache.jl:32-36)
+function message_residuals(bpc::B200BeliefPropagationCache, es)
+  s = Int32[bpc.vid[src(e)] for e in es]
+  d = Int32[bpc.vid[dst(e)] for e in es]
+  out = zeros(Float64, length(es))
+  GC.@preserve s d out check(ccall((:itn_message_residuals, LIB), Cint,
+    (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Cint, Ptr{Cdouble}), bpc.h, s, d, length(es), out))
+  return out
+end
+
+# vertex_scalars / edge_scalars (abstract...cache.jl:83-97; region_scalar beliefpropagationcache.jl:107-119)
+function region_scalars(bpc::B200BeliefPropagationCache)
+  zv = Vector{bpc.elt}(undef, length(bpc.verts))
+  ze = Vector{bpc.elt}(undef, length(bpc.eds))
+  GC.@preserve zv ze check(ccall((:itn_region_scalars, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), bpc.h, zv, ze))
+  return Dict(zip(bpc.verts, zv)), Dict(zip(bpc.eds, ze))
+end
+
+# two-site reduced density matrices (test_belief_propagation.jl:64-91) on a list of edges: (d_u d_v) x (d_u d_v), unit trace
+function rdm2(bpc::B200BeliefPropagationCache, es)
+  ids = Int32[findfirst(x -> Set((src(x), dst(x))) == Set((src(e), dst(e))), bpc.eds) - 1 for e in es]
+  D = [dim(only(siteinds(bpc.psi, src(bpc.eds[i + 1])))) * dim(only(siteinds(bpc.psi, dst(bpc.eds[i + 1])))) for i in ids]
+  out = Vector{bpc.elt}(undef, sum(abs2, D))
+  GC.@preserve ids out check(ccall((:itn_rdm2, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Cvoid}),
+    bpc.h, ids, length(ids), out))
+  offs = cumsum([0; abs2.(D)])
+  return [reshape(out[offs[k]+1:offs[k+1]], D[k], D[k]) for k in eachindex(D)]
+end
+
+# one-site apply (src/apply.jl:108-116): gate[s', s] on vertex v, in place
+function apply_gate!(bpc::B200BeliefPropagationCache, gate::AbstractMatrix, v; normalize=false)
+  g = Matrix{bpc.elt}(gate)
+  ids = Int32[bpc.vid[v]]
+  GC.@preserve g ids check(ccall((:itn_apply1, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Cvoid}, Cint),
+    bpc.h, ids, 1, g, normalize))
+  return bpc
+end
+
+# map_eigvals(f, A, ...; ishermitian = true, cutoff) (src/apply.jl:21-25) for one Hermitian matrix; f in (:sqrt, :invsqrt, :inv)
+function map_eigvals_matrix(ctx::Context, f::Symbol, m::AbstractMatrix; cutoff=nothing)
+  elt = eltype(m) <: Complex ? ComplexF64 : Float64
+  a = Matrix{elt}(m)
+  out = similar(a)
+  fn = Dict(:sqrt => 0, :invsqrt => 1, :inv => 2)[f]
+  GC.@preserve a out check(ccall((:itn_map_eigvals, LIB), Cint,
+    (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble),
+    ctx.h, dtype_code(elt), fn, size(a, 1), 1, a, out, isnothing(cutoff) ? -1.0 : cutoff))
+  return out
+end
+
+# One Trotter step in one call (include/itn_b200.h: itn_apply_layers): `layers` is a vector of vectors of
+# (gate::Array{T,4}, v1, v2); after every layer `bp_maxiter` synchronous BP sweeps refresh the environments.
+function tebd_step!(bpc::B200BeliefPropagationCache, layers; maxdim=nothing, cutoff=nothing, normalize=false, msg_mode=0,
+  bp_maxiter=0, bp_tol=nothing)
+  eids = Int32[]; ptr = Int32[0]; packed = bpc.elt[]
+  for layer in layers
+    for (gate, v1, v2) in layer
+      eid = findfirst(x -> Set((src(x), dst(x))) == Set((v1, v2)), bpc.eds)
+      isnothing(eid) && error("Vertices where the gates are being applied must be neighbors for now.")
+      g = Array{bpc.elt,4}(gate)
+      src(bpc.eds[eid]) == v1 || (g = permutedims(g, (2, 1, 4, 3)))
+      push!(eids, eid - 1); append!(packed, vec(g))
+    end
+    push!(ptr, length(eids))
+  end
+  seq = reduce(vcat, [[e, reverse(e)] for e in bpc.eds])          # every directed edge, each its own group
+  s = Int32[bpc.vid[src(e)] for e in seq]; d = Int32[bpc.vid[dst(e)] for e in seq]
+  gp = Int32.(0:length(seq))
+  n = length(eids); stride = 256
+  newdim = zeros(Int32, n); terr = zeros(Float64, n); sv = zeros(Float64, stride * n); iters = Ref{Int32}(0)
+  GC.@preserve eids ptr packed s d gp newdim terr sv check(ccall((:itn_apply_layers, LIB), Cint,
+    (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}, Cint, Cdouble, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Cint,
+     Ptr{Int32}, Cint, Cint, Cdouble, Cint, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Int32}),
+    bpc.h, length(layers), ptr, eids, packed, isnothing(maxdim) ? 0 : maxdim, isnothing(cutoff) ? -1.0 : cutoff,
+    normalize, msg_mode, s, d, length(seq), gp, length(seq), bp_maxiter, isnothing(bp_tol) ? -1.0 : bp_tol, 1,
+    newdim, terr, sv, stride, iters))
+  return (; newdim, truncation_error=terr, singular_values=[sv[(i-1)*stride+1:(i-1)*stride+newdim[i]] for i in 1:n],
+    bp_iterations=iters[])
+end
+
 # inner(phi, psi; alg = "bp") / loginner (src/inner.jl:100-171): BilinearFormNetwork(phi, psi) with an explicit bra layer.
 # phi must live on the same graph with the same link dimensions as psi (pad the smaller tensor with zeros otherwise;
 # for inner(phi, A, psi) contract A[v] into psi[v] first and fuse the link pairs with combiners).  The link indices of
