@@ -19,7 +19,8 @@
  *     `axis_edge[i]` = edge id carried by axis i, or -1 for the physical (site) axis.
  *   - messages are chi x chi column-major matrices M[a, a'] with a = ket-side bond index and
  *     a' = bra-side (primed) copy.
- *   - a handle is used by one host thread at a time; distinct handles may be used concurrently.
+ *   - a handle is used by one host thread at a time; handles of DIFFERENT contexts may be used concurrently, handles
+ *     that share a context share its stream and block cache and must be serialised by the caller.
  */
 #ifndef ITN_B200_H
 #define ITN_B200_H
@@ -127,7 +128,9 @@ int itn_msg_get_all(const itn_net* net, void* host, int64_t bytes);
  * update_iteration sequential (:272-287; group_ptr == NULL: Gauss-Seidel over the list, executed as
  * dependency wavefronts with identical arithmetic) or grouped/synchronous (:294-308; group_ptr =
  * ngroups+1 offsets into the list; every group reads the pre-sweep messages, results are written
- * back at the end of the sweep.  Only single-edge groups are supported).
+ * back at the end of the sweep.  Single-edge groups are the synchronous sweep that the batched DMMA kernels and the
+ * multi-GPU path run; a group of several edges is a sequential pass over its edges that starts from the pre-sweep
+ * messages (single GPU, per-message kernels), and the diff of a sweep is divided by the number of groups as in :319-321).
  * updated_message(::Algorithm"contract") (:225-239) and message_diff (:32-36) run on the device.
  * tol < 0: `tol = nothing` (no diff computed).  Outputs may be NULL. */
 int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t* seq_dst, int nseq,
@@ -149,6 +152,11 @@ int itn_logscalar(itn_net* net, double out_re_im[2]);
 /* rescale(bpc) = rescale_messages + rescale_partitions over all ket/bra vertices
  * (beliefpropagationcache.jl:121-139, abstract :349-395; normalize.jl:63-80). */
 int itn_rescale(itn_net* net);
+/* rescale(bpc; verts) / rescale_partitions(bpc, partitions; verts) (abstract :349-395): every message pair is rescaled
+ * (rescale_messages always runs over all quotient edges), but only the site tensors of the n listed vertices (ket and
+ * bra of each, the k = 2 case of :363-372) are divided so that their region scalar becomes 1; the other vertices keep
+ * their tensors.  n = 0 rescales the messages only. */
+int itn_rescale_verts(itn_net* net, const int32_t* verts, int n);
 
 /* expect(psiIpsi, op) (src/expect.jl:5-19) for n vertices; ops: n matrices d x d, column-major
  * O[s_out, s_in]; out: n scalars (network dtype). */

@@ -1302,6 +1302,146 @@ void compute_messages(itn_net* net, const std::vector<MsgJob>& jobs, size_t lo, 
   itn_run_vertex_jobs(net, specs);
 }
 
+// update_iteration(alg, bpc, edge_groups) with groups of several edges (abstractbeliefpropagationcache.jl:294-308,
+// intended semantics): every group is a sequential (Gauss-Seidel) pass over its edges that starts from the PRE-SWEEP
+// messages; the message of every edge of the group is collected, later groups override earlier ones, and everything is
+// written back at the end of the sweep.  update() divides the summed diffs by the number of groups (:319-321).
+// Every update gets its own result buffer, so inside a group only read-after-write dependencies order the work
+// (dependency levels, one batched launch sequence per level).  Parity mode: per-message kernels, single GPU.
+void bp_update_groups(itn_net* net, const std::vector<MsgJob>& jobs, const int32_t* group_ptr, int ngroups, int maxiter,
+                      double tol, int normalize, int32_t* iters, double* last_mean_diff) {
+  itn_ctx* ctx = net->ctx;
+  ITN_REQUIRE(ctx->nranks == 1, ITN_EUNSUPPORTED,
+              "groups of several edges run on a single GPU only (use single-edge groups on a partitioned network)");
+  itn_flush_pending(net);
+  const int nseq = (int)jobs.size();
+  const bool want_diff = tol >= 0.0;
+  const size_t nd = net->M.size();
+  // plan: per job the buffer each incoming message is read from (-1: the pre-sweep message) and its level in the group
+  std::vector<std::vector<int>> reads(nseq);
+  std::vector<int> oldsrc(nseq, -1), level(nseq, 0);
+  std::vector<int> final_job(nd, -1);
+  {
+    std::vector<int> overlay(nd, -1);
+    for (int g = 0; g < ngroups; ++g) {
+      std::vector<int> touched;
+      for (int i = group_ptr[g]; i < group_ptr[g + 1]; ++i) {
+        const MsgJob& J = jobs[i];
+        int lv = 0;
+        const int z = (int)net->inc[J.v].size();
+        reads[i].assign(z, -1);
+        for (int k = 0; k < z; ++k) {
+          const int e = net->inc[J.v][k];
+          if (e == J.did / 2) continue;
+          const int m = net->msg_into(J.v, e);
+          ITN_REQUIRE(overlay[m] >= 0 || net->M[m].p != nullptr, ITN_EINVAL,
+                      "message into vertex " + std::to_string(J.v) + " on edge " + std::to_string(e) +
+                          " does not exist when updating " + std::to_string(J.v) + " -> " +
+                          std::to_string(net->other(J.did / 2, J.v)) + " (initialise messages or use the forest-cover sequence)");
+          reads[i][k] = overlay[m];
+          if (overlay[m] >= 0) lv = std::max(lv, level[overlay[m]] + 1);
+        }
+        if (want_diff) {
+          ITN_REQUIRE(overlay[J.did] >= 0 || net->M[J.did].p != nullptr, ITN_EINVAL,
+                      "tol requires an existing message on every edge of the sequence (tol = nothing on trees)");
+          oldsrc[i] = overlay[J.did];
+          if (overlay[J.did] >= 0) lv = std::max(lv, level[overlay[J.did]] + 1);
+        }
+        level[i] = lv;
+        overlay[J.did] = i;
+        final_job[J.did] = i;
+        touched.push_back(J.did);
+      }
+      for (int d : touched) overlay[d] = -1;
+    }
+  }
+  for (size_t d = 0; d < nd; ++d)
+    if (final_job[d] >= 0 && !net->M[d].p) {
+      alloc_message(net, (int)d);
+      CUDA_CHECK(cudaMemsetAsync(net->M[d].p, 0, (size_t)net->M[d].n * net->planes() * sizeof(double), ctx->stream));
+    }
+  Staged raw(net, jobs), res(net, jobs);
+  DevBuf diffs(ctx, (size_t)std::max(nseq, 1) * sizeof(double));
+  DevBuf dsum(ctx, sizeof(double));
+  cudaEvent_t ev0, ev1;
+  CUDA_CHECK(cudaEventCreate(&ev0));
+  CUDA_CHECK(cudaEventCreate(&ev1));
+  CUDA_CHECK(cudaEventRecord(ev0, ctx->stream));
+  int done = 0;
+  double mean = NAN;
+  try {
+    for (int it = 0; it < maxiter; ++it) {
+      for (int g = 0; g < ngroups; ++g) {
+        const int lo = group_ptr[g], hi = group_ptr[g + 1];
+        int maxlv = -1;
+        for (int i = lo; i < hi; ++i) maxlv = std::max(maxlv, level[i]);
+        for (int lv = 0; lv <= maxlv; ++lv) {
+          std::vector<JobSpec> specs;
+          std::vector<std::vector<const double*>> mats;
+          std::vector<CommitJob> cj;
+          std::vector<int> idx;
+          for (int i = lo; i < hi; ++i)
+            if (level[i] == lv) idx.push_back(i);
+          mats.resize(idx.size());
+          for (size_t q = 0; q < idx.size(); ++q) {
+            const int i = idx[q];
+            mats[q].assign(reads[i].size(), nullptr);
+            for (size_t k = 0; k < reads[i].size(); ++k)
+              if (reads[i][k] >= 0) mats[q][k] = res.ptr[reads[i][k]];
+          }
+          for (size_t q = 0; q < idx.size(); ++q) {
+            const int i = idx[q];
+            specs.push_back({jobs[i].v, 1u << (jobs[i].k + 1), raw.ptr[i], mats[q].data()});
+            const int chi = net->edim[jobs[i].did / 2];
+            const double* old = !want_diff ? nullptr : (oldsrc[i] >= 0 ? res.ptr[oldsrc[i]] : net->M[jobs[i].did].p);
+            cj.push_back({raw.ptr[i], res.ptr[i], old, chi * chi});
+          }
+          itn_run_vertex_jobs(net, specs);
+          // diffs of this level land at consecutive slots; the sum below runs over all nseq slots in job order
+          DevBuf ld(ctx, cj.size() * sizeof(double));
+          itn_run_commit(net, cj, normalize, want_diff ? ld.as<double>() : nullptr);
+          if (want_diff)
+            for (size_t q = 0; q < idx.size(); ++q)
+              CUDA_CHECK(cudaMemcpyAsync(diffs.as<double>() + idx[q], ld.as<double>() + q, sizeof(double),
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+      }
+      // write-back of the sweep: the last listed update of every directed edge
+      std::vector<CommitJob> wb;
+      for (size_t d = 0; d < nd; ++d)
+        if (final_job[d] >= 0) {
+          const int chi = net->edim[d / 2];
+          wb.push_back({res.ptr[final_job[d]], net->M[d].p, nullptr, chi * chi});
+        }
+      itn_run_commit(net, wb, 0, nullptr);
+      ++done;
+      if (want_diff) {
+        k_sum_fixed<<<1, 256, 0, ctx->stream>>>(diffs.as<double>(), nseq, dsum.as<double>());
+        ITN_LAUNCH_CHECK(ctx);
+        double sum = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&sum, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        mean = sum / ngroups;
+        if (mean <= tol) break;
+      }
+    }
+    CUDA_CHECK(cudaEventRecord(ev1, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    net->last_total_ms = ms;
+    net->last_contract_ms = ms;
+  } catch (...) {
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    throw;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (iters) *iters = done;
+  if (last_mean_diff) *last_mean_diff = mean;
+}
+
 }  // namespace
 
 extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t* seq_dst, int nseq,
@@ -1319,13 +1459,20 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   if (nseq == 0 || maxiter == 0) return ITN_OK;
   const bool sync_mode = group_ptr != nullptr;
   if (!sync_mode) itn_flush_pending(net);  // only the synchronous sweep overlaps the upload (see below)
+  bool multi_edge_groups = false;
   if (sync_mode) {
-    ITN_REQUIRE(ngroups == nseq && group_ptr[0] == 0, ITN_EUNSUPPORTED,
-                "grouped update supports single-edge groups only (ngroups must equal nseq)");
-    for (int i = 0; i < ngroups; ++i)
-      ITN_REQUIRE(group_ptr[i + 1] - group_ptr[i] == 1, ITN_EUNSUPPORTED, "grouped update supports single-edge groups only");
+    ITN_REQUIRE(ngroups >= 1 && group_ptr[0] == 0 && group_ptr[ngroups] == nseq, ITN_EINVAL,
+                "group_ptr must hold ngroups + 1 offsets from 0 to nseq");
+    for (int i = 0; i < ngroups; ++i) {
+      ITN_REQUIRE(group_ptr[i + 1] >= group_ptr[i], ITN_EINVAL, "group_ptr must be non-decreasing");
+      multi_edge_groups = multi_edge_groups || group_ptr[i + 1] - group_ptr[i] != 1;
+    }
   }
   std::vector<MsgJob> jobs = make_msg_jobs(net, seq_src, seq_dst, nseq);
+  if (multi_edge_groups) {
+    bp_update_groups(net, jobs, group_ptr, ngroups, maxiter, tol, normalize, iters, last_mean_diff);
+    return ITN_OK;
+  }
   const bool want_diff = tol >= 0.0;
   // multi-GPU: every rank receives the same full sequence and keeps the updates whose source vertex it owns;
   // the messages crossing a cut are exchanged once per sweep (itn_dist.cu)
@@ -1724,9 +1871,30 @@ extern "C" int itn_logscalar(itn_net* net, double out[2]) {
   API_END
 }
 
-extern "C" int itn_rescale(itn_net* net) {
+static int rescale_impl(itn_net* net, const int32_t* verts, int nverts);
+
+extern "C" int itn_rescale(itn_net* net) { return rescale_impl(net, nullptr, -1); }
+
+extern "C" int itn_rescale_verts(itn_net* net, const int32_t* verts, int n) {
+  if (n < 0 || (n > 0 && !verts)) {
+    itn_set_error("itn_rescale_verts: verts must hold n >= 0 vertex ids");
+    return ITN_EINVAL;
+  }
+  return rescale_impl(net, verts, n);
+}
+
+// nverts < 0: every vertex; otherwise only the listed vertices (ket and bra of each) are rescaled
+static int rescale_impl(itn_net* net, const int32_t* verts, int nverts) {
   API_BEGIN
   ITN_REQUIRE(net, ITN_EINVAL, "net is NULL");
+  std::vector<char> sel;
+  if (nverts >= 0) {
+    sel.assign(net->nv, 0);
+    for (int i = 0; i < nverts; ++i) {
+      ITN_REQUIRE(verts[i] >= 0 && verts[i] < net->nv, ITN_EINVAL, "vertex out of range");
+      sel[verts[i]] = 1;
+    }
+  }
   ITN_REQUIRE(!net->has_bra(), ITN_EUNSUPPORTED, "not defined for a bilinear form network (a bra layer is set): only BP updates, region scalars and logscalar are");
   set_device(net->ctx);
   itn_flush_pending(net);
@@ -1750,7 +1918,7 @@ extern "C" int itn_rescale(itn_net* net) {
   std::vector<ScaleJob> sj;
   long long maxn = 0;
   for (int v = 0; v < net->nv; ++v) {
-    if (!itn_is_local(net, v)) continue;
+    if (!itn_is_local(net, v) || (!sel.empty() && !sel[v])) continue;
     sj.push_back({net->T[v].p, net->T[v].n * net->planes(), dz.as<double>() + 2 * v, 1.0});
     maxn = std::max<long long>(maxn, sj.back().n);
   }
@@ -1762,7 +1930,7 @@ extern "C" int itn_rescale(itn_net* net) {
     ITN_LAUNCH_CHECK(ctx);
   }
   for (int v = 0; v < net->nv; ++v)
-    if (itn_is_local(net, v)) net->touch(v);
+    if (itn_is_local(net, v) && (sel.empty() || sel[v])) net->touch(v);
   net->topo_version++;
   API_END
 }
@@ -1981,25 +2149,32 @@ extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void*
     ITN_REQUIRE(v >= 0 && v < net->nv, ITN_EINVAL, "Gate being applied does not share indices with tensor network.");
     ITN_REQUIRE(!seen[v], ITN_EINVAL, "a batch of one-site gates must act on distinct vertices");
     seen[v] = 1;
-    ITN_REQUIRE(itn_is_local(net, v), ITN_EUNSUPPORTED, "one-site gate on a vertex stored by another rank");
-    ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor is not set");
+    // multi-GPU: every rank is called with the same batch; vertices stored by another rank are skipped (their gate
+    // still consumes its place in `gates`), the contract of itn_net_set_tensors / itn_expect1 / itn_apply2
+    if (itn_is_local(net, v)) ITN_REQUIRE(net->T[v].p, ITN_EINVAL, "site tensor is not set");
     g_elems += (size_t)net->sdim[v] * net->sdim[v];
   }
-  DevBuf dg(ctx, g_elems * P * sizeof(double));
-  std::vector<Apply1Job> jobs(n);
-  std::vector<NormJob> nj(n);
+  DevBuf dg(ctx, std::max<size_t>(g_elems, 1) * P * sizeof(double));
+  std::vector<Apply1Job> jobs;
+  std::vector<NormJob> nj;
+  std::vector<int> done;
   size_t off = 0;
   long long maxn = 0;
   for (int i = 0; i < n; ++i) {
     int v = verts[i], d = net->sdim[v];
     ITN_REQUIRE(d <= 8, ITN_EUNSUPPORTED, "one-site gates support site dimensions up to 8");
-    double* g = dg.as<double>() + off * P;
-    upload_planar(net, (const char*)gates + off * P * sizeof(double), (long long)d * d, 1, g);
-    jobs[i] = {net->T[v].p, net->T[v].n, g, d, normalize};
-    nj[i] = {net->T[v].p, net->T[v].n * P};
-    maxn = std::max<long long>(maxn, net->T[v].n);
+    if (itn_is_local(net, v)) {
+      double* g = dg.as<double>() + off * P;
+      upload_planar(net, (const char*)gates + off * P * sizeof(double), (long long)d * d, 1, g);
+      jobs.push_back({net->T[v].p, net->T[v].n, g, d, normalize});
+      nj.push_back({net->T[v].p, net->T[v].n * P});
+      maxn = std::max<long long>(maxn, net->T[v].n);
+      done.push_back(v);
+    }
     off += (size_t)d * d;
   }
+  if (jobs.empty()) return ITN_OK;
+  n = (int)jobs.size();
   DevBuf jb(ctx, jobs.size() * sizeof(Apply1Job));
   const Apply1Job* dj = itn_upload(ctx, jobs, jb);
   unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn / 2 + 255) / 256, 64));
@@ -2012,7 +2187,7 @@ extern "C" int itn_apply1(itn_net* net, const int32_t* verts, int n, const void*
     k_normalize<<<n, 256, 0, ctx->stream>>>(dn);
     ITN_LAUNCH_CHECK(ctx);
   }
-  for (int i = 0; i < n; ++i) net->touch(verts[i]);
+  for (int v : done) net->touch(v);
   net->topo_version++;
   API_END
 }

@@ -604,12 +604,10 @@ size_t fast_smem(bool has_p) {
 template <bool C, bool HAS_P, bool DO_W>
 void launch_phase(itn_net* net, int nverts, const FastArgs& a) {
   const size_t smem = fast_smem<C>(HAS_P);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_fast<C, HAS_P, DO_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_CHECK(cudaFuncSetAttribute(k_fast<C, HAS_P, DO_W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
-  }
+  // function attributes are per device: set them on every launch (a second context on another GPU of the same
+  // process needs its own opt-in to > 48 KB of dynamic shared memory; the call costs a microsecond)
+  CUDA_CHECK(cudaFuncSetAttribute(k_fast<C, HAS_P, DO_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_fast<C, HAS_P, DO_W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const unsigned grid = (unsigned)nverts * a.d * 32;
   k_fast<C, HAS_P, DO_W><<<grid, kThreads, smem, net->ctx->stream>>>(a);
   ITN_LAUNCH_CHECK(net->ctx);
@@ -770,8 +768,16 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
   FastCache* fc = ensure_cache(net);
   if (!fc) return 0;
   itn_ctx* ctx = net->ctx;
+  // a vertex takes part when the sweep lists each of its four outgoing messages exactly once (a sequence that repeats
+  // a directed edge stays on the generic path, which handles every listed update separately)
   std::vector<int> cnt(net->nv, 0);
-  for (size_t i = 0; i < dids.size(); ++i) cnt[srcv[i]]++;
+  {
+    std::vector<char> listed(net->M.size(), 0);
+    for (size_t i = 0; i < dids.size(); ++i) {
+      cnt[srcv[i]] += listed[dids[i]] ? 100 : 1;
+      listed[dids[i]] = 1;
+    }
+  }
   fc->sweep.clear();
   std::vector<int> rank_in_sweep(fc->nb, -1);
   for (int i = 0; i < fc->nb; ++i)

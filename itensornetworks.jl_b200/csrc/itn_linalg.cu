@@ -760,9 +760,9 @@ void launch_jacobi64(itn_ctx* ctx, const SvdJob* dj, unsigned njobs, int maxn) {
   ITN_LAUNCH_CHECK(ctx);
 }
 
-thread_local int g_jacobi_variant = 0;  // 0 = auto, 1 = generic kernel only, 2 = round-robin k_jacobi64 (itn_svd_batch's second opinions)
-
-void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs) {
+// variant: 0 = auto, 1 = generic kernel only, 2 = round-robin k_jacobi64, 3 = odd-even kernel at 3 CTAs per SM
+// (a per-call argument: itn_svd_batch's second opinions; every other caller uses the default)
+void run_jacobi(itn_ctx* ctx, bool cplx, const std::vector<SvdJob>& jobs, int g_jacobi_variant = 0) {
   if (jobs.empty()) return;
   int maxn = 0, maxm = 0;
   size_t need = 0;
@@ -1031,6 +1031,9 @@ struct EigFnJob {
   int chi;
   int* deficient;     // optional: set to 1 when eigenvalues were dropped by the cutoff
   const int* skip;    // optional device flag: non-zero -> nothing to do (the Cholesky test proved full support)
+  double shift;       // > 0: the decomposed matrix was H + shift * 1 (positive definite), lambda_j = sigma_j - shift
+  int* mixed;         // optional (shift == 0): set to 1 when a right singular vector is not an eigenvector (a +-lambda
+                      // pair of an indefinite H mixes in the SVD); the caller then repeats the job with a shift
 };
 // out = V_kept f(lambda) V_kept^H with lambda_j = sigma_j * sign(Re <v_j, (U Sigma)_j>); diagonal inputs
 // short-circuit to f(diag) (map_diag, apply.jl:22).  fn: 0 sqrt, 1 inv sqrt, 2 inv, 3 one (support projector).
@@ -1093,14 +1096,38 @@ __global__ void __launch_bounds__(256) k_eig_fn(const EigFnJob* __restrict__ job
     }
     return;
   }
+  __shared__ int s_perm[256];
   for (int j = tid; j < n; j += blockDim.x) {
     const int col = J.perm[j];
+    s_perm[j] = col;
+    if (J.shift > 0.0) {
+      lam[j] = J.sigma[j] - J.shift;
+      continue;
+    }
     double d = 0.0;
     for (int i = 0; i < n; ++i) {
       d += J.v[col * n + i] * J.us[col * n + i];
       if (C) d += J.v[n2 + col * n + i] * J.us[n2 + col * n + i];
     }
     lam[j] = d < 0.0 ? -J.sigma[j] : J.sigma[j];
+    // <v_j, H v_j> = +-sigma_j when v_j is an eigenvector; anything well inside means a mixed +-lambda pair
+    if (J.mixed && J.sigma[j] > 1e-8 * J.sigma[0] && fabs(d) < 0.9 * J.sigma[j]) *J.mixed = 1;
+  }
+  __syncthreads();
+  if (tid == 0 && J.shift > 0.0) {
+    // eigenvalues of the shifted decomposition come sorted by value: restore the order by decreasing magnitude
+    for (int i = 1; i < n; ++i) {
+      const double l = lam[i];
+      const int c = s_perm[i];
+      int k = i - 1;
+      while (k >= 0 && fabs(lam[k]) < fabs(l)) {
+        lam[k + 1] = lam[k];
+        s_perm[k + 1] = s_perm[k];
+        --k;
+      }
+      lam[k + 1] = l;
+      s_perm[k + 1] = c;
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -1122,7 +1149,7 @@ __global__ void __launch_bounds__(256) k_eig_fn(const EigFnJob* __restrict__ job
     const int r = i % n, c = i / n;
     double ar = 0.0, ai = 0.0;
     for (int j = 0; j < keep; ++j) {
-      const int col = J.perm[j];
+      const int col = s_perm[j];
       const double vr = J.v[col * n + r], vi = C ? J.v[n2 + col * n + r] : 0.0;
       const double wr = J.v[col * n + c], wi = C ? -J.v[n2 + col * n + c] : 0.0;  // conj(V[c, j])
       const double pr = vr * wr - vi * wi, pi = vr * wi + vi * wr;
@@ -1781,9 +1808,50 @@ void itn_dev_map_eigvals(itn_ctx* ctx, bool cplx, int fn, int chi, int n, const 
   ITN_LAUNCH_CHECK(ctx);
   CUDA_CHECK(cudaMemcpyAsync(us.p, h.p, n * n2 * P * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   run_jacobi(ctx, cplx, sj);
+  DevBuf mixed(ctx, (size_t)n * sizeof(int));
+  CUDA_CHECK(cudaMemsetAsync(mixed.p, 0, (size_t)n * sizeof(int), ctx->stream));
+  for (int i = 0; i < n; ++i) ej[i].mixed = mixed.as<int>() + i;
   const EigFnJob* de = itn_upload(ctx, ej, eb);
   if (cplx) k_eig_fn<true><<<n, 256, 0, ctx->stream>>>(de, fn, cutoff);
   else k_eig_fn<false><<<n, 256, 0, ctx->stream>>>(de, fn, cutoff);
+  ITN_LAUNCH_CHECK(ctx);
+  // Indefinite Hermitian input: the right singular vectors of a +-lambda pair are not eigenvectors (H = [[0,1],[1,0]]
+  // has V = 1), which k_eig_fn reports per matrix.  Those matrices are decomposed again as H + shift * 1 with
+  // shift = 2 ||H||_F > spectral radius: positive definite, so its SVD IS its eigen-decomposition, lambda = sigma - shift.
+  // (The unshifted route stays the default: one-sided Jacobi keeps the small eigenvalues of the PSD BP messages to
+  // high relative accuracy, which the inverse square roots of the simple update need.)
+  std::vector<int> hm(n);
+  CUDA_CHECK(cudaMemcpyAsync(hm.data(), mixed.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> redo;
+  for (int i = 0; i < n; ++i)
+    if (hm[i]) redo.push_back(i);
+  if (redo.empty()) return;
+  std::vector<double> hh(n2 * P);
+  std::vector<SvdJob> sj2;
+  std::vector<EigFnJob> ej2;
+  for (int i : redo) {
+    double* hi = h.as<double>() + i * n2 * P;
+    double* ui = us.as<double>() + i * n2 * P;
+    CUDA_CHECK(cudaMemcpyAsync(hh.data(), hi, n2 * P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    double fro = 0.0;
+    for (double x : hh) fro += x * x;
+    const double shift = 2.0 * std::sqrt(fro);
+    for (int k = 0; k < chi; ++k) hh[(size_t)k * chi + k] += shift;
+    CUDA_CHECK(cudaMemcpyAsync(ui, hh.data(), n2 * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    sj2.push_back(sj[i]);
+    EigFnJob e = ej[i];
+    e.shift = shift;
+    e.mixed = nullptr;
+    ej2.push_back(e);
+  }
+  run_jacobi(ctx, cplx, sj2);
+  DevBuf eb2(ctx, ej2.size() * sizeof(EigFnJob));
+  const EigFnJob* de2 = itn_upload(ctx, ej2, eb2);
+  if (cplx) k_eig_fn<true><<<(unsigned)ej2.size(), 256, 0, ctx->stream>>>(de2, fn, cutoff);
+  else k_eig_fn<false><<<(unsigned)ej2.size(), 256, 0, ctx->stream>>>(de2, fn, cutoff);
   ITN_LAUNCH_CHECK(ctx);
 }
 
@@ -1884,19 +1952,15 @@ extern "C" int itn_svd_batch(itn_ctx* ctx, int dtype, int m, int n, int batch, c
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
-  const int saved = g_jacobi_variant;
-  g_jacobi_variant = variant;
   try {
     CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
-    run_jacobi(ctx, cplx, jobs);
+    run_jacobi(ctx, cplx, jobs, variant);
     CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
   } catch (...) {
-    g_jacobi_variant = saved;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     throw;
   }
-  g_jacobi_variant = saved;
   CUDA_CHECK(cudaMemcpyAsync(host_sigma, sig.p, (size_t)batch * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (host_us) {
     if (cplx) k_merge<true><<<g, 256, 0, ctx->stream>>>(us.as<double>(), raw.as<double>(), (int)mn, batch);

@@ -7,5 +7,5 @@ from .cache import (BeliefPropagationCache, Context, GateLayer, apply, apply_lay
 from .graphs import (NamedGraph, default_edge_sequence, edge_coloring, forest_cover, heavy_hex_eagle,
                      named_comb_tree, named_grid, named_path_graph, parallel_edge_sequence)
 from .network import ITensorNetwork, productstate, random_tensornetwork
-from .dist import directed_id, gate_exchange_plan, halo_bytes_per_sweep, halo_plan, init_distributed, partition_vertices
+from .dist import cut_edges, directed_id, gate_exchange_plan, halo_bytes_per_sweep, halo_plan, init_distributed, partition_vertices
 from .partitions import PartitionMap, partition_plan, partitioned_network, tensordot

@@ -53,6 +53,7 @@ _SIGS = {
     "itn_region_scalars": (C.c_int, [_vp, _vp, _vp]),
     "itn_logscalar": (C.c_int, [_vp, _dp]),
     "itn_rescale": (C.c_int, [_vp]),
+    "itn_rescale_verts": (C.c_int, [_vp, _i32p, C.c_int]),
     "itn_expect1": (C.c_int, [_vp, _i32p, C.c_int, _vp, _vp]),
     "itn_rdm2": (C.c_int, [_vp, _i32p, C.c_int, _vp]),
     "itn_apply1": (C.c_int, [_vp, _i32p, C.c_int, _vp, C.c_int]),

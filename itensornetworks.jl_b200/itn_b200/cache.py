@@ -378,9 +378,18 @@ def scalar(bpc):
     return np.exp(logscalar(bpc))
 
 
-def rescale(bpc, inplace=False):
+def rescale(bpc, inplace=False, verts=None):
+    """rescale(bpc; verts) (abstractbeliefpropagationcache.jl:391-395): rescale_messages over every edge, then
+    rescale_partitions restricted to `verts` (None = every vertex; a vertex stands for its ket and bra)."""
     out = bpc if inplace else bpc.copy()
-    check(lib().itn_rescale(out.h))
+    if verts is None:
+        check(lib().itn_rescale(out.h))
+    else:
+        vs = [int(v) for v in verts]
+        if bpc.partition is not None:
+            vs = sorted(set(bpc.partition.group_of[v] for v in vs))
+        _, pv = i32(vs)
+        check(lib().itn_rescale_verts(out.h, pv, len(vs)))
     return out
 
 

@@ -13,18 +13,73 @@ import numpy as np
 from ._lib import check, lib
 
 
-def partition_vertices(graph, nparts):
-    """owner[v] for a strip partition: grids are cut along their first axis (contiguous row blocks),
-    anything else into contiguous vertex-id blocks.  NVSwitch gives every pair of GPUs the same bandwidth,
-    so only the cut size matters, not which ranks are neighbours."""
+def _factorizations(n, k):
+    """All ordered k-tuples of positive integers with product n."""
+    if k == 1:
+        return [(n,)]
+    out = []
+    for f in range(1, n + 1):
+        if n % f == 0:
+            out += [(f,) + rest for rest in _factorizations(n // f, k - 1)]
+    return out
+
+
+def cut_edges(graph, owner):
+    """(total number of edges crossing a cut, largest number of cut edges at one rank)."""
+    per = {}
+    tot = 0
+    for (u, v) in graph.edges:
+        if owner[u] != owner[v]:
+            tot += 1
+            per[owner[u]] = per.get(owner[u], 0) + 1
+            per[owner[v]] = per.get(owner[v], 0) + 1
+    return tot, max(per.values()) if per else 0
+
+
+def _brick_owner(names, shape, parts):
+    own = []
+    for c in names:
+        r = 0
+        for ax in range(len(shape)):
+            r = r * parts[ax] + min(parts[ax] - 1, (c[ax] * parts[ax]) // shape[ax])
+        own.append(r)
+    return own
+
+
+def partition_vertices(graph, nparts, kind="auto"):
+    """owner[v] of a graph partition into `nparts` ranks.
+      "strips"  grids are cut along their first axis (contiguous row blocks / planes),
+      "bricks"  grids are cut into a p_0 x p_1 x ... array of near-cubic blocks (the factorisation of nparts with the
+                fewest cut edges, ties broken by the busiest rank's cut),
+      "auto"    whichever of the two has fewer cut edges at the busiest rank (the halo exchange and the cut-gate traffic
+                of a rank scale with its own cut; NVSwitch gives every pair of GPUs the same bandwidth, so it does not
+                matter which ranks are neighbours).
+    Graphs without grid coordinates are cut into contiguous vertex-id blocks."""
     nparts = int(nparts)
     if nparts <= 1:
         return [0] * graph.nv
     names = getattr(graph, "names", None)
     if names and isinstance(names[0], tuple) and len(names[0]) >= 1:
-        n0 = max(c[0] for c in names) + 1
-        if n0 >= nparts:
-            return [min(nparts - 1, (c[0] * nparts) // n0) for c in names]
+        nd = len(names[0])
+        shape = [max(c[ax] for c in names) + 1 for ax in range(nd)]
+        strips = None
+        if shape[0] >= nparts:
+            strips = _brick_owner(names, shape, (nparts,) + (1,) * (nd - 1))
+        if kind == "strips" and strips is not None:
+            return strips
+        best = None
+        for parts in _factorizations(nparts, nd):
+            if any(parts[ax] > shape[ax] for ax in range(nd)):
+                continue
+            own = _brick_owner(names, shape, parts)
+            tot, mx = cut_edges(graph, own)
+            key = (tot, mx) if kind == "bricks" else (mx, tot)
+            if best is None or key < best[0]:
+                best = (key, own)
+        if best is not None:
+            return best[1]
+        if strips is not None:
+            return strips
     return [min(nparts - 1, (v * nparts) // graph.nv) for v in range(graph.nv)]
 
 

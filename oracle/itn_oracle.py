@@ -342,6 +342,23 @@ def updated_message(net, msgs, v, w, normalize=True):
     return m
 
 
+def updated_message_local(a, incoming, k, normalize=True):
+    """The same update (abstractbeliefpropagationcache.jl:225-239) stated on one vertex alone: `a` = site tensor
+    [s, a_1..a_z], `incoming[j]` = message into the vertex on bond slot j (slot k is ignored), result = message leaving
+    on slot k.  Used where only a sample of a large network is brought to the host (bench.py, full-size tests)."""
+    b = a
+    for j in range(a.ndim - 1):
+        if j != k:
+            b = _absorb(b, 1 + j, incoming[j])
+    axes = [i for i in range(a.ndim) if i != 1 + k]
+    m = np.tensordot(b, a.conj(), axes=(axes, axes))
+    if normalize:
+        n = np.linalg.norm(m)
+        if n != 0:
+            m = m / n
+    return m
+
+
 def message_diff(a, b):
     """1 - |<a^, b^>|^2, first argument conjugated (abstractbeliefpropagationcache.jl:32-36)."""
     na, nb = np.linalg.norm(a), np.linalg.norm(b)
@@ -390,7 +407,8 @@ def bp_update(net, msgs, seq=None, groups=None, maxiter=1, tol=None, normalize=T
         if return_history:
             history.append({k: m.copy() for k, m in msgs.items()})
         if tol is not None:
-            mean_diff = diff / len(seq)
+            # update divides by length(edge_sequence): the number of groups in the grouped form (:319-321)
+            mean_diff = diff / (len(seq) if groups is None else len(groups))
             if mean_diff <= tol:
                 break
     if return_history:
@@ -464,22 +482,25 @@ def rescale_messages(net, msgs):
     return msgs
 
 
-def rescale_partitions(net, msgs):
+def rescale_partitions(net, msgs, verts=None):
     """verts = all ket and bra vertices (normalize.jl:75-76): each ket/bra tensor / its norm,
     then Z_v^(-1/2) spread over ket and bra.  The engine keeps bra == conj(ket), so the ket
-    weight is taken as |Z_v|^(-1/2) (identical when Z_v is real positive, the <psi|psi> case)."""
+    weight is taken as |Z_v|^(-1/2) (identical when Z_v is real positive, the <psi|psi> case).
+    `verts` (abstractbeliefpropagationcache.jl:349-379): only these sites (ket and bra of each) are touched;
+    partitions without a listed vertex are skipped (:365)."""
     net = net.copy()
-    for v in range(net.graph.nv):
+    vs = range(net.graph.nv) if verts is None else sorted(set(int(v) for v in verts))
+    for v in vs:
         net.tensors[v] = net.tensors[v] / np.linalg.norm(net.tensors[v])
-    for v in range(net.graph.nv):
+    for v in vs:
         zv = vertex_scalar(net, msgs, v)
         net.tensors[v] = net.tensors[v] * (abs(zv) ** -0.5)
     return net
 
 
-def rescale(net, msgs):
+def rescale(net, msgs, verts=None):
     msgs = rescale_messages(net, msgs)
-    net = rescale_partitions(net, msgs)
+    net = rescale_partitions(net, msgs, verts)
     return net, msgs
 
 

@@ -116,8 +116,15 @@ def test_halo_plan_is_symmetric():
                 assert pl["recv"] == plans[peer][r]["send"]
         ncut = sum(1 for (u, v) in g.edges if owner[u] != owner[v])
         assert sum(len(pl["send"]) for p in plans for pl in p.values()) == 2 * ncut
-    b = E.halo_bytes_per_sweep(E.named_grid((64, 64)), E.partition_vertices(E.named_grid((64, 64)), 8), [16] * 8064, 16)
+    g64 = E.named_grid((64, 64))
+    b = E.halo_bytes_per_sweep(g64, E.partition_vertices(g64, 8, kind="strips"), [16] * 8064, 16)
     assert b[0] == 64 * 256 * 16 and b[3] == 2 * 64 * 256 * 16  # 256 KiB per cut and direction
+    # bricks: 2 x 4 blocks cut 256 edges in total (strips: 448) and at most 80 at one rank (strips: 128)
+    assert E.cut_edges(g64, E.partition_vertices(g64, 8, kind="strips")) == (448, 128)
+    assert E.cut_edges(g64, E.partition_vertices(g64, 8, kind="bricks")) == (256, 80)
+    g3 = E.named_grid((16, 16, 16))
+    assert E.cut_edges(g3, E.partition_vertices(g3, 8, kind="strips")) == (1792, 512)
+    assert E.cut_edges(g3, E.partition_vertices(g3, 8)) == (768, 192)  # auto = 2 x 2 x 2 bricks
 
 
 def test_gate_exchange_plan_is_symmetric():

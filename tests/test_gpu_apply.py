@@ -61,6 +61,33 @@ def test_map_eigvals(ctx, dtype, n):
     assert rel_err(E.map_eigvals("invsqrt", q, cutoff=1e-12, ctx=ctx), ref) < 1e-8
 
 
+def test_map_eigvals_indefinite_hermitian(ctx):
+    # map_eigvals(f, A; ishermitian = true) is advertised for any Hermitian A (src/apply.jl:9-25), not only PSD ones:
+    # a +-lambda pair mixes in the one-sided Jacobi SVD (H = [[0, 1], [1, 0]] has V = 1), which the engine detects and
+    # redoes through H + shift * 1 (csrc/itn_linalg.cu, itn_dev_map_eigvals)
+    def ref(f, h):
+        w, v = np.linalg.eigh(h)
+        return (v * f(w.astype(np.complex128))) @ v.conj().T
+    h2 = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    inv = E.map_eigvals("inv", h2, ctx=ctx)
+    assert rel_err(inv, h2) < 1e-13  # its own inverse
+    sq = E.map_eigvals("sqrt", h2, ctx=ctx)
+    assert rel_err(sq @ sq, h2) < 1e-12
+    rng = np.random.default_rng(5)
+    for n in (3, 8, 17):
+        a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        w = np.concatenate([np.linspace(0.5, 2.0, n - n // 2), -np.linspace(0.5, 2.0, n // 2)])  # exact +-lambda pairs
+        q, _ = np.linalg.qr(a)
+        h = (q * w) @ q.conj().T
+        h = (h + h.conj().T) / 2
+        assert rel_err(E.map_eigvals("inv", h, ctx=ctx), np.linalg.inv(h)) < 1e-10
+        assert rel_err(E.map_eigvals("sqrt", h, ctx=ctx), ref(np.sqrt, h)) < 1e-10
+        # batch mixing a PSD and an indefinite matrix: only the indefinite one takes the shifted route
+        p = a @ a.conj().T
+        out = E.map_eigvals("inv", np.stack([p, h]), ctx=ctx)
+        assert rel_err(out[0], np.linalg.inv(p)) < 1e-8 and rel_err(out[1], np.linalg.inv(h)) < 1e-10
+
+
 CASES = [
     # name, graph, chi, bp iterations, edge, maxdim, cutoff
     ("grid3x3_chi3_notrunc", lambda: O.grid_graph((3, 3)), 3, 8, 5, None, None),

@@ -235,6 +235,57 @@ def test_dmma_fast_path_chi16(dtype):
         assert abs(ez[v] - O.expect1(net, msgs, v, O.PAULI_Z)) < TOL
 
 
+def test_synchronous_sequence_with_a_repeated_edge(ctx):
+    # the reference accepts arbitrary edge lists: a synchronous sequence that lists a directed edge twice computes it
+    # twice from the pre-sweep messages (same result); the tile path must not take such a vertex (two staged buffers
+    # for one slot), the generic path handles every listed update
+    g = O.grid_graph((4, 4))
+    net, psi = make_pair(g, 16, np.complex128)
+    seq = O.parallel_edge_sequence(g)
+    dup = [e for e in seq if e[0] == 5][:1]  # vertex 5 has degree 4
+    seq2 = seq + dup
+    msgs, _, diff_o = O.bp_update(net, O.identity_messages(net), seq=seq2, groups=O.synchronous_groups(seq2), maxiter=2, tol=0.0)
+    info = {}
+    bpc = E.update(E.BeliefPropagationCache(psi, ctx=ctx), maxiter=2, tol=0.0, edge_sequence=[[e] for e in seq2], info=info)
+    assert_messages_close(bpc, msgs, TOL)
+    assert abs(info["mean_diff"] - diff_o) < 1e-12
+
+
+GROUPED = [
+    ("grid3x3_pairs", lambda: O.grid_graph((3, 3)), 3, 2),
+    ("grid4x4_by_vertex", lambda: O.grid_graph((4, 4)), 2, 0),
+    ("cubic2_triples", lambda: O.grid_graph((2, 2, 2)), 2, 3),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name,mk,chi,gsize", GROUPED, ids=[c[0] for c in GROUPED])
+def test_grouped_schedule_with_multi_edge_groups(ctx, dtype, name, mk, chi, gsize):
+    # update_iteration(alg, bpc, edge_groups) (abstractbeliefpropagationcache.jl:294-308, intended semantics): every group
+    # is a SEQUENTIAL pass over its edges starting from the pre-sweep messages; the results of all groups are written at
+    # the end of the sweep; the diff is divided by the number of groups (:319-321)
+    g = mk()
+    net, psi = make_pair(g, chi, dtype)
+    seq = O.default_edge_sequence(g)  # an order in which later edges of a group read earlier ones
+    if gsize == 0:   # one group per source vertex
+        by_v = {}
+        for e in seq:
+            by_v.setdefault(e[0], []).append(e)
+        groups = list(by_v.values())
+    else:
+        groups = [seq[i:i + gsize] for i in range(0, len(seq), gsize)]
+    flat = [e for grp in groups for e in grp]
+    ptr = np.cumsum([0] + [len(grp) for grp in groups])
+    ranges = [(int(ptr[i]), int(ptr[i + 1])) for i in range(len(groups))]
+    for it in (1, 3):
+        msgs, _, diff_o = O.bp_update(net, O.identity_messages(net), seq=flat, groups=ranges, maxiter=it, tol=0.0)
+        info = {}
+        bpc = E.update(E.BeliefPropagationCache(psi, ctx=ctx), maxiter=it, tol=0.0, edge_sequence=[list(grp) for grp in groups],
+                       info=info)
+        assert_messages_close(bpc, msgs, TOL)
+        assert abs(info["mean_diff"] - diff_o) < 1e-12, (info["mean_diff"], diff_o)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("dims,chi", [((6, 6), 16), ((4, 4), 3), ((9, 8), 16)], ids=["grid6_chi16", "grid4_chi3", "grid9x8_chi16"])
 def test_deferred_upload_first_sweep_overlaps_copy(dtype, dims, chi, monkeypatch):

@@ -1,6 +1,11 @@
-"""Full-size checks (BASELINE.json configs 2 and 4) through size-independent properties: the oracle cannot run
-these sizes in seconds, so the checks are the reference's own property tests (test_belief_propagation.jl:51-53,
-90-91; test_normalize.jl:60-66) plus a device-side second opinion (DMMA kernels vs generic kernels)."""
+"""Full-size checks of BASELINE.json configs 2, 3, 4, 5 against the oracle.
+
+Config 2 (32x32, chi=8) and config 3 (heavy-hex, chi=32) are small enough for the oracle to run whole sweeps: messages,
+<Z> and <ZZ> are compared at 1e-10 (north_star's requirement).  Configs 4 (64x64, chi=16) and 5 (16^3, chi=6) are
+compared on a SAMPLE: the messages into sampled vertices are downloaded, one more production sweep runs on the device,
+and every sampled outgoing message must equal the oracle's updated_message on the downloaded inputs (bench.py's
+`sampled_parity`, the same check the bench line reports); size-independent properties (fixed-point residual, Hermitian
+PSD messages, rescale => all region scalars 1) cover the rest."""
 import numpy as np
 import pytest
 
@@ -10,26 +15,45 @@ pytestmark = pytest.mark.gpu
 EPS = np.finfo(np.float64).eps
 
 
-def torch_random_psi(g, chi, d=2, seed=1234):
+def bench_psi(g, chi, dtype=np.complex128, d=2):
+    """bench.py's synthetic state (one generator per vertex), so the tests check the bytes the bench times."""
     import torch
-    gen = torch.Generator().manual_seed(seed)
-    ts = []
-    for v in range(g.nv):
-        n = d * chi ** g.degree(v)
-        flat = torch.randn(2 * n, generator=gen, dtype=torch.float64).numpy().view(np.complex128) * 2 ** -0.5
-        ts.append(np.ndarray((d,) + (chi,) * g.degree(v), dtype=np.complex128, buffer=flat, order="F"))
-    return E.ITensorNetwork(g, ts, np.complex128)
+
+    import bench
+    tensors, _host, _ = bench.make_psi(torch, g, chi, dtype, d, [True] * g.nv)
+    return tensors, E.ITensorNetwork(g, tensors, dtype)
 
 
-def test_config2_grid32_chi8_converges_and_observables_are_consistent():
+def test_config2_grid32_chi8_messages_and_observables_match_oracle():
+    from oracle import itn_oracle as O
+    go = O.grid_graph((32, 32))
     g = E.named_grid((32, 32))
-    psi = torch_random_psi(g, 8)
+    assert go.edges == g.edges
+    tensors, psi = bench_psi(g, 8)
+    net = O.Network(go, [np.ascontiguousarray(t) for t in tensors], np.complex128)
     ctx = E.Context(0)
-    info = {}
-    bpc = E.update(E.BeliefPropagationCache(psi, ctx=ctx), maxiter=60, tol=1e-14, edge_sequence=E.parallel_edge_sequence(g),
-                   info=info)
-    assert info["iterations"] < 60 and info["mean_diff"] <= 1e-14
+    seq = O.parallel_edge_sequence(go)
+    nsw = 10
+    msgs, _, _ = O.bp_update(net, O.identity_messages(net), seq=seq, groups=O.synchronous_groups(seq), maxiter=nsw)
+    bpc = E.BeliefPropagationCache(psi, ctx=ctx)
+    E.update(bpc, maxiter=nsw, edge_sequence=[[e] for e in seq], inplace=True)
+    worst = max(np.linalg.norm(bpc.message(k) - m) / np.linalg.norm(m) for k, m in msgs.items())
+    assert worst < 1e-10, worst
+    ez = E.expect(bpc, "Z")
     rng = np.random.default_rng(0)
+    verts = list(rng.choice(g.nv, 64, replace=False)) + [0, 31, 1023]
+    for v in verts:
+        assert abs(ez[int(v)] - O.expect1(net, msgs, int(v), O.PAULI_Z)) < 1e-10, v
+    eids = [int(i) for i in rng.choice(g.ne, 24, replace=False)]
+    zz = E.expect2(bpc, eids, "Z", "Z")
+    for e, got in zip(eids, zz):
+        assert abs(got - O.expect2(net, msgs, e, O.PAULI_Z, O.PAULI_Z)) < 1e-10, e
+    lz, lo = E.logscalar(bpc), O.logscalar(net, msgs)
+    assert abs(lz - lo) < 1e-10 * abs(lo)
+    # and to convergence: the reference's property tests at this size
+    info = {}
+    bpc = E.update(bpc, maxiter=60, tol=1e-14, edge_sequence=[[e] for e in seq], info=info)
+    assert info["iterations"] < 60 and info["mean_diff"] <= 1e-14
     edges = [g.edges[i] for i in rng.choice(g.ne, 40, replace=False)]
     res = E.message_residuals(bpc, edges + [(v, u) for u, v in edges])
     assert np.max(res) < 1e-12  # fixed point (second order in the message error)
@@ -41,36 +65,39 @@ def test_config2_grid32_chi8_converges_and_observables_are_consistent():
     zv, ze = E.scalar_factors_quotient(r)
     assert np.allclose(zv, 1.0, atol=1e-10) and np.allclose(ze, 1.0, atol=1e-10)
     assert abs(E.scalar(r) - 1.0) < 1e-8
-    ez = E.expect(bpc, "Z")
-    vals = np.array([ez[v] for v in range(g.nv)])
-    assert np.all(np.abs(vals.imag) < 1e-8) and np.all(np.abs(vals.real) <= 1 + 1e-10)
-    rho = E.rdm2(bpc, [0, 100, 1000])
-    for m in rho:
-        assert abs(np.trace(m) - 1) < 1e-10 and np.min(np.linalg.eigvalsh((m + m.conj().T) / 2)) > -1e-8
 
 
-def test_config4_grid64_chi16_dmma_sweep_equals_generic_updates():
-    g = E.named_grid((64, 64))
-    psi = torch_random_psi(g, 16)
+def _sampled_fullsize(dims, chi, nsample, max_contract_ms=None):
+    import bench
+    g = E.named_grid(dims)
+    tensors, psi = bench_psi(g, chi)
     ctx = E.Context(0)
     seq = E.parallel_edge_sequence(g)
     bpc = E.BeliefPropagationCache(psi, ctx=ctx)
-    del psi
     E.update(bpc, maxiter=3, edge_sequence=seq, inplace=True)
-    rng = np.random.default_rng(1)
-    sample = [g.edges[i] for i in rng.choice(g.ne, 24, replace=False)]
-    sample = sample + [(v, u) for u, v in sample[:8]]
-    ctx.set_path(1)  # generic kernels for the single-message updates
-    expected = {e: E.updated_message(bpc, e) for e in sample}
-    ctx.set_path(0)
-    info = {}
-    E.update(bpc, maxiter=1, tol=0.0, edge_sequence=seq, inplace=True, info=info)  # one more DMMA sweep
-    for e, m in expected.items():
-        got = bpc.message(e)
-        assert np.linalg.norm(got - m) < 1e-11 * np.linalg.norm(m), e
-    assert 0.0 <= info["mean_diff"] < 1.0
+    err, n = bench.sampled_parity(E, bpc, tensors, g, seq, [True] * g.nv, nsample=nsample)
+    assert n >= nsample - 4 and err < 1e-10, (err, n)
     tm = bpc.last_timing()
-    assert tm["contract_ms"] < 200.0  # the DMMA path ran (the generic kernels need ~350 ms per sweep)
+    if max_contract_ms is not None:
+        assert tm["contract_ms"] < max_contract_ms, tm
+    # size-independent properties of the same state
+    rng = np.random.default_rng(1)
+    edges = [g.edges[i] for i in rng.choice(g.ne, 6, replace=False)]
+    for (u, v) in edges:
+        m = bpc.message((u, v))
+        assert abs(np.linalg.norm(m) - 1.0) < 1e-12  # normalised (abstractbeliefpropagationcache.jl:234-237)
+    lz = E.logscalar(bpc)
+    assert np.isfinite(np.real(lz))
+    bpc.close()
+
+
+def test_config4_grid64_chi16_sampled_messages_match_oracle():
+    # the DMMA sweep at full size against the ORACLE (not against another CUDA path)
+    _sampled_fullsize((64, 64), 16, 24, max_contract_ms=200.0)  # the tile path ran (the generic kernels need ~350 ms per sweep)
+
+
+def test_config5_cubic16_chi6_sampled_messages_match_oracle():
+    _sampled_fullsize((16, 16, 16), 6, 20)
 
 
 def test_config3_heavyhex_chi32_bp_and_gate_layer_match_oracle():
