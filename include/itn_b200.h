@@ -218,8 +218,17 @@ int itn_tensordot(itn_ctx* ctx, int dtype, const void* a_host, int nda, const in
 int itn_svd_batch(itn_ctx* ctx, int dtype, int m, int n, int batch, const void* host_in, double* host_sigma,
                   void* host_us, int variant, double* device_ms);
 
+/* The block geometry, operation lists and shared-memory fibre tables the block path (csrc/itn_block.cu) uses for a vertex
+ * with site dimension d, degree z and bond extents chi[0..z) in a bucket of `nverts` vertices, as a flat int32 stream
+ * (layout: csrc/itn_block.cu).  Host only: needs no device.  *nout = number of entries (0: the signature has no plan and
+ * runs on the shape-generic kernels); `out` is filled when cap >= *nout.  tests/block_emulator.py replays it in NumPy. */
+int itn_block_plan_export(int dtype, int d, int z, const int32_t* chi, int nverts, int32_t* out, int cap, int32_t* nout);
+
 /* Number of kernels this library has launched on ctx since creation (bench.py "gpu_launches"). */
 int itn_ctx_launch_count(const itn_ctx* ctx, int64_t* out);
+/* Message updates computed so far on ctx by {the degree-4 chi=16 tile path (csrc/itn_fast.cu), the block path
+ * (csrc/itn_block.cu), the shape-generic per-message / per-vertex kernels (csrc/itn_generic.cu)}: which kernels ran. */
+int itn_ctx_path_counts(const itn_ctx* ctx, int64_t* out3);
 /* Select the message-update implementation: 0 = auto (DMMA tile path where a bucket qualifies, the shape-generic
  * DMMA kernels otherwise), 1 = shape-generic DMMA kernels only, 2 = plain FMA kernels only (the parity tests use
  * 1 and 2 as second and third opinions on the device). */

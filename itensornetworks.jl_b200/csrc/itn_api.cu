@@ -712,6 +712,7 @@ static void free_net_storage(itn_net* net) {
   for (auto& m : net->M)
     if (m.p) itn_tensor_free(net->ctx, m);
   itn_fast_release(net);
+  itn_block_release(net);
   itn_dist_release(net);
 }
 
@@ -734,6 +735,7 @@ extern "C" int itn_net_clone(const itn_net* src, itn_net** out) {
   itn_flush_pending(const_cast<itn_net*>(src));
   std::unique_ptr<itn_net> net(new itn_net(*src));
   net->fast = nullptr;
+  net->block = nullptr;
   net->dist = nullptr;
   for (auto& t : net->T) t.p = nullptr, t.slab = nullptr;
   for (auto& t : net->Tb) t.p = nullptr, t.slab = nullptr;
@@ -1553,6 +1555,8 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   // synchronous sweeps: vertices that qualify go to the DMMA kernels, the rest to the generic kernels
   std::vector<char> handled;
   const int nfast = sync_mode ? itn_fast_bp_plan(net, all_dids, all_src, handled) : 0;
+  // vertices the tile path did not take: the block path (itn_block.cu) for every degree 2..8 / bond extent <= 32
+  const int nblock = sync_mode ? itn_block_bp_plan(net, all_dids, all_src, handled) : 0;
   // the rest of a synchronous sweep: vertices whose outgoing messages are all part of it go to the vertex-level DMMA
   // sweep (shared partial absorptions, itn_run_vertex_sweeps), whatever is left to the per-message kernels
   std::vector<JobSpec> slow_specs;
@@ -1631,9 +1635,20 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
     }
     if (!pipelined_first) {
       itn_flush_pending(net);
-      if (nfast > 0) itn_fast_bp_plan(net, all_dids, all_src, handled);  // rebuild the tile-major copies
+      if (nfast > 0) {  // rebuild the tile-major copies (the block path's share of `handled` is kept)
+        std::vector<char> h1;
+        itn_fast_bp_plan(net, all_dids, all_src, h1);
+      }
     }
   }
+  struct BlockCall {  // per-call buffers of the block path, released on every exit
+    itn_net* net;
+    bool on;
+    ~BlockCall() {
+      if (on) itn_block_bp_end(net);
+    }
+  } block_call{net, nblock > 0};
+  if (nblock > 0) itn_block_bp_begin(net, all_dids, all_src, handled, staged.ptr.data());
 
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
@@ -1672,10 +1687,12 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
             itn_fast_bp_sweep_range(net, swept, ns);
           }
           itn_fast_bp_sweep_end(net);
+          if (nblock > 0) itn_block_bp_run(net);
           itn_run_vertex_sweeps(net, vsweeps);
           itn_run_vertex_jobs(net, slow_specs);
         } else if (sync_mode) {
           if (nfast > 0) itn_fast_bp_sweep(net, all_dids, all_src, handled, staged.ptr.data());
+          if (nblock > 0) itn_block_bp_run(net);
           itn_run_vertex_sweeps(net, vsweeps);
           itn_run_vertex_jobs(net, slow_specs);
         } else {
@@ -1691,6 +1708,13 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
       }
       if (ctx->nranks > 1) itn_dist_exchange(net, global_dids);
       ++done;
+      if (sync_mode) {
+        ctx->path_msgs[0] += nfast;
+        ctx->path_msgs[1] += nblock;
+        ctx->path_msgs[2] += nseq - nfast - nblock;
+      } else {
+        ctx->path_msgs[2] += nseq;
+      }
       if (want_diff) {
         k_sum_fixed<<<1, 256, 0, ctx->stream>>>(diffs.as<double>(), nseq, dsum.as<double>());
         ITN_LAUNCH_CHECK(ctx);
@@ -1725,6 +1749,13 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   for (auto e : cev) cudaEventDestroy(e);
   if (iters) *iters = done;
   if (last_mean_diff) *last_mean_diff = mean;
+  API_END
+}
+
+extern "C" int itn_ctx_path_counts(const itn_ctx* ctx, int64_t* out3) {
+  API_BEGIN
+  ITN_REQUIRE(ctx && out3, ITN_EINVAL, "NULL argument");
+  for (int i = 0; i < 3; ++i) out3[i] = ctx->path_msgs[i];
   API_END
 }
 

@@ -1,0 +1,1266 @@
+// Block path for synchronous BP sweeps: any degree 2..8, any per-bond extent <= 32, real or complex, on the canonical
+// tensor layout (no tile-major copies).
+//
+// Restates updated_message(::Algorithm"contract") (src/caches/abstractbeliefpropagationcache.jl:225-239) for ALL z
+// outgoing messages of a vertex, with the bond set split into a fast group G1 (the first ceil(z/2) bonds, small strides)
+// and a slow group G2 (the rest), and three passes over the tensor:
+//
+//   pass 1  P = A x_{G1} M                                              (blocks: all of G1, a chunk of G2's flat index)
+//   pass 2  out_k = < P x_{G2 \ k} M | A >  for k in G2,   S = A x_{G2} M    (blocks: a chunk of (site, G1), all of G2)
+//   pass 3  out_k = < S x_{G1 \ k} M | A >  for k in G1                   (blocks as in pass 1)
+//
+// "x_j M" is a mode product with the message arriving on bond j, "< B | A >" closes every index except bond k against the
+// conjugated site tensor.  Inside a pass a CTA stages one block of the tensor(s) in shared memory ONCE (cp.async.bulk, one
+// bulk copy per contiguous row, completion on an mbarrier) and runs the whole operation list of the pass on it --
+// several mode products and closes per byte moved, where the shape-generic kernels of itn_generic.cu make one pass over
+// HBM per mode product.  The "all but one" products inside a group share their partial products by divide and conquer
+// (z = 6: 22 units of d chi^7 multiply-adds instead of the 36 of six independent updates; z = 4: 12 of 16; z = 3: 8 of 9).
+//
+// Arithmetic: FP64 tensor-core DMMA in the m8n8k4 shape (mma.sync.aligned.m8n8k4.f64: measured at the full 37 TFLOP/s
+// issue rate on B200, tools/fp64_peak.cu).  The k = 4 shape is what makes chi = 6 affordable: a complex mode product is
+// the REAL product [X_re | X_im] (fibres x 2 chi) times [[M_re, M_im], [-M_im, M_re]] (2 chi x 2 chi), so the reduction
+// length is 2 chi = 12 = three k4 steps with no padding (m16n8k8 pads 12 -> 16 and 6 -> 8: 1.78x the flops; here only the
+// output rows 6 -> 8 pad: 1.33x).  The message fragments sit in REGISTERS for the whole operation (the message is the A
+// operand, 8 output rows x 4 reduction entries per step); the tensor is the B operand, 8 fibres per tile, read from and
+// written back to shared memory.  Closes put the bond index on both M and N and reduce over fibres (k = 4 fibres per step).
+//
+// Shared-memory addressing is table driven: for every mode of the pass the host lists the base address of every fibre of
+// the block, ordered so that the four fibres a half-warp touches together with the four reduction entries of a step fall
+// into 16 different banks whenever the block geometry allows it (plan_fibres below; padding of the row and plane strides
+// is part of the search).
+#include <algorithm>
+#include <array>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+
+#include "itn_internal.h"
+
+namespace {
+
+constexpr int kBT = 256;       // threads per CTA (8 warps)
+constexpr int kNW = kBT / 32;
+constexpr int kMaxGM = 4;      // bonds per group
+constexpr int kMaxOps = 48;
+constexpr int kRedDoubles = 1024;  // close: partial tiles of the fibre splits before the fixed-order sum (chi <= 16)
+constexpr unsigned kNoFibre = 0xFFFFu;
+
+enum { OP_MP = 0, OP_CLOSE = 1, OP_STORE = 2 };
+
+struct BlkOp {
+  unsigned char type, src, dst, mode;  // MP: dst = src x_mode M; CLOSE: out_mode = <src | buffer 0>; STORE: src -> Wout
+};
+struct BlkMode {
+  int chi;    // extent of the bond
+  int S;      // shared-memory stride of the bond index inside the block
+  int ntile;  // fibre tiles (8 fibres each; the table is padded with kNoFibre)
+  int tab;    // offset of the fibre table of this mode (entries)
+  int slot;   // bond slot at the vertex (message / output index)
+};
+struct BlkPass {
+  int nblk;           // blocks per vertex
+  int nrows, rowlen;  // rows per plane and doubles per row moved between HBM and shared memory (a row is contiguous in both)
+  long long grow;     // HBM row stride (doubles)
+  long long gblk;     // HBM offset between consecutive blocks (doubles)
+  long long gplane;   // HBM plane stride = elements of the tensor
+  int nlev;           // shared-memory position of row r: sum over levels of digit_l(r) * lev_s[l], r in mixed radix lev_n
+  int lev_n[4];       //   (padded strides keep every bond stride away from multiples of 8 doubles = the bank period / 2)
+  int lev_s[4];
+  int PL;             // shared-memory plane stride (doubles)
+  int bufsz;          // doubles per buffer (planes * PL)
+  int nbuf;
+  int bulk;           // 1: cp.async.bulk per row, 0: per-thread copies (rows that are not multiples of 16 bytes)
+  int load_p;         // the pass also loads the partially absorbed tensor (buffer 1)
+  int nmodes;
+  BlkMode modes[kMaxGM];
+  int nops;
+  BlkOp ops[kMaxOps];
+  int tab_len;
+};
+struct BlkVertex {
+  const double* X;     // site tensor (canonical planar)
+  const double* Pin;   // partially absorbed tensor read by the pass (pass 2: P, pass 3: S)
+  double* Wout;        // partially absorbed tensor written by the pass (pass 1: P, pass 2: S)
+  const double* msg[8];
+  double* part[8];     // per bond slot: nblk partial messages (planar chi x chi each), summed by k_block_reduce
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// ---- dst = src x_mode M  (message = A operand in registers, tensor = B operand, 8 fibres per tile) ----------------------
+// Complex products run as real ones on the stacked reduction index.  Two stackings:
+//   packed  (KS <= 4, chi <= 8): [re 0..chi-1 | im 0..chi-1] back to back, ceil(2 chi / 4) steps: chi = 6 needs 3 steps, not 4;
+//           fragments A_re = [M_re ; -M_im], A_im = [M_im ; M_re] (2 KS registers of doubles)
+//   aligned (KS >= 8): each plane padded to KS / 2 steps of its own; the sign moves to the tensor operand
+//           (out_re = M_re^T X_re + M_im^T (-X_im), out_im = M_im^T X_re + M_re^T X_im), so only M_re and M_im are kept:
+//           KS doubles of fragments instead of 2 KS (chi = 32: 64 registers instead of 128)
+template <bool C, int KS>
+__device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const double* __restrict__ msg, const double* src,
+                                      double* dst, const unsigned short* __restrict__ tab, const int warp, const int lane) {
+  constexpr bool AL = C && KS >= 8;
+  constexpr int KH = AL ? KS / 2 : KS;  // fragments per array
+  const int chi = M.chi, S = M.S;
+  const int mtj = (chi + 7) >> 3;
+  const int mtd = mtj == 3 ? 4 : mtj;  // warps are dealt out over 1, 2 or 4 row tiles
+  const int mt = warp % mtd, fsub = warp / mtd, fstep = kNW / mtd;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = mt * 8 + g;
+  if (mt >= mtj) return;
+  const int chi2 = chi * chi;
+  const int K2 = (C && !AL) ? 2 * chi : chi;  // length of the (stacked) reduction index walked by ks
+  const int ksj = (K2 + 3) >> 2;
+  double A0[KH], A1[C ? KH : 1];
+#pragma unroll
+  for (int ks = 0; ks < KH; ++ks) {
+    const int kk = 4 * ks + t;
+    A0[ks] = 0.0;
+    if (C) A1[ks] = 0.0;
+    if (ks < ksj && kk < K2 && b < chi) {
+      if (!C) {
+        A0[ks] = msg[kk + chi * b];
+      } else if (AL) {
+        A0[ks] = msg[kk + chi * b];          // M_re
+        A1[ks] = msg[chi2 + kk + chi * b];   // M_im
+      } else if (kk < chi) {
+        A0[ks] = msg[kk + chi * b];          // A_re
+        A1[ks] = msg[chi2 + kk + chi * b];   // A_im
+      } else {
+        A0[ks] = -msg[chi2 + (kk - chi) + chi * b];
+        A1[ks] = msg[(kk - chi) + chi * b];
+      }
+    }
+  }
+  const unsigned short* tb = tab + M.tab;
+  for (int ft = fsub; ft < M.ntile; ft += fstep) {
+    const unsigned fb = tb[ft * 8 + g];
+    const bool fok = fb != kNoFibre;
+    double cre[2] = {0.0, 0.0}, cim[2] = {0.0, 0.0};
+    if (AL) {
+      double xr[KH], xi[KH];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks) {
+        const int kk = 4 * ks + t;
+        const bool ok = fok && ks < ksj && kk < chi;
+        xr[ks] = ok ? src[fb + kk * S] : 0.0;
+        xi[ks] = ok ? src[PL + fb + kk * S] : 0.0;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks) {
+        if (ks < ksj) {
+          dmma884(cre, A0[ks], xr[ks]);
+          dmma884(cim, A1[ks], xr[ks]);
+          dmma884(cim, A0[ks], xi[ks]);
+          dmma884(cre, A1[ks], -xi[ks]);
+        }
+      }
+    } else {
+      double bv[KH];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks) {
+        const int kk = 4 * ks + t;
+        const bool ok = fok && ks < ksj && kk < K2;
+        const int off = (!C || kk < chi) ? kk * S : PL + (kk - chi) * S;
+        bv[ks] = ok ? src[fb + off] : 0.0;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks) {
+        if (ks < ksj) {
+          dmma884(cre, A0[ks], bv[ks]);
+          if (C) dmma884(cim, A1[ks], bv[ks]);
+        }
+      }
+    }
+    const unsigned f0 = __shfl_sync(0xffffffffu, fb, 8 * t), f1 = __shfl_sync(0xffffffffu, fb, 8 * t + 4);
+    if (src == dst) __syncwarp();  // in place (one row tile per fibre): every lane has read its fibres
+    if (b < chi) {
+      if (f0 != kNoFibre) {
+        dst[f0 + b * S] = cre[0];
+        if (C) dst[PL + f0 + b * S] = cim[0];
+      }
+      if (f1 != kNoFibre) {
+        dst[f1 + b * S] = cre[1];
+        if (C) dst[PL + f1 + b * S] = cim[1];
+      }
+    }
+  }
+}
+
+// ---- out[b + chi b'] = sum over the fibres of the block  W[f, b] conj(X[f, b'])  (4 fibres per k step) -------------------
+template <bool C, int MT>
+__device__ __forceinline__ void op_close(const BlkMode M, const int PL, const double* W, const double* X, double* red,
+                                         double* __restrict__ out, const unsigned short* __restrict__ tab, const int warp,
+                                         const int lane, const int tid) {
+  constexpr int NPW = MT == 4 ? 2 : 1;
+  const int chi = M.chi, S = M.S;
+  const int mtj = (chi + 7) >> 3;
+  const int mtd = mtj == 3 ? 4 : mtj;
+  const int g = lane >> 2, t = lane & 3;
+  int mt, nt0, fs, FS;
+  if (mtd == 1) {
+    mt = 0; nt0 = 0; fs = warp; FS = kNW;
+  } else if (mtd == 2) {
+    mt = (warp & 3) >> 1; nt0 = warp & 1; fs = warp >> 2; FS = 2;
+  } else {
+    mt = warp >> 1; nt0 = (warp & 1) * 2; fs = 0; FS = 1;
+  }
+  const int npw = mtd == 4 ? 2 : 1;
+  const int CH = mtd * 8;
+  double acc[NPW][2][2];
+#pragma unroll
+  for (int q = 0; q < NPW; ++q) acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0;
+  const unsigned short* tb = tab + M.tab;
+  const int nks = M.ntile * 2;
+  const int bm = mt * 8 + g;
+  for (int ks = fs; ks < nks; ks += FS) {
+    const unsigned fb = tb[ks * 4 + t];
+    const bool ok = fb != kNoFibre;
+    const bool okm = ok && bm < chi;
+    const double wre = okm ? W[fb + bm * S] : 0.0;
+    const double wim = (C && okm) ? W[PL + fb + bm * S] : 0.0;
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+      if (q < npw) {
+        const int bn = (nt0 + q) * 8 + g;
+        const bool okn = ok && bn < chi;
+        const double xre = okn ? X[fb + bn * S] : 0.0;
+        dmma884(acc[q][0], wre, xre);
+        if (C) {
+          const double xim = okn ? X[PL + fb + bn * S] : 0.0;
+          dmma884(acc[q][0], wim, xim);
+          dmma884(acc[q][1], wim, xre);
+          dmma884(acc[q][1], -wre, xim);
+        }
+      }
+    }
+  }
+  if (mtd == 4) {
+    // one warp owns a pair of 8 x 8 tiles over ALL fibres of the block: no cross-warp sum, straight to the partial buffer
+    const int n2 = chi * chi;
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+      const int row = mt * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = (nt0 + q) * 8 + 2 * t + j;
+        if (row < chi && col < chi) {
+          out[row + chi * col] = acc[q][0][j];
+          if (C) out[n2 + row + chi * col] = acc[q][1][j];
+        }
+      }
+    }
+    return;
+  }
+  // partial tiles of the fibre splits meet in shared memory and are summed in split order
+  const int ch2 = CH * CH;
+#pragma unroll
+  for (int q = 0; q < NPW; ++q) {
+    if (q < npw) {
+      double* r = red + (size_t)fs * (C ? 2 : 1) * ch2;
+      const int row = mt * 8 + g, col = (nt0 + q) * 8 + 2 * t;
+      r[row + CH * col] = acc[q][0][0];
+      r[row + CH * (col + 1)] = acc[q][0][1];
+      if (C) {
+        r[ch2 + row + CH * col] = acc[q][1][0];
+        r[ch2 + row + CH * (col + 1)] = acc[q][1][1];
+      }
+    }
+  }
+  __syncthreads();
+  const int n2 = chi * chi;
+  for (int i = tid; i < (C ? 2 : 1) * n2; i += kBT) {
+    const int p = i / n2, o = i - p * n2;
+    const int row = o % chi, col = o / chi;
+    double a = 0.0;
+    for (int s = 0; s < FS; ++s) a += red[(size_t)(s * (C ? 2 : 1) + p) * ch2 + row + CH * col];
+    out[i] = a;
+  }
+}
+
+template <bool C, int KS, int MT>
+__global__ void __launch_bounds__(kBT, 2) k_block(const BlkPass* __restrict__ gp, const BlkVertex* __restrict__ gv,
+                                                  const unsigned short* __restrict__ gtab) {
+  extern __shared__ __align__(128) double sm[];
+  __shared__ BlkPass P;
+  __shared__ BlkVertex V;
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const int* s = (const int*)gp;
+    int* d = (int*)&P;
+    for (int i = tid; i < (int)(sizeof(BlkPass) / 4); i += kBT) d[i] = s[i];
+  }
+  __syncthreads();
+  const int vi = blockIdx.x / P.nblk, blk = blockIdx.x - vi * P.nblk;
+  {
+    const int* s = (const int*)(gv + vi);
+    int* d = (int*)&V;
+    for (int i = tid; i < (int)(sizeof(BlkVertex) / 4); i += kBT) d[i] = s[i];
+  }
+  double* bufs = sm;
+  double* red = bufs + (size_t)P.nbuf * P.bufsz;
+  unsigned short* tab = (unsigned short*)(red + kRedDoubles);
+  for (int i = tid; i < P.tab_len; i += kBT) tab[i] = gtab[i];
+  constexpr int PLN = C ? 2 : 1;
+  const unsigned mb = smem_u32(&mbar);
+  if (P.bulk && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  // ---- stage the block(s): buffer 0 = site tensor, buffer 1 = partially absorbed tensor ---------------------------------
+  auto row_pos = [&](int row) {
+    int off = 0, q = row;
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (l < P.nlev) {
+        const int dg = q % P.lev_n[l];
+        q /= P.lev_n[l];
+        off += dg * P.lev_s[l];
+      }
+    return off;
+  };
+  const long long goff = (long long)blk * P.gblk;
+  const int nin = P.load_p ? 2 : 1;
+  const int rows_total = nin * PLN * P.nrows;
+  if (P.bulk) {
+    const unsigned rowbytes = (unsigned)P.rowlen * 8u;
+    if (tid == 0) {
+      const unsigned total = rowbytes * (unsigned)rows_total;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(total) : "memory");
+    }
+    for (int r = tid; r < rows_total; r += kBT) {
+      const int which = r / (PLN * P.nrows), rr = r - which * (PLN * P.nrows);
+      const int pl = rr / P.nrows, row = rr - pl * P.nrows;
+      const double* g = (which ? V.Pin : V.X) + (long long)pl * P.gplane + goff + (long long)row * P.grow;
+      const unsigned dsts = smem_u32(bufs + (size_t)which * P.bufsz + (size_t)pl * P.PL + row_pos(row));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dsts),
+                   "l"(g), "r"(rowbytes), "r"(mb)
+                   : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(mb), "r"(0u)
+          : "memory");
+    }
+  } else {
+    const long long tot = (long long)rows_total * P.rowlen;
+    for (long long i = tid; i < tot; i += kBT) {
+      const int r = (int)(i / P.rowlen), c = (int)(i - (long long)r * P.rowlen);
+      const int which = r / (PLN * P.nrows), rr = r - which * (PLN * P.nrows);
+      const int pl = rr / P.nrows, row = rr - pl * P.nrows;
+      bufs[(size_t)which * P.bufsz + (size_t)pl * P.PL + row_pos(row) + c] =
+          (which ? V.Pin : V.X)[(long long)pl * P.gplane + goff + (long long)row * P.grow + c];
+    }
+  }
+  __syncthreads();
+  // ---- the operation list of the pass --------------------------------------------------------------------------------
+  for (int oi = 0; oi < P.nops; ++oi) {
+    const BlkOp op = P.ops[oi];
+    if (op.type == OP_MP) {
+      const BlkMode M = P.modes[op.mode];
+      op_mp<C, KS>(M, P.PL, V.msg[M.slot], bufs + (size_t)op.src * P.bufsz, bufs + (size_t)op.dst * P.bufsz, tab, warp, lane);
+    } else if (op.type == OP_CLOSE) {
+      const BlkMode M = P.modes[op.mode];
+      double* out = V.part[M.slot] + (size_t)blk * PLN * M.chi * M.chi;
+      op_close<C, MT>(M, P.PL, bufs + (size_t)op.src * P.bufsz, bufs, red, out, tab, warp, lane, tid);
+    } else {
+      const double* b = bufs + (size_t)op.src * P.bufsz;
+      const long long tot = (long long)PLN * P.nrows * P.rowlen;
+      for (long long i = tid; i < tot; i += kBT) {
+        const int r = (int)(i / P.rowlen), c = (int)(i - (long long)r * P.rowlen);
+        const int pl = r / P.nrows, row = r - pl * P.nrows;
+        V.Wout[(long long)pl * P.gplane + goff + (long long)row * P.grow + c] = b[(size_t)pl * P.PL + row_pos(row) + c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// staged message = sum of the per-block partials, in block order (deterministic)
+struct BlkRedJob {
+  const double* part;
+  double* out;
+  int nblk, n;  // n = planes * chi^2
+};
+__global__ void __launch_bounds__(128) k_block_reduce(const BlkRedJob* __restrict__ jobs) {
+  const BlkRedJob J = jobs[blockIdx.x];
+  for (int i = threadIdx.x; i < J.n; i += blockDim.x) {
+    double a = 0.0;
+    for (int b = 0; b < J.nblk; ++b) a += J.part[(size_t)b * J.n + i];
+    J.out[i] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// host side: buckets, block geometry, fibre tables, operation lists
+// ------------------------------------------------------------------------------------------------------------------------
+struct Signature {
+  int d, z;
+  std::array<int, 8> chi;
+  bool operator<(const Signature& o) const { return std::tie(d, z, chi) < std::tie(o.d, o.z, o.chi); }
+};
+
+struct ModeGeom {
+  int chi, S, slot;
+  std::vector<int> bases;  // base address of every fibre of the block
+};
+
+inline int mod16(int x) { return ((x % 16) + 16) % 16; }
+
+// Orders the fibres of one mode into tiles of 8 so that the shared-memory accesses of op_mp / op_close are conflict free
+// when the geometry allows it.  Access patterns, per half-warp (16 lanes of 8 bytes = one wavefront when all banks differ):
+//   loads   fibres n = 0..3 (and 4..7) of a tile  x  the four reduction entries of a k step  (op_mp B operand; op_close
+//           reads the same quads with the roles of fibre and entry exchanged)
+//   stores  fibres n = 0, 2, 4, 6 (and 1, 3, 5, 7) of a tile  x  four consecutive output rows
+// Returns the table (padded with kNoFibre) and the number of excess wavefronts it could not avoid.
+int plan_fibres(const ModeGeom& mg, bool cplx, bool aligned, int PL, std::vector<unsigned short>& table) {
+  const int chi = mg.chi, S = mg.S;
+  const int K2 = (cplx && !aligned) ? 2 * chi : chi;
+  const int ksj = (K2 + 3) / 4;
+  std::vector<std::array<int, 4>> pats;  // bank offsets of the four entries of every k step (-1: not loaded)
+  for (int ks = 0; ks < ksj; ++ks) {
+    std::array<int, 4> p;
+    for (int t = 0; t < 4; ++t) {
+      const int kk = 4 * ks + t;
+      p[t] = kk >= K2 ? -1 : mod16((!cplx || aligned || kk < chi) ? kk * S : PL + (kk - chi) * S);
+    }
+    pats.push_back(p);
+  }
+  std::array<int, 4> spat;  // stores and close loads: four consecutive bond indices
+  for (int b = 0; b < 4; ++b) spat[b] = b < chi ? mod16(b * S) : -1;
+  auto cost_pat = [&](const int* r4, const std::array<int, 4>& p) {
+    int cnt[16] = {0}, mx = 0;
+    for (int i = 0; i < 4; ++i)
+      if (r4[i] >= 0)
+        for (int t = 0; t < 4; ++t)
+          if (p[t] >= 0) mx = std::max(mx, ++cnt[(r4[i] + p[t]) & 15]);
+    return std::max(0, mx - 1);
+  };
+  auto load_cost = [&](const int* r4) {
+    int c = cost_pat(r4, spat);
+    for (const auto& p : pats) c += cost_pat(r4, p);
+    return c;
+  };
+  auto store_cost = [&](const int* r4) { return cost_pat(r4, spat); };
+  const int nf = (int)mg.bases.size();
+  std::vector<std::vector<int>> cls(16);
+  for (int f = nf - 1; f >= 0; --f) cls[mod16(mg.bases[f])].push_back(f);
+  // quad types: 4 residues (first = 0) with conflict-free loads, realised greedily at every shift
+  std::vector<std::array<int, 4>> quads;  // fibre ids
+  for (int b = 0; b < 16; ++b)
+    for (int c = b; c < 16; ++c)
+      for (int d = c; d < 16; ++d) {
+        int r4[4] = {0, b, c, d};
+        if (load_cost(r4) != 0) continue;
+        for (int sft = 0; sft < 16; ++sft) {
+          int need[16] = {0};
+          for (int i = 0; i < 4; ++i) need[(r4[i] + sft) & 15]++;
+          while (true) {
+            bool ok = true;
+            for (int r = 0; r < 16; ++r) ok = ok && (int)cls[r].size() >= need[r];
+            if (!ok) break;
+            std::array<int, 4> q;
+            for (int i = 0; i < 4; ++i) {
+              auto& cl = cls[(r4[i] + sft) & 15];
+              q[i] = cl.back();
+              cl.pop_back();
+            }
+            quads.push_back(q);
+          }
+        }
+      }
+  // leftovers: arbitrary quads (conflicts counted below)
+  std::vector<int> left;
+  for (auto& c : cls) left.insert(left.end(), c.begin(), c.end());
+  std::sort(left.begin(), left.end(), std::greater<int>());
+  while (!left.empty()) {
+    std::array<int, 4> q = {-1, -1, -1, -1};
+    for (int i = 0; i < 4 && !left.empty(); ++i) {
+      q[i] = left.back();
+      left.pop_back();
+    }
+    quads.push_back(q);
+  }
+  auto res = [&](int f) { return f < 0 ? -1 : mod16(mg.bases[f]); };
+  // pair quads into tiles [A0 A1 A2 A3 | B0 B1 B2 B3]; the order inside A and B is chosen so that the store quads
+  // {A0, A2, B0, B2} and {A1, A3, B1, B3} are conflict free too when possible.  Costs are memoised per residue pattern.
+  static const int perms[24][4] = {{0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 1, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {0, 3, 2, 1},
+                                   {1, 0, 2, 3}, {1, 0, 3, 2}, {1, 2, 0, 3}, {1, 2, 3, 0}, {1, 3, 0, 2}, {1, 3, 2, 0},
+                                   {2, 0, 1, 3}, {2, 0, 3, 1}, {2, 1, 0, 3}, {2, 1, 3, 0}, {2, 3, 0, 1}, {2, 3, 1, 0},
+                                   {3, 0, 1, 2}, {3, 0, 2, 1}, {3, 1, 0, 2}, {3, 1, 2, 0}, {3, 2, 0, 1}, {3, 2, 1, 0}};
+  auto key_of = [&](const std::array<int, 4>& q) {
+    int k = 0;
+    for (int i = 0; i < 4; ++i) k = k * 17 + (res(q[i]) + 1);
+    return k;
+  };
+  std::map<int, std::vector<int>> by_key;  // residue pattern -> quads not paired yet
+  for (int i = (int)quads.size() - 1; i >= 0; --i) by_key[key_of(quads[i])].push_back(i);
+  struct Best {
+    int cost, pa, pb;
+  };
+  std::map<std::pair<int, int>, Best> memo;
+  auto pair_cost = [&](int qa, int qb) {
+    const std::pair<int, int> k(key_of(quads[qa]), key_of(quads[qb]));
+    auto it = memo.find(k);
+    if (it != memo.end()) return it->second;
+    Best best{1 << 30, 0, 0};
+    for (int pa = 0; pa < 24 && best.cost > 0; ++pa)
+      for (int pb = 0; pb < 24; ++pb) {
+        int ra[4] = {res(quads[qa][perms[pa][0]]), res(quads[qa][perms[pa][2]]), res(quads[qb][perms[pb][0]]), res(quads[qb][perms[pb][2]])};
+        int rb[4] = {res(quads[qa][perms[pa][1]]), res(quads[qa][perms[pa][3]]), res(quads[qb][perms[pb][1]]), res(quads[qb][perms[pb][3]])};
+        const int c = store_cost(ra) + store_cost(rb);
+        if (c < best.cost) {
+          best = {c, pa, pb};
+          if (c == 0) break;
+        }
+      }
+    memo[k] = best;
+    return best;
+  };
+  int excess = 0;
+  table.clear();
+  std::vector<char> used(quads.size(), 0);
+  for (size_t a = 0; a < quads.size(); ++a) {
+    if (used[a]) continue;
+    used[a] = 1;
+    auto& own = by_key[key_of(quads[a])];
+    own.erase(std::find(own.begin(), own.end(), (int)a));
+    int partner = -1;
+    Best pb{1 << 30, 0, 0};
+    for (auto& kv : by_key) {
+      if (kv.second.empty()) continue;
+      const Best c = pair_cost((int)a, kv.second.back());
+      if (c.cost < pb.cost) {
+        pb = c;
+        partner = kv.second.back();
+        if (c.cost == 0) break;
+      }
+    }
+    int f8[8];
+    for (int i = 0; i < 4; ++i) {
+      f8[i] = quads[a][partner >= 0 ? perms[pb.pa][i] : i];
+      f8[4 + i] = partner >= 0 ? quads[partner][perms[pb.pb][i]] : -1;
+    }
+    if (partner >= 0) {
+      used[partner] = 1;
+      auto& pv = by_key[key_of(quads[partner])];
+      pv.erase(std::find(pv.begin(), pv.end(), partner));
+    }
+    for (int i = 0; i < 8; ++i) table.push_back(f8[i] < 0 ? (unsigned short)kNoFibre : (unsigned short)mg.bases[f8[i]]);
+    int la[4] = {res(f8[0]), res(f8[1]), res(f8[2]), res(f8[3])}, lb[4] = {res(f8[4]), res(f8[5]), res(f8[6]), res(f8[7])};
+    int sa[4] = {res(f8[0]), res(f8[2]), res(f8[4]), res(f8[6])}, sb[4] = {res(f8[1]), res(f8[3]), res(f8[5]), res(f8[7])};
+    excess += load_cost(la) + load_cost(lb) + store_cost(sa) + store_cost(sb);
+  }
+  return excess;
+}
+
+struct PassPlan {
+  BlkPass desc;
+  std::vector<unsigned short> table;
+  size_t smem = 0;
+  int excess = 0;
+};
+
+// Emits "all but one" closes for the bond set [lo, hi) of the pass (local mode indices) from buffer T by divide and conquer.
+struct Emitter {
+  BlkPass* P;
+  std::vector<char> busy;  // buffers in use
+  bool ok = true;
+  int maxbuf = 0;
+  int alloc(int not_this = -1) {
+    for (int i = 1; i < (int)busy.size(); ++i)
+      if (!busy[i] && i != not_this) {
+        busy[i] = 1;
+        maxbuf = std::max(maxbuf, i + 1);
+        return i;
+      }
+    ok = false;
+    return 1;
+  }
+  void put(unsigned char type, int src, int dst, int mode) {
+    if (P->nops >= kMaxOps) {
+      ok = false;
+      return;
+    }
+    P->ops[P->nops++] = {type, (unsigned char)src, (unsigned char)dst, (unsigned char)mode};
+  }
+  // absorbs modes [a_lo, a_hi) into T; returns the buffer holding the result (T itself when the range is empty)
+  int absorb(int T, int a_lo, int a_hi) {
+    int cur = T;
+    for (int k = a_lo; k < a_hi; ++k) {
+      const int dst = alloc();
+      put(OP_MP, cur, dst, k);
+      if (cur != T) busy[cur] = 0;
+      cur = dst;
+    }
+    return cur;
+  }
+  void solve(int T, int lo, int hi) {
+    if (hi - lo == 1) {
+      put(OP_CLOSE, T, 0, lo);
+      return;
+    }
+    const int mid = (lo + hi) / 2;
+    const int t1 = absorb(T, mid, hi);
+    solve(t1, lo, mid);
+    if (t1 != T) busy[t1] = 0;
+    const int t2 = absorb(T, lo, mid);
+    solve(t2, mid, hi);
+    if (t2 != T) busy[t2] = 0;
+  }
+};
+
+constexpr size_t kSmemTwoCtas = 113 * 1024;
+constexpr size_t kSmemOneCta = 226 * 1024;
+
+size_t pass_smem(const BlkPass& P, size_t tab_len) {
+  return (size_t)P.nbuf * P.bufsz * sizeof(double) + kRedDoubles * sizeof(double) + ((tab_len * 2 + 15) & ~(size_t)15) + 64;
+}
+
+// k * S mod 16 distinct for the (up to) four consecutive bond indices a half-warp touches together
+bool good_stride(long long S, int chi) {
+  const int n = std::min(chi, 4);
+  int seen = 0;
+  for (int k = 0; k < n; ++k) {
+    const int r = mod16((int)((k * S) % 16));
+    if (seen & (1 << r)) return false;
+    seen |= 1 << r;
+  }
+  return true;
+}
+// smallest stride >= base (same parity) that is good for a bond of extent chi
+long long pad_to_good(long long base, int chi) {
+  for (int p = 0; p < 16; p += 2)
+    if (good_stride(base + p, chi)) return base + p;
+  return base;
+}
+
+struct PassChoice {
+  int chunk = 1;
+  int split = 0;      // fast passes: bonds below `split` stay inside the contiguous row
+  int pad_chunk = 0;  // extra doubles between consecutive chunk slices (fast) -- tried by full evaluation
+  int pad_plane = 0;
+};
+
+// Builds the plan of one pass.  fast (passes 1 and 3): the block holds every index of (site, G1) and `chunk` values of G2's
+// flat index; slow (pass 2): `chunk` values of the flat (site, G1) index and every index of G2.  Rows (contiguous in HBM
+// and in shared memory) are placed in shared memory with padded strides so that no bond stride is a multiple of 8 doubles.
+bool plan_pass(const Signature& sg, int h, int which, bool cplx, bool aligned, const PassChoice& ch, bool with_tables,
+               PassPlan& out) {
+  const int z = sg.z, d = sg.d;
+  long long L = d, XR = 1;
+  for (int k = 0; k < h; ++k) L *= sg.chi[k];
+  for (int k = h; k < z; ++k) XR *= sg.chi[k];
+  const long long n = L * XR;
+  const bool fast = which != 1;
+  const int chunk = ch.chunk;
+  BlkPass& P = out.desc;
+  memset(&P, 0, sizeof(P));
+  P.gplane = n;
+  struct Axis {
+    int n;
+    long long s;
+    int mode;  // local mode index or -1
+  };
+  std::vector<Axis> axes;
+  std::vector<int> mode_slot;
+  long long top;  // doubles per plane
+  if (fast) {
+    if (XR % chunk) return false;
+    const int j = ch.split;
+    long long rowlen = d;
+    axes.push_back({d, 1, -1});
+    long long S = d;
+    for (int k = 0; k < j; ++k) {
+      axes.push_back({sg.chi[k], S, k});
+      S *= sg.chi[k];
+      rowlen = S;
+    }
+    P.nlev = 0;
+    long long nrows = 1;
+    for (int k = j; k < h; ++k) {
+      S = pad_to_good(S, sg.chi[k]);
+      axes.push_back({sg.chi[k], S, k});
+      if (P.nlev >= 3) return false;
+      P.lev_n[P.nlev] = sg.chi[k];
+      P.lev_s[P.nlev] = (int)S;
+      P.nlev++;
+      nrows *= sg.chi[k];
+      S *= sg.chi[k];
+    }
+    S += ch.pad_chunk;
+    axes.push_back({chunk, S, -1});
+    P.lev_n[P.nlev] = chunk;
+    P.lev_s[P.nlev] = (int)S;
+    P.nlev++;
+    nrows *= chunk;
+    top = S * chunk;
+    P.nblk = (int)(XR / chunk);
+    P.nrows = (int)nrows;
+    P.rowlen = (int)rowlen;
+    P.grow = rowlen;
+    P.gblk = L * chunk;
+    // no padding anywhere: the whole block is one contiguous run
+    bool dense = true;
+    {
+      long long expect = rowlen;
+      for (int l = 0; l < P.nlev; ++l) {
+        dense = dense && P.lev_s[l] == expect;
+        expect *= P.lev_n[l];
+      }
+    }
+    if (dense) {
+      P.nrows = 1;
+      P.rowlen = (int)(L * chunk);
+      P.grow = 0;
+      P.nlev = 0;
+    }
+    for (int k = 0; k < h; ++k) mode_slot.push_back(k);
+  } else {
+    if (L % chunk) return false;
+    axes.push_back({chunk, 1, -1});
+    long long S = chunk;
+    P.nlev = 0;
+    for (int k = h; k < z; ++k) {
+      S = pad_to_good(S, sg.chi[k]);
+      axes.push_back({sg.chi[k], S, k - h});
+      if (P.nlev >= 4) return false;
+      P.lev_n[P.nlev] = sg.chi[k];
+      P.lev_s[P.nlev] = (int)S;
+      P.nlev++;
+      S *= sg.chi[k];
+    }
+    top = S;
+    P.nblk = (int)(L / chunk);
+    P.nrows = (int)XR;
+    P.rowlen = chunk;
+    P.grow = L;
+    P.gblk = chunk;
+    for (int k = h; k < z; ++k) mode_slot.push_back(k);
+  }
+  P.PL = (int)top + ch.pad_plane;
+  P.bufsz = (cplx ? 2 : 1) * P.PL;
+  if ((long long)P.bufsz > 60000 || top > 30000) return false;  // 16-bit fibre tables
+  bool even = P.rowlen % 2 == 0 && P.grow % 2 == 0 && P.gblk % 2 == 0 && n % 2 == 0 && P.PL % 2 == 0;
+  for (int l = 0; l < P.nlev; ++l) even = even && P.lev_s[l] % 2 == 0;
+  P.bulk = even ? 1 : 0;
+  P.load_p = which != 0;
+  const int nm = (int)mode_slot.size();
+  P.nmodes = nm;
+  // operation list
+  Emitter em;
+  em.P = &P;
+  em.busy.assign(8, 0);
+  em.busy[0] = 1;
+  if (which == 0) {
+    // P = X x_{G1} M: ping-pong between buffers 1 and 0 (X is dead after its first product)
+    int cur = 0;
+    for (int k = 0; k < nm; ++k) {
+      const int dst = cur == 0 ? 1 : 0;
+      em.put(OP_MP, cur, dst, k);
+      cur = dst;
+    }
+    em.put(OP_STORE, cur, 0, 0);
+    em.maxbuf = 2;
+  } else {
+    em.busy[1] = 1;
+    em.maxbuf = 2;
+    em.solve(1, 0, nm);
+    if (which == 1) {
+      // S = X x_{G2} M; the buffer of P is free now, X (buffer 0) is only read
+      em.busy[1] = 0;
+      int cur = 0;
+      for (int k = 0; k < nm; ++k) {
+        const int dst = em.alloc(cur);
+        em.put(OP_MP, cur, dst, k);
+        if (cur != 0) em.busy[cur] = 0;
+        cur = dst;
+      }
+      em.put(OP_STORE, cur, 0, 0);
+    }
+  }
+  if (!em.ok) return false;
+  P.nbuf = em.maxbuf;
+  // fibre tables
+  out.table.clear();
+  out.excess = 0;
+  size_t tab_len = 0;
+  long long nreal = 1;
+  for (const Axis& a : axes) nreal *= a.n;
+  for (int k = 0; k < nm; ++k) {
+    ModeGeom m;
+    m.slot = mode_slot[k];
+    m.chi = 0;
+    for (const Axis& a : axes)
+      if (a.mode == k) {
+        m.chi = a.n;
+        m.S = (int)a.s;
+      }
+    P.modes[k].chi = m.chi;
+    P.modes[k].S = m.S;
+    P.modes[k].slot = m.slot;
+    if (with_tables) {
+      // every combination of the other axes, first axis fastest
+      std::vector<const Axis*> others;
+      for (const Axis& a : axes)
+        if (a.mode != k) others.push_back(&a);
+      const long long nf = nreal / m.chi;
+      m.bases.resize(nf);
+      for (long long f = 0; f < nf; ++f) {
+        long long q = f, off = 0;
+        for (const Axis* a : others) {
+          off += (q % a->n) * a->s;
+          q /= a->n;
+        }
+        m.bases[f] = (int)off;
+      }
+      std::vector<unsigned short> t;
+      out.excess += plan_fibres(m, cplx, aligned, P.PL, t);
+      P.modes[k].tab = (int)out.table.size();
+      P.modes[k].ntile = (int)t.size() / 8;
+      out.table.insert(out.table.end(), t.begin(), t.end());
+      tab_len = out.table.size();
+    } else {
+      tab_len += (size_t)((nreal / m.chi + 15) & ~7ll);
+    }
+  }
+  P.tab_len = (int)out.table.size();
+  out.smem = pass_smem(P, tab_len);
+  return true;
+}
+
+// Chooses the block of a pass: the largest chunk that leaves two CTAs per SM (one if it must), shrunk while the launch
+// would not cover the SMs; then the paddings with the fewest excess wavefronts.
+bool choose_pass(const Signature& sg, int h, int which, bool cplx, bool aligned, size_t nverts, PassPlan& best) {
+  const int z = sg.z, d = sg.d;
+  long long L = d, XR = 1;
+  for (int k = 0; k < h; ++k) L *= sg.chi[k];
+  for (int k = h; k < z; ++k) XR *= sg.chi[k];
+  const bool fast = which != 1;
+  const long long range = fast ? XR : L;
+  PassChoice ch;
+  if (fast) {
+    // bonds whose natural stride is fine stay inside the contiguous row
+    long long S = d;
+    ch.split = h;
+    for (int k = 0; k < h; ++k) {
+      if (k >= 1 && !good_stride(S, sg.chi[k])) {
+        ch.split = k;
+        break;
+      }
+      S *= sg.chi[k];
+    }
+  }
+  int best_chunk = -1;
+  double best_score = -1;
+  for (long long c = 1; c <= range; ++c) {
+    if (range % c) continue;
+    if (!fast && (c % 2) && (L % 2 == 0) && c != range) continue;  // 16-byte rows
+    PassPlan pp;
+    PassChoice t = ch;
+    t.chunk = (int)c;
+    t.pad_chunk = fast ? 6 : 0;  // room for the paddings tried below
+    t.pad_plane = 6;
+    if (!plan_pass(sg, h, which, cplx, aligned, t, false, pp)) continue;
+    if (pp.smem > kSmemOneCta) continue;
+    const long long nb = (fast ? L : XR) * c;
+    const long long ctas = (long long)pp.desc.nblk * (long long)nverts;
+    const bool two = pp.smem <= kSmemTwoCtas;
+    double score = std::min<double>((double)nb, 4096.0);
+    if (!two) score *= 0.3;
+    if (!fast && c * 8 < 64) score *= 0.5 + c / 16.0;  // short HBM rows waste sectors and bulk-copy issue slots
+    if (ctas < 296) score *= ((double)ctas / 296.0) * 0.9 + 0.1;
+    if (score > best_score) {
+      best_score = score;
+      best_chunk = (int)c;
+    }
+  }
+  if (best_chunk < 0) return false;
+  ch.chunk = best_chunk;
+  bool mixed_steps = false;  // packed complex stacking with a k step that straddles the planes
+  if (cplx && !aligned)
+    for (int k = fast ? 0 : h; k < (fast ? h : z); ++k) mixed_steps = mixed_steps || (sg.chi[k] % 4) != 0;
+  bool have = false;
+  double best_ex = 1e300;
+  for (int pc : {0, 2, 4, 6}) {
+    if (!fast && pc) break;
+    for (int pl : {0, 2, 4, 6, 8, 10, 12, 14}) {
+      if (!mixed_steps && pl) break;
+      PassPlan pp;
+      PassChoice t = ch;
+      t.pad_chunk = pc;
+      t.pad_plane = pl;
+      if (!plan_pass(sg, h, which, cplx, aligned, t, true, pp)) continue;
+      if (pp.smem > kSmemOneCta) continue;
+      const double ex = (double)pp.excess + 1e-3 * (pc + pl);
+      if (ex < best_ex) {
+        best_ex = ex;
+        best = std::move(pp);
+        have = true;
+      }
+      if (have && best.excess == 0) break;
+    }
+    if (have && best.excess == 0) break;
+  }
+  return have;
+}
+
+void kernel_instance(bool cplx, int chimax, int& KS, int& MT) {
+  if (cplx) {
+    KS = chimax <= 2 ? 1 : chimax <= 4 ? 2 : chimax <= 6 ? 3 : chimax <= 8 ? 4 : chimax <= 16 ? 8 : 16;
+    MT = chimax <= 8 ? 1 : chimax <= 16 ? 2 : 4;
+  } else {
+    KS = chimax <= 4 ? 1 : chimax <= 8 ? 2 : chimax <= 16 ? 4 : 8;
+    MT = chimax <= 8 ? 1 : chimax <= 16 ? 2 : 4;
+  }
+}
+
+// Geometry of a signature: independent of the network, shared by every network of the process.
+struct Geometry {
+  Signature sig;
+  int h = 0;
+  int KS = 0, MT = 0;  // kernel instance; KS = 0: the signature has no plan (falls back to the shape-generic kernels)
+  PassPlan pass[3];
+  long long nelem = 0;
+};
+
+struct GeomKey {
+  Signature sig;
+  bool cplx;
+  int fill;  // 0: few vertices (the block size is shrunk so that the launch still covers the SMs), 1: plenty
+  bool operator<(const GeomKey& o) const { return std::tie(sig, cplx, fill) < std::tie(o.sig, o.cplx, o.fill); }
+};
+
+bool block_debug() {
+  static const bool on = getenv("ITN_BLOCK_DEBUG") != nullptr;
+  return on;
+}
+
+const Geometry* geometry_for(const Signature& s, bool cplx, size_t nverts) {
+  static std::map<GeomKey, std::unique_ptr<Geometry>> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  // the vertex count matters only while the launch does not fill the machine
+  const int fill = nverts >= 2048 ? 1 : 0;
+  GeomKey key{s, cplx, fill ? 1 << 30 : (int)nverts};
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second.get();
+  std::unique_ptr<Geometry> g(new Geometry());
+  g->sig = s;
+  g->h = (s.z + 1) / 2;
+  int chimax = 0;
+  g->nelem = s.d;
+  for (int k = 0; k < s.z; ++k) {
+    chimax = std::max(chimax, s.chi[k]);
+    g->nelem *= s.chi[k];
+  }
+  kernel_instance(cplx, chimax, g->KS, g->MT);
+  const bool aligned = cplx && g->KS >= 8;
+  bool ok = true;
+  for (int w = 0; w < 3 && ok; ++w) ok = choose_pass(s, g->h, w, cplx, aligned, nverts, g->pass[w]);
+  if (!ok) g->KS = 0;
+  if (ok && block_debug()) {
+    fprintf(stderr, "[itn block] d=%d z=%d chi=", s.d, s.z);
+    for (int k = 0; k < s.z; ++k) fprintf(stderr, "%d%s", s.chi[k], k + 1 < s.z ? "," : "");
+    fprintf(stderr, " h=%d KS=%d MT=%d verts=%zu\n", g->h, g->KS, g->MT, nverts);
+    for (int w = 0; w < 3; ++w) {
+      const BlkPass& P = g->pass[w].desc;
+      fprintf(stderr, "   pass %d: nblk=%d rows=%d x %d levels=", w + 1, P.nblk, P.nrows, P.rowlen);
+      for (int l = 0; l < P.nlev; ++l) fprintf(stderr, "%dx%d ", P.lev_n[l], P.lev_s[l]);
+      fprintf(stderr, "strides=");
+      for (int k = 0; k < P.nmodes; ++k) fprintf(stderr, "%d ", P.modes[k].S);
+      fprintf(stderr, "PL=%d nbuf=%d bulk=%d ops=%d smem=%zu excess wavefronts=%d of %zu quads\n", P.PL, P.nbuf, P.bulk, P.nops,
+              g->pass[w].smem, g->pass[w].excess, g->pass[w].table.size() / 4);
+    }
+  }
+  const Geometry* r = g.get();
+  cache[key] = std::move(g);
+  return r;
+}
+
+struct Bucket {
+  const Geometry* geo = nullptr;
+  std::vector<int> verts;
+  // device copies of the geometry (per network: they live on its device)
+  BlkPass* d_pass = nullptr;  // [3]
+  unsigned short* d_tab[3] = {nullptr, nullptr, nullptr};
+  // per update() call
+  DevBuf* scratch = nullptr;  // P and S of every vertex
+  DevBuf* part = nullptr;
+  DevBuf* dverts = nullptr;
+  DevBuf* dred = nullptr;
+  size_t nred = 0;
+};
+
+struct BlockCache {
+  std::map<const Geometry*, Bucket> buckets;
+  std::vector<Bucket*> active;
+  std::vector<int> vbucket;
+};
+
+bool signature_of(const itn_net* net, int v, Signature& s) {
+  const int z = (int)net->inc[v].size();
+  if (z < 2 || z > 8 || !net->T[v].p) return false;
+  s.d = net->sdim[v];
+  s.z = z;
+  s.chi.fill(0);
+  for (int k = 0; k < z; ++k) {
+    s.chi[k] = net->edim[net->inc[v][k]];
+    if (s.chi[k] > 32 || s.chi[k] < 1) return false;
+  }
+  return s.d >= 1 && s.d <= 8;
+}
+
+template <bool C, int KS, int MT>
+void launch_inst(itn_ctx* ctx, unsigned grid, size_t smem, const BlkPass* dp, const BlkVertex* dv, const unsigned short* dt) {
+  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  k_block<C, KS, MT><<<grid, kBT, smem, ctx->stream>>>(dp, dv, dt);
+  ITN_LAUNCH_CHECK(ctx);
+}
+
+void launch_pass(itn_ctx* ctx, bool cplx, int KS, unsigned grid, size_t smem, const BlkPass* dp, const BlkVertex* dv,
+                 const unsigned short* dt) {
+  if (cplx) {
+    switch (KS) {
+      case 1: return launch_inst<true, 1, 1>(ctx, grid, smem, dp, dv, dt);
+      case 2: return launch_inst<true, 2, 1>(ctx, grid, smem, dp, dv, dt);
+      case 3: return launch_inst<true, 3, 1>(ctx, grid, smem, dp, dv, dt);
+      case 4: return launch_inst<true, 4, 1>(ctx, grid, smem, dp, dv, dt);
+      case 8: return launch_inst<true, 8, 2>(ctx, grid, smem, dp, dv, dt);
+      default: return launch_inst<true, 16, 4>(ctx, grid, smem, dp, dv, dt);
+    }
+  } else {
+    switch (KS) {
+      case 1: return launch_inst<false, 1, 1>(ctx, grid, smem, dp, dv, dt);
+      case 2: return launch_inst<false, 2, 1>(ctx, grid, smem, dp, dv, dt);
+      case 4: return launch_inst<false, 4, 2>(ctx, grid, smem, dp, dv, dt);
+      default: return launch_inst<false, 8, 4>(ctx, grid, smem, dp, dv, dt);
+    }
+  }
+}
+
+void end_call(Bucket& b) {
+  delete b.scratch;
+  delete b.part;
+  delete b.dverts;
+  delete b.dred;
+  b.scratch = b.part = b.dverts = b.dred = nullptr;
+}
+
+}  // namespace
+
+void itn_block_release(itn_net* net) {
+  if (!net->block) return;
+  BlockCache* bc = (BlockCache*)net->block;
+  for (auto& kv : bc->buckets) {
+    Bucket& b = kv.second;
+    end_call(b);
+    itn_dev_free(net->ctx, b.d_pass);
+    for (auto& t : b.d_tab) itn_dev_free(net->ctx, t);
+  }
+  delete bc;
+  net->block = nullptr;
+}
+
+// Plans a synchronous sweep on the block path: handled[i] = 2 for the message jobs it takes (vertices all of whose
+// outgoing messages are listed exactly once, none of them taken by the tile path, and whose signature has a plan).
+int itn_block_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled) {
+  if (net->ctx->path_mode != 0 || net->has_bra()) return 0;
+  static const bool off = getenv("ITN_NO_BLOCK") != nullptr;
+  if (off) return 0;
+  BlockCache* bc = (BlockCache*)net->block;
+  if (!bc) net->block = bc = new BlockCache();
+  if (handled.size() != dids.size()) handled.assign(dids.size(), 0);
+  std::vector<int> cnt(net->nv, 0);
+  {
+    std::vector<char> listed(net->M.size(), 0);
+    for (size_t i = 0; i < dids.size(); ++i) {
+      cnt[srcv[i]] += (listed[dids[i]] || handled[i]) ? 100 : 1;
+      listed[dids[i]] = 1;
+    }
+  }
+  for (Bucket* b : bc->active) b->verts.clear();
+  bc->active.clear();
+  bc->vbucket.assign(net->nv, -1);
+  // count the vertices of every signature first: the geometry depends on how many blocks the launch will have
+  std::map<Signature, std::vector<int>> by_sig;
+  for (int v = 0; v < net->nv; ++v) {
+    if (cnt[v] != (int)net->inc[v].size()) continue;
+    Signature s;
+    if (signature_of(net, v, s)) by_sig[s].push_back(v);
+  }
+  int n = 0;
+  for (auto& kv : by_sig) {
+    const Geometry* geo = geometry_for(kv.first, net->cplx, kv.second.size());
+    if (geo->KS == 0) continue;
+    Bucket& b = bc->buckets[geo];
+    b.geo = geo;
+    b.verts = kv.second;
+    for (int v : b.verts) bc->vbucket[v] = (int)bc->active.size();
+    bc->active.push_back(&b);
+  }
+  for (size_t i = 0; i < dids.size(); ++i)
+    if (!handled[i] && bc->vbucket[srcv[i]] >= 0) {
+      handled[i] = 2;
+      ++n;
+    }
+  return n;
+}
+
+// Prepares the planned sweep for one itn_bp_update call: device tables, scratch tensors, per-vertex descriptors.  The
+// un-normalised new message of job i (handled[i] == 2) will be written to staged[i] by every itn_block_bp_run.
+void itn_block_bp_begin(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
+                        const std::vector<char>& handled, double* const* staged) {
+  BlockCache* bc = (BlockCache*)net->block;
+  if (!bc || bc->active.empty()) return;
+  itn_ctx* ctx = net->ctx;
+  const int PLN = net->planes();
+  std::vector<std::array<double*, 8>> st(net->nv);
+  for (auto& a : st) a.fill(nullptr);
+  for (size_t i = 0; i < dids.size(); ++i)
+    if (handled[i] == 2) st[srcv[i]][net->slot(srcv[i], dids[i] / 2)] = staged[i];
+  for (Bucket* bp : bc->active) {
+    Bucket& b = *bp;
+    const Geometry& G = *b.geo;
+    const size_t nv = b.verts.size();
+    const int z = G.sig.z;
+    end_call(b);
+    if (!b.d_pass) {
+      b.d_pass = (BlkPass*)itn_dev_alloc(ctx, 3 * sizeof(BlkPass));
+      BlkPass hp[3] = {G.pass[0].desc, G.pass[1].desc, G.pass[2].desc};
+      CUDA_CHECK(cudaMemcpyAsync(b.d_pass, hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+      for (int w = 0; w < 3; ++w) {
+        b.d_tab[w] = (unsigned short*)itn_dev_alloc(ctx, std::max<size_t>(G.pass[w].table.size(), 8) * sizeof(unsigned short));
+        CUDA_CHECK(cudaMemcpyAsync(b.d_tab[w], G.pass[w].table.data(), G.pass[w].table.size() * sizeof(unsigned short),
+                                   cudaMemcpyHostToDevice, ctx->stream));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // hp lives on this stack frame
+    }
+    size_t part_v = 0;  // doubles of partial results per vertex
+    std::vector<size_t> part_off(z);
+    for (int k = 0; k < z; ++k) {
+      part_off[k] = part_v;
+      const int nblk = k < G.h ? G.pass[2].desc.nblk : G.pass[1].desc.nblk;
+      part_v += (size_t)nblk * PLN * G.sig.chi[k] * G.sig.chi[k];
+    }
+    b.scratch = new DevBuf(ctx, nv * 2 * (size_t)G.nelem * PLN * sizeof(double));
+    b.part = new DevBuf(ctx, nv * part_v * sizeof(double));
+    std::vector<BlkVertex> hv(3 * nv);
+    std::vector<BlkRedJob> hr;
+    for (size_t i = 0; i < nv; ++i) {
+      const int v = b.verts[i];
+      double* Pbuf = b.scratch->as<double>() + (2 * i) * (size_t)G.nelem * PLN;
+      double* Sbuf = Pbuf + (size_t)G.nelem * PLN;
+      for (int w = 0; w < 3; ++w) {
+        BlkVertex& V = hv[w * nv + i];
+        memset(&V, 0, sizeof(V));
+        V.X = net->T[v].p;
+        V.Pin = w == 1 ? Pbuf : (w == 2 ? Sbuf : nullptr);
+        V.Wout = w == 0 ? Pbuf : (w == 1 ? Sbuf : nullptr);
+        for (int k = 0; k < z; ++k) {
+          const DevTensor& m = net->M[net->msg_into(v, net->inc[v][k])];
+          ITN_REQUIRE(m.p != nullptr, ITN_EINVAL, "an incoming message is not set");
+          V.msg[k] = m.p;
+          V.part[k] = b.part->as<double>() + i * part_v + part_off[k];
+        }
+      }
+      for (int k = 0; k < z; ++k) {
+        ITN_REQUIRE(st[v][k] != nullptr, ITN_EINVAL, "block sweep: an outgoing message has no staging buffer");
+        const int nblk = k < G.h ? G.pass[2].desc.nblk : G.pass[1].desc.nblk;
+        hr.push_back({b.part->as<double>() + i * part_v + part_off[k], st[v][k], nblk, PLN * G.sig.chi[k] * G.sig.chi[k]});
+      }
+    }
+    b.dverts = new DevBuf(ctx, hv.size() * sizeof(BlkVertex));
+    b.dred = new DevBuf(ctx, hr.size() * sizeof(BlkRedJob));
+    b.nred = hr.size();
+    itn_upload(ctx, hv, *b.dverts);
+    itn_upload(ctx, hr, *b.dred);
+  }
+}
+
+void itn_block_bp_run(itn_net* net) {
+  BlockCache* bc = (BlockCache*)net->block;
+  if (!bc) return;
+  itn_ctx* ctx = net->ctx;
+  for (Bucket* bp : bc->active) {
+    Bucket& b = *bp;
+    const Geometry& G = *b.geo;
+    const size_t nv = b.verts.size();
+    ITN_REQUIRE(b.dverts != nullptr, ITN_EINVAL, "block sweep is not prepared");
+    for (int w = 0; w < 3; ++w)
+      launch_pass(ctx, net->cplx, G.KS, (unsigned)(nv * G.pass[w].desc.nblk), G.pass[w].smem, b.d_pass + w,
+                  b.dverts->as<BlkVertex>() + w * nv, b.d_tab[w]);
+    k_block_reduce<<<(unsigned)b.nred, 128, 0, ctx->stream>>>(b.dred->as<BlkRedJob>());
+    ITN_LAUNCH_CHECK(ctx);
+  }
+}
+
+void itn_block_bp_end(itn_net* net) {
+  BlockCache* bc = (BlockCache*)net->block;
+  if (!bc) return;
+  for (Bucket* b : bc->active) end_call(*b);
+}
+
+// Instrumentation (host only, no device needed): the geometry the block path would use for a vertex signature, as a flat
+// int32 stream, so that tests can replay the operation lists and fibre tables on the host (tests/block_emulator.py):
+//   KS, MT, h, then per pass: nblk, nrows, rowlen, grow, gblk, nlev, lev_n[4], lev_s[4], PL, bufsz, nbuf, bulk, load_p, smem
+//   bytes, excess wavefronts, nmodes, {chi, S, ntile, tab, slot} x nmodes, nops, {type, src, dst, mode} x nops, tab_len, table...
+extern "C" int itn_block_plan_export(int dtype, int d, int z, const int32_t* chi, int nverts, int32_t* out, int cap, int32_t* nout) {
+  try {
+    if (!chi || !nout || z < 1 || z > 8 || (dtype != ITN_F64 && dtype != ITN_C128)) {
+      itn_set_error("itn_block_plan_export: bad arguments");
+      return ITN_EINVAL;
+    }
+    Signature s;
+    s.d = d;
+    s.z = z;
+    s.chi.fill(0);
+    for (int k = 0; k < z; ++k) s.chi[k] = chi[k];
+    std::vector<int32_t> v;
+    bool supported = z >= 2 && d >= 1 && d <= 8;
+    for (int k = 0; k < z; ++k) supported = supported && chi[k] >= 1 && chi[k] <= 32;
+    const Geometry* g = supported ? geometry_for(s, dtype == ITN_C128, (size_t)std::max(nverts, 1)) : nullptr;
+    if (!g || g->KS == 0) {
+      *nout = 0;
+      return ITN_OK;
+    }
+    v.push_back(g->KS);
+    v.push_back(g->MT);
+    v.push_back(g->h);
+    for (int w = 0; w < 3; ++w) {
+      const BlkPass& P = g->pass[w].desc;
+      for (long long x : {(long long)P.nblk, (long long)P.nrows, (long long)P.rowlen, P.grow, P.gblk, (long long)P.nlev,
+                          (long long)P.lev_n[0], (long long)P.lev_n[1], (long long)P.lev_n[2], (long long)P.lev_n[3],
+                          (long long)P.lev_s[0], (long long)P.lev_s[1], (long long)P.lev_s[2], (long long)P.lev_s[3], (long long)P.PL,
+                          (long long)P.bufsz, (long long)P.nbuf, (long long)P.bulk, (long long)P.load_p, (long long)g->pass[w].smem,
+                          (long long)g->pass[w].excess, (long long)P.nmodes})
+        v.push_back((int32_t)x);
+      for (int k = 0; k < P.nmodes; ++k)
+        for (int x : {P.modes[k].chi, P.modes[k].S, P.modes[k].ntile, P.modes[k].tab, P.modes[k].slot}) v.push_back(x);
+      v.push_back(P.nops);
+      for (int o = 0; o < P.nops; ++o)
+        for (int x : {(int)P.ops[o].type, (int)P.ops[o].src, (int)P.ops[o].dst, (int)P.ops[o].mode}) v.push_back(x);
+      v.push_back((int32_t)g->pass[w].table.size());
+      for (unsigned short t : g->pass[w].table) v.push_back((int32_t)t);
+    }
+    *nout = (int32_t)v.size();
+    if (out && cap >= (int)v.size()) memcpy(out, v.data(), v.size() * sizeof(int32_t));
+    return ITN_OK;
+  } catch (const std::exception& e) {
+    itn_set_error(e.what());
+    return ITN_EINVAL;
+  }
+}

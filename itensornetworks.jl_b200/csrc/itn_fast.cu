@@ -765,6 +765,8 @@ void itn_fast_release(itn_net* net) {
 // dimension 16, whose tensor is set and whose four outgoing messages are all part of this sweep.
 int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled) {
   handled.assign(dids.size(), 0);
+  static const bool off = getenv("ITN_NO_TILE") != nullptr;  // experiments: send everything to the block path
+  if (off) return 0;
   FastCache* fc = ensure_cache(net);
   if (!fc) return 0;
   itn_ctx* ctx = net->ctx;
@@ -828,7 +830,7 @@ void itn_fast_bp_sweep_begin(itn_net* net, const std::vector<int>& dids, const s
     }
   }
   for (size_t i = 0; i < dids.size(); ++i) {
-    if (!handled[i]) continue;
+    if (handled[i] != 1) continue;  // 2 = taken by the block path (itn_block.cu)
     const int v = srcv[i];
     const int k = net->slot(v, dids[i] / 2);
     st[(size_t)rank_in_sweep[fc->vslot[v]] * 4 + k] = staged[i];

@@ -42,6 +42,7 @@ struct itn_ctx {
   void* nccl = nullptr;      // ncclComm_t
   void* nccl_lib = nullptr;  // dlopen handle
   int64_t launches = 0;
+  int64_t path_msgs[3] = {0, 0, 0};  // messages computed by the tile path, the block path and the shape-generic kernels
   int nets_alive = 0;          // handles created on this context and not yet destroyed
   bool destroy_pending = false;  // itn_ctx_destroy was called while networks were alive (finalizer order)
   int path_mode = 0;
@@ -143,6 +144,7 @@ struct itn_net {
   double last_total_ms = 0, last_contract_ms = 0;
   std::vector<PendingUpload> pending;  // deferred host tensors: device storage exists, contents arrive with the next consumer
   void* fast = nullptr;  // fast-path cache (owned by itn_fast.cu)
+  void* block = nullptr; // block-path cache (owned by itn_block.cu)
   void* dist = nullptr;  // halo exchange plan and buffers (owned by itn_dist.cu)
 
   int planes() const { return cplx ? 2 : 1; }
@@ -256,6 +258,17 @@ void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs);
 void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs);
 // after the new tensors are committed: marks the tile-major copies that itn_fast_rebuild wrote directly as current
 void itn_fast_commit_direct(itn_net* net);
+
+// ---- block path (itn_block.cu): synchronous sweeps of any degree 2..8 / bond extent <= 32 on the canonical layout ----
+// plan: handled[i] = 2 for the message jobs the block kernels take (jobs with handled[i] != 0 are left alone); returns
+// their number.  begin prepares one itn_bp_update call (device tables, scratch tensors; staged[i] receives the
+// un-normalised new message of job i), run executes one sweep, end releases the per-call buffers.
+int itn_block_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled);
+void itn_block_bp_begin(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
+                        const std::vector<char>& handled, double* const* staged);
+void itn_block_bp_run(itn_net* net);
+void itn_block_bp_end(itn_net* net);
+void itn_block_release(itn_net* net);
 
 // ---- multi-GPU (itn_dist.cu) ----
 bool itn_is_local(const itn_net* net, int v);

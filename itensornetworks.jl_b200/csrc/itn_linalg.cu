@@ -1110,8 +1110,11 @@ __global__ void __launch_bounds__(256) k_eig_fn(const EigFnJob* __restrict__ job
       if (C) d += J.v[n2 + col * n + i] * J.us[n2 + col * n + i];
     }
     lam[j] = d < 0.0 ? -J.sigma[j] : J.sigma[j];
-    // <v_j, H v_j> = +-sigma_j when v_j is an eigenvector; anything well inside means a mixed +-lambda pair
-    if (J.mixed && J.sigma[j] > 1e-8 * J.sigma[0] && fabs(d) < 0.9 * J.sigma[j]) *J.mixed = 1;
+    // <v_j, H v_j> = +sigma_j for every significant j when H is positive semi-definite.  A negative eigenvalue may pair up
+    // with a positive one of (nearly) the same magnitude, and the right singular vectors of such a pair are an arbitrary
+    // rotation of the two eigenvectors (d anywhere in [-sigma, sigma]): any significant d below sigma / 2 sends the
+    // matrix to the shifted route, i.e. every indefinite input takes it
+    if (J.mixed && J.sigma[j] > 1e-8 * J.sigma[0] && d < 0.5 * J.sigma[j]) *J.mixed = 1;
   }
   __syncthreads();
   if (tid == 0 && J.shift > 0.0) {

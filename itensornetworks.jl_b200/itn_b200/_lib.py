@@ -63,7 +63,9 @@ _SIGS = {
     "itn_map_eigvals": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double]),
     "itn_tensordot": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i32p, _vp, C.c_int, _i32p, C.c_int, _i32p, _i32p, _vp]),
     "itn_svd_batch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _dp, _vp, C.c_int, _dp]),
+    "itn_block_plan_export": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _i32p]),
     "itn_ctx_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "itn_ctx_path_counts": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "itn_ctx_set_path": (C.c_int, [_vp, C.c_int]),
     "itn_bp_last_timing": (C.c_int, [_vp, _dp, _dp]),
 }

@@ -48,6 +48,12 @@ class Context:
         check(lib().itn_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def path_counts(self):
+        """Message updates computed so far by (tile path, block path, shape-generic kernels)."""
+        out = (C.c_int64 * 3)()
+        check(lib().itn_ctx_path_counts(self.h, out))
+        return tuple(int(x) for x in out)
+
     def set_path(self, mode):
         """0 = auto (DMMA tile path where it applies), 1 = shape-generic DMMA kernels only, 2 = FMA kernels only."""
         check(lib().itn_ctx_set_path(self.h, int(mode)))
