@@ -79,6 +79,10 @@ struct BlkPass {
   int nops;
   BlkOp ops[kMaxOps];
   int tab_len;
+  int rowtab;              // offset (entries) of the row-position table inside the pass table (nrows entries)
+  int msg_smem;            // 1: the messages of the pass are staged in shared memory (msg_off, doubles), 0: read from L2
+  int msg_off[kMaxGM];
+  int msg_len;             // doubles reserved for the staged messages
 };
 struct BlkVertex {
   const double* X;     // site tensor (canonical planar)
@@ -119,78 +123,93 @@ __device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const doubl
   const int K2 = (C && !AL) ? 2 * chi : chi;  // length of the (stacked) reduction index walked by ks
   const int ksj = (K2 + 3) >> 2;
   double A0[KH], A1[C ? KH : 1];
+  int koff[KH];  // shared-memory offset of this lane's reduction entry in step ks, -1: beyond the end (fragment is zero)
 #pragma unroll
   for (int ks = 0; ks < KH; ++ks) {
     const int kk = 4 * ks + t;
     A0[ks] = 0.0;
     if (C) A1[ks] = 0.0;
-    if (ks < ksj && kk < K2 && b < chi) {
-      if (!C) {
-        A0[ks] = msg[kk + chi * b];
-      } else if (AL) {
-        A0[ks] = msg[kk + chi * b];          // M_re
-        A1[ks] = msg[chi2 + kk + chi * b];   // M_im
-      } else if (kk < chi) {
-        A0[ks] = msg[kk + chi * b];          // A_re
-        A1[ks] = msg[chi2 + kk + chi * b];   // A_im
-      } else {
-        A0[ks] = -msg[chi2 + (kk - chi) + chi * b];
-        A1[ks] = msg[(kk - chi) + chi * b];
+    koff[ks] = -1;
+    if (ks < ksj && kk < K2) {
+      koff[ks] = (!C || AL || kk < chi) ? kk * S : PL + (kk - chi) * S;
+      if (b < chi) {
+        if (!C) {
+          A0[ks] = msg[kk + chi * b];
+        } else if (AL) {
+          A0[ks] = msg[kk + chi * b];          // M_re
+          A1[ks] = msg[chi2 + kk + chi * b];   // M_im
+        } else if (kk < chi) {
+          A0[ks] = msg[kk + chi * b];          // A_re
+          A1[ks] = msg[chi2 + kk + chi * b];   // A_im
+        } else {
+          A0[ks] = -msg[chi2 + (kk - chi) + chi * b];
+          A1[ks] = msg[(kk - chi) + chi * b];
+        }
       }
     }
   }
   const unsigned short* tb = tab + M.tab;
-  for (int ft = fsub; ft < M.ntile; ft += fstep) {
-    const unsigned fb = tb[ft * 8 + g];
-    const bool fok = fb != kNoFibre;
-    double cre[2] = {0.0, 0.0}, cim[2] = {0.0, 0.0};
-    if (AL) {
-      double xr[KH], xi[KH];
+  const int bS = b * S;
+  const bool bok = b < chi;
+  // one tile of 8 fibres: fragments in, products, results out
+  auto load_frags = [&](unsigned fb, double (&x0)[KH], double (&x1)[C ? KH : 1]) {
 #pragma unroll
-      for (int ks = 0; ks < KH; ++ks) {
-        const int kk = 4 * ks + t;
-        const bool ok = fok && ks < ksj && kk < chi;
-        xr[ks] = ok ? src[fb + kk * S] : 0.0;
-        xi[ks] = ok ? src[PL + fb + kk * S] : 0.0;
-      }
+    for (int ks = 0; ks < KH; ++ks) {
+      const bool ok = koff[ks] >= 0 && fb != kNoFibre;
+      x0[ks] = ok ? src[fb + koff[ks]] : 0.0;
+      if (AL) x1[ks] = ok ? src[PL + fb + koff[ks]] : 0.0;
+    }
+  };
+  auto products = [&](const double (&x0)[KH], const double (&x1)[C ? KH : 1], double (&cre)[2], double (&cim)[2]) {
 #pragma unroll
-      for (int ks = 0; ks < KH; ++ks) {
-        if (ks < ksj) {
-          dmma884(cre, A0[ks], xr[ks]);
-          dmma884(cim, A1[ks], xr[ks]);
-          dmma884(cim, A0[ks], xi[ks]);
-          dmma884(cre, A1[ks], -xi[ks]);
-        }
-      }
-    } else {
-      double bv[KH];
-#pragma unroll
-      for (int ks = 0; ks < KH; ++ks) {
-        const int kk = 4 * ks + t;
-        const bool ok = fok && ks < ksj && kk < K2;
-        const int off = (!C || kk < chi) ? kk * S : PL + (kk - chi) * S;
-        bv[ks] = ok ? src[fb + off] : 0.0;
-      }
-#pragma unroll
-      for (int ks = 0; ks < KH; ++ks) {
-        if (ks < ksj) {
-          dmma884(cre, A0[ks], bv[ks]);
-          if (C) dmma884(cim, A1[ks], bv[ks]);
+    for (int ks = 0; ks < KH; ++ks) {
+      if (ks < ksj) {
+        if (AL) {
+          dmma884(cre, A0[ks], x0[ks]);
+          dmma884(cim, A1[ks], x0[ks]);
+          dmma884(cim, A0[ks], x1[ks]);
+          dmma884(cre, A1[ks], -x1[ks]);
+        } else {
+          dmma884(cre, A0[ks], x0[ks]);
+          if (C) dmma884(cim, A1[ks], x0[ks]);
         }
       }
     }
+  };
+  auto store_tile = [&](unsigned fb, const double (&cre)[2], const double (&cim)[2]) {
     const unsigned f0 = __shfl_sync(0xffffffffu, fb, 8 * t), f1 = __shfl_sync(0xffffffffu, fb, 8 * t + 4);
     if (src == dst) __syncwarp();  // in place (one row tile per fibre): every lane has read its fibres
-    if (b < chi) {
+    if (bok) {
       if (f0 != kNoFibre) {
-        dst[f0 + b * S] = cre[0];
-        if (C) dst[PL + f0 + b * S] = cim[0];
+        dst[f0 + bS] = cre[0];
+        if (C) dst[PL + f0 + bS] = cim[0];
       }
       if (f1 != kNoFibre) {
-        dst[f1 + b * S] = cre[1];
-        if (C) dst[PL + f1 + b * S] = cim[1];
+        dst[f1 + bS] = cre[1];
+        if (C) dst[PL + f1 + bS] = cim[1];
       }
     }
+  };
+  int ft = fsub;
+  // two independent tiles per iteration: twice the accumulator chains in flight behind the fixed DMMA latency
+  for (; ft + fstep < M.ntile; ft += 2 * fstep) {
+    const unsigned fbA = tb[ft * 8 + g], fbB = tb[(ft + fstep) * 8 + g];
+    double xa0[KH], xa1[C ? KH : 1], xb0[KH], xb1[C ? KH : 1];
+    load_frags(fbA, xa0, xa1);
+    load_frags(fbB, xb0, xb1);
+    double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0}, br[2] = {0.0, 0.0}, bi[2] = {0.0, 0.0};
+    products(xa0, xa1, ar, ai);
+    products(xb0, xb1, br, bi);
+    store_tile(fbA, ar, ai);
+    store_tile(fbB, br, bi);
+  }
+  if (ft < M.ntile) {
+    const unsigned fbA = tb[ft * 8 + g];
+    double xa0[KH], xa1[C ? KH : 1];
+    load_frags(fbA, xa0, xa1);
+    double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};
+    products(xa0, xa1, ar, ai);
+    store_tile(fbA, ar, ai);
   }
 }
 
@@ -214,34 +233,52 @@ __device__ __forceinline__ void op_close(const BlkMode M, const int PL, const do
   }
   const int npw = mtd == 4 ? 2 : 1;
   const int CH = mtd * 8;
-  double acc[NPW][2][2];
+  double acc[NPW][2][2], acc2[NPW][2][2];  // two k steps in flight: independent accumulator chains, summed at the end
 #pragma unroll
-  for (int q = 0; q < NPW; ++q) acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0;
+  for (int q = 0; q < NPW; ++q) {
+    acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0;
+    acc2[q][0][0] = acc2[q][0][1] = acc2[q][1][0] = acc2[q][1][1] = 0.0;
+  }
   const unsigned short* tb = tab + M.tab;
   const int nks = M.ntile * 2;
   const int bm = mt * 8 + g;
-  for (int ks = fs; ks < nks; ks += FS) {
+  const int bmS = bm * S;
+  const bool mok = bm < chi;
+  auto step = [&](int ks, double (&a)[NPW][2][2]) {
     const unsigned fb = tb[ks * 4 + t];
     const bool ok = fb != kNoFibre;
-    const bool okm = ok && bm < chi;
-    const double wre = okm ? W[fb + bm * S] : 0.0;
-    const double wim = (C && okm) ? W[PL + fb + bm * S] : 0.0;
+    const bool okm = ok && mok;
+    const double wre = okm ? W[fb + bmS] : 0.0;
+    const double wim = (C && okm) ? W[PL + fb + bmS] : 0.0;
 #pragma unroll
     for (int q = 0; q < NPW; ++q) {
       if (q < npw) {
         const int bn = (nt0 + q) * 8 + g;
         const bool okn = ok && bn < chi;
         const double xre = okn ? X[fb + bn * S] : 0.0;
-        dmma884(acc[q][0], wre, xre);
+        dmma884(a[q][0], wre, xre);
         if (C) {
           const double xim = okn ? X[PL + fb + bn * S] : 0.0;
-          dmma884(acc[q][0], wim, xim);
-          dmma884(acc[q][1], wim, xre);
-          dmma884(acc[q][1], -wre, xim);
+          dmma884(a[q][0], wim, xim);
+          dmma884(a[q][1], wim, xre);
+          dmma884(a[q][1], -wre, xim);
         }
       }
     }
+  };
+  int ks = fs;
+  for (; ks + FS < nks; ks += 2 * FS) {
+    step(ks, acc);
+    step(ks + FS, acc2);
   }
+  if (ks < nks) step(ks, acc);
+#pragma unroll
+  for (int q = 0; q < NPW; ++q)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      acc[q][p][0] += acc2[q][p][0];
+      acc[q][p][1] += acc2[q][p][1];
+    }
   if (mtd == 4) {
     // one warp owns a pair of 8 x 8 tiles over ALL fibres of the block: no cross-warp sum, straight to the partial buffer
     const int n2 = chi * chi;
@@ -286,29 +323,17 @@ __device__ __forceinline__ void op_close(const BlkMode M, const int PL, const do
 }
 
 template <bool C, int KS, int MT>
-__global__ void __launch_bounds__(kBT, 2) k_block(const BlkPass* __restrict__ gp, const BlkVertex* __restrict__ gv,
+__global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPass P, const BlkVertex* __restrict__ gv,
                                                   const unsigned short* __restrict__ gtab) {
   extern __shared__ __align__(128) double sm[];
-  __shared__ BlkPass P;
-  __shared__ BlkVertex V;
   __shared__ __align__(8) unsigned long long mbar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  {
-    const int* s = (const int*)gp;
-    int* d = (int*)&P;
-    for (int i = tid; i < (int)(sizeof(BlkPass) / 4); i += kBT) d[i] = s[i];
-  }
-  __syncthreads();
   const int vi = blockIdx.x / P.nblk, blk = blockIdx.x - vi * P.nblk;
-  {
-    const int* s = (const int*)(gv + vi);
-    int* d = (int*)&V;
-    for (int i = tid; i < (int)(sizeof(BlkVertex) / 4); i += kBT) d[i] = s[i];
-  }
+  const BlkVertex* __restrict__ V = gv + vi;
   double* bufs = sm;
   double* red = bufs + (size_t)P.nbuf * P.bufsz;
-  unsigned short* tab = (unsigned short*)(red + kRedDoubles);
-  for (int i = tid; i < P.tab_len; i += kBT) tab[i] = gtab[i];
+  double* msm = red + kRedDoubles;                                    // staged messages (P.msg_smem)
+  unsigned short* tab = (unsigned short*)(msm + P.msg_len);
   constexpr int PLN = C ? 2 : 1;
   const unsigned mb = smem_u32(&mbar);
   if (P.bulk && tid == 0) {
@@ -316,7 +341,8 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const BlkPass* __restrict__ gp
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  // ---- stage the block(s): buffer 0 = site tensor, buffer 1 = partially absorbed tensor ---------------------------------
+  // ---- stage the block(s): buffer 0 = site tensor, buffer 1 = partially absorbed tensor.  The bulk copies are issued
+  // first; the fibre tables and the messages follow with ordinary loads while the copies are in flight. ------------------
   auto row_pos = [&](int row) {
     int off = 0, q = row;
 #pragma unroll
@@ -331,6 +357,8 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const BlkPass* __restrict__ gp
   const long long goff = (long long)blk * P.gblk;
   const int nin = P.load_p ? 2 : 1;
   const int rows_total = nin * PLN * P.nrows;
+  const double* gX = V->X;
+  const double* gP = P.load_p ? V->Pin : nullptr;
   if (P.bulk) {
     const unsigned rowbytes = (unsigned)P.rowlen * 8u;
     if (tid == 0) {
@@ -340,19 +368,11 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const BlkPass* __restrict__ gp
     for (int r = tid; r < rows_total; r += kBT) {
       const int which = r / (PLN * P.nrows), rr = r - which * (PLN * P.nrows);
       const int pl = rr / P.nrows, row = rr - pl * P.nrows;
-      const double* g = (which ? V.Pin : V.X) + (long long)pl * P.gplane + goff + (long long)row * P.grow;
+      const double* g = (which ? gP : gX) + (long long)pl * P.gplane + goff + (long long)row * P.grow;
       const unsigned dsts = smem_u32(bufs + (size_t)which * P.bufsz + (size_t)pl * P.PL + row_pos(row));
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dsts),
                    "l"(g), "r"(rowbytes), "r"(mb)
                    : "memory");
-    }
-    unsigned done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-          : "=r"(done)
-          : "r"(mb), "r"(0u)
-          : "memory");
     }
   } else {
     const long long tot = (long long)rows_total * P.rowlen;
@@ -361,7 +381,28 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const BlkPass* __restrict__ gp
       const int which = r / (PLN * P.nrows), rr = r - which * (PLN * P.nrows);
       const int pl = rr / P.nrows, row = rr - pl * P.nrows;
       bufs[(size_t)which * P.bufsz + (size_t)pl * P.PL + row_pos(row) + c] =
-          (which ? V.Pin : V.X)[(long long)pl * P.gplane + goff + (long long)row * P.grow + c];
+          (which ? gP : gX)[(long long)pl * P.gplane + goff + (long long)row * P.grow + c];
+    }
+  }
+  for (int i = tid; i < P.tab_len; i += kBT) tab[i] = gtab[i];
+  if (P.msg_smem) {
+#pragma unroll
+    for (int k = 0; k < kMaxGM; ++k)
+      if (k < P.nmodes) {
+        const double* __restrict__ gm = V->msg[P.modes[k].slot];
+        const int n = PLN * P.modes[k].chi * P.modes[k].chi;
+        double* d = msm + P.msg_off[k];
+        for (int i = tid; i < n; i += kBT) d[i] = gm[i];
+      }
+  }
+  if (P.bulk) {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(mb), "r"(0u)
+          : "memory");
     }
   }
   __syncthreads();
@@ -370,18 +411,47 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const BlkPass* __restrict__ gp
     const BlkOp op = P.ops[oi];
     if (op.type == OP_MP) {
       const BlkMode M = P.modes[op.mode];
-      op_mp<C, KS>(M, P.PL, V.msg[M.slot], bufs + (size_t)op.src * P.bufsz, bufs + (size_t)op.dst * P.bufsz, tab, warp, lane);
+      const double* msg = P.msg_smem ? msm + P.msg_off[op.mode] : V->msg[M.slot];
+      op_mp<C, KS>(M, P.PL, msg, bufs + (size_t)op.src * P.bufsz, bufs + (size_t)op.dst * P.bufsz, tab, warp, lane);
     } else if (op.type == OP_CLOSE) {
       const BlkMode M = P.modes[op.mode];
-      double* out = V.part[M.slot] + (size_t)blk * PLN * M.chi * M.chi;
+      double* out = V->part[M.slot] + (size_t)blk * PLN * M.chi * M.chi;
       op_close<C, MT>(M, P.PL, bufs + (size_t)op.src * P.bufsz, bufs, red, out, tab, warp, lane, tid);
     } else {
       const double* b = bufs + (size_t)op.src * P.bufsz;
-      const long long tot = (long long)PLN * P.nrows * P.rowlen;
-      for (long long i = tid; i < tot; i += kBT) {
-        const int r = (int)(i / P.rowlen), c = (int)(i - (long long)r * P.rowlen);
-        const int pl = r / P.nrows, row = r - pl * P.nrows;
-        V.Wout[(long long)pl * P.gplane + goff + (long long)row * P.grow + c] = b[(size_t)pl * P.PL + row_pos(row) + c];
+      double* gW = V->Wout;
+      // rows are contiguous on both sides and even in length whenever the pass moves them with bulk copies
+      if (P.bulk) {
+        // 16-byte moves, row positions from the table: a warp per row (long rows) or several rows per warp (short rows)
+        const int half = P.rowlen >> 1;
+        const unsigned short* rt = tab + P.rowtab;
+        if (half >= 32) {
+          for (int pl = 0; pl < PLN; ++pl)
+            for (int row = warp; row < P.nrows; row += kNW) {
+              const double* sp = b + (size_t)pl * P.PL + rt[row];
+              double* gp = gW + (long long)pl * P.gplane + goff + (long long)row * P.grow;
+              for (int c = lane; c < half; c += 32)
+                *reinterpret_cast<double2*>(gp + 2 * c) = *reinterpret_cast<const double2*>(sp + 2 * c);
+            }
+        } else {
+          const int rpw = 32 / half, lr = lane / half, lc = lane - lr * half;
+          for (int pl = 0; pl < PLN; ++pl)
+            for (int row0 = warp * rpw; row0 < P.nrows; row0 += kNW * rpw) {
+              const int row = row0 + lr;
+              if (lr < rpw && row < P.nrows) {
+                const double* sp = b + (size_t)pl * P.PL + rt[row];
+                double* gp = gW + (long long)pl * P.gplane + goff + (long long)row * P.grow;
+                *reinterpret_cast<double2*>(gp + 2 * lc) = *reinterpret_cast<const double2*>(sp + 2 * lc);
+              }
+            }
+        }
+      } else {
+        const long long tot = (long long)PLN * P.nrows * P.rowlen;
+        for (long long i = tid; i < tot; i += kBT) {
+          const int r = (int)(i / P.rowlen), c = (int)(i - (long long)r * P.rowlen);
+          const int pl = r / P.nrows, row = r - pl * P.nrows;
+          gW[(long long)pl * P.gplane + goff + (long long)row * P.grow + c] = b[(size_t)pl * P.PL + row_pos(row) + c];
+        }
       }
     }
     __syncthreads();
@@ -396,7 +466,7 @@ struct BlkRedJob {
 };
 __global__ void __launch_bounds__(128) k_block_reduce(const BlkRedJob* __restrict__ jobs) {
   const BlkRedJob J = jobs[blockIdx.x];
-  for (int i = threadIdx.x; i < J.n; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < J.n; i += gridDim.y * blockDim.x) {
     double a = 0.0;
     for (int b = 0; b < J.nblk; ++b) a += J.part[(size_t)b * J.n + i];
     J.out[i] = a;
@@ -626,7 +696,8 @@ constexpr size_t kSmemTwoCtas = 113 * 1024;
 constexpr size_t kSmemOneCta = 226 * 1024;
 
 size_t pass_smem(const BlkPass& P, size_t tab_len) {
-  return (size_t)P.nbuf * P.bufsz * sizeof(double) + kRedDoubles * sizeof(double) + ((tab_len * 2 + 15) & ~(size_t)15) + 64;
+  return (size_t)P.nbuf * P.bufsz * sizeof(double) + kRedDoubles * sizeof(double) + (size_t)P.msg_len * sizeof(double) +
+         ((tab_len * 2 + 15) & ~(size_t)15) + 64;
 }
 
 // k * S mod 16 distinct for the (up to) four consecutive bond indices a half-warp touches together
@@ -836,7 +907,38 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, bool aligned, c
       tab_len += (size_t)((nreal / m.chi + 15) & ~7ll);
     }
   }
+  // shared-memory position of every row (the kernel's stores read it instead of dividing)
+  P.rowtab = (int)out.table.size();
+  if (with_tables) {
+    for (int row = 0; row < P.nrows; ++row) {
+      int off = 0, q = row;
+      for (int l = 0; l < P.nlev; ++l) {
+        off += (q % P.lev_n[l]) * P.lev_s[l];
+        q /= P.lev_n[l];
+      }
+      out.table.push_back((unsigned short)off);
+    }
+    while (out.table.size() % 8) out.table.push_back(0);
+    tab_len = out.table.size();
+  } else {
+    tab_len += (size_t)((P.nrows + 15) & ~7);
+  }
   P.tab_len = (int)out.table.size();
+  // messages in shared memory (the fragments of every mode product are re-read from them at the start of the operation)
+  // unless that costs the second CTA per SM
+  {
+    int len = 0;
+    for (int k = 0; k < nm; ++k) {
+      P.msg_off[k] = len;
+      len += (cplx ? 2 : 1) * P.modes[k].chi * P.modes[k].chi;
+    }
+    len = (len + 1) & ~1;
+    const size_t without = pass_smem(P, tab_len);
+    const size_t with = without + (size_t)len * sizeof(double);
+    const bool fits = with <= kSmemTwoCtas || (without > kSmemTwoCtas && with <= kSmemOneCta);
+    P.msg_smem = fits ? 1 : 0;
+    P.msg_len = fits ? len : 0;
+  }
   out.smem = pass_smem(P, tab_len);
   return true;
 }
@@ -994,7 +1096,6 @@ struct Bucket {
   const Geometry* geo = nullptr;
   std::vector<int> verts;
   // device copies of the geometry (per network: they live on its device)
-  BlkPass* d_pass = nullptr;  // [3]
   unsigned short* d_tab[3] = {nullptr, nullptr, nullptr};
   // per update() call
   DevBuf* scratch = nullptr;  // P and S of every vertex
@@ -1027,7 +1128,7 @@ template <bool C, int KS, int MT>
 void launch_inst(itn_ctx* ctx, unsigned grid, size_t smem, const BlkPass* dp, const BlkVertex* dv, const unsigned short* dt) {
   CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  k_block<C, KS, MT><<<grid, kBT, smem, ctx->stream>>>(dp, dv, dt);
+  k_block<C, KS, MT><<<grid, kBT, smem, ctx->stream>>>(*dp, dv, dt);  // the descriptor travels as a kernel parameter
   ITN_LAUNCH_CHECK(ctx);
 }
 
@@ -1068,7 +1169,6 @@ void itn_block_release(itn_net* net) {
   for (auto& kv : bc->buckets) {
     Bucket& b = kv.second;
     end_call(b);
-    itn_dev_free(net->ctx, b.d_pass);
     for (auto& t : b.d_tab) itn_dev_free(net->ctx, t);
   }
   delete bc;
@@ -1138,16 +1238,12 @@ void itn_block_bp_begin(itn_net* net, const std::vector<int>& dids, const std::v
     const size_t nv = b.verts.size();
     const int z = G.sig.z;
     end_call(b);
-    if (!b.d_pass) {
-      b.d_pass = (BlkPass*)itn_dev_alloc(ctx, 3 * sizeof(BlkPass));
-      BlkPass hp[3] = {G.pass[0].desc, G.pass[1].desc, G.pass[2].desc};
-      CUDA_CHECK(cudaMemcpyAsync(b.d_pass, hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+    if (!b.d_tab[0]) {
       for (int w = 0; w < 3; ++w) {
         b.d_tab[w] = (unsigned short*)itn_dev_alloc(ctx, std::max<size_t>(G.pass[w].table.size(), 8) * sizeof(unsigned short));
         CUDA_CHECK(cudaMemcpyAsync(b.d_tab[w], G.pass[w].table.data(), G.pass[w].table.size() * sizeof(unsigned short),
                                    cudaMemcpyHostToDevice, ctx->stream));
       }
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // hp lives on this stack frame
     }
     size_t part_v = 0;  // doubles of partial results per vertex
     std::vector<size_t> part_off(z);
@@ -1201,9 +1297,12 @@ void itn_block_bp_run(itn_net* net) {
     const size_t nv = b.verts.size();
     ITN_REQUIRE(b.dverts != nullptr, ITN_EINVAL, "block sweep is not prepared");
     for (int w = 0; w < 3; ++w)
-      launch_pass(ctx, net->cplx, G.KS, (unsigned)(nv * G.pass[w].desc.nblk), G.pass[w].smem, b.d_pass + w,
+      launch_pass(ctx, net->cplx, G.KS, (unsigned)(nv * G.pass[w].desc.nblk), G.pass[w].smem, &G.pass[w].desc,
                   b.dverts->as<BlkVertex>() + w * nv, b.d_tab[w]);
-    k_block_reduce<<<(unsigned)b.nred, 128, 0, ctx->stream>>>(b.dred->as<BlkRedJob>());
+    int chimax = 0;
+    for (int k = 0; k < G.sig.z; ++k) chimax = std::max(chimax, G.sig.chi[k]);
+    const unsigned ry = (unsigned)std::max(1, std::min(16, (net->planes() * chimax * chimax + 127) / 128));
+    k_block_reduce<<<dim3((unsigned)b.nred, ry), 128, 0, ctx->stream>>>(b.dred->as<BlkRedJob>());
     ITN_LAUNCH_CHECK(ctx);
   }
 }

@@ -100,3 +100,47 @@ def test_julia_shim_ccalls_match_the_prototypes():
         assert ret == ("Cstring" if name == "itn_last_error" else "Cint")
         for p, t in zip(params, types):
             assert ("*" in p or "[" in p) == t.startswith("Ptr"), f"{name}: `{p}` vs {t}"
+
+
+def test_julia_shim_implements_the_abstract_cache_interface():
+    # The reference's extension point is dispatch on AbstractBeliefPropagationCache{V, PV}
+    # (src/caches/abstractbeliefpropagationcache.jl:17,44-69) plus the algorithm tag that initialize_cache / update
+    # dispatch on (src/initialize_cache.jl:10-29, abstract :313-337).  Julia is not available here, so this is a static
+    # check that julia/ITNB200.jl defines a method on B200BeliefPropagationCache for every function a new cache type must
+    # provide, and that the front-ends' entry points carry the "bp_b200" tag.
+    jl = open(os.path.join(ROOT, "julia", "ITNB200.jl")).read()
+    m = re.search(r"mutable struct B200BeliefPropagationCache\{([^}]*)\}\s*<:\s*AbstractBeliefPropagationCache\{V,\s*PV\}", jl, flags=re.S)
+    assert m, "the cache must subtype AbstractBeliefPropagationCache{V, PV} with BOTH parameters"
+    assert m.group(1).replace(" ", "").startswith("V,PV")
+    required = ["partitioned_tensornetwork", "messages", "default_update_alg", "default_message_update_alg", "default_bp_maxiter",
+                "default_edge_sequence", "default_bp_edge_sequence", "environment", "region_scalar", "partitions", "rescale",
+                "rescale_messages", "rescale_partitions", "update_factors", "update_factor", "message", "set_message!",
+                "set_messages!", "updated_message", "logscalar", "vertex_scalars", "edge_scalars", "set_default_kwargs", "update",
+                "tensornetwork"]
+    for name in required:
+        pat = r"ITensorNetworks\." + re.escape(name) + r"\((?:[^()]|\([^()]*\))*B200BeliefPropagationCache"
+        assert re.search(pat, jl), f"no B200BeliefPropagationCache method for ITensorNetworks.{name}"
+    for pat in (r"Base\.copy\(bpc::B200BeliefPropagationCache", r"PartitionedGraphs\.quotientedges\(bpc::B200BeliefPropagationCache",
+                r"PartitionedGraphs\.partitioned_vertices\(bpc::B200BeliefPropagationCache",
+                r"DataGraphs\.set_vertex_data!\(bpc::B200BeliefPropagationCache",
+                r"Adapt\.adapt_structure\(to::B200Device, bpc::BeliefPropagationCache\)",
+                r"Adapt\.adapt_structure\(to::Type\{<:Array\}, bpc::B200BeliefPropagationCache\)"):
+        assert re.search(pat, jl), pat
+    # region_scalar for both region kinds
+    assert re.search(r"region_scalar\(bpc::B200BeliefPropagationCache, pv::QuotientVertex", jl)
+    assert re.search(r"region_scalar\(bpc::B200BeliefPropagationCache, pe::QuotientEdge", jl)
+    # the algorithm tag the front-ends dispatch on
+    for fn in ("initialize_cache", "update", "set_default_kwargs", "expect"):
+        assert re.search(r"ITensorNetworks\." + fn + r"\(alg::Algorithm\"bp_b200\"", jl), fn
+    assert re.search(r"ITensors\.apply\(o::ITensor, ψ::AbstractITensorNetwork; envs::B200Environment", jl)
+    # every name imported from ITensorNetworks exists in the reference sources (a typo would fail at `using` time)
+    ref = os.environ.get("ITN_REFERENCE_SRC", "/root/reference/src")
+    if os.path.isdir(ref):
+        src = "\n".join(open(os.path.join(dp, f), errors="ignore").read() for dp, _, fs in os.walk(ref) for f in fs if f.endswith(".jl"))
+        imp = re.search(r"using ITensorNetworks: (.*?)\nusing", jl, flags=re.S).group(1)
+        for name in [x.strip() for x in imp.replace("\n", " ").split(",")]:
+            if name and name != "ITensorNetworks":
+                assert re.search(r"\b" + re.escape(name) + r"\b", src), f"{name} is not defined in the reference"
+        for name in set(re.findall(r"ITensorNetworks\.([a-z_!]+)\(", jl)):
+            assert re.search(r"(function\s+|\.|^|\s)" + re.escape(name) + r"\s*\(", src, flags=re.M), \
+                f"ITensorNetworks.{name} is not a function of the reference"
