@@ -59,6 +59,7 @@ struct BlkMode {
   int ntile;  // fibre tiles (8 fibres each; the table is padded with kNoFibre)
   int tab;    // offset of the fibre table of this mode (entries)
   int slot;   // bond slot at the vertex (message / output index)
+  int exact;  // no padding anywhere: the fibre count is a multiple of 8 and the stacked reduction length a multiple of 4
 };
 struct BlkPass {
   int nblk;           // blocks per vertex
@@ -107,57 +108,54 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 //   aligned (KS >= 8): each plane padded to KS / 2 steps of its own; the sign moves to the tensor operand
 //           (out_re = M_re^T X_re + M_im^T (-X_im), out_im = M_im^T X_re + M_re^T X_im), so only M_re and M_im are kept:
 //           KS doubles of fragments instead of 2 KS (chi = 32: 64 registers instead of 128)
+// One message-fragment value: what lane (g, t) of the warp owning row tile mt holds for reduction step ks
+// (which = 0: first array, 1: second array; see the stackings above).
 template <bool C, int KS>
-__device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const double* __restrict__ msg, const double* src,
-                                      double* dst, const unsigned short* __restrict__ tab, const int warp, const int lane) {
+__device__ __forceinline__ double mp_fragment(const double* __restrict__ msg, int chi, int mt, int ks, int which, int lane) {
   constexpr bool AL = C && KS >= 8;
-  constexpr int KH = AL ? KS / 2 : KS;  // fragments per array
-  const int chi = M.chi, S = M.S;
-  const int mtj = (chi + 7) >> 3;
-  const int mtd = mtj == 3 ? 4 : mtj;  // warps are dealt out over 1, 2 or 4 row tiles
-  const int mt = warp % mtd, fsub = warp / mtd, fstep = kNW / mtd;
   const int g = lane >> 2, t = lane & 3;
-  const int b = mt * 8 + g;
-  if (mt >= mtj) return;
+  const int b = mt * 8 + g, kk = 4 * ks + t;
+  const int K2 = (C && !AL) ? 2 * chi : chi;
+  if (b >= chi || kk >= K2) return 0.0;
   const int chi2 = chi * chi;
-  const int K2 = (C && !AL) ? 2 * chi : chi;  // length of the (stacked) reduction index walked by ks
+  if (!C) return which ? 0.0 : msg[kk + chi * b];
+  if (AL) return which ? msg[chi2 + kk + chi * b] : msg[kk + chi * b];
+  if (kk < chi) return which ? msg[chi2 + kk + chi * b] : msg[kk + chi * b];
+  return which ? msg[(kk - chi) + chi * b] : -msg[chi2 + (kk - chi) + chi * b];
+}
+
+template <bool C, int KS, bool EXACT>
+__device__ __forceinline__ void mp_tiles(const BlkMode M, const int PL, const double (&A0)[(C && KS >= 8) ? KS / 2 : KS],
+                                         const double (&A1)[C ? ((KS >= 8) ? KS / 2 : KS) : 1], const double* src, double* dst,
+                                         const unsigned short* __restrict__ tb, const int fsub, const int fstep, const int b,
+                                         const int lane) {
+  constexpr bool AL = C && KS >= 8;
+  constexpr int KH = AL ? KS / 2 : KS;
+  const int chi = M.chi, S = M.S;
+  const int g = lane >> 2, t = lane & 3;
+  const int K2 = (C && !AL) ? 2 * chi : chi;
   const int ksj = (K2 + 3) >> 2;
-  double A0[KH], A1[C ? KH : 1];
   int koff[KH];  // shared-memory offset of this lane's reduction entry in step ks, -1: beyond the end (fragment is zero)
 #pragma unroll
   for (int ks = 0; ks < KH; ++ks) {
     const int kk = 4 * ks + t;
-    A0[ks] = 0.0;
-    if (C) A1[ks] = 0.0;
-    koff[ks] = -1;
-    if (ks < ksj && kk < K2) {
-      koff[ks] = (!C || AL || kk < chi) ? kk * S : PL + (kk - chi) * S;
-      if (b < chi) {
-        if (!C) {
-          A0[ks] = msg[kk + chi * b];
-        } else if (AL) {
-          A0[ks] = msg[kk + chi * b];          // M_re
-          A1[ks] = msg[chi2 + kk + chi * b];   // M_im
-        } else if (kk < chi) {
-          A0[ks] = msg[kk + chi * b];          // A_re
-          A1[ks] = msg[chi2 + kk + chi * b];   // A_im
-        } else {
-          A0[ks] = -msg[chi2 + (kk - chi) + chi * b];
-          A1[ks] = msg[(kk - chi) + chi * b];
-        }
-      }
-    }
+    koff[ks] = (ks < ksj && kk < K2) ? ((!C || AL || kk < chi) ? kk * S : PL + (kk - chi) * S) : -1;
   }
-  const unsigned short* tb = tab + M.tab;
   const int bS = b * S;
   const bool bok = b < chi;
-  // one tile of 8 fibres: fragments in, products, results out
   auto load_frags = [&](unsigned fb, double (&x0)[KH], double (&x1)[C ? KH : 1]) {
 #pragma unroll
     for (int ks = 0; ks < KH; ++ks) {
-      const bool ok = koff[ks] >= 0 && fb != kNoFibre;
-      x0[ks] = ok ? src[fb + koff[ks]] : 0.0;
-      if (AL) x1[ks] = ok ? src[PL + fb + koff[ks]] : 0.0;
+      if (EXACT) {
+        if (ks < ksj) {
+          x0[ks] = src[fb + koff[ks]];
+          if (AL) x1[ks] = src[PL + fb + koff[ks]];
+        }
+      } else {
+        const bool ok = koff[ks] >= 0 && fb != kNoFibre;
+        x0[ks] = ok ? src[fb + koff[ks]] : 0.0;
+        if (AL) x1[ks] = ok ? src[PL + fb + koff[ks]] : 0.0;
+      }
     }
   };
   auto products = [&](const double (&x0)[KH], const double (&x1)[C ? KH : 1], double (&cre)[2], double (&cim)[2]) {
@@ -180,11 +178,11 @@ __device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const doubl
     const unsigned f0 = __shfl_sync(0xffffffffu, fb, 8 * t), f1 = __shfl_sync(0xffffffffu, fb, 8 * t + 4);
     if (src == dst) __syncwarp();  // in place (one row tile per fibre): every lane has read its fibres
     if (bok) {
-      if (f0 != kNoFibre) {
+      if (EXACT || f0 != kNoFibre) {
         dst[f0 + bS] = cre[0];
         if (C) dst[PL + f0 + bS] = cim[0];
       }
-      if (f1 != kNoFibre) {
+      if (EXACT || f1 != kNoFibre) {
         dst[f1 + bS] = cre[1];
         if (C) dst[PL + f1 + bS] = cim[1];
       }
@@ -192,7 +190,9 @@ __device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const doubl
   };
   int ft = fsub;
   // two independent tiles per iteration: twice the accumulator chains in flight behind the fixed DMMA latency
-  for (; ft + fstep < M.ntile; ft += 2 * fstep) {
+  // (not for chi = 32: its fragments alone take 96 registers, and a tile already has 32 products)
+  constexpr bool TWO = KS < 16;
+  for (; TWO && ft + fstep < M.ntile; ft += 2 * fstep) {
     const unsigned fbA = tb[ft * 8 + g], fbB = tb[(ft + fstep) * 8 + g];
     double xa0[KH], xa1[C ? KH : 1], xb0[KH], xb1[C ? KH : 1];
     load_frags(fbA, xa0, xa1);
@@ -203,7 +203,7 @@ __device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const doubl
     store_tile(fbA, ar, ai);
     store_tile(fbB, br, bi);
   }
-  if (ft < M.ntile) {
+  for (; ft < M.ntile; ft += fstep) {
     const unsigned fbA = tb[ft * 8 + g];
     double xa0[KH], xa1[C ? KH : 1];
     load_frags(fbA, xa0, xa1);
@@ -211,6 +211,39 @@ __device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const doubl
     products(xa0, xa1, ar, ai);
     store_tile(fbA, ar, ai);
   }
+}
+
+// frag != nullptr: the fragment-ordered copy of the message staged in shared memory by the prologue
+// ([row tile][step][array][lane]); otherwise the fragments are gathered from the message in global memory.
+template <bool C, int KS>
+__device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const double* __restrict__ msg,
+                                      const double* __restrict__ frag, const double* src, double* dst,
+                                      const unsigned short* __restrict__ tab, const int warp, const int lane) {
+  constexpr bool AL = C && KS >= 8;
+  constexpr int KH = AL ? KS / 2 : KS;  // fragments per array
+  const int chi = M.chi;
+  const int mtj = (chi + 7) >> 3;
+  const int mtd = mtj == 3 ? 4 : mtj;  // warps are dealt out over 1, 2 or 4 row tiles
+  const int mt = warp % mtd, fsub = warp / mtd, fstep = kNW / mtd;
+  if (mt >= mtj) return;
+  double A0[KH], A1[C ? KH : 1];
+  if (frag) {
+    const double* fr = frag + (size_t)mt * KH * 64 + lane;
+#pragma unroll
+    for (int ks = 0; ks < KH; ++ks) {
+      A0[ks] = fr[ks * 64];
+      if (C) A1[ks] = fr[ks * 64 + 32];
+    }
+  } else {
+#pragma unroll
+    for (int ks = 0; ks < KH; ++ks) {
+      A0[ks] = mp_fragment<C, KS>(msg, chi, mt, ks, 0, lane);
+      if (C) A1[ks] = mp_fragment<C, KS>(msg, chi, mt, ks, 1, lane);
+    }
+  }
+  const int b = mt * 8 + (lane >> 2);
+  if (M.exact) mp_tiles<C, KS, true>(M, PL, A0, A1, src, dst, tab + M.tab, fsub, fstep, b, lane);
+  else mp_tiles<C, KS, false>(M, PL, A0, A1, src, dst, tab + M.tab, fsub, fstep, b, lane);
 }
 
 // ---- out[b + chi b'] = sum over the fibres of the block  W[f, b] conj(X[f, b'])  (4 fibres per k step) -------------------
@@ -365,14 +398,18 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
       const unsigned total = rowbytes * (unsigned)rows_total;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(total) : "memory");
     }
-    for (int r = tid; r < rows_total; r += kBT) {
-      const int which = r / (PLN * P.nrows), rr = r - which * (PLN * P.nrows);
-      const int pl = rr / P.nrows, row = rr - pl * P.nrows;
-      const double* g = (which ? gP : gX) + (long long)pl * P.gplane + goff + (long long)row * P.grow;
-      const unsigned dsts = smem_u32(bufs + (size_t)which * P.bufsz + (size_t)pl * P.PL + row_pos(row));
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dsts),
-                   "l"(g), "r"(rowbytes), "r"(mb)
-                   : "memory");
+    // row positions come from the table in global memory (no divisions); every thread issues the copies of its rows for
+    // both planes of both tensors
+    for (int row = tid; row < P.nrows; row += kBT) {
+      const int pos = gtab[P.rowtab + row];
+      for (int which = 0; which < nin; ++which)
+        for (int pl = 0; pl < PLN; ++pl) {
+          const double* g = (which ? gP : gX) + (long long)pl * P.gplane + goff + (long long)row * P.grow;
+          const unsigned dsts = smem_u32(bufs + (size_t)which * P.bufsz + (size_t)pl * P.PL + pos);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dsts),
+                       "l"(g), "r"(rowbytes), "r"(mb)
+                       : "memory");
+        }
     }
   } else {
     const long long tot = (long long)rows_total * P.rowlen;
@@ -386,13 +423,20 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
   }
   for (int i = tid; i < P.tab_len; i += kBT) tab[i] = gtab[i];
   if (P.msg_smem) {
+    // fragment-ordered copies of the messages: [row tile][step][array][lane], what op_mp keeps in registers per operation
+    constexpr int KHs = (C && KS >= 8) ? KS / 2 : KS;
 #pragma unroll
     for (int k = 0; k < kMaxGM; ++k)
       if (k < P.nmodes) {
         const double* __restrict__ gm = V->msg[P.modes[k].slot];
-        const int n = PLN * P.modes[k].chi * P.modes[k].chi;
+        const int chi = P.modes[k].chi;
+        const int n = ((chi + 7) >> 3) * KHs * 64;
         double* d = msm + P.msg_off[k];
-        for (int i = tid; i < n; i += kBT) d[i] = gm[i];
+        for (int i = tid; i < n; i += kBT) {
+          const int ln = i & 31, which = (i >> 5) & 1, r = i >> 6;
+          const int ks = r % KHs, mt = r / KHs;
+          d[i] = mp_fragment<C, KS>(gm, chi, mt, ks, which, ln);
+        }
       }
   }
   if (P.bulk) {
@@ -411,8 +455,8 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
     const BlkOp op = P.ops[oi];
     if (op.type == OP_MP) {
       const BlkMode M = P.modes[op.mode];
-      const double* msg = P.msg_smem ? msm + P.msg_off[op.mode] : V->msg[M.slot];
-      op_mp<C, KS>(M, P.PL, msg, bufs + (size_t)op.src * P.bufsz, bufs + (size_t)op.dst * P.bufsz, tab, warp, lane);
+      op_mp<C, KS>(M, P.PL, V->msg[M.slot], P.msg_smem ? msm + P.msg_off[op.mode] : nullptr, bufs + (size_t)op.src * P.bufsz,
+                   bufs + (size_t)op.dst * P.bufsz, tab, warp, lane);
     } else if (op.type == OP_CLOSE) {
       const BlkMode M = P.modes[op.mode];
       double* out = V->part[M.slot] + (size_t)blk * PLN * M.chi * M.chi;
@@ -728,8 +772,9 @@ struct PassChoice {
 // Builds the plan of one pass.  fast (passes 1 and 3): the block holds every index of (site, G1) and `chunk` values of G2's
 // flat index; slow (pass 2): `chunk` values of the flat (site, G1) index and every index of G2.  Rows (contiguous in HBM
 // and in shared memory) are placed in shared memory with padded strides so that no bond stride is a multiple of 8 doubles.
-bool plan_pass(const Signature& sg, int h, int which, bool cplx, bool aligned, const PassChoice& ch, bool with_tables,
+bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, const PassChoice& ch, bool with_tables,
                PassPlan& out) {
+  const bool aligned = cplx && ks_inst >= 8;
   const int z = sg.z, d = sg.d;
   long long L = d, XR = 1;
   for (int k = 0; k < h; ++k) L *= sg.chi[k];
@@ -882,6 +927,10 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, bool aligned, c
     P.modes[k].chi = m.chi;
     P.modes[k].S = m.S;
     P.modes[k].slot = m.slot;
+    {
+      const int K2 = (cplx && !aligned) ? 2 * m.chi : m.chi;
+      P.modes[k].exact = ((nreal / m.chi) % 8 == 0 && K2 % 4 == 0) ? 1 : 0;
+    }
     if (with_tables) {
       // every combination of the other axes, first axis fastest
       std::vector<const Axis*> others;
@@ -928,11 +977,12 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, bool aligned, c
   // unless that costs the second CTA per SM
   {
     int len = 0;
+    // fragment-ordered copies, sized by the kernel instance of the vertex (its largest extent, `ks_inst`)
+    const int KHs = (cplx && ks_inst >= 8) ? ks_inst / 2 : ks_inst;
     for (int k = 0; k < nm; ++k) {
       P.msg_off[k] = len;
-      len += (cplx ? 2 : 1) * P.modes[k].chi * P.modes[k].chi;
+      len += ((P.modes[k].chi + 7) / 8) * KHs * 64;
     }
-    len = (len + 1) & ~1;
     const size_t without = pass_smem(P, tab_len);
     const size_t with = without + (size_t)len * sizeof(double);
     const bool fits = with <= kSmemTwoCtas || (without > kSmemTwoCtas && with <= kSmemOneCta);
@@ -945,7 +995,8 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, bool aligned, c
 
 // Chooses the block of a pass: the largest chunk that leaves two CTAs per SM (one if it must), shrunk while the launch
 // would not cover the SMs; then the paddings with the fewest excess wavefronts.
-bool choose_pass(const Signature& sg, int h, int which, bool cplx, bool aligned, size_t nverts, PassPlan& best) {
+bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, size_t nverts, PassPlan& best) {
+  const bool aligned = cplx && ks_inst >= 8;
   const int z = sg.z, d = sg.d;
   long long L = d, XR = 1;
   for (int k = 0; k < h; ++k) L *= sg.chi[k];
@@ -975,7 +1026,7 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, bool aligned,
     t.chunk = (int)c;
     t.pad_chunk = fast ? 6 : 0;  // room for the paddings tried below
     t.pad_plane = 6;
-    if (!plan_pass(sg, h, which, cplx, aligned, t, false, pp)) continue;
+    if (!plan_pass(sg, h, which, cplx, ks_inst, t, false, pp)) continue;
     if (pp.smem > kSmemOneCta) continue;
     const long long nb = (fast ? L : XR) * c;
     const long long ctas = (long long)pp.desc.nblk * (long long)nverts;
@@ -1004,7 +1055,7 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, bool aligned,
       PassChoice t = ch;
       t.pad_chunk = pc;
       t.pad_plane = pl;
-      if (!plan_pass(sg, h, which, cplx, aligned, t, true, pp)) continue;
+      if (!plan_pass(sg, h, which, cplx, ks_inst, t, true, pp)) continue;
       if (pp.smem > kSmemOneCta) continue;
       const double ex = (double)pp.excess + 1e-3 * (pc + pl);
       if (ex < best_ex) {
@@ -1069,9 +1120,8 @@ const Geometry* geometry_for(const Signature& s, bool cplx, size_t nverts) {
     g->nelem *= s.chi[k];
   }
   kernel_instance(cplx, chimax, g->KS, g->MT);
-  const bool aligned = cplx && g->KS >= 8;
   bool ok = true;
-  for (int w = 0; w < 3 && ok; ++w) ok = choose_pass(s, g->h, w, cplx, aligned, nverts, g->pass[w]);
+  for (int w = 0; w < 3 && ok; ++w) ok = choose_pass(s, g->h, w, cplx, g->KS, nverts, g->pass[w]);
   if (!ok) g->KS = 0;
   if (ok && block_debug()) {
     fprintf(stderr, "[itn block] d=%d z=%d chi=", s.d, s.z);
@@ -1348,7 +1398,7 @@ extern "C" int itn_block_plan_export(int dtype, int d, int z, const int32_t* chi
                           (long long)g->pass[w].excess, (long long)P.nmodes})
         v.push_back((int32_t)x);
       for (int k = 0; k < P.nmodes; ++k)
-        for (int x : {P.modes[k].chi, P.modes[k].S, P.modes[k].ntile, P.modes[k].tab, P.modes[k].slot}) v.push_back(x);
+        for (int x : {P.modes[k].chi, P.modes[k].S, P.modes[k].ntile, P.modes[k].tab, P.modes[k].slot}) v.push_back(x);  // (exact is derived)
       v.push_back(P.nops);
       for (int o = 0; o < P.nops; ++o)
         for (int x : {(int)P.ops[o].type, (int)P.ops[o].src, (int)P.ops[o].dst, (int)P.ops[o].mode}) v.push_back(x);

@@ -428,22 +428,26 @@ def _pad_to(t, shape, dtype):
     return out
 
 
-def inner_network(phi: ITensorNetwork, psi: ITensorNetwork, operator: ITensorNetwork = None):
+def inner_network(phi: ITensorNetwork, psi: ITensorNetwork, operator: ITensorNetwork = None, ctx=None):
     """inner_network(phi, psi) / inner_network(phi, A, psi) (src/inner.jl:139-171): returns (ket, bra) host networks of
     equal shapes for BeliefPropagationCache(ket, bra=bra).  The operator layer (a list of arrays A_v[s', s, b_1..b_z] with
-    the bond order of the state) is contracted into
-    the ket site by site (fused bonds a_k + chi_k b_k); differing bond dimensions are zero-padded.  This is host-side
-    layout work (one small tensordot per site), the contractions of BP itself all run on the device."""
+    the bond order of the state) and the ket layer of a vertex form one partition of the three-layer network
+    (src/formnetworks/bilinearformnetwork.jl:23-42): A_v is contracted into the ket on the DEVICE (itn_tensordot, the
+    same in-partition `contract` the multi-site partitions use) and the pair of bonds (a_k, b_k) becomes the fused bond
+    a_k + chi_k b_k of the partition; the host only permutes and reshapes axes.  Differing bond dimensions are zero-padded."""
     g = psi.graph
     ops = None if operator is None else [np.asarray(a) for a in getattr(operator, "tensors", operator)]
     dtype = np.result_type(phi.dtype, psi.dtype, *([a.dtype for a in ops] if ops else []))
+    if ops is not None:
+        from .partitions import tensordot as device_tensordot
+        ctx = ctx or default_context()
     kets = []
     for v in range(g.nv):
         t = psi.tensors[v]
         if ops is not None:
             a = ops[v]
             z = t.ndim - 1
-            r = np.tensordot(a, t, axes=([1], [0]))  # [s', b_1..b_z, a_1..a_z]
+            r = device_tensordot(a, t, [1], [0], ctx)  # [s', b_1..b_z, a_1..a_z], contracted by the engine
             r = np.transpose(r, [0] + [i for k in range(z) for i in (1 + k, 1 + z + k)])  # [s', b_1, a_1, b_2, a_2, ..]
             t = r.reshape([r.shape[0]] + [r.shape[1 + 2 * k] * r.shape[2 + 2 * k] for k in range(z)])  # C order: a fastest
         kets.append(t)
@@ -463,7 +467,7 @@ def loginner(phi, psi, operator=None, alg="bp", cache=None, update_cache=None, c
     creates them; on loopy graphs pass `messages="identity"` or a dict, and `maxiter` in cache_update_kwargs."""
     assert alg == "bp", "only alg=\"bp\" runs on the engine"
     if cache is None:
-        ket, bra = inner_network(phi, psi, operator)
+        ket, bra = inner_network(phi, psi, operator, ctx=ctx)
         cache = BeliefPropagationCache(ket, ctx=ctx, bra=bra, messages=None if messages == "default_bilinear" else messages)
         update_cache = True if update_cache is None else update_cache
     elif update_cache is None:

@@ -210,8 +210,9 @@ def test_gate_exchange_two_ranks_gloo():
 
 
 def test_inner_network_host_layout_matches_oracle():
-    """inner_network (host mirror): zero-padding of unequal bond dimensions and the operator layer fused into the ket
-    (src/inner.jl:139-171) agree with the oracle's restatement; no device call is involved."""
+    """inner_network (host mirror): zero-padding of unequal bond dimensions (src/inner.jl:139-171) agrees with the oracle's
+    restatement; no device call is involved.  The operator layer of <phi|A|psi> is contracted on the device
+    (tests/test_gpu_inner.py::test_operator_layer_is_contracted_on_the_device)."""
     import numpy as np
 
     import itn_b200 as E
@@ -222,11 +223,12 @@ def test_inner_network_host_layout_matches_oracle():
     rng = np.random.default_rng(0)
     ops = [rng.standard_normal((2, 2) + (2,) * len(g.inc[v])) + 0j for v in range(g.nv)]
     eg = E.NamedGraph(g.nv, g.edges)
-    ket, bra = E.inner_network(E.ITensorNetwork(eg, phi.tensors), E.ITensorNetwork(eg, psi.tensors), ops)
-    ref = O.bilinear_network(phi, O.apply_operator_network(O.Network(g, ops, np.complex128), psi))
+    ket, bra = E.inner_network(E.ITensorNetwork(eg, phi.tensors), E.ITensorNetwork(eg, psi.tensors))
+    ref2 = O.bilinear_network(phi, psi)
     for v in range(g.nv):
-        assert ket.tensors[v].shape == bra.tensors[v].shape == ref.tensors[v].shape
-        assert np.array_equal(ket.tensors[v], ref.tensors[v]) and np.array_equal(bra.tensors[v], ref.bra[v])
+        assert ket.tensors[v].shape == bra.tensors[v].shape == ref2.tensors[v].shape
+        assert np.array_equal(ket.tensors[v], ref2.tensors[v]) and np.array_equal(bra.tensors[v], ref2.bra[v])
+    ref = O.bilinear_network(phi, O.apply_operator_network(O.Network(g, ops, np.complex128), psi))
     # BP on the tree (oracle) reproduces the brute-force <phi|A|psi>
     msgs, _, _ = O.bp_update(ref, {}, seq=O.default_edge_sequence(g), maxiter=1)
     exact = O.exact_inner_operator(phi, O.Network(g, ops, np.complex128), psi)

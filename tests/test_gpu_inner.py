@@ -66,6 +66,24 @@ def test_three_layer_inner_on_tree_equals_exact(ctx, dtype):
     assert abs(got - exact) < TOL * abs(exact)
 
 
+def test_operator_layer_is_contracted_on_the_device(ctx):
+    # <phi|A|psi> (src/inner.jl:154-171, bilinearformnetwork.jl:23-42): the operator and ket tensors of a vertex are one
+    # partition; the engine contracts them (itn_tensordot) and the result equals the oracle's fused-bond restatement
+    g = O.random_tree_graph(7, seed=3)
+    phi = O.random_network(g, [2, 3, 2, 1, 2, 3], dtype=np.complex128, seed=1)
+    psi = O.random_network(g, [3, 2, 3, 2, 2, 1], dtype=np.complex128, seed=2)
+    rng = np.random.default_rng(0)
+    ops = [rng.standard_normal((2, 2) + (2,) * len(g.inc[v])) + 0j for v in range(g.nv)]
+    l0 = ctx.launch_count()
+    ket, bra = E.inner_network(host_net(phi), host_net(psi), ops, ctx=ctx)
+    assert ctx.launch_count() - l0 >= g.nv  # one device contraction per vertex
+    ref = O.bilinear_network(phi, O.apply_operator_network(O.Network(g, ops, np.complex128), psi))
+    for v in range(g.nv):
+        assert ket.tensors[v].shape == bra.tensors[v].shape == ref.tensors[v].shape
+        assert np.linalg.norm(ket.tensors[v] - ref.tensors[v]) < 1e-13 * np.linalg.norm(ref.tensors[v])
+        assert np.array_equal(bra.tensors[v], ref.bra[v])
+
+
 CASES = [("grid3x3_chi3", (3, 3), 3), ("grid4x4_chi2", (4, 4), 2), ("cubic3_chi2", (3, 3, 3), 2)]
 
 

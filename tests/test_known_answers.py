@@ -1,0 +1,216 @@
+"""Analytic known-answer tests: states whose BP quantities have closed forms.  They pin the ORACLE (CPU, `not gpu`) and the
+ENGINE (`gpu`) to numbers that come from neither -- the part of "parity unpinned" that can be pinned without a Julia runtime
+(the reference holds no golden vectors):
+
+  product states     bond dimension 1 (and zero-padded to chi > 1: rank-one messages) on loopy graphs: BP is exact,
+                     <Z_v> = cos(2 theta_v), <Z_u Z_v> = product, log Z = sum_v log |psi_v|^2
+  weighted GHZ       a |0..0> + b |1..1> on a tree as delta tensors (chi = 2): <Z_v> = (|a|^2 - |b|^2) / (|a|^2 + |b|^2),
+                     <Z_u Z_v> = 1, Z = |a|^2 + |b|^2, two-site RDM = diag(|a|^2, 0, 0, |b|^2) / Z
+  Schmidt spectra    exp(-i theta Z(x)Z) on |+>|+> = cos(theta) |++> - i sin(theta) |-->: singular values (cos, sin), so
+                     maxdim / cutoff truncation has closed-form kept dimension and truncation error (src/apply.jl:81-88,
+                     relative cutoff on squared singular values); CNOT (H (x) 1) |00>: (1, 1) / sqrt 2
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import itn_oracle as O
+
+Z = np.array([[1.0, 0.0], [0.0, -1.0]])
+TOL = 1e-12
+
+
+def product_network(g, thetas, phis, chi, dtype, scales):
+    ts = []
+    for v in range(g.nv):
+        vec = scales[v] * np.array([math.cos(thetas[v]), np.exp(1j * phis[v]) * math.sin(thetas[v])])
+        if np.dtype(dtype).kind != "c":
+            vec = vec.real
+        t = np.zeros((2,) + (chi,) * g.degree(v), dtype=dtype)
+        t[(slice(None),) + (0,) * g.degree(v)] = vec
+        ts.append(t)
+    return O.Network(g, ts, dtype)
+
+
+def ghz_network(g, a, b, dtype=np.complex128):
+    ts = []
+    for v in range(g.nv):
+        t = np.zeros((2,) + (2,) * g.degree(v), dtype=dtype)
+        t[(0,) * (1 + g.degree(v))] = a if v == 0 else 1.0
+        t[(1,) * (1 + g.degree(v))] = b if v == 0 else 1.0
+        ts.append(t)
+    return O.Network(g, ts, dtype)
+
+
+def zz_gate(theta):
+    zz = np.kron(Z, Z)
+    u = np.diag(np.exp(-1j * theta * np.diag(zz)))
+    return u.reshape(2, 2, 2, 2)
+
+
+def plus_chain(n, chi=1):
+    g = O.chain_graph(n)
+    ts = []
+    for v in range(n):
+        t = np.zeros((2,) + (chi,) * g.degree(v), dtype=np.complex128)
+        t[(slice(None),) + (0,) * g.degree(v)] = 1 / math.sqrt(2)
+        ts.append(t)
+    return g, O.Network(g, ts, np.complex128)
+
+
+# ---- the same checks for the oracle and the engine -------------------------------------------------------------------
+
+
+class OracleSide:
+    name = "oracle"
+
+    def bp(self, net, maxiter):
+        g = net.graph
+        if g.is_tree():
+            msgs, _, _ = O.bp_update(net, {}, seq=O.default_edge_sequence(g), maxiter=1)
+        else:
+            seq = O.parallel_edge_sequence(g)
+            msgs, _, _ = O.bp_update(net, O.identity_messages(net), seq=seq, groups=O.synchronous_groups(seq), maxiter=maxiter)
+        self.net, self.msgs = net, msgs
+
+    def expect_z(self, v):
+        return O.expect1(self.net, self.msgs, v, Z)
+
+    def expect_zz(self, e):
+        return O.expect2(self.net, self.msgs, e, Z, Z)
+
+    def rdm2(self, e):
+        return O.rdm2(self.net, self.msgs, e)
+
+    def logz(self):
+        return O.logscalar(self.net, self.msgs)
+
+    def gate(self, e, gate, maxdim=None, cutoff=None):
+        _, info = O.simple_update_bp(self.net, self.msgs, e, gate, maxdim=maxdim, cutoff=cutoff)
+        return info["newdim"], info["truncerr"], np.asarray(info["svals"][:info["newdim"]])
+
+
+class EngineSide:
+    name = "engine"
+
+    def __init__(self):
+        import itn_b200 as E
+        self.E = E
+        self.ctx = E.Context(0)
+
+    def bp(self, net, maxiter):
+        E = self.E
+        g = net.graph
+        eg = E.NamedGraph(g.nv, g.edges)
+        psi = E.ITensorNetwork(eg, [t.copy() for t in net.tensors], net.dtype)
+        if g.is_tree():
+            self.bpc = E.update(E.BeliefPropagationCache(psi, ctx=self.ctx, messages="default"))
+        else:
+            self.bpc = E.update(E.BeliefPropagationCache(psi, ctx=self.ctx), maxiter=maxiter, edge_sequence=E.parallel_edge_sequence(eg))
+        self.g = g
+
+    def expect_z(self, v):
+        return self.E.expect(self.bpc, "Z", vertices=[v])[v]
+
+    def expect_zz(self, e):
+        return self.E.expect2(self.bpc, [e], "Z", "Z")[0]
+
+    def rdm2(self, e):
+        return self.E.rdm2(self.bpc, [e])[0]
+
+    def logz(self):
+        return self.E.logscalar(self.bpc)
+
+    def gate(self, e, gate, maxdim=None, cutoff=None):
+        got = {}
+        self.E.apply(gate, self.bpc, self.g.edges[e], maxdim=maxdim, cutoff=cutoff, callback=lambda **kw: got.update(kw))
+        sv = np.asarray(got["singular_values"])
+        return len(sv), got["truncation_error"], sv
+
+
+SIDES = [pytest.param(OracleSide, id="oracle"), pytest.param(EngineSide, id="engine", marks=pytest.mark.gpu)]
+
+
+@pytest.mark.parametrize("side", SIDES)
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128], ids=["f64", "c128"])
+@pytest.mark.parametrize("chi", [1, 3])
+def test_product_state_on_a_loopy_grid(side, dtype, chi):
+    s = side()
+    g = O.grid_graph((3, 4))
+    rng = np.random.default_rng(3)
+    th, ph, sc = rng.uniform(0, math.pi, g.nv), rng.uniform(0, 2 * math.pi, g.nv), rng.uniform(0.5, 2.0, g.nv)
+    if np.dtype(dtype).kind != "c":
+        ph = np.zeros(g.nv)  # real amplitudes
+    s.bp(product_network(g, th, ph, chi, dtype, sc), maxiter=3)
+    for v in range(g.nv):
+        assert abs(s.expect_z(v) - math.cos(2 * th[v])) < TOL
+    for e in (0, 5, len(g.edges) - 1):
+        u, v = g.edges[e]
+        assert abs(s.expect_zz(e) - math.cos(2 * th[u]) * math.cos(2 * th[v])) < TOL
+    assert abs(s.logz() - float(np.sum(np.log(sc ** 2)))) < 1e-11
+
+
+@pytest.mark.parametrize("side", SIDES)
+def test_weighted_ghz_on_a_tree(side):
+    s = side()
+    g = O.random_tree_graph(8, seed=4)
+    a, b = 0.8 * np.exp(0.3j), 0.35 * np.exp(-1.1j)
+    s.bp(ghz_network(g, a, b), maxiter=1)
+    zn = abs(a) ** 2 + abs(b) ** 2
+    want = (abs(a) ** 2 - abs(b) ** 2) / zn
+    for v in range(g.nv):
+        assert abs(s.expect_z(v) - want) < TOL
+    for e in range(len(g.edges)):
+        assert abs(s.expect_zz(e) - 1.0) < TOL
+    assert abs(np.exp(s.logz()) - zn) < TOL * zn
+    rho = s.rdm2(2)
+    assert np.allclose(rho, np.diag([abs(a) ** 2, 0, 0, abs(b) ** 2]) / zn, atol=TOL)
+
+
+@pytest.mark.parametrize("side", SIDES)
+@pytest.mark.parametrize("chi", [1, 2])
+def test_schmidt_spectrum_of_a_zz_rotation(side, chi):
+    theta = 0.1
+    c2, s2 = math.cos(theta) ** 2, math.sin(theta) ** 2
+    for n, e in ((2, 0), (4, 1)):
+        # no truncation: singular values (cos, sin)
+        s = side()
+        g, net = plus_chain(n, chi)
+        s.bp(net, 1)
+        dim, terr, sv = s.gate(e, zz_gate(theta))
+        assert dim == 2 * chi or dim == 2  # the reference keeps every singular value without a cutoff (zeros included)
+        assert np.allclose(sorted(sv, reverse=True)[:2], [math.cos(theta), math.sin(theta)], atol=TOL) and abs(terr) < TOL
+        # maxdim = 1: the discarded weight is sin^2 / (cos^2 + sin^2)
+        s = side()
+        s.bp(plus_chain(n, chi)[1], 1)
+        dim, terr, sv = s.gate(e, zz_gate(theta), maxdim=1)
+        assert dim == 1 and abs(terr - s2) < TOL and abs(sv[0] - math.sqrt(c2)) < TOL
+        # relative cutoff above sin^2: truncates; below: keeps both
+        s = side()
+        s.bp(plus_chain(n, chi)[1], 1)
+        dim, terr, sv = s.gate(e, zz_gate(theta), cutoff=2 * s2)
+        assert dim == 1 and abs(terr - s2) < TOL
+        s = side()
+        s.bp(plus_chain(n, chi)[1], 1)
+        dim, terr, sv = s.gate(e, zz_gate(theta), cutoff=0.5 * s2)
+        assert dim == 2 and abs(terr) < TOL and np.allclose(sv, [math.cos(theta), math.sin(theta)], atol=TOL)
+
+
+@pytest.mark.parametrize("side", SIDES)
+def test_bell_pair_from_cnot_hadamard(side):
+    h = np.array([[1, 1], [1, -1]]) / math.sqrt(2)
+    cnot = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=float)  # control = first site
+    u = cnot @ np.kron(h, np.eye(2))                      # row index (s1, s2) with s1 slow
+    gate = u.reshape(2, 2, 2, 2).astype(np.complex128)    # g[s1', s2', s1, s2]
+    g = O.chain_graph(2)
+    ts = [np.zeros((2, 1), dtype=np.complex128) for _ in range(2)]
+    ts[0][0, 0] = ts[1][0, 0] = 1.0
+    s = side()
+    s.bp(O.Network(g, ts, np.complex128), 1)
+    dim, terr, sv = s.gate(0, gate)
+    assert dim == 2 and np.allclose(sv, [1 / math.sqrt(2)] * 2, atol=TOL) and abs(terr) < TOL
+    s = side()
+    s.bp(O.Network(g, ts, np.complex128), 1)
+    dim, terr, sv = s.gate(0, gate, maxdim=1)
+    assert dim == 1 and abs(terr - 0.5) < TOL
