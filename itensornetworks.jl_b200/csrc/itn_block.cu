@@ -98,18 +98,34 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
+// m16n8k4: rows 0-7 of A (a0) feed c[0], c[1], rows 8-15 (a1) feed c[2], c[3]; columns 2t, 2t + 1 as in m8n8k4.  Complex
+// products put the real-part rows in the lower half and the imaginary-part rows in the upper half: one instruction does
+// the work of two m8n8k4 (all FP64 MMA shapes run at the same 37 TFLOP/s on B200, tools/fp64_peak.cu).
+__device__ __forceinline__ void dmma1684(double (&c)[4], double a0, double a1, double b) {
+  asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+               : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+               : "d"(a0), "d"(a1), "d"(b));
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// Per-operation constants, computed once per CTA (one thread per operation) instead of once per warp and operation.
+struct OpConst {
+  int type, src, dst;  // buffer offsets in doubles
+  int frag;            // offset of the fragment-ordered message copy in shared memory, -1: gather from global memory
+  int tab, ntile, S, chi, exact, slot, mode;
+};
+
 // ---- dst = src x_mode M  (message = A operand in registers, tensor = B operand, 8 fibres per tile) ----------------------
 // Complex products run as real ones on the stacked reduction index.  Two stackings:
-//   packed  (KS <= 4, chi <= 8): [re 0..chi-1 | im 0..chi-1] back to back, ceil(2 chi / 4) steps: chi = 6 needs 3 steps, not 4;
-//           fragments A_re = [M_re ; -M_im], A_im = [M_im ; M_re] (2 KS registers of doubles)
-//   aligned (KS >= 8): each plane padded to KS / 2 steps of its own; the sign moves to the tensor operand
-//           (out_re = M_re^T X_re + M_im^T (-X_im), out_im = M_im^T X_re + M_re^T X_im), so only M_re and M_im are kept:
-//           KS doubles of fragments instead of 2 KS (chi = 32: 64 registers instead of 128)
+//   packed  (KS <= 4, chi <= 8): [re 0..chi-1 | im 0..chi-1] back to back, ceil(2 chi / 4) steps: chi = 6 needs 3 steps, not 4.
+//           Fragments A_re = [M_re ; -M_im] (rows of the real part of the output) and A_im = [M_im ; M_re]: one m16n8k4 per
+//           step with A = (A_re, A_im).
+//   aligned (KS >= 8): each plane padded to KS / 2 steps of its own.  Only M_re and M_im are kept (chi = 32: 64 registers):
+//           c1 += (M_re, M_im) x X_re and c2 += (M_im, M_re) x X_im are two independent chains, and
+//           out_re = c1.lo - c2.lo, out_im = c1.hi + c2.hi.
 // One message-fragment value: what lane (g, t) of the warp owning row tile mt holds for reduction step ks
-// (which = 0: first array, 1: second array; see the stackings above).
+// (which = 0: first array, 1: second array).
 template <bool C, int KS>
 __device__ __forceinline__ double mp_fragment(const double* __restrict__ msg, int chi, int mt, int ks, int which, int lane) {
   constexpr bool AL = C && KS >= 8;
@@ -123,112 +139,154 @@ __device__ __forceinline__ double mp_fragment(const double* __restrict__ msg, in
   if (kk < chi) return which ? msg[chi2 + kk + chi * b] : msg[kk + chi * b];
   return which ? msg[(kk - chi) + chi * b] : -msg[chi2 + (kk - chi) + chi * b];
 }
+// shared-memory offset of the reduction entry lane t reads in step ks, -1: beyond the end
+template <bool C, int KS>
+__device__ __forceinline__ int mp_koff(int chi, int S, int PL, int ks, int t) {
+  constexpr bool AL = C && KS >= 8;
+  const int K2 = (C && !AL) ? 2 * chi : chi;
+  const int kk = 4 * ks + t;
+  if (kk >= K2) return -1;
+  return (!C || AL || kk < chi) ? kk * S : PL + (kk - chi) * S;
+}
 
 template <bool C, int KS, bool EXACT>
-__device__ __forceinline__ void mp_tiles(const BlkMode M, const int PL, const double (&A0)[(C && KS >= 8) ? KS / 2 : KS],
-                                         const double (&A1)[C ? ((KS >= 8) ? KS / 2 : KS) : 1], const double* src, double* dst,
-                                         const unsigned short* __restrict__ tb, const int fsub, const int fstep, const int b,
-                                         const int lane) {
+__device__ __forceinline__ void mp_tiles(const OpConst& O, const int PL, const double (&A0)[(C && KS >= 8) ? KS / 2 : KS],
+                                         const double (&A1)[C ? ((KS >= 8) ? KS / 2 : KS) : 1], const int (&koff)[(C && KS >= 8) ? KS / 2 : KS],
+                                         const double* src, double* dst, const unsigned short* __restrict__ tb, const int fsub,
+                                         const int fstep, const int b, const int lane) {
   constexpr bool AL = C && KS >= 8;
   constexpr int KH = AL ? KS / 2 : KS;
-  const int chi = M.chi, S = M.S;
+  const int chi = O.chi, S = O.S;
   const int g = lane >> 2, t = lane & 3;
   const int K2 = (C && !AL) ? 2 * chi : chi;
   const int ksj = (K2 + 3) >> 2;
-  int koff[KH];  // shared-memory offset of this lane's reduction entry in step ks, -1: beyond the end (fragment is zero)
-#pragma unroll
-  for (int ks = 0; ks < KH; ++ks) {
-    const int kk = 4 * ks + t;
-    koff[ks] = (ks < ksj && kk < K2) ? ((!C || AL || kk < chi) ? kk * S : PL + (kk - chi) * S) : -1;
-  }
   const int bS = b * S;
   const bool bok = b < chi;
-  auto load_frags = [&](unsigned fb, double (&x0)[KH], double (&x1)[C ? KH : 1]) {
-#pragma unroll
-    for (int ks = 0; ks < KH; ++ks) {
-      if (EXACT) {
-        if (ks < ksj) {
-          x0[ks] = src[fb + koff[ks]];
-          if (AL) x1[ks] = src[PL + fb + koff[ks]];
-        }
-      } else {
-        const bool ok = koff[ks] >= 0 && fb != kNoFibre;
-        x0[ks] = ok ? src[fb + koff[ks]] : 0.0;
-        if (AL) x1[ks] = ok ? src[PL + fb + koff[ks]] : 0.0;
-      }
-    }
+  auto load1 = [&](unsigned fb, int ks, int plane_off) -> double {
+    if (EXACT) return src[plane_off + fb + koff[ks]];
+    return (koff[ks] >= 0 && fb != kNoFibre) ? src[plane_off + fb + koff[ks]] : 0.0;
   };
-  auto products = [&](const double (&x0)[KH], const double (&x1)[C ? KH : 1], double (&cre)[2], double (&cim)[2]) {
-#pragma unroll
-    for (int ks = 0; ks < KH; ++ks) {
-      if (ks < ksj) {
-        if (AL) {
-          dmma884(cre, A0[ks], x0[ks]);
-          dmma884(cim, A1[ks], x0[ks]);
-          dmma884(cim, A0[ks], x1[ks]);
-          dmma884(cre, A1[ks], -x1[ks]);
-        } else {
-          dmma884(cre, A0[ks], x0[ks]);
-          if (C) dmma884(cim, A1[ks], x0[ks]);
-        }
-      }
-    }
-  };
-  auto store_tile = [&](unsigned fb, const double (&cre)[2], const double (&cim)[2]) {
+  // results of one tile: lane holds (row b; fibres 2t, 2t + 1)
+  auto store_tile = [&](unsigned fb, double r0, double r1, double i0, double i1) {
     const unsigned f0 = __shfl_sync(0xffffffffu, fb, 8 * t), f1 = __shfl_sync(0xffffffffu, fb, 8 * t + 4);
     if (src == dst) __syncwarp();  // in place (one row tile per fibre): every lane has read its fibres
     if (bok) {
       if (EXACT || f0 != kNoFibre) {
-        dst[f0 + bS] = cre[0];
-        if (C) dst[PL + f0 + bS] = cim[0];
+        dst[f0 + bS] = r0;
+        if (C) dst[PL + f0 + bS] = i0;
       }
       if (EXACT || f1 != kNoFibre) {
-        dst[f1 + bS] = cre[1];
-        if (C) dst[PL + f1 + bS] = cim[1];
+        dst[f1 + bS] = r1;
+        if (C) dst[PL + f1 + bS] = i1;
       }
     }
   };
-  int ft = fsub;
-  // two independent tiles per iteration: twice the accumulator chains in flight behind the fixed DMMA latency
-  // (not for chi = 32: its fragments alone take 96 registers, and a tile already has 32 products)
-  constexpr bool TWO = KS < 16;
-  for (; TWO && ft + fstep < M.ntile; ft += 2 * fstep) {
-    const unsigned fbA = tb[ft * 8 + g], fbB = tb[(ft + fstep) * 8 + g];
-    double xa0[KH], xa1[C ? KH : 1], xb0[KH], xb1[C ? KH : 1];
-    load_frags(fbA, xa0, xa1);
-    load_frags(fbB, xb0, xb1);
-    double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0}, br[2] = {0.0, 0.0}, bi[2] = {0.0, 0.0};
-    products(xa0, xa1, ar, ai);
-    products(xb0, xb1, br, bi);
-    store_tile(fbA, ar, ai);
-    store_tile(fbB, br, bi);
-  }
-  for (; ft < M.ntile; ft += fstep) {
-    const unsigned fbA = tb[ft * 8 + g];
-    double xa0[KH], xa1[C ? KH : 1];
-    load_frags(fbA, xa0, xa1);
-    double ar[2] = {0.0, 0.0}, ai[2] = {0.0, 0.0};
-    products(xa0, xa1, ar, ai);
-    store_tile(fbA, ar, ai);
+  if constexpr (AL) {
+    for (int ft = fsub; ft < O.ntile; ft += fstep) {
+      const unsigned fb = tb[ft * 8 + g];
+      double xr[KH], xi[KH];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) {
+          xr[ks] = load1(fb, ks, 0);
+          xi[ks] = load1(fb, ks, PL);
+        }
+      double c1[4] = {0.0, 0.0, 0.0, 0.0}, c2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) {
+          dmma1684(c1, A0[ks], A1[ks], xr[ks]);
+          dmma1684(c2, A1[ks], A0[ks], xi[ks]);
+        }
+      store_tile(fb, c1[0] - c2[0], c1[1] - c2[1], c1[2] + c2[2], c1[3] + c2[3]);
+    }
+  } else if constexpr (C) {
+    int ft = fsub;
+    // two independent tiles per iteration: two accumulator chains in flight behind the fixed DMMA latency
+    for (; ft + fstep < O.ntile; ft += 2 * fstep) {
+      const unsigned fbA = tb[ft * 8 + g], fbB = tb[(ft + fstep) * 8 + g];
+      double xa[KH], xb[KH];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) {
+          xa[ks] = load1(fbA, ks, 0);
+          xb[ks] = load1(fbB, ks, 0);
+        }
+      double ca[4] = {0.0, 0.0, 0.0, 0.0}, cb[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) {
+          dmma1684(ca, A0[ks], A1[ks], xa[ks]);
+          dmma1684(cb, A0[ks], A1[ks], xb[ks]);
+        }
+      store_tile(fbA, ca[0], ca[1], ca[2], ca[3]);
+      store_tile(fbB, cb[0], cb[1], cb[2], cb[3]);
+    }
+    for (; ft < O.ntile; ft += fstep) {
+      const unsigned fbA = tb[ft * 8 + g];
+      double xa[KH];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) xa[ks] = load1(fbA, ks, 0);
+      double ca[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) dmma1684(ca, A0[ks], A1[ks], xa[ks]);
+      store_tile(fbA, ca[0], ca[1], ca[2], ca[3]);
+    }
+  } else {
+    int ft = fsub;
+    for (; ft + fstep < O.ntile; ft += 2 * fstep) {
+      const unsigned fbA = tb[ft * 8 + g], fbB = tb[(ft + fstep) * 8 + g];
+      double xa[KH], xb[KH];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) {
+          xa[ks] = load1(fbA, ks, 0);
+          xb[ks] = load1(fbB, ks, 0);
+        }
+      double ca[2] = {0.0, 0.0}, cb[2] = {0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) {
+          dmma884(ca, A0[ks], xa[ks]);
+          dmma884(cb, A0[ks], xb[ks]);
+        }
+      store_tile(fbA, ca[0], ca[1], 0.0, 0.0);
+      store_tile(fbB, cb[0], cb[1], 0.0, 0.0);
+    }
+    for (; ft < O.ntile; ft += fstep) {
+      const unsigned fbA = tb[ft * 8 + g];
+      double xa[KH];
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) xa[ks] = load1(fbA, ks, 0);
+      double ca[2] = {0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks)
+        if (ks < ksj) dmma884(ca, A0[ks], xa[ks]);
+      store_tile(fbA, ca[0], ca[1], 0.0, 0.0);
+    }
   }
 }
 
-// frag != nullptr: the fragment-ordered copy of the message staged in shared memory by the prologue
-// ([row tile][step][array][lane]); otherwise the fragments are gathered from the message in global memory.
+// msm: the fragment-ordered message copies staged by the prologue ([row tile][step][array][lane]); skoff: the reduction
+// offsets per (mode, step, lane & 3).  Without a staged copy the fragments are gathered from the message in global memory.
 template <bool C, int KS>
-__device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const double* __restrict__ msg,
-                                      const double* __restrict__ frag, const double* src, double* dst,
-                                      const unsigned short* __restrict__ tab, const int warp, const int lane) {
+__device__ __forceinline__ void op_mp(const OpConst& O, const int PL, const double* __restrict__ msg,
+                                      const double* __restrict__ msm, const int* __restrict__ skoff, const double* bufs_c,
+                                      double* bufs, const unsigned short* __restrict__ tab, const int warp, const int lane) {
   constexpr bool AL = C && KS >= 8;
   constexpr int KH = AL ? KS / 2 : KS;  // fragments per array
-  const int chi = M.chi;
+  const int chi = O.chi;
   const int mtj = (chi + 7) >> 3;
   const int mtd = mtj == 3 ? 4 : mtj;  // warps are dealt out over 1, 2 or 4 row tiles
   const int mt = warp % mtd, fsub = warp / mtd, fstep = kNW / mtd;
   if (mt >= mtj) return;
   double A0[KH], A1[C ? KH : 1];
-  if (frag) {
-    const double* fr = frag + (size_t)mt * KH * 64 + lane;
+  int koff[KH];
+  if (O.frag >= 0) {
+    const double* fr = msm + O.frag + (size_t)mt * KH * 64 + lane;
 #pragma unroll
     for (int ks = 0; ks < KH; ++ks) {
       A0[ks] = fr[ks * 64];
@@ -241,18 +299,23 @@ __device__ __forceinline__ void op_mp(const BlkMode M, const int PL, const doubl
       if (C) A1[ks] = mp_fragment<C, KS>(msg, chi, mt, ks, 1, lane);
     }
   }
+  const int* ko = skoff + O.mode * 64 + (lane & 3);
+#pragma unroll
+  for (int ks = 0; ks < KH; ++ks) koff[ks] = ko[ks * 4];
   const int b = mt * 8 + (lane >> 2);
-  if (M.exact) mp_tiles<C, KS, true>(M, PL, A0, A1, src, dst, tab + M.tab, fsub, fstep, b, lane);
-  else mp_tiles<C, KS, false>(M, PL, A0, A1, src, dst, tab + M.tab, fsub, fstep, b, lane);
+  if (O.exact) mp_tiles<C, KS, true>(O, PL, A0, A1, koff, bufs_c + O.src, bufs + O.dst, tab + O.tab, fsub, fstep, b, lane);
+  else mp_tiles<C, KS, false>(O, PL, A0, A1, koff, bufs_c + O.src, bufs + O.dst, tab + O.tab, fsub, fstep, b, lane);
 }
 
 // ---- out[b + chi b'] = sum over the fibres of the block  W[f, b] conj(X[f, b'])  (4 fibres per k step) -------------------
+// Complex: ca += (W_re, W_im) x X_re, cb += (W_im, W_re) x X_im (two independent m16n8k4 chains per tile pair);
+// out_re = ca.lo + cb.lo, out_im = ca.hi - cb.hi.
 template <bool C, int MT>
-__device__ __forceinline__ void op_close(const BlkMode M, const int PL, const double* W, const double* X, double* red,
+__device__ __forceinline__ void op_close(const OpConst& O, const int PL, const double* W, const double* X, double* red,
                                          double* __restrict__ out, const unsigned short* __restrict__ tab, const int warp,
                                          const int lane, const int tid) {
   constexpr int NPW = MT == 4 ? 2 : 1;
-  const int chi = M.chi, S = M.S;
+  const int chi = O.chi, S = O.S;
   const int mtj = (chi + 7) >> 3;
   const int mtd = mtj == 3 ? 4 : mtj;
   const int g = lane >> 2, t = lane & 3;
@@ -266,52 +329,75 @@ __device__ __forceinline__ void op_close(const BlkMode M, const int PL, const do
   }
   const int npw = mtd == 4 ? 2 : 1;
   const int CH = mtd * 8;
-  double acc[NPW][2][2], acc2[NPW][2][2];  // two k steps in flight: independent accumulator chains, summed at the end
-#pragma unroll
-  for (int q = 0; q < NPW; ++q) {
-    acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0;
-    acc2[q][0][0] = acc2[q][0][1] = acc2[q][1][0] = acc2[q][1][1] = 0.0;
-  }
-  const unsigned short* tb = tab + M.tab;
-  const int nks = M.ntile * 2;
+  double acc[NPW][2][2];  // [pair][re / im][column 2t, 2t + 1]
+  const unsigned short* tb = tab + O.tab;
+  const int nks = O.ntile * 2;
   const int bm = mt * 8 + g;
   const int bmS = bm * S;
   const bool mok = bm < chi;
-  auto step = [&](int ks, double (&a)[NPW][2][2]) {
-    const unsigned fb = tb[ks * 4 + t];
-    const bool ok = fb != kNoFibre;
-    const bool okm = ok && mok;
-    const double wre = okm ? W[fb + bmS] : 0.0;
-    const double wim = (C && okm) ? W[PL + fb + bmS] : 0.0;
+  if constexpr (C) {
+    double ca[NPW][4], cb[NPW][4];
 #pragma unroll
-    for (int q = 0; q < NPW; ++q) {
-      if (q < npw) {
-        const int bn = (nt0 + q) * 8 + g;
-        const bool okn = ok && bn < chi;
-        const double xre = okn ? X[fb + bn * S] : 0.0;
-        dmma884(a[q][0], wre, xre);
-        if (C) {
+    for (int q = 0; q < NPW; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ca[q][j] = cb[q][j] = 0.0;
+    for (int ks = fs; ks < nks; ks += FS) {
+      const unsigned fb = tb[ks * 4 + t];
+      const bool ok = O.exact || fb != kNoFibre;
+      const bool okm = ok && mok;
+      const double wre = okm ? W[fb + bmS] : 0.0;
+      const double wim = okm ? W[PL + fb + bmS] : 0.0;
+#pragma unroll
+      for (int q = 0; q < NPW; ++q) {
+        if (q < npw) {
+          const int bn = (nt0 + q) * 8 + g;
+          const bool okn = ok && bn < chi;
+          const double xre = okn ? X[fb + bn * S] : 0.0;
           const double xim = okn ? X[PL + fb + bn * S] : 0.0;
-          dmma884(a[q][0], wim, xim);
-          dmma884(a[q][1], wim, xre);
-          dmma884(a[q][1], -wre, xim);
+          dmma1684(ca[q], wre, wim, xre);
+          dmma1684(cb[q], wim, wre, xim);
         }
       }
     }
-  };
-  int ks = fs;
-  for (; ks + FS < nks; ks += 2 * FS) {
-    step(ks, acc);
-    step(ks + FS, acc2);
-  }
-  if (ks < nks) step(ks, acc);
 #pragma unroll
-  for (int q = 0; q < NPW; ++q)
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      acc[q][p][0] += acc2[q][p][0];
-      acc[q][p][1] += acc2[q][p][1];
+    for (int q = 0; q < NPW; ++q) {
+      acc[q][0][0] = ca[q][0] + cb[q][0];
+      acc[q][0][1] = ca[q][1] + cb[q][1];
+      acc[q][1][0] = ca[q][2] - cb[q][2];
+      acc[q][1][1] = ca[q][3] - cb[q][3];
     }
+  } else {
+    double acc2[NPW][2];
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = acc2[q][0] = acc2[q][1] = 0.0;
+    auto step = [&](int ks, double (&a)[2], int q) {
+      const unsigned fb = tb[ks * 4 + t];
+      const bool ok = O.exact || fb != kNoFibre;
+      const double w = (ok && mok) ? W[fb + bmS] : 0.0;
+      const int bn = (nt0 + q) * 8 + g;
+      const double x = (ok && bn < chi) ? X[fb + bn * S] : 0.0;
+      dmma884(a, w, x);
+    };
+    int ks = fs;
+    for (; ks + FS < nks; ks += 2 * FS) {
+#pragma unroll
+      for (int q = 0; q < NPW; ++q)
+        if (q < npw) {
+          step(ks, acc[q][0], q);
+          step(ks + FS, acc2[q], q);
+        }
+    }
+    if (ks < nks) {
+#pragma unroll
+      for (int q = 0; q < NPW; ++q)
+        if (q < npw) step(ks, acc[q][0], q);
+    }
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+      acc[q][0][0] += acc2[q][0];
+      acc[q][0][1] += acc2[q][1];
+    }
+  }
   if (mtd == 4) {
     // one warp owns a pair of 8 x 8 tiles over ALL fibres of the block: no cross-warp sum, straight to the partial buffer
     const int n2 = chi * chi;
@@ -360,6 +446,8 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
                                                   const unsigned short* __restrict__ gtab) {
   extern __shared__ __align__(128) double sm[];
   __shared__ __align__(8) unsigned long long mbar;
+  __shared__ OpConst sOp[kMaxOps];
+  __shared__ int sKoff[kMaxGM * 64];  // [mode][step (16)][lane & 3]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vi = blockIdx.x / P.nblk, blk = blockIdx.x - vi * P.nblk;
   const BlkVertex* __restrict__ V = gv + vi;
@@ -369,37 +457,46 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
   unsigned short* tab = (unsigned short*)(msm + P.msg_len);
   constexpr int PLN = C ? 2 : 1;
   const unsigned mb = smem_u32(&mbar);
-  if (P.bulk && tid == 0) {
+  if (P.bulk == 1 && tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mb));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  // per-operation constants and per-mode reduction offsets
+  if (tid < P.nops) {
+    const BlkOp op = P.ops[tid];
+    const BlkMode M = P.modes[op.mode];
+    OpConst o;
+    o.type = op.type;
+    o.src = op.src * P.bufsz;
+    o.dst = op.dst * P.bufsz;
+    o.frag = P.msg_smem ? P.msg_off[op.mode] : -1;
+    o.tab = M.tab;
+    o.ntile = M.ntile;
+    o.S = M.S;
+    o.chi = M.chi;
+    o.exact = M.exact;
+    o.slot = M.slot;
+    o.mode = op.mode;
+    sOp[tid] = o;
+  }
+  if (tid < kMaxGM * 64) {
+    const int k = tid >> 6, ks = (tid >> 2) & 15, t = tid & 3;
+    sKoff[tid] = (k < P.nmodes && ks < KS) ? mp_koff<C, KS>(P.modes[k].chi, P.modes[k].S, P.PL, ks, t) : -1;
+  }
   __syncthreads();
-  // ---- stage the block(s): buffer 0 = site tensor, buffer 1 = partially absorbed tensor.  The bulk copies are issued
-  // first; the fibre tables and the messages follow with ordinary loads while the copies are in flight. ------------------
-  auto row_pos = [&](int row) {
-    int off = 0, q = row;
-#pragma unroll
-    for (int l = 0; l < 4; ++l)
-      if (l < P.nlev) {
-        const int dg = q % P.lev_n[l];
-        q /= P.lev_n[l];
-        off += dg * P.lev_s[l];
-      }
-    return off;
-  };
+  // ---- stage the block(s): buffer 0 = site tensor, buffer 1 = partially absorbed tensor.  Long rows travel as bulk
+  // copies (cp.async.bulk, completion on the mbarrier; the copy engine takes one row per instruction), short rows as
+  // 16-byte cp.async of all threads in parallel.  Fibre tables and messages follow while the copies are in flight. -----------
   const long long goff = (long long)blk * P.gblk;
   const int nin = P.load_p ? 2 : 1;
-  const int rows_total = nin * PLN * P.nrows;
   const double* gX = V->X;
   const double* gP = P.load_p ? V->Pin : nullptr;
-  if (P.bulk) {
+  if (P.bulk == 1) {
     const unsigned rowbytes = (unsigned)P.rowlen * 8u;
     if (tid == 0) {
-      const unsigned total = rowbytes * (unsigned)rows_total;
+      const unsigned total = rowbytes * (unsigned)(nin * PLN * P.nrows);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(total) : "memory");
     }
-    // row positions come from the table in global memory (no divisions); every thread issues the copies of its rows for
-    // both planes of both tensors
     for (int row = tid; row < P.nrows; row += kBT) {
       const int pos = gtab[P.rowtab + row];
       for (int which = 0; which < nin; ++which)
@@ -411,13 +508,28 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
                        : "memory");
         }
     }
+  } else if (P.bulk == 2) {
+    // 16-byte chunks: chunk c of row r, rows of `half` chunks; lanes walk the chunks of consecutive rows
+    const int half = P.rowlen >> 1;
+    const int tot = P.nrows * half;
+    for (int i = tid; i < tot; i += kBT) {
+      const int row = i / half, c = i - row * half;
+      const int pos = gtab[P.rowtab + row] + 2 * c;
+      for (int which = 0; which < nin; ++which)
+        for (int pl = 0; pl < PLN; ++pl) {
+          const double* g = (which ? gP : gX) + (long long)pl * P.gplane + goff + (long long)row * P.grow + 2 * c;
+          const unsigned dsts = smem_u32(bufs + (size_t)which * P.bufsz + (size_t)pl * P.PL + pos);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dsts), "l"(g) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
   } else {
-    const long long tot = (long long)rows_total * P.rowlen;
+    const long long tot = (long long)nin * PLN * P.nrows * P.rowlen;
     for (long long i = tid; i < tot; i += kBT) {
       const int r = (int)(i / P.rowlen), c = (int)(i - (long long)r * P.rowlen);
       const int which = r / (PLN * P.nrows), rr = r - which * (PLN * P.nrows);
       const int pl = rr / P.nrows, row = rr - pl * P.nrows;
-      bufs[(size_t)which * P.bufsz + (size_t)pl * P.PL + row_pos(row) + c] =
+      bufs[(size_t)which * P.bufsz + (size_t)pl * P.PL + gtab[P.rowtab + row] + c] =
           (which ? gP : gX)[(long long)pl * P.gplane + goff + (long long)row * P.grow + c];
     }
   }
@@ -439,7 +551,7 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
         }
       }
   }
-  if (P.bulk) {
+  if (P.bulk == 1) {
     unsigned done = 0;
     while (!done) {
       asm volatile(
@@ -448,27 +560,25 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
           : "r"(mb), "r"(0u)
           : "memory");
     }
+  } else if (P.bulk == 2) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   }
   __syncthreads();
   // ---- the operation list of the pass --------------------------------------------------------------------------------
   for (int oi = 0; oi < P.nops; ++oi) {
-    const BlkOp op = P.ops[oi];
-    if (op.type == OP_MP) {
-      const BlkMode M = P.modes[op.mode];
-      op_mp<C, KS>(M, P.PL, V->msg[M.slot], P.msg_smem ? msm + P.msg_off[op.mode] : nullptr, bufs + (size_t)op.src * P.bufsz,
-                   bufs + (size_t)op.dst * P.bufsz, tab, warp, lane);
-    } else if (op.type == OP_CLOSE) {
-      const BlkMode M = P.modes[op.mode];
-      double* out = V->part[M.slot] + (size_t)blk * PLN * M.chi * M.chi;
-      op_close<C, MT>(M, P.PL, bufs + (size_t)op.src * P.bufsz, bufs, red, out, tab, warp, lane, tid);
+    const OpConst O = sOp[oi];
+    if (O.type == OP_MP) {
+      op_mp<C, KS>(O, P.PL, V->msg[O.slot], msm, sKoff, bufs, bufs, tab, warp, lane);
+    } else if (O.type == OP_CLOSE) {
+      double* out = V->part[O.slot] + (size_t)blk * PLN * O.chi * O.chi;
+      op_close<C, MT>(O, P.PL, bufs + O.src, bufs, red, out, tab, warp, lane, tid);
     } else {
-      const double* b = bufs + (size_t)op.src * P.bufsz;
+      const double* b = bufs + O.src;
       double* gW = V->Wout;
-      // rows are contiguous on both sides and even in length whenever the pass moves them with bulk copies
+      const unsigned short* rt = tab + P.rowtab;
       if (P.bulk) {
         // 16-byte moves, row positions from the table: a warp per row (long rows) or several rows per warp (short rows)
         const int half = P.rowlen >> 1;
-        const unsigned short* rt = tab + P.rowtab;
         if (half >= 32) {
           for (int pl = 0; pl < PLN; ++pl)
             for (int row = warp; row < P.nrows; row += kNW) {
@@ -494,7 +604,7 @@ __global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPas
         for (long long i = tid; i < tot; i += kBT) {
           const int r = (int)(i / P.rowlen), c = (int)(i - (long long)r * P.rowlen);
           const int pl = r / P.nrows, row = r - pl * P.nrows;
-          gW[(long long)pl * P.gplane + goff + (long long)row * P.grow + c] = b[(size_t)pl * P.PL + row_pos(row) + c];
+          gW[(long long)pl * P.gplane + goff + (long long)row * P.grow + c] = b[(size_t)pl * P.PL + rt[row] + c];
         }
       }
     }
@@ -871,7 +981,9 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
   if ((long long)P.bufsz > 60000 || top > 30000) return false;  // 16-bit fibre tables
   bool even = P.rowlen % 2 == 0 && P.grow % 2 == 0 && P.gblk % 2 == 0 && n % 2 == 0 && P.PL % 2 == 0;
   for (int l = 0; l < P.nlev; ++l) even = even && P.lev_s[l] % 2 == 0;
-  P.bulk = even ? 1 : 0;
+  // 1: bulk copies (rows of at least 512 bytes: one instruction of the copy engine per row); 2: 16-byte cp.async of all
+  // threads (short rows: a warp issues 32 bulk copies one after the other, 32 cp.async at once); 0: 8-byte loads
+  P.bulk = even ? (P.rowlen * 8 >= 512 ? 1 : 2) : 0;
   P.load_p = which != 0;
   const int nm = (int)mode_slot.size();
   P.nmodes = nm;

@@ -136,6 +136,67 @@ def test_apply2_matches_oracle(ctx, dtype, normalize, name, mk, chi, iters, e, m
         assert abs(ez[v] - O.expect1(ref, m2, v, O.PAULI_Z)) < 1e-9
 
 
+def graded_site(rng, shape, k, kappa, dtype):
+    """Site tensor whose matricisation (every other bond) x (site, bond k) has singular values graded from 1 to 1 / kappa:
+    the matrix simple_update_bp QR-factorises (src/apply.jl:70-76) is then ill conditioned."""
+    nd = len(shape)
+    cols = shape[0] * shape[1 + k]
+    rows = int(np.prod(shape)) // cols
+    cplx = np.dtype(dtype).kind == "c"
+
+    def rnd(m, n):
+        x = rng.standard_normal((m, n))
+        return x + 1j * rng.standard_normal((m, n)) if cplx else x
+    r = min(rows, cols)
+    u, _ = np.linalg.qr(rnd(rows, r))
+    v, _ = np.linalg.qr(rnd(cols, r))
+    sv = np.logspace(0, -np.log10(kappa), r)
+    mat = (u * sv) @ v.conj().T                                   # rows x (s, l)
+    outer = [shape[1 + j] for j in range(nd - 1) if j != k]
+    t = mat.reshape(outer + [shape[0], shape[1 + k]])             # [outer..., s, l]
+    src = [1 + j for j in range(nd - 1) if j != k] + [0, 1 + k]
+    return np.ascontiguousarray(np.transpose(t, np.argsort(src))).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kappa", [1e4, 1e6, 1e8], ids=["k1e4", "k1e6", "k1e8"])
+@pytest.mark.parametrize("name,mk,chi,e", [("grid3x3_chi3", lambda: O.grid_graph((3, 3)), 3, 5),
+                                          ("grid4x4_chi16_tile", lambda: O.grid_graph((4, 4)), 16, 13)], ids=["chi3", "chi16"])
+def test_apply2_ill_conditioned_sites(dtype, kappa, name, mk, chi, e):
+    # The engine takes R from a Cholesky factorisation of the bond environment (Gram matrix: condition number squared)
+    # where the reference QR-factorises the absorbed site tensor.  Singular values, truncation error, kept dimension
+    # and the updated pair must still agree with the oracle's QR route when that matrix has condition number up to 1e8
+    # (a failed Cholesky pivot falls back to the Jacobi eigen route on the device).
+    g = mk()
+    net, psi = make_pair(g, chi, dtype)
+    v1, v2 = g.edges[e]
+    rng = np.random.default_rng(17)
+    for v in (v1, v2):
+        t = graded_site(rng, net.tensors[v].shape, g.slot(v, e), kappa, dtype)
+        net.tensors[v] = t
+        psi.tensors[v] = t.copy()
+    ctx = E.Context(0)
+    msgs, bpc = bp_both(net, psi, ctx, 10)
+    gate = O.random_unitary(4, seed=11, dtype=dtype).reshape(2, 2, 2, 2)
+    for maxdim, cutoff in ((chi, None), (None, 1e-10)):
+        ref, info = O.simple_update_bp(net, msgs, e, gate, maxdim=maxdim, cutoff=cutoff)
+        got = {}
+        out = E.apply(gate, bpc, (v1, v2), maxdim=maxdim, cutoff=cutoff, callback=lambda **kw: got.update(kw))
+        sv = info["svals"]
+        n = info["newdim"]
+        if cutoff is not None:
+            # a kept / dropped decision within rounding of the threshold may flip: compare where the spectrum has a gap
+            w = sv ** 2 / np.sum(sv ** 2)
+            tail = np.cumsum(w[::-1])[::-1]
+            if np.any(np.abs(tail - cutoff) < 1e-3 * cutoff):
+                continue
+        assert out.edge_dim(e) == n, (out.edge_dim(e), n)
+        assert np.max(np.abs(got["singular_values"] - sv[:n])) < TOL * sv[0]
+        assert abs(got["truncation_error"] - info["truncerr"]) < TOL
+        new = [out.factor(v) for v in range(g.nv)]
+        assert rel_err(pair_tensor(new, g, e), pair_tensor(ref.tensors, g, e)) < 1e-9
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_apply2_exact_on_tree(ctx, dtype):
     # BP environments are exact on a tree, so an untruncated simple update reproduces the exact gate
