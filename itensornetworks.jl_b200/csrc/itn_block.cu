@@ -159,7 +159,7 @@ __device__ __forceinline__ void mp_tiles(const OpConst& O, const int PL, const d
   const int chi = O.chi, S = O.S;
   const int g = lane >> 2, t = lane & 3;
   const int K2 = (C && !AL) ? 2 * chi : chi;
-  const int ksj = (K2 + 3) >> 2;
+  const int ksj = EXACT ? KH : ((K2 + 3) >> 2);  // exact modes fill every step of the kernel instance
   const int bS = b * S;
   const bool bok = b < chi;
   auto load1 = [&](unsigned fb, int ks, int plane_off) -> double {
@@ -280,8 +280,8 @@ __device__ __forceinline__ void op_mp(const OpConst& O, const int PL, const doub
   constexpr int KH = AL ? KS / 2 : KS;  // fragments per array
   const int chi = O.chi;
   const int mtj = (chi + 7) >> 3;
-  const int mtd = mtj == 3 ? 4 : mtj;  // warps are dealt out over 1, 2 or 4 row tiles
-  const int mt = warp % mtd, fsub = warp / mtd, fstep = kNW / mtd;
+  const int mtl = mtj > 2 ? 2 : mtj - 1;  // warps are dealt out over 1, 2 or 4 row tiles (log2)
+  const int mt = warp & ((1 << mtl) - 1), fsub = warp >> mtl, fstep = kNW >> mtl;
   if (mt >= mtj) return;
   double A0[KH], A1[C ? KH : 1];
   int koff[KH];
@@ -1040,8 +1040,11 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
     P.modes[k].S = m.S;
     P.modes[k].slot = m.slot;
     {
+      // exact: no padding fibres, and the (stacked) reduction length fills every k4 step of the kernel instance, so the
+      // inner loops of the kernel have compile-time trip counts and no predicates
       const int K2 = (cplx && !aligned) ? 2 * m.chi : m.chi;
-      P.modes[k].exact = ((nreal / m.chi) % 8 == 0 && K2 % 4 == 0) ? 1 : 0;
+      const int KHs = aligned ? ks_inst / 2 : ks_inst;
+      P.modes[k].exact = ((nreal / m.chi) % 8 == 0 && K2 == 4 * KHs) ? 1 : 0;
     }
     if (with_tables) {
       // every combination of the other axes, first axis fastest

@@ -147,23 +147,42 @@ __global__ void __launch_bounds__(kThreads, HAS_P ? 2 : 3) k_fast(const FastArgs
   const int s_site = pidx >> 5;
   const size_t cube = (((size_t)s_site * 16 + q) * 16 + half * kTilesPerCta) * TILE;
 
+  // Staging by the bulk-copy engine (TMA, cp.async.bulk): every operand of the CTA is one contiguous 32 KB half-cube in
+  // HBM, copied as 8 tiles of 4 KB (the shared-memory tile stride TS rotates the banks from tile to tile) by 8 lanes, with
+  // completion signalled on an mbarrier per operand: the partially absorbed tiles P first (the products M_L^T P and
+  // P M_R need nothing else), the site-tensor tiles X second, so that the copy of X overlaps the first two tile products.
+  __shared__ __align__(8) unsigned long long mbar[2];
+  const unsigned mbP = (unsigned)__cvta_generic_to_shared(&mbar[0]), mbX = (unsigned)__cvta_generic_to_shared(&mbar[1]);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbP));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbX));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
   {
-    // two cp.async groups: the partially absorbed tiles P first (the products M_L^T P and P M_R need nothing else),
-    // the site-tensor tiles X second, so that the copy of X overlaps the first two tile products
-    if (HAS_P) {
-      const double* gp = a.Pv[vi] + cube;
-      for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
-        const int w = i / (TILE / 2), r = i - w * (TILE / 2);
-        cp_async16(Ps + w * TS + 2 * r, gp + 2 * i);
+    constexpr unsigned kTileBytes = TILE * sizeof(double);
+    if (warp == 0) {
+      if (lane == 0) {
+        if (HAS_P) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbP), "r"(kTilesPerCta * kTileBytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbX), "r"(kTilesPerCta * kTileBytes) : "memory");
       }
-      asm volatile("cp.async.commit_group;\n" ::);
+      __syncwarp();
+      if (HAS_P && lane < kTilesPerCta) {
+        const double* gp = a.Pv[vi] + cube + (size_t)lane * TILE;
+        const unsigned dsts = (unsigned)__cvta_generic_to_shared(Ps + lane * TS);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dsts),
+                     "l"(gp), "r"(kTileBytes), "r"(mbP)
+                     : "memory");
+      }
+      if (lane >= 16 && lane < 16 + kTilesPerCta) {
+        const int w = lane - 16;
+        const double* gx = a.Xv[vi] + cube + (size_t)w * TILE;
+        const unsigned dsts = (unsigned)__cvta_generic_to_shared(Xs + w * TS);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dsts),
+                     "l"(gx), "r"(kTileBytes), "r"(mbX)
+                     : "memory");
+      }
     }
-    const double* gx = a.Xv[vi] + cube;
-    for (int i = tid; i < kTilesPerCta * TILE / 2; i += kThreads) {
-      const int w = i / (TILE / 2), r = i - w * (TILE / 2);
-      cp_async16(Xs + w * TS + 2 * r, gx + 2 * i);
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
     const double* ml = a.msg[vi * 4 + a.kL];
     const double* mr = a.msg[vi * 4 + a.kR];
     const int o = swz(tid & 15, tid >> 4);
@@ -173,10 +192,19 @@ __global__ void __launch_bounds__(kThreads, HAS_P ? 2 : 3) k_fast(const FastArgs
       MLs[256 + o] = ml[256 + tid];
       MRs[256 + o] = mr[256 + tid];
     }
-    if (HAS_P) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   }
-  __syncthreads();
+  auto mbar_wait = [](unsigned mb) {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(mb), "r"(0u)
+          : "memory");
+    }
+  };
+  mbar_wait(HAS_P ? mbP : mbX);
+  __syncthreads();  // the message tiles (ordinary stores) are visible too
 
   double* X = Xs + warp * TS;
   double* S = Ss + warp * TS;
@@ -193,8 +221,7 @@ __global__ void __launch_bounds__(kThreads, HAS_P ? 2 : 3) k_fast(const FastArgs
     tile_mm<C, false, false, false>(P, MRs, cre, cim, lane);
     __syncwarp();
     store_acc<C>(P, cre, cim, lane);
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();  // X has landed (copied by all threads of the CTA)
+    mbar_wait(mbX);  // X has landed (every thread observes the barrier phase itself: no CTA barrier needed)
     // right output: O[l,l'] = sum_k T[k,l] conj(X[k,l'])
     zero_acc<C>(cre, cim);
     tile_mm<C, true, false, true>(S, X, cre, cim, lane);
