@@ -336,6 +336,26 @@ def ms_estimate_short(args, world):
     return args.steps * 30.0 / max(world, 1) < 400.0
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPU cores NVML lists as local to its GPU, so that the pinned host buffers are allocated on
+    the GPU's NUMA node and the host->device copies of 8 ranks do not cross the socket interconnect (torchrun does not
+    bind ranks).  Best effort: any failure leaves the affinity untouched."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cores = [c for c in cores if c in allowed]
+        if cores:
+            os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return 0
+
+
 def time_sweeps(E, torch, bpc, seq, stream, steps, warmup):
     """Device time (CUDA events on the library's stream) of `steps` synchronous sweeps in one update() call."""
     E.update(bpc, maxiter=max(warmup, 3), edge_sequence=seq, inplace=True)
@@ -387,6 +407,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libitn_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dims, chi, dtype, cfg = WORKLOADS[args.workload]
@@ -473,16 +494,27 @@ def run_ours(args):
         2 for (u, v) in graph.edges if owner[u] == rank or owner[v] == rank)
     d2h = n_stored * chi * chi * comps * 8
     out_host = torch.empty(n_stored * chi * chi * comps, dtype=torch.float64).pin_memory()
+    phases = {"construct": 0.0, "update": 0.0, "download": 0.0, "close": 0.0}
+
     def e2e_step():
         # defer_upload: the constructor registers the pinned host tensors, update() streams them in chunks and runs the
         # sweep of chunk c while chunk c + 1 crosses PCIe (itn_net_set_tensors / ITN_HOST_DEFERRED)
+        t0 = time.perf_counter()
         c2 = E.BeliefPropagationCache(psi, ctx=ctx, owner=owner, dist=(rank, world) if world > 1 else None, defer_upload=True)
+        t1 = time.perf_counter()
         E.update(c2, maxiter=1, edge_sequence=seq, inplace=True)
+        t2 = time.perf_counter()
         c2.messages_into(out_host.numpy())
+        t3 = time.perf_counter()
         c2.close()
+        t4 = time.perf_counter()
+        for k, dt in zip(("construct", "update", "download", "close"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            phases[k] += dt
 
     e2e_step()  # untimed warm-up: the second network's device allocations grow the stream-ordered pool once
     barrier()
+    for k in phases:
+        phases[k] = 0.0
     per_step = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -559,7 +591,8 @@ def run_ours(args):
                              "issued (3/4 of the algorithmic count on degree-4 chi=16 vertices), dmma_pipe_peak the measured DMMA issue "
                              "rate of tools/fp64_peak.cu. FP64 peak, not bf16"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "s_per_step": per_step, "what": "BeliefPropagationCache(psi in pinned host memory, defer_upload=True) + update(maxiter=1) [host->device copy pipelined with the sweep] + download of all messages"},
+                "steps": e2e_steps, "s_per_step": per_step,
+                "host_phases_s_per_step_rank0": {k: v / e2e_steps for k, v in phases.items()}, "what": "BeliefPropagationCache(psi in pinned host memory, defer_upload=True) + update(maxiter=1) [host->device copy pipelined with the sweep] + download of all messages"},
         "gpu_launches": launches, "clocks": clocks,
     }
     if parity is not None:

@@ -25,7 +25,8 @@ def main():
     ctx = E.Context(local)
     E.init_distributed(ctx, rank, world)
     worst = 0.0
-    for dims, chi, dtype in (((6, 4), 3, np.complex128), ((8, 8), 16, np.complex128), ((4, 4), 2, np.float64)):
+    cases = (((6, 4), 3, np.complex128), ((8, 8), 16, np.complex128), ((4, 4), 2, np.float64), ((4, 4, 4), 2, np.complex128))
+    for dims, chi, dtype in cases:
         g = O.grid_graph(dims)
         eg = E.named_grid(dims)
         owner = E.partition_vertices(eg, world)
@@ -55,6 +56,15 @@ def main():
         r = E.rescale(bpc)
         zv2, ze2 = E.scalar_factors_quotient(r)
         worst = max(worst, float(np.max(np.abs(zv2 - 1))), float(np.max(np.abs(ze2 - 1))))
+        # one-site gates on EVERY vertex, called identically on every rank (non-owners skip, src/apply.jl:108-116)
+        kick = O.random_unitary(2, seed=5, dtype=dtype)
+        for v in range(g.nv):
+            net = O.apply1(net, v, kick)
+            E.apply(kick, bpc, (v,), inplace=True)
+        ref, _, _ = O.bp_update(net, ref, seq=seq, groups=O.synchronous_groups(seq), maxiter=2)
+        E.update(bpc, maxiter=2, edge_sequence=[[e] for e in seq], inplace=True)
+        ez = E.expect(bpc, "Z")
+        worst = max(worst, max(abs(ez[v] - O.expect1(net, ref, v, O.PAULI_Z)) for v in range(g.nv)))
         # simple-update gate layers on the partitioned network (src/apply.jl:33-95): interior edges and edges that cross
         # the cut (the guest rank ships its bond environment, the owner returns the T factor); then BP again and <Z>
         gate = O.random_unitary(4, seed=11, dtype=dtype).reshape(2, 2, 2, 2)

@@ -9,11 +9,12 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_partitioned_bp_two_gpus():
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_partitioned_bp_and_gates_match_oracle(nproc):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs (logs of the 2 / 4 / 8 GPU runs: profiles/r2_dist_check_*gpu.log)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(29517 + nproc), os.path.join(ROOT, "tests", "dist_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
