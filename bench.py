@@ -638,7 +638,13 @@ def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch, dist=None, 
     m = rng.standard_normal((d * d, d * d)) + (1j * rng.standard_normal((d * d, d * d)) if np.dtype(dtype).kind == "c" else 0)
     h = (m + m.conj().T) / 2
     w, v = np.linalg.eigh(h)
-    gate = ((v * np.exp(-0.05 * w)) @ v.conj().T).astype(dtype).reshape(d, d, d, d)  # exp(-tau H): imaginary-time step
+    # exp(-i tau H): a real-time (unitary) Trotter gate, so that repeated steps keep the state well scaled -- an
+    # un-normalised imaginary-time gate lets the tensors drift towards under/overflow after a few steps, and the gate
+    # path then spends its time in the rank-deficient fall-backs instead of the kernels being measured
+    if np.dtype(dtype).kind == "c":
+        gate = ((v * np.exp(-0.05j * w)) @ v.conj().T).astype(dtype).reshape(d, d, d, d)
+    else:
+        gate = ((v * np.exp(-0.05 * w)) @ v.conj().T).astype(dtype).reshape(d, d, d, d)
     layers = E.edge_coloring(graph)
     fg, fq = gate_flops(graph, chi, d, np.dtype(dtype).kind == "c")
 

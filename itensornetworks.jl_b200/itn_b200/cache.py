@@ -697,13 +697,14 @@ def tebd_step(bpc, layers, maxdim=None, cutoff=None, normalize=False, msg_mode=0
         edge_sequence = []
     grouped = len(edge_sequence) > 0 and isinstance(edge_sequence[0], list)
     flat = [e for grp in edge_sequence for e in grp] if grouped else list(edge_sequence)
-    _, ps = i32([u for u, _ in flat])
-    _, pd = i32([v for _, v in flat])
-    gp = None
+    # keep every index array referenced until the call returns (the pointers borrow their memory)
+    a_s, ps = i32([u for u, _ in flat])
+    a_d, pd = i32([v for _, v in flat])
+    gp, a_g = None, None
     if grouped:
-        _, gp = i32(np.cumsum([0] + [len(grp) for grp in edge_sequence]))
-    _, pe = i32(all_e)
-    _, pl = i32(ptr)
+        a_g, gp = i32(np.cumsum([0] + [len(grp) for grp in edge_sequence]))
+    a_e, pe = i32(all_e)
+    a_l, pl = i32(ptr)
     iters = C.c_int32()
     check(lib().itn_apply_layers(bpc.h, len(layers), pl, pe, packed.ctypes.data_as(C.c_void_p),
                                  0 if maxdim is None else int(maxdim), -1.0 if cutoff is None else float(cutoff),
@@ -711,6 +712,7 @@ def tebd_step(bpc, layers, maxdim=None, cutoff=None, normalize=False, msg_mode=0
                                  len(edge_sequence) if grouped else 0, int(bp_maxiter), -1.0 if bp_tol is None else float(bp_tol),
                                  1, newdim.ctypes.data_as(C.POINTER(C.c_int32)), terr.ctypes.data_as(C.POINTER(C.c_double)),
                                  sv.ctypes.data_as(C.POINTER(C.c_double)), stride, C.byref(iters)))
+    del a_s, a_d, a_g, a_e, a_l
     bpc._host_refs = None
     bpc._note_newdims(all_e, newdim)  # layers in order: the last gate on an edge wins
     if info is not None:
