@@ -172,6 +172,19 @@ def test_scalars_rescale_observables(ctx, dtype):
         assert rel_err(r.factor(v), net2.tensors[v]) < TOL
     assert_messages_close(r, msgs2, TOL)
     assert abs(E.scalar(r) - 1.0) < 1e-10
+    # rescale(bpc; verts) (abstractbeliefpropagationcache.jl:349-395): messages of every edge, tensors of the listed sites only
+    sub = [0, 3, g.nv - 1]
+    net3, msgs3 = O.rescale(net, msgs, verts=sub)
+    r3 = E.rescale(bpc, verts=sub)
+    assert_messages_close(r3, msgs3, TOL)
+    zv3, ze3 = E.scalar_factors_quotient(r3)
+    assert np.allclose(ze3, 1.0, atol=1e-12) and np.allclose(zv3[sub], 1.0, atol=1e-12)
+    for v in range(g.nv):
+        assert rel_err(r3.factor(v), net3.tensors[v]) < TOL
+        if v not in sub:
+            assert np.array_equal(r3.factor(v), net.tensors[v])  # untouched
+    r0 = E.rescale(bpc, verts=[])  # messages only
+    assert_messages_close(r0, msgs3, TOL)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
