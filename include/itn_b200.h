@@ -193,6 +193,15 @@ int itn_apply_layers(itn_net* net, int nlayers, const int32_t* layer_ptr, const 
                      double bp_tol, int bp_normalize, int32_t* newdim_n, double* truncerr_n, double* svals,
                      int svals_stride, int32_t* bp_iters_total);
 
+/* gauge_walk(tn, edges) (src/abstractitensornetwork.jl:387-393): qr!(tn, src[i] => dst[i]) for i = 0 .. n-1, the loop
+ * behind tree_gauge / tree_orthogonalize (:395-420), which apply(o, psi; ortho = true) runs towards the first gate vertex
+ * before the update (src/apply.jl:109-111, 130-132).  After step i the tensor of src[i] is an isometry from (site, other
+ * bonds) to the bond and the square factor has been multiplied into dst[i]; the state is unchanged.  The factor is the
+ * Hermitian one (G^(1/2) of the Gram matrix, twice: orthonormal to eps), not Householder's triangular R: the gauge differs
+ * from the reference's by a unitary on the bond, every gauge-invariant quantity agrees.  Messages are left untouched (they
+ * belong to the old gauge: re-run itn_bp_update or reset them).  Single GPU. */
+int itn_gauge_walk(itn_net* net, const int32_t* src, const int32_t* dst, int n);
+
 /* map_eigvals(f, A, ...; ishermitian = true, cutoff) (src/apply.jl:21-25) for a batch of n
  * Hermitian chi x chi host matrices; fn: 0 = sqrt, 1 = inv o sqrt, 2 = inv.  cutoff < 0: none. */
 int itn_map_eigvals(itn_ctx* ctx, int dtype, int fn, int chi, int n, const void* host_in,

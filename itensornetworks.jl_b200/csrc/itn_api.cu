@@ -39,7 +39,7 @@ extern "C" int itn_version(void) { return 100; }
 namespace {
 constexpr size_t kBigBlock = (size_t)32 << 20;    // blocks of at least 32 MiB are recycled by the context
 constexpr size_t kBigRound = (size_t)64 << 20;    // their sizes are rounded up to 64 MiB so that similar requests match
-constexpr size_t kBigCacheMax = (size_t)64 << 30; // parked bytes above this are returned to the driver
+constexpr size_t kBigCacheMax = (size_t)96 << 30; // parked bytes above this are returned to the driver
 
 void big_trim(itn_ctx* ctx, size_t keep) {
   while (ctx->big_cached > keep && !ctx->big_free.empty()) {
@@ -63,12 +63,23 @@ void* itn_dev_alloc(itn_ctx* ctx, size_t bytes) {
       ctx->big_free.erase(it);
       return p;
     }
+    static const bool trace = getenv("ITN_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    bool retried = false;
     cudaError_t e = cudaMallocAsync(&p, want, ctx->stream);
     if (e != cudaSuccess) {  // give the parked blocks back and retry once
       cudaGetLastError();
       big_trim(ctx, 0);
       cudaStreamSynchronize(ctx->stream);
       e = cudaMallocAsync(&p, want, ctx->stream);
+      retried = true;
+    }
+    if (trace) {
+      size_t live = 0;
+      for (auto& kv : ctx->big_live) live += kv.second;
+      fprintf(stderr, "[itn trace] big block miss: %zu MiB in %.1f ms%s (parked %zu MiB in %zu blocks, live %zu MiB)\n", want >> 20,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+              retried ? " after trimming the cache" : "", ctx->big_cached >> 20, ctx->big_free.size(), live >> 20);
     }
     if (e != cudaSuccess) {
       cudaGetLastError();
@@ -1470,7 +1481,9 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
       multi_edge_groups = multi_edge_groups || group_ptr[i + 1] - group_ptr[i] != 1;
     }
   }
+  HostTrace trace("bp_update");
   std::vector<MsgJob> jobs = make_msg_jobs(net, seq_src, seq_dst, nseq);
+  trace.mark("jobs");
   if (multi_edge_groups) {
     bp_update_groups(net, jobs, group_ptr, ngroups, maxiter, tol, normalize, iters, last_mean_diff);
     return ITN_OK;
@@ -1544,6 +1557,7 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
     if (level[order[i]] != level[order[i - 1]]) lvl_ptr.push_back(i);
   lvl_ptr.push_back(nseq);
 
+  trace.mark("levels");
   Staged staged(net, sjobs);
   DevBuf diffs(ctx, (size_t)std::max(nseq, 1) * sizeof(double));
   DevBuf dsum(ctx, sizeof(double));
@@ -1555,8 +1569,10 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   // synchronous sweeps: vertices that qualify go to the DMMA kernels, the rest to the generic kernels
   std::vector<char> handled;
   const int nfast = sync_mode ? itn_fast_bp_plan(net, all_dids, all_src, handled) : 0;
+  trace.mark("plan_tile");
   // vertices the tile path did not take: the block path (itn_block.cu) for every degree 2..8 / bond extent <= 32
   const int nblock = sync_mode ? itn_block_bp_plan(net, all_dids, all_src, handled) : 0;
+  trace.mark("plan_block");
   // the rest of a synchronous sweep: vertices whose outgoing messages are all part of it go to the vertex-level DMMA
   // sweep (shared partial absorptions, itn_run_vertex_sweeps), whatever is left to the per-message kernels
   std::vector<JobSpec> slow_specs;
@@ -1648,7 +1664,9 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
       if (on) itn_block_bp_end(net);
     }
   } block_call{net, nblock > 0};
+  trace.mark("plan_rest");
   if (nblock > 0) itn_block_bp_begin(net, all_dids, all_src, handled, staged.ptr.data());
+  trace.mark("block_begin");
 
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
@@ -1726,8 +1744,10 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
         if (mean <= tol) break;
       }
     }
+    trace.mark("launch");
     CUDA_CHECK(cudaEventRecord(ev1, ctx->stream));
     CUDA_CHECK(cudaEventSynchronize(ev1));
+    trace.mark("wait");
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     net->last_total_ms = ms;

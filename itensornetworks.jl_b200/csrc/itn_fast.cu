@@ -32,6 +32,7 @@ namespace {
 constexpr int kChi = 16;
 constexpr int kTilesPerCta = 8;
 constexpr int kThreads = 256;
+constexpr int kChunkSites = 512;  // sites per scratch chunk (c128, d = 2: 1 GB each for P12 and S34, 0.5 GB of partial sums)
 
 // element (r, c) of a 16x16 column-major tile plane.  The row is XOR-ed with a column-dependent multiple of 4
 // chosen so that every DMMA fragment pattern -- (k, n) loads, (m, k) loads and the accumulator store with
@@ -593,6 +594,10 @@ struct FastCache {
   std::vector<int> vslot;  // vertex -> bucket index or -1
   double *F1 = nullptr, *F2 = nullptr, *P12 = nullptr, *S34 = nullptr, *part = nullptr;
   size_t vstride = 0;      // doubles per vertex in F1/F2/P12/S34
+  // P12, S34 and the per-CTA partial sums are scratch of ONE chunk of `chunk` sites: a sweep (and the bond environments
+  // of a gate layer) runs chunk by chunk on the same stream, so a network at rest holds its canonical tensors and the
+  // two tile-major copies only (64 x 64, chi = 16, c128: 24 GB + 2.5 GB of scratch instead of 44 GB)
+  int chunk = 0;
   // current BP sweep
   std::vector<int> sweep;  // bucket indices taking part
   const double** d_tab = nullptr;  // 4 pointer tables of nb entries: F1, F2, P12, S34 of the sweep's vertices
@@ -646,13 +651,14 @@ void sweep_range(itn_net* net, FastCache* fc, int lo, int hi) {
   constexpr int TILE = C ? 512 : 256;
   const int ns = hi - lo;
   if (ns <= 0) return;
+  ITN_REQUIRE(ns <= fc->chunk, ITN_EINVAL, "tile sweep: range exceeds the scratch chunk");
   const double* const* tF1 = fc->d_tab + lo;
   const double* const* tF2 = fc->d_tab + fc->nb + lo;
   const double* const* tP12 = fc->d_tab + 2 * (size_t)fc->nb + lo;
   const double* const* tS34 = fc->d_tab + 3 * (size_t)fc->nb + lo;
   FastArgs a;
   a.msg = fc->d_msg + 4 * (size_t)lo;
-  a.part = fc->part + (size_t)lo * 4 * 32 * fc->d * TILE;
+  a.part = fc->part;
   a.d = fc->d;
   // phase 1: P12 = M1^T X M2 on F1 tiles
   a.Xv = tF1; a.Pv = nullptr; a.Wv = (double* const*)tP12; a.kL = 0; a.kR = 1;
@@ -663,11 +669,8 @@ void sweep_range(itn_net* net, FastCache* fc, int lo, int hi) {
   // phase 3: out2 / out1 from S34 and F1 tiles
   a.Xv = tF1; a.Pv = tS34; a.Wv = nullptr; a.kL = 0; a.kR = 1;
   launch_phase<C, true, false>(net, ns, a);
-}
-
-template <bool C>
-void sweep_reduce(itn_net* net, FastCache* fc) {
-  k_fast_reduce<C><<<(unsigned)fc->sweep.size() * 4, 256, 0, net->ctx->stream>>>(fc->part, fc->d_staged, 32 * fc->d);
+  // fixed-order sum of the per-CTA partials of this chunk into the staged messages
+  k_fast_reduce<C><<<(unsigned)ns * 4, 256, 0, net->ctx->stream>>>(fc->part, fc->d_staged + 4 * (size_t)lo, 32 * fc->d);
   ITN_LAUNCH_CHECK(net->ctx);
 }
 
@@ -735,9 +738,11 @@ FastCache* ensure_cache(itn_net* net) {
       const size_t tb = (size_t)fc->nb * fc->vstride * sizeof(double);
       fc->F1 = (double*)itn_dev_alloc(ctx, tb);
       fc->F2 = (double*)itn_dev_alloc(ctx, tb);
-      fc->P12 = (double*)itn_dev_alloc(ctx, tb);
-      fc->S34 = (double*)itn_dev_alloc(ctx, tb);
-      fc->part = (double*)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * 32 * d * TILE * sizeof(double));
+      fc->chunk = std::min(fc->nb, kChunkSites);
+      const size_t cb = (size_t)fc->chunk * fc->vstride * sizeof(double);
+      fc->P12 = (double*)itn_dev_alloc(ctx, cb);
+      fc->S34 = (double*)itn_dev_alloc(ctx, cb);
+      fc->part = (double*)itn_dev_alloc(ctx, (size_t)fc->chunk * 4 * 32 * d * TILE * sizeof(double));
       fc->d_tab = (const double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
       fc->d_msg = (const double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
       fc->d_staged = (double**)itn_dev_alloc(ctx, (size_t)fc->nb * 4 * sizeof(double*));
@@ -822,8 +827,9 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
     const size_t off = (size_t)fc->sweep[r] * fc->vstride;
     tab[r] = fc->F1 + off;
     tab[fc->nb + r] = fc->F2 + off;
-    tab[2 * (size_t)fc->nb + r] = fc->P12 + off;
-    tab[3 * (size_t)fc->nb + r] = fc->S34 + off;
+    const size_t coff = (r % (size_t)fc->chunk) * fc->vstride;  // scratch slot of sweep position r
+    tab[2 * (size_t)fc->nb + r] = fc->P12 + coff;
+    tab[3 * (size_t)fc->nb + r] = fc->S34 + coff;
   }
   CUDA_CHECK(cudaMemcpyAsync((void*)fc->d_tab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
   int n = 0;
@@ -871,15 +877,15 @@ void itn_fast_bp_sweep_range(itn_net* net, int lo, int hi) {
   ITN_REQUIRE(fc && lo >= 0 && hi <= (int)fc->sweep.size(), ITN_EINVAL, "bad sweep range");
   for (int r = lo; r < hi; ++r)
     ITN_REQUIRE(!fc->stale[fc->sweep[r]], ITN_EINVAL, "tile-major copy of a vertex in the sweep has not been built");
-  if (net->cplx) sweep_range<true>(net, fc, lo, hi);
-  else sweep_range<false>(net, fc, lo, hi);
+  // chunk by chunk: sweep position r uses scratch slot r % chunk, so any piece of at most `chunk` positions is conflict free
+  for (int s0 = lo; s0 < hi; s0 += fc->chunk) {
+    const int s1 = std::min(hi, s0 + fc->chunk);
+    if (net->cplx) sweep_range<true>(net, fc, s0, s1);
+    else sweep_range<false>(net, fc, s0, s1);
+  }
 }
 
-void itn_fast_bp_sweep_end(itn_net* net) {
-  FastCache* fc = (FastCache*)net->fast;
-  if (net->cplx) sweep_reduce<true>(net, fc);
-  else sweep_reduce<false>(net, fc);
-}
+void itn_fast_bp_sweep_end(itn_net*) {}  // every range reduces its own partial sums
 
 void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
                        const std::vector<char>& handled, double* const* staged) {
@@ -915,83 +921,96 @@ bool itn_fast_gate_site_ok(itn_net* net, int v) {
 
 // Bond environments C (n x n planar, n = 16 d) of the listed (vertex, bond slot) pairs; mats[j][slot] are the
 // (hermitised) incoming messages to absorb.
-void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs) {
-  if (jobs.empty()) return;
+void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& all_jobs) {
+  if (all_jobs.empty()) return;
   FastCache* fc = ensure_cache(net);
   ITN_REQUIRE(fc, ITN_EINVAL, "tile path is not available");
   itn_ctx* ctx = net->ctx;
   const int d = fc->d, TILE = net->cplx ? 512 : 256;
-  const size_t nj = jobs.size();
-  // phase-1 pass per group: slots 2,3 need P12 (X = F1, messages 0,1); slots 0,1 need S34 (X = F2, messages 2,3)
-  for (int grp = 0; grp < 2; ++grp) {
-    std::vector<const double*> xv, wv, msg;
-    for (const FastBenvJob& J : jobs) {
-      if ((J.slot >= 2) != (grp == 0)) continue;
-      const size_t off = (size_t)fc->vslot[J.v] * fc->vstride;
-      xv.push_back((grp == 0 ? fc->F1 : fc->F2) + off);
-      wv.push_back((grp == 0 ? fc->P12 : fc->S34) + off);
-      for (int k = 0; k < 4; ++k) msg.push_back(J.mats[k] ? J.mats[k] : net->M[net->msg_into(J.v, net->inc[J.v][k])].p);
-    }
-    if (xv.empty()) continue;
-    const size_t n = xv.size();
-    DevBuf tb(ctx, (2 * n + msg.size()) * sizeof(double*));
-    std::vector<const double*> all(xv);
-    all.insert(all.end(), wv.begin(), wv.end());
-    all.insert(all.end(), msg.begin(), msg.end());
-    const double** dt = (const double**)itn_upload(ctx, all, tb);
-    FastArgs a;
-    a.Xv = dt;
-    a.Pv = nullptr;
-    a.Wv = (double* const*)(dt + n);
-    a.msg = dt + 2 * n;
-    a.part = nullptr;
-    a.d = d;
-    a.kL = grp == 0 ? 0 : 2;
-    a.kR = grp == 0 ? 1 : 3;
-    if (net->cplx) launch_phase<true, false, true>(net, (int)n, a);
-    else launch_phase<false, false, true>(net, (int)n, a);
-  }
-  // close pass
-  std::vector<const double*> tabs;
-  std::vector<int> side(nj);
-  for (const FastBenvJob& J : jobs) tabs.push_back((J.slot >= 2 ? fc->F2 : fc->F1) + (size_t)fc->vslot[J.v] * fc->vstride);
-  for (const FastBenvJob& J : jobs) tabs.push_back((J.slot >= 2 ? fc->P12 : fc->S34) + (size_t)fc->vslot[J.v] * fc->vstride);
-  for (size_t j = 0; j < nj; ++j) {
-    const FastBenvJob& J = jobs[j];
-    const int partner = J.slot ^ 1;  // the other bond of the pair (0,1) or (2,3)
-    tabs.push_back(J.mats[partner] ? J.mats[partner] : net->M[net->msg_into(J.v, net->inc[J.v][partner])].p);
-    side[j] = (J.slot & 1) ? 0 : 1;  // odd slot = right index of the tile
-  }
-  for (const FastBenvJob& J : jobs) tabs.push_back(J.C);
-  DevBuf tb(ctx, tabs.size() * sizeof(double*)), sb(ctx, nj * sizeof(int));
-  const double** dt = (const double**)itn_upload(ctx, tabs, tb);
-  const int* ds = itn_upload(ctx, side, sb);
   ITN_REQUIRE(d == 2, ITN_EINVAL, "tile bond environments need d = 2");
-  DevBuf part(ctx, nj * 3 * 32 * TILE * sizeof(double));
-  BenvArgs b;
-  b.Xv = dt;
-  b.Pv = dt + nj;
-  b.Mv = dt + 2 * nj;
-  b.side = ds;
-  b.part = part.as<double>();
-  b.d = d;
-  const unsigned grid = (unsigned)(nj * 32);
-  if (net->cplx) {
-    const size_t smem = (size_t)(3 * kTilesPerCta + 1) * (512 + 2) * sizeof(double);
-    CUDA_CHECK(cudaFuncSetAttribute(k_benv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_CHECK(cudaFuncSetAttribute(k_benv<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    k_benv<true><<<grid, kThreads, smem, ctx->stream>>>(b);
+  // pieces of at most `chunk` jobs: job j of a piece keeps its partially absorbed tensor in scratch slot (index inside
+  // its group) of P12 (gate bond in the pair (2, 3)) or S34 (pair (0, 1)); pieces follow each other on the stream
+  for (size_t j0 = 0; j0 < all_jobs.size(); j0 += (size_t)fc->chunk) {
+    const size_t j1 = std::min(all_jobs.size(), j0 + (size_t)fc->chunk);
+    const std::vector<FastBenvJob> jobs(all_jobs.begin() + j0, all_jobs.begin() + j1);
+    const size_t nj = jobs.size();
+    std::vector<const double*> wslot(nj);
+    {
+      size_t n0 = 0, n1 = 0;
+      for (size_t j = 0; j < nj; ++j)
+        wslot[j] = jobs[j].slot >= 2 ? fc->P12 + (n0++) * fc->vstride : fc->S34 + (n1++) * fc->vstride;
+    }
+    // phase-1 pass per group: slots 2,3 need P12 (X = F1, messages 0,1); slots 0,1 need S34 (X = F2, messages 2,3)
+    for (int grp = 0; grp < 2; ++grp) {
+      std::vector<const double*> xv, wv, msg;
+      for (size_t j = 0; j < nj; ++j) {
+        const FastBenvJob& J = jobs[j];
+        if ((J.slot >= 2) != (grp == 0)) continue;
+        const size_t off = (size_t)fc->vslot[J.v] * fc->vstride;
+        xv.push_back((grp == 0 ? fc->F1 : fc->F2) + off);
+        wv.push_back(wslot[j]);
+        for (int k = 0; k < 4; ++k) msg.push_back(J.mats[k] ? J.mats[k] : net->M[net->msg_into(J.v, net->inc[J.v][k])].p);
+      }
+      if (xv.empty()) continue;
+      const size_t n = xv.size();
+      DevBuf tb(ctx, (2 * n + msg.size()) * sizeof(double*));
+      std::vector<const double*> all(xv);
+      all.insert(all.end(), wv.begin(), wv.end());
+      all.insert(all.end(), msg.begin(), msg.end());
+      const double** dt = (const double**)itn_upload(ctx, all, tb);
+      FastArgs a;
+      a.Xv = dt;
+      a.Pv = nullptr;
+      a.Wv = (double* const*)(dt + n);
+      a.msg = dt + 2 * n;
+      a.part = nullptr;
+      a.d = d;
+      a.kL = grp == 0 ? 0 : 2;
+      a.kR = grp == 0 ? 1 : 3;
+      if (net->cplx) launch_phase<true, false, true>(net, (int)n, a);
+      else launch_phase<false, false, true>(net, (int)n, a);
+    }
+    // close pass
+    std::vector<const double*> tabs;
+    std::vector<int> side(nj);
+    for (const FastBenvJob& J : jobs) tabs.push_back((J.slot >= 2 ? fc->F2 : fc->F1) + (size_t)fc->vslot[J.v] * fc->vstride);
+    for (size_t j = 0; j < nj; ++j) tabs.push_back(wslot[j]);
+    for (size_t j = 0; j < nj; ++j) {
+      const FastBenvJob& J = jobs[j];
+      const int partner = J.slot ^ 1;  // the other bond of the pair (0,1) or (2,3)
+      tabs.push_back(J.mats[partner] ? J.mats[partner] : net->M[net->msg_into(J.v, net->inc[J.v][partner])].p);
+      side[j] = (J.slot & 1) ? 0 : 1;  // odd slot = right index of the tile
+    }
+    for (const FastBenvJob& J : jobs) tabs.push_back(J.C);
+    DevBuf tb(ctx, tabs.size() * sizeof(double*)), sb(ctx, nj * sizeof(int));
+    const double** dt = (const double**)itn_upload(ctx, tabs, tb);
+    const int* ds = itn_upload(ctx, side, sb);
+    // per-CTA partials of the piece: 3 pairs x 32 CTAs x TILE per job, inside the sweep's partial-sum scratch (4 x 64 x TILE)
+    BenvArgs b;
+    b.Xv = dt;
+    b.Pv = dt + nj;
+    b.Mv = dt + 2 * nj;
+    b.side = ds;
+    b.part = fc->part;
+    b.d = d;
+    const unsigned grid = (unsigned)(nj * 32);
+    if (net->cplx) {
+      const size_t smem = (size_t)(3 * kTilesPerCta + 1) * (512 + 2) * sizeof(double);
+      CUDA_CHECK(cudaFuncSetAttribute(k_benv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_CHECK(cudaFuncSetAttribute(k_benv<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      k_benv<true><<<grid, kThreads, smem, ctx->stream>>>(b);
+      ITN_LAUNCH_CHECK(ctx);
+      k_benv_reduce<true><<<(unsigned)(nj * 3), 256, 0, ctx->stream>>>(fc->part, (double* const*)(dt + 3 * nj), d);
+    } else {
+      const size_t smem = (size_t)(3 * kTilesPerCta + 1) * (256 + 2) * sizeof(double);
+      CUDA_CHECK(cudaFuncSetAttribute(k_benv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_CHECK(cudaFuncSetAttribute(k_benv<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      k_benv<false><<<grid, kThreads, smem, ctx->stream>>>(b);
+      ITN_LAUNCH_CHECK(ctx);
+      k_benv_reduce<false><<<(unsigned)(nj * 3), 256, 0, ctx->stream>>>(fc->part, (double* const*)(dt + 3 * nj), d);
+    }
     ITN_LAUNCH_CHECK(ctx);
-    k_benv_reduce<true><<<(unsigned)(nj * 3), 256, 0, ctx->stream>>>(part.as<double>(), (double* const*)(dt + 3 * nj), d);
-  } else {
-    const size_t smem = (size_t)(3 * kTilesPerCta + 1) * (256 + 2) * sizeof(double);
-    CUDA_CHECK(cudaFuncSetAttribute(k_benv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_CHECK(cudaFuncSetAttribute(k_benv<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    k_benv<false><<<grid, kThreads, smem, ctx->stream>>>(b);
-    ITN_LAUNCH_CHECK(ctx);
-    k_benv_reduce<false><<<(unsigned)(nj * 3), 256, 0, ctx->stream>>>(part.as<double>(), (double* const*)(dt + 3 * nj), d);
   }
-  ITN_LAUNCH_CHECK(ctx);
 }
 
 // New site tensors after the gate: out (canonical layout, bond `slot` now chi_new <= 16) = A . T on the fused (s, l) index.

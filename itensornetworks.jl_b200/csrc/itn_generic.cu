@@ -726,7 +726,7 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
     long long Lacc = 1;
     for (int q = 0; q < nclosed; ++q) {
       int m = order[q];
-      if (m >= 1) {
+      if (m >= 1 && !sp.no_messages) {
         int e = net->inc[v][m - 1];
         const DevTensor& msg = net->M[net->msg_into(v, e)];
         const double* ovr = sp.mats ? sp.mats[m - 1] : nullptr;

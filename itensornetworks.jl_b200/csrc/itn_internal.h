@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -197,6 +200,8 @@ struct JobSpec {
   double* out;         // device, planar No x No
   // optional: mats[k] != nullptr replaces the incoming message on bond slot k (planar chi x chi, device)
   const double* const* mats = nullptr;
+  // true: no message is absorbed on any closed bond (plain Gram matrix of the site tensor over the closed modes)
+  bool no_messages = false;
 };
 // Runs all specs in [lo, hi) batches bounded by the workspace budget. Results in spec.out.
 void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs);
@@ -301,6 +306,26 @@ static inline T* itn_upload(itn_ctx* ctx, const std::vector<T>& h, DevBuf& buf) 
   // runtime, so this is safe for std::vector sources.
   return (T*)buf.p;
 }
+
+// ITN_TRACE=1: host-side phase times of an entry point on stderr (where the host keeps the GPU waiting)
+struct HostTrace {
+  bool on;
+  const char* what;
+  std::chrono::steady_clock::time_point last;
+  std::string line;
+  explicit HostTrace(const char* w) : on(getenv("ITN_TRACE") != nullptr), what(w), last(std::chrono::steady_clock::now()) {}
+  void mark(const char* phase) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof buf, " %s %.2f", phase, std::chrono::duration<double, std::milli>(now - last).count());
+    line += buf;
+    last = now;
+  }
+  ~HostTrace() {
+    if (on) fprintf(stderr, "[itn trace] %s host ms:%s\n", what, line.c_str());
+  }
+};
 
 #define ITN_LAUNCH_CHECK(ctx)                                                        \
   do {                                                                               \

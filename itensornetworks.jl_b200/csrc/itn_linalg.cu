@@ -1858,25 +1858,6 @@ void itn_dev_map_eigvals(itn_ctx* ctx, bool cplx, int fn, int chi, int n, const 
   ITN_LAUNCH_CHECK(ctx);
 }
 
-// ITN_TRACE=1: host-side phase times of itn_apply2 on stderr (where the host keeps the GPU waiting)
-struct HostTrace {
-  bool on;
-  std::chrono::steady_clock::time_point last;
-  std::string line;
-  HostTrace() : on(getenv("ITN_TRACE") != nullptr), last(std::chrono::steady_clock::now()) {}
-  void mark(const char* what) {
-    if (!on) return;
-    const auto now = std::chrono::steady_clock::now();
-    char buf[96];
-    snprintf(buf, sizeof buf, " %s %.2f", what, std::chrono::duration<double, std::milli>(now - last).count());
-    line += buf;
-    last = now;
-  }
-  ~HostTrace() {
-    if (on) fprintf(stderr, "[itn trace] apply2 host ms:%s\n", line.c_str());
-  }
-};
-
 #define API_BEGIN try {
 #define API_END                              \
   }                                          \
@@ -2022,7 +2003,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
                       "environment message into vertex " + std::to_string(v) + " is not set (update the BP cache first)");
     }
   }
-  HostTrace trace;
+  HostTrace trace("apply2");
   trace.mark("validate");
   // ---- geometry of every gate (global metadata), role of this rank ----
   enum { NONE = 0, OWNER = 1, GUEST = 2 };
@@ -2644,8 +2625,10 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       }
     }
   }
+  trace.mark("alloc_new");
   {
     itn_fast_rebuild(net, fast_reb);
+    trace.mark("tile_rebuild");
     if (!slow_sites.empty()) {
       DevBuf sb(ctx, slow_sites.size() * sizeof(SuSite));
       const SuSite* ds = itn_upload(ctx, slow_sites, sb);

@@ -60,6 +60,7 @@ _SIGS = {
     "itn_apply2": (C.c_int, [_vp, _i32p, C.c_int, _vp, C.c_int, C.c_double, C.c_int, C.c_int, _i32p, _dp, _dp, C.c_int]),
     "itn_apply_layers": (C.c_int, [_vp, C.c_int, _i32p, _i32p, _vp, C.c_int, C.c_double, C.c_int, C.c_int, _i32p, _i32p, C.c_int,
                                    _i32p, C.c_int, C.c_int, C.c_double, C.c_int, _i32p, _dp, _dp, C.c_int, _i32p]),
+    "itn_gauge_walk": (C.c_int, [_vp, _i32p, _i32p, C.c_int]),
     "itn_map_eigvals": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double]),
     "itn_tensordot": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i32p, _vp, C.c_int, _i32p, C.c_int, _i32p, _i32p, _vp]),
     "itn_svd_batch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _dp, _vp, C.c_int, _dp]),

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import ITNError, check, i32, lib
-from .graphs import default_edge_sequence
+from .graphs import default_edge_sequence, tree_gauge_sequence
 from .network import ITensorNetwork
 
 _DTYPE_CODE = {np.dtype(np.float64): 0, np.dtype(np.complex128): 1}
@@ -571,14 +571,45 @@ def expect2(bpc, edges, op_u, op_v):
 # ---------------------------------------------------------------------------------------------
 
 
-def apply(gate, bpc, verts, maxdim=None, cutoff=None, normalize=False, callback=None, inplace=False, msg_mode=0):
-    """apply(o, psi; envs, maxdim, cutoff, normalize, callback) (src/apply.jl:97-146) on a BP cache:
-    the product environment is the cache's current messages.  `verts` = (v,) or (v1, v2)."""
+def gauge_walk(bpc, edges, inplace=False):
+    """gauge_walk(tn, edges) (src/abstractitensornetwork.jl:387-393): qr!(tn, u => v) for every (u, v) of `edges`, on the
+    device (itn_gauge_walk).  The messages of the cache are left as they are (they belong to the old gauge)."""
+    out = bpc if inplace else bpc.copy()
+    edges = [(int(u), int(v)) for u, v in edges]
+    for u, v in edges:
+        if not bpc.graph.has_edge(u, v):
+            raise ITNError(1, "Edge not in graph.")
+    a_s, ps = i32([u for u, _ in edges])
+    a_d, pd = i32([v for _, v in edges])
+    check(lib().itn_gauge_walk(out.h, ps, pd, len(edges)))
+    del a_s, a_d
+    return out
+
+
+def tree_gauge(bpc, region, inplace=False):
+    """tree_gauge(psi, region) (src/abstractitensornetwork.jl:407-418): move the gauge of the whole network towards
+    `region` (a vertex or a list of vertices), treating the network as the tree spanned by a spanning tree."""
+    return gauge_walk(bpc, tree_gauge_sequence(bpc.graph, region), inplace=inplace)
+
+
+tree_orthogonalize = tree_gauge  # src/abstractitensornetwork.jl:420
+
+
+def apply(gate, bpc, verts, maxdim=None, cutoff=None, normalize=False, callback=None, inplace=False, msg_mode=0,
+          ortho=False):
+    """apply(o, psi; envs, maxdim, cutoff, normalize, ortho, callback) (src/apply.jl:97-146) on a BP cache:
+    the product environment is the cache's current messages.  `verts` = (v,) or (v1, v2).  ortho=True first gauges the
+    network towards verts[0] (tree_orthogonalize, :109-111 and :130-132); as in the reference the environments are whatever
+    the caller holds (the default `envs = ITensor[]` of the reference is a cache with identity messages)."""
     verts = tuple(int(v) for v in verts)
     if bpc.partition is not None:
         raise ITNError(1, "`apply` requires a product environment (`envs` with no shared edges); the cache groups several "
                           "sites per partition. Contract `envs` to product form before calling.")
+    if len(verts) == 2 and not bpc.graph.has_edge(*verts):
+        raise ITNError(1, "Vertices where the gates are being applied must be neighbors for now.")
     out = bpc if inplace else bpc.copy()
+    if ortho and len(verts) in (1, 2):
+        tree_gauge(out, verts[0], inplace=True)
     if len(verts) == 1:
         g = np.asfortranarray(np.asarray(gate, dtype=bpc.dtype))
         _, pv = i32(verts)

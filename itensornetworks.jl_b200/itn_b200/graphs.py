@@ -167,6 +167,32 @@ def default_edge_sequence(g):
     return seq
 
 
+def tree_gauge_sequence(g, region):
+    """edge_sequence_between_regions(g, vertices(g), region) (src/abstractitensornetwork.jl:399-405): the (child, parent)
+    edges, in post-order from region[0], of a spanning tree (the graph itself when it is a tree), without the edges
+    inside `region` -- the walk of tree_gauge / tree_orthogonalize."""
+    region = [int(region)] if isinstance(region, (int,)) or not hasattr(region, "__iter__") else [int(v) for v in region]
+    if set(region) == set(range(g.nv)) or g.ne == 0:
+        return []
+    sys.setrecursionlimit(max(10000, 4 * g.nv))
+    adj = {}
+    for e in forest_cover(g)[0]:
+        u, v = g.edges[e]
+        adj.setdefault(u, []).append(v)
+        adj.setdefault(v, []).append(u)
+    out = []
+
+    def rec(x, parent):
+        for y in adj.get(x, []):
+            if y != parent:
+                rec(y, x)
+                out.append((y, x))
+
+    rec(region[0], -1)
+    rs = set(region)
+    return [(a, b) for (a, b) in out if not (a in rs and b in rs)]
+
+
 def parallel_edge_sequence(g):
     """edge_sequence(::Algorithm"parallel") (src/edge_sequences.jl:49-51): one group per directed edge."""
     return [[e] for e in list(g.edges) + [(v, u) for (u, v) in g.edges]]

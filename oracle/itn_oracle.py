@@ -679,6 +679,72 @@ def simple_update_bp(net, msgs, e, gate, maxdim=None, cutoff=None, normalize=Fal
     return new, dict(svals=sv, truncerr=truncerr, newdim=n)
 
 
+# ----------------------------------------------------------------------------------------
+# tree gauge  (abstractitensornetwork.jl:376-420) and apply(...; ortho = true)  (apply.jl:109-111, 130-132)
+# ----------------------------------------------------------------------------------------
+
+
+def qr_edge(net, u, v):
+    """qr!(tn, u => v) (abstractitensornetwork.jl:376-385): Q of the tensor at u over (all its other indices) -> bond
+    replaces it, R is multiplied into the tensor at v.  In place on a copy; returns the new network."""
+    g = net.graph
+    e = g.eid[(u, v)]
+    new = net.copy()
+    a = net.tensors[u]
+    k = 1 + g.slot(u, e)
+    am = np.moveaxis(a, k, -1)
+    q, r = np.linalg.qr(am.reshape(-1, am.shape[-1]), mode="reduced")
+    chi = am.shape[-1]
+    if q.shape[1] < chi:  # fewer rows than bond states: pad with zero columns so that the bond keeps its extent
+        q = np.concatenate([q, np.zeros((q.shape[0], chi - q.shape[1]), dtype=q.dtype)], axis=1)
+        r = np.concatenate([r, np.zeros((chi - r.shape[0], chi), dtype=r.dtype)], axis=0)
+    new.tensors[u] = np.ascontiguousarray(np.moveaxis(q.reshape(am.shape), -1, k).astype(net.dtype))
+    kb = 1 + g.slot(v, e)
+    b = np.moveaxis(net.tensors[v], kb, 0)
+    b2 = np.tensordot(r, b, axes=([1], [0]))
+    new.tensors[v] = np.ascontiguousarray(np.moveaxis(b2, 0, kb).astype(net.dtype))
+    return new
+
+
+def gauge_walk(net, edges):
+    """gauge_walk(tn, edges) (abstractitensornetwork.jl:387-393)."""
+    for (u, v) in edges:
+        net = qr_edge(net, u, v)
+    return net
+
+
+def spanning_tree_edges(g: Graph):
+    """Edge ids of a breadth-first spanning forest (the tree itself when g is a tree): the `steiner_tree` of all vertices
+    in edge_sequence_between_regions (abstractitensornetwork.jl:399-405); on a loopy graph which spanning tree the
+    un-vendored routine picks is unpinned, and the host passes the explicit sequence to the engine."""
+    return forest_cover(g)[0] if g.ne else []
+
+
+def tree_gauge_sequence(g: Graph, region):
+    """Edges (child, parent) that move the gauge from everywhere to `region` (a vertex or a list of vertices):
+    post-order DFS edges of the spanning tree rooted at region[0], without the edges inside the region
+    (edge_sequence_between_regions, abstractitensornetwork.jl:399-405)."""
+    region = [region] if np.isscalar(region) else list(region)
+    if set(region) == set(range(g.nv)):
+        return []
+    te = _post_order_dfs_edges(g.nv, spanning_tree_edges(g), g.edges, region[0])
+    rs = set(region)
+    return [(a, b) for (a, b) in te if not (a in rs and b in rs)]
+
+
+def tree_orthogonalize(net, region):
+    """tree_orthogonalize(psi, region) = tree_gauge(psi, region) (abstractitensornetwork.jl:407-420)."""
+    return gauge_walk(net, tree_gauge_sequence(net.graph, region))
+
+
+def apply2_ortho(net, e, gate, maxdim=None, cutoff=None, normalize=False):
+    """apply(o, psi; ortho = true) on the edge e with the default `envs = ITensor[]` (apply.jl:97-139): gauge the tree
+    towards the first gate vertex, then simple_update_bp with no environments (identity messages)."""
+    v1, _ = net.graph.edges[e]
+    net = tree_orthogonalize(net, v1)
+    return simple_update_bp(net, identity_messages(net), e, gate, maxdim=maxdim, cutoff=cutoff, normalize=normalize)
+
+
 def reset_edge_messages(net, msgs, e):
     """Engine convention after a gate changed a bond: both directed messages on e restart from identity."""
     msgs = dict(msgs)

@@ -1,0 +1,11 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh LOGFILE [gpurun options] -- 'command'
+# Retries while gpurun answers "busy" (exit code 3: nothing charged), at most 40 times, 90 s apart.
+log="$1"; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3
