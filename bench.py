@@ -638,9 +638,9 @@ def bench_simple_update(E, bpc, graph, chi, d, dtype, stream, torch, dist=None, 
     m = rng.standard_normal((d * d, d * d)) + (1j * rng.standard_normal((d * d, d * d)) if np.dtype(dtype).kind == "c" else 0)
     h = (m + m.conj().T) / 2
     w, v = np.linalg.eigh(h)
-    # exp(-i tau H): a real-time (unitary) Trotter gate, so that repeated steps keep the state well scaled -- an
-    # un-normalised imaginary-time gate lets the tensors drift towards under/overflow after a few steps, and the gate
-    # path then spends its time in the rank-deficient fall-backs instead of the kernels being measured
+    # exp(-i tau H): a real-time (unitary) Trotter gate; repeated steps keep the state well scaled.  (The slow-down after a
+    # few BP-gauged steps that round 2 first blamed on the gate was the phase drift of the BP messages, DESIGN.md
+    # section 3b / tests/test_phase_drift.py: fixed in the engine, k_commit keeps the Hermitian part.)
     if np.dtype(dtype).kind == "c":
         gate = ((v * np.exp(-0.05j * w)) @ v.conj().T).astype(dtype).reshape(d, d, d, d)
     else:

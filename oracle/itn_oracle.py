@@ -326,8 +326,13 @@ def absorbed_ket(net, msgs, v, skip_edges=()):
     return b
 
 
-def updated_message(net, msgs, v, w, normalize=True):
-    """M_{v->w}[l, l'] = sum A_v[s,..a..,l] conj(A_v[s,..a'..,l']) prod_{u != w} M_{u->v}[a,a']."""
+def updated_message(net, msgs, v, w, normalize=True, hermitize=False):
+    """M_{v->w}[l, l'] = sum A_v[s,..a..,l] conj(A_v[s,..a'..,l']) prod_{u != w} M_{u->v}[a,a'].
+
+    hermitize (NOT in the reference; the engine's stabilisation, csrc/itn_generic.cu k_commit): keep the Hermitian part
+    of the new message of a norm network.  The update is multilinear in the incoming messages, so the complex phases of
+    the messages add up along the graph and grow like (z - 1)^sweeps from rounding level; the Frobenius normalisation of
+    the reference does not remove them (tests/test_phase_drift.py measures it on this restatement)."""
     g = net.graph
     e = g.eid[(v, w)]
     k = g.slot(v, e)
@@ -335,6 +340,8 @@ def updated_message(net, msgs, v, w, normalize=True):
     b = absorbed_ket(net, msgs, v, skip_edges=(e,))
     axes = [i for i in range(a.ndim) if i != 1 + k]
     m = np.tensordot(b, a.conj(), axes=(axes, axes))
+    if hermitize and net.bra is None:
+        m = 0.5 * (m + m.conj().T)
     if normalize:
         n = np.linalg.norm(m)
         if n != 0:
@@ -367,7 +374,7 @@ def message_diff(a, b):
 
 
 def bp_update(net, msgs, seq=None, groups=None, maxiter=1, tol=None, normalize=True,
-              return_history=False):
+              return_history=False, hermitize=False):
     """update(::Algorithm"bp") (abstractbeliefpropagationcache.jl:272-329).
 
     seq    : list of directed edges (v, w)
@@ -388,7 +395,7 @@ def bp_update(net, msgs, seq=None, groups=None, maxiter=1, tol=None, normalize=T
         diff = 0.0
         if groups is None:
             for (v, w) in seq:
-                new = updated_message(net, msgs, v, w, normalize)
+                new = updated_message(net, msgs, v, w, normalize, hermitize)
                 if tol is not None:
                     diff += message_diff(new, msgs[(v, w)])
                 msgs[(v, w)] = new
@@ -397,7 +404,7 @@ def bp_update(net, msgs, seq=None, groups=None, maxiter=1, tol=None, normalize=T
             for (lo, hi) in groups:
                 scratch = dict(msgs)
                 for (v, w) in seq[lo:hi]:
-                    new = updated_message(net, scratch, v, w, normalize)
+                    new = updated_message(net, scratch, v, w, normalize, hermitize)
                     if tol is not None:
                         diff += message_diff(new, scratch[(v, w)])
                     scratch[(v, w)] = new
