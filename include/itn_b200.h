@@ -64,6 +64,11 @@ int itn_ctx_sync(itn_ctx* ctx);
  * (the reference is single-process). */
 int itn_nccl_unique_id(void* out_128_bytes);
 int itn_ctx_init_dist(itn_ctx* ctx, int rank, int nranks, const void* id_128_bytes);
+/* Single-process multi-GPU: n contexts on n distinct devices with communicators from one
+ * ncclCommInitAll; out_n[i] is rank i of n.  Collective entry points may wait for their peers on the host: drive every
+ * context from its own host thread (one Julia task / Python thread per GPU), as one would drive one process per GPU. */
+int itn_ctx_create_group(int n, const int32_t* devices, itn_ctx** out_n);
+int itn_ctx_rank(const itn_ctx* ctx, int32_t* rank, int32_t* nranks);
 
 /* ---- network = partitioned <psi|psi> tensor network + messages ----------------------------
  * Replaces BeliefPropagationCache(ptn; messages) (src/caches/beliefpropagationcache.jl:13-35) over

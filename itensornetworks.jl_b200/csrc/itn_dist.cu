@@ -23,6 +23,7 @@ struct NcclApi {
   void* lib = nullptr;
   decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclSend) Send = nullptr;
   decltype(&ncclRecv) Recv = nullptr;
@@ -44,7 +45,7 @@ NcclApi& api() {
 #define LOAD(sym)                                                                                   \
   a.sym = (decltype(a.sym))dlsym(a.lib, "nccl" #sym);                                               \
   if (!a.sym) throw ItnError(ITN_ENCCL, "libnccl is missing symbol nccl" #sym);
-  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(Send) LOAD(Recv) LOAD(GroupStart) LOAD(GroupEnd)
+  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommInitAll) LOAD(CommDestroy) LOAD(Send) LOAD(Recv) LOAD(GroupStart) LOAD(GroupEnd)
   LOAD(AllReduce) LOAD(GetErrorString)
 #undef LOAD
   return a;
@@ -246,5 +247,53 @@ extern "C" int itn_ctx_init_dist(itn_ctx* ctx, int rank, int nranks, const void*
   ctx->nccl_lib = api().lib;
   ctx->rank = rank;
   ctx->nranks = nranks;
+  API_END
+}
+
+// Single-process multi-GPU ("so Julia needs no MPI"): n contexts, one per listed device, whose
+// communicators come from one ncclCommInitAll call; context i is rank i of n.  Every entry point that involves an
+// exchange (itn_bp_update, itn_apply2, itn_rdm2, ...) is collective and may wait on the host for its peers, so the
+// caller drives each context from its own host thread (Threads.@spawn per GPU in Julia, a Python thread per GPU in
+// tests/test_gpu_dist.py) exactly as it would drive one process per GPU.
+extern "C" int itn_ctx_create_group(int n, const int32_t* devices, itn_ctx** out_n) {
+  API_BEGIN
+  ITN_REQUIRE(n >= 1 && devices && out_n, ITN_EINVAL, "bad arguments");
+  std::vector<int> devs(devices, devices + n);
+  {
+    std::vector<int> sorted = devs;
+    std::sort(sorted.begin(), sorted.end());
+    ITN_REQUIRE(std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end(), ITN_EINVAL,
+                "itn_ctx_create_group: every context needs its own device");
+  }
+  std::vector<itn_ctx*> ctxs(n, nullptr);
+  std::vector<ncclComm_t> comms(n, nullptr);
+  try {
+    for (int i = 0; i < n; ++i) {
+      const int st = itn_ctx_create(devs[i], nullptr, &ctxs[i]);
+      if (st != ITN_OK) throw ItnError(st, itn_last_error());
+    }
+    if (n > 1) NCCL_CHECK(api().CommInitAll(comms.data(), n, devs.data()));
+  } catch (...) {
+    for (itn_ctx* c : ctxs)
+      if (c) itn_ctx_destroy(c);
+    throw;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (n > 1) {
+      ctxs[i]->nccl = comms[i];
+      ctxs[i]->nccl_lib = api().lib;
+    }
+    ctxs[i]->rank = i;
+    ctxs[i]->nranks = n;
+    out_n[i] = ctxs[i];
+  }
+  API_END
+}
+
+extern "C" int itn_ctx_rank(const itn_ctx* ctx, int32_t* rank, int32_t* nranks) {
+  API_BEGIN
+  ITN_REQUIRE(ctx, ITN_EINVAL, "NULL argument");
+  if (rank) *rank = ctx->rank;
+  if (nranks) *nranks = ctx->nranks;
   API_END
 }

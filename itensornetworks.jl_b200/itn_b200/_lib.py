@@ -32,6 +32,8 @@ _SIGS = {
     "itn_ctx_sync": (C.c_int, [_vp]),
     "itn_nccl_unique_id": (C.c_int, [_vp]),
     "itn_ctx_init_dist": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "itn_ctx_create_group": (C.c_int, [C.c_int, _i32p, C.POINTER(_vp)]),
+    "itn_ctx_rank": (C.c_int, [_vp, _i32p, _i32p]),
     "itn_net_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, C.POINTER(_vp)]),
     "itn_net_clone": (C.c_int, [_vp, C.POINTER(_vp)]),
     "itn_net_destroy": (C.c_int, [_vp]),

@@ -40,6 +40,24 @@ class Context:
         self.device = device
         self.rank, self.world = 0, 1  # set by itn_b200.init_distributed
 
+    @classmethod
+    def group(cls, devices):
+        """Single-process multi-GPU: one context per listed device, rank i of n = position in the list, communicators from
+        one ncclCommInitAll (itn_ctx_create_group).  Collective calls (update, apply on cut edges, rdm2 on cut edges, ...)
+        must be issued by one host thread per context."""
+        devices = [int(d) for d in devices]
+        arr, pd = i32(devices)
+        hs = (C.c_void_p * len(devices))()
+        check(lib().itn_ctx_create_group(len(devices), pd, hs))
+        out = []
+        for i, d in enumerate(devices):
+            c = cls.__new__(cls)
+            c.h = C.c_void_p(hs[i])
+            c.device = d
+            c.rank, c.world = i, len(devices)
+            out.append(c)
+        return out
+
     def sync(self):
         check(lib().itn_ctx_sync(self.h))
 

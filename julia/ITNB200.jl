@@ -29,7 +29,7 @@ using ITensors.NDTensors: @Algorithm_str, Algorithm
 using ITensorNetworks: ITensorNetworks, AbstractBeliefPropagationCache, AbstractITensorNetwork, BeliefPropagationCache,
   ITensorNetwork, QuadraticFormNetwork, bra_vertex, default_edge_sequence, default_partitioned_vertices, ket_network,
   ket_vertex, ket_vertices, operator_vertex, original_state_vertex, siteinds, tensornetwork
-using NamedGraphs: NamedEdge
+using NamedGraphs: NamedGraphs, NamedEdge
 using NamedGraphs.PartitionedGraphs: PartitionedGraph, PartitionedGraphs, QuotientEdge, QuotientVertex,
   boundary_quotientedges, quotient_graph, quotientedges, quotientvertices, unpartitioned_graph
 
@@ -48,6 +48,11 @@ mutable struct Context
     out = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:itn_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), device, stream, out))
     ctx = new(out[])
+    finalizer(c -> ccall((:itn_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), ctx)
+    return ctx
+  end
+  function Context(h::Ptr{Cvoid})   # adopts a handle made by itn_ctx_create_group
+    ctx = new(h)
     finalizer(c -> ccall((:itn_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), ctx)
     return ctx
   end
@@ -494,9 +499,9 @@ gate_sites(bpc::B200BeliefPropagationCache, o::ITensor) =
 function ITensors.apply(o::ITensor, ψ::AbstractITensorNetwork; envs::B200Environment, normalize=false, ortho=false,
   callback=Returns(nothing), maxdim=nothing, cutoff=nothing, apply_kwargs...)
   bpc = envs.bpc
-  ortho && error("ortho = true (tree_orthogonalize, src/apply.jl:109-111) is host-side gauge fixing of a tree network: " *
-                 "apply it to psi before building the cache")
   vs = gate_sites(bpc, o)
+  # ortho = true: tree_orthogonalize(psi, v1) before the gate (src/apply.jl:109-111, 130-132), on the device
+  ortho && length(vs) in (1, 2) && tree_orthogonalize!(bpc, vs[1])
   if length(vs) == 1
     v = only(vs)
     s = site_index(bpc, v)
@@ -528,6 +533,45 @@ function ITensors.apply(o::ITensor, ψ::AbstractITensorNetwork; envs::B200Enviro
     error("Gates with more than 2 sites is not supported yet.")
   end
   return ket_network(ITensorNetworks.tensornetwork(bpc))
+end
+
+# gauge_walk(tn, edges) (src/abstractitensornetwork.jl:387-393) on the device tensors: qr!(tn, src => dst) edge by edge
+# (include/itn_b200.h: itn_gauge_walk).  The messages of the cache keep their values (they belong to the old gauge).
+function gauge_walk!(bpc::B200BeliefPropagationCache, es)
+  s = Int32[bpc.vid[src(e)] for e in es]
+  d = Int32[bpc.vid[dst(e)] for e in es]
+  GC.@preserve s d check(ccall((:itn_gauge_walk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Cint),
+    bpc.h, s, d, length(es)))
+  foreach(e -> push!(bpc.stale, src(e), dst(e)), es)
+  return bpc
+end
+
+# tree_gauge / tree_orthogonalize (src/abstractitensornetwork.jl:395-420): the walk is planned by the reference's own
+# edge_sequence_between_regions on the ket graph, the QR steps run on the device
+function tree_orthogonalize!(bpc::B200BeliefPropagationCache, region)
+  region = region isa AbstractVector ? region : [region]
+  g = NamedGraphs.NamedGraph(bpc.verts)                       # graph of the ket network: original vertices, its bonds
+  foreach(e -> Graphs.add_edge!(g, src(e) => dst(e)), bpc.eds)
+  es = ITensorNetworks.edge_sequence_between_regions(g, collect(vertices(g)), region)
+  return gauge_walk!(bpc, es)
+end
+
+# Single-process multi-GPU (include/itn_b200.h: itn_ctx_create_group = ncclCommInitAll): one Context per device, rank i
+# of n = position in `devices`.  Collective calls (update, apply on cut edges, ...) are issued by one task per context,
+# e.g. `Threads.@spawn` per GPU.
+function context_group(devices::Vector{<:Integer})
+  devs = Int32.(devices)
+  hs = Vector{Ptr{Cvoid}}(undef, length(devs))
+  GC.@preserve devs hs check(ccall((:itn_ctx_create_group, LIB), Cint, (Cint, Ptr{Int32}, Ptr{Ptr{Cvoid}}),
+    length(devs), devs, hs))
+  return [Context(h) for h in hs]
+end
+
+function context_rank(ctx::Context)
+  r = Ref{Int32}(0)
+  n = Ref{Int32}(1)
+  check(ccall((:itn_ctx_rank, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), ctx.h, r, n))
+  return Int(r[]), Int(n[])
 end
 
 # One Trotter step in one call (include/itn_b200.h: itn_apply_layers): `layers` is a vector of vectors of two-site gate

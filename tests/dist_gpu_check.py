@@ -1,8 +1,11 @@
-"""torchrun entry: partitioned BP on N GPUs vs the single-process oracle (and observables).
+"""Partitioned BP and gate layers on N GPUs vs the single-process oracle (and observables).
 
+One process per GPU (the layout bench.py's contract launches):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py
-Prints 'DIST_OK' on rank 0 when every rank's stored messages, the all-reduced convergence measure, the region
-scalars and <Z> match the oracle to 1e-10."""
+Single process, one host thread per GPU (itn_ctx_create_group = ncclCommInitAll, SURVEY.md 8b "so Julia needs no MPI"):
+    python tests/dist_gpu_check.py --threads 2
+Prints 'DIST_OK' when every rank's stored messages, the all-reduced convergence measure, the region scalars, <Z>,
+cut-edge RDMs and the gate layers match the oracle to 1e-10."""
 import os
 import sys
 
@@ -13,17 +16,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "itensornetworks.jl_b200"))
 
 
-def main():
-    import torch
-    import torch.distributed as dist
-
-    import itn_b200 as E
-    from oracle import itn_oracle as O
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = E.Context(local)
-    E.init_distributed(ctx, rank, world)
+def run_checks(E, O, ctx, rank, world):
+    """The checks of one rank; every rank (process or thread) runs the same sequence of collective calls."""
     worst = 0.0
     cases = (((6, 4), 3, np.complex128), ((8, 8), 16, np.complex128), ((4, 4), 2, np.float64), ((4, 4, 4), 2, np.complex128))
     for dims, chi, dtype in cases:
@@ -84,6 +78,49 @@ def main():
             E.update(bpc, maxiter=2, edge_sequence=[[e] for e in seq], inplace=True)
         ez = E.expect(bpc, "Z")
         worst = max(worst, max(abs(ez[v] - O.expect1(net, msgs, v, O.PAULI_Z)) for v in range(g.nv)))
+    return worst
+
+
+def main_threads(n):
+    import threading
+
+    import itn_b200 as E
+    from oracle import itn_oracle as O
+    ctxs = E.Context.group(list(range(n)))
+    worst = [None] * n
+    errs = [None] * n
+
+    def work(i):
+        try:
+            worst[i] = run_checks(E, O, ctxs[i], i, n)
+        except BaseException as ex:  # a rank that dies would leave its peers waiting in a collective
+            errs[i] = ex
+            os._exit(3)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    w = max(worst)
+    print(f"single process, {n} threads: worst error over ranks: {w:.3e}")
+    print("DIST_OK" if w < 1e-10 else "DIST_FAIL")
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--threads":
+        return main_threads(int(sys.argv[2]))
+    import torch
+    import torch.distributed as dist
+
+    import itn_b200 as E
+    from oracle import itn_oracle as O
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = E.Context(local)
+    E.init_distributed(ctx, rank, world)
+    worst = run_checks(E, O, ctx, rank, world)
     t = torch.tensor([worst], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

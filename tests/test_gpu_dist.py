@@ -18,3 +18,14 @@ def test_partitioned_bp_and_gates_match_oracle(nproc):
            "--master-port", str(29517 + nproc), os.path.join(ROOT, "tests", "dist_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nthreads", [2])
+def test_single_process_context_group(nthreads):
+    """itn_ctx_create_group (ncclCommInitAll): the same checks from ONE process with one host thread per GPU."""
+    import torch
+    if torch.cuda.device_count() < nthreads:
+        pytest.skip(f"needs {nthreads} GPUs (log of the builder's run: profiles/r2_dist_check_threads2.log)")
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "dist_gpu_check.py"), "--threads", str(nthreads)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
