@@ -1705,12 +1705,18 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
             itn_fast_bp_sweep_range(net, swept, ns);
           }
           itn_fast_bp_sweep_end(net);
-          if (nblock > 0) itn_block_bp_run(net);
+          if (nblock > 0) {
+            itn_block_bp_run(net, false);
+            itn_block_bp_join(net);
+          }
           itn_run_vertex_sweeps(net, vsweeps);
           itn_run_vertex_jobs(net, slow_specs);
         } else if (sync_mode) {
+          // the block buckets (rim vertices of a lattice whose bulk is on the tile path) run on side streams behind the
+          // tile sweep: they read the same pre-sweep messages and write their own staged outputs
+          if (nblock > 0) itn_block_bp_run(net, nfast > 0);
           if (nfast > 0) itn_fast_bp_sweep(net, all_dids, all_src, handled, staged.ptr.data());
-          if (nblock > 0) itn_block_bp_run(net);
+          if (nblock > 0) itn_block_bp_join(net);
           itn_run_vertex_sweeps(net, vsweeps);
           itn_run_vertex_jobs(net, slow_specs);
         } else {

@@ -44,7 +44,7 @@ namespace {
 constexpr int kBT = 256;       // threads per CTA (8 warps)
 constexpr int kNW = kBT / 32;
 constexpr int kMaxGM = 4;      // bonds per group
-constexpr int kMaxOps = 48;
+constexpr int kMaxOps = 24;      // z = 8: 17 operations in pass 2 (12 for the closes of four bonds, 4 + 1 for S)
 constexpr int kRedDoubles = 1024;  // close: partial tiles of the fibre splits before the fixed-order sum (chi <= 16)
 constexpr unsigned kNoFibre = 0xFFFFu;
 
@@ -442,7 +442,7 @@ __device__ __forceinline__ void op_close(const OpConst& O, const int PL, const d
 }
 
 template <bool C, int KS, int MT>
-__global__ void __launch_bounds__(kBT, 2) k_block(const __grid_constant__ BlkPass P, const BlkVertex* __restrict__ gv,
+__global__ void __launch_bounds__(kBT, (KS <= 4 ? 3 : 2)) k_block(const __grid_constant__ BlkPass P, const BlkVertex* __restrict__ gv,
                                                   const unsigned short* __restrict__ gtab) {
   extern __shared__ __align__(128) double sm[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -846,8 +846,27 @@ struct Emitter {
   }
 };
 
-constexpr size_t kSmemTwoCtas = 113 * 1024;
-constexpr size_t kSmemOneCta = 226 * 1024;
+// dynamic shared memory that still lets two CTAs share an SM: 228 KB per SM, 1 KB reserved per CTA, and the kernel's
+// 2176 bytes of static shared memory (sOp, sKoff, mbar) -- 113 KB, the round-2 value, silently dropped the chi = 8 pass 2
+// and the chi = 16 pass 3 (114.6 / 113.3 KB) to one CTA per SM
+bool block_debug() {
+  static const bool on = getenv("ITN_BLOCK_DEBUG") != nullptr;
+  return on;
+}
+
+constexpr size_t kStaticSmem = 2176;
+constexpr size_t kSmemTwoCtasMax = 228 * 1024 / 2 - 1024 - kStaticSmem;
+constexpr size_t kSmemThreeCtasMax = 228 * 1024 / 3 - 1024 - kStaticSmem;
+constexpr size_t kSmemOneCta = 227 * 1024 - kStaticSmem;
+// Resident CTAs per SM the planner sizes the blocks for.  The instances with at most four k4 steps (chi <= 8 complex,
+// chi <= 16 real) compile to <= 80 registers (__launch_bounds__(256, 3)), so three CTAs fit when the block is sized for a
+// third of the shared memory; ITN_BLOCK_CTAS = 2 | 3 overrides the default (experiments).
+int target_ctas(int ks_inst) {
+  static const int env = getenv("ITN_BLOCK_CTAS") ? atoi(getenv("ITN_BLOCK_CTAS")) : 0;
+  if (ks_inst > 4) return 2;
+  return env == 2 ? 2 : 3;  // measured (B200): 12^3 chi = 6 sweep 12.09 -> 11.25 ms, 32 x 32 chi = 8 sweep 0.599 -> 0.589 ms
+}
+thread_local size_t kSmemTwoCtas = kSmemTwoCtasMax;  // budget of the plan being made (set by choose_pass)
 
 size_t pass_smem(const BlkPass& P, size_t tab_len) {
   return (size_t)P.nbuf * P.bufsz * sizeof(double) + kRedDoubles * sizeof(double) + (size_t)P.msg_len * sizeof(double) +
@@ -1112,6 +1131,7 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
 // would not cover the SMs; then the paddings with the fewest excess wavefronts.
 bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, size_t nverts, PassPlan& best) {
   const bool aligned = cplx && ks_inst >= 8;
+  kSmemTwoCtas = target_ctas(ks_inst) == 3 ? kSmemThreeCtasMax : kSmemTwoCtasMax;
   const int z = sg.z, d = sg.d;
   long long L = d, XR = 1;
   for (int k = 0; k < h; ++k) L *= sg.chi[k];
@@ -1132,6 +1152,7 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, 
     }
   }
   int best_chunk = -1;
+  bool best_two = false;
   double best_score = -1;
   for (long long c = 1; c <= range; ++c) {
     if (range % c) continue;
@@ -1143,20 +1164,34 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, 
     t.pad_plane = 6;
     if (!plan_pass(sg, h, which, cplx, ks_inst, t, false, pp)) continue;
     if (pp.smem > kSmemOneCta) continue;
+    if (pp.smem > kSmemTwoCtas && pp.smem < kSmemTwoCtas + kSmemTwoCtas / 8) {
+      // the estimate (room for every padding, table lengths rounded up) is within reach of two CTAs per SM: plan exactly
+      PassPlan ex;
+      PassChoice t0 = ch;
+      t0.chunk = (int)c;
+      const bool okx = plan_pass(sg, h, which, cplx, ks_inst, t0, true, ex);
+      if (block_debug()) fprintf(stderr, "      exact plan of chunk %lld: ok %d smem %zu msgs %d\n", c, (int)okx, ex.smem, ex.desc.msg_smem);
+      if (okx && ex.smem <= kSmemTwoCtas) pp = std::move(ex);
+    }
     const long long nb = (fast ? L : XR) * c;
     const long long ctas = (long long)pp.desc.nblk * (long long)nverts;
     const bool two = pp.smem <= kSmemTwoCtas;
     double score = std::min<double>((double)nb, 4096.0);
-    if (!two) score *= 0.3;
+    if (!two) score *= 0.2;  // one CTA of 8 warps per SM hides neither the staging nor the DMMA latency
     if (!fast && c * 8 < 64) score *= 0.5 + c / 16.0;  // short HBM rows waste sectors and bulk-copy issue slots
     if (ctas < 296) score *= ((double)ctas / 296.0) * 0.9 + 0.1;
+    if (block_debug())
+      fprintf(stderr, "      pass %d candidate chunk %lld: smem %zu (%s, msgs %s) score %.0f\n", which + 1, c, pp.smem,
+              two ? "2 CTAs/SM" : "1 CTA/SM", pp.desc.msg_smem ? "staged" : "global", score);
     if (score > best_score) {
       best_score = score;
       best_chunk = (int)c;
+      best_two = two;
     }
   }
   if (best_chunk < 0) return false;
   ch.chunk = best_chunk;
+  const bool want_two = best_two;
   bool mixed_steps = false;  // packed complex stacking with a k step that straddles the planes
   if (cplx && !aligned)
     for (int k = fast ? 0 : h; k < (fast ? h : z); ++k) mixed_steps = mixed_steps || (sg.chi[k] % 4) != 0;
@@ -1171,7 +1206,7 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, 
       t.pad_chunk = pc;
       t.pad_plane = pl;
       if (!plan_pass(sg, h, which, cplx, ks_inst, t, true, pp)) continue;
-      if (pp.smem > kSmemOneCta) continue;
+      if (pp.smem > (want_two ? kSmemTwoCtas : kSmemOneCta)) continue;
       const double ex = (double)pp.excess + 1e-3 * (pc + pl);
       if (ex < best_ex) {
         best_ex = ex;
@@ -1210,11 +1245,6 @@ struct GeomKey {
   int fill;  // 0: few vertices (the block size is shrunk so that the launch still covers the SMs), 1: plenty
   bool operator<(const GeomKey& o) const { return std::tie(sig, cplx, fill) < std::tie(o.sig, o.cplx, o.fill); }
 };
-
-bool block_debug() {
-  static const bool on = getenv("ITN_BLOCK_DEBUG") != nullptr;
-  return on;
-}
 
 const Geometry* geometry_for(const Signature& s, bool cplx, size_t nverts) {
   static std::map<GeomKey, std::unique_ptr<Geometry>> cache;
@@ -1274,6 +1304,13 @@ struct BlockCache {
   std::map<const Geometry*, Bucket> buckets;
   std::vector<Bucket*> active;
   std::vector<int> vbucket;
+  // the buckets of a sweep are independent (they read the pre-sweep messages and write their own staged outputs): all
+  // but the largest run on side streams, forked from and joined to the context stream with events, so that the few CTAs
+  // of the corner / rim / degree-2 buckets fill the SMs the main bucket leaves idle instead of running one after another
+  std::vector<cudaStream_t> side;
+  cudaEvent_t fork = nullptr;
+  std::vector<cudaEvent_t> join;
+  size_t pending_joins = 0;
 };
 
 bool signature_of(const itn_net* net, int v, Signature& s) {
@@ -1290,30 +1327,31 @@ bool signature_of(const itn_net* net, int v, Signature& s) {
 }
 
 template <bool C, int KS, int MT>
-void launch_inst(itn_ctx* ctx, unsigned grid, size_t smem, const BlkPass* dp, const BlkVertex* dv, const unsigned short* dt) {
+void launch_inst(itn_ctx* ctx, cudaStream_t st, unsigned grid, size_t smem, const BlkPass* dp, const BlkVertex* dv,
+                 const unsigned short* dt) {
   CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  k_block<C, KS, MT><<<grid, kBT, smem, ctx->stream>>>(*dp, dv, dt);  // the descriptor travels as a kernel parameter
+  k_block<C, KS, MT><<<grid, kBT, smem, st>>>(*dp, dv, dt);  // the descriptor travels as a kernel parameter
   ITN_LAUNCH_CHECK(ctx);
 }
 
-void launch_pass(itn_ctx* ctx, bool cplx, int KS, unsigned grid, size_t smem, const BlkPass* dp, const BlkVertex* dv,
-                 const unsigned short* dt) {
+void launch_pass(itn_ctx* ctx, cudaStream_t st, bool cplx, int KS, unsigned grid, size_t smem, const BlkPass* dp,
+                 const BlkVertex* dv, const unsigned short* dt) {
   if (cplx) {
     switch (KS) {
-      case 1: return launch_inst<true, 1, 1>(ctx, grid, smem, dp, dv, dt);
-      case 2: return launch_inst<true, 2, 1>(ctx, grid, smem, dp, dv, dt);
-      case 3: return launch_inst<true, 3, 1>(ctx, grid, smem, dp, dv, dt);
-      case 4: return launch_inst<true, 4, 1>(ctx, grid, smem, dp, dv, dt);
-      case 8: return launch_inst<true, 8, 2>(ctx, grid, smem, dp, dv, dt);
-      default: return launch_inst<true, 16, 4>(ctx, grid, smem, dp, dv, dt);
+      case 1: return launch_inst<true, 1, 1>(ctx, st, grid, smem, dp, dv, dt);
+      case 2: return launch_inst<true, 2, 1>(ctx, st, grid, smem, dp, dv, dt);
+      case 3: return launch_inst<true, 3, 1>(ctx, st, grid, smem, dp, dv, dt);
+      case 4: return launch_inst<true, 4, 1>(ctx, st, grid, smem, dp, dv, dt);
+      case 8: return launch_inst<true, 8, 2>(ctx, st, grid, smem, dp, dv, dt);
+      default: return launch_inst<true, 16, 4>(ctx, st, grid, smem, dp, dv, dt);
     }
   } else {
     switch (KS) {
-      case 1: return launch_inst<false, 1, 1>(ctx, grid, smem, dp, dv, dt);
-      case 2: return launch_inst<false, 2, 1>(ctx, grid, smem, dp, dv, dt);
-      case 4: return launch_inst<false, 4, 2>(ctx, grid, smem, dp, dv, dt);
-      default: return launch_inst<false, 8, 4>(ctx, grid, smem, dp, dv, dt);
+      case 1: return launch_inst<false, 1, 1>(ctx, st, grid, smem, dp, dv, dt);
+      case 2: return launch_inst<false, 2, 1>(ctx, st, grid, smem, dp, dv, dt);
+      case 4: return launch_inst<false, 4, 2>(ctx, st, grid, smem, dp, dv, dt);
+      default: return launch_inst<false, 8, 4>(ctx, st, grid, smem, dp, dv, dt);
     }
   }
 }
@@ -1336,6 +1374,9 @@ void itn_block_release(itn_net* net) {
     end_call(b);
     for (auto& t : b.d_tab) itn_dev_free(net->ctx, t);
   }
+  for (cudaStream_t st : bc->side) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : bc->join) cudaEventDestroy(ev);
+  if (bc->fork) cudaEventDestroy(bc->fork);
   delete bc;
   net->block = nullptr;
 }
@@ -1452,24 +1493,60 @@ void itn_block_bp_begin(itn_net* net, const std::vector<int>& dids, const std::v
   }
 }
 
-void itn_block_bp_run(itn_net* net) {
+// all_side: the caller is about to enqueue other work of the same sweep on the context stream (the tile path): every
+// bucket goes to a side stream.  The context stream picks the results up in itn_block_bp_join.
+void itn_block_bp_run(itn_net* net, bool all_side) {
   BlockCache* bc = (BlockCache*)net->block;
   if (!bc) return;
   itn_ctx* ctx = net->ctx;
-  for (Bucket* bp : bc->active) {
-    Bucket& b = *bp;
+  static const bool serial = getenv("ITN_BLOCK_SERIAL") != nullptr;  // experiments: every bucket on the context stream
+  // largest bucket (by tensor elements) on the context stream, the others on side streams
+  std::vector<Bucket*> order(bc->active.begin(), bc->active.end());
+  std::stable_sort(order.begin(), order.end(), [](const Bucket* a, const Bucket* b) {
+    return (double)a->verts.size() * (double)a->geo->nelem > (double)b->verts.size() * (double)b->geo->nelem;
+  });
+  if (all_side && !serial) order.insert(order.begin(), nullptr);  // nobody on the context stream
+  const size_t nside = (serial || order.size() < 2) ? 0 : order.size() - 1;
+  bc->pending_joins = 0;
+  if (nside) {
+    if (!bc->fork) CUDA_CHECK(cudaEventCreateWithFlags(&bc->fork, cudaEventDisableTiming));
+    while (bc->side.size() < nside) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      bc->side.push_back(st);
+      bc->join.push_back(ev);
+    }
+    CUDA_CHECK(cudaEventRecord(bc->fork, ctx->stream));
+  }
+  for (size_t bi = 0; bi < order.size(); ++bi) {
+    if (!order[bi]) continue;
+    Bucket& b = *order[bi];
     const Geometry& G = *b.geo;
     const size_t nv = b.verts.size();
     ITN_REQUIRE(b.dverts != nullptr, ITN_EINVAL, "block sweep is not prepared");
+    cudaStream_t st = (bi == 0 || nside == 0) ? ctx->stream : bc->side[bi - 1];
+    if (st != ctx->stream) CUDA_CHECK(cudaStreamWaitEvent(st, bc->fork, 0));
     for (int w = 0; w < 3; ++w)
-      launch_pass(ctx, net->cplx, G.KS, (unsigned)(nv * G.pass[w].desc.nblk), G.pass[w].smem, &G.pass[w].desc,
+      launch_pass(ctx, st, net->cplx, G.KS, (unsigned)(nv * G.pass[w].desc.nblk), G.pass[w].smem, &G.pass[w].desc,
                   b.dverts->as<BlkVertex>() + w * nv, b.d_tab[w]);
     int chimax = 0;
     for (int k = 0; k < G.sig.z; ++k) chimax = std::max(chimax, G.sig.chi[k]);
     const unsigned ry = (unsigned)std::max(1, std::min(16, (net->planes() * chimax * chimax + 127) / 128));
-    k_block_reduce<<<dim3((unsigned)b.nred, ry), 128, 0, ctx->stream>>>(b.dred->as<BlkRedJob>());
+    k_block_reduce<<<dim3((unsigned)b.nred, ry), 128, 0, st>>>(b.dred->as<BlkRedJob>());
     ITN_LAUNCH_CHECK(ctx);
+    if (st != ctx->stream) CUDA_CHECK(cudaEventRecord(bc->join[bi - 1], st));
   }
+  bc->pending_joins = nside;
+}
+
+// the context stream waits for the side streams of the last itn_block_bp_run
+void itn_block_bp_join(itn_net* net) {
+  BlockCache* bc = (BlockCache*)net->block;
+  if (!bc) return;
+  for (size_t i = 0; i < bc->pending_joins; ++i) CUDA_CHECK(cudaStreamWaitEvent(net->ctx->stream, bc->join[i], 0));
+  bc->pending_joins = 0;
 }
 
 void itn_block_bp_end(itn_net* net) {

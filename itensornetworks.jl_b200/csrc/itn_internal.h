@@ -271,7 +271,8 @@ void itn_fast_commit_direct(itn_net* net);
 int itn_block_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled);
 void itn_block_bp_begin(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
                         const std::vector<char>& handled, double* const* staged);
-void itn_block_bp_run(itn_net* net);
+void itn_block_bp_run(itn_net* net, bool all_side);  // all_side: the tile path shares the sweep (every bucket on a side stream)
+void itn_block_bp_join(itn_net* net);               // the context stream waits for the side streams of the last run
 void itn_block_bp_end(itn_net* net);
 void itn_block_release(itn_net* net);
 
