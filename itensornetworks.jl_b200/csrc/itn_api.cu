@@ -1568,7 +1568,22 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   }
   // synchronous sweeps: vertices that qualify go to the DMMA kernels, the rest to the generic kernels
   std::vector<char> handled;
-  const int nfast = sync_mode ? itn_fast_bp_plan(net, all_dids, all_src, handled) : 0;
+  // multi-GPU: updates whose message leaves this rank, and the vertices that produce them (they are swept first, their
+  // messages committed and sent while the interior of the sweep runs: itn_dist_exchange_begin / _end)
+  const bool overlap_halo = sync_mode && ctx->nranks > 1 && getenv("ITN_NO_HALO_OVERLAP") == nullptr;
+  std::vector<char> cut_job(nseq, 0), cut_vertex;
+  if (overlap_halo) {
+    cut_vertex.assign(net->nv, 0);
+    for (int i = 0; i < nseq; ++i) {
+      const int w = net->other(sjobs[i].did / 2, sjobs[i].v);
+      if (net->owner[w] != ctx->rank) {
+        cut_job[i] = 1;
+        cut_vertex[sjobs[i].v] = 1;
+      }
+    }
+  }
+  int nfirst = 0;
+  const int nfast = sync_mode ? itn_fast_bp_plan(net, all_dids, all_src, handled, overlap_halo ? &cut_vertex : nullptr, &nfirst) : 0;
   trace.mark("plan_tile");
   // vertices the tile path did not take: the block path (itn_block.cu) for every degree 2..8 / bond extent <= 32
   const int nblock = sync_mode ? itn_block_bp_plan(net, all_dids, all_src, handled) : 0;
@@ -1653,7 +1668,7 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
       itn_flush_pending(net);
       if (nfast > 0) {  // rebuild the tile-major copies (the block path's share of `handled` is kept)
         std::vector<char> h1;
-        itn_fast_bp_plan(net, all_dids, all_src, h1);
+        itn_fast_bp_plan(net, all_dids, all_src, h1, overlap_halo ? &cut_vertex : nullptr, &nfirst);
       }
     }
   }
@@ -1667,6 +1682,26 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   trace.mark("plan_rest");
   if (nblock > 0) itn_block_bp_begin(net, all_dids, all_src, handled, staged.ptr.data());
   trace.mark("block_begin");
+  if (overlap_halo) itn_dist_exchange_prepare(net, global_dids);
+  // commit descriptors of a synchronous sweep: [cut jobs | the rest] (one list, diffs in the same order)
+  std::vector<CommitJob> cj_sync;
+  size_t n_cut_jobs = 0;
+  if (sync_mode) {
+    cj_sync.reserve(nseq);
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < nseq; ++i) {
+        if ((cut_job[i] != 0) != (pass == 0)) continue;
+        const int chi = net->edim[sjobs[i].did / 2];
+        cj_sync.push_back({staged.ptr[i], net->M[sjobs[i].did].p, want_diff ? net->M[sjobs[i].did].p : nullptr, chi * chi});
+      }
+    for (int i = 0; i < nseq; ++i) n_cut_jobs += cut_job[i] ? 1 : 0;
+  }
+  // uploaded once per call (as are the pointer tables of the tile and block paths): nothing inside the sweep loop copies
+  // from pageable memory, so the host runs ahead of the stream and the GPU never waits for the next sweep to be enqueued
+  DevBuf cj_dev(ctx, std::max<size_t>(cj_sync.size(), 1) * sizeof(CommitJob));
+  const CommitJob* d_cj = sync_mode ? itn_upload(ctx, cj_sync, cj_dev) : nullptr;
+  // (the upload-pipelined first sweep uploads the tile path's tables itself; they stay valid for the later sweeps)
+  if (sync_mode && nfast > 0 && !pipelined_first) itn_fast_bp_sweep_begin(net, all_dids, all_src, handled, staged.ptr.data());
 
   cudaEvent_t ev0, ev1;
   CUDA_CHECK(cudaEventCreate(&ev0));
@@ -1676,6 +1711,7 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
   double mean = NAN;
   std::vector<cudaEvent_t> cev;  // event pairs around the contraction kernels
   try {
+    bool halo_in_flight = false;
     for (int it = 0; it < maxiter; ++it) {
       for (size_t l = 0; l + 1 < lvl_ptr.size(); ++l) {
         const size_t lo = lvl_ptr[l], hi = lvl_ptr[l + 1];
@@ -1711,11 +1747,31 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
           }
           itn_run_vertex_sweeps(net, vsweeps);
           itn_run_vertex_jobs(net, slow_specs);
+        } else if (sync_mode && overlap_halo) {
+          // everything that produces a message for another rank first: block buckets (side streams), the cut-adjacent
+          // part of the tile sweep, the generic kernels; commit and send those messages; then the interior
+          if (nblock > 0) itn_block_bp_run(net, nfast > 0);
+          if (nfast > 0) {
+            itn_fast_bp_sweep_range(net, 0, nfirst);
+          }
+          if (nblock > 0) itn_block_bp_join(net);
+          itn_run_vertex_sweeps(net, vsweeps);
+          itn_run_vertex_jobs(net, slow_specs);
+          itn_run_commit_dev(net, d_cj, n_cut_jobs, normalize, want_diff ? diffs.as<double>() : nullptr);
+          itn_dist_exchange_begin(net);
+          halo_in_flight = true;
+          if (nfast > 0) {
+            itn_fast_bp_sweep_range(net, nfirst, (int)itn_fast_sweep_vertices(net, nullptr).size());
+            itn_fast_bp_sweep_end(net);
+          }
         } else if (sync_mode) {
           // the block buckets (rim vertices of a lattice whose bulk is on the tile path) run on side streams behind the
           // tile sweep: they read the same pre-sweep messages and write their own staged outputs
           if (nblock > 0) itn_block_bp_run(net, nfast > 0);
-          if (nfast > 0) itn_fast_bp_sweep(net, all_dids, all_src, handled, staged.ptr.data());
+          if (nfast > 0) {
+            itn_fast_bp_sweep_range(net, 0, (int)itn_fast_sweep_vertices(net, nullptr).size());
+            itn_fast_bp_sweep_end(net);
+          }
           if (nblock > 0) itn_block_bp_join(net);
           itn_run_vertex_sweeps(net, vsweeps);
           itn_run_vertex_jobs(net, slow_specs);
@@ -1723,14 +1779,25 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
           compute_messages(net, sjobs, lo, hi, staged.ptr);
         }
         if (timed) CUDA_CHECK(cudaEventRecord(cev.back(), ctx->stream));
-        std::vector<CommitJob> cj(hi - lo);
-        for (size_t i = lo; i < hi; ++i) {
-          int chi = net->edim[sjobs[i].did / 2];
-          cj[i - lo] = {staged.ptr[i], net->M[sjobs[i].did].p, want_diff ? net->M[sjobs[i].did].p : nullptr, chi * chi};
+        if (halo_in_flight) {
+          itn_run_commit_dev(net, d_cj + n_cut_jobs, cj_sync.size() - n_cut_jobs, normalize, want_diff ? diffs.as<double>() + n_cut_jobs : nullptr);
+        } else if (sync_mode) {
+          itn_run_commit_dev(net, d_cj, cj_sync.size(), normalize, want_diff ? diffs.as<double>() : nullptr);
+        } else {
+          std::vector<CommitJob> cj(hi - lo);
+          for (size_t i = lo; i < hi; ++i) {
+            int chi = net->edim[sjobs[i].did / 2];
+            cj[i - lo] = {staged.ptr[i], net->M[sjobs[i].did].p, want_diff ? net->M[sjobs[i].did].p : nullptr, chi * chi};
+          }
+          itn_run_commit(net, cj, normalize, want_diff ? diffs.as<double>() + lo : nullptr);
         }
-        itn_run_commit(net, cj, normalize, want_diff ? diffs.as<double>() + lo : nullptr);
       }
-      if (ctx->nranks > 1) itn_dist_exchange(net, global_dids);
+      if (halo_in_flight) {
+        itn_dist_exchange_end(net);
+        halo_in_flight = false;
+      } else if (ctx->nranks > 1) {
+        itn_dist_exchange(net, global_dids);
+      }
       ++done;
       if (sync_mode) {
         ctx->path_msgs[0] += nfast;

@@ -441,8 +441,8 @@ __device__ __forceinline__ void op_close(const OpConst& O, const int PL, const d
   }
 }
 
-template <bool C, int KS, int MT>
-__global__ void __launch_bounds__(kBT, (KS <= 4 ? 3 : 2)) k_block(const __grid_constant__ BlkPass P, const BlkVertex* __restrict__ gv,
+template <bool C, int KS, int MT, int NB>
+__global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPass P, const BlkVertex* __restrict__ gv,
                                                   const unsigned short* __restrict__ gtab) {
   extern __shared__ __align__(128) double sm[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -859,12 +859,14 @@ constexpr size_t kSmemTwoCtasMax = 228 * 1024 / 2 - 1024 - kStaticSmem;
 constexpr size_t kSmemThreeCtasMax = 228 * 1024 / 3 - 1024 - kStaticSmem;
 constexpr size_t kSmemOneCta = 227 * 1024 - kStaticSmem;
 // Resident CTAs per SM the planner sizes the blocks for.  The instances with at most four k4 steps (chi <= 8 complex,
-// chi <= 16 real) compile to <= 80 registers (__launch_bounds__(256, 3)), so three CTAs fit when the block is sized for a
-// third of the shared memory; ITN_BLOCK_CTAS = 2 | 3 overrides the default (experiments).
+// chi <= 16 real) also exist in a <= 80 register build (__launch_bounds__(256, 3)) that lets three CTAs share an SM when
+// the block is sized for a third of the shared memory; ITN_BLOCK_CTAS = 3 selects that sizing (experiments).
 int target_ctas(int ks_inst) {
   static const int env = getenv("ITN_BLOCK_CTAS") ? atoi(getenv("ITN_BLOCK_CTAS")) : 0;
   if (ks_inst > 4) return 2;
-  return env == 2 ? 2 : 3;  // measured (B200): 12^3 chi = 6 sweep 12.09 -> 11.25 ms, 32 x 32 chi = 8 sweep 0.599 -> 0.589 ms
+  // measured on B200 with each variant in its own instance (NB = 2: 100 / 113 registers, NB = 3: 79 / 80): 16^3 chi = 6
+  // sweep 28.5 ms with two CTAs of large blocks, 30.1 ms with three CTAs of small ones; 32 x 32 chi = 8: 0.578 / 0.581 ms
+  return env == 3 ? 3 : 2;
 }
 thread_local size_t kSmemTwoCtas = kSmemTwoCtasMax;  // budget of the plan being made (set by choose_pass)
 
@@ -1326,34 +1328,41 @@ bool signature_of(const itn_net* net, int v, Signature& s) {
   return s.d >= 1 && s.d <= 8;
 }
 
-template <bool C, int KS, int MT>
+template <bool C, int KS, int MT, int NB>
 void launch_inst(itn_ctx* ctx, cudaStream_t st, unsigned grid, size_t smem, const BlkPass* dp, const BlkVertex* dv,
                  const unsigned short* dt) {
-  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  k_block<C, KS, MT><<<grid, kBT, smem, st>>>(*dp, dv, dt);  // the descriptor travels as a kernel parameter
+  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  k_block<C, KS, MT, NB><<<grid, kBT, smem, st>>>(*dp, dv, dt);  // the descriptor travels as a kernel parameter
   ITN_LAUNCH_CHECK(ctx);
 }
 
+// NB = resident CTAs per SM the instance is compiled for: the small instances exist for 2 (all the registers they want)
+// and for 3 (at most 80 registers); a pass whose block leaves room for three CTAs in shared memory takes the latter
 void launch_pass(itn_ctx* ctx, cudaStream_t st, bool cplx, int KS, unsigned grid, size_t smem, const BlkPass* dp,
                  const BlkVertex* dv, const unsigned short* dt) {
+  const bool three = KS <= 4 && smem <= kSmemThreeCtasMax;
+#define ITN_BLK(Cx, K, M)                                                                   \
+  return three ? launch_inst<Cx, K, M, 3>(ctx, st, grid, smem, dp, dv, dt)                   \
+               : launch_inst<Cx, K, M, 2>(ctx, st, grid, smem, dp, dv, dt)
   if (cplx) {
     switch (KS) {
-      case 1: return launch_inst<true, 1, 1>(ctx, st, grid, smem, dp, dv, dt);
-      case 2: return launch_inst<true, 2, 1>(ctx, st, grid, smem, dp, dv, dt);
-      case 3: return launch_inst<true, 3, 1>(ctx, st, grid, smem, dp, dv, dt);
-      case 4: return launch_inst<true, 4, 1>(ctx, st, grid, smem, dp, dv, dt);
-      case 8: return launch_inst<true, 8, 2>(ctx, st, grid, smem, dp, dv, dt);
-      default: return launch_inst<true, 16, 4>(ctx, st, grid, smem, dp, dv, dt);
+      case 1: ITN_BLK(true, 1, 1);
+      case 2: ITN_BLK(true, 2, 1);
+      case 3: ITN_BLK(true, 3, 1);
+      case 4: ITN_BLK(true, 4, 1);
+      case 8: return launch_inst<true, 8, 2, 2>(ctx, st, grid, smem, dp, dv, dt);
+      default: return launch_inst<true, 16, 4, 2>(ctx, st, grid, smem, dp, dv, dt);
     }
   } else {
     switch (KS) {
-      case 1: return launch_inst<false, 1, 1>(ctx, st, grid, smem, dp, dv, dt);
-      case 2: return launch_inst<false, 2, 1>(ctx, st, grid, smem, dp, dv, dt);
-      case 4: return launch_inst<false, 4, 2>(ctx, st, grid, smem, dp, dv, dt);
-      default: return launch_inst<false, 8, 4>(ctx, st, grid, smem, dp, dv, dt);
+      case 1: ITN_BLK(false, 1, 1);
+      case 2: ITN_BLK(false, 2, 1);
+      case 4: ITN_BLK(false, 4, 2);
+      default: return launch_inst<false, 8, 4, 2>(ctx, st, grid, smem, dp, dv, dt);
     }
   }
+#undef ITN_BLK
 }
 
 void end_call(Bucket& b) {

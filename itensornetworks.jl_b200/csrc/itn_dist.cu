@@ -82,6 +82,11 @@ struct DistPlan {
   int nsend = 0, nrecv = 0;
   HaloJob *d_send = nullptr, *d_recv = nullptr;
   double *sendbuf = nullptr, *recvbuf = nullptr;
+  // split exchange (itn_dist_exchange_begin / _end): pack + send / recv run on a side stream while the context stream
+  // computes the part of the sweep that no other rank waits for
+  cudaStream_t comm = nullptr;
+  cudaEvent_t ready = nullptr, done = nullptr;
+  bool in_flight = false;
 };
 
 void free_plan(itn_net* net, DistPlan* p) {
@@ -103,6 +108,9 @@ void itn_dist_release(itn_net* net) {
   if (!net->dist) return;
   DistPlan* p = (DistPlan*)net->dist;
   free_plan(net, p);
+  if (p->comm) cudaStreamDestroy(p->comm);
+  if (p->ready) cudaEventDestroy(p->ready);
+  if (p->done) cudaEventDestroy(p->done);
   delete p;
   net->dist = nullptr;
 }
@@ -127,9 +135,8 @@ void itn_dist_p2p(itn_ctx* ctx, const std::vector<P2PSeg>& segs) {
   NCCL_CHECK(api().GroupEnd());
 }
 
-void itn_dist_exchange(itn_net* net, const std::vector<int>& dids) {
+static DistPlan* ensure_plan(itn_net* net, const std::vector<int>& dids) {
   itn_ctx* ctx = net->ctx;
-  if (ctx->nranks == 1) return;
   ITN_REQUIRE(ctx->nccl, ITN_ENCCL, "context is not initialised for multi-GPU use (itn_ctx_init_dist)");
   DistPlan* p = (DistPlan*)net->dist;
   if (!p) net->dist = p = new DistPlan();
@@ -194,20 +201,74 @@ void itn_dist_exchange(itn_net* net, const std::vector<int>& dids) {
     }
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // sj / rj are about to go out of scope
   }
+  return p;
+}
+
+// pack -> grouped send / recv on stream `st`
+static void exchange_on(itn_net* net, DistPlan* p, cudaStream_t st) {
+  itn_ctx* ctx = net->ctx;
   if (p->nsend) {
-    k_halo_pack<<<p->nsend, 128, 0, ctx->stream>>>(p->d_send, p->sendbuf);
+    k_halo_pack<<<p->nsend, 128, 0, st>>>(p->d_send, p->sendbuf);
     ITN_LAUNCH_CHECK(ctx);
   }
   NCCL_CHECK(api().GroupStart());
   for (const Peer& pr : p->peers) {
-    if (pr.send_n) NCCL_CHECK(api().Send(p->sendbuf + pr.send_off, (size_t)pr.send_n, ncclDouble, pr.rank, (ncclComm_t)ctx->nccl, ctx->stream));
-    if (pr.recv_n) NCCL_CHECK(api().Recv(p->recvbuf + pr.recv_off, (size_t)pr.recv_n, ncclDouble, pr.rank, (ncclComm_t)ctx->nccl, ctx->stream));
+    if (pr.send_n) NCCL_CHECK(api().Send(p->sendbuf + pr.send_off, (size_t)pr.send_n, ncclDouble, pr.rank, (ncclComm_t)ctx->nccl, st));
+    if (pr.recv_n) NCCL_CHECK(api().Recv(p->recvbuf + pr.recv_off, (size_t)pr.recv_n, ncclDouble, pr.rank, (ncclComm_t)ctx->nccl, st));
   }
   NCCL_CHECK(api().GroupEnd());
+}
+
+void itn_dist_exchange(itn_net* net, const std::vector<int>& dids) {
+  itn_ctx* ctx = net->ctx;
+  if (ctx->nranks == 1) return;
+  DistPlan* p = ensure_plan(net, dids);
+  exchange_on(net, p, ctx->stream);
   if (p->nrecv) {
     k_halo_unpack<<<p->nrecv, 128, 0, ctx->stream>>>(p->d_recv, p->recvbuf);
     ITN_LAUNCH_CHECK(ctx);
   }
+}
+
+void itn_dist_exchange_prepare(itn_net* net, const std::vector<int>& dids) {
+  if (net->ctx->nranks == 1) return;
+  DistPlan* p = ensure_plan(net, dids);
+  if (!p->comm) {
+    // highest priority: the few CTAs of pack / send / recv are dispatched ahead of the thousands of queued sweep CTAs
+    int lo_prio = 0, hi_prio = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&p->comm, cudaStreamNonBlocking, hi_prio));
+    CUDA_CHECK(cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+  }
+}
+
+// Every message this rank sends has been committed on the context stream: pack and send / receive on the side stream.
+void itn_dist_exchange_begin(itn_net* net) {
+  itn_ctx* ctx = net->ctx;
+  if (ctx->nranks == 1) return;
+  DistPlan* p = (DistPlan*)net->dist;
+  ITN_REQUIRE(p && p->comm, ITN_EINVAL, "halo exchange is not prepared");
+  CUDA_CHECK(cudaEventRecord(p->ready, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(p->comm, p->ready, 0));
+  exchange_on(net, p, p->comm);
+  CUDA_CHECK(cudaEventRecord(p->done, p->comm));
+  p->in_flight = true;
+}
+
+// Every local read of the pre-sweep boundary messages has been enqueued on the context stream: wait for the transfer and
+// unpack the received messages there.
+void itn_dist_exchange_end(itn_net* net) {
+  itn_ctx* ctx = net->ctx;
+  if (ctx->nranks == 1) return;
+  DistPlan* p = (DistPlan*)net->dist;
+  if (!p || !p->in_flight) return;
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, p->done, 0));
+  if (p->nrecv) {
+    k_halo_unpack<<<p->nrecv, 128, 0, ctx->stream>>>(p->d_recv, p->recvbuf);
+    ITN_LAUNCH_CHECK(ctx);
+  }
+  p->in_flight = false;
 }
 
 #define API_BEGIN try {

@@ -795,8 +795,10 @@ void itn_fast_release(itn_net* net) {
 
 // Decide which message jobs the fast path computes: vertices of degree 4 whose four bonds all have
 // dimension 16, whose tensor is set and whose four outgoing messages are all part of this sweep.
-int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled) {
+int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled,
+                     const std::vector<char>* first, int* nfirst) {
   handled.assign(dids.size(), 0);
+  if (nfirst) *nfirst = 0;
   static const bool off = getenv("ITN_NO_TILE") != nullptr;  // experiments: send everything to the block path
   if (off) return 0;
   FastCache* fc = ensure_cache(net);
@@ -819,6 +821,15 @@ int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vect
       rank_in_sweep[i] = (int)fc->sweep.size();
       fc->sweep.push_back(i);
     }
+  if (first) {
+    // multi-GPU: the vertices next to a cut come first, so that their messages can travel while the rest is computed
+    auto is_first = [&](int slot) { return (*first)[fc->verts[slot]] != 0; };
+    std::stable_partition(fc->sweep.begin(), fc->sweep.end(), is_first);
+    int n1 = 0;
+    for (int slot : fc->sweep) n1 += is_first(slot) ? 1 : 0;
+    if (nfirst) *nfirst = n1;
+    for (size_t r = 0; r < fc->sweep.size(); ++r) rank_in_sweep[fc->sweep[r]] = (int)r;
+  }
   fc->sweep_verts.resize(fc->sweep.size());
   for (size_t r = 0; r < fc->sweep.size(); ++r) fc->sweep_verts[r] = fc->verts[fc->sweep[r]];
   if (fc->sweep.empty()) return 0;

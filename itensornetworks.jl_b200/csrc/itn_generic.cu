@@ -705,6 +705,19 @@ void itn_run_commit(itn_net* net, const std::vector<CommitJob>& jobs, int normal
   ITN_LAUNCH_CHECK(ctx);
 }
 
+// the same with descriptors that already live on the device (uploaded once per itn_bp_update call: a pageable upload
+// inside the sweep loop makes the host wait for the stream and the GPU idle while the next sweep is being enqueued)
+void itn_run_commit_dev(itn_net* net, const CommitJob* d_jobs, size_t n, int normalize, double* d_diffs) {
+  if (n == 0) return;
+  itn_ctx* ctx = net->ctx;
+  const int herm = net->has_bra() ? 0 : 1;
+  if (net->cplx)
+    k_commit<true><<<(unsigned)n, 128, 0, ctx->stream>>>(d_jobs, normalize, herm, d_diffs);
+  else
+    k_commit<false><<<(unsigned)n, 128, 0, ctx->stream>>>(d_jobs, normalize, herm, d_diffs);
+  ITN_LAUNCH_CHECK(ctx);
+}
+
 void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
   if (specs.empty()) return;
   itn_ctx* ctx = net->ctx;

@@ -213,6 +213,7 @@ struct SweepSpec {
 bool itn_vertex_sweep_ok(const itn_net* net, int v);
 void itn_run_vertex_sweeps(itn_net* net, const std::vector<SweepSpec>& specs);
 void itn_run_commit(itn_net* net, const std::vector<CommitJob>& jobs, int normalize, double* d_diffs);
+void itn_run_commit_dev(itn_net* net, const CommitJob* d_jobs, size_t n, int normalize, double* d_diffs);
 int itn_open_extent(const itn_net* net, int v, uint32_t open_mask);
 
 struct ModeProdSpec {
@@ -232,7 +233,9 @@ void itn_run_modeprods(itn_ctx* ctx, bool cplx, const std::vector<ModeProdSpec>&
 // Plans a synchronous sweep: handled[i] = 1 for the message jobs (directed id dids[i], source vertex
 // srcv[i]) that the DMMA kernels compute; returns their number.  The sweep writes the un-normalised
 // new messages of those jobs to staged[i].
-int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled);
+// first / nfirst (optional): vertices flagged in `first` take the leading sweep positions; *nfirst = how many did.
+int itn_fast_bp_plan(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv, std::vector<char>& handled,
+                     const std::vector<char>* first = nullptr, int* nfirst = nullptr);
 void itn_fast_bp_sweep(itn_net* net, const std::vector<int>& dids, const std::vector<int>& srcv,
                        const std::vector<char>& handled, double* const* staged);
 void itn_fast_release(itn_net* net);
@@ -281,6 +284,12 @@ bool itn_is_local(const itn_net* net, int v);
 // Sends every message listed in `dids` whose destination vertex lives on another rank to that rank and
 // receives the matching ones (ordered by directed id on both sides); one grouped NCCL send/recv per peer.
 void itn_dist_exchange(itn_net* net, const std::vector<int>& dids);
+// The same exchange in two halves, overlapped with the interior of the sweep: prepare (plan, side stream) once per call;
+// begin after the messages that leave this rank are committed (pack + send / recv on the side stream); end after the last
+// local read of the pre-sweep boundary messages is enqueued (the context stream waits for the transfer and unpacks).
+void itn_dist_exchange_prepare(itn_net* net, const std::vector<int>& dids);
+void itn_dist_exchange_begin(itn_net* net);
+void itn_dist_exchange_end(itn_net* net);
 void itn_dist_allreduce_sum(itn_ctx* ctx, double* dev, int n);
 // One grouped point-to-point exchange on the context stream: per peer, sn doubles out of sbuf and rn doubles into rbuf.
 struct P2PSeg {
