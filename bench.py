@@ -379,7 +379,8 @@ def bench_other_config(E, torch, ctx, stream, name, peak_tf):
     mine = [True] * graph.nv
     tensors, host, _ = make_psi(torch, graph, chi, dtype, d, mine)
     psi = E.ITensorNetwork(graph, tensors, dtype)
-    seq = E.parallel_edge_sequence(graph)
+    # the schedule in wire format, made once (a driver calls update() with the same schedule every step)
+    seq = E.prepare_sequence(E.parallel_edge_sequence(graph))
     bpc = E.BeliefPropagationCache(psi, ctx=ctx)
     steps = 20 if graph.nv < 2000 else 5
     ms = time_sweeps(E, torch, bpc, seq, stream, steps, 3)
@@ -427,7 +428,8 @@ def run_ours(args):
     tensors, host, h2d = make_psi(torch, graph, chi, dtype, d, mine)
     comps = 2 if cplx else 1
     psi = E.ITensorNetwork(graph, tensors, dtype)
-    seq = E.parallel_edge_sequence(graph)
+    # the schedule in wire format, made once (a driver calls update() with the same schedule every step)
+    seq = E.prepare_sequence(E.parallel_edge_sequence(graph))
     n_updates = 2 * graph.ne
     flops_sweep = algorithmic_flops_per_sweep(graph, chi, d, cplx)
 
