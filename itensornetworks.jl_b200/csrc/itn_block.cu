@@ -84,6 +84,10 @@ struct BlkPass {
   int msg_smem;            // 1: the messages of the pass are staged in shared memory (msg_off, doubles), 0: read from L2
   int msg_off[kMaxGM];
   int msg_len;             // doubles reserved for the staged messages
+  int wl;                  // 1: warp-local operation lists (every warp owns whole batch slices of the block, see k_block)
+  int nclose;              // closes of the pass
+  int buf_total;           // doubles reserved for the tensor buffers (warp-local: also the scratch of the final cross-warp sum)
+  int red_len;             // doubles of the cross-warp scratch behind the buffers (0 in warp-local passes)
 };
 struct BlkVertex {
   const double* X;     // site tensor (canonical planar)
@@ -441,19 +445,74 @@ __device__ __forceinline__ void op_close(const OpConst& O, const int PL, const d
   }
 }
 
-template <bool C, int KS, int MT, int NB>
+// Warp-local close (every extent of the pass <= 8: one 8 x 8 tile): the warp sums over ITS tiles (ft = warp, warp + 8, ...)
+// and keeps the partial tile in registers; the cross-warp sum of all closes of the pass happens once, at the end of k_block.
+// r: (re col 2t, re col 2t + 1, im col 2t, im col 2t + 1) of row g -- real: (col 2t, col 2t + 1).
+template <bool C>
+__device__ __forceinline__ void op_close_wl(const OpConst& O, const int PL, const double* W, const double* X,
+                                            const unsigned short* __restrict__ tab, const int warp, const int lane,
+                                            double (&r)[C ? 4 : 2]) {
+  const int chi = O.chi;
+  const int g = lane >> 2, t = lane & 3;
+  const unsigned short* tb = tab + O.tab;
+  const bool mok = g < chi;
+  const int gS = g * O.S;
+  if constexpr (C) {
+    double ca[4] = {0.0, 0.0, 0.0, 0.0}, cb[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int ft = warp; ft < O.ntile; ft += kNW) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const unsigned fb = tb[ft * 8 + h * 4 + t];
+        const bool ok = (O.exact || fb != kNoFibre) && mok;
+        const double wre = ok ? W[fb + gS] : 0.0;
+        const double wim = ok ? W[PL + fb + gS] : 0.0;
+        const double xre = ok ? X[fb + gS] : 0.0;
+        const double xim = ok ? X[PL + fb + gS] : 0.0;
+        dmma1684(ca, wre, wim, xre);
+        dmma1684(cb, wim, wre, xim);
+      }
+    }
+    r[0] = ca[0] + cb[0];
+    r[1] = ca[1] + cb[1];
+    r[2] = ca[2] - cb[2];
+    r[3] = ca[3] - cb[3];
+  } else {
+    double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
+    for (int ft = warp; ft < O.ntile; ft += kNW) {
+      const unsigned f0 = tb[ft * 8 + t], f1 = tb[ft * 8 + 4 + t];
+      const bool ok0 = (O.exact || f0 != kNoFibre) && mok, ok1 = (O.exact || f1 != kNoFibre) && mok;
+      const double w0 = ok0 ? W[f0 + gS] : 0.0, x0 = ok0 ? X[f0 + gS] : 0.0;
+      const double w1 = ok1 ? W[f1 + gS] : 0.0, x1 = ok1 ? X[f1 + gS] : 0.0;
+      dmma884(a0, w0, x0);
+      dmma884(a1, w1, x1);
+    }
+    r[0] = a0[0] + a1[0];
+    r[1] = a0[1] + a1[1];
+  }
+}
+
+constexpr int kMaxClose = 4;  // closes per pass (z = 8: four bonds per group)
+
+// WL (warp-local, every extent of the vertex <= 8): the host deals the batch slices of the block -- the values of the
+// indices no operation of the pass contracts (site index and chunk index in passes 1 / 3, the chunk of the flat
+// (site, G1) index in pass 2) -- out to the 8 warps and orders the fibre tables so that tile ft belongs to warp ft % 8 and
+// touches only that warp's slices.  Every mode product then reads what the same warp wrote: the operation list runs with
+// __syncwarp between operations instead of a CTA barrier after each, products run in place (fewer buffers, larger blocks),
+// closes stay in registers, and ONE cross-warp sum per pass (scratch aliased on the dead tensor buffers) ends the CTA.
+template <bool C, int KS, int MT, int NB, bool WL>
 __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPass P, const BlkVertex* __restrict__ gv,
                                                   const unsigned short* __restrict__ gtab) {
   extern __shared__ __align__(128) double sm[];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ OpConst sOp[kMaxOps];
   __shared__ int sKoff[kMaxGM * 64];  // [mode][step (16)][lane & 3]
+  __shared__ int sCloseOp[kMaxClose];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vi = blockIdx.x / P.nblk, blk = blockIdx.x - vi * P.nblk;
   const BlkVertex* __restrict__ V = gv + vi;
   double* bufs = sm;
-  double* red = bufs + (size_t)P.nbuf * P.bufsz;
-  double* msm = red + kRedDoubles;                                    // staged messages (P.msg_smem)
+  double* red = bufs + P.buf_total;
+  double* msm = red + P.red_len;                                      // staged messages (P.msg_smem)
   unsigned short* tab = (unsigned short*)(msm + P.msg_len);
   constexpr int PLN = C ? 2 : 1;
   const unsigned mb = smem_u32(&mbar);
@@ -478,6 +537,11 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
     o.slot = M.slot;
     o.mode = op.mode;
     sOp[tid] = o;
+  }
+  if (WL && tid == 0) {
+    int c = 0;
+    for (int oi = 0; oi < P.nops; ++oi)
+      if (P.ops[oi].type == OP_CLOSE && c < kMaxClose) sCloseOp[c++] = oi;
   }
   if (tid < kMaxGM * 64) {
     const int k = tid >> 6, ks = (tid >> 2) & 15, t = tid & 3;
@@ -565,14 +629,35 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
   }
   __syncthreads();
   // ---- the operation list of the pass --------------------------------------------------------------------------------
+  constexpr int NR = C ? 4 : 2;
+  double hacc[WL ? kMaxClose : 1][NR];
+#pragma unroll
+  for (int c = 0; c < (WL ? kMaxClose : 1); ++c)
+#pragma unroll
+    for (int j = 0; j < NR; ++j) hacc[c][j] = 0.0;
+  int ci = 0;
   for (int oi = 0; oi < P.nops; ++oi) {
     const OpConst O = sOp[oi];
     if (O.type == OP_MP) {
       op_mp<C, KS>(O, P.PL, V->msg[O.slot], msm, sKoff, bufs, bufs, tab, warp, lane);
+      if (WL) __syncwarp();
     } else if (O.type == OP_CLOSE) {
-      double* out = V->part[O.slot] + (size_t)blk * PLN * O.chi * O.chi;
-      op_close<C, MT>(O, P.PL, bufs + O.src, bufs, red, out, tab, warp, lane, tid);
+      if constexpr (WL) {
+        double r[NR];
+        op_close_wl<C>(O, P.PL, bufs + O.src, bufs, tab, warp, lane, r);
+#pragma unroll
+        for (int c = 0; c < kMaxClose; ++c)
+          if (c == ci) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) hacc[c][j] = r[j];
+          }
+        ++ci;
+      } else {
+        double* out = V->part[O.slot] + (size_t)blk * PLN * O.chi * O.chi;
+        op_close<C, MT>(O, P.PL, bufs + O.src, bufs, red, out, tab, warp, lane, tid);
+      }
     } else {
+      if (WL) __syncthreads();  // rows of the store cross the warps' slices
       const double* b = bufs + O.src;
       double* gW = V->Wout;
       const unsigned short* rt = tab + P.rowtab;
@@ -608,9 +693,41 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
         }
       }
     }
+    if (!WL) __syncthreads();
+  }
+  if constexpr (WL) {
+    // one cross-warp sum for all closes of the pass: [close][warp][plane][8 x 8], on the (dead) tensor buffers
     __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int c = 0; c < kMaxClose; ++c)
+      if (c < P.nclose) {
+        double* q = bufs + (size_t)(c * kNW + warp) * (PLN * 64) + g + 16 * t;
+        q[0] = hacc[c][0];
+        q[8] = hacc[c][1];
+        if (C) {
+          q[64] = hacc[c][2];
+          q[72] = hacc[c][3];
+        }
+      }
+    __syncthreads();
+    for (int c = 0; c < P.nclose; ++c) {
+      const OpConst O = sOp[sCloseOp[c]];
+      const int chi = O.chi, n2 = chi * chi;
+      double* out = V->part[O.slot] + (size_t)blk * PLN * n2;
+      for (int i = tid; i < PLN * n2; i += kBT) {
+        const int p = i / n2, o = i - p * n2;
+        const int col = o / chi, row = o - col * chi;
+        const double* q = bufs + (size_t)c * kNW * (PLN * 64) + p * 64 + row + 8 * col;
+        double a = 0.0;
+#pragma unroll
+        for (int s = 0; s < kNW; ++s) a += q[s * (PLN * 64)];
+        out[i] = a;
+      }
+    }
   }
 }
+
 
 // staged message = sum of the per-block partials, in block order (deterministic)
 struct BlkRedJob {
@@ -795,6 +912,7 @@ struct PassPlan {
   std::vector<unsigned short> table;
   size_t smem = 0;
   int excess = 0;
+  double eff = 1.0;  // warp-local plans: real fibres / fibres of the padded per-warp tiles (averaged over the modes)
 };
 
 // Emits "all but one" closes for the bond set [lo, hi) of the pass (local mode indices) from buffer T by divide and conquer.
@@ -846,6 +964,60 @@ struct Emitter {
   }
 };
 
+// Warp-local passes: one row tile per fibre (every extent <= 8), so a mode product may run in place.  A buffer the
+// caller does not need any more ("owned") is overwritten; the first product on a buffer that must survive goes to a new one.
+struct EmitterWL {
+  BlkPass* P;
+  std::vector<char> busy;
+  bool ok = true;
+  int maxbuf = 0;
+  int alloc() {
+    for (int i = 1; i < (int)busy.size(); ++i)
+      if (!busy[i]) {
+        busy[i] = 1;
+        maxbuf = std::max(maxbuf, i + 1);
+        return i;
+      }
+    ok = false;
+    return 1;
+  }
+  void put(unsigned char type, int src, int dst, int mode) {
+    if (P->nops >= kMaxOps) {
+      ok = false;
+      return;
+    }
+    P->ops[P->nops++] = {type, (unsigned char)src, (unsigned char)dst, (unsigned char)mode};
+  }
+  int absorb(int T, int a_lo, int a_hi, bool owned) {
+    int cur = T;
+    bool mine = owned;
+    for (int k = a_lo; k < a_hi; ++k) {
+      if (mine) {
+        put(OP_MP, cur, cur, k);
+      } else {
+        const int dst = alloc();
+        put(OP_MP, cur, dst, k);
+        cur = dst;
+        mine = true;
+      }
+    }
+    return cur;
+  }
+  void solve(int T, int lo, int hi, bool owned) {
+    if (hi - lo == 1) {
+      put(OP_CLOSE, T, 0, lo);
+      return;
+    }
+    const int mid = (lo + hi) / 2;
+    const int t1 = absorb(T, mid, hi, false);
+    solve(t1, lo, mid, true);
+    busy[t1] = 0;
+    const int t2 = absorb(T, lo, mid, owned);
+    solve(t2, mid, hi, true);
+    if (t2 != T) busy[t2] = 0;
+  }
+};
+
 // dynamic shared memory that still lets two CTAs share an SM: 228 KB per SM, 1 KB reserved per CTA, and the kernel's
 // 2176 bytes of static shared memory (sOp, sKoff, mbar) -- 113 KB, the round-2 value, silently dropped the chi = 8 pass 2
 // and the chi = 16 pass 3 (114.6 / 113.3 KB) to one CTA per SM
@@ -871,8 +1043,7 @@ int target_ctas(int ks_inst) {
 thread_local size_t kSmemTwoCtas = kSmemTwoCtasMax;  // budget of the plan being made (set by choose_pass)
 
 size_t pass_smem(const BlkPass& P, size_t tab_len) {
-  return (size_t)P.nbuf * P.bufsz * sizeof(double) + kRedDoubles * sizeof(double) + (size_t)P.msg_len * sizeof(double) +
-         ((tab_len * 2 + 15) & ~(size_t)15) + 64;
+  return ((size_t)P.buf_total + P.red_len + P.msg_len) * sizeof(double) + ((tab_len * 2 + 15) & ~(size_t)15) + 64;
 }
 
 // k * S mod 16 distinct for the (up to) four consecutive bond indices a half-warp touches together
@@ -898,6 +1069,7 @@ struct PassChoice {
   int split = 0;      // fast passes: bonds below `split` stay inside the contiguous row
   int pad_chunk = 0;  // extra doubles between consecutive chunk slices (fast) -- tried by full evaluation
   int pad_plane = 0;
+  bool wl = false;    // warp-local operation lists (every extent of the vertex <= 8)
 };
 
 // Builds the plan of one pass.  fast (passes 1 and 3): the block holds every index of (site, G1) and `chunk` values of G2's
@@ -1009,39 +1181,81 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
   const int nm = (int)mode_slot.size();
   P.nmodes = nm;
   // operation list
-  Emitter em;
-  em.P = &P;
-  em.busy.assign(8, 0);
-  em.busy[0] = 1;
-  if (which == 0) {
-    // P = X x_{G1} M: ping-pong between buffers 1 and 0 (X is dead after its first product)
-    int cur = 0;
-    for (int k = 0; k < nm; ++k) {
-      const int dst = cur == 0 ? 1 : 0;
-      em.put(OP_MP, cur, dst, k);
-      cur = dst;
+  if (ch.wl) {
+    EmitterWL em;
+    em.P = &P;
+    em.busy.assign(8, 0);
+    em.busy[0] = 1;
+    em.maxbuf = 1;
+    if (which == 0) {
+      for (int k = 0; k < nm; ++k) em.put(OP_MP, 0, 0, k);  // P = X x_{G1} M in place
+      em.put(OP_STORE, 0, 0, 0);
+    } else {
+      em.busy[1] = 1;
+      em.maxbuf = 2;
+      em.solve(1, 0, nm, true);  // the partially absorbed tensor is dead after its closes
+      if (which == 1) {
+        for (int k = 0; k < nm; ++k) em.put(OP_MP, 0, 0, k);  // S = X x_{G2} M in place: every close has read X
+        em.put(OP_STORE, 0, 0, 0);
+      }
     }
-    em.put(OP_STORE, cur, 0, 0);
-    em.maxbuf = 2;
+    if (!em.ok) return false;
+    P.nbuf = em.maxbuf;
   } else {
-    em.busy[1] = 1;
-    em.maxbuf = 2;
-    em.solve(1, 0, nm);
-    if (which == 1) {
-      // S = X x_{G2} M; the buffer of P is free now, X (buffer 0) is only read
-      em.busy[1] = 0;
+    Emitter em;
+    em.P = &P;
+    em.busy.assign(8, 0);
+    em.busy[0] = 1;
+    if (which == 0) {
+      // P = X x_{G1} M: ping-pong between buffers 1 and 0 (X is dead after its first product)
       int cur = 0;
       for (int k = 0; k < nm; ++k) {
-        const int dst = em.alloc(cur);
+        const int dst = cur == 0 ? 1 : 0;
         em.put(OP_MP, cur, dst, k);
-        if (cur != 0) em.busy[cur] = 0;
         cur = dst;
       }
       em.put(OP_STORE, cur, 0, 0);
+      em.maxbuf = 2;
+    } else {
+      em.busy[1] = 1;
+      em.maxbuf = 2;
+      em.solve(1, 0, nm);
+      if (which == 1) {
+        // S = X x_{G2} M; the buffer of P is free now, X (buffer 0) is only read
+        em.busy[1] = 0;
+        int cur = 0;
+        for (int k = 0; k < nm; ++k) {
+          const int dst = em.alloc(cur);
+          em.put(OP_MP, cur, dst, k);
+          if (cur != 0) em.busy[cur] = 0;
+          cur = dst;
+        }
+        em.put(OP_STORE, cur, 0, 0);
+      }
     }
+    if (!em.ok) return false;
+    P.nbuf = em.maxbuf;
   }
-  if (!em.ok) return false;
-  P.nbuf = em.maxbuf;
+  P.wl = ch.wl ? 1 : 0;
+  P.nclose = 0;
+  for (int o = 0; o < P.nops; ++o) P.nclose += P.ops[o].type == OP_CLOSE;
+  if (ch.wl && P.nclose > kMaxClose) return false;
+  {
+    const long long scratch = ch.wl ? (long long)P.nclose * kNW * (cplx ? 2 : 1) * 64 : 0;
+    P.buf_total = (int)std::max<long long>((long long)P.nbuf * P.bufsz, scratch);
+    P.red_len = ch.wl ? 0 : kRedDoubles;
+  }
+  // warp-local: the batch axes (no mode of the pass) are dealt out to the warps in contiguous, balanced runs
+  std::vector<int> owner;  // batch value -> warp
+  long long nbatch = 1;
+  if (ch.wl) {
+    for (const Axis& a : axes)
+      if (a.mode < 0) nbatch *= a.n;
+    owner.resize(nbatch);
+    for (int w = 0; w < kNW; ++w)
+      for (long long v = w * nbatch / kNW; v < (w + 1) * nbatch / kNW; ++v) owner[v] = w;
+  }
+  double eff_sum = 0.0;
   // fibre tables
   out.table.clear();
   out.excess = 0;
@@ -1067,12 +1281,59 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
       const int KHs = aligned ? ks_inst / 2 : ks_inst;
       P.modes[k].exact = ((nreal / m.chi) % 8 == 0 && K2 == 4 * KHs) ? 1 : 0;
     }
-    if (with_tables) {
+    const long long nf = nreal / m.chi;
+    if (ch.wl) {
+      // fibres of the largest per-warp share -> tiles per warp; the table interleaves the warps' tiles (tile ft: warp ft % 8)
+      long long maxb = 0;
+      for (int w = 0; w < kNW; ++w) maxb = std::max(maxb, (w + 1) * nbatch / kNW - w * nbatch / kNW);
+      const long long per_slice = nf / nbatch;
+      const int ntw_est = (int)((maxb * per_slice + 7) / 8);
+      eff_sum += (double)nf / (64.0 * ntw_est);
+      bool uniform = true;
+      for (int w = 0; w < kNW; ++w) uniform = uniform && ((w + 1) * nbatch / kNW - w * nbatch / kNW) == maxb;
+      P.modes[k].exact = (P.modes[k].exact && uniform && (maxb * per_slice) % 8 == 0) ? 1 : 0;
+      if (with_tables) {
+        std::vector<const Axis*> others;
+        for (const Axis& a : axes)
+          if (a.mode != k) others.push_back(&a);
+        std::vector<std::vector<int>> wb(kNW);
+        for (long long f = 0; f < nf; ++f) {
+          long long q = f, off = 0, bv = 0, bmul = 1;
+          for (const Axis* a : others) {
+            const long long dg = q % a->n;
+            off += dg * a->s;
+            q /= a->n;
+            if (a->mode < 0) {
+              bv += dg * bmul;
+              bmul *= a->n;
+            }
+          }
+          wb[owner[bv]].push_back((int)off);
+        }
+        std::vector<std::vector<unsigned short>> wt(kNW);
+        size_t ntw = 0;
+        for (int w = 0; w < kNW; ++w) {
+          if (wb[w].empty()) continue;
+          ModeGeom mw = m;
+          mw.bases = wb[w];
+          out.excess += plan_fibres(mw, cplx, aligned, P.PL, wt[w]);
+          ntw = std::max(ntw, wt[w].size() / 8);
+        }
+        P.modes[k].tab = (int)out.table.size();
+        P.modes[k].ntile = (int)(ntw * kNW);
+        for (size_t j = 0; j < ntw; ++j)
+          for (int w = 0; w < kNW; ++w)
+            for (int i = 0; i < 8; ++i)
+              out.table.push_back(j * 8 + i < wt[w].size() ? wt[w][j * 8 + i] : (unsigned short)kNoFibre);
+        tab_len = out.table.size();
+      } else {
+        tab_len += (size_t)ntw_est * kNW * 8;
+      }
+    } else if (with_tables) {
       // every combination of the other axes, first axis fastest
       std::vector<const Axis*> others;
       for (const Axis& a : axes)
         if (a.mode != k) others.push_back(&a);
-      const long long nf = nreal / m.chi;
       m.bases.resize(nf);
       for (long long f = 0; f < nf; ++f) {
         long long q = f, off = 0;
@@ -1092,6 +1353,7 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
       tab_len += (size_t)((nreal / m.chi + 15) & ~7ll);
     }
   }
+  out.eff = ch.wl ? eff_sum / std::max(nm, 1) : 1.0;
   // shared-memory position of every row (the kernel's stores read it instead of dividing)
   P.rowtab = (int)out.table.size();
   if (with_tables) {
@@ -1131,7 +1393,7 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
 
 // Chooses the block of a pass: the largest chunk that leaves two CTAs per SM (one if it must), shrunk while the launch
 // would not cover the SMs; then the paddings with the fewest excess wavefronts.
-bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, size_t nverts, PassPlan& best) {
+bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, size_t nverts, PassPlan& best, bool wl) {
   const bool aligned = cplx && ks_inst >= 8;
   kSmemTwoCtas = target_ctas(ks_inst) == 3 ? kSmemThreeCtasMax : kSmemTwoCtasMax;
   const int z = sg.z, d = sg.d;
@@ -1141,6 +1403,7 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, 
   const bool fast = which != 1;
   const long long range = fast ? XR : L;
   PassChoice ch;
+  ch.wl = wl;
   if (fast) {
     // bonds whose natural stride is fine stay inside the contiguous row
     long long S = d;
@@ -1178,7 +1441,7 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, 
     const long long nb = (fast ? L : XR) * c;
     const long long ctas = (long long)pp.desc.nblk * (long long)nverts;
     const bool two = pp.smem <= kSmemTwoCtas;
-    double score = std::min<double>((double)nb, 4096.0);
+    double score = std::min<double>((double)nb, 4096.0) * pp.eff;
     if (!two) score *= 0.2;  // one CTA of 8 warps per SM hides neither the staging nor the DMMA latency
     if (!fast && c * 8 < 64) score *= 0.5 + c / 16.0;  // short HBM rows waste sectors and bulk-copy issue slots
     if (ctas < 296) score *= ((double)ctas / 296.0) * 0.9 + 0.1;
@@ -1267,8 +1530,25 @@ const Geometry* geometry_for(const Signature& s, bool cplx, size_t nverts) {
     g->nelem *= s.chi[k];
   }
   kernel_instance(cplx, chimax, g->KS, g->MT);
+  // warp-local passes (k_block<..., WL = true>): every extent <= 8 and a block whose batch slices fill the warps' tiles
+  static const bool wl_off = getenv("ITN_BLOCK_WL") && atoi(getenv("ITN_BLOCK_WL")) == 0;
+  const bool wl_ok = !wl_off && chimax <= 8;
   bool ok = true;
-  for (int w = 0; w < 3 && ok; ++w) ok = choose_pass(s, g->h, w, cplx, g->KS, nverts, g->pass[w]);
+  // (measured, 8^3 chi = 6: warp-local plans whose per-warp tables need padding tiles or lose the conflict-free fibre
+  // order -- a slice holds one parity of the site index -- execute 20 % more instructions and 5x the bank conflicts,
+  // which costs more than the barriers they save; chi = 8 and 4 plan exactly and gain 5 %)
+  for (int w = 0; w < 3 && ok; ++w) {
+    ok = choose_pass(s, g->h, w, cplx, g->KS, nverts, g->pass[w], false);
+    if (ok && wl_ok) {
+      PassPlan wp;
+      bool exact = true;
+      if (choose_pass(s, g->h, w, cplx, g->KS, nverts, wp, true)) {
+        for (int k = 0; k < wp.desc.nmodes; ++k) exact = exact && wp.desc.modes[k].exact;
+        const bool force = getenv("ITN_BLOCK_WL") && atoi(getenv("ITN_BLOCK_WL")) == 2;  // experiments: always
+        if (force || (exact && wp.excess <= g->pass[w].excess + (int)(wp.table.size() / 80))) g->pass[w] = std::move(wp);
+      }
+    }
+  }
   if (!ok) g->KS = 0;
   if (ok && block_debug()) {
     fprintf(stderr, "[itn block] d=%d z=%d chi=", s.d, s.z);
@@ -1280,8 +1560,10 @@ const Geometry* geometry_for(const Signature& s, bool cplx, size_t nverts) {
       for (int l = 0; l < P.nlev; ++l) fprintf(stderr, "%dx%d ", P.lev_n[l], P.lev_s[l]);
       fprintf(stderr, "strides=");
       for (int k = 0; k < P.nmodes; ++k) fprintf(stderr, "%d ", P.modes[k].S);
-      fprintf(stderr, "PL=%d nbuf=%d bulk=%d ops=%d smem=%zu excess wavefronts=%d of %zu quads\n", P.PL, P.nbuf, P.bulk, P.nops,
-              g->pass[w].smem, g->pass[w].excess, g->pass[w].table.size() / 4);
+      fprintf(stderr, "PL=%d nbuf=%d bulk=%d ops=%d smem=%zu excess wavefronts=%d of %zu quads wl=%d eff=%.2f exact=", P.PL, P.nbuf,
+              P.bulk, P.nops, g->pass[w].smem, g->pass[w].excess, g->pass[w].table.size() / 4, P.wl, g->pass[w].eff);
+      for (int k = 0; k < P.nmodes; ++k) fprintf(stderr, "%d", P.modes[k].exact);
+      fprintf(stderr, "\n");
     }
   }
   const Geometry* r = g.get();
@@ -1328,12 +1610,12 @@ bool signature_of(const itn_net* net, int v, Signature& s) {
   return s.d >= 1 && s.d <= 8;
 }
 
-template <bool C, int KS, int MT, int NB>
+template <bool C, int KS, int MT, int NB, bool WL = false>
 void launch_inst(itn_ctx* ctx, cudaStream_t st, unsigned grid, size_t smem, const BlkPass* dp, const BlkVertex* dv,
                  const unsigned short* dt) {
-  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  k_block<C, KS, MT, NB><<<grid, kBT, smem, st>>>(*dp, dv, dt);  // the descriptor travels as a kernel parameter
+  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT, NB, WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_block<C, KS, MT, NB, WL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  k_block<C, KS, MT, NB, WL><<<grid, kBT, smem, st>>>(*dp, dv, dt);  // the descriptor travels as a kernel parameter
   ITN_LAUNCH_CHECK(ctx);
 }
 
@@ -1342,8 +1624,11 @@ void launch_inst(itn_ctx* ctx, cudaStream_t st, unsigned grid, size_t smem, cons
 void launch_pass(itn_ctx* ctx, cudaStream_t st, bool cplx, int KS, unsigned grid, size_t smem, const BlkPass* dp,
                  const BlkVertex* dv, const unsigned short* dt) {
   const bool three = KS <= 4 && smem <= kSmemThreeCtasMax;
-#define ITN_BLK(Cx, K, M)                                                                   \
-  return three ? launch_inst<Cx, K, M, 3>(ctx, st, grid, smem, dp, dv, dt)                   \
+#define ITN_BLK(Cx, K, M)                                                                              \
+  if (dp->wl)                                                                                          \
+    return three ? launch_inst<Cx, K, M, 3, true>(ctx, st, grid, smem, dp, dv, dt)                      \
+                 : launch_inst<Cx, K, M, 2, true>(ctx, st, grid, smem, dp, dv, dt);                     \
+  return three ? launch_inst<Cx, K, M, 3>(ctx, st, grid, smem, dp, dv, dt)                              \
                : launch_inst<Cx, K, M, 2>(ctx, st, grid, smem, dp, dv, dt)
   if (cplx) {
     switch (KS) {
@@ -1358,7 +1643,9 @@ void launch_pass(itn_ctx* ctx, cudaStream_t st, bool cplx, int KS, unsigned grid
     switch (KS) {
       case 1: ITN_BLK(false, 1, 1);
       case 2: ITN_BLK(false, 2, 1);
-      case 4: ITN_BLK(false, 4, 2);
+      case 4:
+        return three ? launch_inst<false, 4, 2, 3>(ctx, st, grid, smem, dp, dv, dt)
+                     : launch_inst<false, 4, 2, 2>(ctx, st, grid, smem, dp, dv, dt);
       default: return launch_inst<false, 8, 4, 2>(ctx, st, grid, smem, dp, dv, dt);
     }
   }
@@ -1567,7 +1854,7 @@ void itn_block_bp_end(itn_net* net) {
 // Instrumentation (host only, no device needed): the geometry the block path would use for a vertex signature, as a flat
 // int32 stream, so that tests can replay the operation lists and fibre tables on the host (tests/block_emulator.py):
 //   KS, MT, h, then per pass: nblk, nrows, rowlen, grow, gblk, nlev, lev_n[4], lev_s[4], PL, bufsz, nbuf, bulk, load_p, smem
-//   bytes, excess wavefronts, nmodes, {chi, S, ntile, tab, slot} x nmodes, nops, {type, src, dst, mode} x nops, tab_len, table...
+//   bytes, excess wavefronts, wl, nmodes, {chi, S, ntile, tab, slot} x nmodes, nops, {type, src, dst, mode} x nops, tab_len, table...
 extern "C" int itn_block_plan_export(int dtype, int d, int z, const int32_t* chi, int nverts, int32_t* out, int cap, int32_t* nout) {
   try {
     if (!chi || !nout || z < 1 || z > 8 || (dtype != ITN_F64 && dtype != ITN_C128)) {
@@ -1596,7 +1883,7 @@ extern "C" int itn_block_plan_export(int dtype, int d, int z, const int32_t* chi
                           (long long)P.lev_n[0], (long long)P.lev_n[1], (long long)P.lev_n[2], (long long)P.lev_n[3],
                           (long long)P.lev_s[0], (long long)P.lev_s[1], (long long)P.lev_s[2], (long long)P.lev_s[3], (long long)P.PL,
                           (long long)P.bufsz, (long long)P.nbuf, (long long)P.bulk, (long long)P.load_p, (long long)g->pass[w].smem,
-                          (long long)g->pass[w].excess, (long long)P.nmodes})
+                          (long long)g->pass[w].excess, (long long)P.wl, (long long)P.nmodes})
         v.push_back((int32_t)x);
       for (int k = 0; k < P.nmodes; ++k)
         for (int x : {P.modes[k].chi, P.modes[k].S, P.modes[k].ntile, P.modes[k].tab, P.modes[k].slot}) v.push_back(x);  // (exact is derived)

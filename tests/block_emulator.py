@@ -42,7 +42,7 @@ class Plan:
             p.nblk, p.nrows, p.rowlen, p.grow, p.gblk, p.nlev = [next(it) for _ in range(6)]
             p.lev_n = [next(it) for _ in range(4)]
             p.lev_s = [next(it) for _ in range(4)]
-            p.PL, p.bufsz, p.nbuf, p.bulk, p.load_p, p.smem, p.excess, p.nmodes = [next(it) for _ in range(8)]
+            p.PL, p.bufsz, p.nbuf, p.bulk, p.load_p, p.smem, p.excess, p.wl, p.nmodes = [next(it) for _ in range(9)]
             p.modes = [dict(zip(("chi", "S", "ntile", "tab", "slot"), [next(it) for _ in range(5)])) for _ in range(p.nmodes)]
             nops = next(it)
             p.ops = [tuple(next(it) for _ in range(4)) for _ in range(nops)]
@@ -75,8 +75,11 @@ class Plan:
             s0 = self._row_pos(p, row)
             dst_flat[g0:g0 + p.rowlen] = buf[s0:s0 + p.rowlen]
 
-    def _fibres(self, p, m):
+    def _fibres(self, p, m, warp=None):
+        """Fibre bases of a mode; warp-local passes: tile ft belongs to warp ft % 8."""
         t = p.table[m["tab"]:m["tab"] + 8 * m["ntile"]]
+        if warp is not None:
+            t = t.reshape(-1, 8)[warp::8].reshape(-1)
         return t[t != NO_FIBRE]
 
     def run_pass(self, w, x_flat, pin_flat, msgs):
@@ -89,23 +92,35 @@ class Plan:
             bufs[0] = self._stage(p, x_flat, blk)
             if p.load_p:
                 bufs[1] = self._stage(p, pin_flat, blk)
+            # warp-local passes: every warp runs the WHOLE operation list on its own tiles before the next warp starts
+            # (no CTA barrier between operations on the device); the store waits for all of them
+            for warp in (range(8) if p.wl else [None]):
+                for (typ, src, dst, mode) in p.ops:
+                    if typ == OP_MP:
+                        m = p.modes[mode]
+                        f = self._fibres(p, m, warp)
+                        if len(f) == 0:
+                            continue
+                        msg = msgs[m["slot"]]
+                        idx = f[:, None] + m["S"] * np.arange(m["chi"])[None, :]      # [fibre, a]
+                        res = bufs[src][idx] @ msg                                   # out[f, b] = sum_a in[f, a] M[a, b]
+                        assert not np.any(np.isnan(res)), "a mode product read an element nobody wrote"
+                        if bufs[dst] is None:
+                            bufs[dst] = np.full(p.PL, np.nan, dtype=x_flat.dtype)
+                        elif dst == src and not p.wl:
+                            bufs[dst] = bufs[dst].copy()
+                        bufs[dst][idx] = res
+                    elif typ == OP_CLOSE:
+                        m = p.modes[mode]
+                        f = self._fibres(p, m, warp)
+                        if len(f) == 0:
+                            continue
+                        idx = f[:, None] + m["S"] * np.arange(m["chi"])[None, :]
+                        part = bufs[src][idx].T @ bufs[0][idx].conj()
+                        assert not np.any(np.isnan(part)), "a close read an element nobody wrote"
+                        outs[m["slot"]] = outs.get(m["slot"], 0) + part
             for (typ, src, dst, mode) in p.ops:
-                if typ == OP_MP:
-                    m = p.modes[mode]
-                    f = self._fibres(p, m)
-                    msg = msgs[m["slot"]]
-                    idx = f[:, None] + m["S"] * np.arange(m["chi"])[None, :]      # [fibre, a]
-                    res = bufs[src][idx] @ msg                                   # out[f, b] = sum_a in[f, a] M[a, b]
-                    if bufs[dst] is None or dst == src:
-                        nb = np.full(p.PL, np.nan, dtype=x_flat.dtype) if bufs[dst] is None else bufs[dst].copy()
-                        bufs[dst] = nb
-                    bufs[dst][idx] = res
-                elif typ == OP_CLOSE:
-                    m = p.modes[mode]
-                    f = self._fibres(p, m)
-                    idx = f[:, None] + m["S"] * np.arange(m["chi"])[None, :]
-                    outs[m["slot"]] = outs.get(m["slot"], 0) + bufs[src][idx].T @ bufs[0][idx].conj()
-                else:
+                if typ == OP_STORE:
                     self._unstage(p, bufs[src], wout, blk)
         return wout, outs
 
@@ -129,4 +144,7 @@ class Plan:
                 f = self._fibres(p, m)
                 assert len(f) == len(set(f.tolist())) == nb // m["chi"], (len(f), nb // m["chi"])
                 assert f.min() >= 0 and f.max() + m["S"] * (m["chi"] - 1) < p.PL
-            assert p.nbuf * p.bufsz * 8 + 8192 <= p.smem <= 227 * 1024
+            assert p.nbuf * p.bufsz * 8 + (0 if p.wl else 8192) <= p.smem <= 227 * 1024
+            if p.wl:
+                for m in p.modes:
+                    assert m["ntile"] % 8 == 0
