@@ -243,6 +243,9 @@ int itn_ctx_launch_count(const itn_ctx* ctx, int64_t* out);
 /* Message updates computed so far on ctx by {the degree-4 chi=16 tile path (csrc/itn_fast.cu), the block path
  * (csrc/itn_block.cu), the shape-generic per-message / per-vertex kernels (csrc/itn_generic.cu)}: which kernels ran. */
 int itn_ctx_path_counts(const itn_ctx* ctx, int64_t* out3);
+/* Gate sides (itn_apply2 / itn_apply_layers on ctx so far) whose R factor was refined by a second Cholesky pass on
+ * A R1^+ (CholeskyQR2): the sides where the reference's QR (src/apply.jl:70-76) sees an ill-conditioned matrix. */
+int itn_ctx_cholqr2_count(const itn_ctx* ctx, int64_t* out);
 /* Select the message-update implementation: 0 = auto (DMMA tile path where a bucket qualifies, the shape-generic
  * DMMA kernels otherwise), 1 = shape-generic DMMA kernels only, 2 = plain FMA kernels only (the parity tests use
  * 1 and 2 as second and third opinions on the device). */

@@ -571,6 +571,7 @@ static void ctx_destroy_now(itn_ctx* ctx) {
   }
   big_trim(ctx, 0);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->pinned_flags) cudaFreeHost(ctx->pinned_flags);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1849,6 +1850,13 @@ extern "C" int itn_ctx_path_counts(const itn_ctx* ctx, int64_t* out3) {
   API_BEGIN
   ITN_REQUIRE(ctx && out3, ITN_EINVAL, "NULL argument");
   for (int i = 0; i < 3; ++i) out3[i] = ctx->path_msgs[i];
+  API_END
+}
+
+extern "C" int itn_ctx_cholqr2_count(const itn_ctx* ctx, int64_t* out) {
+  API_BEGIN
+  ITN_REQUIRE(ctx && out, ITN_EINVAL, "NULL argument");
+  *out = ctx->cholqr2_sides;
   API_END
 }
 

@@ -733,7 +733,7 @@ void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs) {
     ITN_REQUIRE(z + 1 <= ITN_MAX_MODES, ITN_EUNSUPPORTED, "vertex degree too large");
     VJob J;
     memset(&J, 0, sizeof(J));
-    J.a = net->T[v].p;
+    J.a = sp.tensor ? sp.tensor : net->T[v].p;
     J.b = (net->has_bra() && net->Tb[v].p) ? net->Tb[v].p : nullptr;
     J.n = net->T[v].n;
     J.nm = z + 1;

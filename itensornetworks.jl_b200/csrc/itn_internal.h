@@ -45,6 +45,7 @@ struct itn_ctx {
   void* nccl = nullptr;      // ncclComm_t
   void* nccl_lib = nullptr;  // dlopen handle
   int64_t launches = 0;
+  int64_t cholqr2_sides = 0;         // gate sides whose R factor took the second pass (CholeskyQR2, itn_apply2)
   int64_t path_msgs[3] = {0, 0, 0};  // messages computed by the tile path, the block path and the shape-generic kernels
   int nets_alive = 0;          // handles created on this context and not yet destroyed
   bool destroy_pending = false;  // itn_ctx_destroy was called while networks were alive (finalizer order)
@@ -58,6 +59,8 @@ struct itn_ctx {
   std::multimap<size_t, void*> big_free;        // size -> block
   std::unordered_map<void*, size_t> big_live;   // block -> size
   size_t big_cached = 0;                        // bytes parked in big_free
+  int* pinned_flags = nullptr;                  // page-locked landing zone of small device flags (grown on demand)
+  size_t pinned_flags_n = 0;
 };
 
 // Planar storage: re plane [0, n), im plane [n, 2n) (complex only).
@@ -202,6 +205,8 @@ struct JobSpec {
   const double* const* mats = nullptr;
   // true: no message is absorbed on any closed bond (plain Gram matrix of the site tensor over the closed modes)
   bool no_messages = false;
+  // optional: a tensor of the same shape that stands in for the site tensor of v (device, canonical planar)
+  const double* tensor = nullptr;
 };
 // Runs all specs in [lo, hi) batches bounded by the workspace budget. Results in spec.out.
 void itn_run_vertex_jobs(itn_net* net, const std::vector<JobSpec>& specs);

@@ -853,12 +853,16 @@ struct CholJob {
   int* ok;
   int n;
   double shift_rel;
+  int* cond = nullptr;  // optional: set to 1 when the factorisation succeeded but min pivot / max pivot < kCholCondRatio
 };
+// Pivot ratio of the Gram matrix below which the R factor is refined by a second pass (CholeskyQR2, itn_apply2): the
+// ratio bounds kappa(C) = kappa(A~)^2 from below, and the updated pair of a gate carries 30 kappa^2 eps without it.
+constexpr double kCholCondRatio = 1e-4;
 
 template <bool C>
 __global__ void __launch_bounds__(64) k_chol(const CholJob* __restrict__ jobs) {
   extern __shared__ double sm[];
-  __shared__ double s_piv, s_max, s_tr;
+  __shared__ double s_piv, s_max, s_tr, s_pmin, s_pmax;
   __shared__ int s_fail;
   const CholJob J = jobs[blockIdx.x];
   const int n = J.n, n2 = n * n;
@@ -881,6 +885,8 @@ __global__ void __launch_bounds__(64) k_chol(const CholJob* __restrict__ jobs) {
     s_max = mx;
     s_tr = tr;
     s_fail = 0;
+    s_pmin = 1e300;
+    s_pmax = 0.0;
   }
   __syncthreads();
   const double shift = J.shift_rel * s_tr;
@@ -892,6 +898,8 @@ __global__ void __launch_bounds__(64) k_chol(const CholJob* __restrict__ jobs) {
       const double d = Kr[k + n * k];
       if (!(d > thr)) s_fail = 1;
       s_piv = d;
+      s_pmin = fmin(s_pmin, d);
+      s_pmax = fmax(s_pmax, d);
     }
     __syncthreads();
     if (s_fail) break;
@@ -919,7 +927,10 @@ __global__ void __launch_bounds__(64) k_chol(const CholJob* __restrict__ jobs) {
     if (i == 0) *J.ok = 0;
     return;
   }
-  if (i == 0) *J.ok = 1;
+  if (i == 0) {
+    *J.ok = 1;
+    if (J.cond) *J.cond = (s_pmin < kCholCondRatio * s_pmax) ? 1 : 0;
+  }
   if (!J.R || i >= n) return;
   // R[a, o] = conj(L[o, a]) (upper triangular)
   for (int a = 0; a < n; ++a) {
@@ -1538,6 +1549,138 @@ __global__ void __launch_bounds__(256) k_thin_pinv(const ThinJob* __restrict__ j
   if (threadIdx.x == 0) *J.ok = 1;
 }
 
+// R^+ of a thin side, refined: the explicit G^-1 = conj(Gp Gp^H) of k_thin_pinv carries kappa(R)^2 eps.  With
+//   Y = R^H conj(Gp)            (n x X, orthonormal columns up to kappa^2 eps: Y^H Y = Gp^T G conj(Gp) ~ 1)
+//   R^+ = Y (Y^H Y)^-1 Gp^T     (R R^+ = 1 holds for ANY invertible Gp; the inverted matrix is ~ 1, so the result
+//                                carries kappa eps from forming Y and nothing else)
+// the pseudo-inverse is what CholeskyQR2 gives for R^H.  (Y^H Y)^-1 by Gauss-Jordan without pivoting (the matrix is
+// Hermitian positive definite and within kappa^2 eps of the identity).  One CTA per job, everything in shared memory.
+template <bool C>
+__global__ void __launch_bounds__(256) k_thin_pinv2(const ThinJob* __restrict__ jobs) {
+  extern __shared__ double sm[];
+  __shared__ int s_ok;
+  __shared__ double s_pr, s_pi;
+  const ThinJob J = jobs[blockIdx.x];
+  const int X = J.X, n = J.n, x2 = X * X, nx = n * X;
+  if (threadIdx.x == 0) {
+    int ok = *J.okG;
+    for (int q = 0; q < J.n_env; ++q) ok = ok && J.ok_env[q];
+    s_ok = ok;
+  }
+  __syncthreads();
+  if (!s_ok) return;  // *J.ok stays 0: eigen route
+  constexpr int P = C ? 2 : 1;
+  double* Yr = sm;                 // [P][n x X]
+  double* Yi = sm + nx;
+  double* Ar = sm + P * nx;        // [P][X x 2X]: augmented (Y^H Y | 1) -> (1 | W); row a, column b at a + X b
+  double* Ai = Ar + 2 * x2;
+  double* Mr = Ar + P * 2 * x2;    // [P][X x X]: M = W Gp^T
+  double* Mi = Mr + x2;
+  const long long rn = (long long)X * n;
+  // Y[o, i] = sum_k conj(R[k, o]) conj(Gp[k, i])
+  for (int idx = threadIdx.x; idx < nx; idx += blockDim.x) {
+    const int o = idx % n, i = idx / n;
+    double ar = 0.0, ai = 0.0;
+    for (int k = 0; k < X; ++k) {
+      const double xr = J.R[k + (long long)X * o], gr = J.Gp[k + X * i];
+      if (C) {
+        const double xi = J.R[rn + k + (long long)X * o], gi = J.Gp[x2 + k + X * i];
+        ar += xr * gr - xi * gi;     // conj(x) conj(g) = conj(x g)
+        ai -= xr * gi + xi * gr;
+      } else {
+        ar += xr * gr;
+      }
+    }
+    Yr[idx] = ar;
+    if (C) Yi[idx] = ai;
+  }
+  __syncthreads();
+  // A = (Y^H Y | 1)
+  for (int idx = threadIdx.x; idx < 2 * x2; idx += blockDim.x) {
+    const int a = idx % X, b = idx / X;
+    double ar = 0.0, ai = 0.0;
+    if (b < X) {
+      for (int o = 0; o < n; ++o) {
+        const double pr = Yr[o + n * a], qr = Yr[o + n * b];
+        if (C) {
+          const double pi = Yi[o + n * a], qi = Yi[o + n * b];
+          ar += pr * qr + pi * qi;   // conj(p) q
+          ai += pr * qi - pi * qr;
+        } else {
+          ar += pr * qr;
+        }
+      }
+    } else {
+      ar = (b - X == a) ? 1.0 : 0.0;
+    }
+    Ar[idx] = ar;
+    if (C) Ai[idx] = ai;
+  }
+  __syncthreads();
+  // Gauss-Jordan: after step k column k of the left half is e_k
+  for (int k = 0; k < X; ++k) {
+    if (threadIdx.x == 0) {
+      const double pr = Ar[k + X * k], pi = C ? Ai[k + X * k] : 0.0;
+      const double den = pr * pr + pi * pi;
+      s_pr = pr / den;               // 1 / pivot
+      s_pi = -pi / den;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 2 * X; b += blockDim.x) {  // scale row k
+      const double vr = Ar[k + X * b], vi = C ? Ai[k + X * b] : 0.0;
+      Ar[k + X * b] = vr * s_pr - vi * s_pi;
+      if (C) Ai[k + X * b] = vr * s_pi + vi * s_pr;
+    }
+    __syncthreads();
+    // rows a != k: row_a -= A[a, k] row_k, columns b > k only (the others are already final or unused)
+    for (int idx = threadIdx.x; idx < X * (2 * X - k - 1); idx += blockDim.x) {
+      const int a = idx % X, b = k + 1 + idx / X;
+      if (a == k) continue;
+      const double fr = Ar[a + X * k], fi = C ? Ai[a + X * k] : 0.0;
+      const double vr = Ar[k + X * b], vi = C ? Ai[k + X * b] : 0.0;
+      Ar[a + X * b] -= fr * vr - fi * vi;
+      if (C) Ai[a + X * b] -= fr * vi + fi * vr;
+    }
+    __syncthreads();
+  }
+  // M = W Gp^T:  M[a, i] = sum_b W[a, b] Gp[i, b]
+  for (int idx = threadIdx.x; idx < x2; idx += blockDim.x) {
+    const int a = idx % X, i = idx / X;
+    double ar = 0.0, ai = 0.0;
+    for (int b = 0; b < X; ++b) {
+      const double wr = Ar[a + X * (X + b)], gr = J.Gp[i + X * b];
+      if (C) {
+        const double wi = Ai[a + X * (X + b)], gi = J.Gp[x2 + i + X * b];
+        ar += wr * gr - wi * gi;
+        ai += wr * gi + wi * gr;
+      } else {
+        ar += wr * gr;
+      }
+    }
+    Mr[idx] = ar;
+    if (C) Mi[idx] = ai;
+  }
+  __syncthreads();
+  // R^+ = Y M
+  for (int idx = threadIdx.x; idx < nx; idx += blockDim.x) {
+    const int o = idx % n, i = idx / n;
+    double ar = 0.0, ai = 0.0;
+    for (int k = 0; k < X; ++k) {
+      const double yr = Yr[o + n * k], mr = Mr[k + X * i];
+      if (C) {
+        const double yi = Yi[o + n * k], mi = Mi[k + X * i];
+        ar += yr * mr - yi * mi;
+        ai += yr * mi + yi * mr;
+      } else {
+        ar += yr * mr;
+      }
+    }
+    J.Rp[o + (long long)n * i] = ar;
+    if (C) J.Rp[rn + o + (long long)n * i] = ai;
+  }
+  if (threadIdx.x == 0) *J.ok = 1;
+}
+
 // ---- shared-memory versions of the three glue kernels (one CTA per gate / gate side; operands staged once) ----------
 // The plain kernels above read every operand element from global memory once per output element; at 2048 gates per
 // layer they cost ~1 ms each although they move < 0.3 GB.  Selected when the operands of every gate of the batch fit.
@@ -1694,6 +1837,53 @@ __global__ void __launch_bounds__(256) k_su_T_s(const SuEdge* __restrict__ edges
     }
     E.T[side][idx] = accr;
     if (C) E.T[side][tot + idx] = acci;
+  }
+}
+
+// CholeskyQR2: R <- R2 R1 (n x n, column-major R[i + n o]) and R^+ <- R1^+ R2^+ when the second factorisation succeeded
+struct ComposeJob {
+  double* R;         // in: R1, out: R2 R1
+  double* Rp;        // in: R1^+, out: R1^+ R2^+
+  const double* R2;
+  const double* Rp2;
+  const int* ok2;
+  int n;
+};
+template <bool C>
+__global__ void __launch_bounds__(256) k_su_compose(const ComposeJob* __restrict__ jobs) {
+  extern __shared__ double sm[];
+  const ComposeJob J = jobs[blockIdx.x];
+  if (!*J.ok2) return;
+  const int n = J.n, n2 = n * n;
+  constexpr int PLN = C ? 2 : 1;
+  double* a = sm;              // R1, then R1^+
+  double* b = sm + PLN * n2;   // R2, then R2^+
+  for (int which = 0; which < 2; ++which) {
+    double* dst = which ? J.Rp : J.R;
+    const double* lhs = which ? a : b;  // R = R2 R1; R^+ = R1^+ R2^+
+    const double* rhs = which ? b : a;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PLN * n2; i += blockDim.x) {
+      a[i] = dst[i];
+      b[i] = (which ? J.Rp2 : J.R2)[i];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n2; idx += blockDim.x) {
+      const int r = idx % n, c = idx / n;
+      double xr = 0.0, xi = 0.0;
+      for (int k = 0; k < n; ++k) {
+        const double lr = lhs[r + n * k], rr = rhs[k + n * c];
+        if (C) {
+          const double li = lhs[n2 + r + n * k], ri = rhs[n2 + k + n * c];
+          xr += lr * rr - li * ri;
+          xi += lr * ri + li * rr;
+        } else {
+          xr += lr * rr;
+        }
+      }
+      dst[idx] = xr;
+      if (C) dst[n2 + idx] = xi;
+    }
   }
 }
 
@@ -2112,6 +2302,14 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   DevBuf rok(ctx, std::max<size_t>(2 * (size_t)n_own, 1) * sizeof(int)), env_ok(ctx, std::max<size_t>(env_count, 1) * sizeof(int));
   CUDA_CHECK(cudaMemsetAsync(rok.p, 0, std::max<size_t>(2 * (size_t)n_own, 1) * sizeof(int), ctx->stream));
   CUDA_CHECK(cudaMemsetAsync(env_ok.p, 0, std::max<size_t>(env_count, 1) * sizeof(int), ctx->stream));
+  // cond[2 oi + s] = 1: the Cholesky pivots of that bond environment span more than 1 / kCholCondRatio (CholeskyQR2 below)
+  DevBuf cond(ctx, std::max<size_t>(2 * (size_t)n_own, 1) * sizeof(int));
+  CUDA_CHECK(cudaMemsetAsync(cond.p, 0, std::max<size_t>(2 * (size_t)n_own, 1) * sizeof(int), ctx->stream));
+  struct Q2Cand {
+    int gate, side, ovr;  // ovr: index into `overrides`
+  };
+  std::vector<Q2Cand> q2cand;
+  static const bool no_q2 = getenv("ITN_NO_CHOLQR2") != nullptr;
   DevBuf sigs(ctx, std::max<size_t>(sig_total, 1) * sizeof(double)), perms(ctx, std::max<size_t>(sig_total, 1) * sizeof(int));
   // result rows of all gates: filled by the owner of each gate, summed over ranks
   DevBuf res(ctx, (size_t)n * RS * sizeof(double));
@@ -2220,7 +2418,13 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
         SvdJob gjob = {Cm, Vm, sp, pp, g.nn[s], g.nn[s], nullptr, okp};
         gj.push_back(gjob);
         E->rok[s] = okp;
-        if (g.r[s] == g.nn[s] && g.nn[s] <= 64) chol_r.push_back({Cm, E->R[s], E->Rp[s], okp, g.nn[s], 0.0});
+        if (g.r[s] == g.nn[s] && g.nn[s] <= 64) {
+          chol_r.push_back({Cm, E->R[s], E->Rp[s], okp, g.nn[s], 0.0});
+          if (g.loc[s] && !no_q2) {
+            chol_r.back().cond = cond.as<int>() + 2 * (size_t)g.oi + s;
+            q2cand.push_back({i, s, (int)overrides.size()});  // the overrides of this side are appended just below
+          }
+        }
         sp += g.nn[s];
         pp += g.nn[s];
       } else if (s == 1) {  // guest: C of the local side goes to the owner
@@ -2380,6 +2584,24 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     all.insert(all.end(), chol_env.begin(), chol_env.end());
     run_chol(ctx, cplx, all);
   }
+  // pivot-ratio flags of the bond environments travel to the host while the rest of step 2 is enqueued (CholeskyQR2 below)
+  // (page-locked destination: a copy to pageable memory would block the host right here)
+  const int* hcond = nullptr;
+  cudaEvent_t cond_ev = nullptr;
+  if (!q2cand.empty()) {
+    if (ctx->pinned_flags_n < 2 * (size_t)n_own) {
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // an earlier copy may still target the old block
+      if (ctx->pinned_flags) cudaFreeHost(ctx->pinned_flags);
+      ctx->pinned_flags = nullptr;
+      ctx->pinned_flags_n = 0;
+      CUDA_CHECK(cudaMallocHost((void**)&ctx->pinned_flags, 2 * (size_t)n_own * sizeof(int)));
+      ctx->pinned_flags_n = 2 * (size_t)n_own;
+    }
+    hcond = ctx->pinned_flags;
+    CUDA_CHECK(cudaEventCreateWithFlags(&cond_ev, cudaEventDisableTiming));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->pinned_flags, cond.p, 2 * (size_t)n_own * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaEventRecord(cond_ev, ctx->stream));
+  }
   if (!thin.empty()) {
     std::vector<const double*> tres;
     itn_run_modeprods(ctx, cplx, thin_specs, tres);
@@ -2399,13 +2621,28 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     else k_thin_gram<false><<<nt, 256, 0, ctx->stream>>>(dt);
     ITN_LAUNCH_CHECK(ctx);
     run_chol(ctx, cplx, thin_chol_G);
-    const size_t psm = (size_t)P * thin_maxX * thin_maxX * sizeof(double);
-    if (cplx) {
-      CUDA_CHECK(cudaFuncSetAttribute(k_thin_pinv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-      k_thin_pinv<true><<<nt, 256, psm, ctx->stream>>>(dt);
+    // refined pseudo-inverse (k_thin_pinv2) when its operands fit shared memory, the plain one otherwise
+    int thin_maxn = 1;
+    for (const ThinJob& t : thin) thin_maxn = std::max(thin_maxn, t.n);
+    const size_t psm2 = (size_t)P * ((size_t)thin_maxn * thin_maxX + 3 * (size_t)thin_maxX * thin_maxX) * sizeof(double);
+    static const bool no_pinv2 = getenv("ITN_NO_CHOLQR2") != nullptr;
+    if (psm2 <= kGlueSmemMax && !no_pinv2) {
+      if (cplx) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_thin_pinv2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm2));
+        k_thin_pinv2<true><<<nt, 256, psm2, ctx->stream>>>(dt);
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_thin_pinv2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm2));
+        k_thin_pinv2<false><<<nt, 256, psm2, ctx->stream>>>(dt);
+      }
     } else {
-      CUDA_CHECK(cudaFuncSetAttribute(k_thin_pinv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-      k_thin_pinv<false><<<nt, 256, psm, ctx->stream>>>(dt);
+      const size_t psm = (size_t)P * thin_maxX * thin_maxX * sizeof(double);
+      if (cplx) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_thin_pinv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        k_thin_pinv<true><<<nt, 256, psm, ctx->stream>>>(dt);
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_thin_pinv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        k_thin_pinv<false><<<nt, 256, psm, ctx->stream>>>(dt);
+      }
     }
     ITN_LAUNCH_CHECK(ctx);
     for (double* p : thin_scratch) itn_dev_free(ctx, p);  // stream ordered
@@ -2423,6 +2660,88 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     if (cplx) k_eig_fn<true><<<(unsigned)ej_fn.size(), 256, 0, ctx->stream>>>(de, 3, eig_cutoff);
     else k_eig_fn<false><<<(unsigned)ej_fn.size(), 256, 0, ctx->stream>>>(de, 3, eig_cutoff);
     ITN_LAUNCH_CHECK(ctx);
+  }
+  // CholeskyQR2 for ill-conditioned sides.  R from chol(A~^H A~) knows the small directions of A~ to kappa^2 eps only.
+  // Where the pivots say so, the factorisation is repeated on A1 = A R1^+ (a near-isometry on the (s, l) index, formed
+  // with the rebuild kernel): C2 = bond environment of A1 with the same messages, R2 = chol(C2), R = R2 R1 and
+  // R^+ = R1^+ R2^+.  One small read-back decides (no device idle time: see above); well-conditioned layers pay nothing else.
+  if (!q2cand.empty()) {
+    // the host waits for the flags only; the device keeps working on the Jacobi / support jobs enqueued above
+    const cudaError_t ce = cudaEventSynchronize(cond_ev);
+    cudaEventDestroy(cond_ev);
+    CUDA_CHECK(ce);
+    std::vector<SuSite> s2;
+    std::vector<JobSpec> spec2;
+    std::vector<CholJob> chol2;
+    std::vector<ComposeJob> comp;
+    std::vector<double*> scratch2;
+    long long maxn2 = 0;
+    int maxnn = 1;
+    size_t nflag = 0;
+    for (const Q2Cand& q : q2cand) nflag += hcond[2 * (size_t)geo[q.gate].oi + q.side] ? 1 : 0;
+    DevBuf ok2(ctx, std::max<size_t>(nflag, 1) * sizeof(int));
+    CUDA_CHECK(cudaMemsetAsync(ok2.p, 0, std::max<size_t>(nflag, 1) * sizeof(int), ctx->stream));
+    size_t fi = 0;
+    for (const Q2Cand& q : q2cand) {
+      const Geo& g = geo[q.gate];
+      const int sd = q.side;
+      if (!hcond[2 * (size_t)g.oi + sd]) continue;
+      const int v = g.v[sd], nn = g.nn[sd];
+      SuEdge& E = se[g.oi];
+      double* a1 = (double*)itn_dev_alloc(ctx, (size_t)net->T[v].n * P * sizeof(double));
+      double* mats = (double*)itn_dev_alloc(ctx, (size_t)3 * nn * nn * P * sizeof(double));  // C2, R2, R2^+
+      scratch2.push_back(a1);
+      scratch2.push_back(mats);
+      SuSite S;
+      S.a = net->T[v].p;
+      S.out = a1;
+      S.T = E.Rp[sd];
+      S.n_old = S.n_new = net->T[v].n;
+      long long lo = g.d[sd];
+      for (int j = 0; j < g.k[sd]; ++j) lo *= net->edim[net->inc[v][j]];
+      S.lo = lo;
+      S.hi = net->T[v].n / (lo * g.chi);
+      S.d = g.d[sd];
+      S.chi = S.chi_new = g.chi;
+      s2.push_back(S);
+      maxn2 = std::max(maxn2, S.n_new);
+      JobSpec spx;
+      spx.v = v;
+      spx.open_mask = 1u | (1u << (g.k[sd] + 1));
+      spx.out = mats;
+      spx.mats = overrides[q.ovr].data();
+      spx.tensor = a1;
+      spec2.push_back(spx);
+      const size_t n2 = (size_t)nn * nn * P;
+      chol2.push_back({mats, mats + n2, mats + 2 * n2, ok2.as<int>() + fi, nn, 0.0});
+      comp.push_back({E.R[sd], E.Rp[sd], mats + n2, mats + 2 * n2, ok2.as<int>() + fi, nn});
+      maxnn = std::max(maxnn, nn);
+      ++fi;
+    }
+    if (!s2.empty()) {
+      ctx->cholqr2_sides += (int64_t)s2.size();
+      DevBuf sb(ctx, s2.size() * sizeof(SuSite));
+      const SuSite* ds = itn_upload(ctx, s2, sb);
+      unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((maxn2 + 255) / 256, 128));
+      while (gy > 1 && (unsigned long long)gy * s2.size() > 148ull * 32ull) gy = (gy + 1) / 2;
+      if (cplx) k_su_rebuild<true><<<dim3((unsigned)s2.size(), gy), 256, 0, ctx->stream>>>(ds);
+      else k_su_rebuild<false><<<dim3((unsigned)s2.size(), gy), 256, 0, ctx->stream>>>(ds);
+      ITN_LAUNCH_CHECK(ctx);
+      itn_run_vertex_jobs(net, spec2);
+      run_chol(ctx, cplx, chol2);
+      DevBuf cb(ctx, comp.size() * sizeof(ComposeJob));
+      const ComposeJob* dc = itn_upload(ctx, comp, cb);
+      const size_t csm = (size_t)2 * P * maxnn * maxnn * sizeof(double);
+      if (cplx) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_su_compose<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        k_su_compose<true><<<(unsigned)comp.size(), 256, csm, ctx->stream>>>(dc);
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_su_compose<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        k_su_compose<false><<<(unsigned)comp.size(), 256, csm, ctx->stream>>>(dc);
+      }
+      ITN_LAUNCH_CHECK(ctx);
+      for (double* p : scratch2) itn_dev_free(ctx, p);  // stream ordered
+    }
   }
   trace.mark("launch_R");
   // ---- 3. theta', SVD, truncation (owned gates) ----

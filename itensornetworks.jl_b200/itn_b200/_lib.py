@@ -69,6 +69,7 @@ _SIGS = {
     "itn_block_plan_export": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _i32p]),
     "itn_ctx_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "itn_ctx_path_counts": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "itn_ctx_cholqr2_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "itn_ctx_set_path": (C.c_int, [_vp, C.c_int]),
     "itn_bp_last_timing": (C.c_int, [_vp, _dp, _dp]),
 }

@@ -72,6 +72,12 @@ class Context:
         check(lib().itn_ctx_path_counts(self.h, out))
         return tuple(int(x) for x in out)
 
+    def cholqr2_count(self):
+        """Gate sides whose R factor took the second Cholesky pass (ill-conditioned sites, csrc/itn_linalg.cu)."""
+        n = C.c_int64()
+        check(lib().itn_ctx_cholqr2_count(self.h, C.byref(n)))
+        return n.value
+
     def set_path(self, mode):
         """0 = auto (DMMA tile path where it applies), 1 = shape-generic DMMA kernels only, 2 = FMA kernels only."""
         check(lib().itn_ctx_set_path(self.h, int(mode)))

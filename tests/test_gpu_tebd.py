@@ -95,3 +95,52 @@ def test_tebd_step_single_call_equals_host_loop():
         assert np.array_equal(a.factor(v), b.factor(v))
     for (u, v) in g.edges:
         assert np.array_equal(a.message((u, v)), b.message((u, v)))
+
+
+def test_fifty_trotter_steps_track_the_oracle():
+    # 50 kicked-Ising steps on a 3 x 3 grid (200 gate layers, 600 truncations with cutoff = 1e-10 and maxdim = 4),
+    # BP re-run before every layer: the engine's Gram / Cholesky route (CholeskyQR2 where the pivots ask for it) and the
+    # oracle's QR route (src/apply.jl:70-93) must stay together gate by gate -- kept dimension equal, singular values and
+    # truncation error to 1e-10 -- and end with the same <Z>.  Both sides keep the Hermitian part of the messages
+    # (without it the reference's own phases drift after ~40 sweeps).
+    g = O.grid_graph((3, 3))
+    rng = np.random.default_rng(11)
+    tensors = []
+    for v in range(g.nv):
+        a = rng.standard_normal(2) + 1j * rng.standard_normal(2)
+        tensors.append((a / np.linalg.norm(a)).reshape((2,) + (1,) * g.degree(v)))
+    net = O.Network(g, [t.copy() for t in tensors], np.complex128)
+    psi = E.ITensorNetwork(E.NamedGraph(g.nv, g.edges), [t.copy() for t in tensors], np.complex128)
+    ctx = E.Context(0)
+    bpc = E.BeliefPropagationCache(psi, ctx=ctx)
+    msgs = O.identity_messages(net)
+    seq = O.parallel_edge_sequence(g)
+    sync = [[e] for e in seq]
+    layers = O.edge_coloring(g)
+    kick, zz = rx(0.4), rzz(-0.6)
+    maxdim, cutoff, sweeps = 4, 1e-10, 5
+    worst_sv = worst_te = 0.0
+    for step in range(50):
+        for v in range(g.nv):
+            net = O.apply1(net, v, kick)
+            E.apply(kick, bpc, (v,), inplace=True)
+        for layer in layers:
+            msgs, _, _ = O.bp_update(net, msgs, seq=seq, groups=O.synchronous_groups(seq), maxiter=sweeps, hermitize=True)
+            E.update(bpc, maxiter=sweeps, edge_sequence=sync, inplace=True)
+            info = E.apply_layer([zz] * len(layer), bpc, [g.edges[e] for e in layer], maxdim=maxdim, cutoff=cutoff,
+                                 normalize=True)
+            for i, e in enumerate(layer):
+                net, inf = O.simple_update_bp(net, msgs, e, zz, maxdim=maxdim, cutoff=cutoff, normalize=True)
+                msgs = O.reset_edge_messages(net, msgs, e)
+                n = inf["newdim"]
+                assert info["newdim"][i] == n, (step, e, info["newdim"][i], n)
+                sv = np.asarray(info["singular_values"][i])[:n]
+                worst_sv = max(worst_sv, float(np.max(np.abs(sv - inf["svals"][:n])) / inf["svals"][0]))
+                worst_te = max(worst_te, abs(info["truncation_error"][i] - inf["truncerr"]))
+    assert worst_sv < 1e-10 and worst_te < 1e-10, (worst_sv, worst_te)
+    msgs, _, _ = O.bp_update(net, msgs, seq=seq, groups=O.synchronous_groups(seq), maxiter=10, hermitize=True)
+    E.update(bpc, maxiter=10, edge_sequence=sync, inplace=True)
+    ez = E.expect(bpc, "Z")
+    worst = max(abs(ez[v] - O.expect1(net, msgs, v, O.PAULI_Z)) for v in range(g.nv))
+    assert worst < 1e-9, worst
+    assert max(bpc.edge_dim(e) for e in range(g.ne)) == maxdim
