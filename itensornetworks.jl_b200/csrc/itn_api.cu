@@ -1054,6 +1054,11 @@ constexpr size_t kUploadChunkBytes = (size_t)256 << 20;
 
 // Copies every registered-but-deferred host tensor to the device (all consumers other than the pipelined first BP sweep).
 void itn_flush_pending(itn_net* net) {
+  itn_canon_ensure_all(net);
+  itn_flush_uploads(net);
+}
+
+void itn_flush_uploads(itn_net* net) {
   if (net->pending.empty()) return;
   std::vector<PendingUpload> items;
   items.swap(net->pending);
@@ -1666,12 +1671,17 @@ extern "C" int itn_bp_update(itn_net* net, const int32_t* seq_src, const int32_t
       }
     }
     if (!pipelined_first) {
-      itn_flush_pending(net);
+      itn_flush_uploads(net);
       if (nfast > 0) {  // rebuild the tile-major copies (the block path's share of `handled` is kept)
         std::vector<char> h1;
         itn_fast_bp_plan(net, all_dids, all_src, h1, overlap_halo ? &cut_vertex : nullptr, &nfirst);
       }
     }
+  }
+  // vertices whose site tensor exists tile-major only (after a gate layer) and that this call reads canonically
+  if (net->n_canon_stale) {
+    if (sync_mode && nfast > 0) itn_canon_ensure_outside_sweep(net);
+    else itn_canon_ensure_all(net);
   }
   struct BlockCall {  // per-call buffers of the block path, released on every exit
     itn_net* net;

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) k_benv_reduce(const double* __restrict__ 
 struct RebJob {
   const double* X;   // tile-major old tensor (layout of the pair containing the gate bond)
   const double* T;   // planar n x (d chi'), n = 16 d
-  double* out;       // canonical planar new tensor
+  double* out;       // canonical planar new tensor; null: not written (lazy canonical copy, Fown / Foth are the truth)
   long long n_out;   // elements of the new tensor (offset of its imaginary plane)
   long long stI, stJ, stC, stQ;  // canonical strides of the tile's left / right index, the tile index and the CTA index
   int side, chi_new, inner_is_c;  // inner_is_c: the tile index c is the fastest bond (F2 tiles), else the left index is
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rebuild(const RebJob* __restric
   for (int sp = 0; sp < D; ++sp) store_acc<C>(Xs + (sp * kTilesPerCta + warp) * TS, acc[sp][0], acc[sp][1], lane);
   __syncthreads();
   // coalesced write-out: s' fastest, then the fastest bond of the canonical layout
-  const int total = kTilesPerCta * D * 256;
+  const int total = J.out ? kTilesPerCta * D * 256 : 0;
   for (int e = tid; e < total; e += kThreads) {
     const int sp = e % D;
     int w, i, jj;
@@ -609,7 +609,59 @@ struct FastCache {
   std::vector<const double*> built_ptr;  // [nb] and its storage
   std::vector<int> sweep_verts;    // vertices of `sweep`, position order
   std::vector<int> direct;         // slots whose tile-major copies were rewritten by k_rebuild (pending itn_fast_commit_direct)
+  std::vector<int> lazy;           // ... and whose canonical copy k_rebuild did not write (marked canon_stale at the commit)
 };
+
+// tile-major F1 -> canonical planar [s, a1, a2, a3, a4] (the inverse of k_fast_relayout_f1): block (job, a4) writes one
+// contiguous d * 4096 slab
+struct UnlayoutJob {
+  double* dst;
+  long long n;
+  long long slot;
+};
+template <bool C>
+__global__ void __launch_bounds__(256) k_fast_unlayout_f1(const UnlayoutJob* __restrict__ jobs, const double* __restrict__ F1, int d) {
+  constexpr int TILE = C ? 512 : 256;
+  const UnlayoutJob J = jobs[blockIdx.x];
+  const int a4 = blockIdx.y;
+  const size_t base = (size_t)J.slot * d * 256 * TILE;
+  double* dst = J.dst + (size_t)a4 * 4096 * d;
+  for (int i = threadIdx.x; i < 4096 * d; i += blockDim.x) {
+    const int s = i % d, r = i / d;
+    const int a1 = r & 15, a2 = (r >> 4) & 15, a3 = r >> 8;
+    const size_t o = base + (((size_t)s * 16 + a4) * 16 + a3) * TILE + swz(a1, a2);
+    dst[i] = F1[o];
+    if (C) dst[J.n + i] = F1[o + 256];
+  }
+}
+
+void canon_ensure_list(itn_net* net, FastCache* fc, const std::vector<int>& verts) {
+  if (verts.empty()) return;
+  ITN_REQUIRE(fc && fc->F1, ITN_EINVAL, "lazy canonical copy without tile-major storage");
+  itn_ctx* ctx = net->ctx;
+  std::vector<UnlayoutJob> jobs;
+  for (int v : verts) {
+    ITN_REQUIRE(fc->vslot[v] >= 0 && net->T[v].p, ITN_EINVAL, "lazy canonical copy of a vertex outside the tile bucket");
+    jobs.push_back({net->T[v].p, net->T[v].n, (long long)fc->vslot[v]});
+  }
+  DevBuf jb(ctx, jobs.size() * sizeof(UnlayoutJob));
+  const UnlayoutJob* dj = itn_upload(ctx, jobs, jb);
+  dim3 grid((unsigned)jobs.size(), 16);
+  if (net->cplx) k_fast_unlayout_f1<true><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, fc->d);
+  else k_fast_unlayout_f1<false><<<grid, 256, 0, ctx->stream>>>(dj, fc->F1, fc->d);
+  ITN_LAUNCH_CHECK(ctx);
+  for (int v : verts) {
+    net->canon_stale[v] = 0;
+    --net->n_canon_stale;
+  }
+}
+void canon_ensure_all_impl(itn_net* net, FastCache* fc) {
+  if (!net->n_canon_stale) return;
+  std::vector<int> verts;
+  for (int v = 0; v < net->nv; ++v)
+    if (net->canon_stale[v]) verts.push_back(v);
+  canon_ensure_list(net, fc, verts);
+}
 
 void release(itn_net* net, FastCache* fc) {
   itn_ctx* ctx = net->ctx;
@@ -720,7 +772,10 @@ FastCache* ensure_cache(itn_net* net) {
   }
   FastCache* fc = (FastCache*)net->fast;
   if (verts.empty()) {
-    if (fc) release(net, fc);
+    if (fc) {
+      canon_ensure_all_impl(net, fc);  // the tile-major copies are about to go
+      release(net, fc);
+    }
     return nullptr;
   }
   itn_ctx* ctx = net->ctx;
@@ -729,6 +784,7 @@ FastCache* ensure_cache(itn_net* net) {
   if (fc->topo_version != net->topo_version || fc->verts != verts) {
     bool fresh = false;
     if (fc->verts != verts || fc->d != d || !fc->F1) {  // same bucket (e.g. after a gate layer): keep the buffers
+      canon_ensure_all_impl(net, fc);  // the tile-major copies are about to go
       release(net, fc);
       fresh = true;
       fc->verts = verts;
@@ -784,6 +840,26 @@ FastCache* ensure_cache(itn_net* net) {
 }
 
 }  // namespace
+
+void itn_canon_ensure_all(itn_net* net) {
+  if (!net->n_canon_stale) return;
+  canon_ensure_all_impl(net, (FastCache*)net->fast);
+}
+void itn_canon_ensure(itn_net* net, int v) {
+  if (!net->n_canon_stale || !net->canon_stale[v]) return;
+  canon_ensure_list(net, (FastCache*)net->fast, {v});
+}
+void itn_canon_ensure_outside_sweep(itn_net* net) {
+  if (!net->n_canon_stale) return;
+  FastCache* fc = (FastCache*)net->fast;
+  std::vector<char> in_sweep(net->nv, 0);
+  if (fc)
+    for (int slot : fc->sweep) in_sweep[fc->verts[slot]] = 1;
+  std::vector<int> verts;
+  for (int v = 0; v < net->nv; ++v)
+    if (net->canon_stale[v] && !in_sweep[v]) verts.push_back(v);
+  canon_ensure_list(net, fc, verts);
+}
 
 void itn_fast_release(itn_net* net) {
   if (!net->fast) return;
@@ -1035,6 +1111,15 @@ void itn_fast_commit_direct(itn_net* net) {
     fc->built_ptr[slot] = net->T[v].p;
   }
   fc->direct.clear();
+  if (!fc->lazy.empty() && net->canon_stale.size() != (size_t)net->nv) net->canon_stale.assign(net->nv, 0);
+  for (int slot : fc->lazy) {
+    const int v = fc->verts[slot];
+    if (!net->canon_stale[v]) {
+      net->canon_stale[v] = 1;
+      ++net->n_canon_stale;
+    }
+  }
+  fc->lazy.clear();
 }
 
 void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs) {
@@ -1042,6 +1127,8 @@ void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs) {
   FastCache* fc = ensure_cache(net);
   ITN_REQUIRE(fc && fc->d == 2, ITN_EINVAL, "tile path is not available");
   fc->direct.clear();
+  fc->lazy.clear();
+  static const bool no_lazy = getenv("ITN_NO_LAZY_CANON") != nullptr;
   itn_ctx* ctx = net->ctx;
   std::vector<RebJob> rj(jobs.size());
   for (size_t j = 0; j < jobs.size(); ++j) {
@@ -1065,6 +1152,10 @@ void itn_fast_rebuild(itn_net* net, const std::vector<FastRebuildJob>& jobs) {
     R.Fown = direct ? (J.slot >= 2 ? fc->F2 : fc->F1) + off : nullptr;
     R.Foth = direct ? (J.slot >= 2 ? fc->F1 : fc->F2) + off : nullptr;
     if (direct) fc->direct.push_back(fc->vslot[J.v]);
+    if (direct && J.lazy && !no_lazy) {
+      R.out = nullptr;
+      fc->lazy.push_back(fc->vslot[J.v]);
+    }
     if (J.slot >= 2) {  // F2 tiles: (i, j) = (a3, a4), c = a1, q = a2
       R.X = fc->F2 + off;
       R.stI = st[2]; R.stJ = st[3]; R.stC = st[0]; R.stQ = st[1];

@@ -142,10 +142,19 @@ struct itn_net {
   std::vector<DevTensor> M;  // per directed edge
   uint64_t topo_version = 0;  // bumped whenever a tensor pointer / bond dim changes
   std::vector<uint64_t> tver;  // per vertex: bumped whenever the contents (or storage) of its site tensor change
-  void touch(int v) {
+  // Lazy canonical copies: after a gate layer on the tile path the new site tensor of a vertex may exist in the tile-major
+  // layouts only (k_rebuild skipped the canonical write; storage is allocated).  canon_stale[v] marks it; every reader of
+  // T[v] outside the tile kernels goes through itn_canon_ensure* first (itn_flush_pending does it for whole entry points).
+  std::vector<char> canon_stale;
+  int n_canon_stale = 0;
+  void touch(int v) {  // the canonical tensor of v was (re)written
     if (tver.size() != (size_t)nv) tver.assign(nv, 0);
     tver[v]++;
     topo_version++;
+    if (!canon_stale.empty() && canon_stale[v]) {
+      canon_stale[v] = 0;
+      --n_canon_stale;
+    }
   }
   double last_total_ms = 0, last_contract_ms = 0;
   std::vector<PendingUpload> pending;  // deferred host tensors: device storage exists, contents arrive with the next consumer
@@ -174,7 +183,12 @@ struct itn_net {
 };
 
 // copies every deferred host tensor (itn_net_set_tensors with ITN_HOST_DEFERRED) to the device; no-op when none is pending
-void itn_flush_pending(itn_net* net);
+void itn_flush_pending(itn_net* net);  // deferred uploads AND lazy canonical copies: T[v] is valid for every local vertex
+void itn_flush_uploads(itn_net* net);  // deferred uploads only (callers that handle canon_stale themselves)
+// materialise the canonical copy of vertices whose truth lives in the tile-major layouts (itn_fast.cu)
+void itn_canon_ensure_all(itn_net* net);
+void itn_canon_ensure(itn_net* net, int v);
+void itn_canon_ensure_outside_sweep(itn_net* net);  // every stale vertex that is not part of the planned tile sweep
 
 // ---- device memory helpers (stream ordered) ----
 void* itn_dev_alloc(itn_ctx* ctx, size_t bytes);
@@ -265,6 +279,7 @@ struct FastRebuildJob {
   int v, slot, chi_new;
   const double* T;             // planar n x (d chi_new)
   double* out;                 // new tensor, canonical planar
+  bool lazy = false;           // chi_new == 16: the canonical copy may be left unwritten (itn_net::canon_stale)
 };
 bool itn_fast_gate_site_ok(itn_net* net, int v);
 void itn_fast_bond_envs(itn_net* net, const std::vector<FastBenvJob>& jobs);

@@ -2172,8 +2172,11 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   ITN_REQUIRE(!net->has_bra(), ITN_EUNSUPPORTED, "gates are not defined for a bilinear form network (a bra layer is set)");
   if (n == 0) return ITN_OK;
   CUDA_CHECK(cudaSetDevice(net->ctx->device));
-  itn_flush_pending(net);
+  itn_flush_uploads(net);
   itn_ctx* ctx = net->ctx;
+  // sites on the tile path read and write the tile-major layouts only: their canonical copies may stay unwritten
+  // (itn_net::canon_stale); every other reader below calls itn_canon_ensure first
+  if (net->n_canon_stale && ctx->path_mode != 0) itn_canon_ensure_all(net);
   const bool cplx = net->cplx;
   const int P = net->planes();
   const bool multi = ctx->nranks > 1;
@@ -2435,6 +2438,8 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
         cur[g.peer].recvT += tsize(g);
       }
       if (!g.loc[s]) continue;
+      const bool tile_site = itn_fast_gate_site_ok(net, v);
+      if (!tile_site) itn_canon_ensure(net, v);
       // hermitised environments (map_eigvals symmetrises its argument, apply.jl:9-15 with ishermitian = true)
       overrides.emplace_back(net->inc[v].size(), nullptr);
       for (size_t j = 0; j < net->inc[v].size(); ++j) {
@@ -2512,7 +2517,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
           thin_maxX = std::max(thin_maxX, X);
         }
       }
-      if (itn_fast_gate_site_ok(net, v)) {
+      if (tile_site) {
         // degree 4, all bonds 16, d = 2: bond environment on the DMMA tile path
         fast_env.push_back({v, g.k[s], overrides.back().data(), Cm});
         fast_site[2 * (size_t)i + s] = 1;
@@ -2688,6 +2693,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
       if (!hcond[2 * (size_t)g.oi + sd]) continue;
       const int v = g.v[sd], nn = g.nn[sd];
       SuEdge& E = se[g.oi];
+      itn_canon_ensure(net, v);
       double* a1 = (double*)itn_dev_alloc(ctx, (size_t)net->T[v].n * P * sizeof(double));
       double* mats = (double*)itn_dev_alloc(ctx, (size_t)3 * nn * nn * P * sizeof(double));  // C2, R2, R2^+
       scratch2.push_back(a1);
@@ -2809,6 +2815,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
     for (size_t q = 0; q < pspec_site.size(); ++q)
       if (pspec_site[q] == std::make_pair(r.gate, r.side)) idx = (int)q;
     if (idx < 0) {
+      itn_canon_ensure(net, v);
       ModeProdSpec sp;
       memset(&sp, 0, sizeof(sp));
       sp.src = net->T[v].p;
@@ -2935,10 +2942,12 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
         toff += align32((size_t)S.n_new * P);
         sites.push_back(S);
         site_v.push_back(v);
-        if (fast_site[2 * (size_t)i + s] && S.a == net->T[v].p && newdim[i] <= 16)
-          fast_reb.push_back({v, g.k[s], newdim[i], S.T, S.out});
-        else
+        if (fast_site[2 * (size_t)i + s] && S.a == net->T[v].p && newdim[i] <= 16) {
+          fast_reb.push_back({v, g.k[s], newdim[i], S.T, S.out, /*lazy=*/!normalize});
+        } else {
+          itn_canon_ensure(net, v);
           slow_sites.push_back(S);
+        }
         nj.push_back({S.out, S.n_new * P});
         maxn = std::max(maxn, S.n_new);
       }
