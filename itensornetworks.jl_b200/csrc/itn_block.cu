@@ -317,7 +317,7 @@ __device__ __forceinline__ void op_mp(const OpConst& O, const int PL, const doub
 template <bool C, int MT>
 __device__ __forceinline__ void op_close(const OpConst& O, const int PL, const double* W, const double* X, double* red,
                                          double* __restrict__ out, const unsigned short* __restrict__ tab, const int warp,
-                                         const int lane, const int tid) {
+                                         const int lane, const int tid, const bool half_red) {
   constexpr int NPW = MT == 4 ? 2 : 1;
   const int chi = O.chi, S = O.S;
   const int mtj = (chi + 7) >> 3;
@@ -421,6 +421,40 @@ __device__ __forceinline__ void op_close(const OpConst& O, const int PL, const d
   }
   // partial tiles of the fibre splits meet in shared memory and are summed in split order
   const int ch2 = CH * CH;
+  if (half_red && mtd == 1) {
+    // half-size scratch (a plan that fits three CTAs per SM with it): warps 4..7 deposit their tiles, warps 0..3 add
+    // them to their own (each lane updates the elements it owns: no barrier between its read and its write), then the
+    // four sums are added in warp order -- ((w0 + w4) + (w1 + w5)) + ..., fixed, hence deterministic
+    double* r = red + (size_t)(warp & 3) * (C ? 2 : 1) * ch2;
+    const int row = g, col = 2 * t;
+    if (warp >= 4) {
+      r[row + CH * col] = acc[0][0][0];
+      r[row + CH * (col + 1)] = acc[0][0][1];
+      if (C) {
+        r[ch2 + row + CH * col] = acc[0][1][0];
+        r[ch2 + row + CH * (col + 1)] = acc[0][1][1];
+      }
+    }
+    __syncthreads();
+    if (warp < 4) {
+      r[row + CH * col] += acc[0][0][0];
+      r[row + CH * (col + 1)] += acc[0][0][1];
+      if (C) {
+        r[ch2 + row + CH * col] += acc[0][1][0];
+        r[ch2 + row + CH * (col + 1)] += acc[0][1][1];
+      }
+    }
+    __syncthreads();
+    const int n2 = chi * chi;
+    for (int i = tid; i < (C ? 2 : 1) * n2; i += kBT) {
+      const int p = i / n2, o = i - p * n2;
+      const int rw = o % chi, cl = o / chi;
+      double a = 0.0;
+      for (int s = 0; s < 4; ++s) a += red[(size_t)(s * (C ? 2 : 1) + p) * ch2 + rw + CH * cl];
+      out[i] = a;
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < NPW; ++q) {
     if (q < npw) {
@@ -445,9 +479,6 @@ __device__ __forceinline__ void op_close(const OpConst& O, const int PL, const d
   }
 }
 
-// Warp-local close (every extent of the pass <= 8: one 8 x 8 tile): the warp sums over ITS tiles (ft = warp, warp + 8, ...)
-// and keeps the partial tile in registers; the cross-warp sum of all closes of the pass happens once, at the end of k_block.
-// r: (re col 2t, re col 2t + 1, im col 2t, im col 2t + 1) of row g -- real: (col 2t, col 2t + 1).
 template <bool C>
 __device__ __forceinline__ void op_close_wl(const OpConst& O, const int PL, const double* W, const double* X,
                                             const unsigned short* __restrict__ tab, const int warp, const int lane,
@@ -654,7 +685,7 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
         ++ci;
       } else {
         double* out = V->part[O.slot] + (size_t)blk * PLN * O.chi * O.chi;
-        op_close<C, MT>(O, P.PL, bufs + O.src, bufs, red, out, tab, warp, lane, tid);
+        op_close<C, MT>(O, P.PL, bufs + O.src, bufs, red, out, tab, warp, lane, tid, P.red_len < kRedDoubles);
       }
     } else {
       if (WL) __syncthreads();  // rows of the store cross the warps' slices
@@ -913,6 +944,7 @@ struct PassPlan {
   size_t smem = 0;
   int excess = 0;
   double eff = 1.0;  // warp-local plans: real fibres / fibres of the padded per-warp tiles (averaged over the modes)
+  int chunk = 0, split = 0, pad_chunk = 0, pad_plane = 0;  // the PassChoice this plan was made with
 };
 
 // Emits "all but one" closes for the bond set [lo, hi) of the pass (local mode indices) from buffer T by divide and conquer.
@@ -1070,6 +1102,7 @@ struct PassChoice {
   int pad_chunk = 0;  // extra doubles between consecutive chunk slices (fast) -- tried by full evaluation
   int pad_plane = 0;
   bool wl = false;    // warp-local operation lists (every extent of the vertex <= 8)
+  bool half_red = false;  // barrier plans with one 8 x 8 tile per close: half-size cross-warp scratch (one more barrier per close)
 };
 
 // Builds the plan of one pass.  fast (passes 1 and 3): the block holds every index of (site, G1) and `chunk` values of G2's
@@ -1180,8 +1213,12 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
   P.load_p = which != 0;
   const int nm = (int)mode_slot.size();
   P.nmodes = nm;
-  // operation list
-  if (ch.wl) {
+  // operation list.  In-place products need one row tile per fibre (every extent of the vertex <= 8): then a tile's fibres
+  // are read and written by the same warp also when the tiles of an operation are dealt out across the warps, so the
+  // barrier plans use the in-place operation lists too (one buffer less: larger blocks, fewer fixed costs per flop)
+  static const bool no_inplace = getenv("ITN_BLOCK_NO_INPLACE") != nullptr;
+  const bool inplace = ch.wl || (!no_inplace && (cplx ? ks_inst <= 4 : ks_inst <= 2));
+  if (inplace) {
     EmitterWL em;
     em.P = &P;
     em.busy.assign(8, 0);
@@ -1243,7 +1280,7 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
   {
     const long long scratch = ch.wl ? (long long)P.nclose * kNW * (cplx ? 2 : 1) * 64 : 0;
     P.buf_total = (int)std::max<long long>((long long)P.nbuf * P.bufsz, scratch);
-    P.red_len = ch.wl ? 0 : kRedDoubles;
+    P.red_len = ch.wl ? 0 : (ch.half_red ? kRedDoubles / 2 : kRedDoubles);
   }
   // warp-local: the batch axes (no mode of the pass) are dealt out to the warps in contiguous, balanced runs
   std::vector<int> owner;  // batch value -> warp
@@ -1388,6 +1425,10 @@ bool plan_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, co
     P.msg_len = fits ? len : 0;
   }
   out.smem = pass_smem(P, tab_len);
+  out.chunk = ch.chunk;
+  out.split = ch.split;
+  out.pad_chunk = ch.pad_chunk;
+  out.pad_plane = ch.pad_plane;
   return true;
 }
 
@@ -1404,6 +1445,8 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, 
   const long long range = fast ? XR : L;
   PassChoice ch;
   ch.wl = wl;
+  // blocks sized for three CTAs per SM always take the half-size cross-warp scratch
+  ch.half_red = !wl && target_ctas(ks_inst) == 3 && (cplx ? ks_inst <= 4 : ks_inst <= 2);
   if (fast) {
     // bonds whose natural stride is fine stay inside the contiguous row
     long long S = d;
@@ -1481,6 +1524,22 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, 
       if (have && best.excess == 0) break;
     }
     if (have && best.excess == 0) break;
+  }
+  // a barrier plan of a small-extent vertex that misses three CTAs per SM by less than half the cross-warp scratch
+  // takes the half-size scratch (z = 6, chi = 6 pass 2: 77.4 -> 73.3 KB; 24 instead of 16 resident warps)
+  static const bool no_half = getenv("ITN_BLOCK_NO_HALF_RED") != nullptr;
+  const bool small = cplx ? ks_inst <= 4 : ks_inst <= 2;
+  if (have && !wl && small && !no_half && best.smem > kSmemThreeCtasMax &&
+      best.smem <= kSmemThreeCtasMax + (kRedDoubles / 2) * sizeof(double)) {
+    PassChoice t = ch;
+    t.chunk = best.chunk;
+    t.split = best.split;
+    t.pad_chunk = best.pad_chunk;
+    t.pad_plane = best.pad_plane;
+    t.half_red = true;
+    PassPlan hp;
+    if (plan_pass(sg, h, which, cplx, ks_inst, t, true, hp) && hp.smem <= kSmemThreeCtasMax && hp.excess <= best.excess)
+      best = std::move(hp);
   }
   return have;
 }
