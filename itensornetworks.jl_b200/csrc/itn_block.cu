@@ -112,6 +112,15 @@ __device__ __forceinline__ void dmma1684(double (&c)[4], double a0, double a1, d
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// shared-memory accesses by 32-bit byte address: the tile loops keep one base per reduction step / output row and add the
+// fibre's byte offset, one integer add per access (generic pointers cost the compiler two to three, and it rebuilds the
+// bases inside the loop when registers are short).  volatile keeps the loads of a tile ahead of its in-place stores.
+__device__ __forceinline__ double lds64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory"); }
 
 // Per-operation constants, computed once per CTA (one thread per operation) instead of once per warp and operation.
 struct OpConst {
@@ -164,11 +173,18 @@ __device__ __forceinline__ void mp_tiles(const OpConst& O, const int PL, const d
   const int g = lane >> 2, t = lane & 3;
   const int K2 = (C && !AL) ? 2 * chi : chi;
   const int ksj = EXACT ? KH : ((K2 + 3) >> 2);  // exact modes fill every step of the kernel instance
-  const int bS = b * S;
   const bool bok = b < chi;
-  auto load1 = [&](unsigned fb, int ks, int plane_off) -> double {
-    if (EXACT) return src[plane_off + fb + koff[ks]];
-    return (koff[ks] >= 0 && fb != kNoFibre) ? src[plane_off + fb + koff[ks]] : 0.0;
+  const unsigned PL8 = 8u * (unsigned)PL;
+  unsigned ak[KH];  // byte address of reduction entry (ks, lane & 3) of fibre 0
+#pragma unroll
+  for (int ks = 0; ks < KH; ++ks) ak[ks] = smem_u32(src) + 8u * (unsigned)(koff[ks] < 0 ? 0 : koff[ks]);
+  unsigned d0 = smem_u32(dst) + 8u * (unsigned)(b * S), d1 = d0 + PL8;
+  // opaque to the optimiser: otherwise it re-associates (f + b S) * 8 + base inside the loop, two instructions per store
+  asm volatile("" : "+r"(d0), "+r"(d1));
+  // fb: the table entry (fibre base in doubles, kNoFibre for padding)
+  auto load1 = [&](unsigned fb, int ks, unsigned plane_off8) -> double {
+    if (EXACT) return lds64(ak[ks] + (fb << 3) + plane_off8);
+    return (koff[ks] >= 0 && fb != kNoFibre) ? lds64(ak[ks] + (fb << 3) + plane_off8) : 0.0;
   };
   // results of one tile: lane holds (row b; fibres 2t, 2t + 1)
   auto store_tile = [&](unsigned fb, double r0, double r1, double i0, double i1) {
@@ -176,12 +192,12 @@ __device__ __forceinline__ void mp_tiles(const OpConst& O, const int PL, const d
     if (src == dst) __syncwarp();  // in place (one row tile per fibre): every lane has read its fibres
     if (bok) {
       if (EXACT || f0 != kNoFibre) {
-        dst[f0 + bS] = r0;
-        if (C) dst[PL + f0 + bS] = i0;
+        sts64(d0 + (f0 << 3), r0);
+        if (C) sts64(d1 + (f0 << 3), i0);
       }
       if (EXACT || f1 != kNoFibre) {
-        dst[f1 + bS] = r1;
-        if (C) dst[PL + f1 + bS] = i1;
+        sts64(d0 + (f1 << 3), r1);
+        if (C) sts64(d1 + (f1 << 3), i1);
       }
     }
   };
@@ -193,7 +209,7 @@ __device__ __forceinline__ void mp_tiles(const OpConst& O, const int PL, const d
       for (int ks = 0; ks < KH; ++ks)
         if (ks < ksj) {
           xr[ks] = load1(fb, ks, 0);
-          xi[ks] = load1(fb, ks, PL);
+          xi[ks] = load1(fb, ks, PL8);
         }
       double c1[4] = {0.0, 0.0, 0.0, 0.0}, c2[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -345,19 +361,26 @@ __device__ __forceinline__ void op_close(const OpConst& O, const int PL, const d
     for (int q = 0; q < NPW; ++q)
 #pragma unroll
       for (int j = 0; j < 4; ++j) ca[q][j] = cb[q][j] = 0.0;
+    const unsigned PL8 = 8u * (unsigned)PL;
+    const unsigned wb = smem_u32(W) + 8u * (unsigned)bmS;
+    unsigned xb[NPW];
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) xb[q] = smem_u32(X) + 8u * (unsigned)(((nt0 + q) * 8 + g) * S);
+#pragma unroll 2
     for (int ks = fs; ks < nks; ks += FS) {
       const unsigned fb = tb[ks * 4 + t];
+      const unsigned f8 = fb << 3;
       const bool ok = O.exact || fb != kNoFibre;
       const bool okm = ok && mok;
-      const double wre = okm ? W[fb + bmS] : 0.0;
-      const double wim = okm ? W[PL + fb + bmS] : 0.0;
+      const double wre = okm ? lds64(wb + f8) : 0.0;
+      const double wim = okm ? lds64(wb + PL8 + f8) : 0.0;
 #pragma unroll
       for (int q = 0; q < NPW; ++q) {
         if (q < npw) {
           const int bn = (nt0 + q) * 8 + g;
           const bool okn = ok && bn < chi;
-          const double xre = okn ? X[fb + bn * S] : 0.0;
-          const double xim = okn ? X[PL + fb + bn * S] : 0.0;
+          const double xre = okn ? lds64(xb[q] + f8) : 0.0;
+          const double xim = okn ? lds64(xb[q] + PL8 + f8) : 0.0;
           dmma1684(ca[q], wre, wim, xre);
           dmma1684(cb[q], wim, wre, xim);
         }
@@ -489,16 +512,19 @@ __device__ __forceinline__ void op_close_wl(const OpConst& O, const int PL, cons
   const bool mok = g < chi;
   const int gS = g * O.S;
   if constexpr (C) {
+    const unsigned PL8 = 8u * (unsigned)PL;
+    const unsigned wb = smem_u32(W) + 8u * (unsigned)gS, xb = smem_u32(X) + 8u * (unsigned)gS;
     double ca[4] = {0.0, 0.0, 0.0, 0.0}, cb[4] = {0.0, 0.0, 0.0, 0.0};
     for (int ft = warp; ft < O.ntile; ft += kNW) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const unsigned fb = tb[ft * 8 + h * 4 + t];
+        const unsigned f8 = fb << 3;
         const bool ok = (O.exact || fb != kNoFibre) && mok;
-        const double wre = ok ? W[fb + gS] : 0.0;
-        const double wim = ok ? W[PL + fb + gS] : 0.0;
-        const double xre = ok ? X[fb + gS] : 0.0;
-        const double xim = ok ? X[PL + fb + gS] : 0.0;
+        const double wre = ok ? lds64(wb + f8) : 0.0;
+        const double wim = ok ? lds64(wb + PL8 + f8) : 0.0;
+        const double xre = ok ? lds64(xb + f8) : 0.0;
+        const double xim = ok ? lds64(xb + PL8 + f8) : 0.0;
         dmma1684(ca, wre, wim, xre);
         dmma1684(cb, wim, wre, xim);
       }
