@@ -633,15 +633,25 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
     // 16-byte chunks: chunk c of row r, rows of `half` chunks; lanes walk the chunks of consecutive rows
     const int half = P.rowlen >> 1;
     const int tot = P.nrows * half;
+    // (row, c) of chunk i advance by (kBT / half, kBT % half) per iteration: one division per thread, not per chunk
+    const int drow = kBT / half, dc = kBT - drow * half;
+    int row = tid / half, c = tid - row * half;
+    const unsigned sb = smem_u32(bufs);
     for (int i = tid; i < tot; i += kBT) {
-      const int row = i / half, c = i - row * half;
       const int pos = gtab[P.rowtab + row] + 2 * c;
+      const long long go = goff + (long long)row * P.grow + 2 * c;
       for (int which = 0; which < nin; ++which)
         for (int pl = 0; pl < PLN; ++pl) {
-          const double* g = (which ? gP : gX) + (long long)pl * P.gplane + goff + (long long)row * P.grow + 2 * c;
-          const unsigned dsts = smem_u32(bufs + (size_t)which * P.bufsz + (size_t)pl * P.PL + pos);
+          const double* g = (which ? gP : gX) + (long long)pl * P.gplane + go;
+          const unsigned dsts = sb + 8u * (unsigned)(which * P.bufsz + pl * P.PL + pos);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dsts), "l"(g) : "memory");
         }
+      row += drow;
+      c += dc;
+      if (c >= half) {
+        c -= half;
+        ++row;
+      }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   } else {
