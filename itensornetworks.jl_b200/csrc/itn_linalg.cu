@@ -2592,7 +2592,13 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   // pivot-ratio flags of the bond environments travel to the host while the rest of step 2 is enqueued (CholeskyQR2 below)
   // (page-locked destination: a copy to pageable memory would block the host right here)
   const int* hcond = nullptr;
-  cudaEvent_t cond_ev = nullptr;
+  struct EventGuard {  // destroyed on every exit, also when a later launch throws
+    cudaEvent_t ev = nullptr;
+    ~EventGuard() {
+      if (ev) cudaEventDestroy(ev);
+    }
+  } cond_guard;
+  cudaEvent_t& cond_ev = cond_guard.ev;
   if (!q2cand.empty()) {
     if (ctx->pinned_flags_n < 2 * (size_t)n_own) {
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // an earlier copy may still target the old block
@@ -2672,9 +2678,7 @@ extern "C" int itn_apply2(itn_net* net, const int32_t* eids, int n, const void* 
   // R^+ = R1^+ R2^+.  One small read-back decides (no device idle time: see above); well-conditioned layers pay nothing else.
   if (!q2cand.empty()) {
     // the host waits for the flags only; the device keeps working on the Jacobi / support jobs enqueued above
-    const cudaError_t ce = cudaEventSynchronize(cond_ev);
-    cudaEventDestroy(cond_ev);
-    CUDA_CHECK(ce);
+    CUDA_CHECK(cudaEventSynchronize(cond_ev));
     std::vector<SuSite> s2;
     std::vector<JobSpec> spec2;
     std::vector<CholJob> chol2;
