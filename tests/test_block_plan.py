@@ -67,3 +67,20 @@ def test_config5_plan_shape():
         assert p.passes[w].smem <= 113 * 1024, (w, p.passes[w].smem)
     units = sum(1 for w in range(3) for o in p.passes[w].ops if o[0] in (0, 1))
     assert units == 22
+    # in-place operation lists: one buffer for pass 1, three for passes 2 / 3 (X, the partially absorbed tensor, one
+    # temporary); pass 2 takes the half-size cross-warp scratch and fits three CTAs per SM (228 KB / 3 - 1 KB - static)
+    assert [q.nbuf for q in p.passes] == [1, 3, 3]
+    assert p.passes[1].smem <= 228 * 1024 // 3 - 1024 - 2176
+    assert not any(q.wl for q in p.passes)   # chi = 6: a warp's slice would hold one parity of the site index
+
+
+def test_config2_plan_is_warp_local():
+    # z = 4, chi = 8: every pass deals whole batch slices to the warps (exact tiles, no excess wavefronts planned), mode
+    # products in place; the replay above runs such plans warp by warp
+    p = Plan(np.complex128, 2, [8] * 4, 900)
+    assert all(q.wl for q in p.passes)
+    assert [q.nbuf for q in p.passes] == [1, 3, 3]
+    assert all(q.excess == 0 for q in p.passes)
+    for q in p.passes:
+        for src_dst in [(o[1], o[2]) for o in q.ops if o[0] == 0]:
+            assert src_dst[0] == src_dst[1] or src_dst[1] >= 2 or q is p.passes[0]
