@@ -123,10 +123,10 @@ __device__ __forceinline__ double lds64(unsigned a) {
 __device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory"); }
 
 // Per-operation constants, computed once per CTA (one thread per operation) instead of once per warp and operation.
-struct OpConst {
+struct alignas(16) OpConst {  // three 16-byte loads per warp and operation
   int type, src, dst;  // buffer offsets in doubles
   int frag;            // offset of the fragment-ordered message copy in shared memory, -1: gather from global memory
-  int tab, ntile, S, chi, exact, slot, mode;
+  int tab, ntile, S, chi, exact, slot, mode, pad_;
 };
 
 // ---- dst = src x_mode M  (message = A operand in registers, tensor = B operand, 8 fibres per tile) ----------------------
@@ -290,7 +290,7 @@ __device__ __forceinline__ void mp_tiles(const OpConst& O, const int PL, const d
   }
 }
 
-// msm: the fragment-ordered message copies staged by the prologue ([row tile][step][array][lane]); skoff: the reduction
+// msm: the fragment-ordered message copies staged by the prologue ([row tile][step][lane][array]); skoff: the reduction
 // offsets per (mode, step, lane & 3).  Without a staged copy the fragments are gathered from the message in global memory.
 template <bool C, int KS>
 __device__ __forceinline__ void op_mp(const OpConst& O, const int PL, const double* __restrict__ msg,
@@ -306,11 +306,17 @@ __device__ __forceinline__ void op_mp(const OpConst& O, const int PL, const doub
   double A0[KH], A1[C ? KH : 1];
   int koff[KH];
   if (O.frag >= 0) {
-    const double* fr = msm + O.frag + (size_t)mt * KH * 64 + lane;
+    // [row tile][step][lane][array]: both arrays of a lane in one 16-byte load
+    const double* fr = msm + O.frag + (size_t)mt * KH * 64 + 2 * lane;
 #pragma unroll
     for (int ks = 0; ks < KH; ++ks) {
-      A0[ks] = fr[ks * 64];
-      if (C) A1[ks] = fr[ks * 64 + 32];
+      if constexpr (C) {
+        const double2 v = *reinterpret_cast<const double2*>(fr + ks * 64);
+        A0[ks] = v.x;
+        A1[ks] = v.y;
+      } else {
+        A0[ks] = fr[ks * 64];
+      }
     }
   } else {
 #pragma unroll
@@ -593,6 +599,10 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
     o.exact = M.exact;
     o.slot = M.slot;
     o.mode = op.mode;
+    // A close ends with all its reads of the tensor buffers behind a barrier of its own; its trailing sum reads the
+    // cross-warp scratch only, and the barrier that ends the following mode product separates it from the next close
+    // (extents above 16 close without a cross-warp sum and without a barrier of their own: they keep the trailing one)
+    o.pad_ = (op.type == OP_CLOSE && M.chi <= 16 && (tid + 1 == P.nops || P.ops[tid + 1].type == OP_MP)) ? 0 : 1;  // barrier after the op
     sOp[tid] = o;
   }
   if (WL && tid == 0) {
@@ -666,7 +676,7 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
   }
   for (int i = tid; i < P.tab_len; i += kBT) tab[i] = gtab[i];
   if (P.msg_smem) {
-    // fragment-ordered copies of the messages: [row tile][step][array][lane], what op_mp keeps in registers per operation
+    // fragment-ordered copies of the messages: [row tile][step][lane][array], what op_mp keeps in registers per operation
     constexpr int KHs = (C && KS >= 8) ? KS / 2 : KS;
 #pragma unroll
     for (int k = 0; k < kMaxGM; ++k)
@@ -676,7 +686,7 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
         const int n = ((chi + 7) >> 3) * KHs * 64;
         double* d = msm + P.msg_off[k];
         for (int i = tid; i < n; i += kBT) {
-          const int ln = i & 31, which = (i >> 5) & 1, r = i >> 6;
+          const int which = i & 1, ln = (i >> 1) & 31, r = i >> 6;
           const int ks = r % KHs, mt = r / KHs;
           d[i] = mp_fragment<C, KS>(gm, chi, mt, ks, which, ln);
         }
@@ -760,7 +770,7 @@ __global__ void __launch_bounds__(kBT, NB) k_block(const __grid_constant__ BlkPa
         }
       }
     }
-    if (!WL) __syncthreads();
+    if (!WL && O.pad_) __syncthreads();
   }
   if constexpr (WL) {
     // one cross-warp sum for all closes of the pass: [close][warp][plane][8 x 8], on the (dead) tensor buffers
@@ -1094,7 +1104,7 @@ bool block_debug() {
   return on;
 }
 
-constexpr size_t kStaticSmem = 2176;
+constexpr size_t kStaticSmem = 2304;  // ptxas: sOp, sKoff, sCloseOp, mbar
 constexpr size_t kSmemTwoCtasMax = 228 * 1024 / 2 - 1024 - kStaticSmem;
 constexpr size_t kSmemThreeCtasMax = 228 * 1024 / 3 - 1024 - kStaticSmem;
 constexpr size_t kSmemOneCta = 227 * 1024 - kStaticSmem;
