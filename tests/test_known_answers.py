@@ -9,6 +9,9 @@ ENGINE (`gpu`) to numbers that come from neither -- the part of "parity unpinned
   Schmidt spectra    exp(-i theta Z(x)Z) on |+>|+> = cos(theta) |++> - i sin(theta) |-->: singular values (cos, sin), so
                      maxdim / cutoff truncation has closed-form kept dimension and truncation error (src/apply.jl:81-88,
                      relative cutoff on squared singular values); CNOT (H (x) 1) |00>: (1, 1) / sqrt 2
+  weighted W state   sum_i c_i |0..1_i..0> on a chain as an MPS of bond dimension 2: <Z_i> = 1 - 2 p_i, <Z_i Z_j> = 1 - 2 p_i - 2 p_j,
+                     Z = sum |c|^2, the two-site RDM (off-diagonal coherence c_i conj(c_j) / Z), and the Schmidt coefficients
+                     sqrt(sum_{i <= k} p_i), sqrt(sum_{i > k} p_i) across every bond (an identity gate returns them)
 """
 import math
 
@@ -214,3 +217,61 @@ def test_bell_pair_from_cnot_hadamard(side):
     s.bp(O.Network(g, ts, np.complex128), 1)
     dim, terr, sv = s.gate(0, gate, maxdim=1)
     assert dim == 1 and abs(terr - 0.5) < TOL
+
+
+def w_chain(c):
+    """sum_i c_i |0..1_i..0> on an open chain as an MPS of bond dimension 2 (state "no excitation yet" / "one passed"):
+    A^0 = 1, A^1 = c_i |0><1|, boundary vectors <0| and |1>."""
+    n = len(c)
+    g = O.chain_graph(n)
+    a0 = np.eye(2, dtype=np.complex128)
+    ts = []
+    for v in range(n):
+        a1 = np.zeros((2, 2), dtype=np.complex128)
+        a1[0, 1] = c[v]
+        a = np.stack([a0, a1])                     # [s, left, right]
+        if v == 0:
+            t = a[:, 0, :]                         # bond to vertex 1 only
+        elif v == n - 1:
+            t = a[:, :, 1]
+        else:
+            t = a                                  # inc[v] = [edge to v - 1, edge to v + 1]
+        ts.append(np.ascontiguousarray(t))
+    return g, O.Network(g, ts, np.complex128)
+
+
+@pytest.mark.parametrize("side", SIDES)
+def test_weighted_w_state_on_a_chain(side):
+    # BP is exact on a chain.  With p_i = |c_i|^2 / sum |c|^2:  <Z_i> = 1 - 2 p_i,  <Z_i Z_j> = 1 - 2 p_i - 2 p_j,
+    # Z = sum |c|^2, the two-site RDM has the block (c_i, c_j)^H (c_i, c_j) / Z on {|10>, |01>}, and across the bond
+    # (k, k + 1) the Schmidt coefficients are sqrt(sum_{i <= k} p_i), sqrt(sum_{i > k} p_i): an identity gate returns them.
+    rng = np.random.default_rng(21)
+    n = 7
+    c = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    g, net = w_chain(c)
+    p = np.abs(c) ** 2 / np.sum(np.abs(c) ** 2)
+    s = side()
+    s.bp(net, 1)
+    for v in range(n):
+        assert abs(s.expect_z(v) - (1 - 2 * p[v])) < TOL
+    for e in range(n - 1):
+        assert abs(s.expect_zz(e) - (1 - 2 * p[e] - 2 * p[e + 1])) < TOL
+    assert abs(np.exp(s.logz()) - np.sum(np.abs(c) ** 2)) < 1e-11 * np.sum(np.abs(c) ** 2)
+    e = 3
+    rho = np.asarray(s.rdm2(e)).reshape(4, 4)
+    rho = rho / np.trace(rho)
+    want = np.zeros((4, 4), dtype=np.complex128)   # index s_e + 2 s_{e+1} (first site fastest, as rdm2 returns it)
+    want[0, 0] = 1 - p[e] - p[e + 1]
+    amp = np.array([c[e], c[e + 1]]) / np.sqrt(np.sum(np.abs(c) ** 2))   # index 1 = |1_e 0_{e+1}> carries c_e, index 2 c_{e+1}
+    want[1:3, 1:3] = np.outer(amp, amp.conj())
+    assert np.allclose(rho, want, atol=1e-11)
+    ident = np.eye(4, dtype=np.complex128).reshape(2, 2, 2, 2)
+    for k in (0, 2, 5):
+        s = side()
+        s.bp(w_chain(c)[1], 1)
+        dim, terr, sv = s.gate(k, ident)
+        sv = np.sort(np.asarray(sv))[::-1]
+        wl, wr = np.sum(p[:k + 1]), np.sum(p[k + 1:])
+        lo, hi = sorted([wl, wr])
+        assert abs(sv[1] / sv[0] - math.sqrt(lo / hi)) < 1e-11 and abs(terr) < TOL
+        assert np.all(sv[2:] < 1e-7 * sv[0])   # the gate bond carries two Schmidt states, whatever dimension is kept
