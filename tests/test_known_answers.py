@@ -12,6 +12,8 @@ ENGINE (`gpu`) to numbers that come from neither -- the part of "parity unpinned
   weighted W state   sum_i c_i |0..1_i..0> on a chain as an MPS of bond dimension 2: <Z_i> = 1 - 2 p_i, <Z_i Z_j> = 1 - 2 p_i - 2 p_j,
                      Z = sum |c|^2, the two-site RDM (off-diagonal coherence c_i conj(c_j) / Z), and the Schmidt coefficients
                      sqrt(sum_{i <= k} p_i), sqrt(sum_{i > k} p_i) across every bond (an identity gate returns them)
+  cluster state      prod CZ |+>^n on a tree (chi = 2, signs): <Z> = <ZZ> = 0, Z = 1, edge RDMs 1/4 in the interior and
+                     (1 + X_leaf Z_neighbour) / 4 at a leaf -- the stabiliser structure
 """
 import math
 
@@ -275,3 +277,51 @@ def test_weighted_w_state_on_a_chain(side):
         lo, hi = sorted([wl, wr])
         assert abs(sv[1] / sv[0] - math.sqrt(lo / hi)) < 1e-11 and abs(terr) < TOL
         assert np.all(sv[2:] < 1e-7 * sv[0])   # the gate bond carries two Schmidt states, whatever dimension is kept
+
+
+def cluster_network(g):
+    """Graph (cluster) state prod_{(u,v)} CZ_uv |+>^n as a tensor network of bond dimension 2: on every edge the lower
+    vertex copies its spin onto the bond, the higher one applies (-1)^(s a):  T_v[s, a..] = 2^-1/2 prod_out delta(a, s)
+    prod_in (-1)^(s a)."""
+    ts = []
+    for v in range(g.nv):
+        t = np.zeros((2,) + (2,) * g.degree(v), dtype=np.complex128)
+        for idx in np.ndindex(*t.shape):
+            s, amp = idx[0], 1 / math.sqrt(2)
+            for k, e in enumerate(g.inc[v]):
+                a = idx[1 + k]
+                if min(g.edges[e]) == v:
+                    amp *= 1.0 if a == s else 0.0
+                else:
+                    amp *= -1.0 if (s and a) else 1.0
+            t[idx] = amp
+        ts.append(t)
+    return O.Network(g, ts, np.complex128)
+
+
+@pytest.mark.parametrize("side", SIDES)
+def test_cluster_state_on_a_tree(side):
+    # Stabilisers K_v = X_v prod_{w ~ v} Z_w.  On a tree BP is exact: <Z_v> = 0 and <Z_u Z_v> = 0 everywhere, the state is
+    # normalised (Z = 1), the RDM of an edge whose endpoints both have further neighbours is 1/4, and the RDM of a leaf l
+    # with its neighbour v is (1 + X_l Z_v) / 4 (the only stabiliser product supported on the pair).
+    g = O.comb_tree_graph(3, 3)
+    s = side()
+    s.bp(cluster_network(g), 1)
+    for v in range(g.nv):
+        assert abs(s.expect_z(v)) < TOL
+    for e in range(len(g.edges)):
+        assert abs(s.expect_zz(e)) < TOL
+    assert abs(s.logz()) < 1e-11
+    x = np.array([[0.0, 1.0], [1.0, 0.0]])
+    for e, (u, v) in enumerate(g.edges):
+        rho = np.asarray(s.rdm2(e)).reshape(4, 4)       # index s_u + 2 s_v
+        du, dv = g.degree(u), g.degree(v)
+        if du > 1 and dv > 1:
+            want = np.eye(4) / 4
+        elif du == 1 and dv > 1:
+            want = (np.eye(4) + np.kron(Z, x)) / 4      # kron(op_v, op_u): s_u is the fast index
+        elif dv == 1 and du > 1:
+            want = (np.eye(4) + np.kron(x, Z)) / 4
+        else:
+            continue
+        assert np.allclose(rho, want, atol=1e-11), (e, u, v)
