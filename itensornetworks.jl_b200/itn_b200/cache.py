@@ -132,7 +132,13 @@ class BeliefPropagationCache:
         self.dtype = _COMPUTE[self.eltype]     # what the device computes in
         g = self.graph
         self.sdims = [t.shape[0] for t in psi.tensors]
-        self._edims = [psi.edge_dim(e) for e in range(g.ne)]
+        # bond dimensions from the tensor shapes, one pass over the vertices (psi.edge_dim(e) per edge costs a list search each)
+        ed = [0] * g.ne
+        for inc_v, t in zip(g.inc, psi.tensors):
+            shp = t.shape
+            for k, e in enumerate(inc_v):
+                ed[e] = shp[1 + k]
+        self._edims = ed
         # multi-GPU: owner[v] = rank that stores vertex v; dist = (rank, nranks) of this process
         self.owner = None if owner is None else [int(x) for x in owner]
         self.rank = self.ctx.rank if dist is None else int(dist[0])
@@ -222,11 +228,14 @@ class BeliefPropagationCache:
         hosts, addrs = [], []
         dt = self.dtype
         from_buffer, addressof = C.c_char.from_buffer, C.addressof
+        if self._edims is None:
+            self.edge_dim(0) if self.graph.ne else None  # fills the host copy of the bond dimensions
+        ed, sd, inc = self._edims, self.sdims, self.graph.inc
         for v, t in zip(verts, tensors):
             # fast path: an F-ordered array of the device dtype is passed as it is (no per-tensor conversion calls)
             if not (type(t) is np.ndarray and t.dtype == dt and t.flags.f_contiguous):
                 t = np.asfortranarray(np.asarray(t, dtype=dt))
-            if t.shape != self._shape(v):
+            if t.shape != (sd[v], *[ed[e] for e in inc[v]]):
                 raise ITNError(2, f"tensor of vertex {v} has shape {t.shape}, expected {self._shape(v)}")
             hosts.append(t)
             try:  # address of the first element; ndarray.ctypes costs 2 us per tensor (8 ms for a 64 x 64 lattice)
