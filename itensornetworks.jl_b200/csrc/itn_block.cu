@@ -1545,6 +1545,14 @@ bool choose_pass(const Signature& sg, int h, int which, bool cplx, int ks_inst, 
   }
   if (best_chunk < 0) return false;
   ch.chunk = best_chunk;
+  if (wl && !(getenv("ITN_BLOCK_WL") && atoi(getenv("ITN_BLOCK_WL")) == 2)) {
+    // a warp-local plan is only taken when every mode stays exact (geometry_for): known before any table is built,
+    // so the padding search below (a full table per candidate and warp) is skipped for the signatures that fail
+    PassPlan pp;
+    if (!plan_pass(sg, h, which, cplx, ks_inst, ch, false, pp)) return false;
+    for (int k = 0; k < pp.desc.nmodes; ++k)
+      if (!pp.desc.modes[k].exact) return false;
+  }
   const bool want_two = best_two;
   bool mixed_steps = false;  // packed complex stacking with a k step that straddles the planes
   if (cplx && !aligned)
